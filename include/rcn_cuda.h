@@ -1,0 +1,163 @@
+/* rcn_cuda.h -- C ABI of librcn_cuda.so: rcn's training hot path on one B200 (sm_100a).
+ *
+ * The reference (jtstrader/mercer-research, crate `rcn`) has no FFI of its own; its drop-in boundary
+ * is the crate's public Rust API. Each entry point below names the reference
+ * item it replaces (file:line relative to /root/reference/). A Rust facade binds these 1:1
+ * (rust/src/ffi.rs; INTEGRATION.md shows the `extern "C"` block and build.rs step).
+ *
+ * Conventions
+ *  - All matrices are f64 COLUMN-MAJOR (nalgebra storage; serialization.rs:19-22 writes exactly this).
+ *    A batch of B vectors of length n is an n x B column-major matrix: sample b at ptr + b*n.
+ *  - Every data pointer may be a HOST or a DEVICE pointer; the library detects which
+ *    (cudaPointerGetAttributes). Host buffers are staged through the model's stream and the call
+ *    returns after the stream has drained; with device buffers the call only enqueues work on the
+ *    model's stream (capturable into a CUDA graph once shapes have been seen once).
+ *  - Every function returns an rcn_status; rcn_cuda_last_error() gives the thread-local message.
+ *    Where the reference panic!()s on a contract violation the library returns RCN_ERR_SHAPE /
+ *    RCN_ERR_NOT_IMPLEMENTED with the reference's message instead of aborting.
+ *  - A handle is not safe for concurrent mutation (same rule as `&mut self`); distinct handles are
+ *    independent. There is NO CPU fallback: without a usable CUDA device every call fails with
+ *    RCN_ERR_CUDA.
+ */
+#ifndef RCN_CUDA_H
+#define RCN_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rcn_cuda_model* rcn_cuda_handle;
+
+typedef enum rcn_status {
+    RCN_OK = 0,
+    RCN_ERR_INVALID = 1,         /* null pointer, bad enum, zero size */
+    RCN_ERR_SHAPE = 2,           /* reference panics: kernel.rs:127,133,200,247; nalgebra dim mismatch */
+    RCN_ERR_NOT_IMPLEMENTED = 3, /* reference panics "Not implemented": kernel.rs:284,342 (Pooling::Average in rcn's own ops) */
+    RCN_ERR_CUDA = 4,            /* CUDA runtime error / no device */
+    RCN_ERR_STATE = 5,           /* parameters not initialised, etc. */
+    RCN_ERR_OUT_OF_BOUNDS = 6,   /* reference index panic: kernel.rs:156 (SAME padding with a >=5-wide kernel) */
+    RCN_ERR_NAN = 7              /* reference panics on partial_cmp(NaN): kernel.rs:280,338 */
+} rcn_status;
+
+/* enum Padding (kernel.rs:25-28), enum Pooling (kernel.rs:32-35), enum SeparableOperator (kernel.rs:16-21):
+ * values are the Rust declaration order (= bincode variant index). */
+enum { RCN_PADDING_NONE = 0, RCN_PADDING_SAME = 1 };
+enum { RCN_POOLING_AVERAGE = 0, RCN_POOLING_MAX = 1 };
+enum { RCN_OP_TOP = 0, RCN_OP_BOTTOM = 1, RCN_OP_LEFT = 2, RCN_OP_RIGHT = 3 };
+/* enum RCNLayer { Convolve2D(Padding), Pool2D(Pooling) } (rcn.rs:35-38), flattened. */
+enum { RCN_LAYER_CONV_NONE = 0, RCN_LAYER_CONV_SAME = 1, RCN_LAYER_POOL_AVERAGE = 2, RCN_LAYER_POOL_MAX = 3 };
+/* Pixel formats accepted by the image entry points. */
+enum {
+    RCN_PIXELS_U8_ROWMAJOR = 0,  /* `image` crate GrayImage buffer, before get_pixel_matrix (lib.rs:27-33) */
+    RCN_PIXELS_F64_COLMAJOR = 1  /* DMatrix<f64> H x W as get_pixel_matrix returns it */
+};
+
+const char* rcn_cuda_last_error(void);
+int rcn_cuda_version(void);
+int rcn_cuda_device_count(int* count);
+
+/* ---- model lifetime: RCN::new (rcn.rs:58-75) -------------------------------------------------- */
+int rcn_cuda_create(size_t classes, const int32_t* convpool_cfg, size_t n_convpool,
+                    const size_t* feedforward_cfg, size_t n_feedforward, int device,
+                    rcn_cuda_handle* out);
+int rcn_cuda_destroy(rcn_cuda_handle h);
+/* Run on an existing cudaStream_t (e.g. torch's current stream). NULL restores the model's own stream. */
+int rcn_cuda_set_stream(rcn_cuda_handle h, void* cuda_stream);
+int rcn_cuda_synchronize(rcn_cuda_handle h);
+
+/* ---- shapes ------------------------------------------------------------------------------------ */
+/* Geometry walk of flatten_feature_set (rcn.rs:317-356): number of maps and their size. */
+int rcn_cuda_feature_shape(rcn_cuda_handle h, size_t H, size_t W, size_t* n_maps, size_t* map_h, size_t* map_w);
+/* load_weights_and_bias (rcn.rs:425-457): allocates zeroed W_l (rows x cols) and b_l with the reference's
+ * shapes, including its `4^c / 2^p * l` first-layer width. Values are then injected with set_params
+ * (the reference draws them from an unseeded thread_rng, rcn.rs:500-523). */
+int rcn_cuda_init_params(rcn_cuda_handle h, size_t feature_len);
+int rcn_cuda_num_layers(rcn_cuda_handle h, size_t* n_layers);
+int rcn_cuda_layer_shape(rcn_cuda_handle h, size_t layer, size_t* rows, size_t* cols);
+int rcn_cuda_param_count(rcn_cuda_handle h, size_t* n);
+
+/* ---- parameters: Weights / Bias (rcn.rs:28-31; layout of serialization.rs:16-24,109-113) ------ */
+int rcn_cuda_set_weights(rcn_cuda_handle h, size_t layer, size_t rows, size_t cols, const double* w);
+int rcn_cuda_get_weights(rcn_cuda_handle h, size_t layer, double* w);
+int rcn_cuda_set_bias(rcn_cuda_handle h, size_t layer, size_t n, const double* b);
+int rcn_cuda_get_bias(rcn_cuda_handle h, size_t layer, double* b);
+/* Whole model as one flat buffer [W0|b0|W1|b1|...]. */
+int rcn_cuda_set_params(rcn_cuda_handle h, const double* flat, size_t n);
+int rcn_cuda_get_params(rcn_cuda_handle h, double* flat, size_t n);
+/* scale_set (rcn.rs:21): (mean, sd) used by the standardise step. */
+int rcn_cuda_set_scale(rcn_cuda_handle h, double mean, double sd);
+int rcn_cuda_get_scale(rcn_cuda_handle h, double* mean, double* sd);
+
+/* ---- feature stage ----------------------------------------------------------------------------- */
+/* flatten_feature_set (rcn.rs:317-356) over a batch, optionally followed by standardise + clamp
+ * (rcn.rs:407-412 / 86-89) with the model's scale_set. images: B images of H x W in `pixel_format`;
+ * out: L x B. */
+int rcn_cuda_features(rcn_cuda_handle h, const void* images, int pixel_format, size_t B, size_t H, size_t W,
+                      int standardise, double* out);
+/* gen_scales (rcn.rs:230-251): mean and population sd over all L*B values; also stored as scale_set. */
+int rcn_cuda_gen_scales(rcn_cuda_handle h, const double* feats, size_t L, size_t B, double* mean, double* sd);
+/* v <- max((v-mean)/sd, 0) in place (rcn.rs:407-412). */
+int rcn_cuda_standardise(rcn_cuda_handle h, double* feats, size_t n);
+
+/* ---- inference: classify_test (rcn.rs:105-116), classify (rcn.rs:82-98), epoch eval (rcn.rs:152-157) */
+int rcn_cuda_forward(rcn_cuda_handle h, const double* feats, size_t B, double* out_acts /* classes x B */);
+/* argmax with last-max-wins (rcn.rs:92-97) of the forward pass. */
+int rcn_cuda_classify_features(rcn_cuda_handle h, const double* feats, size_t B, int64_t* labels_out);
+int rcn_cuda_classify(rcn_cuda_handle h, const void* images, int pixel_format, size_t B, size_t H, size_t W,
+                      int64_t* labels_out);
+/* Number of samples whose {i : a_i == max a} equals {label} exactly (rcn.rs:153-157). */
+int rcn_cuda_evaluate(rcn_cuda_handle h, const double* feats, const int64_t* labels, size_t B, uint64_t* accept);
+
+/* ---- training: backprop (rcn.rs:260-314) + train_batch (rcn.rs:176-223) ------------------------ */
+/* Targets: exactly one of `onehot` (classes x B, the reference's `y`) and `labels` (class index per sample,
+ * expanded as get_expected_vec does, rcn.rs:466-471) must be non-NULL. */
+
+/* Sum over the batch of backprop()'s (del_w, del_b), written to the model's flat gradient buffer
+ * [dW0|db0|dW1|db1|...] -- the reduction of rcn.rs:190-205 without the update. */
+int rcn_cuda_accumulate_gradients(rcn_cuda_handle h, const double* feats, const double* onehot,
+                                  const int64_t* labels, size_t B);
+/* Same, starting from raw images (features + standardise fused in front). */
+int rcn_cuda_accumulate_gradients_images(rcn_cuda_handle h, const void* images, int pixel_format,
+                                         const int64_t* labels, size_t B, size_t H, size_t W);
+/* W <- W - (eta / batch) * sum_dW, b likewise (rcn.rs:210-222). `batch` is the GLOBAL minibatch size
+ * (the data-parallel trainer all-reduces the gradient buffer between accumulate and apply). */
+int rcn_cuda_apply_gradients(rcn_cuda_handle h, double eta, size_t batch);
+/* train_batch (rcn.rs:176-223) = accumulate + apply on one device. */
+int rcn_cuda_train_batch(rcn_cuda_handle h, const double* feats, const double* onehot, const int64_t* labels,
+                         size_t B, double eta);
+int rcn_cuda_train_batch_images(rcn_cuda_handle h, const void* images, int pixel_format, const int64_t* labels,
+                                size_t B, size_t H, size_t W, double eta);
+/* Optional per-batch metric of the last accumulate/train call, evaluated with the PRE-update parameters:
+ * quadratic cost sum_b 0.5*|a_L - y|^2 and the rcn.rs:153-157 hit count. */
+int rcn_cuda_last_batch_stats(rcn_cuda_handle h, double* cost, uint64_t* hits);
+
+/* Gradient buffer access for the data-parallel trainer. bind: use caller-owned DEVICE memory (e.g. a torch
+ * tensor that NCCL all-reduces) as the flat gradient buffer; NULL restores the internal one. */
+int rcn_cuda_bind_gradient_buffer(rcn_cuda_handle h, double* device_ptr, size_t n);
+int rcn_cuda_gradient_buffer(rcn_cuda_handle h, double** device_ptr, size_t* n);
+int rcn_cuda_get_gradients(rcn_cuda_handle h, double* flat, size_t n);
+/* Debug / parity taps of the last accumulate call: activations a_l (rows_l x B) and deltas (rows_l x B). */
+int rcn_cuda_get_activations(rcn_cuda_handle h, size_t layer, double* out);
+int rcn_cuda_get_deltas(rcn_cuda_handle h, size_t layer, double* out);
+
+/* ---- op-level API: traits Convolve2D (kernel.rs:61-100) and Pool2D (kernel.rs:219-236) -------- */
+/* These need no model; `device` selects the GPU and `cuda_stream` may be NULL. Outputs are caller-allocated:
+ * convolve_2d: H x W (Same) or (H-kh+1) x (W-kw+1) (None); pool_2d: ceil(H/2) x ceil(W/2) (Same) or
+ * floor (None). */
+int rcn_cuda_convolve_2d(int device, void* cuda_stream, const double* m, size_t H, size_t W, const double* kernel,
+                         size_t kh, size_t kw, int padding, double* out);
+int rcn_cuda_convolve_2d_separated(int device, void* cuda_stream, const double* m, size_t H, size_t W, int op,
+                                   int padding, double* out);
+int rcn_cuda_relu(int device, void* cuda_stream, const double* m, size_t n, double* out);
+/* argmax_out (optional, may be NULL) is this library's extension: index 2*dy+dx of the chosen element with
+ * the reference's last-maximal-element-wins rule (kernel.rs:273-281). */
+int rcn_cuda_pool_2d(int device, void* cuda_stream, const double* m, size_t H, size_t W, int padding, int pooling,
+                     double* out, uint8_t* argmax_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCN_CUDA_H */

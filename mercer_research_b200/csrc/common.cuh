@@ -1,0 +1,86 @@
+// common.cuh -- shared host/device helpers for librcn_cuda (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/rcn_cuda.h"
+
+namespace rcn {
+
+// ---- error plumbing -----------------------------------------------------------------------------
+std::string& last_error_ref();
+int fail(int code, const char* fmt, ...);
+
+#define RCN_CUDA_TRY(expr)                                                                        \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return ::rcn::fail(RCN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                               __FILE__, __LINE__);                                               \
+    } while (0)
+
+#define RCN_TRY(expr)             \
+    do {                          \
+        int _rc = (expr);         \
+        if (_rc != RCN_OK) return _rc; \
+    } while (0)
+
+#define RCN_LAUNCH_CHECK()                                                                         \
+    do {                                                                                           \
+        cudaError_t _e = cudaPeekAtLastError();                                                    \
+        if (_e != cudaSuccess)                                                                     \
+            return ::rcn::fail(RCN_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                               __FILE__, __LINE__);                                                \
+    } while (0)
+
+// Is `p` device-accessible memory (device or managed)?  Unregistered host memory reports
+// cudaMemoryTypeUnregistered; pinned host memory cudaMemoryTypeHost.
+inline bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Grow-only device buffer: steady-state training does no allocation (CUDA-graph friendly).
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return RCN_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return fail(RCN_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
+        cap = want;
+        return RCN_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Stages a possibly-host input into device memory on `stream`.
+struct StagedIn {
+    const void* dev = nullptr;
+    int stage(const void* src, size_t bytes, DevBuf& scratch, cudaStream_t stream, bool* was_host) {
+        if (is_device_ptr(src)) { dev = src; return RCN_OK; }
+        RCN_TRY(scratch.reserve(bytes));
+        RCN_CUDA_TRY(cudaMemcpyAsync(scratch.p, src, bytes, cudaMemcpyHostToDevice, stream));
+        dev = scratch.p;
+        if (was_host) *was_host = true;
+        return RCN_OK;
+    }
+};
+
+constexpr int kNumSMs = 148;  // B200
+
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace rcn

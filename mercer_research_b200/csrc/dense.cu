@@ -1,0 +1,423 @@
+// dense.cu -- rcn's fully-connected layers on sm_100a in f64 (the reference computes in f64, so parity is 1e-9).
+//
+// Reference: rcn/src/rcn.rs:105-116 (forward), :260-314 (backprop), :176-223 (batch sum + SGD), :478-492
+// (sigmoid / sigmoid_prime).  The per-sample matvecs / outer products of the reference become three batched
+// GEMM shapes:
+//   forward        A_l     = sigmoid(W_l A_{l-1} + b_l 1^T)
+//   backward-data  D_l     = (W_{l+1}^T D_{l+1}) .* s'(Z_l)
+//   backward-wt    sum dW_l = D_l A_{l-1}^T ,  sum db_l = D_l 1
+// tcgen05.mma has no f64 kind, so the f64 tensor path on B200 is the warp-level DMMA
+// (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4); operands are staged through shared memory with cp.async in a
+// 3-stage ring, accumulators live in registers, bias / sigmoid / sigmoid' / output-delta run in the epilogue.
+//
+// sigmoid'(z) is evaluated as a*(1-a) with a = sigmoid(z) read back from the stored activation: the reference
+// recomputes sigmoid(z) (rcn.rs:491) which is bitwise the same value, and it must NOT be rewritten
+// algebraically (1-a cancels for saturated units and parity depends on cancelling identically).
+#include "dense.cuh"
+
+#include <cstdlib>
+
+namespace rcn {
+
+GemmImpl gemm_impl() {
+    static int impl = -1;
+    if (impl < 0) {
+        const char* e = getenv("RCN_CUDA_GEMM");
+        impl = (e && strcmp(e, "simt") == 0) ? GEMM_SIMT : GEMM_DMMA;
+    }
+    return (GemmImpl)impl;
+}
+
+// rcn.rs:478-483: 1/(1+E^-x).  exp(-x) instead of pow(E,-x): E as an f64 is e*(1-5.3e-17), so the two differ
+// by a relative |x|*5.3e-17 -- far inside the 1e-9 parity tolerance.
+__device__ __forceinline__ double sigmoid1(double z) { return 1.0 / (1.0 + exp(-z)); }
+
+// ------------------------------------------------------------------------------------------------
+// Epilogues.  operator()(m, n, acc) is called once per output element.
+// ------------------------------------------------------------------------------------------------
+struct EpiForward {
+    const double* bias; double* a_out; double* delta_out; const double* onehot; const int64_t* labels; int M;
+    __device__ __forceinline__ void operator()(int m, int n, double v) const {
+        const double z = v + bias[m];                        // w * a + b           (rcn.rs:287)
+        const double a = sigmoid1(z);                        // sigmoid(&z)         (rcn.rs:289)
+        const size_t o = (size_t)n * M + m;
+        a_out[o] = a;
+        if (delta_out) {                                     // (a_L - y) .* sigmoid_prime(z_L)   (rcn.rs:299)
+            const double y = onehot ? onehot[o] : ((labels[n] == (int64_t)m) ? 1.0 : 0.0);
+            const double sp = a * (1.0 - a);
+            delta_out[o] = (a - y) * sp;
+        }
+    }
+};
+struct EpiBackData {
+    const double* a; double* delta_out; int M;
+    __device__ __forceinline__ void operator()(int m, int n, double v) const {
+        const size_t o = (size_t)n * M + m;
+        const double s = a[o];
+        delta_out[o] = v * (s * (1.0 - s));                  // (W^T delta) .* sigmoid_prime(z)  (rcn.rs:306-308)
+    }
+};
+struct EpiStore {  // split-K partial (or final) store, column-major M x N
+    double* out; int M; size_t split_stride;
+    __device__ __forceinline__ void operator()(int m, int n, double v) const {
+        out[(size_t)blockIdx.z * split_stride + (size_t)n * M + m] = v;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// DMMA GEMM:  C(m,n) = sum_k A(m,k) B(k,n), k in this split's range.
+//   A(m,k): AK ? A[m*lda + k] : A[k*lda + m]        B(k,n): BKc ? B[n*ldb + k] : B[k*ldb + n]
+// ------------------------------------------------------------------------------------------------
+constexpr int KT = 16;       // k depth of one shared-memory tile
+constexpr int STAGES = 3;
+constexpr int GEMM_THREADS = 256;
+
+template <int ROWS, bool KCONTIG>
+struct TileLayout {
+    // +4 doubles of pitch: the 4 (k) x 4 (row) doubles a half-warp reads for one DMMA fragment fall into 16
+    // distinct 8-byte bank pairs.
+    static constexpr int PITCH = KCONTIG ? (KT + 4) : (ROWS + 4);
+    static constexpr int ELEMS = KCONTIG ? ROWS * PITCH : KT * PITCH;
+    __device__ __forceinline__ static int idx(int r, int kk) { return KCONTIG ? r * PITCH + kk : kk * PITCH + r; }
+};
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <int ROWS, bool KCONTIG>
+__device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, int ld, int r0, int rmax, int k0,
+                                          int kmax, int tid) {
+    using TL = TileLayout<ROWS, KCONTIG>;
+    constexpr int N = ROWS * KT;
+#pragma unroll
+    for (int e = tid; e < N; e += GEMM_THREADS) {
+        int r, kk;
+        if (KCONTIG) { r = e / KT; kk = e % KT; } else { kk = e / ROWS; r = e % ROWS; }
+        const bool ok = (r0 + r < rmax) && (k0 + kk < kmax);
+        const size_t off = KCONTIG ? (size_t)(r0 + r) * ld + (k0 + kk) : (size_t)(k0 + kk) * ld + (r0 + r);
+        cp_async8(s + TL::idx(r, kk), ok ? g + off : g, ok ? 8 : 0);  // src-size 0 => zero fill
+    }
+}
+
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int BM, int BN, int WM, int WN, bool AK, bool BKc, typename Epi>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_dmma_kernel(const double* __restrict__ A, int lda,
+                                                                      const double* __restrict__ B, int ldb, int M, int N,
+                                                                      int K, int k_per_split, Epi epi) {
+    static_assert((BM / WM) * (BN / WN) == GEMM_THREADS / 32, "warp grid must use all warps");
+    using TA = TileLayout<BM, AK>;
+    using TB = TileLayout<BN, BKc>;
+    constexpr int MF = WM / 8, NF = WN / 8;
+    extern __shared__ __align__(16) double smem_gemm[];
+    double* sA = smem_gemm;
+    double* sB = smem_gemm + STAGES * TA::ELEMS;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp % (BM / WM), wn = warp / (BM / WM);
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int k_begin = blockIdx.z * k_per_split;
+    const int k_end = min(K, k_begin + k_per_split);
+    const int ntiles = (k_end - k_begin + KT - 1) / KT;
+
+    double acc[MF][NF][2];
+#pragma unroll
+    for (int i = 0; i < MF; ++i)
+#pragma unroll
+        for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < ntiles) {
+            load_tile<BM, AK>(sA + s * TA::ELEMS, A, lda, m0, M, k_begin + s * KT, k_end, tid);
+            load_tile<BN, BKc>(sB + s * TB::ELEMS, B, ldb, n0, N, k_begin + s * KT, k_end, tid);
+        }
+        cp_async_commit();
+    }
+
+    for (int kt = 0; kt < ntiles; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();  // tile kt landed for everyone; everyone is done reading tile kt-1's slot
+        {
+            const int nk = kt + STAGES - 1;
+            if (nk < ntiles) {
+                const int slot = nk % STAGES;
+                load_tile<BM, AK>(sA + slot * TA::ELEMS, A, lda, m0, M, k_begin + nk * KT, k_end, tid);
+                load_tile<BN, BKc>(sB + slot * TB::ELEMS, B, ldb, n0, N, k_begin + nk * KT, k_end, tid);
+            }
+            cp_async_commit();
+        }
+        const double* a_s = sA + (kt % STAGES) * TA::ELEMS;
+        const double* b_s = sB + (kt % STAGES) * TB::ELEMS;
+#pragma unroll
+        for (int ks = 0; ks < KT; ks += 4) {
+            double af[MF], bf[NF];
+#pragma unroll
+            for (int i = 0; i < MF; ++i) af[i] = a_s[TA::idx(wm * WM + i * 8 + g, ks + t)];  // A frag: row g, col t
+#pragma unroll
+            for (int j = 0; j < NF; ++j) bf[j] = b_s[TB::idx(wn * WN + j * 8 + g, ks + t)];  // B frag: row t, col g
+#pragma unroll
+            for (int i = 0; i < MF; ++i)
+#pragma unroll
+                for (int j = 0; j < NF; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // C frag: row g, cols 2t, 2t+1
+#pragma unroll
+    for (int i = 0; i < MF; ++i) {
+        const int m = m0 + wm * WM + i * 8 + g;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+            const int n = n0 + wn * WN + j * 8 + 2 * t;
+            if (n < N) epi(m, n, acc[i][j][0]);
+            if (n + 1 < N) epi(m, n + 1, acc[i][j][1]);
+        }
+    }
+}
+
+// Plain one-thread-per-output kernel: slow, obviously correct; cross-checks the DMMA path (RCN_CUDA_GEMM=simt).
+template <bool AK, bool BKc, typename Epi>
+__global__ void gemm_f64_simt_kernel(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb, int M,
+                                     int N, int K, int k_per_split, Epi epi) {
+    const int m = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int n = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (m >= M || n >= N) return;
+    const int k_begin = blockIdx.z * k_per_split, k_end = min(K, k_begin + k_per_split);
+    double acc = 0.0;
+    for (int k = k_begin; k < k_end; ++k) {
+        const double a = AK ? A[(size_t)m * lda + k] : A[(size_t)k * lda + m];
+        const double b = BKc ? B[(size_t)n * ldb + k] : B[(size_t)k * ldb + n];
+        acc = fma(a, b, acc);
+    }
+    epi(m, n, acc);
+}
+
+template <int BM, int BN, int WM, int WN, bool AK, bool BKc, typename Epi>
+static int launch_dmma(const double* A, int lda, const double* B, int ldb, int M, int N, int K, int splits,
+                       int k_per_split, const Epi& epi, cudaStream_t stream) {
+    using TA = TileLayout<BM, AK>;
+    using TB = TileLayout<BN, BKc>;
+    constexpr size_t smem = (size_t)STAGES * (TA::ELEMS + TB::ELEMS) * sizeof(double);
+    auto kern = gemm_f64_dmma_kernel<BM, BN, WM, WN, AK, BKc, Epi>;
+    static bool attr_done = false;  // per instantiation
+    if (!attr_done) {
+        RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    dim3 grid(cdiv(M, BM), cdiv(N, BN), splits);
+    kern<<<grid, GEMM_THREADS, smem, stream>>>(A, lda, B, ldb, M, N, K, k_per_split, epi);
+    RCN_LAUNCH_CHECK();
+    return RCN_OK;
+}
+
+template <bool AK, bool BKc, typename Epi>
+static int launch_gemm(const double* A, int lda, const double* B, int ldb, size_t M_, size_t N_, size_t K_, int splits,
+                       const Epi& epi, cudaStream_t stream) {
+    if (M_ == 0 || N_ == 0) return RCN_OK;
+    if (M_ > 0x7fffffff || N_ > 0x7fffffff || K_ > 0x7fffffff) return fail(RCN_ERR_INVALID, "GEMM dimension too large");
+    const int M = (int)M_, N = (int)N_, K = (int)K_;
+    if (splits < 1) splits = 1;
+    int k_per_split = (K + splits - 1) / splits;
+    k_per_split = ((k_per_split + KT - 1) / KT) * KT;
+    if (k_per_split < KT) k_per_split = KT;
+    splits = K > 0 ? (K + k_per_split - 1) / k_per_split : 1;
+    if (gemm_impl() == GEMM_SIMT) {
+        dim3 grid(cdiv(M, 32), cdiv(N, 8), splits);
+        gemm_f64_simt_kernel<AK, BKc, Epi><<<grid, 256, 0, stream>>>(A, lda, B, ldb, M, N, K, k_per_split, epi);
+        RCN_LAUNCH_CHECK();
+        return RCN_OK;
+    }
+    if (M <= 32) return launch_dmma<32, 128, 32, 16, AK, BKc, Epi>(A, lda, B, ldb, M, N, K, splits, k_per_split, epi, stream);
+    const size_t big_tiles = (size_t)cdiv(M, 128) * cdiv(N, 128) * splits;
+    if (big_tiles >= (size_t)kNumSMs)
+        return launch_dmma<128, 128, 64, 32, AK, BKc, Epi>(A, lda, B, ldb, M, N, K, splits, k_per_split, epi, stream);
+    return launch_dmma<64, 64, 32, 16, AK, BKc, Epi>(A, lda, B, ldb, M, N, K, splits, k_per_split, epi, stream);
+}
+
+// Effective split count launch_gemm will use (so callers can size the partial workspace).
+static int effective_splits(size_t K, int splits) {
+    if (splits < 1) splits = 1;
+    int k_per_split = (int)((K + splits - 1) / splits);
+    k_per_split = ((k_per_split + KT - 1) / KT) * KT;
+    if (k_per_split < KT) k_per_split = KT;
+    return K > 0 ? (int)((K + k_per_split - 1) / k_per_split) : 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layer entry points
+// ------------------------------------------------------------------------------------------------
+int launch_dense_forward(const double* W, const double* b, const double* A_in, size_t M, size_t K, size_t N,
+                         double* A_out, double* delta_out, const double* onehot, const int64_t* labels,
+                         cudaStream_t stream) {
+    EpiForward epi{b, A_out, delta_out, onehot, labels, (int)M};
+    return launch_gemm<false, true, EpiForward>(W, (int)M, A_in, (int)K, M, N, K, 1, epi, stream);
+}
+
+int launch_dense_backward_data(const double* W_up, const double* delta_up, const double* A, size_t M, size_t K,
+                               size_t N, double* delta_out, cudaStream_t stream) {
+    EpiBackData epi{A, delta_out, (int)M};
+    // A(m,k) = W_up[k, m]; W_up is K x M column-major => k-contiguous with lda = K.
+    return launch_gemm<true, true, EpiBackData>(W_up, (int)K, delta_up, (int)K, M, N, K, 1, epi, stream);
+}
+
+__global__ void reduce_splits_kernel(const double* __restrict__ part, int splits, size_t n, double* __restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        double s = part[i];
+        for (int p = 1; p < splits; ++p) s += part[(size_t)p * n + i];
+        out[i] = s;
+    }
+}
+
+// db[m] = sum_n delta[m, n].  One CTA per 32 rows; warp w sums columns w, w+8, ...; fixed-order combine.
+__global__ void __launch_bounds__(256) bias_grad_kernel(const double* __restrict__ delta, int M, int N, double* __restrict__ db) {
+    __shared__ double sm[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int m = blockIdx.x * 32 + lane;
+    double acc = 0.0;
+    if (m < M)
+        for (int n = w; n < N; n += 8) acc += delta[(size_t)n * M + m];
+    sm[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && m < M) {
+        double s = sm[0][lane];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) s += sm[i][lane];
+        db[m] = s;
+    }
+}
+
+int launch_dense_backward_weight(const double* delta, const double* A_prev, size_t M, size_t N, size_t Kb, double* dW,
+                                 double* db, DevBuf& workspace, cudaStream_t stream) {
+    if (M == 0) return RCN_OK;
+    // Split the batch (K) dimension so the small M x N output still fills the machine; partials are summed in
+    // a fixed order (deterministic, unlike the reference's mutex-ordered sum, rcn.rs:190-205).
+    size_t tiles;
+    if (M <= 32) tiles = (size_t)cdiv(M, 32) * cdiv(N, 128);
+    else {
+        tiles = (size_t)cdiv(M, 128) * cdiv(N, 128);
+        if (tiles < (size_t)kNumSMs) tiles = (size_t)cdiv(M, 64) * cdiv(N, 64);
+    }
+    int splits = 1;
+    if (tiles < (size_t)kNumSMs && N > 0) {
+        splits = (int)((2 * kNumSMs + tiles - 1) / tiles);
+        const int max_splits = (int)(Kb / 64) > 0 ? (int)(Kb / 64) : 1;
+        if (splits > max_splits) splits = max_splits;
+        if (splits > 64) splits = 64;
+    }
+    splits = effective_splits(Kb, splits);
+    if (N > 0) {
+        if (splits == 1) {
+            EpiStore epi{dW, (int)M, 0};
+            RCN_TRY((launch_gemm<false, false, EpiStore>(delta, (int)M, A_prev, (int)N, M, N, Kb, 1, epi, stream)));
+        } else {
+            RCN_TRY(workspace.reserve((size_t)splits * M * N * sizeof(double)));
+            EpiStore epi{workspace.as<double>(), (int)M, M * N};
+            RCN_TRY((launch_gemm<false, false, EpiStore>(delta, (int)M, A_prev, (int)N, M, N, Kb, splits, epi, stream)));
+            unsigned grid = cdiv(M * N, 256);
+            if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+            reduce_splits_kernel<<<grid, 256, 0, stream>>>(workspace.as<double>(), splits, M * N, dW);
+            RCN_LAUNCH_CHECK();
+        }
+    }
+    bias_grad_kernel<<<cdiv(M, 32), 256, 0, stream>>>(delta, (int)M, (int)Kb, db);
+    RCN_LAUNCH_CHECK();
+    return RCN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SGD step, argmax, batch statistics
+// ------------------------------------------------------------------------------------------------
+__global__ void sgd_update_kernel(double* __restrict__ p, const double* __restrict__ g, size_t n, double scale) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = p[i] - scale * g[i];  // &lw.0 - (eta / B) * w   (rcn.rs:214,221): product rounded, then subtracted
+}
+
+int launch_sgd_update(double* params, const double* grads, size_t n, double scale, cudaStream_t stream) {
+    if (n == 0) return RCN_OK;
+    unsigned grid = cdiv(n, 256);
+    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    sgd_update_kernel<<<grid, 256, 0, stream>>>(params, grads, n, scale);
+    RCN_LAUNCH_CHECK();
+    return RCN_OK;
+}
+
+__global__ void argmax_last_kernel(const double* __restrict__ acts, int n, size_t B, int64_t* __restrict__ labels) {
+    for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < B; b += (size_t)gridDim.x * blockDim.x) {
+        const double* a = acts + b * n;
+        int best = 0;
+        double bv = a[0];
+        for (int i = 1; i < n; ++i) {
+            const double v = a[i];
+            if (!(v < bv)) { bv = v; best = i; }  // max_by(total_cmp): last maximal element wins (rcn.rs:92-97)
+        }
+        labels[b] = best;
+    }
+}
+
+int launch_argmax_last(const double* acts, size_t n, size_t B, int64_t* labels, cudaStream_t stream) {
+    if (B == 0) return RCN_OK;
+    unsigned grid = cdiv(B, 128);
+    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    argmax_last_kernel<<<grid, 128, 0, stream>>>(acts, (int)n, B, labels);
+    RCN_LAUNCH_CHECK();
+    return RCN_OK;
+}
+
+// Single CTA, fixed summation order => deterministic.  cost = sum_b 0.5*|a-y|^2; hits per rcn.rs:153-157:
+// the set {i : a_i == max a} must equal {label}.
+__global__ void __launch_bounds__(256) batch_stats_kernel(const double* __restrict__ acts, int n, size_t B,
+                                                         const double* __restrict__ onehot,
+                                                         const int64_t* __restrict__ labels, double* __restrict__ stats) {
+    __shared__ double sc[256];
+    __shared__ unsigned long long sh[256];
+    double cost = 0.0;
+    unsigned long long hits = 0;
+    for (size_t b = threadIdx.x; b < B; b += blockDim.x) {
+        const double* a = acts + b * n;
+        double mx = a[0];
+        for (int i = 1; i < n; ++i) mx = fmax(mx, a[i]);
+        bool ok = true;
+        double c = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double y = onehot ? onehot[b * n + i] : ((labels[b] == (int64_t)i) ? 1.0 : 0.0);
+            const double d = a[i] - y;
+            c += d * d;
+            const double r = (a[i] == mx) ? 1.0 : 0.0;
+            ok = ok && (r == y);
+        }
+        cost += 0.5 * c;
+        hits += ok ? 1ull : 0ull;
+    }
+    sc[threadIdx.x] = cost;
+    sh[threadIdx.x] = hits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ct = 0.0;
+        unsigned long long ht = 0;
+        for (int i = 0; i < 256; ++i) { ct += sc[i]; ht += sh[i]; }
+        stats[0] = ct;
+        reinterpret_cast<unsigned long long*>(stats)[1] = ht;
+    }
+}
+
+int launch_batch_stats(const double* acts, size_t n, size_t B, const double* onehot, const int64_t* labels,
+                       double* stats_dev, cudaStream_t stream) {
+    batch_stats_kernel<<<1, 256, 0, stream>>>(acts, (int)n, B, onehot, labels, stats_dev);
+    RCN_LAUNCH_CHECK();
+    return RCN_OK;
+}
+
+}  // namespace rcn

@@ -1,0 +1,38 @@
+// dense.cuh -- fully-connected layer kernels (f64): forward, backward-data, backward-weight, SGD step.
+// Reference: rcn/src/rcn.rs:105-116 (classify_test), :260-314 (backprop), :176-223 (train_batch).
+#pragma once
+#include "common.cuh"
+
+namespace rcn {
+
+enum GemmImpl { GEMM_DMMA = 0, GEMM_SIMT = 1 };
+GemmImpl gemm_impl();  // env RCN_CUDA_GEMM=simt selects the plain SIMT cross-check kernels
+
+// A_out (M x N) = sigmoid(W (M x K) * A_in (K x N) + b 1^T)                         rcn.rs:113 / :287-289
+// If delta_out != NULL (last layer): delta_out = (A_out - Y) .* A_out .* (1 - A_out)  rcn.rs:299
+//   with Y given either as one-hot matrix (M x N) or as labels (N).
+int launch_dense_forward(const double* W, const double* b, const double* A_in, size_t M, size_t K, size_t N,
+                         double* A_out, double* delta_out, const double* onehot, const int64_t* labels,
+                         cudaStream_t stream);
+
+// delta_out (M x N) = (W_up^T (M x K) * delta_up (K x N)) .* A (M x N) .* (1 - A)    rcn.rs:305-309
+// W_up is stored K x M (rows = upper layer width).
+int launch_dense_backward_data(const double* W_up, const double* delta_up, const double* A, size_t M, size_t K,
+                               size_t N, double* delta_out, cudaStream_t stream);
+
+// dW (M x N) = delta (M x Kb) * A_prev (N x Kb)^T, db (M) = delta * 1                 rcn.rs:302-303,309-310 summed
+// over the batch (rcn.rs:190-205).  workspace: split-K partials.
+int launch_dense_backward_weight(const double* delta, const double* A_prev, size_t M, size_t N, size_t Kb, double* dW,
+                                 double* db, DevBuf& workspace, cudaStream_t stream);
+
+// params -= scale * grads   (rcn.rs:210-222, scale = eta / batch formed first)
+int launch_sgd_update(double* params, const double* grads, size_t n, double scale, cudaStream_t stream);
+
+// labels[b] = argmax_i acts[i, b], last maximal element wins (rcn.rs:92-97)
+int launch_argmax_last(const double* acts, size_t n, size_t B, int64_t* labels, cudaStream_t stream);
+
+// stats[0] = sum_b 0.5*|a_b - y_b|^2 (as double), stats[1] = bit pattern of uint64 hit count (rcn.rs:153-157)
+int launch_batch_stats(const double* acts, size_t n, size_t B, const double* onehot, const int64_t* labels,
+                       double* stats_dev, cudaStream_t stream);
+
+}  // namespace rcn

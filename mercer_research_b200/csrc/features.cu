@@ -1,0 +1,542 @@
+// features.cu -- rcn's feature stage on sm_100a: separable Sobel x4 -> ReLU -> 2x2 max-pool stacks, flatten,
+// standardise.  Reference: rcn/src/utils/kernel.rs:38-53,110-349 and rcn/src/rcn.rs:41-46,230-251,317-356,
+// 407-412.  HBM-bound integer/byte work: one image per CTA iteration, all intermediate maps stay in shared
+// memory, the only global traffic is the image read and the feature write (H*W*s_in + L*8 B).
+#include "features.cuh"
+
+namespace rcn {
+
+// ------------------------------------------------------------------------------------------------
+// Plan
+// ------------------------------------------------------------------------------------------------
+int plan_features(const int32_t* cfg, size_t n_cfg, size_t H, size_t W, FeaturePlan* plan) {
+    FeaturePlan p;
+    p.stages.n = 0;
+    size_t maps = 0, h = H, w = W;
+    p.max_elems = H * W;
+    for (size_t i = 0; i < n_cfg; ++i) {
+        const int layer = cfg[i];
+        if (layer == RCN_LAYER_CONV_NONE || layer == RCN_LAYER_CONV_SAME) {
+            if (h < 3 || w < 3)  // kernel.rs:199-201
+                return fail(RCN_ERR_SHAPE,
+                            "convolve_2d_separated expects 'self.shape() >= kernel_shape() > 0', received (%zu, %zu) and (3, 3) respectively.", h, w);
+            if (p.stages.n >= kMaxStages) return fail(RCN_ERR_INVALID, "convpool stack too deep (max %d stages)", kMaxStages);
+            Stage& s = p.stages.s[p.stages.n++];
+            s.kind = 0;
+            s.same = (layer == RCN_LAYER_CONV_SAME);
+            s.first = (maps == 0);
+            s.n_in = maps ? (int)maps : 1;
+            s.h_in = (int)h; s.w_in = (int)w;
+            if (!s.same) { h -= 2; w -= 2; }
+            s.h_c = (int)h; s.w_c = (int)w;
+            s.h_out = s.h_c; s.w_out = s.w_c;
+            maps = maps ? maps * 4 : 4;
+            s.n_out = (int)maps;
+            p.n_conv++;
+            // fuse a directly following pool layer
+            if (i + 1 < n_cfg && (cfg[i + 1] == RCN_LAYER_POOL_MAX || cfg[i + 1] == RCN_LAYER_POOL_AVERAGE)) {
+                if (cfg[i + 1] == RCN_LAYER_POOL_AVERAGE) return fail(RCN_ERR_NOT_IMPLEMENTED, "Not implemented");  // kernel.rs:284
+                if (h < 2 || w < 2)  // kernel.rs:246-251
+                    return fail(RCN_ERR_SHAPE, "stride_2d expected a matrix with dimensions greater than (2, 2), got (%zu, %zu)", h, w);
+                h = (h + 1) / 2; w = (w + 1) / 2;  // always Padding::Same (rcn.rs:344)
+                s.kind = 1;
+                s.h_out = (int)h; s.w_out = (int)w;
+                ++i;
+            }
+        } else if (layer == RCN_LAYER_POOL_MAX || layer == RCN_LAYER_POOL_AVERAGE) {
+            if (maps == 0) continue;  // pooling an empty feature set is a no-op (rcn.rs:343)
+            if (h < 2 || w < 2)
+                return fail(RCN_ERR_SHAPE, "stride_2d expected a matrix with dimensions greater than (2, 2), got (%zu, %zu)", h, w);
+            if (layer == RCN_LAYER_POOL_AVERAGE) return fail(RCN_ERR_NOT_IMPLEMENTED, "Not implemented");
+            if (p.stages.n >= kMaxStages) return fail(RCN_ERR_INVALID, "convpool stack too deep (max %d stages)", kMaxStages);
+            Stage& s = p.stages.s[p.stages.n++];
+            s.kind = 2; s.same = 1; s.first = 0;
+            s.n_in = (int)maps; s.h_in = (int)h; s.w_in = (int)w; s.h_c = (int)h; s.w_c = (int)w;
+            h = (h + 1) / 2; w = (w + 1) / 2;
+            s.h_out = (int)h; s.w_out = (int)w; s.n_out = (int)maps;
+        } else {
+            return fail(RCN_ERR_INVALID, "unknown RCNLayer code %d", layer);
+        }
+        const size_t in_elems = (size_t)p.stages.s[p.stages.n - 1].n_in * p.stages.s[p.stages.n - 1].h_in * p.stages.s[p.stages.n - 1].w_in;
+        if (in_elems > p.max_elems) p.max_elems = in_elems;
+        if (maps * h * w > ((size_t)1 << 30)) return fail(RCN_ERR_INVALID, "feature set too large");
+    }
+    p.n_maps = maps; p.map_h = maps ? h : 0; p.map_w = maps ? w : 0;
+    p.L = maps * p.map_h * p.map_w;
+    *plan = p;
+    return RCN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device arithmetic.  mac(a, k, c) = c + a*k.  The taps are in {0, +-1, +-2}, so a*k is exact in f64 and a
+// fused multiply-add rounds exactly like the reference's separate multiply and add (kernel.rs:164).  Zero
+// taps are kept (inf*0 must stay NaN as in the reference); for T = int the compiler folds them away.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double mac(double a, double k, double c) { return fma(a, k, c); }
+__device__ __forceinline__ int mac(int a, int k, int c) { return a * k + c; }
+
+template <typename T>
+__device__ __forceinline__ T relu1(T v) { return (v >= T(0)) ? v : T(0); }  // kernel.rs:214
+
+// Pre-activation responses of the four operators (kernel.rs:38-53) at output pixel (y, x) of
+// convolve_2d(3x1, p) . convolve_2d(1x3, p)  (kernel.rs:204-205), f is one h x w column-major map.
+// SAME reproduces the reference's padded-copy quirk (kernel.rs:154-158): the result is the
+// Sobel response centred at (y-1, x-1); row 0 is zero; the last input column / last intermediate row are
+// never read.
+template <typename T, bool SAME>
+__device__ __forceinline__ void sobel4(const T* __restrict__ f, int h, int w, int y, int x, T& t, T& l, T& r, T& b) {
+    const T Z = T(0);
+    T ct[3], cb[3], cs[3];  // vertical passes with [1,0,-1], [-1,0,1], [1,2,1] at the three columns
+    if (SAME) {
+        if (y == 0) { t = l = r = b = Z; return; }
+        const int rr = y - 1;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int j = x + k - 2;
+            if (j >= 0 && j <= w - 2) {
+                const T* col = f + (size_t)j * h;
+                const T x0 = (rr >= 1) ? col[rr - 1] : Z;
+                const T x1 = col[rr];
+                const T x2 = col[rr + 1];
+                ct[k] = mac(x2, T(-1), mac(x1, T(0), mac(x0, T(1), Z)));
+                cb[k] = mac(x2, T(1), mac(x1, T(0), mac(x0, T(-1), Z)));
+                cs[k] = mac(x2, T(1), mac(x1, T(2), mac(x0, T(1), Z)));
+            } else {
+                ct[k] = cb[k] = cs[k] = Z;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const T* col = f + (size_t)(x + k) * h;
+            const T x0 = col[y], x1 = col[y + 1], x2 = col[y + 2];
+            ct[k] = mac(x2, T(-1), mac(x1, T(0), mac(x0, T(1), Z)));
+            cb[k] = mac(x2, T(1), mac(x1, T(0), mac(x0, T(-1), Z)));
+            cs[k] = mac(x2, T(1), mac(x1, T(2), mac(x0, T(1), Z)));
+        }
+    }
+    t = mac(ct[2], T(1), mac(ct[1], T(2), mac(ct[0], T(1), Z)));   // Top:    h = [1,2,1]
+    b = mac(cb[2], T(1), mac(cb[1], T(2), mac(cb[0], T(1), Z)));   // Bottom: h = [1,2,1]
+    l = mac(cs[2], T(-1), mac(cs[1], T(0), mac(cs[0], T(1), Z)));  // Left:   h = [1,0,-1]
+    r = mac(cs[2], T(1), mac(cs[1], T(0), mac(cs[0], T(-1), Z)));  // Right:  h = [-1,0,1]
+}
+
+template <typename T>
+__device__ __forceinline__ void sobel4_relu(const Stage& st, const T* __restrict__ f, int y, int x, T& t, T& l, T& r, T& b) {
+    if (st.same) sobel4<T, true>(f, st.h_in, st.w_in, y, x, t, l, r, b);
+    else sobel4<T, false>(f, st.h_in, st.w_in, y, x, t, l, r, b);
+    t = relu1(t); l = relu1(l); r = relu1(r); b = relu1(b);
+}
+
+// Iterator::max_by keeps the LAST maximal element (kernel.rs:278-281): replace unless strictly smaller.
+template <typename T>
+__device__ __forceinline__ void max_last(T& best, T v) { if (!(v < best)) best = v; }
+
+// Runs one stage for one image.  `in`: n_in maps (column-major each, back to back).  emit(slot, y, x, v).
+template <typename T, typename Emit>
+__device__ __forceinline__ void run_stage(const Stage& st, const T* __restrict__ in, Emit emit, int tid, int nthreads) {
+    const int hw_out = st.h_out * st.w_out;
+    const int hw_in = st.h_in * st.w_in;
+    const int items = st.n_in * hw_out;
+    for (int it = tid; it < items; it += nthreads) {
+        const int i = it / hw_out;
+        const int rem = it - i * hw_out;
+        const int x = rem / st.h_out;
+        const int y = rem - x * st.h_out;
+        const T* f = in + (size_t)i * hw_in;
+        if (st.kind == 2) {
+            // pool_2d(Padding::Same, Max): kernel.rs:245-349, zero row/col appended when odd.
+            T best = T(0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int cy = 2 * y + (q >> 1), cx = 2 * x + (q & 1);
+                const T v = (cy < st.h_in && cx < st.w_in) ? f[(size_t)cx * st.h_in + cy] : T(0);
+                if (q == 0) best = v; else max_last(best, v);
+            }
+            emit(i, y, x, best);
+            continue;
+        }
+        T t, l, r, b;
+        if (st.kind == 0) {
+            sobel4_relu<T>(st, f, y, x, t, l, r, b);
+        } else {
+            t = l = r = b = T(0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int cy = 2 * y + (q >> 1), cx = 2 * x + (q & 1);
+                T vt = T(0), vl = T(0), vr = T(0), vb = T(0);
+                if (cy < st.h_c && cx < st.w_c) sobel4_relu<T>(st, f, cy, cx, vt, vl, vr, vb);
+                if (q == 0) { t = vt; l = vl; r = vr; b = vb; }
+                else { max_last(t, vt); max_last(l, vl); max_last(r, vr); max_last(b, vb); }
+            }
+        }
+        // Slot order (rcn.rs:325-339): first conv -> [T,L,R,B]; later convs overwrite slot i with Bottom and
+        // append Top, Left, Right of map i at n + 3i.
+        int sT, sL, sR, sB;
+        if (st.first) { sT = 0; sL = 1; sR = 2; sB = 3; }
+        else { sB = i; sT = st.n_in + 3 * i; sL = sT + 1; sR = sT + 2; }
+        emit(sT, y, x, t); emit(sL, y, x, l); emit(sR, y, x, r); emit(sB, y, x, b);
+    }
+}
+
+template <typename T>
+struct EmitMaps {  // into a map set (shared or global), column-major maps back to back
+    T* out; int h, hw;
+    __device__ __forceinline__ void operator()(int slot, int y, int x, T v) const { out[(size_t)slot * hw + x * h + y] = v; }
+};
+
+template <typename T>
+struct EmitFeatures {  // final stage: flatten (rcn.rs:350-355) + optional standardise/clamp (rcn.rs:407-412)
+    double* out; int h, hw; bool standardise; double mean, sd;
+    __device__ __forceinline__ void operator()(int slot, int y, int x, T v) const {
+        double d = (double)v;
+        if (standardise) { d = (d - mean) / sd; d = (d >= 0.0) ? d : 0.0; }
+        out[(size_t)slot * hw + x * h + y] = d;
+    }
+};
+
+template <typename TIN, typename T>
+__device__ __forceinline__ void load_image(const TIN* __restrict__ src, T* dst, int H, int W, int tid, int nthreads);
+
+// u8 row-major (image crate) -> column-major T: DMatrix::from_row_iterator (lib.rs:29-33)
+template <>
+__device__ __forceinline__ void load_image<uint8_t, int>(const uint8_t* __restrict__ src, int* dst, int H, int W, int tid, int nthreads) {
+    const int n = H * W;
+    for (int i = tid; i < n; i += nthreads) { const int r = i / W, c = i - r * W; dst[c * H + r] = (int)src[i]; }
+}
+template <>
+__device__ __forceinline__ void load_image<uint8_t, double>(const uint8_t* __restrict__ src, double* dst, int H, int W, int tid, int nthreads) {
+    const int n = H * W;
+    for (int i = tid; i < n; i += nthreads) { const int r = i / W, c = i - r * W; dst[c * H + r] = (double)src[i]; }
+}
+template <>
+__device__ __forceinline__ void load_image<double, double>(const double* __restrict__ src, double* dst, int H, int W, int tid, int nthreads) {
+    const int n = H * W;
+    for (int i = tid; i < n; i += nthreads) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused path: whole convpool stack of one image in shared memory.
+// ------------------------------------------------------------------------------------------------
+template <typename TIN, typename T>
+__global__ void __launch_bounds__(256) features_fused_kernel(const TIN* __restrict__ images, int B, int H, int W,
+                                                            const __grid_constant__ StageList sl, int buf_elems,
+                                                            double* __restrict__ out, size_t L, int standardise,
+                                                            double mean, double sd) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* buf0 = reinterpret_cast<T*>(smem_raw);
+    T* buf1 = buf0 + buf_elems;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int img = blockIdx.x; img < B; img += gridDim.x) {
+        load_image<TIN, T>(images + (size_t)img * H * W, buf0, H, W, tid, nt);
+        __syncthreads();
+        T* cur = buf0;
+        T* nxt = buf1;
+        for (int s = 0; s < sl.n; ++s) {
+            const Stage& st = sl.s[s];
+            if (s == sl.n - 1) {
+                EmitFeatures<T> e{out + (size_t)img * L, st.h_out, st.h_out * st.w_out, standardise != 0, mean, sd};
+                run_stage<T>(st, cur, e, tid, nt);
+            } else {
+                EmitMaps<T> e{nxt, st.h_out, st.h_out * st.w_out};
+                run_stage<T>(st, cur, e, tid, nt);
+                __syncthreads();
+                T* tmp = cur; cur = nxt; nxt = tmp;
+            }
+        }
+        __syncthreads();  // the next image overwrites buf0
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layer-by-layer path (map sets too large for shared memory): same stage code over global buffers.
+// ------------------------------------------------------------------------------------------------
+template <typename TIN, typename T>
+__global__ void convert_images_kernel(const TIN* __restrict__ images, T* __restrict__ out, int H, int W, size_t B) {
+    for (size_t img = blockIdx.y; img < B; img += gridDim.y)
+        load_image<TIN, T>(images + img * H * W, out + img * H * W, H, W, blockIdx.x * blockDim.x + threadIdx.x,
+                           gridDim.x * blockDim.x);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) stage_maps_kernel(const __grid_constant__ Stage st, const T* __restrict__ in,
+                                                        size_t in_stride, T* __restrict__ out, size_t out_stride, size_t B) {
+    for (size_t img = blockIdx.y; img < B; img += gridDim.y) {
+        EmitMaps<T> e{out + img * out_stride, st.h_out, st.h_out * st.w_out};
+        run_stage<T>(st, in + img * in_stride, e, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) stage_final_kernel(const __grid_constant__ Stage st, const T* __restrict__ in,
+                                                         size_t in_stride, double* __restrict__ out, size_t L,
+                                                         int standardise, double mean, double sd, size_t B) {
+    for (size_t img = blockIdx.y; img < B; img += gridDim.y) {
+        EmitFeatures<T> e{out + img * L, st.h_out, st.h_out * st.w_out, standardise != 0, mean, sd};
+        run_stage<T>(st, in + img * in_stride, e, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    }
+}
+
+constexpr size_t kFusedSmemLimit = 200 * 1024;
+
+template <typename TIN, typename T>
+static int launch_features_t(const FeaturePlan& plan, const TIN* images, size_t B, size_t H, size_t W, bool standardise,
+                             double mean, double sd, double* out, FeatureScratch& scratch, cudaStream_t stream) {
+    const StageList& sl = plan.stages;
+    const size_t smem = 2 * plan.max_elems * sizeof(T);
+    if (smem <= kFusedSmemLimit) {
+        auto kern = features_fused_kernel<TIN, T>;
+        if (smem > 48 * 1024) RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // One image per CTA iteration; enough CTAs per SM to hide the load -> compute -> store chain.
+        size_t per_sm = smem ? (kFusedSmemLimit / smem) : 8;
+        if (per_sm > 8) per_sm = 8;
+        if (per_sm < 1) per_sm = 1;
+        size_t grid = (size_t)kNumSMs * per_sm;
+        if (grid > B) grid = B;
+        kern<<<(unsigned)grid, 256, smem, stream>>>(images, (int)B, (int)H, (int)W, sl, (int)plan.max_elems, out, plan.L,
+                                                    standardise ? 1 : 0, mean, sd);
+        RCN_LAUNCH_CHECK();
+        return RCN_OK;
+    }
+    // layer-by-layer over global ping-pong buffers
+    size_t max_set = H * W;
+    for (int s = 0; s < sl.n; ++s) {
+        size_t o = (size_t)sl.s[s].n_out * sl.s[s].h_out * sl.s[s].w_out;
+        if (s + 1 < sl.n && o > max_set) max_set = o;
+    }
+    RCN_TRY(scratch.a.reserve(B * max_set * sizeof(T)));
+    RCN_TRY(scratch.b.reserve(B * max_set * sizeof(T)));
+    T* cur = scratch.a.as<T>();
+    T* nxt = scratch.b.as<T>();
+    size_t cur_stride = H * W;
+    {
+        dim3 grid(cdiv(H * W, 256), (unsigned)(B > 32768 ? 32768 : B));
+        if (grid.x > 64) grid.x = 64;
+        convert_images_kernel<TIN, T><<<grid, 256, 0, stream>>>(images, cur, (int)H, (int)W, B);
+        RCN_LAUNCH_CHECK();
+    }
+    for (int s = 0; s < sl.n; ++s) {
+        const Stage& st = sl.s[s];
+        const size_t items = (size_t)st.n_in * st.h_out * st.w_out;
+        dim3 grid(cdiv(items, 256), (unsigned)(B > 32768 ? 32768 : B));
+        if (grid.x > 1024) grid.x = 1024;
+        if (s == sl.n - 1) {
+            stage_final_kernel<T><<<grid, 256, 0, stream>>>(st, cur, cur_stride, out, plan.L, standardise ? 1 : 0, mean, sd, B);
+            RCN_LAUNCH_CHECK();
+        } else {
+            const size_t out_stride = (size_t)st.n_out * st.h_out * st.w_out;
+            stage_maps_kernel<T><<<grid, 256, 0, stream>>>(st, cur, cur_stride, nxt, out_stride, B);
+            RCN_LAUNCH_CHECK();
+            T* tmp = cur; cur = nxt; nxt = tmp;
+            cur_stride = out_stride;
+        }
+    }
+    return RCN_OK;
+}
+
+int launch_features(const FeaturePlan& plan, const void* images, int pixel_format, size_t B, size_t H, size_t W,
+                    bool standardise, double mean, double sd, double* out, FeatureScratch& scratch,
+                    cudaStream_t stream) {
+    if (B == 0 || plan.L == 0) return RCN_OK;  // no conv layer => empty feature vector (rcn.rs:323,339)
+    if (B > ((size_t)1 << 30)) return fail(RCN_ERR_INVALID, "batch too large");
+    if (pixel_format == RCN_PIXELS_U8_ROWMAJOR) {
+        // u8 pixels: every intermediate is an integer bounded by 255 * 4^n_conv, so int32 arithmetic is exact
+        // (and bit-identical to the reference's f64) up to 10 conv layers.
+        if (plan.n_conv <= 10)
+            return launch_features_t<uint8_t, int>(plan, (const uint8_t*)images, B, H, W, standardise, mean, sd, out, scratch, stream);
+        return launch_features_t<uint8_t, double>(plan, (const uint8_t*)images, B, H, W, standardise, mean, sd, out, scratch, stream);
+    }
+    if (pixel_format == RCN_PIXELS_F64_COLMAJOR)
+        return launch_features_t<double, double>(plan, (const double*)images, B, H, W, standardise, mean, sd, out, scratch, stream);
+    return fail(RCN_ERR_INVALID, "unknown pixel format %d", pixel_format);
+}
+
+// ------------------------------------------------------------------------------------------------
+// standardise (rcn.rs:407-412) and gen_scales (rcn.rs:230-251)
+// ------------------------------------------------------------------------------------------------
+__global__ void standardise_kernel(double* __restrict__ v, size_t n, double mean, double sd) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double d = (v[i] - mean) / sd;
+        v[i] = (d >= 0.0) ? d : 0.0;
+    }
+}
+
+int launch_standardise(double* feats, size_t n, double mean, double sd, cudaStream_t stream) {
+    if (n == 0) return RCN_OK;
+    unsigned grid = cdiv(n, 256);
+    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    standardise_kernel<<<grid, 256, 0, stream>>>(feats, n, mean, sd);
+    RCN_LAUNCH_CHECK();
+    return RCN_OK;
+}
+
+__device__ __forceinline__ double block_sum_256(double v, double* sm) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (warp == 0) {
+        s = (lane < (blockDim.x >> 5)) ? sm[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    }
+    __syncthreads();
+    return s;  // valid in warp 0
+}
+
+// pass == 0: partial sums of v; pass == 1: partial sums of (v - mean)^2 with mean = result[0]
+__global__ void __launch_bounds__(256) scale_partial_kernel(const double* __restrict__ v, size_t n, int pass,
+                                                           const double* __restrict__ result, double* __restrict__ partial) {
+    __shared__ double sm[8];
+    const double mean = pass ? result[0] : 0.0;
+    double acc = 0.0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double d = v[i] - mean;
+        acc += pass ? d * d : d;
+    }
+    const double s = block_sum_256(acc, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) scale_final_kernel(const double* __restrict__ partial, int n_part, size_t n, int pass,
+                                                         double* __restrict__ result) {
+    __shared__ double sm[8];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n_part; i += blockDim.x) acc += partial[i];
+    const double s = block_sum_256(acc, sm);
+    if (threadIdx.x == 0) {
+        if (pass == 0) result[0] = s / (double)n;          // mean /= n          (rcn.rs:240)
+        else result[1] = sqrt(s / (double)n);              // sqrt(sd / n)       (rcn.rs:247)
+    }
+}
+
+int launch_gen_scales(const double* feats, size_t n, double* result_dev, DevBuf& scratch, cudaStream_t stream) {
+    if (n == 0) return fail(RCN_ERR_INVALID, "gen_scales on an empty set");
+    int grid = (int)cdiv(n, 256 * 8);
+    if (grid > kNumSMs * 4) grid = kNumSMs * 4;
+    if (grid < 1) grid = 1;
+    RCN_TRY(scratch.reserve((size_t)grid * sizeof(double)));
+    double* partial = scratch.as<double>();
+    for (int pass = 0; pass < 2; ++pass) {
+        scale_partial_kernel<<<grid, 256, 0, stream>>>(feats, n, pass, result_dev, partial);
+        RCN_LAUNCH_CHECK();
+        scale_final_kernel<<<1, 256, 0, stream>>>(partial, grid, n, pass, result_dev);
+        RCN_LAUNCH_CHECK();
+    }
+    return RCN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// op-level kernels: Convolve2D / Pool2D traits on a single matrix (kernel.rs:61-100, 219-236)
+// ------------------------------------------------------------------------------------------------
+// convolve_2d (kernel.rs:110-194) with an arbitrary kernel.  Products are not exact here, so multiply and add
+// are rounded separately (__dmul_rn / __dadd_rn are never contracted), ky outer / kx inner from +0.
+__global__ void conv2d_generic_kernel(const double* __restrict__ m, int H, int W, const double* __restrict__ k, int kh,
+                                      int kw, int same, double* __restrict__ out, int oh, int ow) {
+    const int ph = same ? kh / 2 : 0, pw = same ? kw / 2 : 0;
+    const size_t total = (size_t)oh * ow;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int cx = (int)(idx / oh), cy = (int)(idx - (size_t)cx * oh);
+        double acc = 0.0;
+        for (int ky = 0; ky < kh; ++ky)
+            for (int kx = 0; kx < kw; ++kx) {
+                double p;
+                if (same) {
+                    // padded copy matrix[(cy,cx)] = self[(cy-1,cx-1)] for cy in 1..H+ph, cx in 1..W+pw (kernel.rs:154-158)
+                    const int py = cy + ky, px = cx + kx;
+                    p = (py >= 1 && py < H + ph && px >= 1 && px < W + pw) ? m[(size_t)(px - 1) * H + (py - 1)] : 0.0;
+                } else {
+                    p = m[(size_t)(cx + kx) * H + (cy + ky)];
+                }
+                acc = __dadd_rn(acc, __dmul_rn(p, k[(size_t)kx * kh + ky]));
+            }
+        out[idx] = acc;
+    }
+}
+
+int launch_convolve_2d(const double* m, size_t H, size_t W, const double* k, size_t kh, size_t kw, int padding,
+                       double* out, cudaStream_t stream) {
+    const bool same = padding == RCN_PADDING_SAME;
+    const size_t oh = same ? H : H - kh + 1, ow = same ? W : W - kw + 1;
+    unsigned grid = cdiv(oh * ow, 256);
+    if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+    conv2d_generic_kernel<<<grid, 256, 0, stream>>>(m, (int)H, (int)W, k, (int)kh, (int)kw, same ? 1 : 0, out, (int)oh, (int)ow);
+    RCN_LAUNCH_CHECK();
+    return RCN_OK;
+}
+
+template <bool SAME>
+__global__ void conv_sep_single_kernel(const double* __restrict__ m, int H, int W, int op, double* __restrict__ out, int oh, int ow) {
+    const size_t total = (size_t)oh * ow;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(idx / oh), y = (int)(idx - (size_t)x * oh);
+        double t, l, r, b;
+        sobel4<double, SAME>(m, H, W, y, x, t, l, r, b);
+        const double v = op == RCN_OP_TOP ? t : op == RCN_OP_BOTTOM ? b : op == RCN_OP_LEFT ? l : r;
+        out[idx] = relu1(v);
+    }
+}
+
+int launch_convolve_2d_separated(const double* m, size_t H, size_t W, int op, int padding, double* out, cudaStream_t stream) {
+    const bool same = padding == RCN_PADDING_SAME;
+    const size_t oh = same ? H : H - 2, ow = same ? W : W - 2;
+    unsigned grid = cdiv(oh * ow, 256);
+    if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+    if (same) conv_sep_single_kernel<true><<<grid, 256, 0, stream>>>(m, (int)H, (int)W, op, out, (int)oh, (int)ow);
+    else conv_sep_single_kernel<false><<<grid, 256, 0, stream>>>(m, (int)H, (int)W, op, out, (int)oh, (int)ow);
+    RCN_LAUNCH_CHECK();
+    return RCN_OK;
+}
+
+__global__ void relu_kernel(const double* __restrict__ m, size_t n, double* __restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = relu1(m[i]);
+}
+
+int launch_relu(const double* m, size_t n, double* out, cudaStream_t stream) {
+    if (n == 0) return RCN_OK;
+    unsigned grid = cdiv(n, 256);
+    if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+    relu_kernel<<<grid, 256, 0, stream>>>(m, n, out);
+    RCN_LAUNCH_CHECK();
+    return RCN_OK;
+}
+
+// pool_2d (kernel.rs:245-349), Max only.  pad_h/pad_w: zero row/col appended (Padding::Same on odd sizes).
+__global__ void pool2d_kernel(const double* __restrict__ m, int H, int W, double* __restrict__ out, int oh, int ow,
+                              uint8_t* __restrict__ argmax, int* __restrict__ nan_flag) {
+    const size_t total = (size_t)oh * ow;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int rx = (int)(idx / oh), ry = (int)(idx - (size_t)rx * oh);
+        double best = 0.0;
+        int bi = 0;
+        bool nan = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {  // pooler[py + 2*px] = m[(2ry+px, 2rx+py)]  (kernel.rs:273-277)
+            const int cy = 2 * ry + (q >> 1), cx = 2 * rx + (q & 1);
+            const double v = (cy < H && cx < W) ? m[(size_t)cx * H + cy] : 0.0;
+            nan |= (v != v);
+            if (q == 0) { best = v; bi = 0; }
+            else if (!(v < best)) { best = v; bi = q; }
+        }
+        out[idx] = best;
+        if (argmax) argmax[idx] = (uint8_t)bi;
+        if (nan && nan_flag) *nan_flag = 1;
+    }
+}
+
+int launch_pool_2d(const double* m, size_t H, size_t W, int padding, double* out, uint8_t* argmax, int* nan_flag,
+                   cudaStream_t stream) {
+    const bool same = padding == RCN_PADDING_SAME;
+    const size_t oh = same ? (H + 1) / 2 : H / 2, ow = same ? (W + 1) / 2 : W / 2;
+    if (oh * ow == 0) return RCN_OK;
+    unsigned grid = cdiv(oh * ow, 256);
+    if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+    pool2d_kernel<<<grid, 256, 0, stream>>>(m, (int)H, (int)W, out, (int)oh, (int)ow, argmax, nan_flag);
+    RCN_LAUNCH_CHECK();
+    return RCN_OK;
+}
+
+}  // namespace rcn

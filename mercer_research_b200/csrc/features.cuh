@@ -1,0 +1,59 @@
+// features.cuh -- feature-stage declarations (Sobel-separated conv -> ReLU -> 2x2 max-pool stacks).
+#pragma once
+#include "common.cuh"
+
+namespace rcn {
+
+// One executable stage of a convpool stack (rcn.rs:317-348). A Convolve2D layer directly followed by a
+// Pool2D layer is fused into one stage so the 4x-larger conv output never leaves registers.
+struct Stage {
+    int kind;         // 0 = conv (+relu), 1 = conv (+relu) + max-pool, 2 = max-pool only
+    int same;         // conv padding == Padding::Same
+    int first;        // conv input is the raw image: one map, output slots [T,L,R,B] (rcn.rs:339)
+    int n_in;         // input maps
+    int h_in, w_in;   // input map size
+    int h_c, w_c;     // conv output size (pool-only: == input size)
+    int h_out, w_out; // stage output map size
+    int n_out;        // output maps
+};
+constexpr int kMaxStages = 24;
+struct StageList {
+    Stage s[kMaxStages];
+    int n;
+};
+
+struct FeaturePlan {
+    StageList stages;
+    size_t n_maps = 0, map_h = 0, map_w = 0, L = 0;
+    size_t max_elems = 0;  // largest per-image map set any stage reads (elements)
+    int n_conv = 0;
+};
+
+// Walks convpool_cfg for an H x W input; returns RCN_ERR_SHAPE / RCN_ERR_NOT_IMPLEMENTED where the
+// reference would panic.
+int plan_features(const int32_t* cfg, size_t n_cfg, size_t H, size_t W, FeaturePlan* plan);
+
+// Scratch owned by the caller (model): ping-pong buffers for the layer-by-layer path.
+struct FeatureScratch {
+    DevBuf a, b;
+};
+
+// images: DEVICE pointer, B images in `pixel_format`; out: DEVICE L x B.
+int launch_features(const FeaturePlan& plan, const void* images, int pixel_format, size_t B, size_t H, size_t W,
+                    bool standardise, double mean, double sd, double* out, FeatureScratch& scratch,
+                    cudaStream_t stream);
+
+int launch_standardise(double* feats, size_t n, double mean, double sd, cudaStream_t stream);
+// Deterministic two-pass mean / population-sd; result[0]=mean, result[1]=sd (device), needs scratch.
+int launch_gen_scales(const double* feats, size_t n, double* result_dev, DevBuf& scratch, cudaStream_t stream);
+
+// op-level kernels (single matrix, device pointers)
+int launch_convolve_2d(const double* m, size_t H, size_t W, const double* k, size_t kh, size_t kw, int padding,
+                       double* out, cudaStream_t stream);
+int launch_convolve_2d_separated(const double* m, size_t H, size_t W, int op, int padding, double* out,
+                                 cudaStream_t stream);
+int launch_relu(const double* m, size_t n, double* out, cudaStream_t stream);
+int launch_pool_2d(const double* m, size_t H, size_t W, int padding, double* out, uint8_t* argmax, int* nan_flag,
+                   cudaStream_t stream);
+
+}  // namespace rcn

@@ -1,0 +1,756 @@
+// model.cu -- the C ABI of librcn_cuda.so (include/rcn_cuda.h): model handle, device buffers, host<->device
+// staging, and the layer dispatch that replaces rcn's per-sample CPU loops (rcn/src/rcn.rs) with batched
+// kernels (features.cu, dense.cu).
+#include <memory>
+#include <new>
+#include <vector>
+
+#include "dense.cuh"
+#include "features.cuh"
+
+namespace rcn {
+
+std::string& last_error_ref() {
+    thread_local std::string s;
+    return s;
+}
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error_ref() = buf;
+    return code;
+}
+
+}  // namespace rcn
+
+using namespace rcn;
+
+struct rcn_cuda_model {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    size_t classes = 0;
+    std::vector<int32_t> cfg;
+    std::vector<size_t> ff;
+
+    // parameters: flat [W0|b0|W1|b1|...], W_l column-major rows[l] x cols[l] (serialization.rs:19-22 order)
+    bool params_ready = false;
+    std::vector<size_t> rows, cols, w_off, b_off;
+    size_t n_params = 0, sum_rows = 0;
+    DevBuf params, grads_own;
+    double* grads = nullptr;
+    bool grads_bound = false;
+    double mean = 1.0, sd = 1.0;  // scale_set starts at (1, 1)  (rcn.rs:71)
+
+    // feature plan cache
+    bool plan_valid = false;
+    size_t plan_H = 0, plan_W = 0;
+    FeaturePlan plan;
+    FeatureScratch fscratch;
+
+    // scratch (grow-only)
+    DevBuf in_stage, tgt_stage, feats, acts, deltas, gemm_ws, out_stage, small, red_ws;
+    size_t last_B = 0;          // batch of the last accumulate call (taps)
+    bool stats_valid = false;
+
+    double* act(size_t l, size_t B) const {
+        size_t off = 0;
+        for (size_t j = 0; j < l; ++j) off += rows[j];
+        return acts.as<double>() + off * B;
+    }
+    double* delta(size_t l, size_t B) const {
+        size_t off = 0;
+        for (size_t j = 0; j < l; ++j) off += rows[j];
+        return deltas.as<double>() + off * B;
+    }
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() { /* leave the device selected: one process drives one GPU */ }
+};
+
+#define RCN_ENTER(h)                                                                     \
+    if (!(h)) return fail(RCN_ERR_INVALID, "null model handle");                         \
+    DeviceGuard _guard((h)->device);                                                     \
+    if (!_guard.ok) return fail(RCN_ERR_CUDA, "cudaSetDevice(%d) failed", (h)->device);
+
+int ensure_plan(rcn_cuda_model* h, size_t H, size_t W) {
+    if (h->plan_valid && h->plan_H == H && h->plan_W == W) return RCN_OK;
+    if (H == 0 || W == 0 || H > 32768 || W > 32768) return fail(RCN_ERR_INVALID, "bad image size %zu x %zu", H, W);
+    RCN_TRY(plan_features(h->cfg.data(), h->cfg.size(), H, W, &h->plan));
+    h->plan_valid = true; h->plan_H = H; h->plan_W = W;
+    return RCN_OK;
+}
+
+size_t pixel_bytes(int fmt) { return fmt == RCN_PIXELS_U8_ROWMAJOR ? 1 : 8; }
+
+// Copies a device result to a possibly-host destination; `synced` is set when the stream was drained.
+int deliver(rcn_cuda_model* h, void* dst, const void* dev_src, size_t bytes) {
+    if (bytes == 0) return RCN_OK;
+    if (is_device_ptr(dst)) {
+        if (dst != dev_src) RCN_CUDA_TRY(cudaMemcpyAsync(dst, dev_src, bytes, cudaMemcpyDeviceToDevice, h->stream));
+        return RCN_OK;
+    }
+    RCN_CUDA_TRY(cudaMemcpyAsync(dst, dev_src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return RCN_OK;
+}
+
+int require_params(rcn_cuda_model* h) {
+    if (!h->params_ready) return fail(RCN_ERR_STATE, "parameters not initialised: call rcn_cuda_init_params first");
+    return RCN_OK;
+}
+
+// features (+ optional standardise) into h->feats for device or host images
+int features_into(rcn_cuda_model* h, const void* images, int fmt, size_t B, size_t H, size_t W, bool standardise,
+                  double* out_dev) {
+    RCN_TRY(ensure_plan(h, H, W));
+    if (fmt != RCN_PIXELS_U8_ROWMAJOR && fmt != RCN_PIXELS_F64_COLMAJOR) return fail(RCN_ERR_INVALID, "unknown pixel format %d", fmt);
+    if (B == 0 || h->plan.L == 0) return RCN_OK;
+    if (!images) return fail(RCN_ERR_INVALID, "null images");
+    StagedIn in;
+    RCN_TRY(in.stage(images, B * H * W * pixel_bytes(fmt), h->in_stage, h->stream, nullptr));
+    return launch_features(h->plan, in.dev, fmt, B, H, W, standardise, h->mean, h->sd, out_dev, h->fscratch, h->stream);
+}
+
+// forward pass over device feats (cols[0] x B); fills acts; last layer also fills deltas when targets given
+int forward_dev(rcn_cuda_model* h, const double* feats, size_t B, const double* onehot, const int64_t* labels,
+                bool want_delta) {
+    const size_t n = h->rows.size();
+    RCN_TRY(h->acts.reserve(h->sum_rows * B * sizeof(double)));
+    if (want_delta) RCN_TRY(h->deltas.reserve(h->sum_rows * B * sizeof(double)));
+    for (size_t l = 0; l < n; ++l) {
+        const double* a_in = l == 0 ? feats : h->act(l - 1, B);
+        const bool last = (l + 1 == n);
+        RCN_TRY(launch_dense_forward(h->params.as<double>() + h->w_off[l], h->params.as<double>() + h->b_off[l], a_in,
+                                     h->rows[l], h->cols[l], B, h->act(l, B),
+                                     (last && want_delta) ? h->delta(l, B) : nullptr, onehot, labels, h->stream));
+    }
+    return RCN_OK;
+}
+
+int accumulate_dev(rcn_cuda_model* h, const double* feats, const double* onehot, const int64_t* labels, size_t B) {
+    const size_t n = h->rows.size();
+    if (B == 0) {
+        RCN_CUDA_TRY(cudaMemsetAsync(h->grads, 0, h->n_params * sizeof(double), h->stream));
+        return RCN_OK;
+    }
+    RCN_TRY(forward_dev(h, feats, B, onehot, labels, true));
+    for (size_t l = n - 1; l-- > 0;)  // rcn.rs:305-311
+        RCN_TRY(launch_dense_backward_data(h->params.as<double>() + h->w_off[l + 1], h->delta(l + 1, B), h->act(l, B),
+                                           h->rows[l], h->rows[l + 1], B, h->delta(l, B), h->stream));
+    for (size_t l = 0; l < n; ++l) {
+        const double* a_prev = l == 0 ? feats : h->act(l - 1, B);
+        RCN_TRY(launch_dense_backward_weight(h->delta(l, B), a_prev, h->rows[l], h->cols[l], B, h->grads + h->w_off[l],
+                                             h->grads + h->b_off[l], h->gemm_ws, h->stream));
+    }
+    RCN_TRY(h->small.reserve(64));
+    RCN_TRY(launch_batch_stats(h->act(n - 1, B), h->rows[n - 1], B, onehot, labels, h->small.as<double>(), h->stream));
+    h->stats_valid = true;
+    h->last_B = B;
+    return RCN_OK;
+}
+
+// stage targets (exactly one of onehot / labels)
+int stage_targets(rcn_cuda_model* h, const double* onehot, const int64_t* labels, size_t B, const double** oh_dev,
+                  const int64_t** lb_dev) {
+    *oh_dev = nullptr; *lb_dev = nullptr;
+    if ((onehot == nullptr) == (labels == nullptr))
+        return fail(RCN_ERR_INVALID, "exactly one of onehot / labels must be given");
+    StagedIn in;
+    if (onehot) {
+        RCN_TRY(in.stage(onehot, h->classes * B * sizeof(double), h->tgt_stage, h->stream, nullptr));
+        *oh_dev = (const double*)in.dev;
+    } else {
+        RCN_TRY(in.stage(labels, B * sizeof(int64_t), h->tgt_stage, h->stream, nullptr));
+        *lb_dev = (const int64_t*)in.dev;
+    }
+    return RCN_OK;
+}
+
+int check_feature_width(rcn_cuda_model* h, size_t L) {
+    if (h->cols[0] != L)  // nalgebra `w * a` dimension mismatch (reference panics; see rcn.rs:443 quirk)
+        return fail(RCN_ERR_SHAPE, "Matrix multiplication dimensions mismatch: first layer expects %zu inputs, feature vector has %zu",
+                    h->cols[0], L);
+    return RCN_OK;
+}
+
+thread_local DevBuf tl_op_in, tl_op_k, tl_op_out, tl_op_aux;
+
+}  // namespace
+
+extern "C" {
+
+const char* rcn_cuda_last_error(void) { return last_error_ref().c_str(); }
+int rcn_cuda_version(void) { return 100; }
+
+int rcn_cuda_device_count(int* count) {
+    if (!count) return fail(RCN_ERR_INVALID, "null count");
+    RCN_CUDA_TRY(cudaGetDeviceCount(count));
+    return RCN_OK;
+}
+
+int rcn_cuda_create(size_t classes, const int32_t* convpool_cfg, size_t n_convpool, const size_t* feedforward_cfg,
+                    size_t n_feedforward, int device, rcn_cuda_handle* out) {
+    if (!out) return fail(RCN_ERR_INVALID, "null out handle");
+    *out = nullptr;
+    if (n_convpool && !convpool_cfg) return fail(RCN_ERR_INVALID, "null convpool_cfg");
+    if (n_feedforward && !feedforward_cfg) return fail(RCN_ERR_INVALID, "null feedforward_cfg");
+    for (size_t i = 0; i < n_convpool; ++i)
+        if (convpool_cfg[i] < 0 || convpool_cfg[i] > 3) return fail(RCN_ERR_INVALID, "unknown RCNLayer code %d", convpool_cfg[i]);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(RCN_ERR_CUDA, "no CUDA device available (%s); librcn_cuda has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= ndev) return fail(RCN_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    RCN_CUDA_TRY(cudaSetDevice(device));
+    std::unique_ptr<rcn_cuda_model> m(new (std::nothrow) rcn_cuda_model());
+    if (!m) return fail(RCN_ERR_INVALID, "out of host memory");
+    m->device = device;
+    m->classes = classes;
+    m->cfg.assign(convpool_cfg, convpool_cfg + n_convpool);
+    m->ff.assign(feedforward_cfg, feedforward_cfg + n_feedforward);
+    RCN_CUDA_TRY(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+    m->stream = m->own_stream;
+    *out = m.release();
+    return RCN_OK;
+}
+
+int rcn_cuda_destroy(rcn_cuda_handle h) {
+    if (!h) return RCN_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
+    DevBuf* bufs[] = {&h->params, &h->grads_own, &h->in_stage, &h->tgt_stage, &h->feats, &h->acts, &h->deltas,
+                      &h->gemm_ws, &h->out_stage, &h->small, &h->red_ws, &h->fscratch.a, &h->fscratch.b};
+    for (DevBuf* b : bufs) b->release();
+    delete h;
+    return RCN_OK;
+}
+
+int rcn_cuda_set_stream(rcn_cuda_handle h, void* cuda_stream) {
+    RCN_ENTER(h);
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return RCN_OK;
+}
+
+int rcn_cuda_synchronize(rcn_cuda_handle h) {
+    RCN_ENTER(h);
+    RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return RCN_OK;
+}
+
+int rcn_cuda_feature_shape(rcn_cuda_handle h, size_t H, size_t W, size_t* n_maps, size_t* map_h, size_t* map_w) {
+    RCN_ENTER(h);
+    RCN_TRY(ensure_plan(h, H, W));
+    if (n_maps) *n_maps = h->plan.n_maps;
+    if (map_h) *map_h = h->plan.map_h;
+    if (map_w) *map_w = h->plan.map_w;
+    return RCN_OK;
+}
+
+int rcn_cuda_init_params(rcn_cuda_handle h, size_t l) {
+    RCN_ENTER(h);
+    // load_weights_and_bias (rcn.rs:425-457)
+    if (h->ff.empty()) return fail(RCN_ERR_OUT_OF_BOUNDS, "index out of bounds: feedforward_cfg is empty (rcn.rs:444)");
+    unsigned c = 0, p = 0;
+    for (int32_t layer : h->cfg) {
+        if (layer == RCN_LAYER_CONV_NONE || layer == RCN_LAYER_CONV_SAME) c += 1; else p += 2;
+    }
+    if (c > 20 || p > 60) return fail(RCN_ERR_INVALID, "convpool stack too deep");
+    size_t pc = 1, pp = 1;
+    for (unsigned i = 0; i < c; ++i) pc *= 4;
+    for (unsigned i = 0; i < p; ++i) pp *= 2;
+    size_t a = pc / pp * l;  // 4^c / 2^p * l, integer division first (rcn.rs:443)
+    size_t b = h->ff[0];
+    const size_t n = h->ff.size() + 1;
+    h->rows.clear(); h->cols.clear(); h->w_off.clear(); h->b_off.clear();
+    size_t off = 0, sum_rows = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (b == 0) return fail(RCN_ERR_INVALID, "layer %zu has zero neurons", i);
+        h->rows.push_back(b); h->cols.push_back(a);  // dims = (output_size, input_size)  (rcn.rs:502)
+        h->w_off.push_back(off); off += a * b;
+        h->b_off.push_back(off); off += b;
+        sum_rows += b;
+        a = b;
+        b = (i + 1 < h->ff.size()) ? h->ff[i + 1] : h->classes;
+    }
+    h->n_params = off; h->sum_rows = sum_rows;
+    RCN_TRY(h->params.reserve(off * sizeof(double)));
+    RCN_CUDA_TRY(cudaMemsetAsync(h->params.p, 0, off * sizeof(double), h->stream));
+    if (!h->grads_bound) {
+        RCN_TRY(h->grads_own.reserve(off * sizeof(double)));
+        h->grads = h->grads_own.as<double>();
+        RCN_CUDA_TRY(cudaMemsetAsync(h->grads, 0, off * sizeof(double), h->stream));
+    }
+    h->params_ready = true;
+    h->stats_valid = false;
+    return RCN_OK;
+}
+
+int rcn_cuda_num_layers(rcn_cuda_handle h, size_t* n_layers) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (n_layers) *n_layers = h->rows.size();
+    return RCN_OK;
+}
+
+int rcn_cuda_layer_shape(rcn_cuda_handle h, size_t layer, size_t* rows, size_t* cols) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (layer >= h->rows.size()) return fail(RCN_ERR_INVALID, "layer %zu out of range", layer);
+    if (rows) *rows = h->rows[layer];
+    if (cols) *cols = h->cols[layer];
+    return RCN_OK;
+}
+
+int rcn_cuda_param_count(rcn_cuda_handle h, size_t* n) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (n) *n = h->n_params;
+    return RCN_OK;
+}
+
+static int copy_in(rcn_cuda_handle h, double* dst_dev, const double* src, size_t n) {
+    if (!src) return fail(RCN_ERR_INVALID, "null source");
+    if (n == 0) return RCN_OK;
+    const bool dev = is_device_ptr(src);
+    RCN_CUDA_TRY(cudaMemcpyAsync(dst_dev, src, n * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    if (!dev) RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));  // pageable source may be reused by the caller
+    return RCN_OK;
+}
+
+int rcn_cuda_set_weights(rcn_cuda_handle h, size_t layer, size_t rows, size_t cols, const double* w) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (layer >= h->rows.size()) return fail(RCN_ERR_INVALID, "layer %zu out of range", layer);
+    if (rows != h->rows[layer] || cols != h->cols[layer])
+        return fail(RCN_ERR_SHAPE, "weights for layer %zu must be %zu x %zu, got %zu x %zu", layer, h->rows[layer], h->cols[layer], rows, cols);
+    return copy_in(h, h->params.as<double>() + h->w_off[layer], w, rows * cols);
+}
+
+int rcn_cuda_get_weights(rcn_cuda_handle h, size_t layer, double* w) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (layer >= h->rows.size() || !w) return fail(RCN_ERR_INVALID, "bad layer / null destination");
+    return deliver(h, w, h->params.as<double>() + h->w_off[layer], h->rows[layer] * h->cols[layer] * sizeof(double));
+}
+
+int rcn_cuda_set_bias(rcn_cuda_handle h, size_t layer, size_t n, const double* b) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (layer >= h->rows.size()) return fail(RCN_ERR_INVALID, "layer %zu out of range", layer);
+    if (n != h->rows[layer]) return fail(RCN_ERR_SHAPE, "bias for layer %zu must have %zu entries, got %zu", layer, h->rows[layer], n);
+    return copy_in(h, h->params.as<double>() + h->b_off[layer], b, n);
+}
+
+int rcn_cuda_get_bias(rcn_cuda_handle h, size_t layer, double* b) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (layer >= h->rows.size() || !b) return fail(RCN_ERR_INVALID, "bad layer / null destination");
+    return deliver(h, b, h->params.as<double>() + h->b_off[layer], h->rows[layer] * sizeof(double));
+}
+
+int rcn_cuda_set_params(rcn_cuda_handle h, const double* flat, size_t n) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (n != h->n_params) return fail(RCN_ERR_SHAPE, "model has %zu parameters, got %zu", h->n_params, n);
+    return copy_in(h, h->params.as<double>(), flat, n);
+}
+
+int rcn_cuda_get_params(rcn_cuda_handle h, double* flat, size_t n) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (n != h->n_params || !flat) return fail(RCN_ERR_SHAPE, "model has %zu parameters, got %zu", h->n_params, n);
+    return deliver(h, flat, h->params.p, n * sizeof(double));
+}
+
+int rcn_cuda_set_scale(rcn_cuda_handle h, double mean, double sd) {
+    RCN_ENTER(h);
+    h->mean = mean; h->sd = sd;
+    return RCN_OK;
+}
+
+int rcn_cuda_get_scale(rcn_cuda_handle h, double* mean, double* sd) {
+    RCN_ENTER(h);
+    if (mean) *mean = h->mean;
+    if (sd) *sd = h->sd;
+    return RCN_OK;
+}
+
+int rcn_cuda_features(rcn_cuda_handle h, const void* images, int pixel_format, size_t B, size_t H, size_t W,
+                      int standardise, double* out) {
+    RCN_ENTER(h);
+    RCN_TRY(ensure_plan(h, H, W));
+    const size_t bytes = h->plan.L * B * sizeof(double);
+    if (bytes == 0) return RCN_OK;
+    if (!out) return fail(RCN_ERR_INVALID, "null output");
+    double* out_dev = out;
+    const bool out_is_dev = is_device_ptr(out);
+    if (!out_is_dev) { RCN_TRY(h->feats.reserve(bytes)); out_dev = h->feats.as<double>(); }
+    RCN_TRY(features_into(h, images, pixel_format, B, H, W, standardise != 0, out_dev));
+    if (!out_is_dev) RCN_TRY(deliver(h, out, out_dev, bytes));
+    return RCN_OK;
+}
+
+int rcn_cuda_gen_scales(rcn_cuda_handle h, const double* feats, size_t L, size_t B, double* mean, double* sd) {
+    RCN_ENTER(h);
+    if (!feats || L * B == 0) return fail(RCN_ERR_INVALID, "gen_scales needs a non-empty set");
+    StagedIn in;
+    RCN_TRY(in.stage(feats, L * B * sizeof(double), h->in_stage, h->stream, nullptr));
+    RCN_TRY(h->small.reserve(64));
+    double* res = h->small.as<double>() + 4;
+    RCN_TRY(launch_gen_scales((const double*)in.dev, L * B, res, h->red_ws, h->stream));
+    double host[2];
+    RCN_CUDA_TRY(cudaMemcpyAsync(host, res, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+    RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->mean = host[0]; h->sd = host[1];  // self.scale_set = (mean, sd)  (rcn.rs:249-250)
+    if (mean) *mean = host[0];
+    if (sd) *sd = host[1];
+    return RCN_OK;
+}
+
+int rcn_cuda_standardise(rcn_cuda_handle h, double* feats, size_t n) {
+    RCN_ENTER(h);
+    if (n == 0) return RCN_OK;
+    if (!feats) return fail(RCN_ERR_INVALID, "null feats");
+    if (is_device_ptr(feats)) return launch_standardise(feats, n, h->mean, h->sd, h->stream);
+    RCN_TRY(h->in_stage.reserve(n * sizeof(double)));
+    RCN_CUDA_TRY(cudaMemcpyAsync(h->in_stage.p, feats, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    RCN_TRY(launch_standardise(h->in_stage.as<double>(), n, h->mean, h->sd, h->stream));
+    return deliver(h, feats, h->in_stage.p, n * sizeof(double));
+}
+
+int rcn_cuda_forward(rcn_cuda_handle h, const double* feats, size_t B, double* out_acts) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (B == 0) return RCN_OK;
+    if (!feats || !out_acts) return fail(RCN_ERR_INVALID, "null feats / output");
+    StagedIn in;
+    RCN_TRY(in.stage(feats, h->cols[0] * B * sizeof(double), h->in_stage, h->stream, nullptr));
+    RCN_TRY(forward_dev(h, (const double*)in.dev, B, nullptr, nullptr, false));
+    const size_t n = h->rows.size();
+    return deliver(h, out_acts, h->act(n - 1, B), h->rows[n - 1] * B * sizeof(double));
+}
+
+static int classify_dev_feats(rcn_cuda_handle h, const double* feats_dev, size_t B, int64_t* labels_out) {
+    RCN_TRY(forward_dev(h, feats_dev, B, nullptr, nullptr, false));
+    const size_t n = h->rows.size();
+    int64_t* lab_dev = labels_out;
+    const bool out_dev = is_device_ptr(labels_out);
+    if (!out_dev) { RCN_TRY(h->out_stage.reserve(B * sizeof(int64_t))); lab_dev = h->out_stage.as<int64_t>(); }
+    RCN_TRY(launch_argmax_last(h->act(n - 1, B), h->rows[n - 1], B, lab_dev, h->stream));
+    if (!out_dev) RCN_TRY(deliver(h, labels_out, lab_dev, B * sizeof(int64_t)));
+    return RCN_OK;
+}
+
+int rcn_cuda_classify_features(rcn_cuda_handle h, const double* feats, size_t B, int64_t* labels_out) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (B == 0) return RCN_OK;
+    if (!feats || !labels_out) return fail(RCN_ERR_INVALID, "null feats / output");
+    StagedIn in;
+    RCN_TRY(in.stage(feats, h->cols[0] * B * sizeof(double), h->in_stage, h->stream, nullptr));
+    return classify_dev_feats(h, (const double*)in.dev, B, labels_out);
+}
+
+int rcn_cuda_classify(rcn_cuda_handle h, const void* images, int pixel_format, size_t B, size_t H, size_t W,
+                      int64_t* labels_out) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (B == 0) return RCN_OK;
+    if (!labels_out) return fail(RCN_ERR_INVALID, "null output");
+    RCN_TRY(ensure_plan(h, H, W));
+    RCN_TRY(check_feature_width(h, h->plan.L));
+    RCN_TRY(h->feats.reserve(h->plan.L * B * sizeof(double)));
+    RCN_TRY(features_into(h, images, pixel_format, B, H, W, true, h->feats.as<double>()));  // rcn.rs:84-89
+    return classify_dev_feats(h, h->feats.as<double>(), B, labels_out);
+}
+
+int rcn_cuda_evaluate(rcn_cuda_handle h, const double* feats, const int64_t* labels, size_t B, uint64_t* accept) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (!accept) return fail(RCN_ERR_INVALID, "null accept");
+    *accept = 0;
+    if (B == 0) return RCN_OK;
+    if (!feats || !labels) return fail(RCN_ERR_INVALID, "null feats / labels");
+    StagedIn in, lb;
+    RCN_TRY(in.stage(feats, h->cols[0] * B * sizeof(double), h->in_stage, h->stream, nullptr));
+    RCN_TRY(lb.stage(labels, B * sizeof(int64_t), h->tgt_stage, h->stream, nullptr));
+    RCN_TRY(forward_dev(h, (const double*)in.dev, B, nullptr, nullptr, false));
+    const size_t n = h->rows.size();
+    RCN_TRY(h->small.reserve(64));
+    double* st = h->small.as<double>() + 2;
+    RCN_TRY(launch_batch_stats(h->act(n - 1, B), h->rows[n - 1], B, nullptr, (const int64_t*)lb.dev, st, h->stream));
+    uint64_t host[2];
+    RCN_CUDA_TRY(cudaMemcpyAsync(host, st, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+    RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *accept = host[1];
+    return RCN_OK;
+}
+
+int rcn_cuda_accumulate_gradients(rcn_cuda_handle h, const double* feats, const double* onehot, const int64_t* labels,
+                                  size_t B) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    const double* oh = nullptr; const int64_t* lb = nullptr;
+    const double* f_dev = nullptr;
+    bool host_in = false;
+    if (B) {
+        if (!feats) return fail(RCN_ERR_INVALID, "null feats");
+        RCN_TRY(stage_targets(h, onehot, labels, B, &oh, &lb));
+        StagedIn in;
+        RCN_TRY(in.stage(feats, h->cols[0] * B * sizeof(double), h->in_stage, h->stream, &host_in));
+        f_dev = (const double*)in.dev;
+    }
+    RCN_TRY(accumulate_dev(h, f_dev, oh, lb, B));
+    if (host_in || (onehot && !is_device_ptr(onehot)) || (labels && !is_device_ptr(labels)))
+        RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));  // caller may reuse host buffers
+    return RCN_OK;
+}
+
+int rcn_cuda_accumulate_gradients_images(rcn_cuda_handle h, const void* images, int pixel_format, const int64_t* labels,
+                                         size_t B, size_t H, size_t W) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    RCN_TRY(ensure_plan(h, H, W));
+    RCN_TRY(check_feature_width(h, h->plan.L));
+    const double* oh = nullptr; const int64_t* lb = nullptr;
+    if (B) {
+        if (!labels) return fail(RCN_ERR_INVALID, "null labels");
+        RCN_TRY(stage_targets(h, nullptr, labels, B, &oh, &lb));
+        RCN_TRY(h->feats.reserve(h->plan.L * B * sizeof(double)));
+        RCN_TRY(features_into(h, images, pixel_format, B, H, W, true, h->feats.as<double>()));
+    }
+    RCN_TRY(accumulate_dev(h, h->feats.as<double>(), oh, lb, B));
+    if (B && (!is_device_ptr(images) || !is_device_ptr(labels))) RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return RCN_OK;
+}
+
+int rcn_cuda_apply_gradients(rcn_cuda_handle h, double eta, size_t batch) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (batch == 0) return RCN_OK;  // chunks_exact never yields an empty batch (rcn.rs:147)
+    const double scale = eta / (double)batch;  // (eta / batch.len() as f64)  (rcn.rs:214)
+    return launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale, h->stream);
+}
+
+int rcn_cuda_train_batch(rcn_cuda_handle h, const double* feats, const double* onehot, const int64_t* labels, size_t B,
+                         double eta) {
+    RCN_TRY(rcn_cuda_accumulate_gradients(h, feats, onehot, labels, B));
+    return rcn_cuda_apply_gradients(h, eta, B);
+}
+
+int rcn_cuda_train_batch_images(rcn_cuda_handle h, const void* images, int pixel_format, const int64_t* labels, size_t B,
+                                size_t H, size_t W, double eta) {
+    RCN_TRY(rcn_cuda_accumulate_gradients_images(h, images, pixel_format, labels, B, H, W));
+    return rcn_cuda_apply_gradients(h, eta, B);
+}
+
+int rcn_cuda_last_batch_stats(rcn_cuda_handle h, double* cost, uint64_t* hits) {
+    RCN_ENTER(h);
+    if (!h->stats_valid) return fail(RCN_ERR_STATE, "no batch has been accumulated yet");
+    double host[2];
+    RCN_CUDA_TRY(cudaMemcpyAsync(host, h->small.p, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+    RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (cost) *cost = host[0];
+    if (hits) memcpy(hits, &host[1], sizeof(uint64_t));
+    return RCN_OK;
+}
+
+int rcn_cuda_bind_gradient_buffer(rcn_cuda_handle h, double* device_ptr, size_t n) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (!device_ptr) {
+        RCN_TRY(h->grads_own.reserve(h->n_params * sizeof(double)));
+        h->grads = h->grads_own.as<double>();
+        h->grads_bound = false;
+        return RCN_OK;
+    }
+    if (n != h->n_params) return fail(RCN_ERR_SHAPE, "gradient buffer must hold %zu doubles, got %zu", h->n_params, n);
+    if (!is_device_ptr(device_ptr)) return fail(RCN_ERR_INVALID, "gradient buffer must be device memory");
+    h->grads = device_ptr;
+    h->grads_bound = true;
+    return RCN_OK;
+}
+
+int rcn_cuda_gradient_buffer(rcn_cuda_handle h, double** device_ptr, size_t* n) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (device_ptr) *device_ptr = h->grads;
+    if (n) *n = h->n_params;
+    return RCN_OK;
+}
+
+int rcn_cuda_get_gradients(rcn_cuda_handle h, double* flat, size_t n) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (n != h->n_params || !flat) return fail(RCN_ERR_SHAPE, "model has %zu parameters, got %zu", h->n_params, n);
+    return deliver(h, flat, h->grads, n * sizeof(double));
+}
+
+int rcn_cuda_get_activations(rcn_cuda_handle h, size_t layer, double* out) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (layer >= h->rows.size() || !out) return fail(RCN_ERR_INVALID, "bad layer / null destination");
+    if (!h->last_B) return fail(RCN_ERR_STATE, "no batch has been accumulated yet");
+    return deliver(h, out, h->act(layer, h->last_B), h->rows[layer] * h->last_B * sizeof(double));
+}
+
+int rcn_cuda_get_deltas(rcn_cuda_handle h, size_t layer, double* out) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (layer >= h->rows.size() || !out) return fail(RCN_ERR_INVALID, "bad layer / null destination");
+    if (!h->last_B) return fail(RCN_ERR_STATE, "no batch has been accumulated yet");
+    return deliver(h, out, h->delta(layer, h->last_B), h->rows[layer] * h->last_B * sizeof(double));
+}
+
+// ---- op-level API ---------------------------------------------------------------------------------
+namespace {
+struct OpCtx {
+    cudaStream_t stream = nullptr;
+    int enter(int device, void* cuda_stream) {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) {
+            cudaGetLastError();
+            return fail(RCN_ERR_CUDA, "no CUDA device available; librcn_cuda has no CPU fallback");
+        }
+        if (device < 0 || device >= ndev) return fail(RCN_ERR_INVALID, "device %d out of range", device);
+        RCN_CUDA_TRY(cudaSetDevice(device));
+        stream = (cudaStream_t)cuda_stream;  // NULL = legacy default stream
+        return RCN_OK;
+    }
+    int in(const void* src, size_t bytes, DevBuf& buf, const void** dev) {
+        if (is_device_ptr(src)) { *dev = src; return RCN_OK; }
+        RCN_TRY(buf.reserve(bytes));
+        RCN_CUDA_TRY(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, stream));
+        *dev = buf.p;
+        return RCN_OK;
+    }
+    int out(void* dst, size_t bytes, DevBuf& buf, void** dev, bool* host) {
+        if (is_device_ptr(dst)) { *dev = dst; *host = false; return RCN_OK; }
+        RCN_TRY(buf.reserve(bytes));
+        *dev = buf.p; *host = true;
+        return RCN_OK;
+    }
+    int finish(void* dst, const void* dev, size_t bytes, bool host) {
+        if (host) {
+            RCN_CUDA_TRY(cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, stream));
+            RCN_CUDA_TRY(cudaStreamSynchronize(stream));
+        }
+        return RCN_OK;
+    }
+};
+}  // namespace
+
+int rcn_cuda_convolve_2d(int device, void* cuda_stream, const double* m, size_t H, size_t W, const double* kernel,
+                         size_t kh, size_t kw, int padding, double* out) {
+    if (!m || !kernel || !out) return fail(RCN_ERR_INVALID, "null pointer");
+    if (padding != RCN_PADDING_NONE && padding != RCN_PADDING_SAME) return fail(RCN_ERR_INVALID, "unknown padding %d", padding);
+    // kernel.rs:123-128
+    if ((kh == 0 && kw == 0) || kh > H || kw > W || kh == 0 || kw == 0)
+        return fail(RCN_ERR_SHAPE, "convolve_2d expects 'self.shape() >= kernel_shape() > 0', received (%zu, %zu) and (%zu, %zu) respectively.", H, W, kh, kw);
+    // kernel.rs:131-135
+    if ((kh % 2 == 0 || kw % 2 == 0) && padding == RCN_PADDING_SAME)
+        return fail(RCN_ERR_SHAPE, "convolve_2d expects kernel dimensions to be odd when padding mode set to 'SAME', got (%zu, %zu)", kh, kw);
+    // kernel.rs:154-158: the padded copy indexes self[(cy-1, cx-1)] up to cy = H + kh/2 - 1 => out of bounds for kh/2 >= 2
+    if (padding == RCN_PADDING_SAME && (kh / 2 >= 2 || kw / 2 >= 2))
+        return fail(RCN_ERR_OUT_OF_BOUNDS, "Matrix index out of bounds. (SAME padding with a (%zu, %zu) kernel, kernel.rs:156)", kh, kw);
+    if (H > 32768 || W > 32768) return fail(RCN_ERR_INVALID, "matrix too large");
+    OpCtx c;
+    RCN_TRY(c.enter(device, cuda_stream));
+    const bool same = padding == RCN_PADDING_SAME;
+    const size_t on = same ? H * W : (H - kh + 1) * (W - kw + 1);
+    const void *m_dev = nullptr, *k_dev = nullptr; void* o_dev = nullptr; bool host = false;
+    RCN_TRY(c.in(m, H * W * 8, tl_op_in, &m_dev));
+    RCN_TRY(c.in(kernel, kh * kw * 8, tl_op_k, &k_dev));
+    RCN_TRY(c.out(out, on * 8, tl_op_out, &o_dev, &host));
+    RCN_TRY(launch_convolve_2d((const double*)m_dev, H, W, (const double*)k_dev, kh, kw, padding, (double*)o_dev, c.stream));
+    return c.finish(out, o_dev, on * 8, host);
+}
+
+int rcn_cuda_convolve_2d_separated(int device, void* cuda_stream, const double* m, size_t H, size_t W, int op, int padding,
+                                   double* out) {
+    if (!m || !out) return fail(RCN_ERR_INVALID, "null pointer");
+    if (padding != RCN_PADDING_NONE && padding != RCN_PADDING_SAME) return fail(RCN_ERR_INVALID, "unknown padding %d", padding);
+    if (op < 0 || op > 3) return fail(RCN_ERR_INVALID, "unknown SeparableOperator %d", op);
+    if (H < 3 || W < 3)  // kernel.rs:199-201
+        return fail(RCN_ERR_SHAPE, "convolve_2d_separated expects 'self.shape() >= kernel_shape() > 0', received (%zu, %zu) and (3, 3) respectively.", H, W);
+    if (H > 32768 || W > 32768) return fail(RCN_ERR_INVALID, "matrix too large");
+    OpCtx c;
+    RCN_TRY(c.enter(device, cuda_stream));
+    const bool same = padding == RCN_PADDING_SAME;
+    const size_t on = same ? H * W : (H - 2) * (W - 2);
+    const void* m_dev = nullptr; void* o_dev = nullptr; bool host = false;
+    RCN_TRY(c.in(m, H * W * 8, tl_op_in, &m_dev));
+    RCN_TRY(c.out(out, on * 8, tl_op_out, &o_dev, &host));
+    RCN_TRY(launch_convolve_2d_separated((const double*)m_dev, H, W, op, padding, (double*)o_dev, c.stream));
+    return c.finish(out, o_dev, on * 8, host);
+}
+
+int rcn_cuda_relu(int device, void* cuda_stream, const double* m, size_t n, double* out) {
+    if (n == 0) return RCN_OK;
+    if (!m || !out) return fail(RCN_ERR_INVALID, "null pointer");
+    OpCtx c;
+    RCN_TRY(c.enter(device, cuda_stream));
+    const void* m_dev = nullptr; void* o_dev = nullptr; bool host = false;
+    RCN_TRY(c.in(m, n * 8, tl_op_in, &m_dev));
+    RCN_TRY(c.out(out, n * 8, tl_op_out, &o_dev, &host));
+    RCN_TRY(launch_relu((const double*)m_dev, n, (double*)o_dev, c.stream));
+    return c.finish(out, o_dev, n * 8, host);
+}
+
+int rcn_cuda_pool_2d(int device, void* cuda_stream, const double* m, size_t H, size_t W, int padding, int pooling,
+                     double* out, uint8_t* argmax_out) {
+    if (!m || !out) return fail(RCN_ERR_INVALID, "null pointer");
+    if (padding != RCN_PADDING_NONE && padding != RCN_PADDING_SAME) return fail(RCN_ERR_INVALID, "unknown padding %d", padding);
+    if (pooling != RCN_POOLING_AVERAGE && pooling != RCN_POOLING_MAX) return fail(RCN_ERR_INVALID, "unknown pooling %d", pooling);
+    if (H < 2 || W < 2)  // kernel.rs:246-251
+        return fail(RCN_ERR_SHAPE, "stride_2d expected a matrix with dimensions greater than (2, 2), got (%zu, %zu)", H, W);
+    if (pooling != RCN_POOLING_MAX) return fail(RCN_ERR_NOT_IMPLEMENTED, "Not implemented");  // kernel.rs:283-285
+    if (H > 32768 || W > 32768) return fail(RCN_ERR_INVALID, "matrix too large");
+    OpCtx c;
+    RCN_TRY(c.enter(device, cuda_stream));
+    const bool same = padding == RCN_PADDING_SAME;
+    const size_t oh = same ? (H + 1) / 2 : H / 2, ow = same ? (W + 1) / 2 : W / 2;
+    const size_t on = oh * ow;
+    const void* m_dev = nullptr; void* o_dev = nullptr; bool host = false;
+    RCN_TRY(c.in(m, H * W * 8, tl_op_in, &m_dev));
+    RCN_TRY(c.out(out, on * 8, tl_op_out, &o_dev, &host));
+    // aux: [int nan_flag | pad to 16 | argmax bytes]
+    RCN_TRY(tl_op_aux.reserve(16 + on));
+    int* flag = tl_op_aux.as<int>();
+    RCN_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), c.stream));
+    uint8_t* am_dev = nullptr;
+    bool am_host = false;
+    if (argmax_out) {
+        if (is_device_ptr(argmax_out)) am_dev = argmax_out;
+        else { am_dev = tl_op_aux.as<uint8_t>() + 16; am_host = true; }
+    }
+    RCN_TRY(launch_pool_2d((const double*)m_dev, H, W, padding, (double*)o_dev, am_dev, flag, c.stream));
+    int nan = 0;
+    RCN_CUDA_TRY(cudaMemcpyAsync(&nan, flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    if (am_host) RCN_CUDA_TRY(cudaMemcpyAsync(argmax_out, am_dev, on, cudaMemcpyDeviceToHost, c.stream));
+    if (host) RCN_CUDA_TRY(cudaMemcpyAsync(out, o_dev, on * 8, cudaMemcpyDeviceToHost, c.stream));
+    RCN_CUDA_TRY(cudaStreamSynchronize(c.stream));
+    if (nan) return fail(RCN_ERR_NAN, "called `Option::unwrap()` on a `None` value (partial_cmp on NaN, kernel.rs:280)");
+    return RCN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,422 @@
+"""Host-side mirror of rcn's model layer (rcn/src/rcn.rs): ``RCN``, ``RCNLayer``, ``Weights`` / ``Bias`` access,
+``train`` / ``classify`` -- same names, argument meaning and error behaviour -- driving librcn_cuda.so.
+
+Batches are numpy arrays (staged through the device) or torch CUDA tensors (used in place, on torch's current
+stream):  images ``(B, H, W)`` uint8 (the `image` crate's row-major Luma8 buffer) or float64 ``(B, H, W)`` indexed
+(row, col); features ``(B, L)`` float64; labels ``(B,)`` int64; one-hot targets ``(B, classes)`` float64.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _lib
+from .kernel import Padding, Pooling, _is_torch
+
+
+@dataclass(frozen=True)
+class RCNLayer:
+    """``enum RCNLayer { Convolve2D(Padding), Pool2D(Pooling) }`` (rcn.rs:35-38)."""
+    kind: str
+    arg: int
+
+    @staticmethod
+    def Convolve2D(padding: Padding) -> "RCNLayer":
+        return RCNLayer("Convolve2D", int(Padding(padding)))
+
+    @staticmethod
+    def Pool2D(pooling: Pooling) -> "RCNLayer":
+        return RCNLayer("Pool2D", int(Pooling(pooling)))
+
+    @property
+    def code(self) -> int:
+        """RCN_LAYER_* code of include/rcn_cuda.h."""
+        return self.arg if self.kind == "Convolve2D" else 2 + self.arg
+
+
+def _layer_code(layer) -> int:
+    return layer.code if isinstance(layer, RCNLayer) else int(layer)
+
+
+class _Buf:
+    """Pointer + keep-alive for a host (numpy) or device (torch) buffer."""
+
+    def __init__(self, x, dtype, shape_tail=None):
+        if _is_torch(x):
+            import torch
+            tdt = {np.float64: torch.float64, np.uint8: torch.uint8, np.int64: torch.int64}[dtype]
+            if not x.is_cuda:
+                raise ValueError("torch tensors must live on a CUDA device (pass numpy arrays for host data)")
+            self.store = x.to(tdt).contiguous()
+            self.ptr = self.store.data_ptr()
+            self.shape = tuple(self.store.shape)
+            self.torch = True
+            self.device = x.device
+        else:
+            self.store = np.ascontiguousarray(x, dtype=dtype)
+            self.ptr = self.store.ctypes.data
+            self.shape = self.store.shape
+            self.torch = False
+            self.device = None
+
+
+class RCN:
+    """Rust Convolutional Neural Network on a B200 (rcn.rs:15-25).
+
+    ``training_path`` / ``testing_path`` are kept for API parity with ``RCN::new`` (rcn.rs:58-64); the array entry
+    points below take data directly.
+    """
+
+    def __init__(self, classes: int, convpool_cfg: Sequence, feedforward_cfg: Sequence[int],
+                 training_path: str = "", testing_path: str = "", device: int = 0):
+        self._lib = _lib.load()
+        self.classes = int(classes)
+        self.convpool_cfg = list(convpool_cfg)
+        self.feedforward_cfg = [int(x) for x in feedforward_cfg]
+        self.training_path = training_path
+        self.testing_path = testing_path
+        self.device = int(device)
+        codes = [_layer_code(l) for l in self.convpool_cfg]
+        cfg = (C.c_int32 * max(1, len(codes)))(*codes)
+        ff = (C.c_size_t * max(1, len(self.feedforward_cfg)))(*self.feedforward_cfg)
+        h = C.c_void_p()
+        _lib.check(self._lib.rcn_cuda_create(self.classes, cfg, len(codes), ff, len(self.feedforward_cfg), self.device,
+                                             C.byref(h)))
+        self._h = h
+        self._shapes: List[Tuple[int, int]] = []
+
+    # -- lifetime ---------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rcn_cuda_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: Optional[int]):
+        """Run on an existing cudaStream_t (int handle, e.g. ``torch.cuda.current_stream().cuda_stream``)."""
+        _lib.check(self._lib.rcn_cuda_set_stream(self._h, cuda_stream))
+
+    def synchronize(self):
+        _lib.check(self._lib.rcn_cuda_synchronize(self._h))
+
+    def _use_torch_stream(self, *bufs):
+        for b in bufs:
+            if b is not None and b.torch:
+                import torch
+                self.set_stream(torch.cuda.current_stream(b.device).cuda_stream)
+                return
+
+    # -- shapes / parameters ----------------------------------------------------------------------------------
+    def feature_shape(self, H: int, W: int) -> Tuple[int, int, int]:
+        """(n_maps, map_h, map_w) of flatten_feature_set (rcn.rs:317-356) for an H x W image."""
+        n, h, w = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        _lib.check(self._lib.rcn_cuda_feature_shape(self._h, H, W, C.byref(n), C.byref(h), C.byref(w)))
+        return n.value, h.value, w.value
+
+    def feature_len(self, H: int, W: int) -> int:
+        n, h, w = self.feature_shape(H, W)
+        return n * h * w
+
+    def load_weights_and_bias(self, l: int):
+        """rcn.rs:425-457: allocate the reference's layer shapes for feature length ``l`` (zero-filled; inject
+        values with set_weights / set_bias / set_params)."""
+        _lib.check(self._lib.rcn_cuda_init_params(self._h, int(l)))
+        n = C.c_size_t()
+        _lib.check(self._lib.rcn_cuda_num_layers(self._h, C.byref(n)))
+        self._shapes = []
+        for i in range(n.value):
+            r, c = C.c_size_t(), C.c_size_t()
+            _lib.check(self._lib.rcn_cuda_layer_shape(self._h, i, C.byref(r), C.byref(c)))
+            self._shapes.append((r.value, c.value))
+
+    @property
+    def layer_shapes(self) -> List[Tuple[int, int]]:
+        return list(self._shapes)
+
+    @property
+    def n_params(self) -> int:
+        return sum(r * c + r for r, c in self._shapes)
+
+    def set_weights(self, layer: int, w):
+        """``Weights`` (rcn.rs:28): (rows, cols) matrix, stored column-major like nalgebra."""
+        w = np.asarray(w, dtype=np.float64)
+        buf = np.asfortranarray(w)
+        _lib.check(self._lib.rcn_cuda_set_weights(self._h, layer, w.shape[0], w.shape[1], buf.ctypes.data))
+
+    def get_weights(self, layer: int) -> np.ndarray:
+        r, c = self._shapes[layer]
+        buf = np.zeros((r, c), order="F")
+        _lib.check(self._lib.rcn_cuda_get_weights(self._h, layer, buf.ctypes.data))
+        return buf
+
+    def set_bias(self, layer: int, b):
+        b = np.ascontiguousarray(b, dtype=np.float64).ravel()
+        _lib.check(self._lib.rcn_cuda_set_bias(self._h, layer, b.size, b.ctypes.data))
+
+    def get_bias(self, layer: int) -> np.ndarray:
+        buf = np.zeros(self._shapes[layer][0])
+        _lib.check(self._lib.rcn_cuda_get_bias(self._h, layer, buf.ctypes.data))
+        return buf
+
+    def set_params(self, flat):
+        flat = np.ascontiguousarray(flat, dtype=np.float64).ravel()
+        _lib.check(self._lib.rcn_cuda_set_params(self._h, flat.ctypes.data, flat.size))
+
+    def get_params(self) -> np.ndarray:
+        buf = np.zeros(self.n_params)
+        _lib.check(self._lib.rcn_cuda_get_params(self._h, buf.ctypes.data, buf.size))
+        return buf
+
+    def get_gradients(self) -> np.ndarray:
+        buf = np.zeros(self.n_params)
+        _lib.check(self._lib.rcn_cuda_get_gradients(self._h, buf.ctypes.data, buf.size))
+        return buf
+
+    @property
+    def scale_set(self) -> Tuple[float, float]:
+        m, s = C.c_double(), C.c_double()
+        _lib.check(self._lib.rcn_cuda_get_scale(self._h, C.byref(m), C.byref(s)))
+        return m.value, s.value
+
+    @scale_set.setter
+    def scale_set(self, ms):
+        _lib.check(self._lib.rcn_cuda_set_scale(self._h, float(ms[0]), float(ms[1])))
+
+    # -- feature stage ----------------------------------------------------------------------------------------
+    def _images(self, images):
+        if _is_torch(images):
+            import torch
+            if images.dtype == torch.uint8:
+                b = _Buf(images, np.uint8)
+                return b, _lib.PIXELS_U8_ROWMAJOR, b.shape
+            b = _Buf(images.transpose(1, 2), np.float64)  # (B, W, H) contiguous == column-major H x W images
+            return b, _lib.PIXELS_F64_COLMAJOR, (b.shape[0], b.shape[2], b.shape[1])
+        a = np.asarray(images)
+        if a.ndim != 3:
+            raise ValueError("images must be (B, H, W)")
+        if a.dtype == np.uint8:
+            b = _Buf(a, np.uint8)
+            return b, _lib.PIXELS_U8_ROWMAJOR, a.shape
+        b = _Buf(np.ascontiguousarray(np.transpose(a, (0, 2, 1)), dtype=np.float64), np.float64)
+        return b, _lib.PIXELS_F64_COLMAJOR, a.shape
+
+    def flatten_feature_set(self, images, standardise: bool = False, out=None):
+        """rcn.rs:317-356 over a batch (optionally followed by the standardise+clamp of rcn.rs:407-412 with
+        ``scale_set``). Returns (B, L) float64 -- numpy for numpy input, a torch CUDA tensor for torch input."""
+        buf, fmt, (B, H, W) = self._images(images)
+        L = self.feature_len(H, W)
+        self._use_torch_stream(buf)
+        if buf.torch:
+            import torch
+            o = out if out is not None else torch.empty((B, L), dtype=torch.float64, device=buf.device)
+            optr = o.data_ptr()
+        else:
+            o = np.zeros((B, L))
+            optr = o.ctypes.data
+        _lib.check(self._lib.rcn_cuda_features(self._h, buf.ptr, fmt, B, H, W, 1 if standardise else 0, optr))
+        return o
+
+    def gen_scales(self, feats) -> Tuple[float, float]:
+        """rcn.rs:230-251: mean / population sd over all features of all samples; stored as ``scale_set``."""
+        f = _Buf(feats, np.float64)
+        self._use_torch_stream(f)
+        m, s = C.c_double(), C.c_double()
+        _lib.check(self._lib.rcn_cuda_gen_scales(self._h, f.ptr, f.shape[1], f.shape[0], C.byref(m), C.byref(s)))
+        return m.value, s.value
+
+    def standardise(self, feats):
+        """rcn.rs:407-412: returns max((v - mean) / sd, 0)."""
+        if _is_torch(feats):
+            f = _Buf(feats.clone(), np.float64)
+            self._use_torch_stream(f)
+            _lib.check(self._lib.rcn_cuda_standardise(self._h, f.ptr, f.store.numel()))
+            return f.store
+        o = np.array(feats, dtype=np.float64, order="C", copy=True)
+        _lib.check(self._lib.rcn_cuda_standardise(self._h, o.ctypes.data, o.size))
+        return o
+
+    # -- inference --------------------------------------------------------------------------------------------
+    def classify_test(self, feats):
+        """rcn.rs:105-116 over a batch: (B, L) features -> (B, classes) output activations."""
+        f = _Buf(feats, np.float64)
+        self._use_torch_stream(f)
+        B = f.shape[0]
+        n_out = self._shapes[-1][0]
+        if f.torch:
+            import torch
+            o = torch.empty((B, n_out), dtype=torch.float64, device=f.device)
+            optr = o.data_ptr()
+        else:
+            o = np.zeros((B, n_out))
+            optr = o.ctypes.data
+        _lib.check(self._lib.rcn_cuda_forward(self._h, f.ptr, B, optr))
+        return o
+
+    def classify_features(self, feats):
+        """argmax (last maximal element wins, rcn.rs:92-97) of classify_test."""
+        f = _Buf(feats, np.float64)
+        self._use_torch_stream(f)
+        B = f.shape[0]
+        if f.torch:
+            import torch
+            o = torch.empty((B,), dtype=torch.int64, device=f.device)
+            optr = o.data_ptr()
+        else:
+            o = np.zeros(B, dtype=np.int64)
+            optr = o.ctypes.data
+        _lib.check(self._lib.rcn_cuda_classify_features(self._h, f.ptr, B, optr))
+        return o
+
+    def classify_images(self, images):
+        """``classify`` (rcn.rs:82-98) over a batch of decoded grayscale images -> class indices."""
+        buf, fmt, (B, H, W) = self._images(images)
+        self._use_torch_stream(buf)
+        if buf.torch:
+            import torch
+            o = torch.empty((B,), dtype=torch.int64, device=buf.device)
+            optr = o.data_ptr()
+        else:
+            o = np.zeros(B, dtype=np.int64)
+            optr = o.ctypes.data
+        _lib.check(self._lib.rcn_cuda_classify(self._h, buf.ptr, fmt, B, H, W, optr))
+        return o
+
+    def classify(self, img_path: str) -> int:
+        """``RCN::classify`` (rcn.rs:82-98): open, grayscale, features, standardise, forward, argmax."""
+        from .data import load_grayscale
+        img = load_grayscale(img_path)
+        return int(self.classify_images(img[None, :, :])[0])
+
+    def evaluate(self, feats, labels) -> int:
+        """Epoch evaluation rule (rcn.rs:152-157): number of samples whose max set equals the one-hot exactly."""
+        f = _Buf(feats, np.float64)
+        l = _Buf(labels, np.int64)
+        self._use_torch_stream(f, l)
+        acc = C.c_uint64()
+        _lib.check(self._lib.rcn_cuda_evaluate(self._h, f.ptr, l.ptr, f.shape[0], C.byref(acc)))
+        return acc.value
+
+    # -- training ---------------------------------------------------------------------------------------------
+    def _targets(self, onehot, labels):
+        oh = _Buf(onehot, np.float64) if onehot is not None else None
+        lb = _Buf(labels, np.int64) if labels is not None else None
+        return oh, lb
+
+    def accumulate_gradients(self, feats, onehot=None, labels=None):
+        """Batch sum of backprop (rcn.rs:260-314, 190-205) into the flat gradient buffer; no update."""
+        f = _Buf(feats, np.float64)
+        oh, lb = self._targets(onehot, labels)
+        self._use_torch_stream(f, oh, lb)
+        self._B_hint = f.shape[0]
+        _lib.check(self._lib.rcn_cuda_accumulate_gradients(self._h, f.ptr, oh.ptr if oh else None,
+                                                           lb.ptr if lb else None, f.shape[0]))
+
+    def accumulate_gradients_images(self, images, labels):
+        buf, fmt, (B, H, W) = self._images(images)
+        lb = _Buf(labels, np.int64)
+        self._use_torch_stream(buf, lb)
+        self._B_hint = B
+        _lib.check(self._lib.rcn_cuda_accumulate_gradients_images(self._h, buf.ptr, fmt, lb.ptr, B, H, W))
+
+    def apply_gradients(self, eta: float, batch: int):
+        """W <- W - (eta / batch) * sum dW (rcn.rs:210-222)."""
+        _lib.check(self._lib.rcn_cuda_apply_gradients(self._h, float(eta), int(batch)))
+
+    def train_batch(self, feats, eta: float, onehot=None, labels=None):
+        """``train_batch`` (rcn.rs:176-223) on (B, L) standardised features."""
+        f = _Buf(feats, np.float64)
+        oh, lb = self._targets(onehot, labels)
+        self._use_torch_stream(f, oh, lb)
+        self._B_hint = f.shape[0]
+        _lib.check(self._lib.rcn_cuda_train_batch(self._h, f.ptr, oh.ptr if oh else None, lb.ptr if lb else None,
+                                                  f.shape[0], float(eta)))
+
+    def train_batch_images(self, images, labels, eta: float):
+        """Features (rcn.rs:317-356) + standardise (rcn.rs:407-412) + train_batch (rcn.rs:176-223), fused on device."""
+        buf, fmt, (B, H, W) = self._images(images)
+        lb = _Buf(labels, np.int64)
+        self._use_torch_stream(buf, lb)
+        self._B_hint = B
+        _lib.check(self._lib.rcn_cuda_train_batch_images(self._h, buf.ptr, fmt, lb.ptr, B, H, W, float(eta)))
+
+    def last_batch_stats(self) -> Tuple[float, int]:
+        """(quadratic cost, hits) of the last accumulated batch, evaluated with the pre-update parameters."""
+        c, h = C.c_double(), C.c_uint64()
+        _lib.check(self._lib.rcn_cuda_last_batch_stats(self._h, C.byref(c), C.byref(h)))
+        return c.value, h.value
+
+    def activations(self, layer: int) -> np.ndarray:
+        """a_{layer+1} of the last accumulated batch, (B, rows)."""
+        B = self._last_B()
+        buf = np.zeros((B, self._shapes[layer][0]))
+        _lib.check(self._lib.rcn_cuda_get_activations(self._h, layer, buf.ctypes.data))
+        return buf
+
+    def deltas(self, layer: int) -> np.ndarray:
+        B = self._last_B()
+        buf = np.zeros((B, self._shapes[layer][0]))
+        _lib.check(self._lib.rcn_cuda_get_deltas(self._h, layer, buf.ctypes.data))
+        return buf
+
+    def _last_B(self) -> int:
+        return getattr(self, "_B_hint", 0)
+
+    def bind_gradient_buffer(self, tensor):
+        """Use a caller-owned torch CUDA float64 tensor (n_params) as the flat gradient buffer (all-reduce target)."""
+        if tensor is None:
+            _lib.check(self._lib.rcn_cuda_bind_gradient_buffer(self._h, None, 0))
+            self._grad_keepalive = None
+            return
+        self._grad_keepalive = tensor
+        _lib.check(self._lib.rcn_cuda_bind_gradient_buffer(self._h, tensor.data_ptr(), tensor.numel()))
+
+    # -- whole-run driver (rcn.rs:126-167) --------------------------------------------------------------------
+    def train_arrays(self, train_images, train_labels, test_images, test_labels, batch_size: int, epochs: int,
+                     eta: float, seed: int = 0, log=print):
+        """``RCN::train`` (rcn.rs:126-167) on in-memory decoded images instead of PNG directories: features for
+        both sets, scale_set from each set in turn (so it ends up holding the TEST set's statistics, rcn.rs:134-137),
+        per-epoch shuffle (harness-seeded instead of thread_rng), ``chunks_exact`` batches (remainder dropped),
+        per-epoch evaluation and the reference's log line. Parameters must already be present (inject them with
+        set_params) or are drawn N(0,1) from ``seed`` like rcn.rs:500-523."""
+        rng = np.random.default_rng(seed)
+        tr = self.flatten_feature_set(np.asarray(train_images))
+        self.gen_scales(tr)
+        tr = self.standardise(tr)
+        te = self.flatten_feature_set(np.asarray(test_images))
+        self.gen_scales(te)
+        te = self.standardise(te)
+        train_labels = np.asarray(train_labels, dtype=np.int64)
+        test_labels = np.asarray(test_labels, dtype=np.int64)
+        if not self._shapes:
+            self.load_weights_and_bias(tr.shape[1])
+            self.set_params(rng.standard_normal(self.n_params))
+        history = []
+        n = tr.shape[0]
+        for e in range(epochs):
+            perm = rng.permutation(n)
+            for s in range(0, n - batch_size + 1, batch_size):  # chunks_exact (rcn.rs:147)
+                idx = perm[s:s + batch_size]
+                self.train_batch(tr[idx], eta, labels=train_labels[idx])
+            accept = self.evaluate(te, test_labels)
+            history.append(accept)
+            if log:
+                log("Epoch {}: {}/{} [{:.2f}%]".format(e, accept, te.shape[0], accept / te.shape[0] * 100.0))
+        return history
+
+    def train(self, batch_size: int, epochs: int, eta: float, training_class_size_limit: int,
+              testing_class_size_limit: int, seed: int = 0, log=print):
+        """``RCN::train`` (rcn.rs:126-133) on the PNG class-directory trees given to the constructor."""
+        from .data import load_data
+        rng = np.random.default_rng(seed)
+        tr_x, tr_y = load_data(self.training_path, training_class_size_limit, rng)
+        te_x, te_y = load_data(self.testing_path, testing_class_size_limit, rng)
+        return self.train_arrays(tr_x, tr_y, te_x, te_y, batch_size, epochs, eta, seed=seed, log=log)

@@ -1,0 +1,243 @@
+"""GPU parity tests of the dense layers / backprop / SGD step through the C ABI.
+Tolerance: 1e-9 relative (the reference computes in f64, BASELINE.json north_star); labels bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CP = [1, 3]
+
+
+@pytest.fixture(scope="module")
+def api(built_library):
+    import mercer_research_b200 as m
+    return m
+
+
+def make_model(api, sizes, classes, n_in, seed=0xC0FFEE, scale=1.0):
+    """Model with no convpool layers so the first dense layer takes n_in directly (4^0/2^0 * l)."""
+    model = api.RCN(classes, [], sizes)
+    model.load_weights_and_bias(n_in)
+    net = O.Net(model.layer_shapes)
+    params = np.random.default_rng(seed).standard_normal(net.n_params) * scale
+    model.set_params(params)
+    return model, net, params
+
+
+def test_kat_mlp_step(api):
+    """SURVEY.md Appendix B 3-2-2 MLP."""
+    model = api.RCN(2, [], [2])
+    model.load_weights_and_bias(3)
+    assert model.layer_shapes == [(2, 3), (2, 2)]
+    model.set_weights(0, [[0.1, -0.2, 0.3], [0.4, 0.5, -0.6]]); model.set_bias(0, [0.01, -0.02])
+    model.set_weights(1, [[0.7, -0.8], [-0.9, 1.0]]); model.set_bias(1, [0.03, 0.04])
+    x = np.array([[1.0, 0.5, -1.5]]); y = np.array([[0.0, 1.0]])
+    model.train_batch(x, 3.0, onehot=y)
+    assert_close(model.activations(0), [[0.3917409692534856, 0.8220063142137535]], what="a1")
+    assert_close(model.activations(1), [[0.41256147606104177, 0.6246750573701205]], what="a2")
+    assert_close(model.deltas(1), [[0.099986132119507, -0.08799723356765517]], what="d2")
+    assert_close(model.deltas(0), [[0.035548466979736765, -0.024578376854694016]], what="d1")
+    assert_close(model.get_weights(1), [[0.5824940070747917, -1.046567695808136], [-0.7965836352917443, 1.217002844877865]], what="W2'")
+    assert_close(model.get_bias(1), [-0.26995839635852104, 0.3039917007029655], what="b2'")
+    assert_close(model.get_weights(0), [[-0.006645400939210289, -0.25332270046960514, 0.45996810140881544],
+                                        [0.47373513056408206, 0.536867565282041, -0.710602695846123]], what="W1'")
+    assert_close(model.get_bias(0), [-0.0966454009392103, 0.05373513056408204], what="b1'")
+
+
+def test_golden_dense_mnist8(api):
+    g = np.load(os.path.join(GOLD, "dense_mnist8.npz"))
+    model = api.RCN(10, [], [30])
+    model.load_weights_and_bias(784)
+    model.set_params(g["params"])
+    assert_close(model.classify_test(g["X"]), g["acts"], what="acts")
+    assert np.array_equal(model.classify_features(g["X"]), g["pred"])
+    model.train_batch(g["X"], 3.0, labels=g["labels"])
+    assert_close(model.get_gradients(), g["grads"], what="grads")
+    assert_close(model.get_params(), g["new_params"], what="params'")
+    assert_close(model.deltas(0)[0], g["sample0_deltas"][:30], what="delta1[0]")
+
+
+SHAPES = [
+    # (n_in, hidden sizes, classes, B)
+    (784, [30], 10, 32),          # config C1
+    (784, [30], 10, 1024),        # config C2
+    (1024, [256], 10, 512),       # config C3 network
+    (37, [13, 7], 3, 5),          # odd everything
+    (12, [7, 5], 3, 1),           # single sample
+    (300, [129, 65, 33], 17, 200),
+    (640, [384, 256], 10, 2048),  # exercises the 128x128 tiles and split-K
+]
+
+
+@pytest.mark.parametrize("n_in,hidden,classes,B", SHAPES)
+def test_train_batch_parity(api, n_in, hidden, classes, B):
+    model, net, params = make_model(api, hidden, classes, n_in, scale=1.0 if n_in < 100 else 0.05)
+    rng = np.random.default_rng(B)
+    X = np.maximum(rng.standard_normal((B, n_in)), 0)
+    labels = (np.arange(B) % classes).astype(np.int64)
+    Y = np.eye(classes)[labels]
+    want_params, want_grads = net.train_batch(params, X, Y, 3.0, n_threads=1)
+    want_acts = net.forward(params, X)
+    got_acts = model.classify_test(X)
+    assert_close(got_acts, want_acts, what="forward")
+    assert np.array_equal(model.classify_features(X), O.argmax_last(want_acts))
+    assert model.evaluate(X, labels) == O.accuracy(want_acts, labels)
+    model.train_batch(X, 3.0, labels=labels)
+    # per-sample taps for a few samples
+    for b in sorted({0, B // 2, B - 1}):
+        _, zs, acts, deltas = net.backprop(params, X[b], Y[b])
+        o = 0
+        for l, (r, _) in enumerate(net.shapes):
+            assert_close(model.activations(l)[b], acts[o:o + r], what=f"a[{l}][{b}]")
+            assert_close(model.deltas(l)[b], deltas[o:o + r], what=f"delta[{l}][{b}]")
+            o += r
+    assert_close(model.get_gradients(), want_grads, what="sum dW/db")
+    assert_close(model.get_params(), want_params, what="post-step params")
+    cost, hits = model.last_batch_stats()
+    assert hits == O.accuracy(want_acts, labels)
+    assert abs(cost - 0.5 * np.sum((want_acts - Y) ** 2)) <= 1e-9 * max(1.0, cost)
+    # one-hot targets give the same step as labels
+    model2, _, _ = make_model(api, hidden, classes, n_in, scale=1.0 if n_in < 100 else 0.05)
+    model2.train_batch(X, 3.0, onehot=Y)
+    assert np.array_equal(model2.get_params(), model.get_params())
+
+
+def test_saturated_units_unscaled_init(api):
+    """The reference draws N(0,1) weights unscaled (rcn.rs:509), so 784-wide layers saturate: sigmoid' = a*(1-a)
+    cancels catastrophically and parity requires cancelling identically (DESIGN.md 'faithful quirks')."""
+    model, net, params = make_model(api, [30], 10, 784, scale=1.0)
+    rng = np.random.default_rng(5)
+    X = np.maximum(rng.standard_normal((256, 784)), 0)
+    labels = (np.arange(256) % 10).astype(np.int64)
+    want_params, want_grads = net.train_batch(params, X, np.eye(10)[labels], 3.0)
+    model.train_batch(X, 3.0, labels=labels)
+    assert_close(model.get_gradients(), want_grads, what="grads")
+    assert_close(model.get_params(), want_params, what="params")
+
+
+def test_dmma_matches_simt_kernels(api):
+    """The DMMA tensor path and the plain SIMT cross-check kernels must agree to rounding."""
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, sys
+sys.path.insert(0, %r)
+import mercer_research_b200 as m
+model = m.RCN(10, [], [384, 256]); model.load_weights_and_bias(640)
+model.set_params(np.random.default_rng(1).standard_normal(model.n_params) * 0.05)
+X = np.maximum(np.random.default_rng(2).standard_normal((512, 640)), 0)
+model.train_batch(X, 3.0, labels=(np.arange(512) %% 10).astype(np.int64))
+np.save(sys.argv[1], model.get_params())
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for impl in ("dmma", "simt"):
+        path = f"/tmp/rcn_gemm_{impl}.npy"
+        env = dict(os.environ, RCN_CUDA_GEMM=impl)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env)
+        outs.append(np.load(path))
+    assert_close(outs[0], outs[1], rtol=1e-11, what="dmma vs simt")
+
+
+def test_full_pipeline_config_c2(api):
+    """BASELINE.json configs[1]: MNIST-shaped CNN, batch 1024, images -> features -> fwd -> bwd -> SGD."""
+    rng = np.random.default_rng(0x5EED)
+    B = 1024
+    imgs = rng.integers(0, 256, size=(B, 28, 28), dtype=np.uint8)
+    labels = (np.arange(B) % 10).astype(np.int64)
+    model = api.RCN(10, [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max)], [30])
+    raw = O.features_u8(CP, imgs)
+    mean, sd = O.gen_scales(raw)
+    model.scale_set = (mean, sd)
+    model.load_weights_and_bias(model.feature_len(28, 28))
+    assert model.layer_shapes == [(30, 784), (10, 30)]
+    net = O.Net(model.layer_shapes)
+    params = np.random.default_rng(0xC0FFEE).standard_normal(net.n_params)
+    model.set_params(params)
+    X = O.standardise(raw, mean, sd)
+    Y = np.eye(10)[labels]
+    want_params, want_grads = net.train_batch(params, X, Y, 3.0)
+    pred_before = model.classify_images(imgs)
+    assert np.array_equal(pred_before, O.argmax_last(net.forward(params, X)))          # labels bit-exact
+    model.train_batch_images(imgs, labels, 3.0)
+    assert_close(model.get_gradients(), want_grads, what="grads")
+    assert_close(model.get_params(), want_params, what="params")
+    assert np.array_equal(model.classify_images(imgs), O.argmax_last(net.forward(want_params, X)))
+    # threaded CPU reduction (the reference's rayon+mutex order) stays within tolerance of the GPU too
+    thr_params, _ = net.train_batch(params, X, Y, 3.0, n_threads=8)
+    assert_close(model.get_params(), thr_params, what="params vs threaded oracle")
+
+
+def test_multi_step_training_tracks_oracle(api):
+    """20 consecutive SGD steps: errors must not compound beyond tolerance."""
+    model, net, params = make_model(api, [16], 4, 40, scale=0.3)
+    rng = np.random.default_rng(8)
+    p = params.copy()
+    for step in range(20):
+        X = np.maximum(rng.standard_normal((24, 40)), 0)
+        labels = rng.integers(0, 4, 24).astype(np.int64)
+        p, _ = net.train_batch(p, X, np.eye(4)[labels], 3.0)
+        model.train_batch(X, 3.0, labels=labels)
+    assert_close(model.get_params(), p, rtol=1e-9, what="params after 20 steps")
+
+
+def test_split_phase_equals_train_batch(api):
+    """accumulate on two half batches + external sum + apply(global batch) == one train_batch (the DP contract)."""
+    import torch
+    model, net, params = make_model(api, [30], 10, 784, scale=0.05)
+    rng = np.random.default_rng(12)
+    X = np.maximum(rng.standard_normal((64, 784)), 0)
+    labels = (np.arange(64) % 10).astype(np.int64)
+    want, _ = net.train_batch(params, X, np.eye(10)[labels], 3.0)
+    g = torch.zeros(model.n_params, dtype=torch.float64, device="cuda")
+    model.bind_gradient_buffer(g)
+    model.accumulate_gradients(X[:32], labels=labels[:32])
+    model.synchronize()
+    g0 = g.clone()
+    model.accumulate_gradients(X[32:], labels=labels[32:])
+    model.synchronize()
+    g += g0
+    torch.cuda.synchronize()
+    model.apply_gradients(3.0, 64)
+    assert_close(model.get_params(), want, what="split-phase params")
+
+
+def test_shape_quirk_and_state_errors(api):
+    """rcn.rs:443: one conv + two pools gives 4/16*l = 0 input columns -> `w * a` dimension mismatch."""
+    model = api.RCN(10, [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max),
+                         api.RCNLayer.Pool2D(api.Pooling.Max)], [30])
+    with pytest.raises(api.RcnCudaError):
+        model.classify_test(np.zeros((1, 196)))            # parameters not initialised
+    L = model.feature_len(28, 28)
+    assert L == 4 * 7 * 7
+    model.load_weights_and_bias(L)
+    assert model.layer_shapes[0] == (30, 0)
+    imgs = np.zeros((2, 28, 28), dtype=np.uint8)
+    with pytest.raises(api.RcnCudaError) as e:
+        model.train_batch_images(imgs, np.zeros(2, dtype=np.int64), 3.0)
+    assert e.value.status == 2
+    empty_ff = api.RCN(10, [], [])
+    with pytest.raises(api.RcnCudaError):
+        empty_ff.load_weights_and_bias(10)                 # feedforward_cfg[0] (rcn.rs:444)
+
+
+def test_train_arrays_epoch_driver(api):
+    """RCN::train semantics on in-memory images: chunks_exact drops the remainder, scale_set ends up holding the
+    TEST set's statistics (rcn.rs:134-137), accuracy uses the exact-one-hot rule."""
+    rng = np.random.default_rng(4)
+    tr = rng.integers(0, 256, size=(53, 28, 28), dtype=np.uint8)
+    te = rng.integers(0, 256, size=(20, 28, 28), dtype=np.uint8)
+    trl = (np.arange(53) % 10).astype(np.int64)
+    tel = (np.arange(20) % 10).astype(np.int64)
+    model = api.RCN(10, [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max)], [30])
+    lines = []
+    hist = model.train_arrays(tr, trl, te, tel, batch_size=10, epochs=2, eta=3.0, seed=1, log=lines.append)
+    assert len(hist) == 2 and lines[0].startswith("Epoch 0: ") and lines[0].endswith("%]")
+    te_raw = O.features_u8(CP, te)
+    m, s = O.gen_scales(te_raw)
+    gm, gs = model.scale_set
+    assert abs(gm - m) <= 1e-12 * m and abs(gs - s) <= 1e-12 * s
