@@ -143,6 +143,16 @@ int rcn_cuda_get_gradients(rcn_cuda_handle h, double* flat, size_t n);
 int rcn_cuda_get_activations(rcn_cuda_handle h, size_t layer, double* out);
 int rcn_cuda_get_deltas(rcn_cuda_handle h, size_t layer, double* out);
 
+/* ---- launch accounting (bench.py: gpu_launches, per-kernel durations for the roofline) ------------------ */
+/* Number of kernels this library has launched in this process. */
+int rcn_cuda_kernel_launches(uint64_t* count);
+/* on != 0: start bracketing every kernel launch with CUDA events on its stream (clears old records);
+ * on == 0: stop.  Adds two event records per launch -- never enable inside a timed region. */
+int rcn_cuda_profile_enable(int on);
+/* Synchronises the device and writes a JSON object {"kernel": {"launches": n, "total_ms": t}, ...} for the
+ * records collected since the last enable. */
+int rcn_cuda_profile_report(char* json_out, size_t capacity);
+
 /* ---- op-level API: traits Convolve2D (kernel.rs:61-100) and Pool2D (kernel.rs:219-236) -------- */
 /* These need no model; `device` selects the GPU and `cuda_stream` may be NULL. Outputs are caller-allocated:
  * convolve_2d: H x W (Same) or (H-kh+1) x (W-kw+1) (None); pool_2d: ceil(H/2) x ceil(W/2) (Same) or

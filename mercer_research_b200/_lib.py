@@ -61,6 +61,9 @@ SIGNATURES = {
     "rcn_cuda_get_gradients": [_vp, _vp, _sz],
     "rcn_cuda_get_activations": [_vp, _sz, _vp],
     "rcn_cuda_get_deltas": [_vp, _sz, _vp],
+    "rcn_cuda_kernel_launches": [C.POINTER(C.c_uint64)],
+    "rcn_cuda_profile_enable": [_i],
+    "rcn_cuda_profile_report": [C.c_char_p, _sz],
     "rcn_cuda_convolve_2d": [_i, _vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _vp],
     "rcn_cuda_convolve_2d_separated": [_i, _vp, _vp, _sz, _sz, _i, _i, _vp],
     "rcn_cuda_relu": [_i, _vp, _vp, _sz, _vp],
@@ -106,3 +109,21 @@ def check(status: int) -> None:
     if status != RCN_OK:
         msg = load().rcn_cuda_last_error()
         raise RcnCudaError(status, msg.decode("utf-8", "replace") if msg else "")
+
+
+def kernel_launches() -> int:
+    """Kernels launched by librcn_cuda in this process (bench.py's gpu_launches)."""
+    n = C.c_uint64()
+    check(load().rcn_cuda_kernel_launches(C.byref(n)))
+    return n.value
+
+
+def profile_enable(on: bool) -> None:
+    check(load().rcn_cuda_profile_enable(1 if on else 0))
+
+
+def profile_report() -> dict:
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    check(load().rcn_cuda_profile_report(buf, len(buf)))
+    return json.loads(buf.value.decode())

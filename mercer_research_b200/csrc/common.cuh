@@ -39,6 +39,25 @@ int fail(int code, const char* fmt, ...);
                                __FILE__, __LINE__);                                                \
     } while (0)
 
+// ---- launch accounting / built-in per-kernel timing ---------------------------------------------------
+// Every kernel launch goes through RCN_LAUNCH: it bumps the process-wide launch counter (bench.py's
+// gpu_launches) and, when profiling is enabled (rcn_cuda_profile_enable), brackets the launch with CUDA
+// events on the launching stream so bench.py can report per-kernel durations for the roofline.
+struct LaunchScope {
+    cudaStream_t stream;
+    int slot;
+    LaunchScope(const char* name, cudaStream_t s);
+    ~LaunchScope();
+};
+#define RCN_LAUNCH(name, stream, ...)                 \
+    do {                                              \
+        {                                             \
+            ::rcn::LaunchScope _ls(name, stream);     \
+            __VA_ARGS__;                              \
+        }                                             \
+        RCN_LAUNCH_CHECK();                           \
+    } while (0)
+
 // Is `p` device-accessible memory (device or managed)?  Unregistered host memory reports
 // cudaMemoryTypeUnregistered; pinned host memory cudaMemoryTypeHost.
 inline bool is_device_ptr(const void* p) {

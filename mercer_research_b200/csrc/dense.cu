@@ -206,7 +206,7 @@ __global__ void gemm_f64_simt_kernel(const double* __restrict__ A, int lda, cons
 }
 
 template <int BM, int BN, int WM, int WN, bool AK, bool BKc, typename Epi>
-static int launch_dmma(const double* A, int lda, const double* B, int ldb, int M, int N, int K, int splits,
+static int launch_dmma(const char* name, const double* A, int lda, const double* B, int ldb, int M, int N, int K, int splits,
                        int k_per_split, const Epi& epi, cudaStream_t stream) {
     using TA = TileLayout<BM, AK>;
     using TB = TileLayout<BN, BKc>;
@@ -218,14 +218,13 @@ static int launch_dmma(const double* A, int lda, const double* B, int ldb, int M
         attr_done = true;
     }
     dim3 grid(cdiv(M, BM), cdiv(N, BN), splits);
-    kern<<<grid, GEMM_THREADS, smem, stream>>>(A, lda, B, ldb, M, N, K, k_per_split, epi);
-    RCN_LAUNCH_CHECK();
+    RCN_LAUNCH(name, stream, kern<<<grid, GEMM_THREADS, smem, stream>>>(A, lda, B, ldb, M, N, K, k_per_split, epi));
     return RCN_OK;
 }
 
 template <bool AK, bool BKc, typename Epi>
-static int launch_gemm(const double* A, int lda, const double* B, int ldb, size_t M_, size_t N_, size_t K_, int splits,
-                       const Epi& epi, cudaStream_t stream) {
+static int launch_gemm(const char* name, const double* A, int lda, const double* B, int ldb, size_t M_, size_t N_, size_t K_,
+                       int splits, const Epi& epi, cudaStream_t stream) {
     if (M_ == 0 || N_ == 0) return RCN_OK;
     if (M_ > 0x7fffffff || N_ > 0x7fffffff || K_ > 0x7fffffff) return fail(RCN_ERR_INVALID, "GEMM dimension too large");
     const int M = (int)M_, N = (int)N_, K = (int)K_;
@@ -236,15 +235,14 @@ static int launch_gemm(const double* A, int lda, const double* B, int ldb, size_
     splits = K > 0 ? (K + k_per_split - 1) / k_per_split : 1;
     if (gemm_impl() == GEMM_SIMT) {
         dim3 grid(cdiv(M, 32), cdiv(N, 8), splits);
-        gemm_f64_simt_kernel<AK, BKc, Epi><<<grid, 256, 0, stream>>>(A, lda, B, ldb, M, N, K, k_per_split, epi);
-        RCN_LAUNCH_CHECK();
+        RCN_LAUNCH(name, stream, gemm_f64_simt_kernel<AK, BKc, Epi><<<grid, 256, 0, stream>>>(A, lda, B, ldb, M, N, K, k_per_split, epi));
         return RCN_OK;
     }
-    if (M <= 32) return launch_dmma<32, 128, 32, 16, AK, BKc, Epi>(A, lda, B, ldb, M, N, K, splits, k_per_split, epi, stream);
+    if (M <= 32) return launch_dmma<32, 128, 32, 16, AK, BKc, Epi>(name, A, lda, B, ldb, M, N, K, splits, k_per_split, epi, stream);
     const size_t big_tiles = (size_t)cdiv(M, 128) * cdiv(N, 128) * splits;
     if (big_tiles >= (size_t)kNumSMs)
-        return launch_dmma<128, 128, 64, 32, AK, BKc, Epi>(A, lda, B, ldb, M, N, K, splits, k_per_split, epi, stream);
-    return launch_dmma<64, 64, 32, 16, AK, BKc, Epi>(A, lda, B, ldb, M, N, K, splits, k_per_split, epi, stream);
+        return launch_dmma<128, 128, 64, 32, AK, BKc, Epi>(name, A, lda, B, ldb, M, N, K, splits, k_per_split, epi, stream);
+    return launch_dmma<64, 64, 32, 16, AK, BKc, Epi>(name, A, lda, B, ldb, M, N, K, splits, k_per_split, epi, stream);
 }
 
 // Effective split count launch_gemm will use (so callers can size the partial workspace).
@@ -263,14 +261,14 @@ int launch_dense_forward(const double* W, const double* b, const double* A_in, s
                          double* A_out, double* delta_out, const double* onehot, const int64_t* labels,
                          cudaStream_t stream) {
     EpiForward epi{b, A_out, delta_out, onehot, labels, (int)M};
-    return launch_gemm<false, true, EpiForward>(W, (int)M, A_in, (int)K, M, N, K, 1, epi, stream);
+    return launch_gemm<false, true, EpiForward>("dense_forward_gemm", W, (int)M, A_in, (int)K, M, N, K, 1, epi, stream);
 }
 
 int launch_dense_backward_data(const double* W_up, const double* delta_up, const double* A, size_t M, size_t K,
                                size_t N, double* delta_out, cudaStream_t stream) {
     EpiBackData epi{A, delta_out, (int)M};
     // A(m,k) = W_up[k, m]; W_up is K x M column-major => k-contiguous with lda = K.
-    return launch_gemm<true, true, EpiBackData>(W_up, (int)K, delta_up, (int)K, M, N, K, 1, epi, stream);
+    return launch_gemm<true, true, EpiBackData>("dense_backward_data_gemm", W_up, (int)K, delta_up, (int)K, M, N, K, 1, epi, stream);
 }
 
 __global__ void reduce_splits_kernel(const double* __restrict__ part, int splits, size_t n, double* __restrict__ out) {
@@ -321,19 +319,17 @@ int launch_dense_backward_weight(const double* delta, const double* A_prev, size
     if (N > 0) {
         if (splits == 1) {
             EpiStore epi{dW, (int)M, 0};
-            RCN_TRY((launch_gemm<false, false, EpiStore>(delta, (int)M, A_prev, (int)N, M, N, Kb, 1, epi, stream)));
+            RCN_TRY((launch_gemm<false, false, EpiStore>("dense_backward_weight_gemm", delta, (int)M, A_prev, (int)N, M, N, Kb, 1, epi, stream)));
         } else {
             RCN_TRY(workspace.reserve((size_t)splits * M * N * sizeof(double)));
             EpiStore epi{workspace.as<double>(), (int)M, M * N};
-            RCN_TRY((launch_gemm<false, false, EpiStore>(delta, (int)M, A_prev, (int)N, M, N, Kb, splits, epi, stream)));
+            RCN_TRY((launch_gemm<false, false, EpiStore>("dense_backward_weight_gemm", delta, (int)M, A_prev, (int)N, M, N, Kb, splits, epi, stream)));
             unsigned grid = cdiv(M * N, 256);
             if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-            reduce_splits_kernel<<<grid, 256, 0, stream>>>(workspace.as<double>(), splits, M * N, dW);
-            RCN_LAUNCH_CHECK();
+            RCN_LAUNCH("reduce_splits_kernel", stream, reduce_splits_kernel<<<grid, 256, 0, stream>>>(workspace.as<double>(), splits, M * N, dW));
         }
     }
-    bias_grad_kernel<<<cdiv(M, 32), 256, 0, stream>>>(delta, (int)M, (int)Kb, db);
-    RCN_LAUNCH_CHECK();
+    RCN_LAUNCH("bias_grad_kernel", stream, bias_grad_kernel<<<cdiv(M, 32), 256, 0, stream>>>(delta, (int)M, (int)Kb, db));
     return RCN_OK;
 }
 
@@ -349,8 +345,7 @@ int launch_sgd_update(double* params, const double* grads, size_t n, double scal
     if (n == 0) return RCN_OK;
     unsigned grid = cdiv(n, 256);
     if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-    sgd_update_kernel<<<grid, 256, 0, stream>>>(params, grads, n, scale);
-    RCN_LAUNCH_CHECK();
+    RCN_LAUNCH("sgd_update_kernel", stream, sgd_update_kernel<<<grid, 256, 0, stream>>>(params, grads, n, scale));
     return RCN_OK;
 }
 
@@ -371,8 +366,7 @@ int launch_argmax_last(const double* acts, size_t n, size_t B, int64_t* labels, 
     if (B == 0) return RCN_OK;
     unsigned grid = cdiv(B, 128);
     if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-    argmax_last_kernel<<<grid, 128, 0, stream>>>(acts, (int)n, B, labels);
-    RCN_LAUNCH_CHECK();
+    RCN_LAUNCH("argmax_last_kernel", stream, argmax_last_kernel<<<grid, 128, 0, stream>>>(acts, (int)n, B, labels));
     return RCN_OK;
 }
 
@@ -415,8 +409,7 @@ __global__ void __launch_bounds__(256) batch_stats_kernel(const double* __restri
 
 int launch_batch_stats(const double* acts, size_t n, size_t B, const double* onehot, const int64_t* labels,
                        double* stats_dev, cudaStream_t stream) {
-    batch_stats_kernel<<<1, 256, 0, stream>>>(acts, (int)n, B, onehot, labels, stats_dev);
-    RCN_LAUNCH_CHECK();
+    RCN_LAUNCH("batch_stats_kernel", stream, batch_stats_kernel<<<1, 256, 0, stream>>>(acts, (int)n, B, onehot, labels, stats_dev));
     return RCN_OK;
 }
 

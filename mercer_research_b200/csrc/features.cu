@@ -293,9 +293,8 @@ static int launch_features_t(const FeaturePlan& plan, const TIN* images, size_t 
         if (per_sm < 1) per_sm = 1;
         size_t grid = (size_t)kNumSMs * per_sm;
         if (grid > B) grid = B;
-        kern<<<(unsigned)grid, 256, smem, stream>>>(images, (int)B, (int)H, (int)W, sl, (int)plan.max_elems, out, plan.L,
-                                                    standardise ? 1 : 0, mean, sd);
-        RCN_LAUNCH_CHECK();
+        RCN_LAUNCH("features_fused_kernel", stream, kern<<<(unsigned)grid, 256, smem, stream>>>(images, (int)B, (int)H, (int)W, sl, (int)plan.max_elems, out, plan.L,
+                                                    standardise ? 1 : 0, mean, sd));
         return RCN_OK;
     }
     // layer-by-layer over global ping-pong buffers
@@ -312,8 +311,7 @@ static int launch_features_t(const FeaturePlan& plan, const TIN* images, size_t 
     {
         dim3 grid(cdiv(H * W, 256), (unsigned)(B > 32768 ? 32768 : B));
         if (grid.x > 64) grid.x = 64;
-        convert_images_kernel<TIN, T><<<grid, 256, 0, stream>>>(images, cur, (int)H, (int)W, B);
-        RCN_LAUNCH_CHECK();
+        RCN_LAUNCH("convert_images_kernel", stream, convert_images_kernel<TIN, T><<<grid, 256, 0, stream>>>(images, cur, (int)H, (int)W, B));
     }
     for (int s = 0; s < sl.n; ++s) {
         const Stage& st = sl.s[s];
@@ -321,12 +319,10 @@ static int launch_features_t(const FeaturePlan& plan, const TIN* images, size_t 
         dim3 grid(cdiv(items, 256), (unsigned)(B > 32768 ? 32768 : B));
         if (grid.x > 1024) grid.x = 1024;
         if (s == sl.n - 1) {
-            stage_final_kernel<T><<<grid, 256, 0, stream>>>(st, cur, cur_stride, out, plan.L, standardise ? 1 : 0, mean, sd, B);
-            RCN_LAUNCH_CHECK();
+            RCN_LAUNCH("stage_final_kernel", stream, stage_final_kernel<T><<<grid, 256, 0, stream>>>(st, cur, cur_stride, out, plan.L, standardise ? 1 : 0, mean, sd, B));
         } else {
             const size_t out_stride = (size_t)st.n_out * st.h_out * st.w_out;
-            stage_maps_kernel<T><<<grid, 256, 0, stream>>>(st, cur, cur_stride, nxt, out_stride, B);
-            RCN_LAUNCH_CHECK();
+            RCN_LAUNCH("stage_maps_kernel", stream, stage_maps_kernel<T><<<grid, 256, 0, stream>>>(st, cur, cur_stride, nxt, out_stride, B));
             T* tmp = cur; cur = nxt; nxt = tmp;
             cur_stride = out_stride;
         }
@@ -365,8 +361,7 @@ int launch_standardise(double* feats, size_t n, double mean, double sd, cudaStre
     if (n == 0) return RCN_OK;
     unsigned grid = cdiv(n, 256);
     if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-    standardise_kernel<<<grid, 256, 0, stream>>>(feats, n, mean, sd);
-    RCN_LAUNCH_CHECK();
+    RCN_LAUNCH("standardise_kernel", stream, standardise_kernel<<<grid, 256, 0, stream>>>(feats, n, mean, sd));
     return RCN_OK;
 }
 
@@ -420,10 +415,8 @@ int launch_gen_scales(const double* feats, size_t n, double* result_dev, DevBuf&
     RCN_TRY(scratch.reserve((size_t)grid * sizeof(double)));
     double* partial = scratch.as<double>();
     for (int pass = 0; pass < 2; ++pass) {
-        scale_partial_kernel<<<grid, 256, 0, stream>>>(feats, n, pass, result_dev, partial);
-        RCN_LAUNCH_CHECK();
-        scale_final_kernel<<<1, 256, 0, stream>>>(partial, grid, n, pass, result_dev);
-        RCN_LAUNCH_CHECK();
+        RCN_LAUNCH("scale_partial_kernel", stream, scale_partial_kernel<<<grid, 256, 0, stream>>>(feats, n, pass, result_dev, partial));
+        RCN_LAUNCH("scale_final_kernel", stream, scale_final_kernel<<<1, 256, 0, stream>>>(partial, grid, n, pass, result_dev));
     }
     return RCN_OK;
 }
@@ -462,8 +455,7 @@ int launch_convolve_2d(const double* m, size_t H, size_t W, const double* k, siz
     const size_t oh = same ? H : H - kh + 1, ow = same ? W : W - kw + 1;
     unsigned grid = cdiv(oh * ow, 256);
     if (grid > kNumSMs * 16) grid = kNumSMs * 16;
-    conv2d_generic_kernel<<<grid, 256, 0, stream>>>(m, (int)H, (int)W, k, (int)kh, (int)kw, same ? 1 : 0, out, (int)oh, (int)ow);
-    RCN_LAUNCH_CHECK();
+    RCN_LAUNCH("conv2d_generic_kernel", stream, conv2d_generic_kernel<<<grid, 256, 0, stream>>>(m, (int)H, (int)W, k, (int)kh, (int)kw, same ? 1 : 0, out, (int)oh, (int)ow));
     return RCN_OK;
 }
 
@@ -484,9 +476,8 @@ int launch_convolve_2d_separated(const double* m, size_t H, size_t W, int op, in
     const size_t oh = same ? H : H - 2, ow = same ? W : W - 2;
     unsigned grid = cdiv(oh * ow, 256);
     if (grid > kNumSMs * 16) grid = kNumSMs * 16;
-    if (same) conv_sep_single_kernel<true><<<grid, 256, 0, stream>>>(m, (int)H, (int)W, op, out, (int)oh, (int)ow);
-    else conv_sep_single_kernel<false><<<grid, 256, 0, stream>>>(m, (int)H, (int)W, op, out, (int)oh, (int)ow);
-    RCN_LAUNCH_CHECK();
+    if (same) RCN_LAUNCH("conv_sep_single_kernel", stream, conv_sep_single_kernel<true><<<grid, 256, 0, stream>>>(m, (int)H, (int)W, op, out, (int)oh, (int)ow));
+    else RCN_LAUNCH("conv_sep_single_kernel", stream, conv_sep_single_kernel<false><<<grid, 256, 0, stream>>>(m, (int)H, (int)W, op, out, (int)oh, (int)ow));
     return RCN_OK;
 }
 
@@ -499,8 +490,7 @@ int launch_relu(const double* m, size_t n, double* out, cudaStream_t stream) {
     if (n == 0) return RCN_OK;
     unsigned grid = cdiv(n, 256);
     if (grid > kNumSMs * 16) grid = kNumSMs * 16;
-    relu_kernel<<<grid, 256, 0, stream>>>(m, n, out);
-    RCN_LAUNCH_CHECK();
+    RCN_LAUNCH("relu_kernel", stream, relu_kernel<<<grid, 256, 0, stream>>>(m, n, out));
     return RCN_OK;
 }
 
@@ -534,8 +524,7 @@ int launch_pool_2d(const double* m, size_t H, size_t W, int padding, double* out
     if (oh * ow == 0) return RCN_OK;
     unsigned grid = cdiv(oh * ow, 256);
     if (grid > kNumSMs * 16) grid = kNumSMs * 16;
-    pool2d_kernel<<<grid, 256, 0, stream>>>(m, (int)H, (int)W, out, (int)oh, (int)ow, argmax, nan_flag);
-    RCN_LAUNCH_CHECK();
+    RCN_LAUNCH("pool2d_kernel", stream, pool2d_kernel<<<grid, 256, 0, stream>>>(m, (int)H, (int)W, out, (int)oh, (int)ow, argmax, nan_flag));
     return RCN_OK;
 }
 

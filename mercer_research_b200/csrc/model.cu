@@ -1,12 +1,16 @@
 // model.cu -- the C ABI of librcn_cuda.so (include/rcn_cuda.h): model handle, device buffers, host<->device
 // staging, and the layer dispatch that replaces rcn's per-sample CPU loops (rcn/src/rcn.rs) with batched
 // kernels (features.cu, dense.cu).
+#include <atomic>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <vector>
 
 #include "dense.cuh"
 #include "features.cuh"
+#include "smallnet.cuh"
 
 namespace rcn {
 
@@ -23,6 +27,34 @@ int fail(int code, const char* fmt, ...) {
     va_end(ap);
     last_error_ref() = buf;
     return code;
+}
+
+// ---- launch accounting / per-kernel event timing --------------------------------------------------------
+namespace {
+struct ProfRecord { const char* name; cudaEvent_t start, stop; };
+std::atomic<unsigned long long> g_launches{0};
+std::atomic<bool> g_profiling{false};
+std::mutex g_prof_mu;
+std::vector<ProfRecord> g_prof;
+}  // namespace
+
+LaunchScope::LaunchScope(const char* name, cudaStream_t s) : stream(s), slot(-1) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!g_profiling.load(std::memory_order_relaxed)) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return; }
+    ProfRecord r{name, nullptr, nullptr};
+    if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaEventRecord(r.start, s);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(r);
+    slot = (int)g_prof.size() - 1;
+}
+
+LaunchScope::~LaunchScope() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].stop, stream);
 }
 
 }  // namespace rcn
@@ -45,6 +77,8 @@ struct rcn_cuda_model {
     double* grads = nullptr;
     bool grads_bound = false;
     double mean = 1.0, sd = 1.0;  // scale_set starts at (1, 1)  (rcn.rs:71)
+    SmallNetDesc small_desc{};      // fused path for narrow networks (smallnet.cu)
+    bool use_small = false;
 
     // feature plan cache
     bool plan_valid = false;
@@ -131,6 +165,8 @@ int forward_dev(rcn_cuda_model* h, const double* feats, size_t B, const double* 
     const size_t n = h->rows.size();
     RCN_TRY(h->acts.reserve(h->sum_rows * B * sizeof(double)));
     if (want_delta) RCN_TRY(h->deltas.reserve(h->sum_rows * B * sizeof(double)));
+    if (h->use_small && !want_delta)
+        return launch_smallnet_forward(h->small_desc, h->params.as<double>(), feats, B, h->acts.as<double>(), h->stream);
     for (size_t l = 0; l < n; ++l) {
         const double* a_in = l == 0 ? feats : h->act(l - 1, B);
         const bool last = (l + 1 == n);
@@ -145,6 +181,17 @@ int accumulate_dev(rcn_cuda_model* h, const double* feats, const double* onehot,
     const size_t n = h->rows.size();
     if (B == 0) {
         RCN_CUDA_TRY(cudaMemsetAsync(h->grads, 0, h->n_params * sizeof(double), h->stream));
+        return RCN_OK;
+    }
+    if (h->use_small) {
+        RCN_TRY(h->acts.reserve(h->sum_rows * B * sizeof(double)));
+        RCN_TRY(h->deltas.reserve(h->sum_rows * B * sizeof(double)));
+        RCN_TRY(h->small.reserve(64));
+        RCN_TRY(launch_smallnet_backprop(h->small_desc, h->params.as<double>(), feats, B, onehot, labels,
+                                         h->acts.as<double>(), h->deltas.as<double>(), h->grads, h->small.as<double>(),
+                                         h->gemm_ws, h->stream));
+        h->stats_valid = true;
+        h->last_B = B;
         return RCN_OK;
     }
     RCN_TRY(forward_dev(h, feats, B, onehot, labels, true));
@@ -291,6 +338,19 @@ int rcn_cuda_init_params(rcn_cuda_handle h, size_t l) {
         b = (i + 1 < h->ff.size()) ? h->ff[i + 1] : h->classes;
     }
     h->n_params = off; h->sum_rows = sum_rows;
+    {   // fused small-network path (smallnet.cu) unless RCN_CUDA_SMALLNET=0
+        SmallNetDesc d{};
+        h->use_small = false;
+        const char* env = getenv("RCN_CUDA_SMALLNET");
+        if (n <= (size_t)kSmallNetMaxLayers && h->cols[0] >= 1 && h->cols[0] < (1u << 24) && off < (1u << 30) &&
+            !(env && env[0] == '0')) {
+            d.n_layers = (int)n; d.n_in = (int)h->cols[0]; d.n_params = (int)off;
+            for (size_t i = 0; i < n; ++i) { d.rows[i] = (int)h->rows[i]; d.w_off[i] = (int)h->w_off[i]; d.b_off[i] = (int)h->b_off[i]; }
+            bool ok = true;
+            for (size_t i = 0; i < n; ++i) ok = ok && h->rows[i] <= 32;
+            if (ok && smallnet_eligible(d)) { h->small_desc = d; h->use_small = true; }
+        }
+    }
     RCN_TRY(h->params.reserve(off * sizeof(double)));
     RCN_CUDA_TRY(cudaMemsetAsync(h->params.p, 0, off * sizeof(double), h->stream));
     if (!h->grads_bound) {
@@ -618,6 +678,51 @@ int rcn_cuda_get_deltas(rcn_cuda_handle h, size_t layer, double* out) {
     if (layer >= h->rows.size() || !out) return fail(RCN_ERR_INVALID, "bad layer / null destination");
     if (!h->last_B) return fail(RCN_ERR_STATE, "no batch has been accumulated yet");
     return deliver(h, out, h->delta(layer, h->last_B), h->rows[layer] * h->last_B * sizeof(double));
+}
+
+// ---- launch accounting ------------------------------------------------------------------------------
+int rcn_cuda_kernel_launches(uint64_t* count) {
+    if (!count) return fail(RCN_ERR_INVALID, "null count");
+    *count = g_launches.load();
+    return RCN_OK;
+}
+
+int rcn_cuda_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (on) {
+        for (auto& r : g_prof) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
+        g_prof.clear();
+    }
+    g_profiling.store(on != 0);
+    return RCN_OK;
+}
+
+int rcn_cuda_profile_report(char* json_out, size_t capacity) {
+    if (!json_out || capacity < 3) return fail(RCN_ERR_INVALID, "report buffer too small");
+    RCN_CUDA_TRY(cudaDeviceSynchronize());
+    std::map<std::string, std::pair<unsigned long long, double>> agg;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        for (auto& r : g_prof) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, r.start, r.stop) != cudaSuccess) { cudaGetLastError(); continue; }
+            auto& a = agg[r.name];
+            a.first += 1; a.second += ms;
+        }
+    }
+    std::string js = "{";
+    bool first = true;
+    for (auto& kv : agg) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "%s\"%s\": {\"launches\": %llu, \"total_ms\": %.6f}", first ? "" : ", ", kv.first.c_str(),
+                 kv.second.first, kv.second.second);
+        js += buf;
+        first = false;
+    }
+    js += "}";
+    if (js.size() + 1 > capacity) return fail(RCN_ERR_INVALID, "report needs %zu bytes", js.size() + 1);
+    memcpy(json_out, js.c_str(), js.size() + 1);
+    return RCN_OK;
 }
 
 // ---- op-level API ---------------------------------------------------------------------------------

@@ -138,6 +138,11 @@ class RCN:
             _lib.check(self._lib.rcn_cuda_layer_shape(self._h, i, C.byref(r), C.byref(c)))
             self._shapes.append((r.value, c.value))
 
+    def _require_params(self):
+        if not self._shapes:  # raises RCN_ERR_STATE from the library
+            n = C.c_size_t()
+            _lib.check(self._lib.rcn_cuda_param_count(self._h, C.byref(n)))
+
     @property
     def layer_shapes(self) -> List[Tuple[int, int]]:
         return list(self._shapes)
@@ -172,11 +177,13 @@ class RCN:
         _lib.check(self._lib.rcn_cuda_set_params(self._h, flat.ctypes.data, flat.size))
 
     def get_params(self) -> np.ndarray:
+        self._require_params()
         buf = np.zeros(self.n_params)
         _lib.check(self._lib.rcn_cuda_get_params(self._h, buf.ctypes.data, buf.size))
         return buf
 
     def get_gradients(self) -> np.ndarray:
+        self._require_params()
         buf = np.zeros(self.n_params)
         _lib.check(self._lib.rcn_cuda_get_gradients(self._h, buf.ctypes.data, buf.size))
         return buf
@@ -247,6 +254,7 @@ class RCN:
     # -- inference --------------------------------------------------------------------------------------------
     def classify_test(self, feats):
         """rcn.rs:105-116 over a batch: (B, L) features -> (B, classes) output activations."""
+        self._require_params()
         f = _Buf(feats, np.float64)
         self._use_torch_stream(f)
         B = f.shape[0]
@@ -263,6 +271,7 @@ class RCN:
 
     def classify_features(self, feats):
         """argmax (last maximal element wins, rcn.rs:92-97) of classify_test."""
+        self._require_params()
         f = _Buf(feats, np.float64)
         self._use_torch_stream(f)
         B = f.shape[0]
@@ -298,6 +307,7 @@ class RCN:
 
     def evaluate(self, feats, labels) -> int:
         """Epoch evaluation rule (rcn.rs:152-157): number of samples whose max set equals the one-hot exactly."""
+        self._require_params()
         f = _Buf(feats, np.float64)
         l = _Buf(labels, np.int64)
         self._use_torch_stream(f, l)
@@ -313,6 +323,7 @@ class RCN:
 
     def accumulate_gradients(self, feats, onehot=None, labels=None):
         """Batch sum of backprop (rcn.rs:260-314, 190-205) into the flat gradient buffer; no update."""
+        self._require_params()
         f = _Buf(feats, np.float64)
         oh, lb = self._targets(onehot, labels)
         self._use_torch_stream(f, oh, lb)
@@ -333,6 +344,7 @@ class RCN:
 
     def train_batch(self, feats, eta: float, onehot=None, labels=None):
         """``train_batch`` (rcn.rs:176-223) on (B, L) standardised features."""
+        self._require_params()
         f = _Buf(feats, np.float64)
         oh, lb = self._targets(onehot, labels)
         self._use_torch_stream(f, oh, lb)
@@ -356,12 +368,14 @@ class RCN:
 
     def activations(self, layer: int) -> np.ndarray:
         """a_{layer+1} of the last accumulated batch, (B, rows)."""
+        self._require_params()
         B = self._last_B()
         buf = np.zeros((B, self._shapes[layer][0]))
         _lib.check(self._lib.rcn_cuda_get_activations(self._h, layer, buf.ctypes.data))
         return buf
 
     def deltas(self, layer: int) -> np.ndarray:
+        self._require_params()
         B = self._last_B()
         buf = np.zeros((B, self._shapes[layer][0]))
         _lib.check(self._lib.rcn_cuda_get_deltas(self._h, layer, buf.ctypes.data))

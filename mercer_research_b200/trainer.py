@@ -1,0 +1,73 @@
+"""Data-parallel trainer: the B200 equivalent of rcn's only parallelism strategy, the per-minibatch gradient sum
+over worker threads (rcn/src/rcn.rs:190-205), scaled from host threads to the GPUs of one box.
+
+One process per GPU (torch.distributed, NCCL over NVLink 5 / NVSwitch). Every rank holds a full parameter replica,
+runs features + forward + backward on its contiguous shard of the global minibatch, producing gradient SUMS in one
+flat f64 buffer [dW0|db0|dW1|db1|...]; ONE all-reduce(sum) of that buffer per step; every replica then applies the
+identical ``W -= (eta / B_global) * g`` (rcn.rs:210-222), so replicas stay bit-identical to each other and differ from
+the single-GPU result only by summation order. No other collective is on the data path.
+
+The compute backend is any object with ``n_params``, ``bind_gradient_buffer(t)``, ``accumulate_gradients_images``,
+``accumulate_gradients``, ``apply_gradients`` and ``last_batch_stats`` -- in the product that is ``RCN`` (CUDA);
+the gloo CPU tests plug in a checker-backed stand-in to exercise exactly this host logic without a GPU.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+
+def shard_bounds(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of a global minibatch; the global batch must divide evenly (all BASELINE configs do)."""
+    if global_batch % world:
+        raise ValueError(f"global batch {global_batch} is not divisible by world size {world}")
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+class DataParallelTrainer:
+    def __init__(self, model, eta: float, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+        self.model = model
+        self.eta = float(eta)
+        self.group = group
+        self.dist = dist if dist.is_available() and dist.is_initialized() else None
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+        self.rank = self.dist.get_rank(group) if self.dist else 0
+        if device is None:
+            device = torch.device("cuda", model.device)
+        # the all-reduce target IS the kernels' output buffer: no staging copy on either side of the collective
+        self.grads = torch.zeros(model.n_params, dtype=torch.float64, device=device)
+        model.bind_gradient_buffer(self.grads)
+
+    # -- one step of rcn.rs:176-223 on this rank's shard ------------------------------------------------------------
+    def _reduce_and_apply(self, local_batch: int):
+        if self.world > 1:
+            self.dist.all_reduce(self.grads, op=self.dist.ReduceOp.SUM, group=self.group)
+        self.model.apply_gradients(self.eta, local_batch * self.world)
+
+    def step_images(self, images, labels):
+        """images: this rank's shard, (B_local, H, W) uint8 / float64 (torch CUDA tensor or numpy); labels (B_local,)."""
+        self.model.accumulate_gradients_images(images, labels)
+        self._reduce_and_apply(int(images.shape[0]))
+
+    def step_features(self, feats, labels=None, onehot=None):
+        self.model.accumulate_gradients(feats, onehot=onehot, labels=labels)
+        self._reduce_and_apply(int(feats.shape[0]))
+
+    def step_images_host(self, images, labels):
+        """End-to-end step from HOST buffers (numpy, ideally pinned): H2D of the shard inside the call, and the step's
+        metric (quadratic cost, hits -- evaluated with the pre-update parameters) read back from the device."""
+        self.model.accumulate_gradients_images(images, labels)
+        self._reduce_and_apply(int(images.shape[0]))
+        return self.model.last_batch_stats()
+
+    def step_global_images(self, images, labels):
+        """Convenience: every rank passes the same GLOBAL batch and trains on its own contiguous shard of it."""
+        lo, hi = shard_bounds(int(images.shape[0]), self.rank, self.world)
+        self.step_images(images[lo:hi], labels[lo:hi])
+
+    def describe(self) -> str:
+        ar = "none (1 GPU)" if self.world == 1 else f"1x NCCL all-reduce(sum) of {self.model.n_params} f64 per step"
+        return ("features(+standardise) -> fwd -> bwd-data -> bwd-weight(+db) -> batch stats -> " + ar +
+                " -> SGD update; kernels launched through the C ABI on torch's current stream")

@@ -143,6 +143,34 @@ np.save(sys.argv[1], model.get_params())
     assert_close(outs[0], outs[1], rtol=1e-11, what="dmma vs simt")
 
 
+def test_generic_gemm_path_on_the_canonical_net(api):
+    """784-30-10 normally takes the fused small-network kernels; RCN_CUDA_SMALLNET=0 forces the generic tiled GEMM
+    path, which must meet the same bar."""
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+import mercer_research_b200 as m
+import oracle as O
+from conftest import assert_close
+model = m.RCN(10, [], [30]); model.load_weights_and_bias(784)
+net = O.Net(model.layer_shapes)
+params = np.random.default_rng(1).standard_normal(net.n_params) * 0.05
+model.set_params(params)
+X = np.maximum(np.random.default_rng(2).standard_normal((300, 784)), 0)
+labels = (np.arange(300) %% 10).astype(np.int64)
+want, grads = net.train_batch(params, X, np.eye(10)[labels], 3.0)
+model.train_batch(X, 3.0, labels=labels)
+assert_close(model.get_gradients(), grads, what="grads")
+assert_close(model.get_params(), want, what="params")
+print("ok")
+''' % ((os.path.dirname(os.path.dirname(os.path.abspath(__file__))),) * 2)
+    env = dict(os.environ, RCN_CUDA_SMALLNET="0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_full_pipeline_config_c2(api):
     """BASELINE.json configs[1]: MNIST-shaped CNN, batch 1024, images -> features -> fwd -> bwd -> SGD."""
     rng = np.random.default_rng(0x5EED)
