@@ -64,7 +64,9 @@ int rcn_cuda_create(size_t classes, const int32_t* convpool_cfg, size_t n_convpo
                     const size_t* feedforward_cfg, size_t n_feedforward, int device,
                     rcn_cuda_handle* out);
 int rcn_cuda_destroy(rcn_cuda_handle h);
-/* Run on an existing cudaStream_t (e.g. torch's current stream). NULL restores the model's own stream. */
+/* Run on an existing cudaStream_t (e.g. torch's current stream). NULL is the CUDA legacy default stream (what
+ * torch hands out as its default stream); RCN_STREAM_OWN restores the model's private non-blocking stream. */
+#define RCN_STREAM_OWN ((void*)(intptr_t)-1)
 int rcn_cuda_set_stream(rcn_cuda_handle h, void* cuda_stream);
 int rcn_cuda_synchronize(rcn_cuda_handle h);
 
@@ -133,6 +135,21 @@ int rcn_cuda_train_batch_images(rcn_cuda_handle h, const void* images, int pixel
 /* Optional per-batch metric of the last accumulate/train call, evaluated with the PRE-update parameters:
  * quadratic cost sum_b 0.5*|a_L - y|^2 and the rcn.rs:153-157 hit count. */
 int rcn_cuda_last_batch_stats(rcn_cuda_handle h, double* cost, uint64_t* hits);
+
+/* ---- epoch mode: the inner loop of RCN::train (rcn.rs:144-149) over a dataset resident in HBM ------------
+ * `for batch in training_set.chunks_exact(batch_size) { train_batch(batch, eta) }` with the batch selection done on
+ * the DEVICE: step k trains on samples perm[pos .. pos+B) (perm == NULL: identity), pos advances by B after each
+ * update and wraps to 0 once fewer than B samples remain (the remainder is dropped like chunks_exact does).
+ * Nothing about a step depends on host state, so one captured CUDA graph replays for every step of every epoch
+ * (re-shuffle by rewriting `perm` in place between epochs). All pointers must be DEVICE pointers and stay valid. */
+int rcn_cuda_epoch_bind(rcn_cuda_handle h, const void* images, int pixel_format, const int64_t* labels,
+                        const int64_t* perm, size_t n_samples, size_t H, size_t W, size_t B);
+int rcn_cuda_epoch_seek(rcn_cuda_handle h, size_t position);
+int rcn_cuda_epoch_position(rcn_cuda_handle h, size_t* position); /* synchronises the stream */
+/* accumulate: gradient sums of the current chunk into the gradient buffer; apply: update + advance. */
+int rcn_cuda_epoch_accumulate(rcn_cuda_handle h);
+int rcn_cuda_epoch_apply(rcn_cuda_handle h, double eta, size_t global_batch);
+int rcn_cuda_epoch_step(rcn_cuda_handle h, double eta); /* accumulate + apply with global_batch = B */
 
 /* Gradient buffer access for the data-parallel trainer. bind: use caller-owned DEVICE memory (e.g. a torch
  * tensor that NCCL all-reduces) as the flat gradient buffer; NULL restores the internal one. */

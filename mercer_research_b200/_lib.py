@@ -56,6 +56,12 @@ SIGNATURES = {
     "rcn_cuda_train_batch": [_vp, _vp, _vp, _vp, _sz, _d],
     "rcn_cuda_train_batch_images": [_vp, _vp, _i, _vp, _sz, _sz, _sz, _d],
     "rcn_cuda_last_batch_stats": [_vp, C.POINTER(_d), C.POINTER(C.c_uint64)],
+    "rcn_cuda_epoch_bind": [_vp, _vp, _i, _vp, _vp, _sz, _sz, _sz, _sz],
+    "rcn_cuda_epoch_seek": [_vp, _sz],
+    "rcn_cuda_epoch_position": [_vp, _szp],
+    "rcn_cuda_epoch_accumulate": [_vp],
+    "rcn_cuda_epoch_apply": [_vp, _d, _sz],
+    "rcn_cuda_epoch_step": [_vp, _d],
     "rcn_cuda_bind_gradient_buffer": [_vp, _vp, _sz],
     "rcn_cuda_gradient_buffer": [_vp, C.POINTER(_vp), _szp],
     "rcn_cuda_get_gradients": [_vp, _vp, _sz],

@@ -26,7 +26,9 @@ int launch_dense_backward_weight(const double* delta, const double* A_prev, size
                                  double* db, DevBuf& workspace, cudaStream_t stream);
 
 // params -= scale * grads   (rcn.rs:210-222, scale = eta / batch formed first)
-int launch_sgd_update(double* params, const double* grads, size_t n, double scale, cudaStream_t stream);
+// cursor (optional): device-side position of the epoch walk, advanced by `batch` with chunks_exact wrap-around.
+int launch_sgd_update(double* params, const double* grads, size_t n, double scale, cudaStream_t stream,
+                      long long* cursor = nullptr, long long batch = 0, long long n_samples = 0);
 
 // labels[b] = argmax_i acts[i, b], last maximal element wins (rcn.rs:92-97)
 int launch_argmax_last(const double* acts, size_t n, size_t B, int64_t* labels, cudaStream_t stream);

@@ -4,6 +4,8 @@
 // memory, the only global traffic is the image read and the feature write (H*W*s_in + L*8 B).
 #include "features.cuh"
 
+#include <cmath>
+
 namespace rcn {
 
 // ------------------------------------------------------------------------------------------------
@@ -67,153 +69,11 @@ int plan_features(const int32_t* cfg, size_t n_cfg, size_t H, size_t W, FeatureP
     return RCN_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// Device arithmetic.  mac(a, k, c) = c + a*k.  The taps are in {0, +-1, +-2}, so a*k is exact in f64 and a
-// fused multiply-add rounds exactly like the reference's separate multiply and add (kernel.rs:164).  Zero
-// taps are kept (inf*0 must stay NaN as in the reference); for T = int the compiler folds them away.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double mac(double a, double k, double c) { return fma(a, k, c); }
-__device__ __forceinline__ int mac(int a, int k, int c) { return a * k + c; }
+}  // namespace rcn
 
-template <typename T>
-__device__ __forceinline__ T relu1(T v) { return (v >= T(0)) ? v : T(0); }  // kernel.rs:214
+#include "features_device.cuh"
 
-// Pre-activation responses of the four operators (kernel.rs:38-53) at output pixel (y, x) of
-// convolve_2d(3x1, p) . convolve_2d(1x3, p)  (kernel.rs:204-205), f is one h x w column-major map.
-// SAME reproduces the reference's padded-copy quirk (kernel.rs:154-158): the result is the
-// Sobel response centred at (y-1, x-1); row 0 is zero; the last input column / last intermediate row are
-// never read.
-template <typename T, bool SAME>
-__device__ __forceinline__ void sobel4(const T* __restrict__ f, int h, int w, int y, int x, T& t, T& l, T& r, T& b) {
-    const T Z = T(0);
-    T ct[3], cb[3], cs[3];  // vertical passes with [1,0,-1], [-1,0,1], [1,2,1] at the three columns
-    if (SAME) {
-        if (y == 0) { t = l = r = b = Z; return; }
-        const int rr = y - 1;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int j = x + k - 2;
-            if (j >= 0 && j <= w - 2) {
-                const T* col = f + (size_t)j * h;
-                const T x0 = (rr >= 1) ? col[rr - 1] : Z;
-                const T x1 = col[rr];
-                const T x2 = col[rr + 1];
-                ct[k] = mac(x2, T(-1), mac(x1, T(0), mac(x0, T(1), Z)));
-                cb[k] = mac(x2, T(1), mac(x1, T(0), mac(x0, T(-1), Z)));
-                cs[k] = mac(x2, T(1), mac(x1, T(2), mac(x0, T(1), Z)));
-            } else {
-                ct[k] = cb[k] = cs[k] = Z;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const T* col = f + (size_t)(x + k) * h;
-            const T x0 = col[y], x1 = col[y + 1], x2 = col[y + 2];
-            ct[k] = mac(x2, T(-1), mac(x1, T(0), mac(x0, T(1), Z)));
-            cb[k] = mac(x2, T(1), mac(x1, T(0), mac(x0, T(-1), Z)));
-            cs[k] = mac(x2, T(1), mac(x1, T(2), mac(x0, T(1), Z)));
-        }
-    }
-    t = mac(ct[2], T(1), mac(ct[1], T(2), mac(ct[0], T(1), Z)));   // Top:    h = [1,2,1]
-    b = mac(cb[2], T(1), mac(cb[1], T(2), mac(cb[0], T(1), Z)));   // Bottom: h = [1,2,1]
-    l = mac(cs[2], T(-1), mac(cs[1], T(0), mac(cs[0], T(1), Z)));  // Left:   h = [1,0,-1]
-    r = mac(cs[2], T(1), mac(cs[1], T(0), mac(cs[0], T(-1), Z)));  // Right:  h = [-1,0,1]
-}
-
-template <typename T>
-__device__ __forceinline__ void sobel4_relu(const Stage& st, const T* __restrict__ f, int y, int x, T& t, T& l, T& r, T& b) {
-    if (st.same) sobel4<T, true>(f, st.h_in, st.w_in, y, x, t, l, r, b);
-    else sobel4<T, false>(f, st.h_in, st.w_in, y, x, t, l, r, b);
-    t = relu1(t); l = relu1(l); r = relu1(r); b = relu1(b);
-}
-
-// Iterator::max_by keeps the LAST maximal element (kernel.rs:278-281): replace unless strictly smaller.
-template <typename T>
-__device__ __forceinline__ void max_last(T& best, T v) { if (!(v < best)) best = v; }
-
-// Runs one stage for one image.  `in`: n_in maps (column-major each, back to back).  emit(slot, y, x, v).
-template <typename T, typename Emit>
-__device__ __forceinline__ void run_stage(const Stage& st, const T* __restrict__ in, Emit emit, int tid, int nthreads) {
-    const int hw_out = st.h_out * st.w_out;
-    const int hw_in = st.h_in * st.w_in;
-    const int items = st.n_in * hw_out;
-    for (int it = tid; it < items; it += nthreads) {
-        const int i = it / hw_out;
-        const int rem = it - i * hw_out;
-        const int x = rem / st.h_out;
-        const int y = rem - x * st.h_out;
-        const T* f = in + (size_t)i * hw_in;
-        if (st.kind == 2) {
-            // pool_2d(Padding::Same, Max): kernel.rs:245-349, zero row/col appended when odd.
-            T best = T(0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int cy = 2 * y + (q >> 1), cx = 2 * x + (q & 1);
-                const T v = (cy < st.h_in && cx < st.w_in) ? f[(size_t)cx * st.h_in + cy] : T(0);
-                if (q == 0) best = v; else max_last(best, v);
-            }
-            emit(i, y, x, best);
-            continue;
-        }
-        T t, l, r, b;
-        if (st.kind == 0) {
-            sobel4_relu<T>(st, f, y, x, t, l, r, b);
-        } else {
-            t = l = r = b = T(0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int cy = 2 * y + (q >> 1), cx = 2 * x + (q & 1);
-                T vt = T(0), vl = T(0), vr = T(0), vb = T(0);
-                if (cy < st.h_c && cx < st.w_c) sobel4_relu<T>(st, f, cy, cx, vt, vl, vr, vb);
-                if (q == 0) { t = vt; l = vl; r = vr; b = vb; }
-                else { max_last(t, vt); max_last(l, vl); max_last(r, vr); max_last(b, vb); }
-            }
-        }
-        // Slot order (rcn.rs:325-339): first conv -> [T,L,R,B]; later convs overwrite slot i with Bottom and
-        // append Top, Left, Right of map i at n + 3i.
-        int sT, sL, sR, sB;
-        if (st.first) { sT = 0; sL = 1; sR = 2; sB = 3; }
-        else { sB = i; sT = st.n_in + 3 * i; sL = sT + 1; sR = sT + 2; }
-        emit(sT, y, x, t); emit(sL, y, x, l); emit(sR, y, x, r); emit(sB, y, x, b);
-    }
-}
-
-template <typename T>
-struct EmitMaps {  // into a map set (shared or global), column-major maps back to back
-    T* out; int h, hw;
-    __device__ __forceinline__ void operator()(int slot, int y, int x, T v) const { out[(size_t)slot * hw + x * h + y] = v; }
-};
-
-template <typename T>
-struct EmitFeatures {  // final stage: flatten (rcn.rs:350-355) + optional standardise/clamp (rcn.rs:407-412)
-    double* out; int h, hw; bool standardise; double mean, sd;
-    __device__ __forceinline__ void operator()(int slot, int y, int x, T v) const {
-        double d = (double)v;
-        if (standardise) { d = (d - mean) / sd; d = (d >= 0.0) ? d : 0.0; }
-        out[(size_t)slot * hw + x * h + y] = d;
-    }
-};
-
-template <typename TIN, typename T>
-__device__ __forceinline__ void load_image(const TIN* __restrict__ src, T* dst, int H, int W, int tid, int nthreads);
-
-// u8 row-major (image crate) -> column-major T: DMatrix::from_row_iterator (lib.rs:29-33)
-template <>
-__device__ __forceinline__ void load_image<uint8_t, int>(const uint8_t* __restrict__ src, int* dst, int H, int W, int tid, int nthreads) {
-    const int n = H * W;
-    for (int i = tid; i < n; i += nthreads) { const int r = i / W, c = i - r * W; dst[c * H + r] = (int)src[i]; }
-}
-template <>
-__device__ __forceinline__ void load_image<uint8_t, double>(const uint8_t* __restrict__ src, double* dst, int H, int W, int tid, int nthreads) {
-    const int n = H * W;
-    for (int i = tid; i < n; i += nthreads) { const int r = i / W, c = i - r * W; dst[c * H + r] = (double)src[i]; }
-}
-template <>
-__device__ __forceinline__ void load_image<double, double>(const double* __restrict__ src, double* dst, int H, int W, int tid, int nthreads) {
-    const int n = H * W;
-    for (int i = tid; i < n; i += nthreads) dst[i] = src[i];
-}
+namespace rcn {
 
 // ------------------------------------------------------------------------------------------------
 // Fused path: whole convpool stack of one image in shared memory.
@@ -221,21 +81,23 @@ __device__ __forceinline__ void load_image<double, double>(const double* __restr
 template <typename TIN, typename T>
 __global__ void __launch_bounds__(256) features_fused_kernel(const TIN* __restrict__ images, int B, int H, int W,
                                                             const __grid_constant__ StageList sl, int buf_elems,
-                                                            double* __restrict__ out, size_t L, int standardise,
-                                                            double mean, double sd) {
+                                                            double* __restrict__ out, size_t L, const Standardise sc,
+                                                            const BatchIndex bi) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* buf0 = reinterpret_cast<T*>(smem_raw);
     T* buf1 = buf0 + buf_elems;
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int img = blockIdx.x; img < B; img += gridDim.x) {
-        load_image<TIN, T>(images + (size_t)img * H * W, buf0, H, W, tid, nt);
+        const size_t src = source_image(bi, (size_t)img);
+        if (tid == 0 && bi.labels_batch) bi.labels_batch[img] = bi.labels_all[src];
+        load_image<TIN, T>(images + src * H * W, buf0, H, W, tid, nt);
         __syncthreads();
         T* cur = buf0;
         T* nxt = buf1;
         for (int s = 0; s < sl.n; ++s) {
             const Stage& st = sl.s[s];
             if (s == sl.n - 1) {
-                EmitFeatures<T> e{out + (size_t)img * L, st.h_out, st.h_out * st.w_out, standardise != 0, mean, sd};
+                EmitFeatures<T> e{out + (size_t)img * L, st.h_out, st.h_out * st.w_out, sc};
                 run_stage<T>(st, cur, e, tid, nt);
             } else {
                 EmitMaps<T> e{nxt, st.h_out, st.h_out * st.w_out};
@@ -252,10 +114,14 @@ __global__ void __launch_bounds__(256) features_fused_kernel(const TIN* __restri
 // Layer-by-layer path (map sets too large for shared memory): same stage code over global buffers.
 // ------------------------------------------------------------------------------------------------
 template <typename TIN, typename T>
-__global__ void convert_images_kernel(const TIN* __restrict__ images, T* __restrict__ out, int H, int W, size_t B) {
-    for (size_t img = blockIdx.y; img < B; img += gridDim.y)
-        load_image<TIN, T>(images + img * H * W, out + img * H * W, H, W, blockIdx.x * blockDim.x + threadIdx.x,
+__global__ void convert_images_kernel(const TIN* __restrict__ images, T* __restrict__ out, int H, int W, size_t B,
+                                      const BatchIndex bi) {
+    for (size_t img = blockIdx.y; img < B; img += gridDim.y) {
+        const size_t src = source_image(bi, img);
+        if (blockIdx.x == 0 && threadIdx.x == 0 && bi.labels_batch) bi.labels_batch[img] = bi.labels_all[src];
+        load_image<TIN, T>(images + src * H * W, out + img * H * W, H, W, blockIdx.x * blockDim.x + threadIdx.x,
                            gridDim.x * blockDim.x);
+    }
 }
 
 template <typename T>
@@ -270,9 +136,9 @@ __global__ void __launch_bounds__(256) stage_maps_kernel(const __grid_constant__
 template <typename T>
 __global__ void __launch_bounds__(256) stage_final_kernel(const __grid_constant__ Stage st, const T* __restrict__ in,
                                                          size_t in_stride, double* __restrict__ out, size_t L,
-                                                         int standardise, double mean, double sd, size_t B) {
+                                                         const Standardise sc, size_t B) {
     for (size_t img = blockIdx.y; img < B; img += gridDim.y) {
-        EmitFeatures<T> e{out + img * L, st.h_out, st.h_out * st.w_out, standardise != 0, mean, sd};
+        EmitFeatures<T> e{out + img * L, st.h_out, st.h_out * st.w_out, sc};
         run_stage<T>(st, in + img * in_stride, e, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
     }
 }
@@ -280,8 +146,9 @@ __global__ void __launch_bounds__(256) stage_final_kernel(const __grid_constant_
 constexpr size_t kFusedSmemLimit = 200 * 1024;
 
 template <typename TIN, typename T>
-static int launch_features_t(const FeaturePlan& plan, const TIN* images, size_t B, size_t H, size_t W, bool standardise,
-                             double mean, double sd, double* out, FeatureScratch& scratch, cudaStream_t stream) {
+static int launch_features_t(const FeaturePlan& plan, const TIN* images, size_t B, size_t H, size_t W,
+                             const Standardise& sc, double* out, FeatureScratch& scratch, cudaStream_t stream,
+                             const BatchIndex& bi) {
     const StageList& sl = plan.stages;
     const size_t smem = 2 * plan.max_elems * sizeof(T);
     if (smem <= kFusedSmemLimit) {
@@ -294,7 +161,7 @@ static int launch_features_t(const FeaturePlan& plan, const TIN* images, size_t 
         size_t grid = (size_t)kNumSMs * per_sm;
         if (grid > B) grid = B;
         RCN_LAUNCH("features_fused_kernel", stream, kern<<<(unsigned)grid, 256, smem, stream>>>(images, (int)B, (int)H, (int)W, sl, (int)plan.max_elems, out, plan.L,
-                                                    standardise ? 1 : 0, mean, sd));
+                                                    sc, bi));
         return RCN_OK;
     }
     // layer-by-layer over global ping-pong buffers
@@ -311,7 +178,7 @@ static int launch_features_t(const FeaturePlan& plan, const TIN* images, size_t 
     {
         dim3 grid(cdiv(H * W, 256), (unsigned)(B > 32768 ? 32768 : B));
         if (grid.x > 64) grid.x = 64;
-        RCN_LAUNCH("convert_images_kernel", stream, convert_images_kernel<TIN, T><<<grid, 256, 0, stream>>>(images, cur, (int)H, (int)W, B));
+        RCN_LAUNCH("convert_images_kernel", stream, convert_images_kernel<TIN, T><<<grid, 256, 0, stream>>>(images, cur, (int)H, (int)W, B, bi));
     }
     for (int s = 0; s < sl.n; ++s) {
         const Stage& st = sl.s[s];
@@ -319,7 +186,7 @@ static int launch_features_t(const FeaturePlan& plan, const TIN* images, size_t 
         dim3 grid(cdiv(items, 256), (unsigned)(B > 32768 ? 32768 : B));
         if (grid.x > 1024) grid.x = 1024;
         if (s == sl.n - 1) {
-            RCN_LAUNCH("stage_final_kernel", stream, stage_final_kernel<T><<<grid, 256, 0, stream>>>(st, cur, cur_stride, out, plan.L, standardise ? 1 : 0, mean, sd, B));
+            RCN_LAUNCH("stage_final_kernel", stream, stage_final_kernel<T><<<grid, 256, 0, stream>>>(st, cur, cur_stride, out, plan.L, sc, B));
         } else {
             const size_t out_stride = (size_t)st.n_out * st.h_out * st.w_out;
             RCN_LAUNCH("stage_maps_kernel", stream, stage_maps_kernel<T><<<grid, 256, 0, stream>>>(st, cur, cur_stride, nxt, out_stride, B));
@@ -330,20 +197,58 @@ static int launch_features_t(const FeaturePlan& plan, const TIN* images, size_t 
     return RCN_OK;
 }
 
+// Host check that the 3-instruction Markstein division equals IEEE division for every integer feature value
+// 0..vmax with this (mean, sd): makes the fast epilogue provably bit-exact for the u8 pipeline.
+static bool standardise_fast_ok(double mean, double sd, long long vmax, double* rcp_out) {
+    if (!(sd > 0.0) || !std::isfinite(sd) || !std::isfinite(mean) || vmax > (1ll << 22)) return false;
+    const volatile double rcp_v = 1.0 / sd;
+    const double rcp = rcp_v;
+    for (long long v = 0; v <= vmax; ++v) {
+        const double a = (double)v - mean;
+        const volatile double exact = a / sd;
+        const volatile double q = a * rcp;
+        const double rem = std::fma(-q, sd, a);
+        const double fast = std::fma(rem, rcp, (double)q);
+        const double ex = exact;
+        if (std::memcmp(&fast, &ex, sizeof(double)) != 0) return false;
+    }
+    *rcp_out = rcp;
+    return true;
+}
+
+Standardise make_standardise(const FeaturePlan& plan, int pixel_format, bool standardise, double mean, double sd) {
+    Standardise sc{standardise ? 1 : 0, mean, sd, 0.0};
+    if (standardise && pixel_format == RCN_PIXELS_U8_ROWMAJOR && plan.n_conv <= 10) {
+        // cache of the last verified (mean, sd, vmax): set_scale is rare, steps are not
+        static thread_local double c_mean = 0, c_sd = 0, c_rcp = 0;
+        static thread_local long long c_vmax = -1;
+        static thread_local bool c_ok = false;
+        const long long vmax = 255ll << (2 * plan.n_conv);
+        if (!(c_vmax == vmax && c_mean == mean && c_sd == sd)) {
+            c_ok = standardise_fast_ok(mean, sd, vmax, &c_rcp);
+            c_mean = mean; c_sd = sd; c_vmax = vmax;
+        }
+        if (c_ok) { sc.mode = 2; sc.rcp = c_rcp; }
+    }
+    return sc;
+}
+
 int launch_features(const FeaturePlan& plan, const void* images, int pixel_format, size_t B, size_t H, size_t W,
                     bool standardise, double mean, double sd, double* out, FeatureScratch& scratch,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, const BatchIndex* index) {
+    const BatchIndex bi = index ? *index : BatchIndex{};
     if (B == 0 || plan.L == 0) return RCN_OK;  // no conv layer => empty feature vector (rcn.rs:323,339)
     if (B > ((size_t)1 << 30)) return fail(RCN_ERR_INVALID, "batch too large");
+    const Standardise sc = make_standardise(plan, pixel_format, standardise, mean, sd);
     if (pixel_format == RCN_PIXELS_U8_ROWMAJOR) {
         // u8 pixels: every intermediate is an integer bounded by 255 * 4^n_conv, so int32 arithmetic is exact
         // (and bit-identical to the reference's f64) up to 10 conv layers.
         if (plan.n_conv <= 10)
-            return launch_features_t<uint8_t, int>(plan, (const uint8_t*)images, B, H, W, standardise, mean, sd, out, scratch, stream);
-        return launch_features_t<uint8_t, double>(plan, (const uint8_t*)images, B, H, W, standardise, mean, sd, out, scratch, stream);
+            return launch_features_t<uint8_t, int>(plan, (const uint8_t*)images, B, H, W, sc, out, scratch, stream, bi);
+        return launch_features_t<uint8_t, double>(plan, (const uint8_t*)images, B, H, W, sc, out, scratch, stream, bi);
     }
     if (pixel_format == RCN_PIXELS_F64_COLMAJOR)
-        return launch_features_t<double, double>(plan, (const double*)images, B, H, W, standardise, mean, sd, out, scratch, stream);
+        return launch_features_t<double, double>(plan, (const double*)images, B, H, W, sc, out, scratch, stream, bi);
     return fail(RCN_ERR_INVALID, "unknown pixel format %d", pixel_format);
 }
 

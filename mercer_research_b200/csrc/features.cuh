@@ -38,10 +38,30 @@ struct FeatureScratch {
     DevBuf a, b;
 };
 
+// Standardise + clamp epilogue (rcn.rs:407-412). mode 0: off; 1: IEEE division; 2: host-verified exact fast division.
+struct Standardise {
+    int mode;
+    double mean, sd, rcp;
+};
+
+// Optional device-side indirection for epoch training (rcn.rs:144-149: the shuffled training set is walked in
+// chunks_exact(batch) steps): image b of this step is dataset image perm[*cursor + b] (perm == NULL: identity) and
+// its label is copied to labels_batch[b].  Everything is read on the device, so one captured CUDA graph replays
+// for every step of every epoch.
+struct BatchIndex {
+    const long long* cursor = nullptr;
+    const long long* perm = nullptr;
+    const long long* labels_all = nullptr;
+    long long* labels_batch = nullptr;
+};
+
+// Epilogue descriptor for a batch: picks the host-verified exact fast division when the input is u8.
+Standardise make_standardise(const FeaturePlan& plan, int pixel_format, bool standardise, double mean, double sd);
+
 // images: DEVICE pointer, B images in `pixel_format`; out: DEVICE L x B.
 int launch_features(const FeaturePlan& plan, const void* images, int pixel_format, size_t B, size_t H, size_t W,
                     bool standardise, double mean, double sd, double* out, FeatureScratch& scratch,
-                    cudaStream_t stream);
+                    cudaStream_t stream, const BatchIndex* index = nullptr);
 
 int launch_standardise(double* feats, size_t n, double mean, double sd, cudaStream_t stream);
 // Deterministic two-pass mean / population-sd; result[0]=mean, result[1]=sd (device), needs scratch.

@@ -87,7 +87,14 @@ struct rcn_cuda_model {
     FeatureScratch fscratch;
 
     // scratch (grow-only)
-    DevBuf in_stage, tgt_stage, feats, acts, deltas, gemm_ws, out_stage, small, red_ws;
+    DevBuf in_stage, tgt_stage, feats, acts, deltas, gemm_ws, out_stage, small, red_ws, sn_counters;
+    // epoch mode (rcn.rs:144-149 on a resident dataset)
+    const void* ep_images = nullptr;
+    const int64_t* ep_labels = nullptr;
+    const int64_t* ep_perm = nullptr;
+    int ep_fmt = 0;
+    size_t ep_n = 0, ep_H = 0, ep_W = 0, ep_B = 0;
+    DevBuf ep_state;            // [cursor (int64) | pad | labels_batch (B x int64)]
     size_t last_B = 0;          // batch of the last accumulate call (taps)
     bool stats_valid = false;
 
@@ -166,7 +173,8 @@ int forward_dev(rcn_cuda_model* h, const double* feats, size_t B, const double* 
     RCN_TRY(h->acts.reserve(h->sum_rows * B * sizeof(double)));
     if (want_delta) RCN_TRY(h->deltas.reserve(h->sum_rows * B * sizeof(double)));
     if (h->use_small && !want_delta)
-        return launch_smallnet_forward(h->small_desc, h->params.as<double>(), feats, B, h->acts.as<double>(), h->stream);
+        return launch_smallnet_forward(h->small_desc, h->params.as<double>(), const_cast<double*>(feats), B,
+                                       h->acts.as<double>(), nullptr, h->stream);
     for (size_t l = 0; l < n; ++l) {
         const double* a_in = l == 0 ? feats : h->act(l - 1, B);
         const bool last = (l + 1 == n);
@@ -177,23 +185,25 @@ int forward_dev(rcn_cuda_model* h, const double* feats, size_t B, const double* 
     return RCN_OK;
 }
 
-int accumulate_dev(rcn_cuda_model* h, const double* feats, const double* onehot, const int64_t* labels, size_t B) {
+int accumulate_dev(rcn_cuda_model* h, const double* feats, const double* onehot, const int64_t* labels, size_t B,
+                   const SmallNetFront* front = nullptr) {
     const size_t n = h->rows.size();
     if (B == 0) {
         RCN_CUDA_TRY(cudaMemsetAsync(h->grads, 0, h->n_params * sizeof(double), h->stream));
         return RCN_OK;
     }
-    if (h->use_small) {
+    if (h->use_small && B <= smallnet_max_batch()) {
         RCN_TRY(h->acts.reserve(h->sum_rows * B * sizeof(double)));
         RCN_TRY(h->deltas.reserve(h->sum_rows * B * sizeof(double)));
         RCN_TRY(h->small.reserve(64));
-        RCN_TRY(launch_smallnet_backprop(h->small_desc, h->params.as<double>(), feats, B, onehot, labels,
-                                         h->acts.as<double>(), h->deltas.as<double>(), h->grads, h->small.as<double>(),
-                                         h->gemm_ws, h->stream));
+        RCN_TRY(launch_smallnet_backprop(h->small_desc, h->params.as<double>(), const_cast<double*>(feats), B, onehot,
+                                         labels, h->acts.as<double>(), h->deltas.as<double>(), h->grads,
+                                         h->small.as<double>(), h->gemm_ws, front, h->stream));
         h->stats_valid = true;
         h->last_B = B;
         return RCN_OK;
     }
+    if (front) return fail(RCN_ERR_STATE, "internal: fused front end requested on the generic path");
     RCN_TRY(forward_dev(h, feats, B, onehot, labels, true));
     for (size_t l = n - 1; l-- > 0;)  // rcn.rs:305-311
         RCN_TRY(launch_dense_backward_data(h->params.as<double>() + h->w_off[l + 1], h->delta(l + 1, B), h->act(l, B),
@@ -208,6 +218,31 @@ int accumulate_dev(rcn_cuda_model* h, const double* feats, const double* onehot,
     h->stats_valid = true;
     h->last_B = B;
     return RCN_OK;
+}
+
+// images (DEVICE) -> gradient sums.  The canonical narrow network with u8 pixels runs the convpool stack inside
+// kernel A (smallnet.cu); everything else runs the feature kernel(s) first.  `bi` (optional) is the epoch-mode
+// device-side batch selection; without it `labels` are this batch's labels.
+int accumulate_images_dev(rcn_cuda_model* h, const void* images, int fmt, const int64_t* labels, size_t B, size_t H,
+                          size_t W, const BatchIndex* bi) {
+    RCN_TRY(h->feats.reserve(h->plan.L * B * sizeof(double)));
+    const int64_t* step_labels = bi ? (const int64_t*)bi->labels_batch : labels;
+    static const bool fuse_env = []() { const char* e = getenv("RCN_CUDA_FUSED_FRONT"); return !(e && e[0] == '0'); }();
+    if (fuse_env && h->use_small && B <= smallnet_max_batch() && fmt == RCN_PIXELS_U8_ROWMAJOR && h->plan.n_conv <= 10 &&
+        h->plan.L > 0) {
+        SmallNetFront fr{};
+        fr.images = (const uint8_t*)images;
+        fr.H = (int)H; fr.W = (int)W;
+        fr.max_elems = (int)h->plan.max_elems;
+        fr.stages = h->plan.stages;
+        fr.sc = make_standardise(h->plan, fmt, true, h->mean, h->sd);
+        if (bi) fr.bi = *bi;
+        if (smallnet_front_fits(h->small_desc, fr))
+            return accumulate_dev(h, h->feats.as<double>(), nullptr, step_labels, B, &fr);
+    }
+    RCN_TRY(launch_features(h->plan, images, fmt, B, H, W, true, h->mean, h->sd, h->feats.as<double>(), h->fscratch,
+                            h->stream, bi));
+    return accumulate_dev(h, h->feats.as<double>(), nullptr, step_labels, B);
 }
 
 // stage targets (exactly one of onehot / labels)
@@ -284,7 +319,7 @@ int rcn_cuda_destroy(rcn_cuda_handle h) {
     cudaStreamSynchronize(h->stream);
     if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
     DevBuf* bufs[] = {&h->params, &h->grads_own, &h->in_stage, &h->tgt_stage, &h->feats, &h->acts, &h->deltas,
-                      &h->gemm_ws, &h->out_stage, &h->small, &h->red_ws, &h->fscratch.a, &h->fscratch.b};
+                      &h->gemm_ws, &h->out_stage, &h->small, &h->red_ws, &h->ep_state, &h->sn_counters, &h->fscratch.a, &h->fscratch.b};
     for (DevBuf* b : bufs) b->release();
     delete h;
     return RCN_OK;
@@ -292,7 +327,7 @@ int rcn_cuda_destroy(rcn_cuda_handle h) {
 
 int rcn_cuda_set_stream(rcn_cuda_handle h, void* cuda_stream) {
     RCN_ENTER(h);
-    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    h->stream = (cuda_stream == RCN_STREAM_OWN) ? h->own_stream : (cudaStream_t)cuda_stream;
     return RCN_OK;
 }
 
@@ -594,10 +629,15 @@ int rcn_cuda_accumulate_gradients_images(rcn_cuda_handle h, const void* images, 
     if (B) {
         if (!labels) return fail(RCN_ERR_INVALID, "null labels");
         RCN_TRY(stage_targets(h, nullptr, labels, B, &oh, &lb));
-        RCN_TRY(h->feats.reserve(h->plan.L * B * sizeof(double)));
-        RCN_TRY(features_into(h, images, pixel_format, B, H, W, true, h->feats.as<double>()));
+        if (pixel_format != RCN_PIXELS_U8_ROWMAJOR && pixel_format != RCN_PIXELS_F64_COLMAJOR)
+            return fail(RCN_ERR_INVALID, "unknown pixel format %d", pixel_format);
+        if (!images) return fail(RCN_ERR_INVALID, "null images");
+        StagedIn in;
+        RCN_TRY(in.stage(images, B * H * W * pixel_bytes(pixel_format), h->in_stage, h->stream, nullptr));
+        RCN_TRY(accumulate_images_dev(h, in.dev, pixel_format, lb, B, H, W, nullptr));
+    } else {
+        RCN_TRY(accumulate_dev(h, nullptr, nullptr, nullptr, 0));
     }
-    RCN_TRY(accumulate_dev(h, h->feats.as<double>(), oh, lb, B));
     if (B && (!is_device_ptr(images) || !is_device_ptr(labels))) RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
     return RCN_OK;
 }
@@ -631,6 +671,72 @@ int rcn_cuda_last_batch_stats(rcn_cuda_handle h, double* cost, uint64_t* hits) {
     if (cost) *cost = host[0];
     if (hits) memcpy(hits, &host[1], sizeof(uint64_t));
     return RCN_OK;
+}
+
+int rcn_cuda_epoch_bind(rcn_cuda_handle h, const void* images, int pixel_format, const int64_t* labels,
+                        const int64_t* perm, size_t n_samples, size_t H, size_t W, size_t B) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (!images || !labels || B == 0 || n_samples < B) return fail(RCN_ERR_INVALID, "epoch_bind needs images, labels and n_samples >= B > 0");
+    if (!is_device_ptr(images) || !is_device_ptr(labels) || (perm && !is_device_ptr(perm)))
+        return fail(RCN_ERR_INVALID, "epoch mode needs a dataset resident in device memory");
+    if (pixel_format != RCN_PIXELS_U8_ROWMAJOR && pixel_format != RCN_PIXELS_F64_COLMAJOR)
+        return fail(RCN_ERR_INVALID, "unknown pixel format %d", pixel_format);
+    RCN_TRY(ensure_plan(h, H, W));
+    RCN_TRY(check_feature_width(h, h->plan.L));
+    RCN_TRY(h->ep_state.reserve((2 + B) * sizeof(int64_t)));
+    RCN_CUDA_TRY(cudaMemsetAsync(h->ep_state.p, 0, (2 + B) * sizeof(int64_t), h->stream));
+    RCN_TRY(h->feats.reserve(h->plan.L * B * sizeof(double)));
+    h->ep_images = images; h->ep_labels = labels; h->ep_perm = perm; h->ep_fmt = pixel_format;
+    h->ep_n = n_samples; h->ep_H = H; h->ep_W = W; h->ep_B = B;
+    return RCN_OK;
+}
+
+int rcn_cuda_epoch_seek(rcn_cuda_handle h, size_t position) {
+    RCN_ENTER(h);
+    if (!h->ep_images) return fail(RCN_ERR_STATE, "no dataset bound: call rcn_cuda_epoch_bind first");
+    if (position + h->ep_B > h->ep_n) return fail(RCN_ERR_INVALID, "position %zu leaves fewer than B samples", position);
+    const long long pos = (long long)position;
+    RCN_CUDA_TRY(cudaMemcpyAsync(h->ep_state.p, &pos, sizeof(pos), cudaMemcpyHostToDevice, h->stream));
+    RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return RCN_OK;
+}
+
+int rcn_cuda_epoch_position(rcn_cuda_handle h, size_t* position) {
+    RCN_ENTER(h);
+    if (!h->ep_images || !position) return fail(RCN_ERR_STATE, "no dataset bound / null output");
+    long long pos = 0;
+    RCN_CUDA_TRY(cudaMemcpyAsync(&pos, h->ep_state.p, sizeof(pos), cudaMemcpyDeviceToHost, h->stream));
+    RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *position = (size_t)pos;
+    return RCN_OK;
+}
+
+int rcn_cuda_epoch_accumulate(rcn_cuda_handle h) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (!h->ep_images) return fail(RCN_ERR_STATE, "no dataset bound: call rcn_cuda_epoch_bind first");
+    BatchIndex bi;
+    bi.cursor = h->ep_state.as<long long>();
+    bi.perm = (const long long*)h->ep_perm;
+    bi.labels_all = (const long long*)h->ep_labels;
+    bi.labels_batch = h->ep_state.as<long long>() + 2;
+    return accumulate_images_dev(h, h->ep_images, h->ep_fmt, nullptr, h->ep_B, h->ep_H, h->ep_W, &bi);
+}
+
+int rcn_cuda_epoch_apply(rcn_cuda_handle h, double eta, size_t global_batch) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (!h->ep_images) return fail(RCN_ERR_STATE, "no dataset bound: call rcn_cuda_epoch_bind first");
+    if (global_batch == 0) return fail(RCN_ERR_INVALID, "global batch is zero");
+    const double scale = eta / (double)global_batch;
+    return launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale, h->stream, h->ep_state.as<long long>(),
+                             (long long)h->ep_B, (long long)h->ep_n);
+}
+
+int rcn_cuda_epoch_step(rcn_cuda_handle h, double eta) {
+    RCN_TRY(rcn_cuda_epoch_accumulate(h));
+    return rcn_cuda_epoch_apply(h, eta, h->ep_B);
 }
 
 int rcn_cuda_bind_gradient_buffer(rcn_cuda_handle h, double* device_ptr, size_t n) {

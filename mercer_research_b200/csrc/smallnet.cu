@@ -1,21 +1,28 @@
 // smallnet.cu -- fused training step for rcn's canonical network family: one wide input layer (n_in = feature
 // length, e.g. 784) into narrow sigmoid layers (every layer width <= 32, e.g. 784-30-10, main.rs:51-62).
 //
-// Reference: rcn/src/rcn.rs:260-314 (backprop), :176-223 (batch sum), :105-116 (forward), :152-157 (accuracy).
-// At these sizes the generic tiled GEMMs of dense.cu are launch/latency bound (M = 30 or 10), so the whole
-// backprop of a minibatch runs as three kernels with no shared-memory operand staging at all:
+// Reference: rcn/src/rcn.rs:317-356 + 407-412 (features), :260-314 (backprop), :176-223 (batch sum), :105-116
+// (forward), :152-157 (accuracy).  At these sizes the generic tiled GEMMs of dense.cu are launch/latency bound
+// (M = 30 or 10), so a whole minibatch runs as TWO kernels (plus the SGD update):
 //
-//   A  smallnet_fwd_bwd_kernel    one CTA per 8 samples.  z1 = W1 a0 on the f64 tensor path (DMMA.8x8x4): each of the
-//                                 8 warps owns a K-range of the 784-deep contraction and streams its W1 / a0
-//                                 fragments straight from L2 into registers; partial sums meet in 16 KB of shared
-//                                 memory; the narrow layers, the output delta, the backward-data chain and the
-//                                 batch statistics finish in registers/shared memory.  Writes a_l, delta_l.
-//   B  smallnet_wgrad_kernel      dW1 = Delta1 A0^T split over (64-column group, K-split of the batch): DMMA again,
-//                                 operands straight from L2; an extra CTA per K-split does db1 and the narrow
-//                                 layers' dW/db.  Writes per-split partial gradient vectors.
-//   C  smallnet_reduce_kernel     sums the K-split partials in a fixed order into the flat gradient buffer (the
-//                                 all-reduce target) and finalises the batch statistics.
+//   A  smallnet_fwd_bwd_kernel   one 16-warp CTA per 8 samples.
+//        (fused front end, u8 images) two warps per image run the convpool stack in shared memory with exact
+//        int32 arithmetic and write the standardised feature vector both to HBM (kernel B reads it) and into a
+//        padded shared-memory tile;
+//        z1 = W1 a0 on the f64 tensor path (DMMA.8x8x4): each warp owns a K-range of the 784-deep contraction,
+//        streams its W1 fragments straight from L2 into registers and reads the a0 fragments from the tile;
+//        partial sums meet in shared memory; the narrow layers (weights prefetched to shared memory), the output
+//        delta, the backward-data chain and the batch statistics finish on chip.  Writes a_l, delta_l.
+//   B  smallnet_wgrad_kernel     dW1 = Delta1 A0^T over (64-column group) x (K-split of the batch): the Delta1 slice
+//        is staged once in shared memory, the A0 fragments stream from L2 with 16 loads in flight per lane, DMMA
+//        again; one extra CTA per K-split does db1 and the narrow layers' dW/db.  The last CTA of each column
+//        group to finish (atomic ticket) sums the K-split partials in a FIXED order into the flat gradient buffer
+//        (the all-reduce target) -- deterministic, unlike the reference's mutex-ordered sum (rcn.rs:190-205).
 #include "smallnet.cuh"
+
+#include "features_device.cuh"
+
+#include <cooperative_groups.h>
 
 namespace rcn {
 
@@ -27,58 +34,137 @@ __device__ __forceinline__ void sn_dmma(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-constexpr int SN_TB = 8;        // samples per CTA in kernel A (one DMMA n-fragment)
-constexpr int SN_THREADS = 256;
-constexpr int SN_WARPS = 8;
+constexpr int SN_TB = 8;          // samples per CTA in kernel A (one DMMA n-fragment)
+constexpr int SNA_THREADS = 512;  // kernel A
+constexpr int SNA_WARPS = 16;
+constexpr int SNB_THREADS = 256;  // kernel B
+constexpr int SN_TILE_PAD = 4;    // a0 tile row pitch = n_in + 4 doubles: conflict-free B-fragment reads
+constexpr int SN_DPITCH = 36;     // delta slice row pitch (doubles): conflict-free A-fragment reads
+constexpr int SN_MAX_SMALL = 32 + (kSmallNetMaxLayers - 1) * (32 * 32 + 32);  // params after W0
+
+// final-stage emit of the fused front end: standardised feature -> shared tile + HBM
+struct EmitTile {
+    double* tile; double* gout; int h, hw; Standardise sc;
+    __device__ __forceinline__ void operator()(int slot, int y, int x, int v) const {
+        double d = (double)v;
+        if (sc.mode == 1) {
+            d = (d - sc.mean) / sc.sd;
+            d = (d >= 0.0) ? d : 0.0;
+        } else if (sc.mode == 2) {  // host-verified exact Markstein division, see EmitFeatures
+            const double a = d - sc.mean;
+            const double q = __dmul_rn(a, sc.rcp);
+            const double rem = fma(-q, sc.sd, a);
+            d = fma(rem, sc.rcp, q);
+            d = (d >= 0.0) ? d : 0.0;
+        }
+        const int idx = slot * hw + x * h + y;
+        tile[idx] = d;
+        gout[idx] = d;
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // Kernel A
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SN_THREADS) smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d,
-                                                                      const double* __restrict__ params,
-                                                                      const double* __restrict__ feats, int B,
-                                                                      const double* __restrict__ onehot,
-                                                                      const int64_t* __restrict__ labels,
-                                                                      double* __restrict__ acts, double* __restrict__ deltas,
-                                                                      double* __restrict__ stats_partial, int backward) {
-    __shared__ double zpart[SN_WARPS][32][SN_TB];           // per-warp partial z1 (16 KB)
-    __shared__ double s_act[kSmallNetMaxLayers][SN_TB][33]; // a_l for this CTA's samples
+template <bool FUSED>
+__global__ void __launch_bounds__(SNA_THREADS, 1)
+smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __restrict__ params,
+                        double* __restrict__ feats, int B, const double* __restrict__ onehot,
+                        const int64_t* __restrict__ labels, double* __restrict__ acts, double* __restrict__ deltas,
+                        double* __restrict__ stats_partial, int backward, const __grid_constant__ SmallNetFront fr) {
+    extern __shared__ __align__(16) unsigned char sn_smem[];
+    double* zpart = reinterpret_cast<double*>(sn_smem);                 // [16][32][8]
+    double* s_small = zpart + SNA_WARPS * 32 * SN_TB;                   // params after W0: b0 | W1 | b1 | ...
+    double* tile = s_small + SN_MAX_SMALL;                              // FUSED: [8][n_in + 4]
+    __shared__ double s_act[kSmallNetMaxLayers][SN_TB][33];
     __shared__ double s_del[kSmallNetMaxLayers][SN_TB][33];
     __shared__ double s_cost[SN_TB];
     __shared__ unsigned long long s_hit[SN_TB];
+    __shared__ long long s_label[SN_TB];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int s0 = blockIdx.x * SN_TB;
     const int L = d.n_in, R0 = d.rows[0];
     const int mf = (R0 + 7) >> 3;
+    const int pitch = L + SN_TILE_PAD;
+    const int small_base = d.b_off[0];
+    const int n_small = d.n_params - small_base;
 
-    // ---- layer 0: z = W0 a0 on DMMA, K split across warps ------------------------------------------------------
+    // prefetch biases + narrow-layer weights (overlaps with the front end / the DMMA phase)
+    for (int i = tid; i < n_small; i += SNA_THREADS) s_small[i] = __ldg(params + small_base + i);
+
+    if (FUSED) {
+        // ---- fused front end: two warps per image --------------------------------------------------------------
+        int* bufs = reinterpret_cast<int*>(tile + SN_TB * pitch);
+        const int n_img = tid >> 6, lt = tid & 63;
+        const int sample = s0 + n_img;
+        const bool live = sample < B;
+        int* buf0 = bufs + (size_t)n_img * 2 * fr.max_elems;
+        int* buf1 = buf0 + fr.max_elems;
+        double* trow = tile + (size_t)n_img * pitch;
+        if (live) {
+            const size_t src = source_image(fr.bi, (size_t)sample);
+            if (lt == 0) {
+                const long long lab = fr.bi.cursor ? fr.bi.labels_all[src] : (labels ? labels[sample] : 0);
+                s_label[n_img] = lab;
+                if (fr.bi.labels_batch) fr.bi.labels_batch[sample] = lab;
+            }
+            load_image<uint8_t, int>(fr.images + src * fr.H * fr.W, buf0, fr.H, fr.W, lt, 64);
+        } else {
+            for (int i = lt; i < pitch; i += 64) trow[i] = 0.0;
+            if (lt == 0) s_label[n_img] = -1;
+        }
+        __syncthreads();
+        int* cur = buf0;
+        int* nxt = buf1;
+        for (int s = 0; s < fr.stages.n; ++s) {
+            const Stage& st = fr.stages.s[s];
+            if (live) {
+                if (s == fr.stages.n - 1) {
+                    EmitTile e{trow, feats + (size_t)sample * L, st.h_out, st.h_out * st.w_out, fr.sc};
+                    run_stage<int>(st, cur, e, lt, 64);
+                } else {
+                    EmitMaps<int> e{nxt, st.h_out, st.h_out * st.w_out};
+                    run_stage<int>(st, cur, e, lt, 64);
+                }
+            }
+            __syncthreads();
+            int* tmp = cur; cur = nxt; nxt = tmp;
+        }
+    } else {
+        if (tid < SN_TB) s_label[tid] = (labels && s0 + tid < B) ? labels[s0 + tid] : -1;
+    }
+
+    // ---- layer 0: z = W0 a0 on DMMA, K split across the 16 warps ----------------------------------------------------
     {
         const double* __restrict__ W0 = params + d.w_off[0];
         const int ksteps = (L + 3) >> 2;
-        const int per = (ksteps + SN_WARPS - 1) / SN_WARPS;
+        const int per = (ksteps + SNA_WARPS - 1) / SNA_WARPS;
         const int ks_begin = warp * per;
         const int ks_end = min(ksteps, ks_begin + per);
         double acc[4][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.0;
+        bool rowok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rowok[i] = (i < mf) && (i * 8 + g < R0);
         const int sample = s0 + g;
         const bool sample_ok = sample < B;
         const double* __restrict__ frow = feats + (size_t)(sample_ok ? sample : 0) * L;
-        constexpr int U = 4;
+        const double* trow = tile + (size_t)g * pitch;
+        constexpr int U = 7;
         for (int ks = ks_begin; ks < ks_end; ks += U) {
             double af[U][4], bf[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int k = (ks + u) * 4 + t;
                 const bool kok = (ks + u) < ks_end && k < L;
-                bf[u] = (kok && sample_ok) ? __ldg(frow + k) : 0.0;           // B frag: row t (k), col g (sample)
+                const double* wp = W0 + (size_t)k * R0 + g;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int m = i * 8 + g;
-                    af[u][i] = (kok && i < mf && m < R0) ? __ldg(W0 + (size_t)k * R0 + m) : 0.0;  // A frag: row g (m), col t (k)
-                }
+                for (int i = 0; i < 4; ++i) af[u][i] = (kok && rowok[i]) ? __ldg(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
+                if (FUSED) bf[u] = kok ? trow[k] : 0.0;                                        // B frag: row t (k), col g (sample)
+                else bf[u] = (kok && sample_ok) ? __ldg(frow + k) : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
@@ -88,12 +174,15 @@ __global__ void __launch_bounds__(SN_THREADS) smallnet_fwd_bwd_kernel(const __gr
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {  // C frag: row g (m), cols 2t, 2t+1 (sample)
-            zpart[warp][i * 8 + g][2 * t] = acc[i][0];
-            zpart[warp][i * 8 + g][2 * t + 1] = acc[i][1];
+            zpart[(warp * 32 + i * 8 + g) * SN_TB + 2 * t] = acc[i][0];
+            zpart[(warp * 32 + i * 8 + g) * SN_TB + 2 * t + 1] = acc[i][1];
         }
     }
     __syncthreads();
+    if (tid >= 32 * SN_TB) return;   // the narrow part needs one thread per (sample, neuron); no barriers below use the rest
 
+    // NOTE: only warps 0..7 continue; they synchronise with a named barrier of 256 threads.
+#define SN_BAR() asm volatile("bar.sync 1, 256;" ::: "memory")
     const int n = tid >> 5;       // sample within the tile
     const int m = tid & 31;       // neuron
     const int sample = s0 + n;
@@ -101,24 +190,29 @@ __global__ void __launch_bounds__(SN_THREADS) smallnet_fwd_bwd_kernel(const __gr
     {
         double z = 0.0;
 #pragma unroll
-        for (int w = 0; w < SN_WARPS; ++w) z += zpart[w][m][n];
+        for (int w = 0; w < SNA_WARPS; ++w) z += zpart[(w * 32 + m) * SN_TB + n];
         if (m < R0) {
-            z = z + params[d.b_off[0] + m];             // w * a + b      (rcn.rs:287)
+            z = z + s_small[m];                         // w * a + b      (rcn.rs:287)
             s_act[0][n][m] = sn_sigmoid(z);             // sigmoid(&z)    (rcn.rs:289)
         }
     }
-    __syncthreads();
+    SN_BAR();
     // ---- narrow layers ---------------------------------------------------------------------------------------------
     for (int l = 1; l < d.n_layers; ++l) {
         const int R = d.rows[l], C = d.rows[l - 1];
         if (m < R) {
-            const double* __restrict__ W = params + d.w_off[l];
-            double z = 0.0;
-            for (int k = 0; k < C; ++k) z = fma(W[(size_t)k * R + m], s_act[l - 1][n][k], z);
-            z = z + params[d.b_off[l] + m];
+            const double* W = s_small + (d.w_off[l] - small_base);
+            double z0 = 0.0, z1 = 0.0;
+            int k = 0;
+            for (; k + 1 < C; k += 2) {
+                z0 = fma(W[k * R + m], s_act[l - 1][n][k], z0);
+                z1 = fma(W[(k + 1) * R + m], s_act[l - 1][n][k + 1], z1);
+            }
+            if (k < C) z0 = fma(W[k * R + m], s_act[l - 1][n][k], z0);
+            const double z = (z0 + z1) + s_small[d.b_off[l] - small_base + m];
             s_act[l][n][m] = sn_sigmoid(z);
         }
-        __syncthreads();
+        SN_BAR();
     }
     const int last = d.n_layers - 1;
     const int RL = d.rows[last];
@@ -133,7 +227,7 @@ __global__ void __launch_bounds__(SN_THREADS) smallnet_fwd_bwd_kernel(const __gr
     if (!backward) return;
     // ---- output delta (rcn.rs:299) and batch statistics (rcn.rs:152-157) --------------------------------------------
     double y = 0.0;
-    if (m < RL && live) y = onehot ? onehot[(size_t)sample * RL + m] : ((labels[sample] == (int64_t)m) ? 1.0 : 0.0);
+    if (m < RL && live) y = onehot ? onehot[(size_t)sample * RL + m] : ((s_label[n] == (long long)m) ? 1.0 : 0.0);
     if (m < RL) {
         const double a = s_act[last][n][m];
         s_del[last][n][m] = (a - y) * (a * (1.0 - a));
@@ -146,7 +240,7 @@ __global__ void __launch_bounds__(SN_THREADS) smallnet_fwd_bwd_kernel(const __gr
             for (int i = 1; i < RL; ++i) mx = fmax(mx, s_act[last][n][i]);
             bool ok = true;
             for (int i = 0; i < RL; ++i) {
-                const double yi = onehot ? onehot[(size_t)sample * RL + i] : ((labels[sample] == (int64_t)i) ? 1.0 : 0.0);
+                const double yi = onehot ? onehot[(size_t)sample * RL + i] : ((s_label[n] == (long long)i) ? 1.0 : 0.0);
                 const double a = s_act[last][n][i];
                 const double df = a - yi;
                 cost += df * df;
@@ -158,18 +252,23 @@ __global__ void __launch_bounds__(SN_THREADS) smallnet_fwd_bwd_kernel(const __gr
         s_cost[n] = cost;
         s_hit[n] = hit;
     }
-    __syncthreads();
+    SN_BAR();
     // ---- backward-data chain (rcn.rs:305-309) -------------------------------------------------------------------------
     for (int l = last - 1; l >= 0; --l) {
         const int R = d.rows[l], Ru = d.rows[l + 1];
         if (m < R) {
-            const double* __restrict__ Wu = params + d.w_off[l + 1];  // Ru x R column-major: (k, m) at m*Ru + k
-            double v = 0.0;
-            for (int k = 0; k < Ru; ++k) v = fma(Wu[(size_t)m * Ru + k], s_del[l + 1][n][k], v);
+            const double* Wu = s_small + (d.w_off[l + 1] - small_base);  // Ru x R column-major: (k, m) at m*Ru + k
+            double v0 = 0.0, v1 = 0.0;
+            int k = 0;
+            for (; k + 1 < Ru; k += 2) {
+                v0 = fma(Wu[m * Ru + k], s_del[l + 1][n][k], v0);
+                v1 = fma(Wu[m * Ru + k + 1], s_del[l + 1][n][k + 1], v1);
+            }
+            if (k < Ru) v0 = fma(Wu[m * Ru + k], s_del[l + 1][n][k], v0);
             const double a = s_act[l][n][m];
-            s_del[l][n][m] = v * (a * (1.0 - a));
+            s_del[l][n][m] = (v0 + v1) * (a * (1.0 - a));
         }
-        __syncthreads();
+        SN_BAR();
     }
     {
         size_t off = 0;
@@ -185,104 +284,193 @@ __global__ void __launch_bounds__(SN_THREADS) smallnet_fwd_bwd_kernel(const __gr
         stats_partial[2 * blockIdx.x] = c;
         reinterpret_cast<unsigned long long*>(stats_partial)[2 * blockIdx.x + 1] = h;
     }
+#undef SN_BAR
 }
 
 // ------------------------------------------------------------------------------------------------
-// Kernel B: per-K-split partial gradients.  blockIdx.x < col_groups: 64 columns of dW0 (one n-fragment per warp);
-// blockIdx.x == col_groups: db0 and the narrow layers.  blockIdx.y = K-split (a range of `ksplit` samples).
+// Kernel B: dW/db.  grid = (col_groups + 1, S) launched as thread-block CLUSTERS of (1, S, 1): the S CTAs of a
+// cluster own the same 64 columns of dW0 (or, for blockIdx.x == col_groups, db0 + the narrow layers) and one K-split
+// of the batch each.  Every CTA leaves its partial tile in its own shared memory; after a cluster barrier each rank
+// sums 1/S of the tile over all S ranks through distributed shared memory, in rank order (deterministic), and
+// writes the flat gradient buffer.  No partials ever touch L2/HBM.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SN_THREADS) smallnet_wgrad_kernel(const __grid_constant__ SmallNetDesc d,
-                                                                    const double* __restrict__ feats,
-                                                                    const double* __restrict__ acts,
-                                                                    const double* __restrict__ deltas, int B, int ksplit,
-                                                                    int col_groups, double* __restrict__ partial) {
+constexpr int SNB_TILE = 32 * 64;   // padded partial tile: 32 rows x 64 columns
+
+__global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __grid_constant__ SmallNetDesc d,
+                                                                     const double* __restrict__ feats,
+                                                                     const double* __restrict__ acts,
+                                                                     const double* __restrict__ deltas, int B, int ksplit,
+                                                                     int col_groups, double* __restrict__ grads,
+                                                                     const double* __restrict__ stats_partial, int n_stat,
+                                                                     double* __restrict__ stats) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ __align__(16) double sD[2][64 * SN_DPITCH];   // double-buffered 64-sample delta_0 chunk (36 KB)
+    extern __shared__ __align__(16) double sP[];              // partial tile: SNB_TILE (col CTAs) or n_small doubles
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int L = d.n_in, R0 = d.rows[0];
-    const int b_begin = blockIdx.y * ksplit;
+    const int S = gridDim.y;
+    const int rank = blockIdx.y;                               // == cluster.block_rank() for cluster dims (1, S, 1)
+    const int b_begin = rank * ksplit;
     const int b_end = min(B, b_begin + ksplit);
-    double* __restrict__ out = partial + (size_t)blockIdx.y * d.n_params;
+    const bool is_col = (int)blockIdx.x < col_groups;
+    const int small_base = d.b_off[0];
+    const int n_small = d.n_params - small_base;
 
-    if ((int)blockIdx.x < col_groups) {
+    if (is_col) {
         const int mf = (R0 + 7) >> 3;
         const int col = blockIdx.x * 64 + warp * 8 + g;     // B frag column (feature index)
         const bool col_ok = col < L;
+        constexpr int U = 16;                                // 64 samples per chunk
         double acc[4][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.0;
-        constexpr int U = 4;
-        for (int kb = b_begin; kb < b_end; kb += 4 * U) {
-            double af[U][4], bf[U];
+        int buf = 0;
+        for (int c0 = b_begin; c0 < b_end; c0 += 4 * U, buf ^= 1) {
+            double bf[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int b = kb + u * 4 + t;
-                const bool bok = b < b_end;
-                bf[u] = (bok && col_ok) ? feats[(size_t)b * L + col] : 0.0;           // B frag: row t (sample), col g (feature)
+            for (int u = 0; u < U; ++u) {                    // 16 A0 loads in flight per lane
+                const int b = c0 + u * 4 + t;
+                bf[u] = (b < b_end && col_ok) ? feats[(size_t)b * L + col] : 0.0;   // B frag: row t (sample), col g (feature)
+            }
+            double* sd = sD[buf];
+            {
+                double vd[8];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int m = i * 8 + g;
-                    af[u][i] = (bok && i < mf && m < R0) ? deltas[(size_t)b * R0 + m] : 0.0;  // A frag: row g (m), col t (sample)
+                for (int u = 0; u < 8; ++u) {            // 64 x 32 slice = 8 elements per thread, all loads first
+                    const int idx = u * SNB_THREADS + tid;
+                    const int kk = idx >> 5, mm = idx & 31;
+                    const int b = c0 + kk;
+                    vd[u] = (mm < R0 && b < b_end) ? deltas[(size_t)b * R0 + mm] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = u * SNB_THREADS + tid;
+                    sd[(idx >> 5) * SN_DPITCH + (idx & 31)] = vd[u];
                 }
             }
+            __syncthreads();   // chunk staged; the other buffer is free again because everyone passed this barrier
 #pragma unroll
-            for (int u = 0; u < U; ++u)
+            for (int u = 0; u < U; ++u) {
+                const int kk = u * 4 + t;
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    if (i < mf) sn_dmma(acc[i][0], acc[i][1], af[u][i], bf[u]);
+                    if (i < mf) sn_dmma(acc[i][0], acc[i][1], sd[kk * SN_DPITCH + i * 8 + g], bf[u]);  // A frag: row g (m), col t
+            }
         }
-        const int c0 = blockIdx.x * 64 + warp * 8 + 2 * t;
+        const int cl = warp * 8 + 2 * t;                    // C frag: row g (m), cols 2t, 2t+1
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int m = i * 8 + g;
-            if (m < R0) {
-                if (c0 < L) out[d.w_off[0] + (size_t)c0 * R0 + m] = acc[i][0];
-                if (c0 + 1 < L) out[d.w_off[0] + (size_t)(c0 + 1) * R0 + m] = acc[i][1];
+            sP[cl * 32 + i * 8 + g] = acc[i][0];
+            sP[(cl + 1) * 32 + i * 8 + g] = acc[i][1];
+        }
+    } else {
+        // ---- db_l (all layers) and dW_l (narrow layers): every output of the "small" parameter block b0|W1|b1|...
+        // is owned by one thread; delta / activation chunks of 64 samples are staged in shared memory so the
+        // per-sample loop never waits on L2.  Samples are summed in index order (rcn.rs:302-303,309-310).
+        int SR = 0;
+        for (int l = 0; l < d.n_layers; ++l) SR += d.rows[l];
+        double* sDel = sP + n_small;              // [64][SR]
+        double* sAct = sDel + 64 * SR;            // [64][SR]
+        constexpr int MAXO = (SN_MAX_SMALL + SNB_THREADS - 1) / SNB_THREADS;
+        double acc[MAXO];
+        int o_del[MAXO], o_act[MAXO];             // row offsets into a staged sample: delta row, activation row (-1: bias)
+#pragma unroll
+        for (int j = 0; j < MAXO; ++j) {
+            acc[j] = 0.0; o_del[j] = -1; o_act[j] = -1;
+            const int o = tid + j * SNB_THREADS;
+            if (o < n_small) {
+                const int p = o + small_base;     // index into the flat parameter vector
+                int rowoff = 0;
+                for (int l = 0; l < d.n_layers; ++l) {
+                    const int R = d.rows[l];
+                    if (p >= d.b_off[l] && p < d.b_off[l] + R) { o_del[j] = rowoff + (p - d.b_off[l]); break; }
+                    if (l >= 1 && p >= d.w_off[l] && p < d.b_off[l]) {
+                        const int q = p - d.w_off[l];
+                        o_del[j] = rowoff + q % R;
+                        o_act[j] = (rowoff - d.rows[l - 1]) + q / R;
+                        break;
+                    }
+                    rowoff += R;
+                }
             }
         }
-        return;
-    }
-    // ---- db0 and the narrow layers: one thread per output, samples in index order ----------------------------------
-    size_t act_off = 0;   // rows before layer l (activations/deltas are stored layer after layer, rows_l x B each)
-    for (int l = 0; l < d.n_layers; ++l) {
-        const int R = d.rows[l];
-        const double* __restrict__ dl = deltas + act_off * B;
-        for (int mrow = tid; mrow < R; mrow += SN_THREADS) {       // db_l = sum_b delta_l   (rcn.rs:302,309)
-            double s = 0.0;
-            for (int b = b_begin; b < b_end; ++b) s += dl[(size_t)b * R + mrow];
-            out[d.b_off[l] + mrow] = s;
-        }
-        if (l >= 1) {                                              // dW_l = sum_b delta_l a_{l-1}^T   (rcn.rs:303,310)
-            const int C = d.rows[l - 1];
-            const double* __restrict__ ap = acts + (act_off - C) * B;
-            for (int o = tid; o < R * C; o += SN_THREADS) {
-                const int mrow = o % R, k = o / R;
-                double s = 0.0;
-                for (int b = b_begin; b < b_end; ++b) s = fma(dl[(size_t)b * R + mrow], ap[(size_t)b * C + k], s);
-                out[d.w_off[l] + (size_t)k * R + mrow] = s;
+        for (int c0 = b_begin; c0 < b_end; c0 += 64) {
+            const int nb = min(64, b_end - c0);
+            int rowoff = 0;
+            for (int l = 0; l < d.n_layers; ++l) {
+                const int R = d.rows[l];
+                const double* __restrict__ gd = deltas + (size_t)rowoff * B + (size_t)c0 * R;
+                const double* __restrict__ ga = acts + (size_t)rowoff * B + (size_t)c0 * R;
+                // 8 loads in flight per thread before the first shared-memory store (one L2 round trip per 1024 elements)
+                for (int base = 0; base < nb * R; base += 4 * SNB_THREADS) {
+                    double vd[4], va[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = base + u * SNB_THREADS + tid;
+                        const bool ok = i < nb * R;
+                        vd[u] = ok ? gd[i] : 0.0;
+                        va[u] = ok ? ga[i] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = base + u * SNB_THREADS + tid;
+                        if (i < nb * R) {
+                            const int b = i / R, mrow = i - b * R;
+                            sDel[b * SR + rowoff + mrow] = vd[u];
+                            sAct[b * SR + rowoff + mrow] = va[u];
+                        }
+                    }
+                }
+                rowoff += R;
             }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < MAXO; ++j) {
+                if (o_del[j] >= 0) {
+                    double a = acc[j];
+                    if (o_act[j] >= 0) {
+                        for (int b = 0; b < nb; ++b) a = fma(sDel[b * SR + o_del[j]], sAct[b * SR + o_act[j]], a);
+                    } else {
+                        for (int b = 0; b < nb; ++b) a += sDel[b * SR + o_del[j]];
+                    }
+                    acc[j] = a;
+                }
+            }
+            __syncthreads();
         }
-        act_off += R;
+#pragma unroll
+        for (int j = 0; j < MAXO; ++j) {
+            const int o = tid + j * SNB_THREADS;
+            if (o < n_small) sP[o] = acc[j];
+        }
     }
-}
 
-// ------------------------------------------------------------------------------------------------
-// Kernel C: fixed-order sum of the K-split partials -> flat gradient buffer; batch statistics.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) smallnet_reduce_kernel(const double* __restrict__ partial, int splits, int n_params,
-                                                             double* __restrict__ grads,
-                                                             const double* __restrict__ stats_partial, int n_stat,
-                                                             double* __restrict__ stats) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_params; i += gridDim.x * blockDim.x) {
-        double s = partial[i];
-        for (int p = 1; p < splits; ++p) s += partial[(size_t)p * n_params + i];
-        grads[i] = s;
+    // ---- cross-split reduction through distributed shared memory, rank order ----------------------------------------
+    cluster.sync();
+    const int n_out = is_col ? SNB_TILE : n_small;
+    const int per = (n_out + S - 1) / S;
+    const int o_lo = rank * per, o_hi = min(n_out, o_lo + per);
+    for (int o = o_lo + tid; o < o_hi; o += SNB_THREADS) {
+        double s = 0.0;
+        for (int q = 0; q < S; ++q) {
+            const double* remote = cluster.map_shared_rank(sP, q);
+            s += remote[o];
+        }
+        if (is_col) {
+            const int m = o & 31, col = blockIdx.x * 64 + (o >> 5);
+            if (m < R0 && col < L) grads[d.w_off[0] + (size_t)col * R0 + m] = s;
+        } else {
+            grads[small_base + o] = s;
+        }
     }
-    if (blockIdx.x == 0 && threadIdx.x < 32 && stats) {
+    if (!is_col && rank == 0 && tid < 32 && stats) {
         // 32 lanes, each a contiguous chunk in order, then a fixed-order shuffle tree => deterministic
-        const int per = (n_stat + 31) / 32;
+        const int per_l = (n_stat + 31) / 32;
         double c = 0.0;
         unsigned long long h = 0;
-        for (int i = threadIdx.x * per; i < min(n_stat, (int)(threadIdx.x + 1) * per); ++i) {
+        for (int i = tid * per_l; i < min(n_stat, (tid + 1) * per_l); ++i) {
             c += stats_partial[2 * i];
             h += reinterpret_cast<const unsigned long long*>(stats_partial)[2 * i + 1];
         }
@@ -291,11 +479,12 @@ __global__ void __launch_bounds__(256) smallnet_reduce_kernel(const double* __re
             c += __shfl_down_sync(0xffffffffu, c, o);
             h += __shfl_down_sync(0xffffffffu, h, o);
         }
-        if (threadIdx.x == 0) {
+        if (tid == 0) {
             stats[0] = c;
             reinterpret_cast<unsigned long long*>(stats)[1] = h;
         }
     }
+    cluster.sync();   // nobody leaves while a peer may still read its tile
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -308,46 +497,97 @@ bool smallnet_eligible(const SmallNetDesc& d) {
     return d.n_in >= 1;
 }
 
-int smallnet_ksplit(size_t B) {
-    size_t ks = (B + 31) / 32;
-    ks = (ks + 3) / 4 * 4;
-    if (ks < 64) ks = 64;
-    return (int)ks;
+// K-splits of the batch = cluster size of kernel B (portable maximum 8), each a whole number of 64-sample chunks.
+static void smallnet_splits(size_t B, int* splits, int* ksplit) {
+    int s = 1;
+    while (s < 8 && (size_t)s * 64 < B) s *= 2;
+    size_t ks = (B + s - 1) / s;
+    ks = (ks + 63) / 64 * 64;
+    *splits = (int)((B + ks - 1) / ks);
+    if (*splits < 1) *splits = 1;
+    *ksplit = (int)ks;
 }
 
-int launch_smallnet_forward(const SmallNetDesc& d, const double* params, const double* feats, size_t B, double* acts,
-                            cudaStream_t stream) {
-    if (B == 0) return RCN_OK;
-    RCN_LAUNCH("smallnet_fwd_bwd_kernel", stream,
-               smallnet_fwd_bwd_kernel<<<cdiv(B, SN_TB), SN_THREADS, 0, stream>>>(d, params, feats, (int)B, nullptr, nullptr,
-                                                                                  acts, nullptr, nullptr, 0));
+size_t smallnet_max_batch() { return (size_t)1 << 22; }
+
+static size_t kernel_a_smem(const SmallNetDesc& d, const SmallNetFront* fr) {
+    size_t bytes = ((size_t)SNA_WARPS * 32 * SN_TB + SN_MAX_SMALL) * sizeof(double);
+    if (fr) bytes += (size_t)SN_TB * (d.n_in + SN_TILE_PAD) * sizeof(double) + (size_t)SN_TB * 2 * fr->max_elems * sizeof(int);
+    return bytes;
+}
+
+bool smallnet_front_fits(const SmallNetDesc& d, const SmallNetFront& fr) { return kernel_a_smem(d, &fr) <= 200 * 1024; }
+
+static int launch_kernel_a(const SmallNetDesc& d, const double* params, double* feats, size_t B, const double* onehot,
+                           const int64_t* labels, double* acts, double* deltas, double* stats_partial, int backward,
+                           const SmallNetFront* fr, cudaStream_t stream) {
+    const unsigned n_tiles = cdiv(B, SN_TB);
+    const size_t smem = kernel_a_smem(d, fr);
+    static SmallNetFront empty_front{};
+    if (fr) {
+        auto kern = smallnet_fwd_bwd_kernel<true>;
+        static size_t attr = 0;
+        if (smem > attr) { RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+        RCN_LAUNCH("smallnet_fwd_bwd_kernel(fused features)", stream,
+                   kern<<<n_tiles, SNA_THREADS, smem, stream>>>(d, params, feats, (int)B, onehot, labels, acts, deltas,
+                                                               stats_partial, backward, *fr));
+    } else {
+        auto kern = smallnet_fwd_bwd_kernel<false>;
+        static size_t attr = 0;
+        if (smem > attr) { RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+        RCN_LAUNCH("smallnet_fwd_bwd_kernel", stream,
+                   kern<<<n_tiles, SNA_THREADS, smem, stream>>>(d, params, feats, (int)B, onehot, labels, acts, deltas,
+                                                               stats_partial, backward, empty_front));
+    }
     return RCN_OK;
 }
 
-int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, const double* feats, size_t B,
-                             const double* onehot, const int64_t* labels, double* acts, double* deltas, double* grads,
-                             double* stats, DevBuf& workspace, cudaStream_t stream) {
+int launch_smallnet_forward(const SmallNetDesc& d, const double* params, double* feats, size_t B, double* acts,
+                            const SmallNetFront* front, cudaStream_t stream) {
     if (B == 0) return RCN_OK;
-    if (B > 0x7fffffff / 64) return fail(RCN_ERR_INVALID, "batch too large for the fused small-network path");
-    const int ksplit = smallnet_ksplit(B);
-    const int splits = (int)cdiv(B, ksplit);
+    return launch_kernel_a(d, params, feats, B, nullptr, nullptr, acts, nullptr, nullptr, 0, front, stream);
+}
+
+int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double* feats, size_t B, const double* onehot,
+                             const int64_t* labels, double* acts, double* deltas, double* grads, double* stats,
+                             DevBuf& workspace, const SmallNetFront* front, cudaStream_t stream) {
+    if (B == 0) return RCN_OK;
+    if (B > smallnet_max_batch()) return fail(RCN_ERR_INVALID, "batch too large for the fused small-network path");
+    int splits, ksplit;
+    smallnet_splits(B, &splits, &ksplit);
     const int n_tiles = (int)cdiv(B, SN_TB);
-    // workspace: [splits][n_params] partial gradients | [n_tiles][2] statistics partials
-    const size_t part_elems = (size_t)splits * d.n_params;
-    RCN_TRY(workspace.reserve((part_elems + 2 * (size_t)n_tiles) * sizeof(double)));
-    double* partial = workspace.as<double>();
-    double* stats_partial = partial + part_elems;
-    RCN_LAUNCH("smallnet_fwd_bwd_kernel", stream,
-               smallnet_fwd_bwd_kernel<<<n_tiles, SN_THREADS, 0, stream>>>(d, params, feats, (int)B, onehot, labels, acts,
-                                                                           deltas, stats_partial, 1));
     const int col_groups = (int)cdiv(d.n_in, 64);
-    dim3 grid(col_groups + 1, splits);
+    RCN_TRY(workspace.reserve(2 * (size_t)n_tiles * sizeof(double)));   // per-tile statistics partials
+    double* stats_partial = workspace.as<double>();
+    RCN_TRY(launch_kernel_a(d, params, feats, B, onehot, labels, acts, deltas, stats_partial, 1, front, stream));
+
+    const int n_small = d.n_params - d.b_off[0];
+    int sum_rows = 0;
+    for (int l = 0; l < d.n_layers; ++l) sum_rows += d.rows[l];
+    const size_t narrow_elems = (size_t)n_small + 2 * 64 * (size_t)sum_rows;   // partial block + staged delta/act chunk
+    const size_t smem_b = (narrow_elems > (size_t)SNB_TILE ? narrow_elems : (size_t)SNB_TILE) * sizeof(double);
+    static size_t attr_b = 0;
+    if (smem_b > attr_b) {   // static 36 KB + dynamic tile exceeds the 48 KB default
+        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        attr_b = smem_b;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(col_groups + 1, splits, 1);
+    cfg.blockDim = dim3(SNB_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem_b;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = splits;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int Bi = (int)B;
     RCN_LAUNCH("smallnet_wgrad_kernel", stream,
-               smallnet_wgrad_kernel<<<grid, SN_THREADS, 0, stream>>>(d, feats, acts, deltas, (int)B, ksplit, col_groups, partial));
-    unsigned rgrid = cdiv(d.n_params, 256);
-    if (rgrid > (unsigned)kNumSMs) rgrid = kNumSMs;
-    RCN_LAUNCH("smallnet_reduce_kernel", stream,
-               smallnet_reduce_kernel<<<rgrid, 256, 0, stream>>>(partial, splits, d.n_params, grads, stats_partial, n_tiles, stats));
+               cudaLaunchKernelEx(&cfg, smallnet_wgrad_kernel, d, (const double*)feats, (const double*)acts,
+                                  (const double*)deltas, Bi, ksplit, col_groups, grads, (const double*)stats_partial, n_tiles,
+                                  stats));
     return RCN_OK;
 }
 

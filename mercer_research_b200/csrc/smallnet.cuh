@@ -1,6 +1,7 @@
 // smallnet.cuh -- fused training step for narrow sigmoid networks (every layer width <= 32), see smallnet.cu.
 #pragma once
 #include "common.cuh"
+#include "features.cuh"
 
 namespace rcn {
 
@@ -15,15 +16,28 @@ struct SmallNetDesc {
     int n_params;
 };
 
+// Optional fused front end of kernel A: u8 images -> convpool stack -> standardised features, in shared memory.
+struct SmallNetFront {
+    const uint8_t* images;
+    int H, W;
+    int max_elems;                     // largest per-image map set any stage reads (elements)
+    StageList stages;
+    Standardise sc;
+    BatchIndex bi;
+};
+
 bool smallnet_eligible(const SmallNetDesc& d);
+size_t smallnet_max_batch();
+bool smallnet_front_fits(const SmallNetDesc& d, const SmallNetFront& fr);
 
 // acts: sum(rows) x B (layer after layer, rows_l x B column-major each), same layout for deltas.
-int launch_smallnet_forward(const SmallNetDesc& d, const double* params, const double* feats, size_t B, double* acts,
-                            cudaStream_t stream);
+// With a front end, `feats` (n_in x B) is an OUTPUT (kernel B and the parity taps read it); without, an input.
+int launch_smallnet_forward(const SmallNetDesc& d, const double* params, double* feats, size_t B, double* acts,
+                            const SmallNetFront* front, cudaStream_t stream);
 // Full backprop of a minibatch: fills acts, deltas, the flat gradient buffer (batch sums) and stats[0..1]
 // (quadratic cost, hit count as uint64 bits).
-int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, const double* feats, size_t B,
-                             const double* onehot, const int64_t* labels, double* acts, double* deltas, double* grads,
-                             double* stats, DevBuf& workspace, cudaStream_t stream);
+int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double* feats, size_t B, const double* onehot,
+                             const int64_t* labels, double* acts, double* deltas, double* grads, double* stats,
+                             DevBuf& workspace, const SmallNetFront* front, cudaStream_t stream);
 
 }  // namespace rcn

@@ -102,7 +102,10 @@ class RCN:
             pass
 
     def set_stream(self, cuda_stream: Optional[int]):
-        """Run on an existing cudaStream_t (int handle, e.g. ``torch.cuda.current_stream().cuda_stream``)."""
+        """Run on an existing cudaStream_t (int handle, e.g. ``torch.cuda.current_stream().cuda_stream``; 0 / None is
+        the CUDA legacy default stream). ``set_stream(-1)`` restores the model's private stream."""
+        if cuda_stream is not None and cuda_stream < 0:
+            cuda_stream = C.c_void_p(-1).value
         _lib.check(self._lib.rcn_cuda_set_stream(self._h, cuda_stream))
 
     def synchronize(self):
@@ -359,6 +362,38 @@ class RCN:
         self._use_torch_stream(buf, lb)
         self._B_hint = B
         _lib.check(self._lib.rcn_cuda_train_batch_images(self._h, buf.ptr, fmt, lb.ptr, B, H, W, float(eta)))
+
+    # -- epoch mode (rcn.rs:144-149 on a dataset resident in HBM) ---------------------------------------------------
+    def epoch_bind(self, images, labels, batch: int, perm=None):
+        """Bind a device-resident dataset (torch CUDA tensors): images (N, H, W) uint8, labels (N,) int64, optional
+        ``perm`` (N,) int64 shuffle that may be rewritten in place between epochs. Step k then trains on samples
+        ``perm[pos:pos+batch]`` with ``pos`` kept on the device (chunks_exact semantics, remainder dropped)."""
+        buf, fmt, (N, H, W) = self._images(images)
+        lb = _Buf(labels, np.int64)
+        pm = _Buf(perm, np.int64) if perm is not None else None
+        if not (buf.torch and lb.torch and (pm is None or pm.torch)):
+            raise ValueError("epoch mode needs torch CUDA tensors (the dataset stays resident in HBM)")
+        self._use_torch_stream(buf)
+        self._epoch_keepalive = (buf, lb, pm)
+        self._B_hint = int(batch)
+        _lib.check(self._lib.rcn_cuda_epoch_bind(self._h, buf.ptr, fmt, lb.ptr, pm.ptr if pm else None, N, H, W, int(batch)))
+
+    def epoch_seek(self, position: int):
+        _lib.check(self._lib.rcn_cuda_epoch_seek(self._h, int(position)))
+
+    def epoch_position(self) -> int:
+        p = C.c_size_t()
+        _lib.check(self._lib.rcn_cuda_epoch_position(self._h, C.byref(p)))
+        return p.value
+
+    def epoch_accumulate(self):
+        _lib.check(self._lib.rcn_cuda_epoch_accumulate(self._h))
+
+    def epoch_apply(self, eta: float, global_batch: int):
+        _lib.check(self._lib.rcn_cuda_epoch_apply(self._h, float(eta), int(global_batch)))
+
+    def epoch_step(self, eta: float):
+        _lib.check(self._lib.rcn_cuda_epoch_step(self._h, float(eta)))
 
     def last_batch_stats(self) -> Tuple[float, int]:
         """(quadratic cost, hits) of the last accumulated batch, evaluated with the pre-update parameters."""

@@ -67,6 +67,46 @@ class DataParallelTrainer:
         lo, hi = shard_bounds(int(images.shape[0]), self.rank, self.world)
         self.step_images(images[lo:hi], labels[lo:hi])
 
+    # -- epoch mode: device-resident dataset, device-side batch cursor, one CUDA graph per step shape ---------------
+    def bind_dataset(self, images, labels, batch: int, perm=None):
+        """This rank's dataset shard (torch CUDA tensors). ``batch`` is the per-rank minibatch."""
+        self.model.epoch_bind(images, labels, batch, perm)
+        self.local_batch = int(batch)
+        self.graph = None
+
+    def _epoch_step_eager(self):
+        import torch
+        self.model.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.model.epoch_accumulate()
+        if self.world > 1:
+            self.dist.all_reduce(self.grads, op=self.dist.ReduceOp.SUM, group=self.group)
+        self.model.epoch_apply(self.eta, self.local_batch * self.world)
+
+    def capture(self, warmup: int = 3):
+        """Captures one epoch step (kernels + the NCCL all-reduce) into a CUDA graph; later epoch_step() calls replay
+        it. The batch selection lives in device memory, so the same graph serves every step of every epoch."""
+        import torch
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._epoch_step_eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._epoch_step_eager()
+        self.graph = graph
+        self.model.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.model.epoch_seek(0)
+        return graph
+
+    def epoch_step(self):
+        if getattr(self, "graph", None) is not None:
+            self.graph.replay()
+        else:
+            self._epoch_step_eager()
+
     def describe(self) -> str:
         ar = "none (1 GPU)" if self.world == 1 else f"1x NCCL all-reduce(sum) of {self.model.n_params} f64 per step"
         return ("features(+standardise) -> fwd -> bwd-data -> bwd-weight(+db) -> batch stats -> " + ar +

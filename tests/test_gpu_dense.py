@@ -269,3 +269,50 @@ def test_train_arrays_epoch_driver(api):
     m, s = O.gen_scales(te_raw)
     gm, gs = model.scale_set
     assert abs(gm - m) <= 1e-12 * m and abs(gs - s) <= 1e-12 * s
+
+
+def test_epoch_mode_and_cuda_graph(api):
+    """Epoch mode (device-side cursor + perm, rcn.rs:144-149) eager and as a replayed CUDA graph must equal
+    explicit train_batch_images calls on the same chunks, including the chunks_exact wrap-around."""
+    import torch
+    from mercer_research_b200.trainer import DataParallelTrainer
+    rng = np.random.default_rng(77)
+    N, B = 1000, 96                      # 10 full chunks, remainder 40 dropped
+    imgs = rng.integers(0, 256, size=(N, 28, 28), dtype=np.uint8)
+    labels = rng.integers(0, 10, N).astype(np.int64)
+    perm = rng.permutation(N).astype(np.int64)
+    cfg = [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max)]
+
+    def fresh():
+        m = api.RCN(10, cfg, [30])
+        m.scale_set = (20.0, 35.0)
+        m.load_weights_and_bias(784)
+        m.set_params(np.random.default_rng(3).standard_normal(m.n_params) * 0.05)
+        return m
+
+    ref = fresh()
+    n_steps = 13                          # wraps after 10
+    for k in range(n_steps):
+        pos = (k % 10) * B
+        idx = perm[pos:pos + B]
+        ref.train_batch_images(imgs[idx], labels[idx], 3.0)
+    want = ref.get_params()
+
+    d_imgs, d_labels, d_perm = torch.from_numpy(imgs).cuda(), torch.from_numpy(labels).cuda(), torch.from_numpy(perm).cuda()
+    eager = fresh()
+    eager.epoch_bind(d_imgs, d_labels, B, perm=d_perm)
+    for k in range(n_steps):
+        eager.epoch_step(3.0)
+    assert eager.epoch_position() == 3 * B
+    assert np.array_equal(eager.get_params(), want)
+
+    graphed = fresh()
+    tr = DataParallelTrainer(graphed, eta=3.0)
+    tr.bind_dataset(d_imgs, d_labels, B, perm=d_perm)
+    tr.capture(warmup=2)
+    graphed.set_params(np.random.default_rng(3).standard_normal(graphed.n_params) * 0.05)   # undo the warm-up steps
+    for k in range(n_steps):
+        tr.epoch_step()
+    torch.cuda.synchronize()
+    assert np.array_equal(graphed.get_params(), want)
+    assert graphed.epoch_position() == 3 * B
