@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(SNA_THREADS, 1)
 smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __restrict__ params,
                         double* __restrict__ feats, int B, const double* __restrict__ onehot,
                         const int64_t* __restrict__ labels, double* __restrict__ acts, double* __restrict__ deltas,
-                        double* __restrict__ stats_partial, int backward, const __grid_constant__ SmallNetFront fr) {
+                        double* __restrict__ stats_partial, double* __restrict__ small_partial, int backward,
+                        const __grid_constant__ SmallNetFront fr) {
     extern __shared__ __align__(16) unsigned char sn_smem[];
     double* zpart = reinterpret_cast<double*>(sn_smem);                 // [16][32][8]
     double* s_small = zpart + SNA_WARPS * 32 * SN_TB;                   // params after W0: b0 | W1 | b1 | ...
@@ -284,6 +285,30 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
         stats_partial[2 * blockIdx.x] = c;
         reinterpret_cast<unsigned long long*>(stats_partial)[2 * blockIdx.x + 1] = h;
     }
+    // ---- this tile's share of db_l (all layers) and dW_l (narrow layers): everything is already in shared memory.
+    // One value per entry of the "small" parameter block b0|W1|b1|...; kernel B sums the tiles in index order.
+    {
+        const int n_live = min(SN_TB, B - s0);
+        for (int o = tid; o < n_small; o += 32 * SN_TB) {
+            const int p = o + small_base;
+            double acc = 0.0;
+            for (int l = 0; l < d.n_layers; ++l) {
+                const int R = d.rows[l];
+                if (p >= d.b_off[l] && p < d.b_off[l] + R) {                 // db_l = sum_b delta_l      (rcn.rs:302,309)
+                    const int mr = p - d.b_off[l];
+                    for (int b = 0; b < n_live; ++b) acc += s_del[l][b][mr];
+                    break;
+                }
+                if (l >= 1 && p >= d.w_off[l] && p < d.b_off[l]) {           // dW_l = sum_b delta_l a_{l-1}^T (rcn.rs:303,310)
+                    const int q = p - d.w_off[l];
+                    const int mr = q % R, k = q / R;
+                    for (int b = 0; b < n_live; ++b) acc = fma(s_del[l][b][mr], s_act[l - 1][b][k], acc);
+                    break;
+                }
+            }
+            small_partial[(size_t)blockIdx.x * n_small + o] = acc;
+        }
+    }
 #undef SN_BAR
 }
 
@@ -298,7 +323,7 @@ constexpr int SNB_TILE = 32 * 64;   // padded partial tile: 32 rows x 64 columns
 
 __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __grid_constant__ SmallNetDesc d,
                                                                      const double* __restrict__ feats,
-                                                                     const double* __restrict__ acts,
+                                                                     const double* __restrict__ small_partial,
                                                                      const double* __restrict__ deltas, int B, int ksplit,
                                                                      int col_groups, double* __restrict__ grads,
                                                                      const double* __restrict__ stats_partial, int n_stat,
@@ -366,84 +391,20 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
             sP[(cl + 1) * 32 + i * 8 + g] = acc[i][1];
         }
     } else {
-        // ---- db_l (all layers) and dW_l (narrow layers): every output of the "small" parameter block b0|W1|b1|...
-        // is owned by one thread; delta / activation chunks of 64 samples are staged in shared memory so the
-        // per-sample loop never waits on L2.  Samples are summed in index order (rcn.rs:302-303,309-310).
-        int SR = 0;
-        for (int l = 0; l < d.n_layers; ++l) SR += d.rows[l];
-        double* sDel = sP + n_small;              // [64][SR]
-        double* sAct = sDel + 64 * SR;            // [64][SR]
-        constexpr int MAXO = (SN_MAX_SMALL + SNB_THREADS - 1) / SNB_THREADS;
-        double acc[MAXO];
-        int o_del[MAXO], o_act[MAXO];             // row offsets into a staged sample: delta row, activation row (-1: bias)
+        // ---- db_l (all layers) and dW_l (narrow layers): kernel A left one partial per 8-sample tile; sum this
+        // rank's tiles in index order (8 loads in flight per thread).
+        const int t_begin = b_begin / SN_TB;
+        const int t_end = (b_end + SN_TB - 1) / SN_TB;
+        for (int o = tid; o < n_small; o += SNB_THREADS) {
+            double s = 0.0;
+            for (int tb = t_begin; tb < t_end; tb += 8) {
+                double v[8];
 #pragma unroll
-        for (int j = 0; j < MAXO; ++j) {
-            acc[j] = 0.0; o_del[j] = -1; o_act[j] = -1;
-            const int o = tid + j * SNB_THREADS;
-            if (o < n_small) {
-                const int p = o + small_base;     // index into the flat parameter vector
-                int rowoff = 0;
-                for (int l = 0; l < d.n_layers; ++l) {
-                    const int R = d.rows[l];
-                    if (p >= d.b_off[l] && p < d.b_off[l] + R) { o_del[j] = rowoff + (p - d.b_off[l]); break; }
-                    if (l >= 1 && p >= d.w_off[l] && p < d.b_off[l]) {
-                        const int q = p - d.w_off[l];
-                        o_del[j] = rowoff + q % R;
-                        o_act[j] = (rowoff - d.rows[l - 1]) + q / R;
-                        break;
-                    }
-                    rowoff += R;
-                }
+                for (int u = 0; u < 8; ++u) v[u] = (tb + u < t_end) ? small_partial[(size_t)(tb + u) * n_small + o] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s += v[u];
             }
-        }
-        for (int c0 = b_begin; c0 < b_end; c0 += 64) {
-            const int nb = min(64, b_end - c0);
-            int rowoff = 0;
-            for (int l = 0; l < d.n_layers; ++l) {
-                const int R = d.rows[l];
-                const double* __restrict__ gd = deltas + (size_t)rowoff * B + (size_t)c0 * R;
-                const double* __restrict__ ga = acts + (size_t)rowoff * B + (size_t)c0 * R;
-                // 8 loads in flight per thread before the first shared-memory store (one L2 round trip per 1024 elements)
-                for (int base = 0; base < nb * R; base += 4 * SNB_THREADS) {
-                    double vd[4], va[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = base + u * SNB_THREADS + tid;
-                        const bool ok = i < nb * R;
-                        vd[u] = ok ? gd[i] : 0.0;
-                        va[u] = ok ? ga[i] : 0.0;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = base + u * SNB_THREADS + tid;
-                        if (i < nb * R) {
-                            const int b = i / R, mrow = i - b * R;
-                            sDel[b * SR + rowoff + mrow] = vd[u];
-                            sAct[b * SR + rowoff + mrow] = va[u];
-                        }
-                    }
-                }
-                rowoff += R;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < MAXO; ++j) {
-                if (o_del[j] >= 0) {
-                    double a = acc[j];
-                    if (o_act[j] >= 0) {
-                        for (int b = 0; b < nb; ++b) a = fma(sDel[b * SR + o_del[j]], sAct[b * SR + o_act[j]], a);
-                    } else {
-                        for (int b = 0; b < nb; ++b) a += sDel[b * SR + o_del[j]];
-                    }
-                    acc[j] = a;
-                }
-            }
-            __syncthreads();
-        }
-#pragma unroll
-        for (int j = 0; j < MAXO; ++j) {
-            const int o = tid + j * SNB_THREADS;
-            if (o < n_small) sP[o] = acc[j];
+            sP[o] = s;
         }
     }
 
@@ -519,8 +480,8 @@ static size_t kernel_a_smem(const SmallNetDesc& d, const SmallNetFront* fr) {
 bool smallnet_front_fits(const SmallNetDesc& d, const SmallNetFront& fr) { return kernel_a_smem(d, &fr) <= 200 * 1024; }
 
 static int launch_kernel_a(const SmallNetDesc& d, const double* params, double* feats, size_t B, const double* onehot,
-                           const int64_t* labels, double* acts, double* deltas, double* stats_partial, int backward,
-                           const SmallNetFront* fr, cudaStream_t stream) {
+                           const int64_t* labels, double* acts, double* deltas, double* stats_partial,
+                           double* small_partial, int backward, const SmallNetFront* fr, cudaStream_t stream) {
     const unsigned n_tiles = cdiv(B, SN_TB);
     const size_t smem = kernel_a_smem(d, fr);
     static SmallNetFront empty_front{};
@@ -530,14 +491,14 @@ static int launch_kernel_a(const SmallNetDesc& d, const double* params, double* 
         if (smem > attr) { RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
         RCN_LAUNCH("smallnet_fwd_bwd_kernel(fused features)", stream,
                    kern<<<n_tiles, SNA_THREADS, smem, stream>>>(d, params, feats, (int)B, onehot, labels, acts, deltas,
-                                                               stats_partial, backward, *fr));
+                                                               stats_partial, small_partial, backward, *fr));
     } else {
         auto kern = smallnet_fwd_bwd_kernel<false>;
         static size_t attr = 0;
         if (smem > attr) { RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
         RCN_LAUNCH("smallnet_fwd_bwd_kernel", stream,
                    kern<<<n_tiles, SNA_THREADS, smem, stream>>>(d, params, feats, (int)B, onehot, labels, acts, deltas,
-                                                               stats_partial, backward, empty_front));
+                                                               stats_partial, small_partial, backward, empty_front));
     }
     return RCN_OK;
 }
@@ -545,7 +506,7 @@ static int launch_kernel_a(const SmallNetDesc& d, const double* params, double* 
 int launch_smallnet_forward(const SmallNetDesc& d, const double* params, double* feats, size_t B, double* acts,
                             const SmallNetFront* front, cudaStream_t stream) {
     if (B == 0) return RCN_OK;
-    return launch_kernel_a(d, params, feats, B, nullptr, nullptr, acts, nullptr, nullptr, 0, front, stream);
+    return launch_kernel_a(d, params, feats, B, nullptr, nullptr, acts, nullptr, nullptr, nullptr, 0, front, stream);
 }
 
 int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double* feats, size_t B, const double* onehot,
@@ -557,15 +518,14 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
     smallnet_splits(B, &splits, &ksplit);
     const int n_tiles = (int)cdiv(B, SN_TB);
     const int col_groups = (int)cdiv(d.n_in, 64);
-    RCN_TRY(workspace.reserve(2 * (size_t)n_tiles * sizeof(double)));   // per-tile statistics partials
-    double* stats_partial = workspace.as<double>();
-    RCN_TRY(launch_kernel_a(d, params, feats, B, onehot, labels, acts, deltas, stats_partial, 1, front, stream));
-
     const int n_small = d.n_params - d.b_off[0];
-    int sum_rows = 0;
-    for (int l = 0; l < d.n_layers; ++l) sum_rows += d.rows[l];
-    const size_t narrow_elems = (size_t)n_small + 2 * 64 * (size_t)sum_rows;   // partial block + staged delta/act chunk
-    const size_t smem_b = (narrow_elems > (size_t)SNB_TILE ? narrow_elems : (size_t)SNB_TILE) * sizeof(double);
+    // workspace: per-tile statistics partials [n_tiles][2] | per-tile small-parameter gradient partials [n_tiles][n_small]
+    RCN_TRY(workspace.reserve((2 + (size_t)n_small) * (size_t)n_tiles * sizeof(double)));
+    double* stats_partial = workspace.as<double>();
+    double* small_partial = stats_partial + 2 * (size_t)n_tiles;
+    RCN_TRY(launch_kernel_a(d, params, feats, B, onehot, labels, acts, deltas, stats_partial, small_partial, 1, front, stream));
+
+    const size_t smem_b = (size_t)(n_small > SNB_TILE ? n_small : SNB_TILE) * sizeof(double);
     static size_t attr_b = 0;
     if (smem_b > attr_b) {   // static 36 KB + dynamic tile exceeds the 48 KB default
         RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
@@ -585,7 +545,7 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
     cfg.numAttrs = 1;
     const int Bi = (int)B;
     RCN_LAUNCH("smallnet_wgrad_kernel", stream,
-               cudaLaunchKernelEx(&cfg, smallnet_wgrad_kernel, d, (const double*)feats, (const double*)acts,
+               cudaLaunchKernelEx(&cfg, smallnet_wgrad_kernel, d, (const double*)feats, (const double*)small_partial,
                                   (const double*)deltas, Bi, ksplit, col_groups, grads, (const double*)stats_partial, n_tiles,
                                   stats));
     return RCN_OK;
