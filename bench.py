@@ -40,6 +40,13 @@ WORKLOADS = {
     "c5": dict(desc="dense-heavy head 64x64 [C,P] 4096-4096-4096-10, batch 8192 per GPU",
                H=64, W=64, cfg=[1, 3], ff=[4096, 4096], classes=10, batch=8192),
 }
+_RESULT_FD = 1
+
+
+def emit_result(line: dict):
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+
+
 ETA = 3.0  # main.rs:32
 DATA_SEED, PARAM_SEED = 0x5EED, 0xC0FFEE
 
@@ -172,7 +179,7 @@ def run_reference(args, wl, rank, world):
                          "sample": f"{done} steps of batch {B} (features+fwd+bwd+SGD) on {cores} host threads"},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit_result(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -306,11 +313,22 @@ def run_gpu(args, wl, rank, world, local_rank):
     h2d = B * H * W + B * 8
     d2h = 16
 
+    # every collective is done: tear the process group down on ALL ranks together, then rank 0 alone continues with
+    # the single-GPU profiling pass and the CPU baseline (nothing below uses torch.distributed)
+    if world > 1:
+        trainer.graph = None            # the captured graph holds NCCL work: drop it before leaving the group
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        if rank != 0:
+            # destroy_process_group() was seen to block with a captured NCCL graph on this stack (torch 2.11 / NCCL
+            # 2.28): leave without running the destructors; every collective has completed at the barrier above.
+            sys.stdout.flush(); sys.stderr.flush()
+            os._exit(0)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
 
+    print("[bench] rank 0: collective phases done, profiling pass", file=sys.stderr, flush=True)
     # ---- per-kernel durations (CUDA events on the launching stream) for the roofline; separate pass ---------------
     prof_steps = min(args.steps, 50)
     _lib.profile_enable(True)
@@ -348,6 +366,7 @@ def run_gpu(args, wl, rank, world, local_rank):
                                                                    "MEASURED_PEAKS.json has no f64 figure)",
                 "precision": "f64", "fp64_dgemm_tflops_measured": fp64_peak, "kernels": kernels}
 
+    print("[bench] rank 0: cpu baseline", file=sys.stderr, flush=True)
     # ---- CPU baseline on this box's host cores (bounded sample, ~10-20 s) ------------------------------------------
     cpu_ips, cpu_ms, cpu_done, cores = cpu_train_steps(wl, steps=10 ** 6, warmup=2, max_seconds=12.0)
 
@@ -368,9 +387,10 @@ def run_gpu(args, wl, rank, world, local_rank):
                          "sample": f"{cpu_done} steps of batch {B} (features+fwd+bwd+SGD) on {cores} host threads, "
                                    "oracle/rcn_oracle.cpp (C++ restatement of rcn's CPU path, not rustc output)"},
     }
-    print(json.dumps(line), flush=True)
+    emit_result(line)
     if world > 1:
-        dist.destroy_process_group()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -382,6 +402,12 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
+    # stdout must carry exactly ONE JSON line: route everything else that writes to fd 1 (e.g. NCCL's version banner)
+    # to stderr and keep the real stdout for the result line.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -1,0 +1,54 @@
+//! `extern "C"` bindings of include/rcn_cuda.h (1:1, hand-written; no bindgen needed).
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_double, c_int, c_void};
+
+#[repr(C)]
+pub struct rcn_cuda_model {
+    _private: [u8; 0],
+}
+pub type rcn_cuda_handle = *mut rcn_cuda_model;
+
+pub const RCN_OK: c_int = 0;
+pub const RCN_ERR_SHAPE: c_int = 2;
+pub const RCN_ERR_NOT_IMPLEMENTED: c_int = 3;
+pub const RCN_PIXELS_U8_ROWMAJOR: c_int = 0;
+pub const RCN_PIXELS_F64_COLMAJOR: c_int = 1;
+
+extern "C" {
+    pub fn rcn_cuda_last_error() -> *const c_char;
+    pub fn rcn_cuda_create(classes: usize, convpool_cfg: *const i32, n_convpool: usize, feedforward_cfg: *const usize,
+                           n_feedforward: usize, device: c_int, out: *mut rcn_cuda_handle) -> c_int;
+    pub fn rcn_cuda_destroy(h: rcn_cuda_handle) -> c_int;
+    pub fn rcn_cuda_feature_shape(h: rcn_cuda_handle, H: usize, W: usize, n_maps: *mut usize, map_h: *mut usize,
+                                  map_w: *mut usize) -> c_int;
+    pub fn rcn_cuda_init_params(h: rcn_cuda_handle, feature_len: usize) -> c_int;
+    pub fn rcn_cuda_num_layers(h: rcn_cuda_handle, n: *mut usize) -> c_int;
+    pub fn rcn_cuda_layer_shape(h: rcn_cuda_handle, layer: usize, rows: *mut usize, cols: *mut usize) -> c_int;
+    pub fn rcn_cuda_set_weights(h: rcn_cuda_handle, layer: usize, rows: usize, cols: usize, w: *const c_double) -> c_int;
+    pub fn rcn_cuda_get_weights(h: rcn_cuda_handle, layer: usize, w: *mut c_double) -> c_int;
+    pub fn rcn_cuda_set_bias(h: rcn_cuda_handle, layer: usize, n: usize, b: *const c_double) -> c_int;
+    pub fn rcn_cuda_get_bias(h: rcn_cuda_handle, layer: usize, b: *mut c_double) -> c_int;
+    pub fn rcn_cuda_set_scale(h: rcn_cuda_handle, mean: c_double, sd: c_double) -> c_int;
+    pub fn rcn_cuda_get_scale(h: rcn_cuda_handle, mean: *mut c_double, sd: *mut c_double) -> c_int;
+    pub fn rcn_cuda_features(h: rcn_cuda_handle, images: *const c_void, pixel_format: c_int, B: usize, H: usize, W: usize,
+                             standardise: c_int, out: *mut c_double) -> c_int;
+    pub fn rcn_cuda_gen_scales(h: rcn_cuda_handle, feats: *const c_double, L: usize, B: usize, mean: *mut c_double,
+                               sd: *mut c_double) -> c_int;
+    pub fn rcn_cuda_standardise(h: rcn_cuda_handle, feats: *mut c_double, n: usize) -> c_int;
+    pub fn rcn_cuda_forward(h: rcn_cuda_handle, feats: *const c_double, B: usize, out_acts: *mut c_double) -> c_int;
+    pub fn rcn_cuda_classify(h: rcn_cuda_handle, images: *const c_void, pixel_format: c_int, B: usize, H: usize, W: usize,
+                             labels_out: *mut i64) -> c_int;
+    pub fn rcn_cuda_evaluate(h: rcn_cuda_handle, feats: *const c_double, labels: *const i64, B: usize,
+                             accept: *mut u64) -> c_int;
+    pub fn rcn_cuda_train_batch(h: rcn_cuda_handle, feats: *const c_double, onehot: *const c_double, labels: *const i64,
+                                B: usize, eta: c_double) -> c_int;
+    pub fn rcn_cuda_train_batch_images(h: rcn_cuda_handle, images: *const c_void, pixel_format: c_int, labels: *const i64,
+                                       B: usize, H: usize, W: usize, eta: c_double) -> c_int;
+    pub fn rcn_cuda_convolve_2d(device: c_int, stream: *mut c_void, m: *const c_double, H: usize, W: usize,
+                                kernel: *const c_double, kh: usize, kw: usize, padding: c_int, out: *mut c_double) -> c_int;
+    pub fn rcn_cuda_convolve_2d_separated(device: c_int, stream: *mut c_void, m: *const c_double, H: usize, W: usize,
+                                          op: c_int, padding: c_int, out: *mut c_double) -> c_int;
+    pub fn rcn_cuda_relu(device: c_int, stream: *mut c_void, m: *const c_double, n: usize, out: *mut c_double) -> c_int;
+    pub fn rcn_cuda_pool_2d(device: c_int, stream: *mut c_void, m: *const c_double, H: usize, W: usize, padding: c_int,
+                            pooling: c_int, out: *mut c_double, argmax_out: *mut u8) -> c_int;
+}
