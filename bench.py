@@ -86,60 +86,123 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NVML is polled in-process every few ms (a timed region of this workload can be shorter than one `nvidia-smi -lms`
+    period); samples carry a host timestamp and only those inside [mark_begin, mark_end] are reported. Falls back to an
+    `nvidia-smi -lms 100` subprocess when pynvml is unavailable."""
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, gpu_index, period_s=0.004):
+        self.gpu, self.period = gpu_index, period_s
+        self.samples, self.windows = [], []
+        self.stop_flag = False
+        self.thread = None
+        self.max_mhz = None
+        self.mode = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                    idx = int(ids[self.gpu])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.mode = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.mode = "nvidia-smi"
+            try:
+                q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                              "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.thread = threading.Thread(target=self._poll_smi, daemon=True)
+                self.thread.start()
+            except Exception:
+                self.mode = None
 
-    def _read(self):
+    def _poll_nvml(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.perf_counter(), sm, mask))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def _poll_smi(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm, mx = float(f[0]), float(f[1])
+            except (ValueError, IndexError):
+                continue
+            self.max_mhz = mx
+            mask = 0
+            for bit, v in zip([0x8, 0x40, 0x20, 0x4], f[2:6]):
+                if v.lower().startswith("active"):
+                    mask |= bit
+            self.samples.append((time.perf_counter(), sm, mask))
+
+    def mark_begin(self):
+        self._t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.windows.append((self._t0, time.perf_counter()))
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        time.sleep(0.02 if self.mode == "nvml" else 0.15)
+        self.stop_flag = True
+        if self.mode == "nvidia-smi":
+            self.proc.terminate()
+        inside = [x for x in self.samples if any(a <= x[0] <= b for a, b in self.windows)]
+        note = "samples inside the timed regions"
+        if not inside and self.windows:      # region shorter than one sampling period: nearest samples under the same load
+            a, b = self.windows[0][0], self.windows[-1][1]
+            inside = [x for x in self.samples if a - 0.25 <= x[0] <= b + 0.05]
+            note = "timed region shorter than a sampling period: samples within 250 ms before it (warm-up, same load)"
+        mask = 0
+        for x in inside:
+            mask |= x[2]
+        sm = [x[1] for x in inside]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(name for bit, name in self.REASONS.items() if mask & bit), "samples": len(sm),
+                "source": self.mode, "note": note}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle's threaded train step (C++ restatement of rcn's CPU path -- NOT rustc output)
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_train_steps(wl, steps, warmup, max_seconds=None):
+def cpu_sample_batch(wl, cores):
+    """Bounded CPU sample: the full minibatch when one CPU step is small, else a sub-batch of the same workload sized
+    to ~2e10 flop per step (the per-sample cost of the reference algorithm does not depend on the batch size)."""
+    shapes = layer_shapes(wl)
+    fwd, bwd_d, bwd_w = dense_flops_per_image(shapes)
+    per_image = fwd + bwd_d + bwd_w + 12 * 4 * wl["H"] * wl["W"]
+    b = int(2e10 // per_image)
+    b = max(4 * cores, b - b % max(1, cores))
+    return min(wl["batch"], b)
+
+
+def cpu_train_steps(wl, steps, warmup, max_seconds=None, batch=None):
     import oracle as O
-    B, H, W = wl["batch"], wl["H"], wl["W"]
+    B, H, W = batch or wl["batch"], wl["H"], wl["W"]
     shapes = layer_shapes(wl)
     net = O.Net(shapes)
     rng = np.random.default_rng(DATA_SEED)
@@ -149,34 +212,39 @@ def cpu_train_steps(wl, steps, warmup, max_seconds=None):
     params = np.random.default_rng(PARAM_SEED).standard_normal(net.n_params)
     mean, sd = O.gen_scales(O.features_u8(wl["cfg"], images[0][:min(B, 256)]))
     cores = os.cpu_count() or 1
+    t_w = time.perf_counter()
     for i in range(warmup):
         net.train_step_u8(wl["cfg"], params, images[i % n_pool], labels, mean, sd, ETA, cores)
+        if max_seconds and time.perf_counter() - t_w > max_seconds / 2:
+            break
     t0 = time.perf_counter()
     done = 0
     for i in range(steps):
         net.train_step_u8(wl["cfg"], params, images[i % n_pool], labels, mean, sd, ETA, cores)
         done += 1
-        if max_seconds and time.perf_counter() - t0 > max_seconds and done >= 3:
+        if max_seconds and time.perf_counter() - t0 > max_seconds:
             break
     dt = time.perf_counter() - t0
-    return done * B / dt, dt / done * 1e3, done, cores
+    return done * B / dt, dt / done * 1e3, done, cores, B
 
 
 def run_reference(args, wl, rank, world):
     if rank != 0:
         return
-    # bounded sample: each step is one minibatch of the same workload on all host threads; cap the run at ~2 min
-    B = wl["batch"]
-    ips, ms, done, cores = cpu_train_steps(wl, args.steps, args.warmup, max_seconds=120.0)
+    # bounded sample: each step is one (sub-)minibatch of the same workload on all host threads; cap the run at ~2 min
+    cores = os.cpu_count() or 1
+    Bs = cpu_sample_batch(wl, cores)
+    ips, ms, done, cores, Bs = cpu_train_steps(wl, args.steps, args.warmup, max_seconds=100.0, batch=Bs)
+    sample = (f"{done} steps of batch {Bs} (features+fwd+bwd+SGD) on {cores} host threads" +
+              ("" if Bs == wl["batch"] else f"; sub-batch of the {wl['batch']}-image minibatch, per-sample cost is batch-independent"))
     line = {
         "impl": "reference", "metric": "training images/sec", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": done, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "batch_per_step": B, "pixels": "u8", "eta": ETA,
+        "config": {"workload": wl["desc"], "batch_per_step": Bs, "pixels": "u8", "eta": ETA,
                    "note": "C++ restatement of rcn's CPU path (oracle/rcn_oracle.cpp: per-sample matvec backprop, worker threads "
                            "+ mutex-ordered gradient sum as rcn.rs:176-223); the Rust crate cannot be built here (no rustc)"},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{done} steps of batch {B} (features+fwd+bwd+SGD) on {cores} host threads"},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit_result(line)
@@ -260,20 +328,32 @@ def run_gpu(args, wl, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    barrier()
-    l0 = _lib.kernel_launches()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    # warm-up: at least W steps and at least ~0.3 s of the same load, so clocks have ramped before the timed region
+    n_warm = max(args.warmup, 3)
+    t_w = time.perf_counter()
+    for i in range(n_warm):
+        step(i)
+    torch.cuda.synchronize()
+    per_step = max((time.perf_counter() - t_w) / n_warm, 1e-6)
+    extra = torch.tensor([min(200000, int(0.3 / per_step))], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(extra, 0)            # every rank must run the same number of (all-reducing) steps
+    for i in range(int(extra.item())):
+        step(n_warm + i)
+    n_warm += int(extra.item())
+    barrier()
+    l0 = _lib.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.mark_begin()
     e0.record(stream)
     for i in range(args.steps):
         step(args.warmup + i)
     e1.record(stream)
     barrier()
-    clk = clocks.stop() if rank == 0 else None
+    clocks.mark_end()
     launches = _lib.kernel_launches() - l0
     if kernels_per_step is not None:
         launches = kernels_per_step * args.steps   # graph replays re-launch the captured kernels
@@ -298,12 +378,14 @@ def run_gpu(args, wl, rank, world, local_rank):
     for i in range(3):
         e2e_step(i)
     barrier()
-    t0 = time.perf_counter()
+    clocks.mark_begin()
     e0.record(stream)
     for i in range(args.steps):
         e2e_step(i)
     e1.record(stream)
     barrier()
+    clocks.mark_end()
+    clk = clocks.stop() if rank == 0 else None
     e2e_ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
@@ -340,39 +422,69 @@ def run_gpu(args, wl, rank, world, local_rank):
     _lib.profile_enable(False)
     pk = peaks()
     fwd, bwd_d, bwd_w = dense_flops_per_image(shapes)
-    alg = {  # algorithmic work per launch of each kernel
-        "features_fused_kernel": ("hbm", B * (H * W * 1 + L * 8)),
-        "dense_forward_gemm": ("tensor", B * fwd / len(shapes)),
-        "dense_backward_data_gemm": ("tensor", B * bwd_d / max(1, len(shapes) - 1)),
-        "dense_backward_weight_gemm": ("tensor", B * bwd_w / len(shapes)),
-        "sgd_update_kernel": ("hbm", 3 * n_params * 8),
+    sum_rows = sum(r for r, _ in shapes)
+    act_bytes = 2 * sum_rows * 8                      # a_l and delta_l written once per sample
+    # algorithmic work per launch of each kernel: (bound, bytes, flops)
+    alg = {
+        "features_fused_kernel": ("hbm", B * (H * W * 1 + L * 8), B * 48 * H * W),
+        "smallnet_fwd_bwd_kernel(fused features)": ("hbm", B * (H * W * 1 + 8 + L * 8 + act_bytes) + n_params * 8,
+                                                    B * (48 * H * W + fwd + bwd_d)),
+        "smallnet_fwd_bwd_kernel": ("hbm", B * (L * 8 + 8 + act_bytes) + n_params * 8, B * (fwd + bwd_d)),
+        "smallnet_wgrad_kernel": ("hbm", B * (L + shapes[0][0]) * 8 + n_params * 8, B * bwd_w),
+        "dense_forward_gemm": ("tensor", None, B * fwd / len(shapes)),
+        "dense_backward_data_gemm": ("tensor", None, B * bwd_d / max(1, len(shapes) - 1)),
+        "dense_backward_weight_gemm": ("tensor", None, B * bwd_w / len(shapes)),
+        "sgd_update_kernel": ("hbm", 3 * n_params * 8, 2 * n_params),
     }
     kernels = {k: {"launches_per_step": v["launches"] / prof_steps, "avg_us": v["total_ms"] / v["launches"] * 1e3,
                    "share": None} for k, v in prof.items()}
     tot = sum(v["total_ms"] for v in prof.values())
+    fp64_peak = measure_fp64_peak(torch, dev)
     for k, v in prof.items():
         kernels[k]["share"] = round(v["total_ms"] / tot, 4)
+        if k in alg:
+            d_s = v["total_ms"] / v["launches"] * 1e-3
+            bnd, nbytes, nflops = alg[k]
+            kernels[k]["bound"] = bnd
+            if nbytes:
+                kernels[k]["GBps"] = round(nbytes / d_s / 1e9, 1)
+                kernels[k]["frac_hbm"] = round(nbytes / d_s / 1e9 / pk["hbm_gbs"], 4)
+            if nflops:
+                kernels[k]["TFLOPs_f64"] = round(nflops / d_s / 1e12, 3)
+                kernels[k]["frac_fp64"] = round(nflops / d_s / 1e12 / fp64_peak, 4)
     top = max(prof, key=lambda k: prof[k]["total_ms"])
-    fp64_peak = measure_fp64_peak(torch, dev)
-    bound, work = alg.get(top, ("hbm", 0))
+    bound, nbytes, nflops = alg.get(top, ("hbm", 0, 0))
     dur_s = prof[top]["total_ms"] / prof[top]["launches"] * 1e-3
     if bound == "hbm":
-        achieved, peak, unit = work / dur_s / 1e9, pk["hbm_gbs"], "GB/s"
+        achieved, peak, unit = nbytes / dur_s / 1e9, pk["hbm_gbs"], "GB/s"
     else:
-        achieved, peak, unit = work / dur_s / 1e12, fp64_peak, "TFLOP/s"
+        achieved, peak, unit = nflops / dur_s / 1e12, fp64_peak, "TFLOP/s"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed `ncu --set full` capture
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload, {}).get(top)
+    step_bytes = B * (H * W + 8) + 3 * n_params * 8           # compulsory HBM traffic of a whole step (intermediates on chip / in L2)
+    step_flops = B * (48 * H * W + fwd + bwd_d + bwd_w)
     roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-                "frac": achieved / peak if peak else None, "traffic": None,
+                "frac": achieved / peak if peak else None, "traffic": traffic,
                 "peak_source": pk["source"] if bound == "hbm" else "torch.matmul f64 8192^3 measured in this run (f64 DMMA path; "
                                                                    "MEASURED_PEAKS.json has no f64 figure)",
-                "precision": "f64", "fp64_dgemm_tflops_measured": fp64_peak, "kernels": kernels}
+                "precision": "f64", "fp64_dgemm_tflops_measured": fp64_peak,
+                "durations": "CUDA events around every launch on the launching stream, separate eager pass of "
+                             f"{prof_steps} steps (the timed region replays a CUDA graph)",
+                "whole_step": {"ms": ms_step, "compulsory_GBps": step_bytes / (ms_step * 1e-3) / 1e9,
+                               "TFLOPs_f64": step_flops / (ms_step * 1e-3) / 1e12,
+                               "frac_fp64": step_flops / (ms_step * 1e-3) / 1e12 / fp64_peak},
+                "kernels": kernels}
 
     print("[bench] rank 0: cpu baseline", file=sys.stderr, flush=True)
     # ---- CPU baseline on this box's host cores (bounded sample, ~10-20 s) ------------------------------------------
-    cpu_ips, cpu_ms, cpu_done, cores = cpu_train_steps(wl, steps=10 ** 6, warmup=2, max_seconds=12.0)
+    Bs = cpu_sample_batch(wl, os.cpu_count() or 1)
+    cpu_ips, cpu_ms, cpu_done, cores, Bs = cpu_train_steps(wl, steps=10 ** 6, warmup=2, max_seconds=12.0, batch=Bs)
 
     line = {
         "metric": "training images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["desc"], "batch_per_gpu": B, "global_batch": B * world, "pixels": "u8", "eta": ETA,
                    "params": n_params, "parallelism": f"dp{world}",
@@ -384,7 +496,7 @@ def run_gpu(args, wl, rank, world, local_rank):
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_ips, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{cpu_done} steps of batch {B} (features+fwd+bwd+SGD) on {cores} host threads, "
+                         "sample": f"{cpu_done} steps of batch {Bs} (features+fwd+bwd+SGD) on {cores} host threads, "
                                    "oracle/rcn_oracle.cpp (C++ restatement of rcn's CPU path, not rustc output)"},
     }
     emit_result(line)
@@ -396,7 +508,7 @@ def run_gpu(args, wl, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
