@@ -184,6 +184,45 @@ int rcn_cuda_relu(int device, void* cuda_stream, const double* m, size_t n, doub
 int rcn_cuda_pool_2d(int device, void* cuda_stream, const double* m, size_t H, size_t W, int padding, int pooling,
                      double* out, uint8_t* argmax_out);
 
+/* ---- EXTENSIONS: operations BASELINE.json's north_star names that the reference does NOT implement ---------------
+ * ("parity unpinned": no reference code, test or golden vector exists, the checker
+ * is oracle/ext_oracle.cpp written from the definitions.)  Conventions extend the reference's own: cross-correlation
+ * without kernel flip and Padding::{None,Same} as Convolve2D::convolve_2d (kernel.rs:110-194); the 2x2 / stride-2
+ * window, bottom/right zero padding and last-maximal-element rule of Pool2D::pool_2d (kernel.rs:245-349).
+ * Tensors with channels are NHWC f64: x[((b*H + y)*W + x)*C + c]; weights w[co][ky][kx][ci]; dense-head matrices stay
+ * column-major (n x B).  `device` / `cuda_stream` / host-or-device pointers as for the op-level API above. */
+enum { RCN_ACT_NONE = 0, RCN_ACT_RELU = 1, RCN_ACT_SIGMOID = 2 };
+
+/* x1: learned convolution.  y = act(conv(x, w) + bias); Same keeps H x W (odd kernels), None gives (H-kh+1) x (W-kw+1). */
+int rcn_cuda_ext_conv2d_forward(int device, void* cuda_stream, const double* x, size_t B, size_t H, size_t W, size_t Ci,
+                                const double* w, const double* bias /* may be NULL */, size_t Co, size_t kh, size_t kw,
+                                int padding, int activation, double* y);
+/* dz = dy .* act'(y), with act' expressed through the stored output y (sigmoid: y(1-y), relu: y > 0). */
+int rcn_cuda_ext_activation_backward(int device, void* cuda_stream, const double* y, const double* dy, size_t n,
+                                     int activation, double* dz);
+/* dx = conv_transpose(dz, w), optionally fused with the previous layer's activation derivative:
+ * dx .*= act_prev'(y_prev) when y_prev != NULL (y_prev has x's shape).  H, W, Ci describe x. */
+int rcn_cuda_ext_conv2d_backward_data(int device, void* cuda_stream, const double* dz, size_t B, size_t H, size_t W,
+                                      size_t Ci, const double* w, size_t Co, size_t kh, size_t kw, int padding,
+                                      const double* y_prev, int activation_prev, double* dx);
+/* dw[co][ky][kx][ci] = sum over batch and pixels of dz * x (deterministic fixed-order split reduction); db[co] = sum dz
+ * (db may be NULL). */
+int rcn_cuda_ext_conv2d_backward_weight(int device, void* cuda_stream, const double* x, const double* dz, size_t B, size_t H,
+                                        size_t W, size_t Ci, size_t Co, size_t kh, size_t kw, int padding, double* dw,
+                                        double* db);
+/* x2: NHWC pooling, 2x2 window / stride 2.  pooling = RCN_POOLING_MAX or RCN_POOLING_AVERAGE (divides by 4 always).
+ * argmax_out (max only, may be NULL): 2*dy+dx of the chosen element, last maximal element wins. */
+int rcn_cuda_ext_pool2d_forward(int device, void* cuda_stream, const double* x, size_t B, size_t H, size_t W, size_t C,
+                                int padding, int pooling, double* y, uint8_t* argmax_out);
+/* H, W describe the pooling INPUT; dy / argmax have the pooled shape.  Max: dy is routed to the argmax element
+ * (dropped when that element is the zero padding); average: dy / 4 to every in-bounds element of the window. */
+int rcn_cuda_ext_pool2d_backward(int device, void* cuda_stream, const double* dy, const uint8_t* argmax, size_t B, size_t H,
+                                 size_t W, size_t C, int padding, int pooling, double* dx);
+/* x3: softmax + cross-entropy on column-major logits z (n x B): probs = softmax(z_b), loss[b] = -sum_i y_i log p_i,
+ * delta = probs - y (gradient of loss[b] w.r.t. z_b).  Exactly one of onehot (n x B) / labels (B); any output may be NULL. */
+int rcn_cuda_ext_softmax_xent(int device, void* cuda_stream, const double* z, size_t n, size_t B, const double* onehot,
+                              const int64_t* labels, double* probs, double* loss, double* delta);
+
 #ifdef __cplusplus
 }
 #endif

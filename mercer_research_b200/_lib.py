@@ -74,6 +74,14 @@ SIGNATURES = {
     "rcn_cuda_convolve_2d_separated": [_i, _vp, _vp, _sz, _sz, _i, _i, _vp],
     "rcn_cuda_relu": [_i, _vp, _vp, _sz, _vp],
     "rcn_cuda_pool_2d": [_i, _vp, _vp, _sz, _sz, _i, _i, _vp, _vp],
+    # extensions (not in the reference)
+    "rcn_cuda_ext_conv2d_forward": [_i, _vp, _vp, _sz, _sz, _sz, _sz, _vp, _vp, _sz, _sz, _sz, _i, _i, _vp],
+    "rcn_cuda_ext_activation_backward": [_i, _vp, _vp, _vp, _sz, _i, _vp],
+    "rcn_cuda_ext_conv2d_backward_data": [_i, _vp, _vp, _sz, _sz, _sz, _sz, _vp, _sz, _sz, _sz, _i, _vp, _i, _vp],
+    "rcn_cuda_ext_conv2d_backward_weight": [_i, _vp, _vp, _vp, _sz, _sz, _sz, _sz, _sz, _sz, _sz, _i, _vp, _vp],
+    "rcn_cuda_ext_pool2d_forward": [_i, _vp, _vp, _sz, _sz, _sz, _sz, _i, _i, _vp, _vp],
+    "rcn_cuda_ext_pool2d_backward": [_i, _vp, _vp, _vp, _sz, _sz, _sz, _sz, _i, _i, _vp],
+    "rcn_cuda_ext_softmax_xent": [_i, _vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp, _vp],
 }
 _RESTYPES = {"rcn_cuda_last_error": C.c_char_p}
 

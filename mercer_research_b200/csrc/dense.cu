@@ -14,6 +14,7 @@
 // recomputes sigmoid(z) (rcn.rs:491) which is bitwise the same value, and it must NOT be rewritten
 // algebraically (1-a cancels for saturated units and parity depends on cancelling identically).
 #include "dense.cuh"
+#include "gemm_f64.cuh"
 
 #include <cstdlib>
 
@@ -65,193 +66,32 @@ struct EpiStore {  // split-K partial (or final) store, column-major M x N
 };
 
 // ------------------------------------------------------------------------------------------------
-// DMMA GEMM:  C(m,n) = sum_k A(m,k) B(k,n), k in this split's range.
+// Dense GEMM dispatch on the shared DMMA core (gemm_f64.cuh):
 //   A(m,k): AK ? A[m*lda + k] : A[k*lda + m]        B(k,n): BKc ? B[n*ldb + k] : B[k*ldb + n]
 // ------------------------------------------------------------------------------------------------
-constexpr int KT = 16;       // k depth of one shared-memory tile
-constexpr int STAGES = 3;
-constexpr int GEMM_THREADS = 256;
-
-template <int ROWS, bool KCONTIG>
-struct TileLayout {
-    // +4 doubles of pitch: the 4 (k) x 4 (row) doubles a half-warp reads for one DMMA fragment fall into 16
-    // distinct 8-byte bank pairs.
-    static constexpr int PITCH = KCONTIG ? (KT + 4) : (ROWS + 4);
-    static constexpr int ELEMS = KCONTIG ? ROWS * PITCH : KT * PITCH;
-    __device__ __forceinline__ static int idx(int r, int kk) { return KCONTIG ? r * PITCH + kk : kk * PITCH + r; }
-};
-
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, int src_bytes) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-template <int ROWS, bool KCONTIG>
-__device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, int ld, int r0, int rmax, int k0,
-                                          int kmax, int tid) {
-    using TL = TileLayout<ROWS, KCONTIG>;
-    constexpr int N = ROWS * KT;
-#pragma unroll
-    for (int e = tid; e < N; e += GEMM_THREADS) {
-        int r, kk;
-        if (KCONTIG) { r = e / KT; kk = e % KT; } else { kk = e / ROWS; r = e % ROWS; }
-        const bool ok = (r0 + r < rmax) && (k0 + kk < kmax);
-        const size_t off = KCONTIG ? (size_t)(r0 + r) * ld + (k0 + kk) : (size_t)(k0 + kk) * ld + (r0 + r);
-        cp_async8(s + TL::idx(r, kk), ok ? g + off : g, ok ? 8 : 0);  // src-size 0 => zero fill
-    }
-}
-
-__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
-template <int BM, int BN, int WM, int WN, bool AK, bool BKc, typename Epi>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_dmma_kernel(const double* __restrict__ A, int lda,
-                                                                      const double* __restrict__ B, int ldb, int M, int N,
-                                                                      int K, int k_per_split, Epi epi) {
-    static_assert((BM / WM) * (BN / WN) == GEMM_THREADS / 32, "warp grid must use all warps");
-    using TA = TileLayout<BM, AK>;
-    using TB = TileLayout<BN, BKc>;
-    constexpr int MF = WM / 8, NF = WN / 8;
-    extern __shared__ __align__(16) double smem_gemm[];
-    double* sA = smem_gemm;
-    double* sB = smem_gemm + STAGES * TA::ELEMS;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t = lane & 3;
-    const int wm = warp % (BM / WM), wn = warp / (BM / WM);
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-    const int k_begin = blockIdx.z * k_per_split;
-    const int k_end = min(K, k_begin + k_per_split);
-    const int ntiles = (k_end - k_begin + KT - 1) / KT;
-
-    double acc[MF][NF][2];
-#pragma unroll
-    for (int i = 0; i < MF; ++i)
-#pragma unroll
-        for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < ntiles) {
-            load_tile<BM, AK>(sA + s * TA::ELEMS, A, lda, m0, M, k_begin + s * KT, k_end, tid);
-            load_tile<BN, BKc>(sB + s * TB::ELEMS, B, ldb, n0, N, k_begin + s * KT, k_end, tid);
-        }
-        cp_async_commit();
-    }
-
-    for (int kt = 0; kt < ntiles; ++kt) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();  // tile kt landed for everyone; everyone is done reading tile kt-1's slot
-        {
-            const int nk = kt + STAGES - 1;
-            if (nk < ntiles) {
-                const int slot = nk % STAGES;
-                load_tile<BM, AK>(sA + slot * TA::ELEMS, A, lda, m0, M, k_begin + nk * KT, k_end, tid);
-                load_tile<BN, BKc>(sB + slot * TB::ELEMS, B, ldb, n0, N, k_begin + nk * KT, k_end, tid);
-            }
-            cp_async_commit();
-        }
-        const double* a_s = sA + (kt % STAGES) * TA::ELEMS;
-        const double* b_s = sB + (kt % STAGES) * TB::ELEMS;
-#pragma unroll
-        for (int ks = 0; ks < KT; ks += 4) {
-            double af[MF], bf[NF];
-#pragma unroll
-            for (int i = 0; i < MF; ++i) af[i] = a_s[TA::idx(wm * WM + i * 8 + g, ks + t)];  // A frag: row g, col t
-#pragma unroll
-            for (int j = 0; j < NF; ++j) bf[j] = b_s[TB::idx(wn * WN + j * 8 + g, ks + t)];  // B frag: row t, col g
-#pragma unroll
-            for (int i = 0; i < MF; ++i)
-#pragma unroll
-                for (int j = 0; j < NF; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-        }
-    }
-    cp_async_wait<0>();
-
-    // C frag: row g, cols 2t, 2t+1
-#pragma unroll
-    for (int i = 0; i < MF; ++i) {
-        const int m = m0 + wm * WM + i * 8 + g;
-        if (m >= M) continue;
-#pragma unroll
-        for (int j = 0; j < NF; ++j) {
-            const int n = n0 + wn * WN + j * 8 + 2 * t;
-            if (n < N) epi(m, n, acc[i][j][0]);
-            if (n + 1 < N) epi(m, n + 1, acc[i][j][1]);
-        }
-    }
-}
-
-// Plain one-thread-per-output kernel: slow, obviously correct; cross-checks the DMMA path (RCN_CUDA_GEMM=simt).
-template <bool AK, bool BKc, typename Epi>
-__global__ void gemm_f64_simt_kernel(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb, int M,
-                                     int N, int K, int k_per_split, Epi epi) {
-    const int m = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int n = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (m >= M || n >= N) return;
-    const int k_begin = blockIdx.z * k_per_split, k_end = min(K, k_begin + k_per_split);
-    double acc = 0.0;
-    for (int k = k_begin; k < k_end; ++k) {
-        const double a = AK ? A[(size_t)m * lda + k] : A[(size_t)k * lda + m];
-        const double b = BKc ? B[(size_t)n * ldb + k] : B[(size_t)k * ldb + n];
-        acc = fma(a, b, acc);
-    }
-    epi(m, n, acc);
-}
-
-template <int BM, int BN, int WM, int WN, bool AK, bool BKc, typename Epi>
-static int launch_dmma(const char* name, const double* A, int lda, const double* B, int ldb, int M, int N, int K, int splits,
-                       int k_per_split, const Epi& epi, cudaStream_t stream) {
-    using TA = TileLayout<BM, AK>;
-    using TB = TileLayout<BN, BKc>;
-    constexpr size_t smem = (size_t)STAGES * (TA::ELEMS + TB::ELEMS) * sizeof(double);
-    auto kern = gemm_f64_dmma_kernel<BM, BN, WM, WN, AK, BKc, Epi>;
-    static bool attr_done = false;  // per instantiation
-    if (!attr_done) {
-        RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
-    dim3 grid(cdiv(M, BM), cdiv(N, BN), splits);
-    RCN_LAUNCH(name, stream, kern<<<grid, GEMM_THREADS, smem, stream>>>(A, lda, B, ldb, M, N, K, k_per_split, epi));
-    return RCN_OK;
-}
-
 template <bool AK, bool BKc, typename Epi>
 static int launch_gemm(const char* name, const double* A, int lda, const double* B, int ldb, size_t M_, size_t N_, size_t K_,
                        int splits, const Epi& epi, cudaStream_t stream) {
     if (M_ == 0 || N_ == 0) return RCN_OK;
     if (M_ > 0x7fffffff || N_ > 0x7fffffff || K_ > 0x7fffffff) return fail(RCN_ERR_INVALID, "GEMM dimension too large");
     const int M = (int)M_, N = (int)N_, K = (int)K_;
-    if (splits < 1) splits = 1;
-    int k_per_split = (K + splits - 1) / splits;
-    k_per_split = ((k_per_split + KT - 1) / KT) * KT;
-    if (k_per_split < KT) k_per_split = KT;
-    splits = K > 0 ? (K + k_per_split - 1) / k_per_split : 1;
+    int k_per_split;
+    split_plan(K, splits, k_per_split);
     if (gemm_impl() == GEMM_SIMT) {
         dim3 grid(cdiv(M, 32), cdiv(N, 8), splits);
         RCN_LAUNCH(name, stream, gemm_f64_simt_kernel<AK, BKc, Epi><<<grid, 256, 0, stream>>>(A, lda, B, ldb, M, N, K, k_per_split, epi));
         return RCN_OK;
     }
-    if (M <= 32) return launch_dmma<32, 128, 32, 16, AK, BKc, Epi>(name, A, lda, B, ldb, M, N, K, splits, k_per_split, epi, stream);
-    const size_t big_tiles = (size_t)cdiv(M, 128) * cdiv(N, 128) * splits;
-    if (big_tiles >= (size_t)kNumSMs)
-        return launch_dmma<128, 128, 64, 32, AK, BKc, Epi>(name, A, lda, B, ldb, M, N, K, splits, k_per_split, epi, stream);
-    return launch_dmma<64, 64, 32, 16, AK, BKc, Epi>(name, A, lda, B, ldb, M, N, K, splits, k_per_split, epi, stream);
+    const DenseLoader<AK> la{A, lda, M};
+    const DenseLoader<BKc> lb{B, ldb, N};
+    return launch_gemm_tiles(name, la, lb, M, N, K, splits, k_per_split, epi, stream);
 }
 
 // Effective split count launch_gemm will use (so callers can size the partial workspace).
 static int effective_splits(size_t K, int splits) {
-    if (splits < 1) splits = 1;
-    int k_per_split = (int)((K + splits - 1) / splits);
-    k_per_split = ((k_per_split + KT - 1) / KT) * KT;
-    if (k_per_split < KT) k_per_split = KT;
-    return K > 0 ? (int)((K + k_per_split - 1) / k_per_split) : 1;
+    int k_per_split;
+    split_plan((int)K, splits, k_per_split);
+    return splits;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -297,6 +137,18 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const double* __restrict
     }
 }
 
+int launch_reduce_splits(const double* partials, int splits, size_t n, double* out, cudaStream_t stream) {
+    unsigned grid = cdiv(n, 256);
+    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    RCN_LAUNCH("reduce_splits_kernel", stream, reduce_splits_kernel<<<grid, 256, 0, stream>>>(partials, splits, n, out));
+    return RCN_OK;
+}
+
+int launch_bias_grad(const double* delta, size_t M, size_t N, double* db, cudaStream_t stream) {
+    RCN_LAUNCH("bias_grad_kernel", stream, bias_grad_kernel<<<cdiv(M, 32), 256, 0, stream>>>(delta, (int)M, (int)N, db));
+    return RCN_OK;
+}
+
 int launch_dense_backward_weight(const double* delta, const double* A_prev, size_t M, size_t N, size_t Kb, double* dW,
                                  double* db, DevBuf& workspace, cudaStream_t stream) {
     if (M == 0) return RCN_OK;
@@ -324,13 +176,10 @@ int launch_dense_backward_weight(const double* delta, const double* A_prev, size
             RCN_TRY(workspace.reserve((size_t)splits * M * N * sizeof(double)));
             EpiStore epi{workspace.as<double>(), (int)M, M * N};
             RCN_TRY((launch_gemm<false, false, EpiStore>("dense_backward_weight_gemm", delta, (int)M, A_prev, (int)N, M, N, Kb, splits, epi, stream)));
-            unsigned grid = cdiv(M * N, 256);
-            if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-            RCN_LAUNCH("reduce_splits_kernel", stream, reduce_splits_kernel<<<grid, 256, 0, stream>>>(workspace.as<double>(), splits, M * N, dW));
+            RCN_TRY(launch_reduce_splits(workspace.as<double>(), splits, M * N, dW, stream));
         }
     }
-    RCN_LAUNCH("bias_grad_kernel", stream, bias_grad_kernel<<<cdiv(M, 32), 256, 0, stream>>>(delta, (int)M, (int)Kb, db));
-    return RCN_OK;
+    return launch_bias_grad(delta, M, Kb, db, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

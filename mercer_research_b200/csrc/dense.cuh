@@ -25,6 +25,11 @@ int launch_dense_backward_data(const double* W_up, const double* delta_up, const
 int launch_dense_backward_weight(const double* delta, const double* A_prev, size_t M, size_t N, size_t Kb, double* dW,
                                  double* db, DevBuf& workspace, cudaStream_t stream);
 
+// out[i] = sum_p partials[p*n + i], p ascending (deterministic split-K combine)
+int launch_reduce_splits(const double* partials, int splits, size_t n, double* out, cudaStream_t stream);
+// db[m] = sum_n delta[m + n*M]  (delta M x N column-major), fixed summation order
+int launch_bias_grad(const double* delta, size_t M, size_t N, double* db, cudaStream_t stream);
+
 // params -= scale * grads   (rcn.rs:210-222, scale = eta / batch formed first)
 // cursor (optional): device-side position of the epoch walk, advanced by `batch` with chunks_exact wrap-around.
 int launch_sgd_update(double* params, const double* grads, size_t n, double scale, cudaStream_t stream,

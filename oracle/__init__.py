@@ -34,8 +34,8 @@ class RefPanic(Exception):
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "rcn_oracle.cpp")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("rcn_oracle.cpp", "ext_oracle.cpp", "Makefile")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(s) for s in srcs):
         subprocess.run(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), check=True)
     return _SO
 
