@@ -290,7 +290,7 @@ def run_gpu(args, wl, rank, world, local_rank):
     model.load_weights_and_bias(L)
     assert model.layer_shapes == shapes
     model.set_params(np.random.default_rng(PARAM_SEED).standard_normal(n_params))   # same replica on every rank
-    trainer = DataParallelTrainer(model, eta=ETA)
+    trainer = DataParallelTrainer(model, eta=ETA, exchange=args.exchange)
 
     # synthetic dataset resident in HBM, larger than L2 (126 MB) so that consecutive steps never hit in L2
     pool_bytes = 192 << 20
@@ -313,6 +313,7 @@ def run_gpu(args, wl, rank, world, local_rank):
     # so ONE captured CUDA graph (all kernels + the all-reduce) replays for every step.
     all_labels = labels.repeat(n_batches)
     trainer.bind_dataset(images.view(n_batches * B, H, W), all_labels, B)
+    step_desc = trainer.describe()
     kernels_per_step = None
     if not args.no_graph:
         l_before = _lib.kernel_launches()
@@ -365,23 +366,26 @@ def run_gpu(args, wl, rank, world, local_rank):
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
 
-    # ---- e2e: the reference-facing call with HOST buffers (pinned), H2D + D2H inside the timed region -------------
-    n_host = 8
-    h_images = torch.randint(0, 256, (n_host, B, H, W), dtype=torch.uint8).pin_memory()
-    h_labels = (torch.arange(B) % wl["classes"]).to(torch.int64).pin_memory()
-    hi = [h_images[i].numpy() for i in range(n_host)]
-    hl = h_labels.numpy()
+    # ---- e2e: the reference-facing call with HOST buffers (pinned): the chunks_exact loop of rcn.rs:147-149 over a
+    # host-resident dataset; every step's H2D copy and the D2H read of its (cost, hits) are inside the timed region -----
+    n_host = max(2, min(args.steps, (512 << 20) // (B * H * W)))
+    h_images = torch.randint(0, 256, (n_host * B, H, W), dtype=torch.uint8).pin_memory()
+    h_labels = (torch.arange(n_host * B) % wl["classes"]).to(torch.int64).pin_memory()
+    hi, hl = h_images.numpy(), h_labels.numpy()
 
-    def e2e_step(i):
-        return trainer.step_images_host(hi[i % n_host], hl)   # returns (cost, hits) read back from the device
+    def e2e_steps(n):
+        done = 0
+        while done < n:
+            m = min(n_host, n - done)
+            cost, hits = trainer.train_epoch_host(hi[:m * B], hl[:m * B], B)
+            assert len(cost) == m
+            done += m
 
-    for i in range(3):
-        e2e_step(i)
+    e2e_steps(3)
     barrier()
     clocks.mark_begin()
     e0.record(stream)
-    for i in range(args.steps):
-        e2e_step(i)
+    e2e_steps(args.steps)
     e1.record(stream)
     barrier()
     clocks.mark_end()
@@ -402,6 +406,10 @@ def run_gpu(args, wl, rank, world, local_rank):
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
+        if trainer.p2p:                 # rank 0's profiling pass below must not wait for peers that have left
+            model.dp_shutdown()
+            trainer.p2p = False
+            dist.barrier()
         if rank != 0:
             # destroy_process_group() was seen to block with a captured NCCL graph on this stack (torch 2.11 / NCCL
             # 2.28): leave without running the destructors; every collective has completed at the barrier above.
@@ -489,10 +497,12 @@ def run_gpu(args, wl, rank, world, local_rank):
         "config": {"workload": wl["desc"], "batch_per_gpu": B, "global_batch": B * world, "pixels": "u8", "eta": ETA,
                    "params": n_params, "parallelism": f"dp{world}",
                    "l2_policy": f"inputs rotate over {n_batches} resident batches = {n_batches * B * H * W / 2 ** 20:.0f} MiB > 126 MB L2",
-                   "step": trainer.describe(), "cuda_graph": not args.no_graph},
+                   "step": step_desc, "cuda_graph": not args.no_graph},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / args.steps, "host_buffers": "pinned"},
+                "ms_per_step": e2e_ms / args.steps, "host_buffers": "pinned",
+                "api": "rcn_cuda_train_epoch_host (chunks_exact loop over a host dataset; H2D of step k+1 overlaps step k; "
+                       "per-step cost/hits read back)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_ips, "unit": "images/s", "cores": cores, "kind": "port",
@@ -513,6 +523,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="multi-GPU gradient exchange: fused NVLink peer-memory kernel, NCCL all-reduce, or by size")
     args = ap.parse_args()
     # stdout must carry exactly ONE JSON line: route everything else that writes to fd 1 (e.g. NCCL's version banner)
     # to stderr and keep the real stdout for the result line.

@@ -151,6 +151,33 @@ int rcn_cuda_epoch_accumulate(rcn_cuda_handle h);
 int rcn_cuda_epoch_apply(rcn_cuda_handle h, double eta, size_t global_batch);
 int rcn_cuda_epoch_step(rcn_cuda_handle h, double eta); /* accumulate + apply with global_batch = B */
 
+/* The same loop over a HOST-resident (already shuffled) dataset: `for batch in training_set.chunks_exact(B) {
+ * train_batch(batch, eta) }` (rcn.rs:147-149). The host->device copy of chunk k+1 runs on a second stream while the
+ * kernels of chunk k execute (double-buffered staging; pin the host buffers for real overlap); every step's result --
+ * quadratic cost and rcn.rs:153-157 hit count under the pre-update parameters -- is copied back per step into
+ * cost_out / hits_out (n_samples / B entries each, may be NULL). global_batch = 0 means B x (data-parallel world).
+ * In a connected data-parallel group every rank calls this with its own shard of each global minibatch. */
+int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_format, const int64_t* labels,
+                              size_t n_samples, size_t H, size_t W, size_t B, double eta, size_t global_batch,
+                              double* cost_out, uint64_t* hits_out, size_t* n_steps_out);
+
+/* ---- data-parallel group: gradient exchange fused with the update over NVLink peer memory -------------------------
+ * The reduction of rcn.rs:190-205 across the GPUs of one box. After a group is connected,
+ * rcn_cuda_apply_gradients / rcn_cuda_epoch_apply / rcn_cuda_train_epoch_host run ONE kernel that pushes this rank's
+ * gradient sums into every peer's receive slots over NVLink, waits for the peers' pushes, adds the ranks in rank
+ * order (replicas stay bit-identical) and applies W -= (eta / global_batch) * sum. No host-side collective call is
+ * needed between accumulate and apply. Intended for latency-bound gradient sizes (up to ~1M parameters); larger
+ * models use an NCCL all-reduce on the bound gradient buffer instead (mercer_research_b200/trainer.py).
+ *   dp_init          allocates this rank's communication block; ipc_handle_out (64 bytes, may be NULL) receives its
+ *                    cudaIpcMemHandle_t for ranks living in other processes.
+ *   dp_connect_ipc   all_handles = world x 64 bytes, the handles of ranks 0..world-1 (own entry ignored).
+ *   dp_connect_local group = world handles living in THIS process (one per device; peer access is enabled).
+ * Every rank must execute the same sequence of apply calls. */
+int rcn_cuda_dp_init(rcn_cuda_handle h, int world, int rank, void* ipc_handle_out);
+int rcn_cuda_dp_connect_ipc(rcn_cuda_handle h, const void* all_handles);
+int rcn_cuda_dp_connect_local(rcn_cuda_handle h, const rcn_cuda_handle* group);
+int rcn_cuda_dp_shutdown(rcn_cuda_handle h);
+
 /* Gradient buffer access for the data-parallel trainer. bind: use caller-owned DEVICE memory (e.g. a torch
  * tensor that NCCL all-reduces) as the flat gradient buffer; NULL restores the internal one. */
 int rcn_cuda_bind_gradient_buffer(rcn_cuda_handle h, double* device_ptr, size_t n);

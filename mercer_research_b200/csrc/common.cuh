@@ -98,6 +98,19 @@ struct StagedIn {
     }
 };
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: remembers, per kernel call site and device, the
+// largest size already granted (one process may drive several GPUs, e.g. rcn_cuda_dp_connect_local).
+struct SmemAttrCache {
+    size_t granted[64] = {};
+    bool need(size_t smem) {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) { cudaGetLastError(); return true; }
+        if (smem <= granted[d]) return false;
+        granted[d] = smem;
+        return true;
+    }
+};
+
 constexpr int kNumSMs = 148;  // B200
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }

@@ -265,11 +265,9 @@ int launch_conv2d_forward(const double* x, const double* w, const double* bias, 
     if (use_direct(s)) {
         const size_t kk = s.kh * s.kw * s.Ci;
         const size_t smem = ((DT + s.kh - 1) * (DT + s.kw - 1) * s.Ci + s.Co * kk) * sizeof(double);
-        static size_t attr = 48 * 1024;
-        if (smem > attr) {
+        static SmemAttrCache attr;
+        if (smem > 48 * 1024 && attr.need(smem))
             RCN_CUDA_TRY(cudaFuncSetAttribute(conv2d_direct_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = smem;
-        }
         if (s.B > 65535) return fail(RCN_ERR_INVALID, "batch too large for the direct convolution kernel");
         dim3 grid(cdiv(s.Wo, DT), cdiv(s.Ho, DT), (unsigned)s.B);
         RCN_LAUNCH("conv2d_direct_small_kernel", stream,

@@ -173,11 +173,8 @@ static int launch_dmma(const char* name, const ALoad& la, const BLoad& lb, int M
     constexpr size_t smem = (size_t)STAGES * (TA::ELEMS + TB::ELEMS) * sizeof(double) +
                             (size_t)(BM * ALoad::kPrepInts + BN * BLoad::kPrepInts) * sizeof(int);
     auto kern = gemm_f64_dmma_kernel<BM, BN, WM, WN, ALoad, BLoad, Epi>;
-    static bool attr_done = false;  // per instantiation
-    if (!attr_done) {
-        RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    static SmemAttrCache attr;  // per instantiation
+    if (attr.need(smem)) RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(cdiv(M, BM), cdiv(N, BN), splits);
     RCN_LAUNCH(name, stream, kern<<<grid, GEMM_THREADS, smem, stream>>>(la, lb, M, N, K, k_per_split, epi));
     return RCN_OK;

@@ -12,6 +12,7 @@
 #include "features.cuh"
 #include "smallnet.cuh"
 #include "opctx.cuh"
+#include "dp.cuh"
 
 namespace rcn {
 
@@ -98,6 +99,13 @@ struct rcn_cuda_model {
     DevBuf ep_state;            // [cursor (int64) | pad | labels_batch (B x int64)]
     size_t last_B = 0;          // batch of the last accumulate call (taps)
     bool stats_valid = false;
+    // data-parallel group (dp.cu) and the pipelined host-dataset loop (rcn_cuda_train_epoch_host)
+    DpState dp;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    DevBuf host_slot[2];
+    double* stats_host = nullptr;   // pinned, 2 doubles per step
+    size_t stats_host_cap = 0;
 
     double* act(size_t l, size_t B) const {
         size_t off = 0;
@@ -317,6 +325,14 @@ int rcn_cuda_destroy(rcn_cuda_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+        if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
+        h->host_slot[i].release();
+    }
+    if (h->stats_host) cudaFreeHost(h->stats_host);
+    dp_release(h->dp);
     DevBuf* bufs[] = {&h->params, &h->grads_own, &h->in_stage, &h->tgt_stage, &h->feats, &h->acts, &h->deltas,
                       &h->gemm_ws, &h->out_stage, &h->small, &h->red_ws, &h->ep_state, &h->sn_counters, &h->fscratch.a, &h->fscratch.b};
     for (DevBuf* b : bufs) b->release();
@@ -646,6 +662,8 @@ int rcn_cuda_apply_gradients(rcn_cuda_handle h, double eta, size_t batch) {
     RCN_TRY(require_params(h));
     if (batch == 0) return RCN_OK;  // chunks_exact never yields an empty batch (rcn.rs:147)
     const double scale = eta / (double)batch;  // (eta / batch.len() as f64)  (rcn.rs:214)
+    if (h->dp.connected)   // exchange over NVLink peer memory fused with the update (dp.cu)
+        return launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale, h->stream, nullptr, 0, 0);
     return launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale, h->stream);
 }
 
@@ -729,6 +747,9 @@ int rcn_cuda_epoch_apply(rcn_cuda_handle h, double eta, size_t global_batch) {
     if (!h->ep_images) return fail(RCN_ERR_STATE, "no dataset bound: call rcn_cuda_epoch_bind first");
     if (global_batch == 0) return fail(RCN_ERR_INVALID, "global batch is zero");
     const double scale = eta / (double)global_batch;
+    if (h->dp.connected)
+        return launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale, h->stream, h->ep_state.as<long long>(),
+                                       (long long)h->ep_B, (long long)h->ep_n);
     return launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale, h->stream, h->ep_state.as<long long>(),
                              (long long)h->ep_B, (long long)h->ep_n);
 }
@@ -736,6 +757,137 @@ int rcn_cuda_epoch_apply(rcn_cuda_handle h, double eta, size_t global_batch) {
 int rcn_cuda_epoch_step(rcn_cuda_handle h, double eta) {
     RCN_TRY(rcn_cuda_epoch_accumulate(h));
     return rcn_cuda_epoch_apply(h, eta, h->ep_B);
+}
+
+// ---- pipelined loop over a HOST-resident dataset: rcn.rs:147-149 ------------------------------------------------------
+int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_format, const int64_t* labels,
+                              size_t n_samples, size_t H, size_t W, size_t B, double eta, size_t global_batch,
+                              double* cost_out, uint64_t* hits_out, size_t* n_steps_out) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (n_steps_out) *n_steps_out = 0;
+    if (B == 0) return fail(RCN_ERR_INVALID, "batch size is zero");
+    if (pixel_format != RCN_PIXELS_U8_ROWMAJOR && pixel_format != RCN_PIXELS_F64_COLMAJOR)
+        return fail(RCN_ERR_INVALID, "unknown pixel format %d", pixel_format);
+    const size_t n_steps = n_samples / B;       // chunks_exact: the remainder is dropped (rcn.rs:147)
+    if (n_steps == 0) return RCN_OK;
+    if (!images || !labels) return fail(RCN_ERR_INVALID, "null images / labels");
+    if (is_device_ptr(images) || is_device_ptr(labels))
+        return fail(RCN_ERR_INVALID, "train_epoch_host takes HOST buffers; use rcn_cuda_epoch_bind for a device-resident dataset");
+    RCN_TRY(ensure_plan(h, H, W));
+    RCN_TRY(check_feature_width(h, h->plan.L));
+    if (global_batch == 0) global_batch = B * (size_t)(h->dp.connected ? h->dp.world : 1);
+    const size_t img_bytes = B * H * W * pixel_bytes(pixel_format);
+    if (!h->copy_stream) {
+        RCN_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            RCN_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+            RCN_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming));
+        }
+    }
+    for (int i = 0; i < 2; ++i) RCN_TRY(h->host_slot[i].reserve(img_bytes));
+    // the labels of the whole epoch go up in ONE copy (one driver call per step less); images stream chunk by chunk
+    RCN_TRY(h->tgt_stage.reserve(n_steps * B * sizeof(int64_t)));
+    RCN_CUDA_TRY(cudaMemcpyAsync(h->tgt_stage.p, labels, n_steps * B * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    const int64_t* labels_dev = h->tgt_stage.as<int64_t>();
+    if (h->stats_host_cap < n_steps) {
+        if (h->stats_host) cudaFreeHost(h->stats_host);
+        h->stats_host = nullptr; h->stats_host_cap = 0;
+        RCN_CUDA_TRY(cudaHostAlloc((void**)&h->stats_host, n_steps * 2 * sizeof(double), cudaHostAllocDefault));
+        h->stats_host_cap = n_steps;
+    }
+    // everything the previous user of the staging slots enqueued on the compute stream must be finished first
+    RCN_CUDA_TRY(cudaEventRecord(h->ev_consumed[0], h->stream));
+    RCN_CUDA_TRY(cudaEventRecord(h->ev_consumed[1], h->stream));
+    const double scale = eta / (double)global_batch;   // (eta / batch.len() as f64)  (rcn.rs:214)
+    const char* img = (const char*)images;
+    for (size_t k = 0; k < n_steps; ++k) {
+        const int slot = (int)(k & 1);
+        char* dst = h->host_slot[slot].as<char>();
+        // H2D of chunk k on the copy stream: overlaps the kernels of chunk k-1
+        RCN_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0));
+        RCN_CUDA_TRY(cudaMemcpyAsync(dst, img + k * img_bytes, img_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        RCN_CUDA_TRY(cudaEventRecord(h->ev_copied[slot], h->copy_stream));
+        RCN_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copied[slot], 0));
+        RCN_TRY(accumulate_images_dev(h, dst, pixel_format, labels_dev + k * B, B, H, W, nullptr));
+        RCN_CUDA_TRY(cudaEventRecord(h->ev_consumed[slot], h->stream));
+        if (h->dp.connected)
+            RCN_TRY(launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale, h->stream, nullptr, 0, 0));
+        else
+            RCN_TRY(launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale, h->stream));
+        // D2H of this step's result (cost, hits evaluated with the pre-update parameters)
+        RCN_CUDA_TRY(cudaMemcpyAsync(h->stats_host + 2 * k, h->small.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    RCN_CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+    for (size_t k = 0; k < n_steps; ++k) {
+        if (cost_out) cost_out[k] = h->stats_host[2 * k];
+        if (hits_out) memcpy(&hits_out[k], &h->stats_host[2 * k + 1], sizeof(uint64_t));
+    }
+    if (n_steps_out) *n_steps_out = n_steps;
+    return RCN_OK;
+}
+
+// ---- data-parallel group (dp.cu) -------------------------------------------------------------------------------------
+int rcn_cuda_dp_init(rcn_cuda_handle h, int world, int rank, void* ipc_handle_out) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    RCN_TRY(dp_alloc(h->dp, world, rank, h->n_params, h->stream));
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t hd;
+        RCN_CUDA_TRY(cudaIpcGetMemHandle(&hd, h->dp.block));
+        static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(ipc_handle_out, &hd, sizeof(hd));
+    }
+    return RCN_OK;
+}
+
+int rcn_cuda_dp_connect_ipc(rcn_cuda_handle h, const void* all_handles) {
+    RCN_ENTER(h);
+    if (!h->dp.block) return fail(RCN_ERR_STATE, "call rcn_cuda_dp_init first");
+    if (!all_handles) return fail(RCN_ERR_INVALID, "null handles");
+    for (int q = 0; q < h->dp.world; ++q) {
+        if (q == h->dp.rank) continue;
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, (const char*)all_handles + (size_t)q * sizeof(hd), sizeof(hd));
+        void* p = nullptr;
+        RCN_CUDA_TRY(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+        h->dp.peers[q] = p; h->dp.imported[q] = true;
+    }
+    h->dp.connected = h->dp.world > 1;
+    return RCN_OK;
+}
+
+int rcn_cuda_dp_connect_local(rcn_cuda_handle h, const rcn_cuda_handle* group) {
+    RCN_ENTER(h);
+    if (!h->dp.block) return fail(RCN_ERR_STATE, "call rcn_cuda_dp_init first");
+    if (!group) return fail(RCN_ERR_INVALID, "null group");
+    for (int q = 0; q < h->dp.world; ++q) {
+        if (q == h->dp.rank) continue;
+        rcn_cuda_model* o = group[q];
+        if (!o || !o->dp.block || o->dp.world != h->dp.world || o->dp.rank != q || o->dp.n != h->dp.n)
+            return fail(RCN_ERR_INVALID, "group member %d is not an initialised rank %d of a %d-rank group with %zu parameters", q, q,
+                        h->dp.world, h->dp.n);
+        if (o->device != h->device) {
+            int can = 0;
+            RCN_CUDA_TRY(cudaDeviceCanAccessPeer(&can, h->device, o->device));
+            if (!can) return fail(RCN_ERR_CUDA, "device %d cannot access device %d as a peer", h->device, o->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(RCN_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d) failed: %s", o->device, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        h->dp.peers[q] = o->dp.block; h->dp.imported[q] = false;
+    }
+    h->dp.connected = h->dp.world > 1;
+    return RCN_OK;
+}
+
+int rcn_cuda_dp_shutdown(rcn_cuda_handle h) {
+    RCN_ENTER(h);
+    RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    dp_release(h->dp);
+    return RCN_OK;
 }
 
 int rcn_cuda_bind_gradient_buffer(rcn_cuda_handle h, double* device_ptr, size_t n) {

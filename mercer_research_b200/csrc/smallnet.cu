@@ -487,15 +487,15 @@ static int launch_kernel_a(const SmallNetDesc& d, const double* params, double* 
     static SmallNetFront empty_front{};
     if (fr) {
         auto kern = smallnet_fwd_bwd_kernel<true>;
-        static size_t attr = 0;
-        if (smem > attr) { RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+        static SmemAttrCache attr;
+        if (attr.need(smem)) RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RCN_LAUNCH("smallnet_fwd_bwd_kernel(fused features)", stream,
                    kern<<<n_tiles, SNA_THREADS, smem, stream>>>(d, params, feats, (int)B, onehot, labels, acts, deltas,
                                                                stats_partial, small_partial, backward, *fr));
     } else {
         auto kern = smallnet_fwd_bwd_kernel<false>;
-        static size_t attr = 0;
-        if (smem > attr) { RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+        static SmemAttrCache attr;
+        if (attr.need(smem)) RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RCN_LAUNCH("smallnet_fwd_bwd_kernel", stream,
                    kern<<<n_tiles, SNA_THREADS, smem, stream>>>(d, params, feats, (int)B, onehot, labels, acts, deltas,
                                                                stats_partial, small_partial, backward, empty_front));
@@ -526,11 +526,9 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
     RCN_TRY(launch_kernel_a(d, params, feats, B, onehot, labels, acts, deltas, stats_partial, small_partial, 1, front, stream));
 
     const size_t smem_b = (size_t)(n_small > SNB_TILE ? n_small : SNB_TILE) * sizeof(double);
-    static size_t attr_b = 0;
-    if (smem_b > attr_b) {   // static 36 KB + dynamic tile exceeds the 48 KB default
+    static SmemAttrCache attr_b;
+    if (attr_b.need(smem_b))   // static 36 KB + dynamic tile exceeds the 48 KB default
         RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-        attr_b = smem_b;
-    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(col_groups + 1, splits, 1);
     cfg.blockDim = dim3(SNB_THREADS, 1, 1);

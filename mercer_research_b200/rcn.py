@@ -395,6 +395,49 @@ class RCN:
     def epoch_step(self, eta: float):
         _lib.check(self._lib.rcn_cuda_epoch_step(self._h, float(eta)))
 
+    def train_epoch_host(self, images, labels, batch: int, eta: float, global_batch: int = 0):
+        """``for batch in training_set.chunks_exact(batch) { train_batch(batch, eta) }`` (rcn.rs:147-149) over a HOST
+        dataset (numpy, already shuffled; pin it for copy/compute overlap). The copy of chunk k+1 overlaps the kernels of
+        chunk k. Returns per-step (cost, hits) arrays, read back from the device every step."""
+        a = np.asarray(images)
+        if a.ndim != 3:
+            raise ValueError("images must be (N, H, W)")
+        if a.dtype == np.uint8:
+            img, fmt = np.ascontiguousarray(a), _lib.PIXELS_U8_ROWMAJOR
+        else:
+            img, fmt = np.ascontiguousarray(np.transpose(a, (0, 2, 1)), dtype=np.float64), _lib.PIXELS_F64_COLMAJOR
+        lab = np.ascontiguousarray(labels, dtype=np.int64)
+        N, H, W = a.shape
+        n_steps = N // int(batch)
+        cost = np.zeros(n_steps)
+        hits = np.zeros(n_steps, dtype=np.uint64)
+        done = C.c_size_t()
+        self._B_hint = int(batch)
+        _lib.check(self._lib.rcn_cuda_train_epoch_host(self._h, img.ctypes.data, fmt, lab.ctypes.data, N, H, W, int(batch),
+                                                       float(eta), int(global_batch), cost.ctypes.data, hits.ctypes.data,
+                                                       C.byref(done)))
+        return cost[:done.value], hits[:done.value]
+
+    # -- data-parallel group: exchange fused with the update over NVLink peer memory (csrc/dp.cu) --------------------
+    def dp_init(self, world: int, rank: int) -> bytes:
+        """Allocates this rank's communication block; returns its 64-byte CUDA IPC handle for the other processes."""
+        buf = C.create_string_buffer(64)
+        _lib.check(self._lib.rcn_cuda_dp_init(self._h, int(world), int(rank), buf))
+        return buf.raw
+
+    def dp_connect_ipc(self, handles: Sequence[bytes]):
+        """handles[r] = dp_init() result of rank r (one process per GPU)."""
+        blob = b"".join(handles)
+        _lib.check(self._lib.rcn_cuda_dp_connect_ipc(self._h, blob))
+
+    def dp_connect_local(self, group: Sequence["RCN"]):
+        """group[r] = the RCN of rank r living in THIS process (one per device)."""
+        arr = (C.c_void_p * len(group))(*[g._h.value for g in group])
+        _lib.check(self._lib.rcn_cuda_dp_connect_local(self._h, arr))
+
+    def dp_shutdown(self):
+        _lib.check(self._lib.rcn_cuda_dp_shutdown(self._h))
+
     def last_batch_stats(self) -> Tuple[float, int]:
         """(quadratic cost, hits) of the last accumulated batch, evaluated with the pre-update parameters."""
         c, h = C.c_double(), C.c_uint64()

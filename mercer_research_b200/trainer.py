@@ -24,8 +24,15 @@ def shard_bounds(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
     return rank * per, (rank + 1) * per
 
 
+# One-shot exchange over NVLink peer memory (csrc/dp.cu) is used while every rank pushes at most this many bytes per
+# step; above it the exchange is bandwidth-bound and NCCL's all-reduce (ring / NVLS in-switch reduction) wins.
+P2P_MAX_PUSH_BYTES = 8 << 20
+
+
 class DataParallelTrainer:
-    def __init__(self, model, eta: float, device=None, group=None):
+    """``exchange``: "auto" (fused NVLink peer-memory kernel for small gradient buffers, NCCL otherwise), "p2p", "nccl"."""
+
+    def __init__(self, model, eta: float, device=None, group=None, exchange: str = "auto"):
         import torch
         import torch.distributed as dist
         self.model = model
@@ -39,12 +46,22 @@ class DataParallelTrainer:
         # the all-reduce target IS the kernels' output buffer: no staging copy on either side of the collective
         self.grads = torch.zeros(model.n_params, dtype=torch.float64, device=device)
         model.bind_gradient_buffer(self.grads)
+        self.p2p = False
+        if self.world > 1 and exchange != "nccl" and hasattr(model, "dp_init") and device.type == "cuda":
+            small = model.n_params * 8 * (self.world - 1) <= P2P_MAX_PUSH_BYTES
+            if exchange == "p2p" or small:
+                mine = model.dp_init(self.world, self.rank)          # 64-byte CUDA IPC handle of this rank's block
+                handles = [None] * self.world
+                self.dist.all_gather_object(handles, mine, group=group)
+                model.dp_connect_ipc(handles)
+                self.dist.barrier(group=group)
+                self.p2p = True
 
     # -- one step of rcn.rs:176-223 on this rank's shard ------------------------------------------------------------
     def _reduce_and_apply(self, local_batch: int):
-        if self.world > 1:
+        if self.world > 1 and not self.p2p:
             self.dist.all_reduce(self.grads, op=self.dist.ReduceOp.SUM, group=self.group)
-        self.model.apply_gradients(self.eta, local_batch * self.world)
+        self.model.apply_gradients(self.eta, local_batch * self.world)   # p2p: exchange fused into this kernel
 
     def step_images(self, images, labels):
         """images: this rank's shard, (B_local, H, W) uint8 / float64 (torch CUDA tensor or numpy); labels (B_local,)."""
@@ -62,6 +79,19 @@ class DataParallelTrainer:
         self._reduce_and_apply(int(images.shape[0]))
         return self.model.last_batch_stats()
 
+    def train_epoch_host(self, images, labels, batch: int):
+        """This rank's shard of a host-resident dataset walked in ``chunks_exact(batch)`` steps (rcn.rs:147-149) with the
+        H2D copy of the next chunk overlapping the current step; returns per-step (cost, hits) of this rank's shard.
+        With the NCCL exchange the loop is driven step by step from here (the collective is a host call)."""
+        if self.world == 1 or self.p2p:
+            return self.model.train_epoch_host(images, labels, batch, self.eta, batch * self.world)
+        import numpy as np
+        n_steps = int(images.shape[0]) // int(batch)
+        cost, hits = np.zeros(n_steps), np.zeros(n_steps, dtype=np.uint64)
+        for k in range(n_steps):
+            cost[k], hits[k] = self.step_images_host(images[k * batch:(k + 1) * batch], labels[k * batch:(k + 1) * batch])
+        return cost, hits
+
     def step_global_images(self, images, labels):
         """Convenience: every rank passes the same GLOBAL batch and trains on its own contiguous shard of it."""
         lo, hi = shard_bounds(int(images.shape[0]), self.rank, self.world)
@@ -78,7 +108,7 @@ class DataParallelTrainer:
         import torch
         self.model.set_stream(torch.cuda.current_stream().cuda_stream)
         self.model.epoch_accumulate()
-        if self.world > 1:
+        if self.world > 1 and not self.p2p:
             self.dist.all_reduce(self.grads, op=self.dist.ReduceOp.SUM, group=self.group)
         self.model.epoch_apply(self.eta, self.local_batch * self.world)
 
@@ -108,6 +138,12 @@ class DataParallelTrainer:
             self._epoch_step_eager()
 
     def describe(self) -> str:
-        ar = "none (1 GPU)" if self.world == 1 else f"1x NCCL all-reduce(sum) of {self.model.n_params} f64 per step"
+        if self.world == 1:
+            ar = "none (1 GPU) -> SGD update"
+        elif self.p2p:
+            ar = (f"gradient exchange of {self.model.n_params} f64 over NVLink peer memory fused with the SGD update "
+                  "(one kernel, rank-ordered sum)")
+        else:
+            ar = f"1x NCCL all-reduce(sum) of {self.model.n_params} f64 per step -> SGD update"
         return ("features(+standardise) -> fwd -> bwd-data -> bwd-weight(+db) -> batch stats -> " + ar +
-                " -> SGD update; kernels launched through the C ABI on torch's current stream")
+                "; kernels launched through the C ABI on torch's current stream")

@@ -316,3 +316,84 @@ def test_epoch_mode_and_cuda_graph(api):
     torch.cuda.synchronize()
     assert np.array_equal(graphed.get_params(), want)
     assert graphed.epoch_position() == 3 * B
+
+
+def test_train_epoch_host_equals_step_by_step(api):
+    """The pipelined host-dataset loop (double-buffered H2D on a copy stream) == train_batch_images chunk by chunk,
+    remainder dropped like chunks_exact (rcn.rs:147-149); per-step (cost, hits) equal last_batch_stats."""
+    rng = np.random.default_rng(21)
+    B, N = 64, 64 * 5 + 17
+    images = rng.integers(0, 256, size=(N, 28, 28), dtype=np.uint8)
+    labels = rng.integers(0, 10, size=N).astype(np.int64)
+    cfg = [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max)]
+    params = None
+    results = []
+    for mode in ("loop", "epoch"):
+        model = api.RCN(10, cfg, [30])
+        model.load_weights_and_bias(784)
+        if params is None:
+            params = np.random.default_rng(22).standard_normal(model.n_params)
+        model.set_params(params)
+        model.scale_set = (40.0, 60.0)
+        if mode == "loop":
+            stats = []
+            for k in range(N // B):
+                model.train_batch_images(images[k * B:(k + 1) * B], labels[k * B:(k + 1) * B], 3.0)
+                stats.append(model.last_batch_stats())
+            cost = np.array([s[0] for s in stats]); hits = np.array([s[1] for s in stats], dtype=np.uint64)
+        else:
+            cost, hits = model.train_epoch_host(images, labels, B, 3.0)
+            assert len(cost) == N // B
+        results.append((model.get_params(), cost, hits))
+    assert np.array_equal(results[0][0], results[1][0]), "same kernels, same order: parameters must be bit-identical"
+    assert np.array_equal(results[0][1], results[1][1]) and np.array_equal(results[0][2], results[1][2])
+
+
+def test_dp_peer_memory_exchange_two_gpus(api):
+    """Two ranks on two GPUs of this box (one process, peer access): the fused NVLink exchange + update kernel keeps the
+    replicas bit-identical and equals single-GPU training on the global minibatch within summation order."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import threading
+    rng = np.random.default_rng(23)
+    Bg, steps = 128, 4
+    images = rng.integers(0, 256, size=(steps, Bg, 28, 28), dtype=np.uint8)
+    labels = rng.integers(0, 10, size=(steps, Bg)).astype(np.int64)
+    cfg = [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max)]
+    ref = api.RCN(10, cfg, [30], device=0)
+    ref.load_weights_and_bias(784)
+    params = np.random.default_rng(24).standard_normal(ref.n_params)
+    ref.set_params(params); ref.scale_set = (40.0, 60.0)
+    for k in range(steps):
+        ref.train_batch_images(images[k], labels[k], 3.0)
+    want = ref.get_params()
+    ranks = []
+    for r in range(2):
+        m = api.RCN(10, cfg, [30], device=r)
+        m.load_weights_and_bias(784)
+        m.set_params(params); m.scale_set = (40.0, 60.0)
+        m.dp_init(2, r)
+        ranks.append(m)
+    for m in ranks:
+        m.dp_connect_local(ranks)
+    half = Bg // 2
+
+    def work(r):
+        m = ranks[r]
+        for k in range(steps):
+            m.accumulate_gradients_images(images[k, r * half:(r + 1) * half], labels[k, r * half:(r + 1) * half])
+            m.apply_gradients(3.0, Bg)
+        m.synchronize()
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+    [t.start() for t in th]
+    [t.join(timeout=60) for t in th]
+    assert not any(t.is_alive() for t in th), "ranks did not finish (exchange deadlock?)"
+    p0, p1 = ranks[0].get_params(), ranks[1].get_params()
+    assert np.array_equal(p0, p1), "replicas must stay bit-identical"
+    assert_close(p0, want, rtol=1e-9, what="2-rank parameters vs single GPU")
+    g0, g1 = ranks[0].get_gradients(), ranks[1].get_gradients()
+    assert np.array_equal(g0, g1), "gradient buffers hold the same global sum on every rank"
+    for m in ranks:
+        m.dp_shutdown()
