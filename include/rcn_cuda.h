@@ -250,6 +250,17 @@ int rcn_cuda_ext_pool2d_backward(int device, void* cuda_stream, const double* dy
 int rcn_cuda_ext_softmax_xent(int device, void* cuda_stream, const double* z, size_t n, size_t B, const double* onehot,
                               const int64_t* labels, double* probs, double* loss, double* delta);
 
+/* The GEMM building block of the dense and convolution layers, exposed for testing and benchmarking:
+ * C (M x N, column-major) = A * B with A(m,k) = a_kcontig ? A[m*lda + k] : A[k*lda + m] and
+ * B(k,n) = b_kcontig ? B[n*ldb + k] : B[k*ldb + n].
+ *   impl 0: f64 tensor path (DMMA, mma.sync.m8n8k4.f64), cp.async-staged.
+ *   impl 1: tcgen05 / TMEM / TMA integer-slice path: both operands are split into six 7-bit int8 slices under per-row
+ *           power-of-two scales, the 21 slice products with i+j <= 5 run as exact s8 x s8 -> s32 tensor-core MMAs and are
+ *           recombined in f64 (truncation ~ 1e-12 of the row scales; operands must be finite; K <= 65536).
+ * The dense layers pick impl 1 automatically for large shapes (env RCN_CUDA_GEMM = dmma | tc | simt overrides). */
+int rcn_cuda_ext_gemm_f64(int device, void* cuda_stream, const double* A, size_t lda, int a_kcontig, const double* B,
+                          size_t ldb, int b_kcontig, size_t M, size_t N, size_t K, int impl, double* C);
+
 #ifdef __cplusplus
 }
 #endif

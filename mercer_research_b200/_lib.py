@@ -87,6 +87,7 @@ SIGNATURES = {
     "rcn_cuda_ext_pool2d_forward": [_i, _vp, _vp, _sz, _sz, _sz, _sz, _i, _i, _vp, _vp],
     "rcn_cuda_ext_pool2d_backward": [_i, _vp, _vp, _vp, _sz, _sz, _sz, _sz, _i, _i, _vp],
     "rcn_cuda_ext_softmax_xent": [_i, _vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp, _vp],
+    "rcn_cuda_ext_gemm_f64": [_i, _vp, _vp, _sz, _i, _vp, _sz, _i, _sz, _sz, _sz, _i, _vp],
 }
 _RESTYPES = {"rcn_cuda_last_error": C.c_char_p}
 

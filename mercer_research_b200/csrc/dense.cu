@@ -15,6 +15,8 @@
 // algebraically (1-a cancels for saturated units and parity depends on cancelling identically).
 #include "dense.cuh"
 #include "gemm_f64.cuh"
+#include "opctx.cuh"
+#include "ozaki.cuh"
 
 #include <cstdlib>
 
@@ -24,9 +26,18 @@ GemmImpl gemm_impl() {
     static int impl = -1;
     if (impl < 0) {
         const char* e = getenv("RCN_CUDA_GEMM");
-        impl = (e && strcmp(e, "simt") == 0) ? GEMM_SIMT : GEMM_DMMA;
+        impl = !e ? GEMM_AUTO : strcmp(e, "simt") == 0 ? GEMM_SIMT : strcmp(e, "dmma") == 0 ? GEMM_DMMA : strcmp(e, "tc") == 0 ? GEMM_TC : GEMM_AUTO;
     }
     return (GemmImpl)impl;
+}
+
+// tcgen05 integer-slice path (ozaki.cuh) when the contraction is really dense: full 128 x 64 tiles, deep K, and enough
+// work to amortise slicing both operands; everything else (skinny layers like 4096 -> 10) stays on DMMA.
+static bool use_tensor_cores(size_t M, size_t N, size_t K, OzakiWorkspace* oz) {
+    if (!oz || !ozaki_available() || K > 65536) return false;
+    if (gemm_impl() == GEMM_TC) return M >= 1 && N >= 1 && K >= 1;
+    if (gemm_impl() != GEMM_AUTO) return false;
+    return M >= 256 && N >= 256 && K >= 512 && (double)M * (double)N * (double)K >= 8.0e9;
 }
 
 // rcn.rs:478-483: 1/(1+E^-x).  exp(-x) instead of pow(E,-x): E as an f64 is e*(1-5.3e-17), so the two differ
@@ -71,10 +82,14 @@ struct EpiStore {  // split-K partial (or final) store, column-major M x N
 // ------------------------------------------------------------------------------------------------
 template <bool AK, bool BKc, typename Epi>
 static int launch_gemm(const char* name, const double* A, int lda, const double* B, int ldb, size_t M_, size_t N_, size_t K_,
-                       int splits, const Epi& epi, cudaStream_t stream) {
+                       int splits, const Epi& epi, cudaStream_t stream, OzakiWorkspace* oz = nullptr) {
     if (M_ == 0 || N_ == 0) return RCN_OK;
     if (M_ > 0x7fffffff || N_ > 0x7fffffff || K_ > 0x7fffffff) return fail(RCN_ERR_INVALID, "GEMM dimension too large");
     const int M = (int)M_, N = (int)N_, K = (int)K_;
+    if (splits <= 1 && use_tensor_cores(M_, N_, K_, oz)) {
+        const OzOperand oa{A, (size_t)lda, AK}, ob{B, (size_t)ldb, BKc};
+        return launch_gemm_ozaki(name, oa, ob, M, N, K, epi, *oz, stream);
+    }
     int k_per_split;
     split_plan(K, splits, k_per_split);
     if (gemm_impl() == GEMM_SIMT) {
@@ -99,16 +114,20 @@ static int effective_splits(size_t K, int splits) {
 // ------------------------------------------------------------------------------------------------
 int launch_dense_forward(const double* W, const double* b, const double* A_in, size_t M, size_t K, size_t N,
                          double* A_out, double* delta_out, const double* onehot, const int64_t* labels,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, OzakiWorkspace* oz) {
     EpiForward epi{b, A_out, delta_out, onehot, labels, (int)M};
-    return launch_gemm<false, true, EpiForward>("dense_forward_gemm", W, (int)M, A_in, (int)K, M, N, K, 1, epi, stream);
+    const bool tc = use_tensor_cores(M, N, K, oz);
+    return launch_gemm<false, true, EpiForward>(tc ? "dense_forward_gemm(tcgen05 int8 slices)" : "dense_forward_gemm", W, (int)M, A_in,
+                                                (int)K, M, N, K, 1, epi, stream, oz);
 }
 
 int launch_dense_backward_data(const double* W_up, const double* delta_up, const double* A, size_t M, size_t K,
-                               size_t N, double* delta_out, cudaStream_t stream) {
+                               size_t N, double* delta_out, cudaStream_t stream, OzakiWorkspace* oz) {
     EpiBackData epi{A, delta_out, (int)M};
     // A(m,k) = W_up[k, m]; W_up is K x M column-major => k-contiguous with lda = K.
-    return launch_gemm<true, true, EpiBackData>("dense_backward_data_gemm", W_up, (int)K, delta_up, (int)K, M, N, K, 1, epi, stream);
+    const bool tc = use_tensor_cores(M, N, K, oz);
+    return launch_gemm<true, true, EpiBackData>(tc ? "dense_backward_data_gemm(tcgen05 int8 slices)" : "dense_backward_data_gemm", W_up,
+                                                (int)K, delta_up, (int)K, M, N, K, 1, epi, stream, oz);
 }
 
 __global__ void reduce_splits_kernel(const double* __restrict__ part, int splits, size_t n, double* __restrict__ out) {
@@ -150,8 +169,15 @@ int launch_bias_grad(const double* delta, size_t M, size_t N, double* db, cudaSt
 }
 
 int launch_dense_backward_weight(const double* delta, const double* A_prev, size_t M, size_t N, size_t Kb, double* dW,
-                                 double* db, DevBuf& workspace, cudaStream_t stream) {
+                                 double* db, DevBuf& workspace, cudaStream_t stream, OzakiWorkspace* oz) {
     if (M == 0) return RCN_OK;
+    if (N > 0 && use_tensor_cores(M, N, Kb, oz)) {
+        // enough output tiles to fill the machine without splitting the batch: one exact pass, deterministic by construction
+        EpiStore epi{dW, (int)M, 0};
+        RCN_TRY((launch_gemm<false, false, EpiStore>("dense_backward_weight_gemm(tcgen05 int8 slices)", delta, (int)M, A_prev, (int)N, M,
+                                                     N, Kb, 1, epi, stream, oz)));
+        return launch_bias_grad(delta, M, Kb, db, stream);
+    }
     // Split the batch (K) dimension so the small M x N output still fills the machine; partials are summed in
     // a fixed order (deterministic, unlike the reference's mutex-ordered sum, rcn.rs:190-205).
     size_t tiles;
@@ -272,3 +298,43 @@ int launch_batch_stats(const double* acts, size_t n, size_t B, const double* one
 }
 
 }  // namespace rcn
+
+using namespace rcn;
+
+extern "C" int rcn_cuda_ext_gemm_f64(int device, void* cuda_stream, const double* A, size_t lda, int a_kcontig, const double* B,
+                                     size_t ldb, int b_kcontig, size_t M, size_t N, size_t K, int impl, double* C) {
+    if (!A || !B || !C) return fail(RCN_ERR_INVALID, "null pointer");
+    if (M == 0 || N == 0) return RCN_OK;
+    if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff) return fail(RCN_ERR_INVALID, "GEMM dimension too large");
+    if (impl != 0 && impl != 1) return fail(RCN_ERR_INVALID, "impl must be 0 (DMMA) or 1 (tcgen05 integer slices)");
+    OpCtx c;
+    RCN_TRY(c.enter(device, cuda_stream));
+    const size_t a_elems = a_kcontig ? (M - 1) * lda + K : (K ? (K - 1) * lda + M : 0);
+    const size_t b_elems = b_kcontig ? (N - 1) * ldb + K : (K ? (K - 1) * ldb + N : 0);
+    const void *a_dev = nullptr, *b_dev = nullptr; void* c_dev = nullptr; bool host = false;
+    RCN_TRY(c.in(A, a_elems * 8, tl_op_in, &a_dev));
+    RCN_TRY(c.in(B, b_elems * 8, tl_op_in2, &b_dev));
+    RCN_TRY(c.out(C, M * N * 8, tl_op_out, &c_dev, &host));
+    EpiStore epi{(double*)c_dev, (int)M, 0};
+    if (impl == 1) {
+        if (!ozaki_available()) return fail(RCN_ERR_CUDA, "tensor-map encoding is not available from this driver");
+        static thread_local OzakiWorkspace ws;
+        const OzOperand oa{(const double*)a_dev, lda, a_kcontig != 0}, ob{(const double*)b_dev, ldb, b_kcontig != 0};
+        RCN_TRY(launch_gemm_ozaki("ext_gemm_f64(tcgen05 int8 slices)", oa, ob, (int)M, (int)N, (int)K, epi, ws, c.stream));
+    } else {
+        int splits = 1, kps;
+        split_plan((int)K, splits, kps);
+#define RCN_EXT_GEMM(AKC, BKC)                                                                       \
+        {                                                                                            \
+            const DenseLoader<AKC> la{(const double*)a_dev, (int)lda, (int)M};                       \
+            const DenseLoader<BKC> lb{(const double*)b_dev, (int)ldb, (int)N};                       \
+            RCN_TRY(launch_gemm_tiles("ext_gemm_f64(dmma)", la, lb, (int)M, (int)N, (int)K, 1, kps, epi, c.stream)); \
+        }
+        if (a_kcontig && b_kcontig) RCN_EXT_GEMM(true, true)
+        else if (a_kcontig) RCN_EXT_GEMM(true, false)
+        else if (b_kcontig) RCN_EXT_GEMM(false, true)
+        else RCN_EXT_GEMM(false, false)
+#undef RCN_EXT_GEMM
+    }
+    return c.finish(C, c_dev, M * N * 8, host);
+}

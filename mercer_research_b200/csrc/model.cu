@@ -13,6 +13,7 @@
 #include "smallnet.cuh"
 #include "opctx.cuh"
 #include "dp.cuh"
+#include "ozaki.cuh"
 
 namespace rcn {
 
@@ -101,6 +102,7 @@ struct rcn_cuda_model {
     bool stats_valid = false;
     // data-parallel group (dp.cu) and the pipelined host-dataset loop (rcn_cuda_train_epoch_host)
     DpState dp;
+    OzakiWorkspace oz;              // tcgen05 integer-slice GEMM scratch (wide dense layers)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     DevBuf host_slot[2];
@@ -189,7 +191,7 @@ int forward_dev(rcn_cuda_model* h, const double* feats, size_t B, const double* 
         const bool last = (l + 1 == n);
         RCN_TRY(launch_dense_forward(h->params.as<double>() + h->w_off[l], h->params.as<double>() + h->b_off[l], a_in,
                                      h->rows[l], h->cols[l], B, h->act(l, B),
-                                     (last && want_delta) ? h->delta(l, B) : nullptr, onehot, labels, h->stream));
+                                     (last && want_delta) ? h->delta(l, B) : nullptr, onehot, labels, h->stream, &h->oz));
     }
     return RCN_OK;
 }
@@ -216,11 +218,11 @@ int accumulate_dev(rcn_cuda_model* h, const double* feats, const double* onehot,
     RCN_TRY(forward_dev(h, feats, B, onehot, labels, true));
     for (size_t l = n - 1; l-- > 0;)  // rcn.rs:305-311
         RCN_TRY(launch_dense_backward_data(h->params.as<double>() + h->w_off[l + 1], h->delta(l + 1, B), h->act(l, B),
-                                           h->rows[l], h->rows[l + 1], B, h->delta(l, B), h->stream));
+                                           h->rows[l], h->rows[l + 1], B, h->delta(l, B), h->stream, &h->oz));
     for (size_t l = 0; l < n; ++l) {
         const double* a_prev = l == 0 ? feats : h->act(l - 1, B);
         RCN_TRY(launch_dense_backward_weight(h->delta(l, B), a_prev, h->rows[l], h->cols[l], B, h->grads + h->w_off[l],
-                                             h->grads + h->b_off[l], h->gemm_ws, h->stream));
+                                             h->grads + h->b_off[l], h->gemm_ws, h->stream, &h->oz));
     }
     RCN_TRY(h->small.reserve(64));
     RCN_TRY(launch_batch_stats(h->act(n - 1, B), h->rows[n - 1], B, onehot, labels, h->small.as<double>(), h->stream));
@@ -333,6 +335,7 @@ int rcn_cuda_destroy(rcn_cuda_handle h) {
     }
     if (h->stats_host) cudaFreeHost(h->stats_host);
     dp_release(h->dp);
+    h->oz.release();
     DevBuf* bufs[] = {&h->params, &h->grads_own, &h->in_stage, &h->tgt_stage, &h->feats, &h->acts, &h->deltas,
                       &h->gemm_ws, &h->out_stage, &h->small, &h->red_ws, &h->ep_state, &h->sn_counters, &h->fscratch.a, &h->fscratch.b};
     for (DevBuf* b : bufs) b->release();

@@ -1,0 +1,174 @@
+// ozaki.cu -- operand slicing and TMA descriptors for the tcgen05 integer-slice GEMM (see ozaki.cuh for the scheme).
+//
+// Slicing is HBM-bound byte work (8 B read, 6 B written per element, twice over the operand because the per-row scale
+// needs the row maximum first; the second sweep is served by L2 for the row blocks a CTA owns): coalesced loads along
+// the operand's contiguous dimension, and for operands whose contraction index is NOT the contiguous one a
+// shared-memory tile transpose so that the int8 planes are always written k-contiguous in 64-byte runs.
+#include "ozaki.cuh"
+
+#include <cuda_runtime_api.h>
+
+namespace rcn {
+
+namespace {
+
+// x = scale * sum_j q_j 2^(-7j): t = x * 2^(6-e) in (-64, 64); q_0 = rint(t); t = (t - q_0) * 128; ...  (every step exact)
+__device__ __forceinline__ void slice6(double x, double inv, int8_t (&q)[OZ_S]) {
+    double t = x * inv;
+#pragma unroll
+    for (int j = 0; j < OZ_S; ++j) {
+        const double r = rint(t);
+        q[j] = (int8_t)(int)r;
+        t = (t - r) * 128.0;
+    }
+}
+
+// row scale from the row maximum: amax = f * 2^e, f in [0.5, 1)  =>  |x| * 2^-e < 1
+__device__ __forceinline__ void row_scale(double amax, double& inv, double& scale) {
+    if (!(amax > 1e-290) || !(amax < 1e290)) { inv = 0.0; scale = 0.0; return; }   // zero / denormal / non-finite row: all-zero slices
+    int e;
+    frexp(amax, &e);
+    inv = ldexp(1.0, 6 - e);
+    scale = ldexp(1.0, e - 6);
+}
+
+// element (r, k) at X[r*ld + k]: one warp per row.
+__global__ void __launch_bounds__(256) ozaki_slice_kmajor_kernel(const double* __restrict__ X, size_t ld, int R, int K, int Kp,
+                                                                 int8_t* __restrict__ planes, double* __restrict__ scale) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + warp;
+    if (r >= R) return;
+    const double* row = X + (size_t)r * ld;
+    double amax = 0.0;
+    for (int k = lane; k < K; k += 32) amax = fmax(amax, fabs(row[k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    double inv, sc;
+    row_scale(amax, inv, sc);
+    if (lane == 0) scale[r] = sc;
+    const size_t plane = (size_t)R * Kp;
+    for (int k4 = lane * 4; k4 < Kp; k4 += 128) {
+        int8_t q[4][OZ_S];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k4 + u;
+            slice6(k < K ? row[k] : 0.0, inv, q[u]);
+        }
+#pragma unroll
+        for (int j = 0; j < OZ_S; ++j) {
+            const uint32_t w = (uint32_t)(uint8_t)q[0][j] | ((uint32_t)(uint8_t)q[1][j] << 8) | ((uint32_t)(uint8_t)q[2][j] << 16) |
+                               ((uint32_t)(uint8_t)q[3][j] << 24);
+            *reinterpret_cast<uint32_t*>(planes + (size_t)j * plane + (size_t)r * Kp + k4) = w;
+        }
+    }
+}
+
+// element (r, k) at X[k*ld + r]: one CTA per 32 rows, all k; shared-memory transpose to k-contiguous planes.
+constexpr int TR_PITCH = 68;   // bytes per (slice, row) line of the 64-k tile: 17 words -> conflict-free byte scatter
+__global__ void __launch_bounds__(256) ozaki_slice_rmajor_kernel(const double* __restrict__ X, size_t ld, int R, int K, int Kp,
+                                                                 int8_t* __restrict__ planes, double* __restrict__ scale) {
+    __shared__ double red[8][32];
+    __shared__ double s_inv[32];
+    __shared__ __align__(4) int8_t tile[OZ_S][32][TR_PITCH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r0 = blockIdx.x * 32;
+    const int r = r0 + lane;
+    const bool rok = r < R;
+    double amax = 0.0;
+    for (int k = warp; k < K; k += 32) {        // 4 loads in flight per thread
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (rok && k + 8 * u < K) ? X[(size_t)(k + 8 * u) * ld + r] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) amax = fmax(amax, fabs(v[u]));
+    }
+    red[warp][lane] = amax;
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) amax = fmax(amax, red[w][lane]);
+        double inv, sc;
+        row_scale(amax, inv, sc);
+        s_inv[lane] = inv;
+        if (rok) scale[r] = sc;
+    }
+    __syncthreads();
+    const double inv = s_inv[lane];
+    const size_t plane = (size_t)R * Kp;
+    for (int kb = 0; kb < Kp; kb += 64) {
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = kb + warp * 8 + j;
+            v[j] = (rok && k < K) ? X[(size_t)k * ld + r] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int8_t q[OZ_S];
+            slice6(v[j], inv, q);
+#pragma unroll
+            for (int s = 0; s < OZ_S; ++s) tile[s][lane][warp * 8 + j] = q[s];
+        }
+        __syncthreads();
+        // write-out: per (slice, row) 64 contiguous bytes = 16 words
+#pragma unroll
+        for (int i = 0; i < OZ_S * 32 * 16 / 256; ++i) {
+            const int idx = threadIdx.x + i * 256;
+            const int s = idx / 512, rem = idx % 512;
+            const int rr = rem / 16, w = rem % 16;
+            if (r0 + rr < R)
+                *reinterpret_cast<uint32_t*>(planes + (size_t)s * plane + (size_t)(r0 + rr) * Kp + kb + 4 * w) =
+                    *reinterpret_cast<const uint32_t*>(&tile[s][rr][4 * w]);
+        }
+        __syncthreads();
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+}  // namespace
+
+bool ozaki_available() { return encode_tiled_fn() != nullptr; }
+
+int ozaki_slice(const OzOperand& op, int rows, int K, int Kp, int8_t* planes, double* scale, cudaStream_t stream) {
+    if (rows <= 0) return RCN_OK;
+    if (op.kcontig) {
+        RCN_LAUNCH("ozaki_slice_kmajor_kernel", stream,
+                   ozaki_slice_kmajor_kernel<<<cdiv(rows, 8), 256, 0, stream>>>(op.p, op.ld, rows, K, Kp, planes, scale));
+    } else {
+        RCN_LAUNCH("ozaki_slice_rmajor_kernel", stream,
+                   ozaki_slice_rmajor_kernel<<<cdiv(rows, 32), 256, 0, stream>>>(op.p, op.ld, rows, K, Kp, planes, scale));
+    }
+    return RCN_OK;
+}
+
+int ozaki_make_tensor_map(CUtensorMap* map, const int8_t* planes, int rows, int Kp, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(RCN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)OZ_S};
+    const cuuint64_t strides[2] = {(cuuint64_t)Kp, (cuuint64_t)rows * (cuuint64_t)Kp};   // bytes, dims 1 and 2
+    const cuuint32_t box[3] = {(cuuint32_t)OZ_BK, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(planes), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail(RCN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows %d, Kp %d)", (int)rc, rows, Kp);
+    return RCN_OK;
+}
+
+}  // namespace rcn

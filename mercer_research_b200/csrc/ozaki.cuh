@@ -1,0 +1,280 @@
+// ozaki.cuh -- f64-grade GEMM on the 5th-generation tensor cores (tcgen05 / TMEM / TMA) by integer slicing.
+//
+// Why: rcn computes in f64 (rcn/src/rcn.rs:28-31,49) and the parity bar is 1e-9, but tcgen05.mma has no f64 kind, so
+// the wide dense layers (BASELINE config 5: 4096-4096-4096, batch 8192; rcn.rs:105-116 forward, :260-314 backprop
+// expressed as batched GEMMs) would be capped by the 37 TFLOP/s DMMA pipe.  The Ozaki scheme splits
+// every operand row into S signed 7-bit integer slices under a per-row power-of-two scale,
+//     x[r,k] = scale[r] * sum_j q_j[r,k] * 2^(-7j),      q_j in [-64, 64]  (int8),
+// so that every slice product  sum_k qa_i[m,k] * qb_j[n,k]  is an EXACT int32 dot product on `tcgen05.mma kind::i8`.
+// Pairs with equal i+j = d share a weight 2^(-7d) and are accumulated into the SAME int32 TMEM accumulator (still
+// exact: (d+1) * K * 64^2 < 2^31 for K <= 2^16), and diagonals d > D are dropped (their weight is below the target
+// accuracy).  With S = 6, D = 5: 21 int8 MMAs per k-step, truncation ~ 7 * 2^-42 relative to the row scales.
+//
+// Kernel (one 128 x 64 output tile per CTA, 192 threads, warp-specialised):
+//   warp 0      TMA producer: per 64-deep k-block, 6 A-slice boxes (128 x 64 B) + 6 B-slice boxes (64 x 64 B),
+//               SWIZZLE_64B, 3-stage ring guarded by full/empty mbarriers;
+//   warp 1      TMEM allocator + MMA issuer: one elected thread issues 2 x 21 tcgen05.mma (M128 N64 K32, s8 x s8 -> s32)
+//               per stage into 6 TMEM accumulators (384 of 512 columns), tcgen05.commit frees the smem slot;
+//   warps 2-5   epilogue: tcgen05.ld the 6 diagonals, Horner-combine them in f64, apply the row scales and the layer's
+//               epilogue functor (bias + sigmoid, sigmoid', store ...), coalesced column-major stores.
+// The slices are produced by ozaki.cu's slicing kernels (HBM-bound: 8 B in, 6 B out per element).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace rcn {
+
+constexpr int OZ_S = 6;            // slices per operand
+constexpr int OZ_D = 5;            // highest diagonal kept (i + j <= OZ_D)
+constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 64, OZ_STAGES = 3;
+constexpr int OZ_A_TILE = OZ_BM * OZ_BK;       // bytes of one A slice tile
+constexpr int OZ_B_TILE = OZ_BN * OZ_BK;
+constexpr int OZ_STAGE_BYTES = OZ_S * (OZ_A_TILE + OZ_B_TILE);
+constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int OZ_THREADS = 192;
+constexpr int OZ_TMEM_COLS = 512;
+
+struct OzakiWorkspace {
+    DevBuf a_slices, b_slices, a_scale, b_scale;
+    void release() { a_slices.release(); b_slices.release(); a_scale.release(); b_scale.release(); }
+};
+
+// Operand as the GEMM sees it: `rows` x K (rows = M for A, N for B); kcontig: element (r, k) at p[r*ld + k], else p[k*ld + r].
+struct OzOperand {
+    const double* p;
+    size_t ld;
+    bool kcontig;
+};
+
+// Slices one operand into int8 planes [OZ_S][rows][Kp] (Kp = K rounded up to 64, zero padded) and scale[rows].
+int ozaki_slice(const OzOperand& op, int rows, int K, int Kp, int8_t* planes, double* scale, cudaStream_t stream);
+// 3-D tensor map over planes [OZ_S][rows][Kp], box = (64 B of k, box_rows, 1 slice), SWIZZLE_64B.
+int ozaki_make_tensor_map(CUtensorMap* map, const int8_t* planes, int rows, int Kp, int box_rows);
+bool ozaki_available();
+
+// ---- device helpers ------------------------------------------------------------------------------------------------
+namespace oz {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows 64 B apart, 8-row groups
+// 512 B apart (SBO), LBO = 1 (unused for swizzled K-major), version 1 (Blackwell), layout type 4 (SWIZZLE_64B).
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);          // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                              // leading byte offset (16-byte units), bits [16,30)
+    d |= (uint64_t)(512 >> 4) << 32;                     // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                              // descriptor version, bits [46,48)
+    d |= (uint64_t)4 << 61;                              // layout type SWIZZLE_64B, bits [61,64)
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::i8: D = s32, A = B = signed int8, both K-major,
+// N = 64, M = 128, dense, no saturation.
+constexpr uint32_t kInstrDescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kInstrDescI8), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+}  // namespace oz
+
+// C(m, n) = sum_k A(m, k) B(n, k), delivered to epi(m, n, value).  Tile (blockIdx.x, blockIdx.y) = (m-tile, n-tile).
+template <typename Epi>
+__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                    const __grid_constant__ CUtensorMap map_b,
+                                                                    const double* __restrict__ scale_a,
+                                                                    const double* __restrict__ scale_b, int M, int N, int Kp,
+                                                                    int m_tiles, int n_tiles, Epi epi) {
+    extern __shared__ unsigned char oz_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OZ_STAGES * OZ_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + OZ_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + OZ_STAGES;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // rasterisation: groups of 8 m-tiles sweep all n-tiles, so concurrently resident CTAs share operand tiles in L2
+    int tile = blockIdx.x;
+    const int group = 8 * n_tiles;
+    const int g = tile / group;
+    const int g_m0 = g * 8;
+    const int g_rows = min(8, m_tiles - g_m0);
+    const int in_g = tile - g * group;
+    const int m_tile = g_m0 + in_g % g_rows;
+    const int n_tile = in_g / g_rows;
+    const int m0 = m_tile * OZ_BM, n0 = n_tile * OZ_BN;
+    const int n_kb = Kp / OZ_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < OZ_STAGES; ++s) { oz::mbar_init(full_bar + s, 1); oz::mbar_init(empty_bar + s, 1); }
+        oz::mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz::smem_u32(tmem_base_slot)), "r"(OZ_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    oz::tc_fence_before();
+    __syncthreads();
+    oz::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_base_slot);
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int stage = kb % OZ_STAGES;
+                const uint32_t phase = (kb / OZ_STAGES) & 1;
+                oz::mbar_wait(empty_bar + stage, phase ^ 1);
+                oz::mbar_expect_tx(full_bar + stage, OZ_STAGE_BYTES);
+                unsigned char* sa = smem + stage * OZ_STAGE_BYTES;
+                unsigned char* sb = sa + OZ_S * OZ_A_TILE;
+#pragma unroll
+                for (int s = 0; s < OZ_S; ++s) oz::tma_load_3d(sa + s * OZ_A_TILE, &map_a, full_bar + stage, kb * OZ_BK, m0, s);
+#pragma unroll
+                for (int s = 0; s < OZ_S; ++s) oz::tma_load_3d(sb + s * OZ_B_TILE, &map_b, full_bar + stage, kb * OZ_BK, n0, s);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int stage = kb % OZ_STAGES;
+                const uint32_t phase = (kb / OZ_STAGES) & 1;
+                oz::mbar_wait(full_bar + stage, phase);
+                oz::tc_fence_after();
+                const uint32_t sa = oz::smem_u32(smem + stage * OZ_STAGE_BYTES);
+                const uint32_t sb = sa + OZ_S * OZ_A_TILE;
+#pragma unroll
+                for (int ks = 0; ks < OZ_BK / 32; ++ks) {
+#pragma unroll
+                    for (int i = 0; i < OZ_S; ++i) {
+                        const uint64_t da = oz::smem_desc_sw64(sa + i * OZ_A_TILE + ks * 32);
+#pragma unroll
+                        for (int j = 0; j + i <= OZ_D && j < OZ_S; ++j) {
+                            const uint64_t db = oz::smem_desc_sw64(sb + j * OZ_B_TILE + ks * 32);
+                            // the first MMA into diagonal d = i + j is (kb, ks, i) = (0, 0, 0)
+                            oz::mma_i8(tmem_base + (uint32_t)((i + j) * OZ_BN), da, db, (kb | ks | i) != 0 ? 1u : 0u);
+                        }
+                    }
+                }
+                oz::tc_commit(empty_bar + stage);       // frees the smem slot once these MMAs have read it
+            }
+            oz::tc_commit(tmem_full_bar);               // accumulators complete
+        }
+    } else {
+        // ===== epilogue (warps 2..5): TMEM lane quadrant = warp % 4 =====
+        const int quad = warp & 3;
+        const int m = m0 + quad * 32 + lane;
+        oz::mbar_wait(tmem_full_bar, 0);
+        oz::tc_fence_after();
+        const double sa = (m < M) ? scale_a[m] : 0.0;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        constexpr double kW = 1.0 / 128.0;   // 2^-7 between neighbouring diagonals
+#pragma unroll 1
+        for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+            double acc[16];
+            {
+                int32_t v[16];
+                oz::tmem_ld16(lane_addr + (uint32_t)(OZ_D * OZ_BN + c0), v);
+                oz::tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 16; ++q) acc[q] = (double)v[q];
+            }
+#pragma unroll
+            for (int d = OZ_D - 1; d >= 0; --d) {
+                int32_t v[16];
+                oz::tmem_ld16(lane_addr + (uint32_t)(d * OZ_BN + c0), v);
+                oz::tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 16; ++q) acc[q] = fma(acc[q], kW, (double)v[q]);   // Horner over the diagonals
+            }
+            if (m < M) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int n = n0 + c0 + q;
+                    if (n < N) epi(m, n, acc[q] * sa * __ldg(scale_b + n));
+                }
+            }
+        }
+        oz::tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        oz::tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(OZ_TMEM_COLS) : "memory");
+    }
+}
+
+// Host launcher: slices both operands, builds the tensor maps and runs the tile kernel.
+template <typename Epi>
+static int launch_gemm_ozaki(const char* name, const OzOperand& A, const OzOperand& B, int M, int N, int K, const Epi& epi,
+                             OzakiWorkspace& ws, cudaStream_t stream) {
+    if (M <= 0 || N <= 0) return RCN_OK;
+    if (K > 65536) return fail(RCN_ERR_INVALID, "tcgen05 integer-slice GEMM supports K <= 65536 (exact int32 accumulation)");
+    const int Kp = ((K + OZ_BK - 1) / OZ_BK) * OZ_BK;
+    RCN_TRY(ws.a_slices.reserve((size_t)OZ_S * M * Kp));
+    RCN_TRY(ws.b_slices.reserve((size_t)OZ_S * N * Kp));
+    RCN_TRY(ws.a_scale.reserve((size_t)M * sizeof(double)));
+    RCN_TRY(ws.b_scale.reserve((size_t)N * sizeof(double)));
+    RCN_TRY(ozaki_slice(A, M, K, Kp, ws.a_slices.as<int8_t>(), ws.a_scale.as<double>(), stream));
+    RCN_TRY(ozaki_slice(B, N, K, Kp, ws.b_slices.as<int8_t>(), ws.b_scale.as<double>(), stream));
+    CUtensorMap map_a, map_b;
+    RCN_TRY(ozaki_make_tensor_map(&map_a, ws.a_slices.as<int8_t>(), M, Kp, OZ_BM));
+    RCN_TRY(ozaki_make_tensor_map(&map_b, ws.b_slices.as<int8_t>(), N, Kp, OZ_BN));
+    auto kern = ozaki_gemm_kernel<Epi>;
+    static SmemAttrCache attr;
+    if (attr.need(OZ_SMEM_BYTES)) RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES));
+    const int m_tiles = (M + OZ_BM - 1) / OZ_BM, n_tiles = (N + OZ_BN - 1) / OZ_BN;
+    RCN_LAUNCH(name, stream,
+               kern<<<(unsigned)(m_tiles * n_tiles), OZ_THREADS, OZ_SMEM_BYTES, stream>>>(map_a, map_b, ws.a_scale.as<double>(),
+                                                                                          ws.b_scale.as<double>(), M, N, Kp,
+                                                                                          m_tiles, n_tiles, epi));
+    return RCN_OK;
+}
+
+}  // namespace rcn

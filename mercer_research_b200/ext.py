@@ -151,3 +151,22 @@ def softmax_xent(z, onehot=None, labels=None):
     _lib.check(_lib.load().rcn_cuda_ext_softmax_xent(dev, stream, Z.ptr, n, B, Oh.ptr if Oh else None, Lb.ptr if Lb else None,
                                                      _ptr(p), _ptr(loss), _ptr(delta)))
     return p, loss, delta
+
+
+def gemm_f64(a, b, impl: int = 1, a_kcontig: bool = True, b_kcontig: bool = True):
+    """C (M x N) = A (M x K) @ B (K x N) through the library's GEMM building block (include/rcn_cuda.h).
+    ``a`` is given as a numpy (M, K) array, ``b`` as (K, N); *_kcontig chooses the memory layout handed to the kernel
+    (k-contiguous or row-contiguous), which selects the slicing / loader variant. impl 0 = DMMA, 1 = tcgen05 int8 slices."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    M, K = a.shape
+    K2, N = b.shape
+    assert K == K2
+    abuf = np.ascontiguousarray(a) if a_kcontig else np.ascontiguousarray(a.T)     # [m][k] or [k][m]
+    bbuf = np.ascontiguousarray(b.T) if b_kcontig else np.ascontiguousarray(b)     # [n][k] or [k][n]
+    lda = K if a_kcontig else M
+    ldb = K if b_kcontig else N
+    c = np.zeros((N, M))                                                           # column-major M x N
+    _lib.check(_lib.load().rcn_cuda_ext_gemm_f64(0, None, abuf.ctypes.data, lda, int(a_kcontig), bbuf.ctypes.data, ldb,
+                                                 int(b_kcontig), M, N, K, int(impl), c.ctypes.data))
+    return c.T

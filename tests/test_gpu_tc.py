@@ -1,0 +1,104 @@
+"""GPU tests of the tcgen05 / TMEM / TMA integer-slice GEMM (csrc/ozaki.cuh) that carries the wide dense layers:
+f64-grade results from exact int8 tensor-core products. Checked against numpy f64 and against the oracle through the
+dense-layer API with the path forced (RCN_CUDA_GEMM=tc)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def X(built_library):
+    from mercer_research_b200 import ext
+    return ext
+
+
+def check(got, want, what, rel=1e-9):
+    """north_star bar for f64: 1e-9 relative. Slice truncation is relative to the operand ROW scales, so elements that
+    cancel to ~0 are bounded by rel * 1e-2 * max|want| instead of their own magnitude."""
+    scale = float(np.max(np.abs(want)))
+    err = np.abs(got - want)
+    bound = rel * np.abs(want) + rel * 1e-2 * scale
+    assert np.isfinite(got).all(), what
+    assert (err <= bound).all(), (what, float((err / np.maximum(bound, 1e-300)).max()), float(err.max() / scale))
+    assert float(np.linalg.norm(got - want) / np.linalg.norm(want)) < 1e-10, what
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (128, 64, 192), (256, 128, 512), (200, 100, 300), (1, 1, 1), (130, 70, 1000),
+                                   (512, 384, 2048)])
+@pytest.mark.parametrize("layouts", [(True, True), (False, True), (False, False), (True, False)])
+def test_gemm_tc_matches_numpy(X, M, N, K, layouts):
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    a = rng.standard_normal((M, K))
+    b = rng.standard_normal((K, N))
+    want = a @ b
+    got = X.gemm_f64(a, b, impl=1, a_kcontig=layouts[0], b_kcontig=layouts[1])
+    check(got, want, f"tc gemm {M}x{N}x{K} {layouts}")
+    ref = X.gemm_f64(a, b, impl=0, a_kcontig=layouts[0], b_kcontig=layouts[1])
+    check(ref, want, f"dmma gemm {M}x{N}x{K} {layouts}", rel=1e-12)
+
+
+def test_gemm_tc_wide_dynamic_range_and_exact_integers(X):
+    rng = np.random.default_rng(5)
+    # rows with very different scales, a zero row, a zero column
+    a = rng.standard_normal((256, 320)) * np.exp(rng.uniform(-30, 30, size=(256, 1)))
+    b = rng.standard_normal((320, 128)) * np.exp(rng.uniform(-30, 30, size=(1, 128)))
+    a[7] = 0.0
+    b[:, 9] = 0.0
+    want = a @ b
+    got = X.gemm_f64(a, b, impl=1)
+    rel = np.abs(got - want) / (np.abs(a) @ np.abs(b) + 1e-300)      # error relative to the row/column scales
+    assert float(rel.max()) < 1e-10
+    assert np.all(got[7] == 0.0) and np.all(got[:, 9] == 0.0)
+    # small integers are represented exactly by the slices => exact products
+    ai = rng.integers(-50, 51, size=(128, 256)).astype(np.float64)
+    bi = rng.integers(-50, 51, size=(256, 64)).astype(np.float64)
+    assert np.array_equal(X.gemm_f64(ai, bi, impl=1), ai @ bi)
+
+
+SCRIPT = r"""
+import json, sys
+import numpy as np
+sys.path.insert(0, %(root)r)
+import oracle as O
+from mercer_research_b200 import RCN, _lib
+rng = np.random.default_rng(31)
+sizes, n_in, classes, B = [384, 256], 512, 10, 320
+model = RCN(classes, [], sizes)
+model.load_weights_and_bias(n_in)
+net = O.Net(model.layer_shapes)
+params = np.random.default_rng(32).standard_normal(net.n_params) / 8
+model.set_params(params)
+feats = np.maximum(rng.standard_normal((B, n_in)), 0)
+labels = rng.integers(0, classes, size=B)
+_lib.profile_enable(True)
+model.accumulate_gradients(feats, labels=labels)
+names = sorted(_lib.profile_report())
+_lib.profile_enable(False)
+g = model.get_gradients()
+model.apply_gradients(3.0, B)
+p = model.get_params()
+want_p, want_g = net.train_batch(params, feats, np.eye(classes)[labels], 3.0)
+acts = [model.activations(l) for l in range(3)]
+ref_acts = net.forward_all(params, feats) if hasattr(net, "forward_all") else None
+def rel(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+print(json.dumps({"kernels": names, "grad_rel": rel(g, want_g), "param_rel": rel(p, want_p),
+                  "pred_equal": bool(np.array_equal(O.argmax_last(acts[-1]), O.argmax_last(net.forward(params, feats))))}))
+"""
+
+
+def test_dense_layers_forced_through_tensor_cores_match_oracle(built_library):
+    env = dict(os.environ, RCN_CUDA_GEMM="tc", RCN_CUDA_SMALLNET="0")
+    out = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}], env=env, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert any("tcgen05" in k for k in r["kernels"]), r["kernels"]
+    assert r["grad_rel"] < 1e-9 and r["param_rel"] < 1e-9, r
+    assert r["pred_equal"], "predicted labels must be exact"
