@@ -432,41 +432,75 @@ def run_gpu(args, wl, rank, world, local_rank):
     fwd, bwd_d, bwd_w = dense_flops_per_image(shapes)
     sum_rows = sum(r for r, _ in shapes)
     act_bytes = 2 * sum_rows * 8                      # a_l and delta_l written once per sample
-    # algorithmic work per launch of each kernel: (bound, bytes, flops)
+    int8_peak = 2.0 * (pk["bf16_tflops"] or 1590.0)   # kind::i8 issues at twice the bf16 rate; bf16 is the measured figure
+
+    def on_tc(M, N, K):                               # mirrors use_tensor_cores() in csrc/dense.cu
+        return M >= 256 and N >= 256 and K >= 512 and float(M) * N * K >= 8.0e9
+
+    # algorithmic work per step of each kernel NAME: name -> [bound, bytes, flops]; the per-launch
+    # figure is this divided by the launches per step the profiler counted
     alg = {
-        "features_fused_kernel": ("hbm", B * (H * W * 1 + L * 8), B * 48 * H * W),
-        "smallnet_fwd_bwd_kernel(fused features)": ("hbm", B * (H * W * 1 + 8 + L * 8 + act_bytes) + n_params * 8,
-                                                    B * (48 * H * W + fwd + bwd_d)),
-        "smallnet_fwd_bwd_kernel": ("hbm", B * (L * 8 + 8 + act_bytes) + n_params * 8, B * (fwd + bwd_d)),
-        "smallnet_wgrad_kernel": ("hbm", B * (L + shapes[0][0]) * 8 + n_params * 8, B * bwd_w),
-        "dense_forward_gemm": ("tensor", None, B * fwd / len(shapes)),
-        "dense_backward_data_gemm": ("tensor", None, B * bwd_d / max(1, len(shapes) - 1)),
-        "dense_backward_weight_gemm": ("tensor", None, B * bwd_w / len(shapes)),
-        "sgd_update_kernel": ("hbm", 3 * n_params * 8, 2 * n_params),
+        "features_fused_kernel": ["hbm", B * (H * W * 1 + L * 8), B * 48 * H * W],
+        "smallnet_fwd_bwd_kernel(fused features)": ["hbm", B * (H * W * 1 + 8 + L * 8 + act_bytes) + n_params * 8,
+                                                    B * (48 * H * W + fwd + bwd_d)],
+        "smallnet_fwd_bwd_kernel": ["hbm", B * (L * 8 + 8 + act_bytes) + n_params * 8, B * (fwd + bwd_d)],
+        "smallnet_wgrad_kernel": ["hbm", B * (L + shapes[0][0]) * 8 + n_params * 8, B * bwd_w],
+        "sgd_update_kernel": ["hbm", 3 * n_params * 8, 2 * n_params],
+        "dp_allreduce_sgd_kernel": ["hbm", 3 * n_params * 8, 2 * n_params],
+        "bias_grad_kernel": ["hbm", B * sum_rows * 8, B * sum_rows],
     }
+    for tag in ("forward", "backward_data", "backward_weight"):
+        for suffix in ("", "(tcgen05 int8 slices)"):
+            alg[f"dense_{tag}_gemm{suffix}"] = ["tensor", 0, 0]
+    slice_bytes = 0
+    for li, (r, c) in enumerate(shapes):
+        f = 2.0 * r * c * B
+        tc_f, tc_w = on_tc(r, B, c), on_tc(r, c, B)
+        alg["dense_forward_gemm" + ("(tcgen05 int8 slices)" if tc_f else "")][2] += f
+        alg["dense_backward_weight_gemm" + ("(tcgen05 int8 slices)" if tc_w else "")][2] += f
+        slice_bytes += (14 * (r * c + c * B) if tc_f else 0) + (14 * (r * B + c * B) if tc_w else 0)
+        if li >= 1:
+            rp = shapes[li - 1][0]                    # backward-data into layer li-1: M = rp, K = r, N = B
+            tc_d = on_tc(rp, B, r)
+            alg["dense_backward_data_gemm" + ("(tcgen05 int8 slices)" if tc_d else "")][2] += 2.0 * rp * r * B
+            slice_bytes += 14 * (rp * r + r * B) if tc_d else 0
+    alg["ozaki_slice"] = ["hbm", slice_bytes, 0]      # both slicing kernels together: 8 B read + 6 B written per element
     kernels = {k: {"launches_per_step": v["launches"] / prof_steps, "avg_us": v["total_ms"] / v["launches"] * 1e3,
                    "share": None} for k, v in prof.items()}
     tot = sum(v["total_ms"] for v in prof.values())
     fp64_peak = measure_fp64_peak(torch, dev)
     for k, v in prof.items():
         kernels[k]["share"] = round(v["total_ms"] / tot, 4)
-        if k in alg:
-            d_s = v["total_ms"] / v["launches"] * 1e-3
-            bnd, nbytes, nflops = alg[k]
+        key = "ozaki_slice" if k.startswith("ozaki_slice") else k
+        if key in alg:
+            d_s = v["total_ms"] / prof_steps * 1e-3          # seconds of this kernel name per step
+            if key == "ozaki_slice":
+                d_s = sum(x["total_ms"] for n_, x in prof.items() if n_.startswith("ozaki_slice")) / prof_steps * 1e-3
+            bnd, nbytes, nflops = alg[key]
             kernels[k]["bound"] = bnd
             if nbytes:
                 kernels[k]["GBps"] = round(nbytes / d_s / 1e9, 1)
                 kernels[k]["frac_hbm"] = round(nbytes / d_s / 1e9 / pk["hbm_gbs"], 4)
-            if nflops:
+            if nflops and "tcgen05" in k:
+                kernels[k]["f64_equiv_TFLOPs"] = round(nflops / d_s / 1e12, 2)
+                kernels[k]["int8_TOPs"] = round(21 * nflops / d_s / 1e12, 1)     # 21 slice products per f64 product
+                kernels[k]["frac_int8_tensor"] = round(21 * nflops / d_s / 1e12 / int8_peak, 4)
+            elif nflops:
                 kernels[k]["TFLOPs_f64"] = round(nflops / d_s / 1e12, 3)
                 kernels[k]["frac_fp64"] = round(nflops / d_s / 1e12 / fp64_peak, 4)
     top = max(prof, key=lambda k: prof[k]["total_ms"])
     bound, nbytes, nflops = alg.get(top, ("hbm", 0, 0))
-    dur_s = prof[top]["total_ms"] / prof[top]["launches"] * 1e-3
+    dur_s = prof[top]["total_ms"] / prof_steps * 1e-3        # all launches of the top kernel in one step
+    peak_source = pk["source"]
     if bound == "hbm":
         achieved, peak, unit = nbytes / dur_s / 1e9, pk["hbm_gbs"], "GB/s"
+    elif "tcgen05" in top:
+        achieved, peak, unit = 21 * nflops / dur_s / 1e12, int8_peak, "TFLOP/s"
+        peak_source = ("int8 tensor peak taken as 2 x the measured bf16 cuBLAS figure of MEASURED_PEAKS.json (kind::i8 issues at twice "
+                       "the bf16 rate; nominal 4500); achieved = 21 exact int8 slice products per f64 product, in int8 TOP/s")
     else:
         achieved, peak, unit = nflops / dur_s / 1e12, fp64_peak, "TFLOP/s"
+        peak_source = "torch.matmul f64 8192^3 measured in this run (f64 DMMA path; MEASURED_PEAKS.json has no f64 figure)"
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed `ncu --set full` capture
     if os.path.exists(tpath):
@@ -475,8 +509,7 @@ def run_gpu(args, wl, rank, world, local_rank):
     step_flops = B * (48 * H * W + fwd + bwd_d + bwd_w)
     roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
                 "frac": achieved / peak if peak else None, "traffic": traffic,
-                "peak_source": pk["source"] if bound == "hbm" else "torch.matmul f64 8192^3 measured in this run (f64 DMMA path; "
-                                                                   "MEASURED_PEAKS.json has no f64 figure)",
+                "peak_source": peak_source,
                 "precision": "f64", "fp64_dgemm_tflops_measured": fp64_peak,
                 "durations": "CUDA events around every launch on the launching stream, separate eager pass of "
                              f"{prof_steps} steps (the timed region replays a CUDA graph)",

@@ -77,6 +77,9 @@ int rcn_cuda_feature_shape(rcn_cuda_handle h, size_t H, size_t W, size_t* n_maps
  * shapes, including its `4^c / 2^p * l` first-layer width. Values are then injected with set_params
  * (the reference draws them from an unseeded thread_rng, rcn.rs:500-523). */
 int rcn_cuda_init_params(rcn_cuda_handle h, size_t feature_len);
+/* Explicit layer shapes (rows[i] x cols[i], cols[i] == rows[i-1]) for a model restored from a bincode checkpoint
+ * (bincode::deserialize, main.rs:50 / backend/src/main.rs:68): the file, not the config, decides the matrices. */
+int rcn_cuda_init_params_shapes(rcn_cuda_handle h, const size_t* rows, const size_t* cols, size_t n_layers);
 int rcn_cuda_num_layers(rcn_cuda_handle h, size_t* n_layers);
 int rcn_cuda_layer_shape(rcn_cuda_handle h, size_t layer, size_t* rows, size_t* cols);
 int rcn_cuda_param_count(rcn_cuda_handle h, size_t* n);

@@ -32,6 +32,7 @@ SIGNATURES = {
     "rcn_cuda_synchronize": [_vp],
     "rcn_cuda_feature_shape": [_vp, _sz, _sz, _szp, _szp, _szp],
     "rcn_cuda_init_params": [_vp, _sz],
+    "rcn_cuda_init_params_shapes": [_vp, _vp, _vp, _sz],
     "rcn_cuda_num_layers": [_vp, _szp],
     "rcn_cuda_layer_shape": [_vp, _sz, _szp, _szp],
     "rcn_cuda_param_count": [_vp, _szp],

@@ -364,31 +364,18 @@ int rcn_cuda_feature_shape(rcn_cuda_handle h, size_t H, size_t W, size_t* n_maps
     return RCN_OK;
 }
 
-int rcn_cuda_init_params(rcn_cuda_handle h, size_t l) {
-    RCN_ENTER(h);
-    // load_weights_and_bias (rcn.rs:425-457)
-    if (h->ff.empty()) return fail(RCN_ERR_OUT_OF_BOUNDS, "index out of bounds: feedforward_cfg is empty (rcn.rs:444)");
-    unsigned c = 0, p = 0;
-    for (int32_t layer : h->cfg) {
-        if (layer == RCN_LAYER_CONV_NONE || layer == RCN_LAYER_CONV_SAME) c += 1; else p += 2;
-    }
-    if (c > 20 || p > 60) return fail(RCN_ERR_INVALID, "convpool stack too deep");
-    size_t pc = 1, pp = 1;
-    for (unsigned i = 0; i < c; ++i) pc *= 4;
-    for (unsigned i = 0; i < p; ++i) pp *= 2;
-    size_t a = pc / pp * l;  // 4^c / 2^p * l, integer division first (rcn.rs:443)
-    size_t b = h->ff[0];
-    const size_t n = h->ff.size() + 1;
+namespace {
+// Installs explicit layer shapes (rows[i] x cols[i]), allocates zeroed parameters / gradients, picks the fused path.
+int install_shapes(rcn_cuda_model* h, const std::vector<size_t>& rows, const std::vector<size_t>& cols) {
+    const size_t n = rows.size();
     h->rows.clear(); h->cols.clear(); h->w_off.clear(); h->b_off.clear();
     size_t off = 0, sum_rows = 0;
     for (size_t i = 0; i < n; ++i) {
-        if (b == 0) return fail(RCN_ERR_INVALID, "layer %zu has zero neurons", i);
-        h->rows.push_back(b); h->cols.push_back(a);  // dims = (output_size, input_size)  (rcn.rs:502)
-        h->w_off.push_back(off); off += a * b;
-        h->b_off.push_back(off); off += b;
-        sum_rows += b;
-        a = b;
-        b = (i + 1 < h->ff.size()) ? h->ff[i + 1] : h->classes;
+        if (rows[i] == 0) return fail(RCN_ERR_INVALID, "layer %zu has zero neurons", i);
+        h->rows.push_back(rows[i]); h->cols.push_back(cols[i]);  // dims = (output_size, input_size)  (rcn.rs:502)
+        h->w_off.push_back(off); off += rows[i] * cols[i];
+        h->b_off.push_back(off); off += rows[i];
+        sum_rows += rows[i];
     }
     h->n_params = off; h->sum_rows = sum_rows;
     {   // fused small-network path (smallnet.cu) unless RCN_CUDA_SMALLNET=0
@@ -414,6 +401,42 @@ int rcn_cuda_init_params(rcn_cuda_handle h, size_t l) {
     h->params_ready = true;
     h->stats_valid = false;
     return RCN_OK;
+}
+}  // namespace
+
+int rcn_cuda_init_params(rcn_cuda_handle h, size_t l) {
+    RCN_ENTER(h);
+    // load_weights_and_bias (rcn.rs:425-457)
+    if (h->ff.empty()) return fail(RCN_ERR_OUT_OF_BOUNDS, "index out of bounds: feedforward_cfg is empty (rcn.rs:444)");
+    unsigned c = 0, p = 0;
+    for (int32_t layer : h->cfg) {
+        if (layer == RCN_LAYER_CONV_NONE || layer == RCN_LAYER_CONV_SAME) c += 1; else p += 2;
+    }
+    if (c > 20 || p > 60) return fail(RCN_ERR_INVALID, "convpool stack too deep");
+    size_t pc = 1, pp = 1;
+    for (unsigned i = 0; i < c; ++i) pc *= 4;
+    for (unsigned i = 0; i < p; ++i) pp *= 2;
+    size_t a = pc / pp * l;  // 4^c / 2^p * l, integer division first (rcn.rs:443)
+    size_t b = h->ff[0];
+    const size_t n = h->ff.size() + 1;
+    std::vector<size_t> rows, cols;
+    for (size_t i = 0; i < n; ++i) {
+        rows.push_back(b); cols.push_back(a);
+        a = b;
+        b = (i + 1 < h->ff.size()) ? h->ff[i + 1] : h->classes;
+    }
+    return install_shapes(h, rows, cols);
+}
+
+// A deserialized model carries whatever matrices its checkpoint holds (main.rs:50): install explicit shapes.
+int rcn_cuda_init_params_shapes(rcn_cuda_handle h, const size_t* rows, const size_t* cols, size_t n_layers) {
+    RCN_ENTER(h);
+    if (!rows || !cols || n_layers == 0) return fail(RCN_ERR_INVALID, "need at least one layer shape");
+    for (size_t i = 1; i < n_layers; ++i)
+        if (cols[i] != rows[i - 1])
+            return fail(RCN_ERR_SHAPE, "Matrix multiplication dimensions mismatch: layer %zu has %zu inputs, layer %zu has %zu outputs", i,
+                        cols[i], i - 1, rows[i - 1]);
+    return install_shapes(h, std::vector<size_t>(rows, rows + n_layers), std::vector<size_t>(cols, cols + n_layers));
 }
 
 int rcn_cuda_num_layers(rcn_cuda_handle h, size_t* n_layers) {

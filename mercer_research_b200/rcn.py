@@ -90,6 +90,17 @@ class RCN:
         self._shapes: List[Tuple[int, int]] = []
 
     # -- lifetime ---------------------------------------------------------------------------------------------
+    def save(self, path: str = "./rcn.bin"):
+        """``fs::write("./rcn.bin", bincode::serialize(&model)?)`` (main.rs:77), byte-compatible with the reference."""
+        from . import serialization
+        serialization.save(self, path)
+
+    @staticmethod
+    def load(path: str = "./rcn.bin", device: int = 0) -> "RCN":
+        """``bincode::deserialize`` of a reference (or own) checkpoint onto a B200 (main.rs:47-50)."""
+        from . import serialization
+        return serialization.load(path, device=device)
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.rcn_cuda_destroy(self._h)
@@ -140,6 +151,13 @@ class RCN:
             r, c = C.c_size_t(), C.c_size_t()
             _lib.check(self._lib.rcn_cuda_layer_shape(self._h, i, C.byref(r), C.byref(c)))
             self._shapes.append((r.value, c.value))
+
+    def load_weights_and_bias_shapes(self, shapes):
+        """Explicit (rows, cols) per layer, for a model restored from a checkpoint (serialization.py)."""
+        rows = (C.c_size_t * len(shapes))(*[int(s[0]) for s in shapes])
+        cols = (C.c_size_t * len(shapes))(*[int(s[1]) for s in shapes])
+        _lib.check(self._lib.rcn_cuda_init_params_shapes(self._h, rows, cols, len(shapes)))
+        self._shapes = [(int(s[0]), int(s[1])) for s in shapes]
 
     def _require_params(self):
         if not self._shapes:  # raises RCN_ERR_STATE from the library

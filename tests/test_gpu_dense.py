@@ -397,3 +397,22 @@ def test_dp_peer_memory_exchange_two_gpus(api):
     assert np.array_equal(g0, g1), "gradient buffers hold the same global sum on every rank"
     for m in ranks:
         m.dp_shutdown()
+
+
+def test_checkpoint_round_trip_on_device(api, tmp_path):
+    """rcn.bin (bincode layout, serialization.py): save a trained model, reload it, same predictions and parameters."""
+    rng = np.random.default_rng(41)
+    cfg = [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max)]
+    model = api.RCN(10, cfg, [30], "images/train", "images/test")
+    model.load_weights_and_bias(784)
+    model.set_params(rng.standard_normal(model.n_params))
+    model.scale_set = (41.5, 63.25)
+    images = rng.integers(0, 256, size=(32, 28, 28), dtype=np.uint8)
+    model.train_batch_images(images, rng.integers(0, 10, size=32), 3.0)
+    path = str(tmp_path / "rcn.bin")
+    model.save(path)
+    back = api.RCN.load(path)
+    assert back.layer_shapes == model.layer_shapes and back.scale_set == model.scale_set
+    assert back.training_path == "images/train" and back.testing_path == "images/test"
+    assert np.array_equal(back.get_params(), model.get_params())
+    assert np.array_equal(back.classify_images(images), model.classify_images(images))
