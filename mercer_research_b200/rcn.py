@@ -490,36 +490,82 @@ class RCN:
         _lib.check(self._lib.rcn_cuda_bind_gradient_buffer(self._h, tensor.data_ptr(), tensor.numel()))
 
     # -- whole-run driver (rcn.rs:126-167) --------------------------------------------------------------------
+    def _set_stats(self, images_dev, chunk: int = 16384) -> Tuple[float, float]:
+        """gen_scales (rcn.rs:230-251) over a whole device-resident set: mean / population sd of all raw features."""
+        import torch
+        n = images_dev.shape[0]
+        if n <= chunk:
+            return self.gen_scales(self.flatten_feature_set(images_dev))
+        feats = torch.cat([self.flatten_feature_set(images_dev[i:i + chunk]) for i in range(0, n, chunk)])
+        return self.gen_scales(feats)
+
     def train_arrays(self, train_images, train_labels, test_images, test_labels, batch_size: int, epochs: int,
-                     eta: float, seed: int = 0, log=print):
-        """``RCN::train`` (rcn.rs:126-167) on in-memory decoded images instead of PNG directories: features for
-        both sets, scale_set from each set in turn (so it ends up holding the TEST set's statistics, rcn.rs:134-137),
-        per-epoch shuffle (harness-seeded instead of thread_rng), ``chunks_exact`` batches (remainder dropped),
-        per-epoch evaluation and the reference's log line. Parameters must already be present (inject them with
-        set_params) or are drawn N(0,1) from ``seed`` like rcn.rs:500-523."""
+                     eta: float, seed: int = 0, log=print, cuda_graph: bool = True):
+        """``RCN::train`` (rcn.rs:126-167) on in-memory decoded images instead of PNG directories, with both sets
+        RESIDENT IN HBM: scale_set from each set in turn (the training steps standardise with the training set's
+        statistics, evaluation with the test set's, and scale_set ends up holding the TEST set's, rcn.rs:134-137,406);
+        per-epoch shuffle (harness-seeded permutation instead of thread_rng, rewritten in place on the device);
+        ``chunks_exact`` batches selected on the device by the epoch cursor (remainder dropped, rcn.rs:147); per-epoch
+        evaluation with the exact-one-hot rule (rcn.rs:152-157) and the reference's log line (rcn.rs:158-164).
+        Parameters must already be present (inject them with set_params) or are drawn N(0,1) from ``seed`` like
+        rcn.rs:500-523. Returns the per-epoch accept counts."""
+        import torch
+        dev = torch.device("cuda", self.device)
         rng = np.random.default_rng(seed)
-        tr = self.flatten_feature_set(np.asarray(train_images))
-        self.gen_scales(tr)
-        tr = self.standardise(tr)
-        te = self.flatten_feature_set(np.asarray(test_images))
-        self.gen_scales(te)
-        te = self.standardise(te)
-        train_labels = np.asarray(train_labels, dtype=np.int64)
-        test_labels = np.asarray(test_labels, dtype=np.int64)
+        tr = torch.as_tensor(np.ascontiguousarray(train_images)).to(dev)
+        te = torch.as_tensor(np.ascontiguousarray(test_images)).to(dev)
+        if tr.dtype != torch.uint8:
+            tr, te = tr.to(torch.float64), te.to(torch.float64)
+        tr_y = torch.as_tensor(np.asarray(train_labels, dtype=np.int64)).to(dev)
+        te_y = torch.as_tensor(np.asarray(test_labels, dtype=np.int64)).to(dev)
+        n, H, W = int(tr.shape[0]), int(tr.shape[1]), int(tr.shape[2])
+        stream = torch.cuda.current_stream(dev)
+        self.set_stream(stream.cuda_stream)
+        tr_stats = self._set_stats(tr)
+        te_stats = self._set_stats(te)
         if not self._shapes:
-            self.load_weights_and_bias(tr.shape[1])
+            self.load_weights_and_bias(self.feature_len(H, W))
             self.set_params(rng.standard_normal(self.n_params))
         history = []
-        n = tr.shape[0]
+        n_steps = n // int(batch_size)
+        perm = torch.arange(n, dtype=torch.int64, device=dev)
+        graph = None
+        if n_steps:
+            self.scale_set = tr_stats
+            self.epoch_bind(tr, tr_y, int(batch_size), perm)
+            if cuda_graph and tr.dtype == torch.uint8:
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(stream)
+                with torch.cuda.stream(side):
+                    self.set_stream(side.cuda_stream)
+                    self.epoch_accumulate()                   # warm-up launch outside capture (allocations, attributes)
+                stream.wait_stream(side)
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+                    self.epoch_step(eta)
+                self.set_stream(stream.cuda_stream)
         for e in range(epochs):
-            perm = rng.permutation(n)
-            for s in range(0, n - batch_size + 1, batch_size):  # chunks_exact (rcn.rs:147)
-                idx = perm[s:s + batch_size]
-                self.train_batch(tr[idx], eta, labels=train_labels[idx])
-            accept = self.evaluate(te, test_labels)
+            if n_steps:
+                perm.copy_(torch.as_tensor(rng.permutation(n)), non_blocking=False)   # training_set.shuffle (rcn.rs:146)
+                self.scale_set = tr_stats
+                self.epoch_seek(0)
+                for _ in range(n_steps):                      # chunks_exact(batch_size) (rcn.rs:147-149)
+                    if graph is not None:
+                        graph.replay()
+                    else:
+                        self.epoch_step(eta)
+            self.scale_set = te_stats
+            accept = 0
+            for i in range(0, int(te.shape[0]), 16384):
+                feats = self.flatten_feature_set(te[i:i + 16384], standardise=True)
+                accept += self.evaluate(feats, te_y[i:i + 16384])
             history.append(accept)
             if log:
-                log("Epoch {}: {}/{} [{:.2f}%]".format(e, accept, te.shape[0], accept / te.shape[0] * 100.0))
+                log("Epoch {}: {}/{} [{:.2f}%]".format(e, accept, int(te.shape[0]), accept / max(1, int(te.shape[0])) * 100.0))
+        self.scale_set = te_stats
+        self.synchronize()
         return history
 
     def train(self, batch_size: int, epochs: int, eta: float, training_class_size_limit: int,

@@ -416,3 +416,38 @@ def test_checkpoint_round_trip_on_device(api, tmp_path):
     assert back.training_path == "images/train" and back.testing_path == "images/test"
     assert np.array_equal(back.get_params(), model.get_params())
     assert np.array_equal(back.classify_images(images), model.classify_images(images))
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_train_arrays_matches_oracle_epoch_loop(api, graph):
+    """The device-resident epoch driver (device-side shuffle indirection + cursor, optional CUDA graph) against the
+    oracle running rcn.rs:144-165 literally: same permutations, same batches, train/test statistics applied the same way."""
+    rng = np.random.default_rng(51)
+    n, nt, B, epochs = 77, 40, 16, 3
+    tr = rng.integers(0, 256, size=(n, 28, 28), dtype=np.uint8)
+    te = rng.integers(0, 256, size=(nt, 28, 28), dtype=np.uint8)
+    trl = rng.integers(0, 10, size=n).astype(np.int64)
+    tel = rng.integers(0, 10, size=nt).astype(np.int64)
+    model = api.RCN(10, [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max)], [30])
+    model.load_weights_and_bias(784)
+    net = O.Net(model.layer_shapes)
+    params = np.random.default_rng(52).standard_normal(net.n_params) * 0.1
+    model.set_params(params)
+    hist = model.train_arrays(tr, trl, te, tel, batch_size=B, epochs=epochs, eta=0.5, seed=7, log=None, cuda_graph=graph)
+    # oracle
+    ftr, fte = O.features_u8(CP, tr), O.features_u8(CP, te)
+    mtr, mte = O.gen_scales(ftr), O.gen_scales(fte)
+    xtr, xte = O.standardise(ftr, *mtr), O.standardise(fte, *mte)
+    r2 = np.random.default_rng(7)
+    p = params.copy()
+    want_hist = []
+    for _ in range(epochs):
+        perm = r2.permutation(n)
+        for s in range(0, n - B + 1, B):
+            idx = perm[s:s + B]
+            p, _ = net.train_batch(p, xtr[idx], np.eye(10)[trl[idx]], 0.5)
+        want_hist.append(O.accuracy(net.forward(p, xte), tel))
+    assert hist == want_hist
+    assert_close(model.get_params(), p, rtol=1e-9, what="parameters after the epoch loop")
+    gm, gs = model.scale_set
+    assert abs(gm - mte[0]) <= 1e-12 * mte[0] and abs(gs - mte[1]) <= 1e-12 * mte[1]
