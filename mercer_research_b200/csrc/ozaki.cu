@@ -63,39 +63,60 @@ __global__ void __launch_bounds__(256) ozaki_slice_kmajor_kernel(const double* _
     }
 }
 
-// element (r, k) at X[k*ld + r]: one CTA per 32 rows, all k; shared-memory transpose to k-contiguous planes.
+// element (r, k) at X[k*ld + r] (r contiguous).  Two kernels so that the machine is full even for 4096-row operands:
+//   amax:  grid (rows/32, k-splits), per-row maxima combined with atomicMax on the bit pattern (|x| >= 0: bit order ==
+//          value order), 8 loads in flight per thread;
+//   slice: grid (rows/32, k-chunks of RM_KCHUNK): slices a 32-row x 64-k tile at a time and transposes it through
+//          shared memory so the int8 planes are written k-contiguous in 64-byte runs.
 constexpr int TR_PITCH = 68;   // bytes per (slice, row) line of the 64-k tile: 17 words -> conflict-free byte scatter
-__global__ void __launch_bounds__(256) ozaki_slice_rmajor_kernel(const double* __restrict__ X, size_t ld, int R, int K, int Kp,
-                                                                 int8_t* __restrict__ planes, double* __restrict__ scale) {
+constexpr int RM_KCHUNK = 512;
+
+__global__ void __launch_bounds__(256) ozaki_amax_rmajor_kernel(const double* __restrict__ X, size_t ld, int R, int K, int k_per_cta,
+                                                                unsigned long long* __restrict__ amax_bits) {
     __shared__ double red[8][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 32 + lane;
+    const int k_lo = blockIdx.y * k_per_cta, k_hi = min(K, k_lo + k_per_cta);
+    double amax = 0.0;
+    if (r < R) {
+        for (int k = k_lo + warp; k < k_hi; k += 64) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (k + 8 * u < k_hi) ? X[(size_t)(k + 8 * u) * ld + r] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) amax = fmax(amax, fabs(v[u]));
+        }
+    }
+    red[warp][lane] = amax;
+    __syncthreads();
+    if (warp == 0 && r < R) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) amax = fmax(amax, red[w][lane]);
+        if (amax == amax) atomicMax(amax_bits + r, (unsigned long long)__double_as_longlong(amax));
+        else atomicMax(amax_bits + r, 0x7FF8000000000000ull);    // NaN poisons the row (row_scale zeroes it)
+    }
+}
+
+__global__ void __launch_bounds__(256) ozaki_slice_rmajor_kernel(const double* __restrict__ X, size_t ld, int R, int K, int Kp,
+                                                                 const unsigned long long* __restrict__ amax_bits,
+                                                                 int8_t* __restrict__ planes, double* __restrict__ scale) {
     __shared__ double s_inv[32];
     __shared__ __align__(4) int8_t tile[OZ_S][32][TR_PITCH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r0 = blockIdx.x * 32;
     const int r = r0 + lane;
     const bool rok = r < R;
-    double amax = 0.0;
-    for (int k = warp; k < K; k += 32) {        // 4 loads in flight per thread
-        double v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = (rok && k + 8 * u < K) ? X[(size_t)(k + 8 * u) * ld + r] : 0.0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) amax = fmax(amax, fabs(v[u]));
-    }
-    red[warp][lane] = amax;
-    __syncthreads();
     if (warp == 0) {
-#pragma unroll
-        for (int w = 1; w < 8; ++w) amax = fmax(amax, red[w][lane]);
-        double inv, sc;
-        row_scale(amax, inv, sc);
+        double inv = 0.0, sc = 0.0;
+        if (rok) row_scale(__longlong_as_double((long long)amax_bits[r]), inv, sc);
         s_inv[lane] = inv;
-        if (rok) scale[r] = sc;
+        if (rok && blockIdx.y == 0) scale[r] = sc;
     }
     __syncthreads();
     const double inv = s_inv[lane];
     const size_t plane = (size_t)R * Kp;
-    for (int kb = 0; kb < Kp; kb += 64) {
+    const int kb_lo = blockIdx.y * RM_KCHUNK, kb_hi = min(Kp, kb_lo + RM_KCHUNK);
+    for (int kb = kb_lo; kb < kb_hi; kb += 64) {
         double v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -145,14 +166,25 @@ EncodeTiledFn encode_tiled_fn() {
 
 bool ozaki_available() { return encode_tiled_fn() != nullptr; }
 
-int ozaki_slice(const OzOperand& op, int rows, int K, int Kp, int8_t* planes, double* scale, cudaStream_t stream) {
+int ozaki_slice(const OzOperand& op, int rows, int K, int Kp, int8_t* planes, double* scale, double* scale_scratch,
+                cudaStream_t stream) {
     if (rows <= 0) return RCN_OK;
     if (op.kcontig) {
         RCN_LAUNCH("ozaki_slice_kmajor_kernel", stream,
                    ozaki_slice_kmajor_kernel<<<cdiv(rows, 8), 256, 0, stream>>>(op.p, op.ld, rows, K, Kp, planes, scale));
     } else {
+        // the scale array doubles as the per-row |x| maximum (bit pattern) between the two kernels
+        unsigned long long* amax_bits = reinterpret_cast<unsigned long long*>(scale_scratch);
+        RCN_CUDA_TRY(cudaMemsetAsync(amax_bits, 0, (size_t)rows * sizeof(unsigned long long), stream));
+        int ksplit = (int)((4 * (size_t)kNumSMs + cdiv(rows, 32) - 1) / cdiv(rows, 32));
+        if (ksplit > (K + 255) / 256) ksplit = (K + 255) / 256;
+        if (ksplit < 1) ksplit = 1;
+        const int k_per_cta = (K + ksplit - 1) / ksplit;
+        RCN_LAUNCH("ozaki_amax_rmajor_kernel", stream,
+                   ozaki_amax_rmajor_kernel<<<dim3(cdiv(rows, 32), (unsigned)ksplit), 256, 0, stream>>>(op.p, op.ld, rows, K, k_per_cta, amax_bits));
         RCN_LAUNCH("ozaki_slice_rmajor_kernel", stream,
-                   ozaki_slice_rmajor_kernel<<<cdiv(rows, 32), 256, 0, stream>>>(op.p, op.ld, rows, K, Kp, planes, scale));
+                   ozaki_slice_rmajor_kernel<<<dim3(cdiv(rows, 32), cdiv(Kp, RM_KCHUNK)), 256, 0, stream>>>(op.p, op.ld, rows, K, Kp, amax_bits,
+                                                                                                           planes, scale));
     }
     return RCN_OK;
 }
