@@ -257,9 +257,10 @@ int rcn_cuda_ext_softmax_xent(int device, void* cuda_stream, const double* z, si
  * C (M x N, column-major) = A * B with A(m,k) = a_kcontig ? A[m*lda + k] : A[k*lda + m] and
  * B(k,n) = b_kcontig ? B[n*ldb + k] : B[k*ldb + n].
  *   impl 0: f64 tensor path (DMMA, mma.sync.m8n8k4.f64), cp.async-staged.
- *   impl 1: tcgen05 / TMEM / TMA integer-slice path: both operands are split into six 7-bit int8 slices under per-row
- *           power-of-two scales, the 21 slice products with i+j <= 5 run as exact s8 x s8 -> s32 tensor-core MMAs and are
- *           recombined in f64 (truncation ~ 1e-12 of the row scales; operands must be finite; K <= 65536).
+ *   impl 1: tcgen05 / TMEM / TMA integer-slice path: both operands are written as five balanced base-256 digit planes
+ *           (int8) under per-row power-of-two scales, the 15 plane products with i+j <= 4 run as exact s8 x s8 -> s32
+ *           tensor-core MMAs and are recombined in f64 (truncation ~ 6e-11 of the result; operands must be finite;
+ *           K <= 16384).
  * The dense layers pick impl 1 automatically for large shapes (env RCN_CUDA_GEMM = dmma | tc | simt overrides). */
 int rcn_cuda_ext_gemm_f64(int device, void* cuda_stream, const double* A, size_t lda, int a_kcontig, const double* B,
                           size_t ldb, int b_kcontig, size_t M, size_t N, size_t K, int impl, double* C);

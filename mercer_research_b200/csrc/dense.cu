@@ -34,7 +34,7 @@ GemmImpl gemm_impl() {
 // tcgen05 integer-slice path (ozaki.cuh) when the contraction is really dense: full 128 x 64 tiles, deep K, and enough
 // work to amortise slicing both operands; everything else (skinny layers like 4096 -> 10) stays on DMMA.
 static bool use_tensor_cores(size_t M, size_t N, size_t K, OzakiWorkspace* oz) {
-    if (!oz || !ozaki_available() || K > 65536) return false;
+    if (!oz || !ozaki_available() || K > (size_t)OZ_MAX_K) return false;
     if (gemm_impl() == GEMM_TC) return M >= 1 && N >= 1 && K >= 1;
     if (gemm_impl() != GEMM_AUTO) return false;
     return M >= 256 && N >= 256 && K >= 512 && (double)M * (double)N * (double)K >= 8.0e9;

@@ -12,20 +12,35 @@ namespace rcn {
 
 namespace {
 
-// x = scale * sum_j q_j 2^(-7j): t = x * 2^(6-e) in (-64, 64); q_0 = rint(t); t = (t - q_0) * 128; ...  (every step exact)
+// x = scale * (q_0 + sum_{j>=1} d_j 2^(-8j)) with BALANCED digits: t = x * 2^(6-e) in (-64, 64); q_0 = rint(t);
+// r = t - q_0 in [-0.5, 0.5]; d_j = rint(256 r), r = 256 r - d_j ...  Every step is exact in f64.  A digit that rounds
+// to +128 (r within 2^-9 of +0.5) is rewritten as -128 with a carry into the next more significant digit, so all
+// planes are int8 with zero-mean digits (dropped terms then add up like sqrt(K), not K); |q_0| <= 65.
 __device__ __forceinline__ void slice6(double x, double inv, int8_t (&q)[OZ_S]) {
+    int d[OZ_S];
     double t = x * inv;
+    double f = rint(t);
+    d[0] = (int)f;
+    t = (t - f) * 256.0;
 #pragma unroll
-    for (int j = 0; j < OZ_S; ++j) {
-        const double r = rint(t);
-        q[j] = (int8_t)(int)r;
-        t = (t - r) * 128.0;
+    for (int j = 1; j < OZ_S; ++j) {
+        f = rint(t);
+        d[j] = (int)f;
+        t = (t - f) * 256.0;
     }
+#pragma unroll
+    for (int j = OZ_S - 1; j >= 1; --j) {
+        const int carry = d[j] == 128 ? 1 : 0;
+        d[j] -= carry << 8;
+        d[j - 1] += carry;
+    }
+#pragma unroll
+    for (int j = 0; j < OZ_S; ++j) q[j] = (int8_t)d[j];
 }
 
 // row scale from the row maximum: amax = f * 2^e, f in [0.5, 1)  =>  |x| * 2^-e < 1
 __device__ __forceinline__ void row_scale(double amax, double& inv, double& scale) {
-    if (!(amax > 1e-290) || !(amax < 1e290)) { inv = 0.0; scale = 0.0; return; }   // zero / denormal / non-finite row: all-zero slices
+    if (!(amax > 1e-290) || !(amax < 1e290)) { inv = 0.0; scale = 0.0; return; }   // zero / denormal / non-finite row: all-zero planes
     int e;
     frexp(amax, &e);
     inv = ldexp(1.0, 6 - e);

@@ -2,22 +2,24 @@
 //
 // Why: rcn computes in f64 (rcn/src/rcn.rs:28-31,49) and the parity bar is 1e-9, but tcgen05.mma has no f64 kind, so
 // the wide dense layers (BASELINE config 5: 4096-4096-4096, batch 8192; rcn.rs:105-116 forward, :260-314 backprop
-// expressed as batched GEMMs) would be capped by the 37 TFLOP/s DMMA pipe.  The Ozaki scheme splits
-// every operand row into S signed 7-bit integer slices under a per-row power-of-two scale,
-//     x[r,k] = scale[r] * sum_j q_j[r,k] * 2^(-7j),      q_j in [-64, 64]  (int8),
-// so that every slice product  sum_k qa_i[m,k] * qb_j[n,k]  is an EXACT int32 dot product on `tcgen05.mma kind::i8`.
-// Pairs with equal i+j = d share a weight 2^(-7d) and are accumulated into the SAME int32 TMEM accumulator (still
-// exact: (d+1) * K * 64^2 < 2^31 for K <= 2^16), and diagonals d > D are dropped (their weight is below the target
-// accuracy).  With S = 6, D = 5: 21 int8 MMAs per k-step, truncation ~ 7 * 2^-42 relative to the row scales.
+// expressed as batched GEMMs) would be capped by the 37 TFLOP/s DMMA pipe.  The Ozaki scheme writes
+// every operand row as S balanced base-256 digits under a per-row power-of-two scale,
+//     x[r,k] = scale[r] * ( q_0[r,k] + sum_{j>=1} d_j[r,k] * 2^(-8j) ),   |q_0| <= 65, d_j in [-128, 127]   (all int8),
+// so that every digit-plane product  sum_k a_i[m,k] * b_j[n,k]  is an EXACT int32 dot product on `tcgen05.mma kind::i8`.
+// Pairs with equal i+j = d share the weight 2^(-8d) and accumulate into the SAME int32 TMEM accumulator -- still exact
+// while 5 * K * 128^2 < 2^31, i.e. K <= 16384 -- and diagonals d > D are dropped: the digits are zero-mean, so what is
+// dropped adds up like sqrt(K) and stays ~6e-11 of the result for S = 5, D = 4 (15 int8 MMAs per k-step).
 //
-// Kernel (one 128 x 64 output tile per CTA, 192 threads, warp-specialised):
-//   warp 0      TMA producer: per 64-deep k-block, 6 A-slice boxes (128 x 64 B) + 6 B-slice boxes (64 x 64 B),
+// Kernel (one 128 x 96 output tile per CTA, 192 threads, warp-specialised):
+//   warp 0      TMA producer: per 64-deep k-block, 5 A-plane boxes (128 x 64 B) + 5 B-plane boxes (96 x 64 B),
 //               SWIZZLE_64B, 3-stage ring guarded by full/empty mbarriers;
-//   warp 1      TMEM allocator + MMA issuer: one elected thread issues 2 x 21 tcgen05.mma (M128 N64 K32, s8 x s8 -> s32)
-//               per stage into 6 TMEM accumulators (384 of 512 columns), tcgen05.commit frees the smem slot;
-//   warps 2-5   epilogue: tcgen05.ld the 6 diagonals, Horner-combine them in f64, apply the row scales and the layer's
+//   warp 1      TMEM allocator + MMA issuer: one elected thread issues 2 x 15 tcgen05.mma (M128 N96 K32, 8-bit -> s32)
+//               per stage into 5 TMEM accumulators (480 of 512 columns), tcgen05.commit frees the smem slot;
+//   warps 2-5   epilogue: tcgen05.ld the 5 diagonals, Horner-combine them in f64, apply the row scales and the layer's
 //               epilogue functor (bias + sigmoid, sigmoid', store ...), coalesced column-major stores.
-// The slices are produced by ozaki.cu's slicing kernels (HBM-bound: 8 B in, 6 B out per element).
+// Measured limiter (profiles/): the tensor core's operand fetch from shared memory (SS-mode MMA reads the 128-row A
+// tile for every instruction), not L2 or HBM -- hence the widest N tile TMEM allows and the fewest digit planes.
+// The planes are produced by ozaki.cu's slicing kernels (HBM-bound: 8 B in, 5 B out per element).
 #pragma once
 #include <cuda.h>
 
@@ -25,9 +27,11 @@
 
 namespace rcn {
 
-constexpr int OZ_S = 6;            // slices per operand
-constexpr int OZ_D = 5;            // highest diagonal kept (i + j <= OZ_D)
-constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 64, OZ_STAGES = 3;
+constexpr int OZ_S = 5;            // digit planes per operand
+constexpr int OZ_D = 4;            // highest diagonal kept (i + j <= OZ_D)
+constexpr int OZ_BM = 128, OZ_BN = 96, OZ_BK = 64, OZ_STAGES = 3;
+constexpr int OZ_MAX_K = 16384;    // exact int32 accumulation bound (see above)
+constexpr int OZ_PAIRS = 15;       // digit-plane products per f64 product: |{(i,j): i+j <= OZ_D}|
 constexpr int OZ_A_TILE = OZ_BM * OZ_BK;       // bytes of one A slice tile
 constexpr int OZ_B_TILE = OZ_BN * OZ_BK;
 constexpr int OZ_STAGE_BYTES = OZ_S * (OZ_A_TILE + OZ_B_TILE);
@@ -121,7 +125,7 @@ __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t smem_addr) {
     return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::i8: D = s32, A = B = signed int8, both K-major,
-// N = 64, M = 128, dense, no saturation.
+// N = 96, M = 128, dense, no saturation.
 constexpr uint32_t kInstrDescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
 
 __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
         oz::tc_fence_after();
         const double sa = (m < M) ? scale_a[m] : 0.0;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        constexpr double kW = 1.0 / 128.0;   // 2^-7 between neighbouring diagonals
+        constexpr double kW = 1.0 / 256.0;   // 2^-8 between neighbouring diagonals
 #pragma unroll 1
         for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
             double acc[16];
@@ -296,7 +300,7 @@ template <typename Epi>
 static int launch_gemm_ozaki(const char* name, const OzOperand& A, const OzOperand& B, int M, int N, int K, const Epi& epi,
                              OzakiWorkspace& ws, cudaStream_t stream) {
     if (M <= 0 || N <= 0) return RCN_OK;
-    if (K > 65536) return fail(RCN_ERR_INVALID, "tcgen05 integer-slice GEMM supports K <= 65536 (exact int32 accumulation)");
+    if (K > OZ_MAX_K) return fail(RCN_ERR_INVALID, "tcgen05 integer-slice GEMM supports K <= %d (exact int32 accumulation)", OZ_MAX_K);
     const int Kp = ((K + OZ_BK - 1) / OZ_BK) * OZ_BK;
     RCN_TRY(ws.a_slices.reserve((size_t)OZ_S * M * Kp));
     RCN_TRY(ws.b_slices.reserve((size_t)OZ_S * N * Kp));

@@ -55,5 +55,5 @@ _lib.profile_enable(False)
 out["tc_kernels_ms"] = {k: v["total_ms"] / v["launches"] for k, v in prof.items()}
 mma = [v for k, v in out["tc_kernels_ms"].items() if "ext_gemm" in k]
 if mma:
-    out["tc_mma_kernel_int8_tops"] = 21 * flops / mma[0] / 1e9
+    out["tc_mma_kernel_int8_tops"] = 15 * flops / mma[0] / 1e9
 print(json.dumps(out))
