@@ -399,6 +399,18 @@ def run_gpu(args, wl, rank, world, local_rank):
     h2d = B * H * W + B * 8
     d2h = 16
 
+    # ---- per-kernel durations (CUDA events on the launching stream) for the roofline; separate eager pass that EVERY
+    # rank runs (the exchange kernel / all-reduce needs all of them); rank 0 reports its own records ------------------
+    prof_steps = min(args.steps, 50)
+    barrier()
+    _lib.profile_enable(True)
+    for i in range(prof_steps):
+        trainer.step_images(images[i % n_batches], labels)
+    torch.cuda.synchronize()
+    prof = _lib.profile_report()
+    _lib.profile_enable(False)
+    barrier()
+
     # every collective is done: tear the process group down on ALL ranks together, then rank 0 alone continues with
     # the single-GPU profiling pass and the CPU baseline (nothing below uses torch.distributed)
     if world > 1:
@@ -418,16 +430,7 @@ def run_gpu(args, wl, rank, world, local_rank):
     if rank != 0:
         return
 
-    print("[bench] rank 0: collective phases done, profiling pass", file=sys.stderr, flush=True)
-    # ---- per-kernel durations (CUDA events on the launching stream) for the roofline; separate pass ---------------
-    prof_steps = min(args.steps, 50)
-    _lib.profile_enable(True)
-    for i in range(prof_steps):
-        model.accumulate_gradients_images(images[i % n_batches], labels)
-        model.apply_gradients(ETA, B * world)
-    torch.cuda.synchronize()
-    prof = _lib.profile_report()
-    _lib.profile_enable(False)
+    print("[bench] rank 0: collective phases done", file=sys.stderr, flush=True)
     pk = peaks()
     fwd, bwd_d, bwd_w = dense_flops_per_image(shapes)
     sum_rows = sum(r for r, _ in shapes)

@@ -7,7 +7,7 @@ fn main() {
     let csrc = root.join("mercer_research_b200").join("csrc");
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
-    let sources = ["model.cu", "features.cu", "dense.cu", "smallnet.cu"];
+    let sources = ["model.cu", "features.cu", "dense.cu", "smallnet.cu", "conv.cu", "extops.cu", "dp.cu", "ozaki.cu"];
     let mut objs = Vec::new();
     for s in sources {
         let obj = out.join(s.replace(".cu", ".o"));

@@ -44,6 +44,42 @@ extern "C" {
                                 B: usize, eta: c_double) -> c_int;
     pub fn rcn_cuda_train_batch_images(h: rcn_cuda_handle, images: *const c_void, pixel_format: c_int, labels: *const i64,
                                        B: usize, H: usize, W: usize, eta: c_double) -> c_int;
+    // ---- epoch loop over a host dataset, data-parallel group, checkpoint shapes -----------------------------------
+    pub fn rcn_cuda_train_epoch_host(h: rcn_cuda_handle, images: *const c_void, pixel_format: c_int, labels: *const i64,
+                                     n_samples: usize, H: usize, W: usize, B: usize, eta: c_double, global_batch: usize,
+                                     cost_out: *mut c_double, hits_out: *mut u64, n_steps_out: *mut usize) -> c_int;
+    pub fn rcn_cuda_dp_init(h: rcn_cuda_handle, world: c_int, rank: c_int, ipc_handle_out: *mut c_void) -> c_int;
+    pub fn rcn_cuda_dp_connect_ipc(h: rcn_cuda_handle, all_handles: *const c_void) -> c_int;
+    pub fn rcn_cuda_dp_connect_local(h: rcn_cuda_handle, group: *const rcn_cuda_handle) -> c_int;
+    pub fn rcn_cuda_dp_shutdown(h: rcn_cuda_handle) -> c_int;
+    pub fn rcn_cuda_init_params_shapes(h: rcn_cuda_handle, rows: *const usize, cols: *const usize, n_layers: usize) -> c_int;
+    pub fn rcn_cuda_accumulate_gradients_images(h: rcn_cuda_handle, images: *const c_void, pixel_format: c_int,
+                                                labels: *const i64, B: usize, H: usize, W: usize) -> c_int;
+    pub fn rcn_cuda_apply_gradients(h: rcn_cuda_handle, eta: c_double, batch: usize) -> c_int;
+    pub fn rcn_cuda_last_batch_stats(h: rcn_cuda_handle, cost: *mut c_double, hits: *mut u64) -> c_int;
+    // ---- extensions (not in the reference): learned conv, NHWC pooling, softmax cross-entropy, GEMM block ----------
+    pub fn rcn_cuda_ext_conv2d_forward(device: c_int, stream: *mut c_void, x: *const c_double, B: usize, H: usize, W: usize,
+                                       Ci: usize, w: *const c_double, bias: *const c_double, Co: usize, kh: usize, kw: usize,
+                                       padding: c_int, activation: c_int, y: *mut c_double) -> c_int;
+    pub fn rcn_cuda_ext_activation_backward(device: c_int, stream: *mut c_void, y: *const c_double, dy: *const c_double,
+                                            n: usize, activation: c_int, dz: *mut c_double) -> c_int;
+    pub fn rcn_cuda_ext_conv2d_backward_data(device: c_int, stream: *mut c_void, dz: *const c_double, B: usize, H: usize,
+                                             W: usize, Ci: usize, w: *const c_double, Co: usize, kh: usize, kw: usize,
+                                             padding: c_int, y_prev: *const c_double, activation_prev: c_int,
+                                             dx: *mut c_double) -> c_int;
+    pub fn rcn_cuda_ext_conv2d_backward_weight(device: c_int, stream: *mut c_void, x: *const c_double, dz: *const c_double,
+                                               B: usize, H: usize, W: usize, Ci: usize, Co: usize, kh: usize, kw: usize,
+                                               padding: c_int, dw: *mut c_double, db: *mut c_double) -> c_int;
+    pub fn rcn_cuda_ext_pool2d_forward(device: c_int, stream: *mut c_void, x: *const c_double, B: usize, H: usize, W: usize,
+                                       C: usize, padding: c_int, pooling: c_int, y: *mut c_double, argmax_out: *mut u8) -> c_int;
+    pub fn rcn_cuda_ext_pool2d_backward(device: c_int, stream: *mut c_void, dy: *const c_double, argmax: *const u8, B: usize,
+                                        H: usize, W: usize, C: usize, padding: c_int, pooling: c_int, dx: *mut c_double) -> c_int;
+    pub fn rcn_cuda_ext_softmax_xent(device: c_int, stream: *mut c_void, z: *const c_double, n: usize, B: usize,
+                                     onehot: *const c_double, labels: *const i64, probs: *mut c_double, loss: *mut c_double,
+                                     delta: *mut c_double) -> c_int;
+    pub fn rcn_cuda_ext_gemm_f64(device: c_int, stream: *mut c_void, A: *const c_double, lda: usize, a_kcontig: c_int,
+                                 B: *const c_double, ldb: usize, b_kcontig: c_int, M: usize, N: usize, K: usize, impl_: c_int,
+                                 C: *mut c_double) -> c_int;
     pub fn rcn_cuda_convolve_2d(device: c_int, stream: *mut c_void, m: *const c_double, H: usize, W: usize,
                                 kernel: *const c_double, kh: usize, kw: usize, padding: c_int, out: *mut c_double) -> c_int;
     pub fn rcn_cuda_convolve_2d_separated(device: c_int, stream: *mut c_void, m: *const c_double, H: usize, W: usize,
