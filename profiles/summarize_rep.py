@@ -17,7 +17,10 @@ M = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", 
      "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
      "launch__block_size", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
      "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
-     "smsp__warp_issue_stalled_barrier_per_warp_active.pct", "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct"]
+     "smsp__warp_issue_stalled_barrier_per_warp_active.pct", "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct",
+     "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+     "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]
 NAMES = {"smallnet_fwd_bwd_kernel<1>": "smallnet_fwd_bwd_kernel(fused features)", "smallnet_fwd_bwd_kernel<0>": "smallnet_fwd_bwd_kernel"}
 
 
@@ -37,6 +40,10 @@ def main(rep, workload, out_txt):
         name = re.sub(r"\(.*", "", name)
         rec = agg.setdefault(name, collections.defaultdict(list))
         for m in M:
+            if m not in col:
+                cands = [h for h in hdr if h.endswith(m)]
+                if cands:
+                    col[m] = col[cands[0]]
             if m in col and r[col[m]] not in ("", "n/a"):
                 v = r[col[m]]
                 rec[m].append(to_bytes(v, units[col[m]]) if "bytes" in m else float(v.replace(",", "")))
