@@ -537,8 +537,8 @@ def run_gpu(args, wl, rank, world, local_rank):
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps, "host_buffers": "pinned",
-                "api": "rcn_cuda_train_epoch_host (chunks_exact loop over a host dataset; H2D of step k+1 overlaps step k; "
-                       "per-step cost/hits read back)"},
+                "api": "rcn_cuda_train_epoch_host (chunks_exact loop over a pinned host dataset: the GPU pulls chunk k+1 over PCIe "
+                       "while chunk k trains, one CUDA graph launch per step, per-step cost/hits written back to host memory)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_ips, "unit": "images/s", "cores": cores, "kind": "port",

@@ -155,10 +155,12 @@ int rcn_cuda_epoch_apply(rcn_cuda_handle h, double eta, size_t global_batch);
 int rcn_cuda_epoch_step(rcn_cuda_handle h, double eta); /* accumulate + apply with global_batch = B */
 
 /* The same loop over a HOST-resident (already shuffled) dataset: `for batch in training_set.chunks_exact(B) {
- * train_batch(batch, eta) }` (rcn.rs:147-149). The host->device copy of chunk k+1 runs on a second stream while the
- * kernels of chunk k execute (double-buffered staging; pin the host buffers for real overlap); every step's result --
- * quadratic cost and rcn.rs:153-157 hit count under the pre-update parameters -- is copied back per step into
- * cost_out / hits_out (n_samples / B entries each, may be NULL). global_batch = 0 means B x (data-parallel world).
+ * train_batch(batch, eta) }` (rcn.rs:147-149). The host->device transfer of chunk k+1 overlaps the kernels of chunk k:
+ * with PINNED u8 images and a narrow network the GPU pulls the next chunk over PCIe itself (zero-copy loads into a
+ * two-slot ring) on a parallel branch of ONE CUDA graph that the host launches once per step, and the step's result is
+ * written straight into pinned host memory; otherwise double-buffered cudaMemcpyAsync on a copy stream. Every step's
+ * result -- quadratic cost and rcn.rs:153-157 hit count under the pre-update parameters -- lands in cost_out / hits_out
+ * (n_samples / B entries each, may be NULL). global_batch = 0 means B x (data-parallel world).
  * In a connected data-parallel group every rank calls this with its own shard of each global minibatch. */
 int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_format, const int64_t* labels,
                               size_t n_samples, size_t H, size_t W, size_t B, double eta, size_t global_batch,

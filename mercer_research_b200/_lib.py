@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "librcn_cuda.so")
+SO_PATH = os.environ.get("RCN_CUDA_LIB") or os.path.join(_HERE, "librcn_cuda.so")   # env override: A/B-testing a build
 
 RCN_OK = 0
 STATUS_NAMES = {

@@ -212,10 +212,16 @@ int launch_dense_backward_weight(const double* delta, const double* A_prev, size
 // SGD step, argmax, batch statistics
 // ------------------------------------------------------------------------------------------------
 __global__ void sgd_update_kernel(double* __restrict__ p, const double* __restrict__ g, size_t n, double scale,
-                                  long long* __restrict__ cursor, long long batch, long long n_samples) {
+                                  long long* __restrict__ cursor, long long batch, long long n_samples,
+                                  const double* __restrict__ stats, double* __restrict__ stats_ring) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         p[i] = p[i] - scale * g[i];  // &lw.0 - (eta / B) * w   (rcn.rs:214,221): product rounded, then subtracted
     if (cursor && blockIdx.x == 0 && threadIdx.x == 0) {
+        if (stats_ring) {   // this step's {cost, hits} straight into the (pinned host) result ring: one 16-byte write
+            double* dst = stats_ring + 2 * (*cursor / batch);
+            dst[0] = stats[0];
+            dst[1] = stats[1];
+        }
         // next chunk of training_set.chunks_exact(batch) (rcn.rs:147); the remainder is dropped, then wrap
         long long c = *cursor + batch;
         if (c + batch > n_samples) c = 0;
@@ -224,12 +230,12 @@ __global__ void sgd_update_kernel(double* __restrict__ p, const double* __restri
 }
 
 int launch_sgd_update(double* params, const double* grads, size_t n, double scale, cudaStream_t stream,
-                      long long* cursor, long long batch, long long n_samples) {
+                      long long* cursor, long long batch, long long n_samples, const double* stats, double* stats_ring) {
     if (n == 0) return RCN_OK;
     unsigned grid = cdiv(n, 256);
     if (grid > kNumSMs * 8) grid = kNumSMs * 8;
     RCN_LAUNCH("sgd_update_kernel", stream,
-               sgd_update_kernel<<<grid, 256, 0, stream>>>(params, grads, n, scale, cursor, batch, n_samples));
+               sgd_update_kernel<<<grid, 256, 0, stream>>>(params, grads, n, scale, cursor, batch, n_samples, stats, stats_ring));
     return RCN_OK;
 }
 

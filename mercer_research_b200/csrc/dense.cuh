@@ -36,8 +36,11 @@ int launch_bias_grad(const double* delta, size_t M, size_t N, double* db, cudaSt
 
 // params -= scale * grads   (rcn.rs:210-222, scale = eta / batch formed first)
 // cursor (optional): device-side position of the epoch walk, advanced by `batch` with chunks_exact wrap-around.
+// stats / stats_ring (optional, with cursor): the step's {cost, hits} pair is copied to stats_ring + 2 * (cursor / batch)
+// (pinned host memory in rcn_cuda_train_epoch_host) before the cursor advances.
 int launch_sgd_update(double* params, const double* grads, size_t n, double scale, cudaStream_t stream,
-                      long long* cursor = nullptr, long long batch = 0, long long n_samples = 0);
+                      long long* cursor = nullptr, long long batch = 0, long long n_samples = 0, const double* stats = nullptr,
+                      double* stats_ring = nullptr);
 
 // labels[b] = argmax_i acts[i, b], last maximal element wins (rcn.rs:92-97)
 int launch_argmax_last(const double* acts, size_t n, size_t B, int64_t* labels, cudaStream_t stream);

@@ -73,7 +73,8 @@ template <int WORLD>   // 0 = runtime world size
 __global__ void __launch_bounds__(256) dp_allreduce_sgd_kernel(const DpPeers peers, int world_rt, int rank, size_t n,
                                                                double* __restrict__ params, double* __restrict__ grads,
                                                                double scale, long long* __restrict__ cursor, long long batch,
-                                                               long long n_samples) {
+                                                               long long n_samples, const double* __restrict__ stats,
+                                                               double* __restrict__ stats_ring) {
     const int world = WORLD ? WORLD : world_rt;
     char* self = peers.p[rank];
     DpCtrl* ctrl = reinterpret_cast<DpCtrl*>(self);
@@ -130,6 +131,11 @@ __global__ void __launch_bounds__(256) dp_allreduce_sgd_kernel(const DpPeers pee
             ctrl->done_ctas = 0;
             *reinterpret_cast<volatile long long*>(&ctrl->step) = step;
             if (cursor) {
+                if (stats_ring) {
+                    double* dst = stats_ring + 2 * (*cursor / batch);
+                    dst[0] = stats[0];
+                    dst[1] = stats[1];
+                }
                 long long cc = *cursor + batch;
                 if (cc + batch > n_samples) cc = 0;
                 *cursor = cc;
@@ -140,7 +146,7 @@ __global__ void __launch_bounds__(256) dp_allreduce_sgd_kernel(const DpPeers pee
 }
 
 int launch_dp_allreduce_sgd(const DpState& st, double* params, double* grads, double scale, cudaStream_t stream,
-                            long long* cursor, long long batch, long long n_samples) {
+                            long long* cursor, long long batch, long long n_samples, const double* stats, double* stats_ring) {
     if (!st.connected) return fail(RCN_ERR_STATE, "data-parallel group is not connected");
     if (st.n == 0) return RCN_OK;
     DpPeers pp{};
@@ -149,7 +155,7 @@ int launch_dp_allreduce_sgd(const DpState& st, double* params, double* grads, do
 #define RCN_DP_LAUNCH(W)                                                                                                       \
     RCN_LAUNCH("dp_allreduce_sgd_kernel", stream,                                                                              \
                dp_allreduce_sgd_kernel<W><<<grid, 256, 0, stream>>>(pp, st.world, st.rank, st.n, params, grads, scale, cursor, \
-                                                                   batch, n_samples))
+                                                                   batch, n_samples, stats, stats_ring))
     switch (st.world) {
         case 2: RCN_DP_LAUNCH(2); break;
         case 4: RCN_DP_LAUNCH(4); break;

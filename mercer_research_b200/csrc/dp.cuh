@@ -25,6 +25,7 @@ void dp_release(DpState& st);
 // params[i] -= scale * sum_r grads_r[i], r ascending, identical on every rank; grads[i] <- the global sum.
 // cursor / batch / n_samples: optional epoch cursor advanced like sgd_update_kernel does.
 int launch_dp_allreduce_sgd(const DpState& st, double* params, double* grads, double scale, cudaStream_t stream,
-                            long long* cursor, long long batch, long long n_samples);
+                            long long* cursor, long long batch, long long n_samples, const double* stats = nullptr,
+                            double* stats_ring = nullptr);
 
 }  // namespace rcn

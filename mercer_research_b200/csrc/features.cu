@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) features_fused_kernel(const TIN* __restri
     for (int img = blockIdx.x; img < B; img += gridDim.x) {
         const size_t src = source_image(bi, (size_t)img);
         if (tid == 0 && bi.labels_batch) bi.labels_batch[img] = bi.labels_all[src];
-        load_image<TIN, T>(images + src * H * W, buf0, H, W, tid, nt);
+        load_image<TIN, T>(images + image_slot(bi, src) * H * W, buf0, H, W, tid, nt);
         __syncthreads();
         T* cur = buf0;
         T* nxt = buf1;
@@ -119,7 +119,7 @@ __global__ void convert_images_kernel(const TIN* __restrict__ images, T* __restr
     for (size_t img = blockIdx.y; img < B; img += gridDim.y) {
         const size_t src = source_image(bi, img);
         if (blockIdx.x == 0 && threadIdx.x == 0 && bi.labels_batch) bi.labels_batch[img] = bi.labels_all[src];
-        load_image<TIN, T>(images + src * H * W, out + img * H * W, H, W, blockIdx.x * blockDim.x + threadIdx.x,
+        load_image<TIN, T>(images + image_slot(bi, src) * H * W, out + img * H * W, H, W, blockIdx.x * blockDim.x + threadIdx.x,
                            gridDim.x * blockDim.x);
     }
 }

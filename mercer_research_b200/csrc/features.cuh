@@ -53,6 +53,9 @@ struct BatchIndex {
     const long long* perm = nullptr;
     const long long* labels_all = nullptr;
     long long* labels_batch = nullptr;
+    // Streaming from a HOST dataset (rcn_cuda_train_epoch_host): `images` is a ring of `window` image slots and image
+    // i of the walk lives in slot i % window (labels are still indexed by i).  0 = images hold the whole dataset.
+    long long window = 0;
 };
 
 // Epilogue descriptor for a batch: picks the host-verified exact fast division when the input is u8.

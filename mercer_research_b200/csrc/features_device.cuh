@@ -221,6 +221,10 @@ __device__ __forceinline__ size_t source_image(const BatchIndex& bi, size_t img)
     const long long pos = *bi.cursor + (long long)img;
     return (size_t)(bi.perm ? bi.perm[pos] : pos);
 }
+// where that image's pixels live: the dataset itself, or a ring of `window` slots when streaming from the host
+__device__ __forceinline__ size_t image_slot(const BatchIndex& bi, size_t src) {
+    return bi.window ? (size_t)((unsigned)src % (unsigned)bi.window) : src;   // 32-bit: a streamed epoch has < 2^32 samples
+}
 
 
 }  // namespace rcn

@@ -60,6 +60,30 @@ LaunchScope::~LaunchScope() {
     if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].stop, stream);
 }
 
+// ---- streaming from a pinned HOST dataset (rcn_cuda_train_epoch_host fast path) ---------------------------------------
+// State block in device memory: [0] cursor (samples, advanced by the update kernel), [1] n_steps, [2] host image base.
+// The prefetch kernel reads chunk k+1 = cursor/B + 1 straight from pinned host memory (zero-copy loads over PCIe, 16 B
+// per thread, coalesced) into ring slot (k+1) % 2 while the training kernels of chunk k run on the other graph branch.
+__global__ void __launch_bounds__(256) host_prefetch_kernel(const long long* __restrict__ state, unsigned char* __restrict__ ring,
+                                                            long long B, long long img_bytes) {
+    const long long k1 = state[0] / B + 1;
+    if (k1 >= state[1]) return;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(state[2]) + k1 * B * img_bytes;
+    unsigned char* dst = ring + ((k1 * B) % (2 * B)) * img_bytes;
+    const long long n16 = B * img_bytes / 16;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
+        d4[i] = s4[i];
+}
+
+bool is_pinned_host_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost && a.devicePointer != nullptr;
+}
+
+
 }  // namespace rcn
 
 using namespace rcn;
@@ -108,6 +132,21 @@ struct rcn_cuda_model {
     DevBuf host_slot[2];
     double* stats_host = nullptr;   // pinned, 2 doubles per step
     size_t stats_host_cap = 0;
+    // streaming variant: the GPU pulls chunk k+1 from pinned host memory while it trains on chunk k; one graph per step
+    DevBuf hs_ring, hs_state;
+    cudaGraphExec_t hs_graph = nullptr;
+    cudaEvent_t hs_fork = nullptr, hs_join = nullptr;
+    struct HsKey {
+        size_t B = 0, H = 0, W = 0, n_steps = 0;
+        double scale = 0.0;
+        const void *labels = nullptr, *stats = nullptr, *ring = nullptr, *state = nullptr, *grads = nullptr;
+        cudaStream_t stream = nullptr;
+        bool dp = false;
+        bool operator==(const HsKey& o) const {
+            return B == o.B && H == o.H && W == o.W && n_steps == o.n_steps && scale == o.scale && labels == o.labels &&
+                   stats == o.stats && ring == o.ring && state == o.state && grads == o.grads && stream == o.stream && dp == o.dp;
+        }
+    } hs_key;
 
     double* act(size_t l, size_t B) const {
         size_t off = 0;
@@ -334,6 +373,10 @@ int rcn_cuda_destroy(rcn_cuda_handle h) {
         h->host_slot[i].release();
     }
     if (h->stats_host) cudaFreeHost(h->stats_host);
+    if (h->hs_graph) cudaGraphExecDestroy(h->hs_graph);
+    if (h->hs_fork) cudaEventDestroy(h->hs_fork);
+    if (h->hs_join) cudaEventDestroy(h->hs_join);
+    h->hs_ring.release(); h->hs_state.release();
     dp_release(h->dp);
     h->oz.release();
     DevBuf* bufs[] = {&h->params, &h->grads_own, &h->in_stage, &h->tgt_stage, &h->feats, &h->acts, &h->deltas,
@@ -810,18 +853,111 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
             RCN_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
             RCN_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming));
         }
+        RCN_CUDA_TRY(cudaEventCreateWithFlags(&h->hs_fork, cudaEventDisableTiming));
+        RCN_CUDA_TRY(cudaEventCreateWithFlags(&h->hs_join, cudaEventDisableTiming));
     }
-    for (int i = 0; i < 2; ++i) RCN_TRY(h->host_slot[i].reserve(img_bytes));
-    // the labels of the whole epoch go up in ONE copy (one driver call per step less); images stream chunk by chunk
-    RCN_TRY(h->tgt_stage.reserve(n_steps * B * sizeof(int64_t)));
-    RCN_CUDA_TRY(cudaMemcpyAsync(h->tgt_stage.p, labels, n_steps * B * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-    const int64_t* labels_dev = h->tgt_stage.as<int64_t>();
     if (h->stats_host_cap < n_steps) {
         if (h->stats_host) cudaFreeHost(h->stats_host);
         h->stats_host = nullptr; h->stats_host_cap = 0;
         RCN_CUDA_TRY(cudaHostAlloc((void**)&h->stats_host, n_steps * 2 * sizeof(double), cudaHostAllocDefault));
         h->stats_host_cap = n_steps;
     }
+    // ---- streaming fast path: pinned u8 dataset + fused small-network kernels: the GPU pulls chunk k+1 over PCIe itself
+    // (zero-copy loads) while chunk k trains; per-step results are written straight into pinned host memory; the host
+    // launches ONE CUDA graph per step and nothing else.
+    static const bool stream_env = []() { const char* e = getenv("RCN_CUDA_HOST_STREAMING"); return !(e && e[0] == '0'); }();
+    if (stream_env && pixel_format == RCN_PIXELS_U8_ROWMAJOR && h->use_small && B <= smallnet_max_batch() && img_bytes % 16 == 0 &&
+        (reinterpret_cast<uintptr_t>(images) & 15) == 0 && is_pinned_host_ptr(images) && h->plan.L > 0 && h->plan.n_conv <= 10) {
+        SmallNetFront probe{};
+        probe.H = (int)H; probe.W = (int)W; probe.max_elems = (int)h->plan.max_elems; probe.stages = h->plan.stages;
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        RCN_CUDA_TRY(cudaStreamIsCapturing(h->stream, &cs));
+        if (smallnet_front_fits(h->small_desc, probe) && cs == cudaStreamCaptureStatusNone) {
+            // The legacy default stream cannot be captured: run the loop on the model's own stream, ordered after whatever
+            // the caller has enqueued on the legacy stream; the call drains that stream before it returns.
+            struct StreamSwap {
+                rcn_cuda_model* m; cudaStream_t saved;
+                StreamSwap(rcn_cuda_model* m_) : m(m_), saved(m_->stream) {}
+                ~StreamSwap() { m->stream = saved; }
+            } swap_guard(h);
+            if (h->stream == nullptr) {
+                RCN_CUDA_TRY(cudaEventRecord(h->hs_fork, nullptr));
+                RCN_CUDA_TRY(cudaStreamWaitEvent(h->own_stream, h->hs_fork, 0));
+                h->stream = h->own_stream;
+            }
+            RCN_TRY(h->hs_ring.reserve(2 * img_bytes));
+            RCN_TRY(h->hs_state.reserve((4 + B) * sizeof(long long)));
+            RCN_TRY(h->tgt_stage.reserve(n_steps * B * sizeof(int64_t)));
+            RCN_TRY(h->feats.reserve(h->plan.L * B * sizeof(double)));
+            const double scale_s = eta / (double)global_batch;
+            long long* st = h->hs_state.as<long long>();
+            BatchIndex bi;
+            bi.cursor = st;
+            bi.labels_all = h->tgt_stage.as<long long>();
+            bi.labels_batch = st + 4;
+            bi.window = (long long)(2 * B);
+            // state, labels of the whole epoch and chunk 0 go up with plain copies; everything after that is graph replays
+            const long long init[4] = {0, (long long)n_steps, (long long)reinterpret_cast<uintptr_t>(images), 0};
+            RCN_CUDA_TRY(cudaMemcpyAsync(st, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+            RCN_CUDA_TRY(cudaMemcpyAsync(h->tgt_stage.p, labels, n_steps * B * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+            RCN_CUDA_TRY(cudaMemcpyAsync(h->hs_ring.p, images, img_bytes, cudaMemcpyHostToDevice, h->stream));
+            rcn_cuda_model::HsKey key;
+            key.B = B; key.H = H; key.W = W; key.n_steps = n_steps; key.scale = scale_s; key.labels = h->tgt_stage.p;
+            key.stats = h->stats_host; key.ring = h->hs_ring.p; key.state = st; key.grads = h->grads; key.stream = h->stream;
+            key.dp = h->dp.connected;
+            if (!h->hs_graph || !(key == h->hs_key)) {
+                if (h->hs_graph) { cudaGraphExecDestroy(h->hs_graph); h->hs_graph = nullptr; }
+                // warm-up outside capture: reserves every scratch buffer and sets kernel attributes (no parameter update)
+                RCN_TRY(accumulate_images_dev(h, h->hs_ring.p, pixel_format, nullptr, B, H, W, &bi));
+                RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+                cudaGraph_t graph = nullptr;
+                RCN_CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+                int rc = RCN_OK;
+                do {
+                    if (cudaEventRecord(h->hs_fork, h->stream) != cudaSuccess || cudaStreamWaitEvent(h->copy_stream, h->hs_fork, 0) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph fork failed"); break; }
+                    {
+                        LaunchScope ls("host_prefetch_kernel", h->copy_stream);
+                        host_prefetch_kernel<<<32, 256, 0, h->copy_stream>>>(st, h->hs_ring.as<unsigned char>(), (long long)B, (long long)(H * W));
+                    }
+                    if (cudaPeekAtLastError() != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "prefetch kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+                    if (cudaEventRecord(h->hs_join, h->copy_stream) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph join failed"); break; }
+                    rc = accumulate_images_dev(h, h->hs_ring.p, pixel_format, nullptr, B, H, W, &bi);
+                    if (rc != RCN_OK) break;
+                    if (cudaStreamWaitEvent(h->stream, h->hs_join, 0) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph join failed"); break; }
+                    if (h->dp.connected)
+                        rc = launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale_s, h->stream, st, (long long)B,
+                                                     (long long)(n_steps * B), h->small.as<double>(), h->stats_host);
+                    else
+                        rc = launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale_s, h->stream, st, (long long)B,
+                                               (long long)(n_steps * B), h->small.as<double>(), h->stats_host);
+                } while (0);
+                cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+                if (rc != RCN_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+                if (ce != cudaSuccess || !graph) return fail(RCN_ERR_CUDA, "stream capture of the training step failed: %s", cudaGetErrorString(ce));
+                ce = cudaGraphInstantiate(&h->hs_graph, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) { h->hs_graph = nullptr; return fail(RCN_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
+                h->hs_key = key;
+            }
+            for (size_t k = 0; k < n_steps; ++k) RCN_CUDA_TRY(cudaGraphLaunch(h->hs_graph, h->stream));
+            g_launches.fetch_add((unsigned long long)n_steps * 4, std::memory_order_relaxed);   // prefetch + A + B + update per replay
+            RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+            for (size_t k = 0; k < n_steps; ++k) {
+                if (cost_out) cost_out[k] = h->stats_host[2 * k];
+                if (hits_out) memcpy(&hits_out[k], &h->stats_host[2 * k + 1], sizeof(uint64_t));
+            }
+            h->stats_valid = true;
+            h->last_B = B;
+            if (n_steps_out) *n_steps_out = n_steps;
+            return RCN_OK;
+        }
+    }
+    // ---- general path: double-buffered cudaMemcpyAsync on the copy stream -----------------------------------------------
+    for (int i = 0; i < 2; ++i) RCN_TRY(h->host_slot[i].reserve(img_bytes));
+    // the labels of the whole epoch go up in ONE copy (one driver call per step less); images stream chunk by chunk
+    RCN_TRY(h->tgt_stage.reserve(n_steps * B * sizeof(int64_t)));
+    RCN_CUDA_TRY(cudaMemcpyAsync(h->tgt_stage.p, labels, n_steps * B * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    const int64_t* labels_dev = h->tgt_stage.as<int64_t>();
     // everything the previous user of the staging slots enqueued on the compute stream must be finished first
     RCN_CUDA_TRY(cudaEventRecord(h->ev_consumed[0], h->stream));
     RCN_CUDA_TRY(cudaEventRecord(h->ev_consumed[1], h->stream));

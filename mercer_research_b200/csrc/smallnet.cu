@@ -111,7 +111,7 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
                 s_label[n_img] = lab;
                 if (fr.bi.labels_batch) fr.bi.labels_batch[sample] = lab;
             }
-            load_image<uint8_t, int>(fr.images + src * fr.H * fr.W, buf0, fr.H, fr.W, lt, 64);
+            load_image<uint8_t, int>(fr.images + image_slot(fr.bi, src) * fr.H * fr.W, buf0, fr.H, fr.W, lt, 64);
         } else {
             for (int i = lt; i < pitch; i += 64) trow[i] = 0.0;
             if (lt == 0) s_label[n_img] = -1;

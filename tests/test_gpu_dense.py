@@ -328,7 +328,10 @@ def test_train_epoch_host_equals_step_by_step(api):
     cfg = [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max)]
     params = None
     results = []
-    for mode in ("loop", "epoch"):
+    import torch
+    pinned = torch.from_numpy(images).pin_memory()       # pinned host memory takes the streaming (zero-copy prefetch) path
+    pinned_labels = torch.from_numpy(labels).pin_memory()
+    for mode in ("loop", "epoch", "epoch-pinned", "epoch-pinned-again"):
         model = api.RCN(10, cfg, [30])
         model.load_weights_and_bias(784)
         if params is None:
@@ -341,12 +344,19 @@ def test_train_epoch_host_equals_step_by_step(api):
                 model.train_batch_images(images[k * B:(k + 1) * B], labels[k * B:(k + 1) * B], 3.0)
                 stats.append(model.last_batch_stats())
             cost = np.array([s[0] for s in stats]); hits = np.array([s[1] for s in stats], dtype=np.uint64)
-        else:
+        elif mode == "epoch":
             cost, hits = model.train_epoch_host(images, labels, B, 3.0)
             assert len(cost) == N // B
+        else:
+            if mode.endswith("again"):                   # second epoch on the same handle replays the cached graph
+                model.train_epoch_host(pinned.numpy(), pinned_labels.numpy(), B, 3.0)
+                model.set_params(params)
+            cost, hits = model.train_epoch_host(pinned.numpy(), pinned_labels.numpy(), B, 3.0)
+            assert len(cost) == N // B
         results.append((model.get_params(), cost, hits))
-    assert np.array_equal(results[0][0], results[1][0]), "same kernels, same order: parameters must be bit-identical"
-    assert np.array_equal(results[0][1], results[1][1]) and np.array_equal(results[0][2], results[1][2])
+    for other in results[1:]:
+        assert np.array_equal(results[0][0], other[0]), "same kernels, same order: parameters must be bit-identical"
+        assert np.array_equal(results[0][1], other[1]) and np.array_equal(results[0][2], other[2])
 
 
 def test_dp_peer_memory_exchange_two_gpus(api):
