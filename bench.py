@@ -438,7 +438,8 @@ def run_gpu(args, wl, rank, world, local_rank):
     int8_peak = 2.0 * (pk["bf16_tflops"] or 1590.0)   # kind::i8 issues at twice the bf16 rate; bf16 is the measured figure
 
     def on_tc(M, N, K):                               # mirrors use_tensor_cores() in csrc/dense.cu
-        return M >= 256 and N >= 256 and K >= 512 and float(M) * N * K >= 8.0e9
+        tiles = -(-M // 128) * -(-N // 96)
+        return M >= 256 and N >= 256 and K >= 512 and K <= 16384 and tiles >= 74 and float(M) * N * K >= 4.0e9
 
     # algorithmic work per step of each kernel NAME: name -> [bound, bytes, flops]; the per-launch
     # figure is this divided by the launches per step the profiler counted

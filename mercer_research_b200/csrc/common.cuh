@@ -111,6 +111,22 @@ struct SmemAttrCache {
     }
 };
 
+// Scratch of the deterministic two-stage reductions (bias gradient, batch statistics): every CTA leaves a partial, the
+// last CTA to arrive (ticket counter, self-resetting) adds the partials in index order.
+struct ReduceScratch {
+    static constexpr size_t kTicketBytes = 4096;   // 1024 u32 tickets, zeroed when the buffer is (re)allocated
+    DevBuf buf;
+    int ensure(size_t partial_bytes, cudaStream_t s) {
+        const size_t want = kTicketBytes + partial_bytes;
+        if (want <= buf.cap) return RCN_OK;
+        RCN_TRY(buf.reserve(want));
+        RCN_CUDA_TRY(cudaMemsetAsync(buf.p, 0, kTicketBytes, s));
+        return RCN_OK;
+    }
+    unsigned* tickets() const { return buf.as<unsigned>(); }
+    double* partials() const { return reinterpret_cast<double*>(buf.as<char>() + kTicketBytes); }
+};
+
 constexpr int kNumSMs = 148;  // B200
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }

@@ -340,7 +340,12 @@ int launch_conv2d_backward_weight(const double* x, const double* dz, const ConvS
         RCN_TRY(launch_gemm_tiles("conv2d_backward_weight_igemm", la, lb, M, N, Kc, splits, kps, epi, stream));
         RCN_TRY(launch_reduce_splits(ws.as<double>(), splits, (size_t)M * N, dw, stream));
     }
-    if (db) RCN_TRY(launch_bias_grad(dz, (size_t)M, (size_t)Kc, db, stream));
+    if (db) {
+        static thread_local ReduceScratch tl_rs[64];   // one per device this thread drives
+        int dev = 0;
+        RCN_CUDA_TRY(cudaGetDevice(&dev));
+        RCN_TRY(launch_bias_grad(dz, (size_t)M, (size_t)Kc, db, tl_rs[dev & 63], stream));
+    }
     return RCN_OK;
 }
 

@@ -37,7 +37,9 @@ static bool use_tensor_cores(size_t M, size_t N, size_t K, OzakiWorkspace* oz) {
     if (!oz || !ozaki_available() || K > (size_t)OZ_MAX_K) return false;
     if (gemm_impl() == GEMM_TC) return M >= 1 && N >= 1 && K >= 1;
     if (gemm_impl() != GEMM_AUTO) return false;
-    return M >= 256 && N >= 256 && K >= 512 && (double)M * (double)N * (double)K >= 8.0e9;
+    // enough 128 x 96 tiles to occupy at least half of the SMs, and enough work per tile to amortise slicing both operands
+    const size_t tiles = ((M + OZ_BM - 1) / OZ_BM) * ((N + OZ_BN - 1) / OZ_BN);
+    return M >= 256 && N >= 256 && K >= 512 && tiles >= (size_t)kNumSMs / 2 && (double)M * (double)N * (double)K >= 4.0e9;
 }
 
 // rcn.rs:478-483: 1/(1+E^-x).  exp(-x) instead of pow(E,-x): E as an f64 is e*(1-5.3e-17), so the two differ
@@ -138,20 +140,50 @@ __global__ void reduce_splits_kernel(const double* __restrict__ part, int splits
     }
 }
 
-// db[m] = sum_n delta[m, n].  One CTA per 32 rows; warp w sums columns w, w+8, ...; fixed-order combine.
-__global__ void __launch_bounds__(256) bias_grad_kernel(const double* __restrict__ delta, int M, int N, double* __restrict__ db) {
+// db[m] = sum_n delta[m, n].  Grid (row blocks of 32, column splits): lane = row, warp = column phase inside the CTA's
+// column range, 4 loads in flight per thread; per-CTA partials meet in the scratch buffer and the last CTA of a row
+// block to arrive adds them in split order (deterministic, no atomics on the data).
+__global__ void __launch_bounds__(256) bias_grad_kernel(const double* __restrict__ delta, int M, int N, int n_per_split,
+                                                        double* __restrict__ db, double* __restrict__ partial,
+                                                        unsigned* __restrict__ tickets) {
     __shared__ double sm[8][33];
+    __shared__ bool s_last;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int m = blockIdx.x * 32 + lane;
+    const int S = gridDim.y;
+    const int n_lo = blockIdx.y * n_per_split, n_hi = min(N, n_lo + n_per_split);
     double acc = 0.0;
-    if (m < M)
-        for (int n = w; n < N; n += 8) acc += delta[(size_t)n * M + m];
+    if (m < M) {
+        for (int n = n_lo + w; n < n_hi; n += 32) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (n + 8 * u < n_hi) ? delta[(size_t)(n + 8 * u) * M + m] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc += v[u];
+        }
+    }
     sm[w][lane] = acc;
     __syncthreads();
-    if (w == 0 && m < M) {
+    if (w == 0) {
         double s = sm[0][lane];
 #pragma unroll
         for (int i = 1; i < 8; ++i) s += sm[i][lane];
+        if (S == 1) { if (m < M) db[m] = s; return; }
+        if (m < M) partial[(size_t)blockIdx.y * M + m] = s;
+    }
+    if (S == 1) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(tickets + blockIdx.x, 1u);
+        s_last = (t == (unsigned)S - 1);
+        if (s_last) tickets[blockIdx.x] = 0;
+    }
+    __syncthreads();
+    if (s_last && w == 0 && m < M) {
+        __threadfence();
+        double s = 0.0;
+        for (int q = 0; q < S; ++q) s += __ldcg(partial + (size_t)q * M + m);
         db[m] = s;
     }
 }
@@ -163,20 +195,34 @@ int launch_reduce_splits(const double* partials, int splits, size_t n, double* o
     return RCN_OK;
 }
 
-int launch_bias_grad(const double* delta, size_t M, size_t N, double* db, cudaStream_t stream) {
-    RCN_LAUNCH("bias_grad_kernel", stream, bias_grad_kernel<<<cdiv(M, 32), 256, 0, stream>>>(delta, (int)M, (int)N, db));
+int launch_bias_grad(const double* delta, size_t M, size_t N, double* db, ReduceScratch& rs, cudaStream_t stream) {
+    if (M == 0) return RCN_OK;
+    const unsigned row_blocks = cdiv(M, 32);
+    if (row_blocks > 1023) return fail(RCN_ERR_INVALID, "layer too wide for the bias-gradient reduction");
+    // enough column splits to cover the machine a few times over, each at least 256 columns deep
+    unsigned S = (4 * kNumSMs + row_blocks - 1) / row_blocks;
+    const unsigned max_s = (unsigned)((N + 255) / 256);
+    if (S > max_s) S = max_s;
+    if (S < 1) S = 1;
+    int n_per_split = (int)((N + S - 1) / S);
+    n_per_split = (n_per_split + 31) / 32 * 32;
+    S = (unsigned)((N + n_per_split - 1) / n_per_split);
+    if (S < 1) S = 1;
+    RCN_TRY(rs.ensure((size_t)S * M * sizeof(double), stream));
+    RCN_LAUNCH("bias_grad_kernel", stream,
+               bias_grad_kernel<<<dim3(row_blocks, S), 256, 0, stream>>>(delta, (int)M, (int)N, n_per_split, db, rs.partials(), rs.tickets()));
     return RCN_OK;
 }
 
 int launch_dense_backward_weight(const double* delta, const double* A_prev, size_t M, size_t N, size_t Kb, double* dW,
-                                 double* db, DevBuf& workspace, cudaStream_t stream, OzakiWorkspace* oz) {
+                                 double* db, DevBuf& workspace, ReduceScratch& rs, cudaStream_t stream, OzakiWorkspace* oz) {
     if (M == 0) return RCN_OK;
     if (N > 0 && use_tensor_cores(M, N, Kb, oz)) {
         // enough output tiles to fill the machine without splitting the batch: one exact pass, deterministic by construction
         EpiStore epi{dW, (int)M, 0};
         RCN_TRY((launch_gemm<false, false, EpiStore>("dense_backward_weight_gemm(tcgen05 int8 slices)", delta, (int)M, A_prev, (int)N, M,
                                                      N, Kb, 1, epi, stream, oz)));
-        return launch_bias_grad(delta, M, Kb, db, stream);
+        return launch_bias_grad(delta, M, Kb, db, rs, stream);
     }
     // Split the batch (K) dimension so the small M x N output still fills the machine; partials are summed in
     // a fixed order (deterministic, unlike the reference's mutex-ordered sum, rcn.rs:190-205).
@@ -205,7 +251,7 @@ int launch_dense_backward_weight(const double* delta, const double* A_prev, size
             RCN_TRY(launch_reduce_splits(workspace.as<double>(), splits, M * N, dW, stream));
         }
     }
-    return launch_bias_grad(delta, M, Kb, db, stream);
+    return launch_bias_grad(delta, M, Kb, db, rs, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -260,16 +306,19 @@ int launch_argmax_last(const double* acts, size_t n, size_t B, int64_t* labels, 
     return RCN_OK;
 }
 
-// Single CTA, fixed summation order => deterministic.  cost = sum_b 0.5*|a-y|^2; hits per rcn.rs:153-157:
-// the set {i : a_i == max a} must equal {label}.
+// cost = sum_b 0.5*|a-y|^2; hits per rcn.rs:153-157: the set {i : a_i == max a} must equal {label}.  One thread per
+// sample, 256 samples per CTA; per-CTA partials are added in CTA order by the last CTA to arrive => deterministic.
 __global__ void __launch_bounds__(256) batch_stats_kernel(const double* __restrict__ acts, int n, size_t B,
                                                          const double* __restrict__ onehot,
-                                                         const int64_t* __restrict__ labels, double* __restrict__ stats) {
+                                                         const int64_t* __restrict__ labels, double* __restrict__ stats,
+                                                         double* __restrict__ partial, unsigned* __restrict__ ticket) {
     __shared__ double sc[256];
     __shared__ unsigned long long sh[256];
+    __shared__ bool s_last;
     double cost = 0.0;
     unsigned long long hits = 0;
-    for (size_t b = threadIdx.x; b < B; b += blockDim.x) {
+    const size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (b < B) {
         const double* a = acts + b * n;
         double mx = a[0];
         for (int i = 1; i < n; ++i) mx = fmax(mx, a[i]);
@@ -282,8 +331,8 @@ __global__ void __launch_bounds__(256) batch_stats_kernel(const double* __restri
             const double r = (a[i] == mx) ? 1.0 : 0.0;
             ok = ok && (r == y);
         }
-        cost += 0.5 * c;
-        hits += ok ? 1ull : 0ull;
+        cost = 0.5 * c;
+        hits = ok ? 1ull : 0ull;
     }
     sc[threadIdx.x] = cost;
     sh[threadIdx.x] = hits;
@@ -292,14 +341,35 @@ __global__ void __launch_bounds__(256) batch_stats_kernel(const double* __restri
         double ct = 0.0;
         unsigned long long ht = 0;
         for (int i = 0; i < 256; ++i) { ct += sc[i]; ht += sh[i]; }
+        partial[2 * blockIdx.x] = ct;
+        reinterpret_cast<unsigned long long*>(partial)[2 * blockIdx.x + 1] = ht;
+        __threadfence();
+        const unsigned t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+        if (s_last) *ticket = 0;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        double ct = 0.0;
+        unsigned long long ht = 0;
+        for (unsigned i = 0; i < gridDim.x; ++i) {
+            ct += __ldcg(partial + 2 * i);
+            ht += __ldcg(reinterpret_cast<const unsigned long long*>(partial) + 2 * i + 1);
+        }
         stats[0] = ct;
         reinterpret_cast<unsigned long long*>(stats)[1] = ht;
     }
 }
 
 int launch_batch_stats(const double* acts, size_t n, size_t B, const double* onehot, const int64_t* labels,
-                       double* stats_dev, cudaStream_t stream) {
-    RCN_LAUNCH("batch_stats_kernel", stream, batch_stats_kernel<<<1, 256, 0, stream>>>(acts, (int)n, B, onehot, labels, stats_dev));
+                       double* stats_dev, ReduceScratch& rs, cudaStream_t stream) {
+    const unsigned grid = B ? cdiv(B, 256) : 1;
+    RCN_TRY(rs.ensure(((size_t)2 * grid + 2048) * sizeof(double), stream));
+    // shares the partial region with bias_grad_kernel (stream-ordered, each consumes its partials before it ends);
+    // ticket 1023 is reserved for this kernel
+    RCN_LAUNCH("batch_stats_kernel", stream,
+               batch_stats_kernel<<<grid, 256, 0, stream>>>(acts, (int)n, B, onehot, labels, stats_dev, rs.partials(), rs.tickets() + 1023));
     return RCN_OK;
 }
 

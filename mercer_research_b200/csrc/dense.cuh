@@ -27,12 +27,12 @@ int launch_dense_backward_data(const double* W_up, const double* delta_up, const
 // dW (M x N) = delta (M x Kb) * A_prev (N x Kb)^T, db (M) = delta * 1                 rcn.rs:302-303,309-310 summed
 // over the batch (rcn.rs:190-205).  workspace: split-K partials.
 int launch_dense_backward_weight(const double* delta, const double* A_prev, size_t M, size_t N, size_t Kb, double* dW,
-                                 double* db, DevBuf& workspace, cudaStream_t stream, OzakiWorkspace* oz = nullptr);
+                                 double* db, DevBuf& workspace, ReduceScratch& rs, cudaStream_t stream, OzakiWorkspace* oz = nullptr);
 
 // out[i] = sum_p partials[p*n + i], p ascending (deterministic split-K combine)
 int launch_reduce_splits(const double* partials, int splits, size_t n, double* out, cudaStream_t stream);
 // db[m] = sum_n delta[m + n*M]  (delta M x N column-major), fixed summation order
-int launch_bias_grad(const double* delta, size_t M, size_t N, double* db, cudaStream_t stream);
+int launch_bias_grad(const double* delta, size_t M, size_t N, double* db, ReduceScratch& rs, cudaStream_t stream);
 
 // params -= scale * grads   (rcn.rs:210-222, scale = eta / batch formed first)
 // cursor (optional): device-side position of the epoch walk, advanced by `batch` with chunks_exact wrap-around.
@@ -47,6 +47,6 @@ int launch_argmax_last(const double* acts, size_t n, size_t B, int64_t* labels, 
 
 // stats[0] = sum_b 0.5*|a_b - y_b|^2 (as double), stats[1] = bit pattern of uint64 hit count (rcn.rs:153-157)
 int launch_batch_stats(const double* acts, size_t n, size_t B, const double* onehot, const int64_t* labels,
-                       double* stats_dev, cudaStream_t stream);
+                       double* stats_dev, ReduceScratch& rs, cudaStream_t stream);
 
 }  // namespace rcn

@@ -115,6 +115,7 @@ struct rcn_cuda_model {
 
     // scratch (grow-only)
     DevBuf in_stage, tgt_stage, feats, acts, deltas, gemm_ws, out_stage, small, red_ws, sn_counters;
+    ReduceScratch rs;           // deterministic two-stage reductions (bias gradient, batch statistics)
     // epoch mode (rcn.rs:144-149 on a resident dataset)
     const void* ep_images = nullptr;
     const int64_t* ep_labels = nullptr;
@@ -261,10 +262,10 @@ int accumulate_dev(rcn_cuda_model* h, const double* feats, const double* onehot,
     for (size_t l = 0; l < n; ++l) {
         const double* a_prev = l == 0 ? feats : h->act(l - 1, B);
         RCN_TRY(launch_dense_backward_weight(h->delta(l, B), a_prev, h->rows[l], h->cols[l], B, h->grads + h->w_off[l],
-                                             h->grads + h->b_off[l], h->gemm_ws, h->stream, &h->oz));
+                                             h->grads + h->b_off[l], h->gemm_ws, h->rs, h->stream, &h->oz));
     }
     RCN_TRY(h->small.reserve(64));
-    RCN_TRY(launch_batch_stats(h->act(n - 1, B), h->rows[n - 1], B, onehot, labels, h->small.as<double>(), h->stream));
+    RCN_TRY(launch_batch_stats(h->act(n - 1, B), h->rows[n - 1], B, onehot, labels, h->small.as<double>(), h->rs, h->stream));
     h->stats_valid = true;
     h->last_B = B;
     return RCN_OK;
@@ -380,7 +381,7 @@ int rcn_cuda_destroy(rcn_cuda_handle h) {
     dp_release(h->dp);
     h->oz.release();
     DevBuf* bufs[] = {&h->params, &h->grads_own, &h->in_stage, &h->tgt_stage, &h->feats, &h->acts, &h->deltas,
-                      &h->gemm_ws, &h->out_stage, &h->small, &h->red_ws, &h->ep_state, &h->sn_counters, &h->fscratch.a, &h->fscratch.b};
+                      &h->gemm_ws, &h->out_stage, &h->small, &h->red_ws, &h->ep_state, &h->sn_counters, &h->fscratch.a, &h->fscratch.b, &h->rs.buf};
     for (DevBuf* b : bufs) b->release();
     delete h;
     return RCN_OK;
@@ -675,7 +676,7 @@ int rcn_cuda_evaluate(rcn_cuda_handle h, const double* feats, const int64_t* lab
     const size_t n = h->rows.size();
     RCN_TRY(h->small.reserve(64));
     double* st = h->small.as<double>() + 2;
-    RCN_TRY(launch_batch_stats(h->act(n - 1, B), h->rows[n - 1], B, nullptr, (const int64_t*)lb.dev, st, h->stream));
+    RCN_TRY(launch_batch_stats(h->act(n - 1, B), h->rows[n - 1], B, nullptr, (const int64_t*)lb.dev, st, h->rs, h->stream));
     uint64_t host[2];
     RCN_CUDA_TRY(cudaMemcpyAsync(host, st, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
     RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
