@@ -21,6 +21,7 @@
 #include "dense.cuh"
 #include "gemm_f64.cuh"
 #include "opctx.cuh"
+#include "ozaki.cuh"
 
 namespace rcn {
 
@@ -36,15 +37,6 @@ __device__ __forceinline__ double act_backward_from_output(double y, int act) {
     if (act == ACT_SIGMOID) return y * (1.0 - y);                // rcn.rs:490-492
     return 1.0;
 }
-
-// Geometry of one gather: tensor t is [B][Hi][Wi][C]; the pixel grid enumerated by the GEMM is [B][Ho][Wo];
-// tap (ky, kx) of grid pixel (oy, ox) reads t[b, oy + ky - ph, ox + kx - pw, :] (zero outside).
-struct ConvGeom {
-    const double* t;
-    int Hi, Wi, C, Ho, Wo, kh, kw, ph, pw;
-    int n_pix;   // B * Ho * Wo
-    int n_k;     // kh * kw * C
-};
 
 // B operand with rows = grid pixels and contraction k = (ky, kx, c), c fastest (forward, backward-data).
 struct Im2colPixelRows {
@@ -150,6 +142,23 @@ struct EpiConvWeight {    // split-K partial (or final) of dW in [co][k] order
     }
 };
 
+// tcgen05 path (ozaki.cuh): grid pixels are the 128-row M side, channels the N side
+struct EpiConvForwardT {   // y[pix*Co + co] = act(acc + bias[co])
+    const double* bias; double* y; int Co, act;
+    __device__ __forceinline__ void operator()(int m, int n, double v) const {
+        if (bias) v += __ldg(bias + n);
+        y[(size_t)m * Co + n] = act_forward(v, act);
+    }
+};
+struct EpiConvBackDataT {  // dx[pix*Ci + ci] = acc * act'(y_prev)
+    const double* y_prev; double* dx; int Ci, act;
+    __device__ __forceinline__ void operator()(int m, int n, double v) const {
+        const size_t o = (size_t)m * Ci + n;
+        if (y_prev) v *= act_backward_from_output(y_prev[o], act);
+        dx[o] = v;
+    }
+};
+
 // w'[ci][ky'][kx'][co] = w[co][kh-1-ky'][kw-1-kx'][ci]
 __global__ void conv_flip_weights_kernel(const double* __restrict__ w, int Co, int kh, int kw, int Ci, double* __restrict__ wt) {
     const int n = Co * kh * kw * Ci;
@@ -250,6 +259,31 @@ int check_conv_shape(size_t B, size_t H, size_t W, size_t Ci, size_t Co, size_t 
     return RCN_OK;
 }
 
+// tcgen05 integer-slice implicit GEMM when the contraction is really dense (wide-channel layers: BASELINE config 4):
+// >= half the SMs worth of 128-pixel x 96-channel tiles, K = kh*kw*C deep enough, enough work to amortise the gather.
+bool conv_use_tc(size_t n_pix, size_t n_out, size_t K) {
+    const GemmImpl impl = gemm_impl();
+    if (impl == GEMM_DMMA || impl == GEMM_SIMT || !ozaki_available() || K > (size_t)OZ_MAX_K) return false;
+    if (impl == GEMM_TC) return true;
+    const size_t tiles = ((n_pix + OZ_BM - 1) / OZ_BM) * ((n_out + OZ_BN - 1) / OZ_BN);
+    return n_out >= 32 && K >= 256 && tiles >= (size_t)kNumSMs / 2 && (double)n_pix * (double)n_out * (double)K >= 2.0e9;
+}
+
+// backward-weight contracts over the pixels (K = B*Ho*Wo, split across CTAs), so the tile count does not matter
+bool conv_wgrad_use_tc(size_t Co, size_t n_k, size_t n_pix) {
+    const GemmImpl impl = gemm_impl();
+    if (impl == GEMM_DMMA || impl == GEMM_SIMT || !ozaki_available()) return false;
+    if (impl == GEMM_TC) return true;
+    return Co >= 64 && n_k >= 256 && n_pix >= 4096 && (double)Co * (double)n_k * (double)n_pix >= 2.0e9;
+}
+
+OzakiWorkspace& conv_tc_workspace() {
+    static thread_local OzakiWorkspace ws[64];   // one per device this thread drives
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return ws[dev & 63];
+}
+
 bool use_direct(const ConvShape& s) {
     static const bool off = []() { const char* e = getenv("RCN_CUDA_CONV_DIRECT"); return e && e[0] == '0'; }();
     const size_t kk = s.kh * s.kw * s.Ci;
@@ -277,8 +311,16 @@ int launch_conv2d_forward(const double* x, const double* w, const double* bias, 
         return RCN_OK;
     }
     const int M = (int)s.Co, N = (int)(s.B * s.Ho * s.Wo), K = (int)(s.kh * s.kw * s.Ci);
+    const ConvGeom geom{x, (int)s.H, (int)s.W, (int)s.Ci, (int)s.Ho, (int)s.Wo, (int)s.kh, (int)s.kw, s.ph, s.pw, N, K};
+    if (conv_use_tc((size_t)N, (size_t)M, (size_t)K)) {
+        OzOperand oa{x, 0, true};                 // im2col rows gathered straight into int8 digit planes
+        oa.gather = 1; oa.g = geom;
+        const OzOperand ob{w, (size_t)K, true};   // w[co][k]
+        const EpiConvForwardT epi{bias, y, M, act};
+        return launch_gemm_ozaki("conv2d_forward_igemm(tcgen05 int8 slices)", oa, ob, N, M, K, epi, conv_tc_workspace(), stream);
+    }
     const DenseLoader<true> la{w, K, M};
-    const Im2colPixelRows lb{ConvGeom{x, (int)s.H, (int)s.W, (int)s.Ci, (int)s.Ho, (int)s.Wo, (int)s.kh, (int)s.kw, s.ph, s.pw, N, K}};
+    const Im2colPixelRows lb{geom};
     const EpiConvForward epi{bias, y, M, act};
     int splits = 1, kps;
     split_plan(K, splits, kps);
@@ -295,10 +337,18 @@ int launch_conv2d_backward_data(const double* dz, const double* w, const ConvSha
     RCN_LAUNCH("conv_flip_weights_kernel", stream,
                conv_flip_weights_kernel<<<grid, 256, 0, stream>>>(w, (int)s.Co, (int)s.kh, (int)s.kw, (int)s.Ci, ws.as<double>()));
     const int M = (int)s.Ci, N = (int)(s.B * s.H * s.W), K = (int)(s.kh * s.kw * s.Co);
-    const DenseLoader<true> la{ws.as<double>(), K, M};
     // gather from dz [B][Ho][Wo][Co] over the INPUT pixel grid with the complementary padding
-    const Im2colPixelRows lb{ConvGeom{dz, (int)s.Ho, (int)s.Wo, (int)s.Co, (int)s.H, (int)s.W, (int)s.kh, (int)s.kw,
-                                      (int)s.kh - 1 - s.ph, (int)s.kw - 1 - s.pw, N, K}};
+    const ConvGeom geom{dz, (int)s.Ho, (int)s.Wo, (int)s.Co, (int)s.H, (int)s.W, (int)s.kh, (int)s.kw,
+                        (int)s.kh - 1 - s.ph, (int)s.kw - 1 - s.pw, N, K};
+    if (conv_use_tc((size_t)N, (size_t)M, (size_t)K)) {
+        OzOperand oa{dz, 0, true};
+        oa.gather = 1; oa.g = geom;
+        const OzOperand ob{ws.as<double>(), (size_t)K, true};   // w'[ci][k]
+        const EpiConvBackDataT epi{y_prev, dx, M, act_prev};
+        return launch_gemm_ozaki("conv2d_backward_data_igemm(tcgen05 int8 slices)", oa, ob, N, M, K, epi, conv_tc_workspace(), stream);
+    }
+    const DenseLoader<true> la{ws.as<double>(), K, M};
+    const Im2colPixelRows lb{geom};
     const EpiConvBackData epi{y_prev, dx, M, act_prev};
     int splits = 1, kps;
     split_plan(K, splits, kps);
@@ -311,6 +361,33 @@ int launch_conv2d_backward_weight(const double* x, const double* dz, const ConvS
     if (Kc == 0) {
         RCN_CUDA_TRY(cudaMemsetAsync(dw, 0, (size_t)M * N * sizeof(double), stream));
         if (db) RCN_CUDA_TRY(cudaMemsetAsync(db, 0, (size_t)M * sizeof(double), stream));
+        return RCN_OK;
+    }
+    if (conv_wgrad_use_tc((size_t)M, (size_t)N, (size_t)Kc)) {
+        // contraction over the grid pixels: dz columns (co) x im2col columns (ky, kx, ci), both gathered straight into
+        // digit planes with per-row scales over ALL pixels; split-K keeps each CTA's contraction inside the exact int32
+        // range and fills the machine; partials are combined in split order (deterministic)
+        OzakiWorkspace& tw = conv_tc_workspace();
+        const int splits = ozaki_plan_splits(M, N, Kc);
+        OzOperand oa{dz, (size_t)M, false};                      // element (co, pix) at dz[pix*Co + co]
+        OzOperand ob{x, 0, false};
+        ob.gather = 2;
+        ob.g = ConvGeom{x, (int)s.H, (int)s.W, (int)s.Ci, (int)s.Ho, (int)s.Wo, (int)s.kh, (int)s.kw, s.ph, s.pw, Kc, N};
+        if (splits == 1) {
+            const EpiOzSplitStore epi{dw, (size_t)N, 1, 0};
+            RCN_TRY(launch_gemm_ozaki("conv2d_backward_weight_igemm(tcgen05 int8 slices)", oa, ob, M, N, Kc, epi, tw, stream, 1));
+        } else {
+            RCN_TRY(tw.partials.reserve((size_t)splits * M * N * sizeof(double)));
+            const EpiOzSplitStore epi{tw.partials.as<double>(), (size_t)N, 1, (size_t)M * N};
+            RCN_TRY(launch_gemm_ozaki("conv2d_backward_weight_igemm(tcgen05 int8 slices)", oa, ob, M, N, Kc, epi, tw, stream, splits));
+            RCN_TRY(launch_reduce_splits(tw.partials.as<double>(), splits, (size_t)M * N, dw, stream));
+        }
+        if (db) {
+            static thread_local ReduceScratch tl_rs2[64];
+            int dev = 0;
+            RCN_CUDA_TRY(cudaGetDevice(&dev));
+            RCN_TRY(launch_bias_grad(dz, (size_t)M, (size_t)Kc, db, tl_rs2[dev & 63], stream));
+        }
         return RCN_OK;
     }
     size_t tiles;

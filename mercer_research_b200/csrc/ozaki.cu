@@ -47,15 +47,41 @@ __device__ __forceinline__ void row_scale(double amax, double& inv, double& scal
     scale = ldexp(1.0, e - 6);
 }
 
-// element (r, k) at X[r*ld + k]: one warp per row.
-__global__ void __launch_bounds__(256) ozaki_slice_kmajor_kernel(const double* __restrict__ X, size_t ld, int R, int K, int Kp,
+// One row of a k-contiguous operand: a strided matrix row, or the im2col row of one grid pixel (gathered, zero padded).
+struct RowReader {
+    const double* row;      // dense
+    ConvGeom g;             // gather
+    int base, oy, ox;       // b*Hi*Wi, oy - ph, ox - pw
+    bool gather;
+    __device__ __forceinline__ RowReader(const OzOperand& op, int r) : row(nullptr), g(op.g), base(0), oy(0), ox(0), gather(op.gather == 1) {
+        if (!gather) { row = op.p + (size_t)r * op.ld; return; }
+        const int n = r + op.pix0;
+        const int b = n / (g.Ho * g.Wo);
+        const int rem = n - b * g.Ho * g.Wo;
+        oy = rem / g.Wo;
+        ox = rem - oy * g.Wo - g.pw;
+        oy -= g.ph;
+        base = b * g.Hi * g.Wi;
+    }
+    __device__ __forceinline__ double at(int k) const {
+        if (!gather) return row[k];
+        const int tap = k / g.C, c = k - tap * g.C;
+        const int ky = tap / g.kw, kx = tap - ky * g.kw;
+        const int iy = oy + ky, ix = ox + kx;
+        if ((unsigned)iy >= (unsigned)g.Hi || (unsigned)ix >= (unsigned)g.Wi) return 0.0;
+        return g.t[((size_t)(base + iy * g.Wi + ix)) * g.C + c];
+    }
+};
+
+// k-contiguous operand: one warp per row.
+__global__ void __launch_bounds__(256) ozaki_slice_kmajor_kernel(const OzOperand op, int R, int K, int Kp,
                                                                  int8_t* __restrict__ planes, double* __restrict__ scale) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + warp;
     if (r >= R) return;
-    const double* row = X + (size_t)r * ld;
+    const RowReader row(op, r);
     double amax = 0.0;
-    for (int k = lane; k < K; k += 32) amax = fmax(amax, fabs(row[k]));
+    for (int k = lane; k < K; k += 32) amax = fmax(amax, fabs(row.at(k)));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     double inv, sc;
@@ -67,7 +93,7 @@ __global__ void __launch_bounds__(256) ozaki_slice_kmajor_kernel(const double* _
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int k = k4 + u;
-            slice6(k < K ? row[k] : 0.0, inv, q[u]);
+            slice6(k < K ? row.at(k) : 0.0, inv, q[u]);
         }
 #pragma unroll
         for (int j = 0; j < OZ_S; ++j) {
@@ -86,18 +112,46 @@ __global__ void __launch_bounds__(256) ozaki_slice_kmajor_kernel(const double* _
 constexpr int TR_PITCH = 68;   // bytes per (slice, row) line of the 64-k tile: 17 words -> conflict-free byte scatter
 constexpr int RM_KCHUNK = 512;
 
-__global__ void __launch_bounds__(256) ozaki_amax_rmajor_kernel(const double* __restrict__ X, size_t ld, int R, int K, int k_per_cta,
+// One row-contiguous operand column r seen along k: a strided matrix, or im2col column (ky, kx, c) over grid pixels.
+struct ColReader {
+    const double* p; size_t ld;   // dense
+    ConvGeom g; int dy, dx, c, pix0;
+    bool gather, valid;
+    __device__ __forceinline__ ColReader(const OzOperand& op, int r, int R)
+        : p(op.p), ld(op.ld), g(op.g), dy(0), dx(0), c(0), pix0(op.pix0), gather(op.gather == 2), valid(r < R) {
+        if (!gather) { p = op.p + r; return; }
+        if (!valid) return;
+        const int tap = r / g.C;
+        c = r - tap * g.C;
+        const int ky = tap / g.kw;
+        dy = ky - g.ph;
+        dx = (tap - ky * g.kw) - g.pw;
+    }
+    __device__ __forceinline__ double at(int k) const {
+        if (!gather) return p[(size_t)k * ld];
+        const int pix = k + pix0;
+        const int b = pix / (g.Ho * g.Wo);
+        const int rem = pix - b * g.Ho * g.Wo;
+        const int oy = rem / g.Wo, ox = rem - oy * g.Wo;
+        const int iy = oy + dy, ix = ox + dx;
+        if ((unsigned)iy >= (unsigned)g.Hi || (unsigned)ix >= (unsigned)g.Wi) return 0.0;
+        return g.t[((size_t)((b * g.Hi + iy) * g.Wi + ix)) * g.C + c];
+    }
+};
+
+__global__ void __launch_bounds__(256) ozaki_amax_rmajor_kernel(const OzOperand op, int R, int K, int k_per_cta,
                                                                 unsigned long long* __restrict__ amax_bits) {
     __shared__ double red[8][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * 32 + lane;
     const int k_lo = blockIdx.y * k_per_cta, k_hi = min(K, k_lo + k_per_cta);
+    const ColReader col(op, r, R);
     double amax = 0.0;
     if (r < R) {
         for (int k = k_lo + warp; k < k_hi; k += 64) {
             double v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = (k + 8 * u < k_hi) ? X[(size_t)(k + 8 * u) * ld + r] : 0.0;
+            for (int u = 0; u < 8; ++u) v[u] = (k + 8 * u < k_hi) ? col.at(k + 8 * u) : 0.0;
 #pragma unroll
             for (int u = 0; u < 8; ++u) amax = fmax(amax, fabs(v[u]));
         }
@@ -112,7 +166,7 @@ __global__ void __launch_bounds__(256) ozaki_amax_rmajor_kernel(const double* __
     }
 }
 
-__global__ void __launch_bounds__(256) ozaki_slice_rmajor_kernel(const double* __restrict__ X, size_t ld, int R, int K, int Kp,
+__global__ void __launch_bounds__(256) ozaki_slice_rmajor_kernel(const OzOperand op, int R, int K, int Kp,
                                                                  const unsigned long long* __restrict__ amax_bits,
                                                                  int8_t* __restrict__ planes, double* __restrict__ scale) {
     __shared__ double s_inv[32];
@@ -129,6 +183,7 @@ __global__ void __launch_bounds__(256) ozaki_slice_rmajor_kernel(const double* _
     }
     __syncthreads();
     const double inv = s_inv[lane];
+    const ColReader col(op, r, R);
     const size_t plane = (size_t)R * Kp;
     const int kb_lo = blockIdx.y * RM_KCHUNK, kb_hi = min(Kp, kb_lo + RM_KCHUNK);
     for (int kb = kb_lo; kb < kb_hi; kb += 64) {
@@ -136,7 +191,7 @@ __global__ void __launch_bounds__(256) ozaki_slice_rmajor_kernel(const double* _
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int k = kb + warp * 8 + j;
-            v[j] = (rok && k < K) ? X[(size_t)k * ld + r] : 0.0;
+            v[j] = (rok && k < K) ? col.at(k) : 0.0;
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -186,7 +241,7 @@ int ozaki_slice(const OzOperand& op, int rows, int K, int Kp, int8_t* planes, do
     if (rows <= 0) return RCN_OK;
     if (op.kcontig) {
         RCN_LAUNCH("ozaki_slice_kmajor_kernel", stream,
-                   ozaki_slice_kmajor_kernel<<<cdiv(rows, 8), 256, 0, stream>>>(op.p, op.ld, rows, K, Kp, planes, scale));
+                   ozaki_slice_kmajor_kernel<<<cdiv(rows, 8), 256, 0, stream>>>(op, rows, K, Kp, planes, scale));
     } else {
         // the scale array doubles as the per-row |x| maximum (bit pattern) between the two kernels
         unsigned long long* amax_bits = reinterpret_cast<unsigned long long*>(scale_scratch);
@@ -196,9 +251,9 @@ int ozaki_slice(const OzOperand& op, int rows, int K, int Kp, int8_t* planes, do
         if (ksplit < 1) ksplit = 1;
         const int k_per_cta = (K + ksplit - 1) / ksplit;
         RCN_LAUNCH("ozaki_amax_rmajor_kernel", stream,
-                   ozaki_amax_rmajor_kernel<<<dim3(cdiv(rows, 32), (unsigned)ksplit), 256, 0, stream>>>(op.p, op.ld, rows, K, k_per_cta, amax_bits));
+                   ozaki_amax_rmajor_kernel<<<dim3(cdiv(rows, 32), (unsigned)ksplit), 256, 0, stream>>>(op, rows, K, k_per_cta, amax_bits));
         RCN_LAUNCH("ozaki_slice_rmajor_kernel", stream,
-                   ozaki_slice_rmajor_kernel<<<dim3(cdiv(rows, 32), cdiv(Kp, RM_KCHUNK)), 256, 0, stream>>>(op.p, op.ld, rows, K, Kp, amax_bits,
+                   ozaki_slice_rmajor_kernel<<<dim3(cdiv(rows, 32), cdiv(Kp, RM_KCHUNK)), 256, 0, stream>>>(op, rows, K, Kp, amax_bits,
                                                                                                            planes, scale));
     }
     return RCN_OK;

@@ -40,15 +40,39 @@ constexpr int OZ_THREADS = 192;
 constexpr int OZ_TMEM_COLS = 512;
 
 struct OzakiWorkspace {
-    DevBuf a_slices, b_slices, a_scale, b_scale;
-    void release() { a_slices.release(); b_slices.release(); a_scale.release(); b_scale.release(); }
+    DevBuf a_slices, b_slices, a_scale, b_scale, partials;
+    void release() { a_slices.release(); b_slices.release(); a_scale.release(); b_scale.release(); partials.release(); }
 };
 
-// Operand as the GEMM sees it: `rows` x K (rows = M for A, N for B); kcontig: element (r, k) at p[r*ld + k], else p[k*ld + r].
+// split-K partial store for the tile kernel (split = blockIdx.y): out[split][m*ld_m + n*ld_n]
+struct EpiOzSplitStore {
+    double* out; size_t ld_m, ld_n, split_stride;
+    __device__ __forceinline__ void operator()(int m, int n, double v) const {
+        out[(size_t)blockIdx.y * split_stride + (size_t)m * ld_m + (size_t)n * ld_n] = v;
+    }
+};
+
+// Geometry of an im2col gather (shared with conv.cu): tensor t is [B][Hi][Wi][C] (NHWC); the pixel grid enumerated by the
+// GEMM is [B][Ho][Wo]; tap (ky, kx) of grid pixel (oy, ox) reads t[b, oy + ky - ph, ox + kx - pw, :] (zero outside).
+struct ConvGeom {
+    const double* t;
+    int Hi, Wi, C, Ho, Wo, kh, kw, ph, pw;
+    int n_pix;   // B * Ho * Wo
+    int n_k;     // kh * kw * C
+};
+
+// Operand as the GEMM sees it: `rows` x K (rows = M for A, N for B).
+//   gather 0: strided matrix; kcontig: element (r, k) at p[r*ld + k], else p[k*ld + r].
+//   gather 1 (kcontig): im2col rows -- r = grid pixel (+ pix0), k = (ky, kx, c), c fastest        (conv forward / backward-data)
+//   gather 2 (!kcontig): im2col columns -- r = (ky, kx, c), k = grid pixel (+ pix0)             (conv backward-weight)
+// Nothing is materialised in f64: the slicing kernels gather straight into the int8 digit planes.
 struct OzOperand {
     const double* p;
     size_t ld;
     bool kcontig;
+    int gather = 0;
+    int pix0 = 0;         // first grid pixel of this (chunk of the) operand
+    ConvGeom g{};
 };
 
 // Slices one operand into int8 planes [OZ_S][rows][Kp] (Kp = K rounded up to 64, zero padded) and scale[rows].
@@ -156,7 +180,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                                                                     const __grid_constant__ CUtensorMap map_b,
                                                                     const double* __restrict__ scale_a,
                                                                     const double* __restrict__ scale_b, int M, int N, int Kp,
-                                                                    int m_tiles, int n_tiles, Epi epi) {
+                                                                    int m_tiles, int n_tiles, int kb_per_split, Epi epi) {
     extern __shared__ unsigned char oz_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OZ_STAGES * OZ_STAGE_BYTES);
@@ -178,7 +202,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
     const int m_tile = g_m0 + in_g % g_rows;
     const int n_tile = (in_g / g_rows) * CLUSTER + (int)crank;
     const int m0 = m_tile * OZ_BM, n0 = n_tile * OZ_BN;
-    const int n_kb = Kp / OZ_BK;
+    // split-K: blockIdx.y owns k-blocks [kb0, kb0 + n_kb); the epilogue functor sees blockIdx.y and stores a partial
+    const int kb0 = blockIdx.y * kb_per_split;
+    const int n_kb = min(Kp / OZ_BK - kb0, kb_per_split);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < OZ_STAGES; ++s) { oz::mbar_init(full_bar + s, 1); oz::mbar_init(empty_bar + s, CLUSTER); }
@@ -211,14 +237,14 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                     constexpr int HALF = OZ_BM / 2;          // my half of the A rows, delivered to both CTAs
 #pragma unroll
                     for (int s = 0; s < OZ_S; ++s)
-                        oz::tma_load_3d_mc(sa + s * OZ_A_TILE + crank * (HALF * OZ_BK), &map_a, full_bar + stage, kb * OZ_BK,
+                        oz::tma_load_3d_mc(sa + s * OZ_A_TILE + crank * (HALF * OZ_BK), &map_a, full_bar + stage, (kb0 + kb) * OZ_BK,
                                            m0 + (int)crank * HALF, s, (uint16_t)0x3);
                 } else {
 #pragma unroll
-                    for (int s = 0; s < OZ_S; ++s) oz::tma_load_3d(sa + s * OZ_A_TILE, &map_a, full_bar + stage, kb * OZ_BK, m0, s);
+                    for (int s = 0; s < OZ_S; ++s) oz::tma_load_3d(sa + s * OZ_A_TILE, &map_a, full_bar + stage, (kb0 + kb) * OZ_BK, m0, s);
                 }
 #pragma unroll
-                for (int s = 0; s < OZ_S; ++s) oz::tma_load_3d(sb + s * OZ_B_TILE, &map_b, full_bar + stage, kb * OZ_BK, n0, s);
+                for (int s = 0; s < OZ_S; ++s) oz::tma_load_3d(sb + s * OZ_B_TILE, &map_b, full_bar + stage, (kb0 + kb) * OZ_BK, n0, s);
             }
         }
     } else if (warp == 1) {
@@ -296,12 +322,34 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
 }
 
 // Host launcher: slices both operands, builds the tensor maps and runs the tile kernel.
+// Smallest split count that keeps every split's contraction inside the exact int32 range and, when the output has
+// few tiles, spreads the k-blocks over about two waves of CTAs (each split at least 8 k-blocks deep).
+inline int ozaki_plan_splits(int M, int N, int K) {
+    const int n_kb = (K + OZ_BK - 1) / OZ_BK;
+    const long tiles = (long)((M + OZ_BM - 1) / OZ_BM) * ((N + OZ_BN - 1) / OZ_BN);
+    int splits = (K + OZ_MAX_K - 1) / OZ_MAX_K;
+    if (tiles < kNumSMs) {
+        int want = (int)((2L * kNumSMs + tiles - 1) / tiles);
+        if (want > n_kb / 8) want = n_kb / 8;
+        if (want > splits) splits = want;
+    }
+    if (splits < 1) splits = 1;
+    const int kbps = (n_kb + splits - 1) / splits;
+    return (n_kb + kbps - 1) / kbps;
+}
+
+// splits > 1: blockIdx.y = split index; `epi` must store a per-split partial (it can read blockIdx.y) that the caller
+// then combines in split order.
 template <typename Epi>
 static int launch_gemm_ozaki(const char* name, const OzOperand& A, const OzOperand& B, int M, int N, int K, const Epi& epi,
-                             OzakiWorkspace& ws, cudaStream_t stream) {
+                             OzakiWorkspace& ws, cudaStream_t stream, int splits = 1) {
     if (M <= 0 || N <= 0) return RCN_OK;
-    if (K > OZ_MAX_K) return fail(RCN_ERR_INVALID, "tcgen05 integer-slice GEMM supports K <= %d (exact int32 accumulation)", OZ_MAX_K);
     const int Kp = ((K + OZ_BK - 1) / OZ_BK) * OZ_BK;
+    if (splits < 1) splits = 1;
+    const int kb_per_split = (Kp / OZ_BK + splits - 1) / splits;
+    splits = (Kp / OZ_BK + kb_per_split - 1) / kb_per_split;
+    if (kb_per_split * OZ_BK > OZ_MAX_K)
+        return fail(RCN_ERR_INVALID, "tcgen05 integer-slice GEMM: %d k per split exceeds %d (exact int32 accumulation)", kb_per_split * OZ_BK, OZ_MAX_K);
     RCN_TRY(ws.a_slices.reserve((size_t)OZ_S * M * Kp));
     RCN_TRY(ws.b_slices.reserve((size_t)OZ_S * N * Kp));
     RCN_TRY(ws.a_scale.reserve((size_t)2 * M * sizeof(double)));
@@ -320,7 +368,7 @@ static int launch_gemm_ozaki(const char* name, const OzOperand& A, const OzOpera
         static SmemAttrCache attr;
         if (attr.need(OZ_SMEM_BYTES)) RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES));
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(m_tiles * n_tiles), 1, 1);
+        cfg.gridDim = dim3((unsigned)(m_tiles * n_tiles), (unsigned)splits, 1);
         cfg.blockDim = dim3(OZ_THREADS, 1, 1);
         cfg.dynamicSmemBytes = OZ_SMEM_BYTES;
         cfg.stream = stream;
@@ -330,15 +378,14 @@ static int launch_gemm_ozaki(const char* name, const OzOperand& A, const OzOpera
         cfg.attrs = at; cfg.numAttrs = 1;
         const double* sa = ws.a_scale.as<double>();
         const double* sb = ws.b_scale.as<double>();
-        RCN_LAUNCH(name, stream, cudaLaunchKernelEx(&cfg, kern, map_a, map_b, sa, sb, M, N, Kp, m_tiles, n_tiles, epi));
+        RCN_LAUNCH(name, stream, cudaLaunchKernelEx(&cfg, kern, map_a, map_b, sa, sb, M, N, Kp, m_tiles, n_tiles, kb_per_split, epi));
     } else {
         auto kern = ozaki_gemm_kernel<Epi, 1>;
         static SmemAttrCache attr;
         if (attr.need(OZ_SMEM_BYTES)) RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES));
         RCN_LAUNCH(name, stream,
-                   kern<<<(unsigned)(m_tiles * n_tiles), OZ_THREADS, OZ_SMEM_BYTES, stream>>>(map_a, map_b, ws.a_scale.as<double>(),
-                                                                                              ws.b_scale.as<double>(), M, N, Kp,
-                                                                                              m_tiles, n_tiles, epi));
+                   kern<<<dim3((unsigned)(m_tiles * n_tiles), (unsigned)splits), OZ_THREADS, OZ_SMEM_BYTES, stream>>>(
+                       map_a, map_b, ws.a_scale.as<double>(), ws.b_scale.as<double>(), M, N, Kp, m_tiles, n_tiles, kb_per_split, epi));
     }
     return RCN_OK;
 }

@@ -102,3 +102,75 @@ def test_dense_layers_forced_through_tensor_cores_match_oracle(built_library):
     assert any("tcgen05" in k for k in r["kernels"]), r["kernels"]
     assert r["grad_rel"] < 1e-9 and r["param_rel"] < 1e-9, r
     assert r["pred_equal"], "predicted labels must be exact"
+
+
+CONV_SCRIPT = r"""
+import json, sys
+import numpy as np
+sys.path.insert(0, %(root)r)
+import oracle.ext as E
+from mercer_research_b200 import ext, _lib
+rng = np.random.default_rng(61)
+out = {}
+for tag, (B, H, W, Ci, Co, kh, kw, pad) in {"same3x3": (2, 12, 10, 32, 48, 3, 3, 1), "valid": (1, 9, 11, 16, 40, 3, 3, 0),
+                                            "odd": (3, 8, 8, 20, 24, 1, 3, 1)}.items():
+    x = np.maximum(rng.standard_normal((B, H, W, Ci)), 0)
+    w = rng.standard_normal((Co, kh, kw, Ci)) / np.sqrt(kh * kw * Ci)
+    b = rng.standard_normal(Co)
+    _lib.profile_enable(True)
+    y = ext.conv2d_forward(x, w, b, pad, 1)
+    want = E.conv2d_forward(x, w, b, pad, 1)
+    dz = rng.standard_normal(want.shape)
+    dx = ext.conv2d_backward_data(dz, w, (H, W), pad)
+    dw, db = ext.conv2d_backward_weight(x, dz, kh, kw, pad)
+    names = sorted(_lib.profile_report())
+    _lib.profile_enable(False)
+    wdx = E.conv2d_backward_data(dz, w, (H, W), pad)
+    wdw, wdb = E.conv2d_backward_weight(x, dz, kh, kw, pad)
+    rel = lambda a, r: float(np.max(np.abs(a - r)) / np.max(np.abs(r)))
+    out[tag] = {"kernels": names, "y": rel(y, want), "dx": rel(dx, wdx), "dw": rel(dw, wdw), "db": rel(db, wdb)}
+print(json.dumps(out))
+"""
+
+
+def test_conv_forced_through_tensor_cores_matches_oracle(built_library):
+    """Learned convolution fwd / bwd-data / bwd-weight as tcgen05 integer-slice implicit GEMMs (im2col gathered straight into
+    int8 digit planes, split-K over the pixels for the weight gradient) against the definition oracle."""
+    env = dict(os.environ, RCN_CUDA_GEMM="tc", RCN_CUDA_CONV_DIRECT="0")
+    out = subprocess.run([sys.executable, "-c", CONV_SCRIPT % {"root": ROOT}], env=env, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    for tag, v in r.items():
+        tc = [k for k in v["kernels"] if "tcgen05" in k]
+        assert len(tc) == 3, (tag, v["kernels"])
+        for key in ("y", "dx", "dw", "db"):
+            assert v[key] < 1e-9, (tag, key, v[key])
+
+
+def test_wide_conv_layer_auto_dispatch(X):
+    """A BASELINE-config-4-shaped layer (64 -> 64 channels, 3x3, 64x64 input, reduced batch) takes the tensor-core path by
+    itself and matches the f64 DMMA implicit GEMM."""
+    import torch
+    from mercer_research_b200 import _lib
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    x = torch.randn(16, 64, 64, 64, dtype=torch.float64, device="cuda", generator=g).clamp_(min=0)
+    w = torch.randn(64, 3, 3, 64, dtype=torch.float64, device="cuda", generator=g) / 24.0
+    b = torch.randn(64, dtype=torch.float64, device="cuda", generator=g)
+    _lib.profile_enable(True)
+    y = X.conv2d_forward(x, w, b, 1, 1)
+    dz = torch.randn(y.shape, dtype=torch.float64, device="cuda", generator=g)
+    dx = X.conv2d_backward_data(dz, w, (64, 64), 1)
+    dw, db = X.conv2d_backward_weight(x, dz, 3, 3, 1)
+    torch.cuda.synchronize()
+    names = sorted(_lib.profile_report())
+    _lib.profile_enable(False)
+    assert sum("tcgen05" in k for k in names) == 3, names
+    # reference: the same ops forced onto DMMA in a subprocess would need the data; compare against float64 torch conv instead
+    xt, wt = x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2)
+    yt = torch.relu(torch.nn.functional.conv2d(xt, wt, b, padding=1)).permute(0, 2, 3, 1)
+    rel = lambda a, r: float((a - r).abs().max() / r.abs().max())
+    assert rel(y, yt) < 1e-9
+    dzt = dz.permute(0, 3, 1, 2)
+    dxt = torch.nn.grad.conv2d_input(xt.shape, wt, dzt, padding=1).permute(0, 2, 3, 1)
+    dwt = torch.nn.grad.conv2d_weight(xt, wt.shape, dzt, padding=1).permute(0, 2, 3, 1)
+    assert rel(dx, dxt) < 1e-9 and rel(dw, dwt) < 1e-9 and rel(db, dz.sum((0, 1, 2))) < 1e-9
