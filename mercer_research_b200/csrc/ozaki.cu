@@ -177,7 +177,9 @@ __global__ void __launch_bounds__(256) ozaki_slice_rmajor_kernel(const OzOperand
     const bool rok = r < R;
     if (warp == 0) {
         double inv = 0.0, sc = 0.0;
-        if (rok) row_scale(__longlong_as_double((long long)amax_bits[r]), inv, sc);
+        // im2col columns (ky, kx, c): the maximum over the pixels is the channel's maximum for every tap (an upper bound at
+        // the borders), so one per-CHANNEL maximum serves all kh*kw rows of that channel
+        if (rok) row_scale(__longlong_as_double((long long)amax_bits[op.gather == 2 ? r % op.g.C : r]), inv, sc);
         s_inv[lane] = inv;
         if (rok && blockIdx.y == 0) scale[r] = sc;
     }
@@ -215,6 +217,37 @@ __global__ void __launch_bounds__(256) ozaki_slice_rmajor_kernel(const OzOperand
     }
 }
 
+// ---- whole-tensor slicing (one scale): convolution inputs whose im2col is done by TMA -------------------------------
+__global__ void __launch_bounds__(256) ozaki_amax_tensor_kernel(const double* __restrict__ x, size_t n, unsigned long long* __restrict__ amax_bits) {
+    double amax = 0.0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) amax = fmax(amax, fabs(x[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) {
+        if (amax == amax) atomicMax(amax_bits, (unsigned long long)__double_as_longlong(amax));
+        else atomicMax(amax_bits, 0x7FF8000000000000ull);
+    }
+}
+
+__global__ void __launch_bounds__(256) ozaki_slice_tensor_kernel(const double* __restrict__ x, size_t n, const unsigned long long* __restrict__ amax_bits,
+                                                                 int8_t* __restrict__ planes, double* __restrict__ scale_out) {
+    double inv, sc;
+    row_scale(__longlong_as_double((long long)*amax_bits), inv, sc);
+    if (blockIdx.x == 0 && threadIdx.x == 0) scale_out[0] = sc;
+    const size_t n4 = n / 4;       // n is a multiple of 64 (C % 64 == 0)
+    for (size_t i4 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i4 < n4; i4 += (size_t)gridDim.x * blockDim.x) {
+        const double2 a = reinterpret_cast<const double2*>(x)[2 * i4], b = reinterpret_cast<const double2*>(x)[2 * i4 + 1];
+        int8_t q[4][OZ_S];
+        slice6(a.x, inv, q[0]); slice6(a.y, inv, q[1]); slice6(b.x, inv, q[2]); slice6(b.y, inv, q[3]);
+#pragma unroll
+        for (int j = 0; j < OZ_S; ++j) {
+            const uint32_t w = (uint32_t)(uint8_t)q[0][j] | ((uint32_t)(uint8_t)q[1][j] << 8) | ((uint32_t)(uint8_t)q[2][j] << 16) |
+                               ((uint32_t)(uint8_t)q[3][j] << 24);
+            reinterpret_cast<uint32_t*>(planes + (size_t)j * n)[i4] = w;
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -246,16 +279,51 @@ int ozaki_slice(const OzOperand& op, int rows, int K, int Kp, int8_t* planes, do
         // the scale array doubles as the per-row |x| maximum (bit pattern) between the two kernels
         unsigned long long* amax_bits = reinterpret_cast<unsigned long long*>(scale_scratch);
         RCN_CUDA_TRY(cudaMemsetAsync(amax_bits, 0, (size_t)rows * sizeof(unsigned long long), stream));
-        int ksplit = (int)((4 * (size_t)kNumSMs + cdiv(rows, 32) - 1) / cdiv(rows, 32));
-        if (ksplit > (K + 255) / 256) ksplit = (K + 255) / 256;
+        // row maxima: of the operand itself, or (im2col columns) of the C channels of the underlying NHWC tensor
+        OzOperand am = op;
+        int am_rows = rows, am_K = K;
+        if (op.gather == 2) {
+            am = OzOperand{op.g.t, (size_t)op.g.C, false};
+            am_rows = op.g.C;
+            am_K = (op.g.n_pix / (op.g.Ho * op.g.Wo)) * op.g.Hi * op.g.Wi;   // every pixel of every image
+        }
+        int ksplit = (int)((4 * (size_t)kNumSMs + cdiv(am_rows, 32) - 1) / cdiv(am_rows, 32));
+        if (ksplit > (am_K + 255) / 256) ksplit = (am_K + 255) / 256;
         if (ksplit < 1) ksplit = 1;
-        const int k_per_cta = (K + ksplit - 1) / ksplit;
+        const int k_per_cta = (am_K + ksplit - 1) / ksplit;
         RCN_LAUNCH("ozaki_amax_rmajor_kernel", stream,
-                   ozaki_amax_rmajor_kernel<<<dim3(cdiv(rows, 32), (unsigned)ksplit), 256, 0, stream>>>(op, rows, K, k_per_cta, amax_bits));
+                   ozaki_amax_rmajor_kernel<<<dim3(cdiv(am_rows, 32), (unsigned)ksplit), 256, 0, stream>>>(am, am_rows, am_K, k_per_cta, amax_bits));
         RCN_LAUNCH("ozaki_slice_rmajor_kernel", stream,
                    ozaki_slice_rmajor_kernel<<<dim3(cdiv(rows, 32), cdiv(Kp, RM_KCHUNK)), 256, 0, stream>>>(op, rows, K, Kp, amax_bits,
                                                                                                            planes, scale));
     }
+    return RCN_OK;
+}
+
+int ozaki_slice_tensor(const double* x, size_t n, int8_t* planes, double* scale_out, cudaStream_t stream) {
+    if (n == 0) return RCN_OK;
+    if (n % 64 || (reinterpret_cast<uintptr_t>(x) & 15)) return fail(RCN_ERR_INVALID, "tensor slicing needs a 16-byte aligned tensor of a multiple of 64 elements");
+    unsigned long long* amax_bits = reinterpret_cast<unsigned long long*>(scale_out + 1);
+    RCN_CUDA_TRY(cudaMemsetAsync(amax_bits, 0, sizeof(unsigned long long), stream));
+    unsigned grid = cdiv(n, 256 * 8);
+    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    RCN_LAUNCH("ozaki_amax_tensor_kernel", stream, ozaki_amax_tensor_kernel<<<grid, 256, 0, stream>>>(x, n, amax_bits));
+    RCN_LAUNCH("ozaki_slice_tensor_kernel", stream, ozaki_slice_tensor_kernel<<<grid, 256, 0, stream>>>(x, n, amax_bits, planes, scale_out));
+    return RCN_OK;
+}
+
+int ozaki_make_conv_tensor_map(CUtensorMap* map, const int8_t* planes, int B, int Hi, int Wi, int C, int tw, int th) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(RCN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)B, (cuuint64_t)OZ_S};
+    const cuuint64_t strides[4] = {(cuuint64_t)C, (cuuint64_t)Wi * C, (cuuint64_t)Hi * Wi * C, (cuuint64_t)B * Hi * Wi * C};
+    const cuuint32_t box[5] = {(cuuint32_t)OZ_BK, (cuuint32_t)tw, (cuuint32_t)th, 1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<int8_t*>(planes), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS)
+        return fail(RCN_ERR_CUDA, "cuTensorMapEncodeTiled (conv) failed with CUresult %d (B %d, H %d, W %d, C %d, box %d x %d)", (int)rc, B, Hi, Wi, C, tw, th);
     return RCN_OK;
 }
 

@@ -75,6 +75,21 @@ struct OzOperand {
     ConvGeom g{};
 };
 
+// A operand gathered by TMA itself (convolution forward / backward-data on NHWC digit planes [S][B][Hi][Wi][C]): the M
+// tile is 128 consecutive grid pixels = a (th x tw) patch, k-block kb = (tap, 64-channel block), and the box of tap
+// (ky, kx) is the patch shifted by (ky - ph, kx - pw) -- out-of-range rows / columns are zero-filled by the TMA unit,
+// which IS the zero padding.  Requires C % 64 == 0 and a pixel grid that tiles into 128-pixel patches.
+struct OzConvA {
+    int enabled;
+    int C, kw, ph, pw, Ho, Wo;
+};
+
+// One power-of-two scale for a whole tensor (all pixels of a convolution input share the contraction scale):
+// planes[s][i] for i < n, scale_out[0] = scale.
+int ozaki_slice_tensor(const double* x, size_t n, int8_t* planes, double* scale_out, cudaStream_t stream);
+// 5-D tensor map over planes [OZ_S][B][Hi][Wi][C], box = (64 channels, tw, th, 1, 1), SWIZZLE_64B.
+int ozaki_make_conv_tensor_map(CUtensorMap* map, const int8_t* planes, int B, int Hi, int Wi, int C, int tw, int th);
+
 // Slices one operand into int8 planes [OZ_S][rows][Kp] (Kp = K rounded up to 64, zero padded) and scale[rows].
 // scale_scratch: `rows` more doubles of scratch (row maxima between the two passes of the row-contiguous variant).
 int ozaki_slice(const OzOperand& op, int rows, int K, int Kp, int8_t* planes, double* scale, double* scale_scratch,
@@ -131,6 +146,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -180,7 +201,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                                                                     const __grid_constant__ CUtensorMap map_b,
                                                                     const double* __restrict__ scale_a,
                                                                     const double* __restrict__ scale_b, int M, int N, int Kp,
-                                                                    int m_tiles, int n_tiles, int kb_per_split, Epi epi) {
+                                                                    int m_tiles, int n_tiles, int kb_per_split,
+                                                                    const OzConvA conv, Epi epi) {
     extern __shared__ unsigned char oz_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OZ_STAGES * OZ_STAGE_BYTES);
@@ -239,6 +261,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                     for (int s = 0; s < OZ_S; ++s)
                         oz::tma_load_3d_mc(sa + s * OZ_A_TILE + crank * (HALF * OZ_BK), &map_a, full_bar + stage, (kb0 + kb) * OZ_BK,
                                            m0 + (int)crank * HALF, s, (uint16_t)0x3);
+                } else if (conv.enabled) {
+                    // k-block -> (tap, channel block); tile -> (image, first row, first column) of its pixel patch
+                    const int kk = (kb0 + kb) * OZ_BK;
+                    const int tap = kk / conv.C, c0 = kk - tap * conv.C;
+                    const int ky = tap / conv.kw, kx = tap - ky * conv.kw;
+                    const int img = m0 / (conv.Ho * conv.Wo);
+                    const int rem = m0 - img * conv.Ho * conv.Wo;
+                    const int oy0 = rem / conv.Wo, ox0 = rem - oy0 * conv.Wo;
+#pragma unroll
+                    for (int s = 0; s < OZ_S; ++s)
+                        oz::tma_load_5d(sa + s * OZ_A_TILE, &map_a, full_bar + stage, c0, ox0 + kx - conv.pw, oy0 + ky - conv.ph, img, s);
                 } else {
 #pragma unroll
                     for (int s = 0; s < OZ_S; ++s) oz::tma_load_3d(sa + s * OZ_A_TILE, &map_a, full_bar + stage, (kb0 + kb) * OZ_BK, m0, s);
@@ -282,7 +315,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
         const int m = m0 + quad * 32 + lane;
         oz::mbar_wait(tmem_full_bar, 0);
         oz::tc_fence_after();
-        const double sa = (m < M) ? scale_a[m] : 0.0;
+        const double sa = (m < M) ? scale_a[conv.enabled ? 0 : m] : 0.0;   // a TMA-gathered tensor has ONE scale
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
         constexpr double kW = 1.0 / 256.0;   // 2^-8 between neighbouring diagonals
 #pragma unroll 1
@@ -378,15 +411,52 @@ static int launch_gemm_ozaki(const char* name, const OzOperand& A, const OzOpera
         cfg.attrs = at; cfg.numAttrs = 1;
         const double* sa = ws.a_scale.as<double>();
         const double* sb = ws.b_scale.as<double>();
-        RCN_LAUNCH(name, stream, cudaLaunchKernelEx(&cfg, kern, map_a, map_b, sa, sb, M, N, Kp, m_tiles, n_tiles, kb_per_split, epi));
+        const OzConvA no_conv{};
+        RCN_LAUNCH(name, stream, cudaLaunchKernelEx(&cfg, kern, map_a, map_b, sa, sb, M, N, Kp, m_tiles, n_tiles, kb_per_split, no_conv, epi));
     } else {
         auto kern = ozaki_gemm_kernel<Epi, 1>;
         static SmemAttrCache attr;
         if (attr.need(OZ_SMEM_BYTES)) RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES));
         RCN_LAUNCH(name, stream,
                    kern<<<dim3((unsigned)(m_tiles * n_tiles), (unsigned)splits), OZ_THREADS, OZ_SMEM_BYTES, stream>>>(
-                       map_a, map_b, ws.a_scale.as<double>(), ws.b_scale.as<double>(), M, N, Kp, m_tiles, n_tiles, kb_per_split, epi));
+                       map_a, map_b, ws.a_scale.as<double>(), ws.b_scale.as<double>(), M, N, Kp, m_tiles, n_tiles, kb_per_split, OzConvA{}, epi));
     }
+    return RCN_OK;
+}
+
+// Convolution forward / backward-data with the im2col done by TMA: C(pix, n) = sum_{tap, c} T[pix + tap, c] * Wk(n, (tap, c)).
+// `g` describes the gather (ConvGeom); wk is the dense [N][kh*kw*C] weight matrix (k-contiguous).  The tensor is sliced
+// ONCE, element-wise (5 B written per element instead of 45 for a materialised im2col), under one tensor-wide scale.
+inline bool ozaki_conv_tma_ok(const ConvGeom& g) {
+    const bool tiles_ok = (g.Wo <= OZ_BM && OZ_BM % g.Wo == 0 && g.Ho % (OZ_BM / g.Wo) == 0) || (g.Wo % OZ_BM == 0);
+    return g.C % OZ_BK == 0 && tiles_ok && g.n_k <= OZ_MAX_K;
+}
+
+template <typename Epi>
+static int launch_conv_ozaki(const char* name, const ConvGeom& g, int B, const double* wk, int N, const Epi& epi, OzakiWorkspace& ws,
+                             cudaStream_t stream) {
+    const int M = g.n_pix, K = g.n_k;            // K is a multiple of 64 because C is
+    if (M <= 0 || N <= 0) return RCN_OK;
+    const size_t n_elems = (size_t)B * g.Hi * g.Wi * g.C;
+    RCN_TRY(ws.a_slices.reserve((size_t)OZ_S * n_elems));
+    RCN_TRY(ws.b_slices.reserve((size_t)OZ_S * N * K));
+    RCN_TRY(ws.a_scale.reserve(2 * sizeof(double)));
+    RCN_TRY(ws.b_scale.reserve((size_t)2 * N * sizeof(double)));
+    RCN_TRY(ozaki_slice_tensor(g.t, n_elems, ws.a_slices.as<int8_t>(), ws.a_scale.as<double>(), stream));
+    const OzOperand ob{wk, (size_t)K, true};
+    RCN_TRY(ozaki_slice(ob, N, K, K, ws.b_slices.as<int8_t>(), ws.b_scale.as<double>(), ws.b_scale.as<double>() + N, stream));
+    const int tw = g.Wo < OZ_BM ? g.Wo : OZ_BM, th = OZ_BM / tw;
+    CUtensorMap map_a, map_b;
+    RCN_TRY(ozaki_make_conv_tensor_map(&map_a, ws.a_slices.as<int8_t>(), B, g.Hi, g.Wi, g.C, tw, th));
+    RCN_TRY(ozaki_make_tensor_map(&map_b, ws.b_slices.as<int8_t>(), N, K, OZ_BN));
+    auto kern = ozaki_gemm_kernel<Epi, 1>;
+    static SmemAttrCache attr;
+    if (attr.need(OZ_SMEM_BYTES)) RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES));
+    const int m_tiles = M / OZ_BM, n_tiles = (N + OZ_BN - 1) / OZ_BN;
+    const OzConvA conv{1, g.C, g.kw, g.ph, g.pw, g.Ho, g.Wo};
+    RCN_LAUNCH(name, stream,
+               kern<<<dim3((unsigned)(m_tiles * n_tiles), 1), OZ_THREADS, OZ_SMEM_BYTES, stream>>>(
+                   map_a, map_b, ws.a_scale.as<double>(), ws.b_scale.as<double>(), M, N, K, m_tiles, n_tiles, K / OZ_BK, conv, epi));
     return RCN_OK;
 }
 

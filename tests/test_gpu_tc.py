@@ -113,7 +113,8 @@ from mercer_research_b200 import ext, _lib
 rng = np.random.default_rng(61)
 out = {}
 for tag, (B, H, W, Ci, Co, kh, kw, pad) in {"same3x3": (2, 12, 10, 32, 48, 3, 3, 1), "valid": (1, 9, 11, 16, 40, 3, 3, 0),
-                                            "odd": (3, 8, 8, 20, 24, 1, 3, 1)}.items():
+                                            "odd": (3, 8, 8, 20, 24, 1, 3, 1), "tma_same": (2, 8, 16, 64, 32, 3, 3, 1),
+                                            "tma_valid": (2, 10, 18, 64, 40, 3, 3, 0), "tma_wide": (1, 4, 128, 128, 96, 3, 3, 1)}.items():
     x = np.maximum(rng.standard_normal((B, H, W, Ci)), 0)
     w = rng.standard_normal((Co, kh, kw, Ci)) / np.sqrt(kh * kw * Ci)
     b = rng.standard_normal(Co)
@@ -143,6 +144,8 @@ def test_conv_forced_through_tensor_cores_matches_oracle(built_library):
     for tag, v in r.items():
         tc = [k for k in v["kernels"] if "tcgen05" in k]
         assert len(tc) == 3, (tag, v["kernels"])
+        if tag.startswith("tma"):
+            assert any("TMA im2col" in k for k in tc), (tag, tc)
         for key in ("y", "dx", "dw", "db"):
             assert v[key] < 1e-9, (tag, key, v[key])
 
