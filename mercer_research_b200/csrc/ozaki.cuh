@@ -10,12 +10,12 @@
 // while 5 * K * 128^2 < 2^31, i.e. K <= 16384 -- and diagonals d > D are dropped: the digits are zero-mean, so what is
 // dropped adds up like sqrt(K) and stays ~6e-11 of the result for S = 5, D = 4 (15 int8 MMAs per k-step).
 //
-// Kernel (one 128 x 96 output tile per CTA, 192 threads, warp-specialised):
+// Kernel (one 128 x 96 output tile per CTA, 320 threads, warp-specialised):
 //   warp 0      TMA producer: per 64-deep k-block, 5 A-plane boxes (128 x 64 B) + 5 B-plane boxes (96 x 64 B),
 //               SWIZZLE_64B, 3-stage ring guarded by full/empty mbarriers;
 //   warp 1      TMEM allocator + MMA issuer: one elected thread issues 2 x 15 tcgen05.mma (M128 N96 K32, 8-bit -> s32)
 //               per stage into 5 TMEM accumulators (480 of 512 columns), tcgen05.commit frees the smem slot;
-//   warps 2-5   epilogue: tcgen05.ld the 5 diagonals, Horner-combine them in f64, apply the row scales and the layer's
+//   warps 2-9   epilogue: tcgen05.ld the 5 diagonals, Horner-combine them in f64, apply the row scales and the layer's
 //               epilogue functor (bias + sigmoid, sigmoid', store ...), coalesced column-major stores.
 // Measured limiter (profiles/): the tensor core's operand fetch from shared memory (SS-mode MMA reads the 128-row A
 // tile for every instruction), not L2 or HBM -- hence the widest N tile TMEM allows and the fewest digit planes.
@@ -36,7 +36,7 @@ constexpr int OZ_A_TILE = OZ_BM * OZ_BK;       // bytes of one A slice tile
 constexpr int OZ_B_TILE = OZ_BN * OZ_BK;
 constexpr int OZ_STAGE_BYTES = OZ_S * (OZ_A_TILE + OZ_B_TILE);
 constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-constexpr int OZ_THREADS = 192;
+constexpr int OZ_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 constexpr int OZ_TMEM_COLS = 512;
 
 struct OzakiWorkspace {
@@ -310,8 +310,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
             oz::tc_commit(tmem_full_bar);               // accumulators complete
         }
     } else {
-        // ===== epilogue (warps 2..5): TMEM lane quadrant = warp % 4 =====
+        // ===== epilogue (warps 2..9): TMEM lane quadrant = warp % 4, the two warps of a quadrant split the columns =====
         const int quad = warp & 3;
+        const int col_half = (warp - 2) >> 2;
         const int m = m0 + quad * 32 + lane;
         oz::mbar_wait(tmem_full_bar, 0);
         oz::tc_fence_after();
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
         constexpr double kW = 1.0 / 256.0;   // 2^-8 between neighbouring diagonals
 #pragma unroll 1
-        for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+        for (int c0 = col_half * (OZ_BN / 2); c0 < (col_half + 1) * (OZ_BN / 2); c0 += 16) {
             double acc[16];
             {
                 int32_t v[16];
