@@ -114,7 +114,7 @@ struct rcn_cuda_model {
     FeatureScratch fscratch;
 
     // scratch (grow-only)
-    DevBuf in_stage, tgt_stage, feats, acts, deltas, gemm_ws, out_stage, small, red_ws, sn_counters;
+    DevBuf in_stage, tgt_stage, feats, acts, deltas, gemm_ws, out_stage, small, red_ws;
     ReduceScratch rs;           // deterministic two-stage reductions (bias gradient, batch statistics)
     // epoch mode (rcn.rs:144-149 on a resident dataset)
     const void* ep_images = nullptr;
@@ -381,7 +381,7 @@ int rcn_cuda_destroy(rcn_cuda_handle h) {
     dp_release(h->dp);
     h->oz.release();
     DevBuf* bufs[] = {&h->params, &h->grads_own, &h->in_stage, &h->tgt_stage, &h->feats, &h->acts, &h->deltas,
-                      &h->gemm_ws, &h->out_stage, &h->small, &h->red_ws, &h->ep_state, &h->sn_counters, &h->fscratch.a, &h->fscratch.b, &h->rs.buf};
+                      &h->gemm_ws, &h->out_stage, &h->small, &h->red_ws, &h->ep_state, &h->fscratch.a, &h->fscratch.b, &h->rs.buf};
     for (DevBuf* b : bufs) b->release();
     delete h;
     return RCN_OK;

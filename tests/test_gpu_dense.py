@@ -461,3 +461,68 @@ def test_train_arrays_matches_oracle_epoch_loop(api, graph):
     assert_close(model.get_params(), p, rtol=1e-9, what="parameters after the epoch loop")
     gm, gs = model.scale_set
     assert abs(gm - mte[0]) <= 1e-12 * mte[0] and abs(gs - mte[1]) <= 1e-12 * mte[1]
+
+
+def test_train_epoch_host_contract(api):
+    """Argument contract of the host-dataset loop: chunks_exact drops a short tail entirely (rcn.rs:147), device buffers are
+    rejected, a wrong feature width is the reference's dimension-mismatch panic, state errors come back as status codes."""
+    import torch
+    cfg = [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max)]
+    model = api.RCN(10, cfg, [30])
+    images = np.zeros((5, 28, 28), dtype=np.uint8)
+    labels = np.zeros(5, dtype=np.int64)
+    with pytest.raises(api.RcnCudaError) as e:
+        model.train_epoch_host(images, labels, 4, 3.0)                       # no parameters yet
+    assert e.value.status == 5
+    model.load_weights_and_bias(784)
+    before = model.get_params()
+    cost, hits = model.train_epoch_host(images, labels, 8, 3.0)              # fewer samples than one batch: no step at all
+    assert len(cost) == 0 and np.array_equal(model.get_params(), before)
+    cost, hits = model.train_epoch_host(images, labels, 2, 3.0)              # 5 samples, batch 2 -> 2 steps, last sample dropped
+    assert len(cost) == 2 and hits.dtype == np.uint64
+    with pytest.raises(api.RcnCudaError) as e:
+        api._lib.check(model._lib.rcn_cuda_train_epoch_host(model._h, torch.zeros(4, 28, 28, dtype=torch.uint8, device="cuda").data_ptr(),
+                                                            0, labels.ctypes.data, 4, 28, 28, 2, 3.0, 0, None, None, None))
+    assert e.value.status == 1
+    wrong = api.RCN(10, cfg, [30])
+    wrong.load_weights_and_bias(100)                                        # first layer expects 100 inputs, features are 784
+    with pytest.raises(api.RcnCudaError) as e:
+        wrong.train_epoch_host(images, labels, 2, 3.0)
+    assert e.value.status == 2 and "mismatch" in e.value.message
+
+
+def test_dp_group_contract(api):
+    cfg = [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max)]
+    model = api.RCN(10, cfg, [30])
+    with pytest.raises(api.RcnCudaError) as e:
+        model.dp_init(2, 0)                                                  # needs parameters (the block is sized by them)
+    assert e.value.status == 5
+    model.load_weights_and_bias(784)
+    for world, rank in [(0, 0), (2, 2), (17, 0), (2, -1)]:
+        with pytest.raises(api.RcnCudaError) as e:
+            model.dp_init(world, rank)
+        assert e.value.status == 1
+    handle = model.dp_init(1, 0)
+    assert len(handle) == 64
+    model.dp_connect_ipc([handle])                                          # a world of one is a no-op group
+    model.set_params(np.zeros(model.n_params))
+    model.train_batch_images(np.zeros((4, 28, 28), dtype=np.uint8), np.zeros(4, dtype=np.int64), 3.0)
+    model.dp_shutdown()
+    other = api.RCN(10, cfg, [30])
+    other.load_weights_and_bias(784)
+    with pytest.raises(api.RcnCudaError) as e:
+        other.dp_connect_ipc([handle])                                      # connect before init
+    assert e.value.status == 5
+
+
+def test_wide_layer_beyond_exact_int32_range_stays_on_dmma(api):
+    """K > 16384 cannot use the integer-slice path (int32 accumulation bound): the layer runs on DMMA and still matches."""
+    from mercer_research_b200 import ext
+    rng = np.random.default_rng(71)
+    a = rng.standard_normal((130, 16500))
+    b = rng.standard_normal((16500, 70))
+    got = ext.gemm_f64(a, b, impl=0)
+    assert_close(got, a @ b, rtol=1e-9, what="dmma, deep K")
+    with pytest.raises(api.RcnCudaError) as e:
+        ext.gemm_f64(a, b, impl=1)
+    assert e.value.status == 1 and "exact int32" in e.value.message
