@@ -177,7 +177,9 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
  *                    cudaIpcMemHandle_t for ranks living in other processes.
  *   dp_connect_ipc   all_handles = world x 64 bytes, the handles of ranks 0..world-1 (own entry ignored).
  *   dp_connect_local group = world handles living in THIS process (one per device; peer access is enabled).
- * Every rank must execute the same sequence of apply calls. */
+ * Every rank must execute the same sequence of apply calls, and in a connected group every accumulate must be followed by
+ * exactly one apply before the next accumulate (the fused small-network kernels already push their gradients to the peers
+ * at the end of accumulate, so that the exchange overlaps the launch of the update). */
 int rcn_cuda_dp_init(rcn_cuda_handle h, int world, int rank, void* ipc_handle_out);
 int rcn_cuda_dp_connect_ipc(rcn_cuda_handle h, const void* all_handles);
 int rcn_cuda_dp_connect_local(rcn_cuda_handle h, const rcn_cuda_handle* group);

@@ -58,6 +58,17 @@ void dp_release(DpState& st) {
     cudaGetLastError();
 }
 
+static_assert(kDpCtrlBytes == kDpCtrlBytesPub, "slot offset mismatch");
+
+DpPush dp_push_desc(const DpState& st) {
+    DpPush d{};
+    d.world = st.connected ? st.world : 1;
+    d.rank = st.rank;
+    d.n = st.n;
+    for (int q = 0; q < st.world && q < kDpMaxWorld; ++q) d.peers[q] = (char*)st.peers[q];
+    return d;
+}
+
 struct DpPeers { char* p[kDpMaxWorld]; };
 
 constexpr unsigned long long kDpSentinel = 0xFFFFFFFFFFFFFFFFull;
@@ -74,7 +85,7 @@ __global__ void __launch_bounds__(256) dp_allreduce_sgd_kernel(const DpPeers pee
                                                                double* __restrict__ params, double* __restrict__ grads,
                                                                double scale, long long* __restrict__ cursor, long long batch,
                                                                long long n_samples, const double* __restrict__ stats,
-                                                               double* __restrict__ stats_ring) {
+                                                               double* __restrict__ stats_ring, int already_pushed) {
     const int world = WORLD ? WORLD : world_rt;
     char* self = peers.p[rank];
     DpCtrl* ctrl = reinterpret_cast<DpCtrl*>(self);
@@ -92,11 +103,13 @@ __global__ void __launch_bounds__(256) dp_allreduce_sgd_kernel(const DpPeers pee
         g[e] = 0.0;
         if (i < hi) {
             g[e] = grads[i];
-            unsigned long long bits = (unsigned long long)__double_as_longlong(g[e]);
-            if (bits == kDpSentinel) bits = kDpQuietNaN;          // a NaN either way; never send the sentinel itself
-            for (int q = 0; q < world; ++q)
-                if (q != rank)
-                    reinterpret_cast<unsigned long long*>(peers.p[q] + kDpCtrlBytes)[par_off + (size_t)rank * n + i] = bits;
+            if (!already_pushed) {
+                unsigned long long bits = (unsigned long long)__double_as_longlong(g[e]);
+                if (bits == kDpSentinel) bits = kDpQuietNaN;          // a NaN either way; never send the sentinel itself
+                for (int q = 0; q < world; ++q)
+                    if (q != rank)
+                        reinterpret_cast<unsigned long long*>(peers.p[q] + kDpCtrlBytes)[par_off + (size_t)rank * n + i] = bits;
+            }
         }
     }
     // ---- receive: poll my elements of every peer's slot in my own block, restore the sentinel, add in rank order ------
@@ -146,7 +159,8 @@ __global__ void __launch_bounds__(256) dp_allreduce_sgd_kernel(const DpPeers pee
 }
 
 int launch_dp_allreduce_sgd(const DpState& st, double* params, double* grads, double scale, cudaStream_t stream,
-                            long long* cursor, long long batch, long long n_samples, const double* stats, double* stats_ring) {
+                            long long* cursor, long long batch, long long n_samples, const double* stats, double* stats_ring,
+                            bool already_pushed) {
     if (!st.connected) return fail(RCN_ERR_STATE, "data-parallel group is not connected");
     if (st.n == 0) return RCN_OK;
     DpPeers pp{};
@@ -155,7 +169,7 @@ int launch_dp_allreduce_sgd(const DpState& st, double* params, double* grads, do
 #define RCN_DP_LAUNCH(W)                                                                                                       \
     RCN_LAUNCH("dp_allreduce_sgd_kernel", stream,                                                                              \
                dp_allreduce_sgd_kernel<W><<<grid, 256, 0, stream>>>(pp, st.world, st.rank, st.n, params, grads, scale, cursor, \
-                                                                   batch, n_samples, stats, stats_ring))
+                                                                   batch, n_samples, stats, stats_ring, already_pushed ? 1 : 0))
     switch (st.world) {
         case 2: RCN_DP_LAUNCH(2); break;
         case 4: RCN_DP_LAUNCH(4); break;

@@ -18,14 +18,39 @@ struct DpState {
     bool imported[kDpMaxWorld] = {};       // mapped with cudaIpcOpenMemHandle (must be closed)
 };
 
+// Handed to a gradient-producing kernel so that it can PUSH its final gradient values into the peers' receive slots
+// itself (the exchange then overlaps that kernel's tail and the next launch); world == 1 means "do not push".
+struct DpPush {
+    char* peers[kDpMaxWorld];
+    int world, rank;
+    unsigned long long n;
+};
+DpPush dp_push_desc(const DpState& st);
+constexpr size_t kDpCtrlBytesPub = 256;   // offset of the receive slots inside a communication block
+
+// Device side of the push: slot [step parity][my rank][i] on every peer = v (the sentinel itself is never sent).
+__device__ __forceinline__ void dp_push_value(const DpPush& dp, size_t par_off, size_t i, double v) {
+    unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    if (bits == 0xFFFFFFFFFFFFFFFFull) bits = 0x7FF8000000000000ull;
+    for (int q = 0; q < dp.world; ++q)
+        if (q != dp.rank)
+            reinterpret_cast<unsigned long long*>(dp.peers[q] + kDpCtrlBytesPub)[par_off + (size_t)dp.rank * dp.n + i] = bits;
+}
+// parity offset of the step this rank is about to exchange (reads the device-side step counter of its own block)
+__device__ __forceinline__ size_t dp_push_parity_offset(const DpPush& dp) {
+    const long long step = *reinterpret_cast<volatile long long*>(dp.peers[dp.rank]) + 1;
+    return (size_t)(step & 1) * dp.world * dp.n;
+}
+
 size_t dp_block_bytes(int world, size_t n);
 int dp_alloc(DpState& st, int world, int rank, size_t n, cudaStream_t stream);
 void dp_release(DpState& st);
 
 // params[i] -= scale * sum_r grads_r[i], r ascending, identical on every rank; grads[i] <- the global sum.
 // cursor / batch / n_samples: optional epoch cursor advanced like sgd_update_kernel does.
+// already_pushed: the gradient kernel pushed this step's values itself (DpPush); the kernel then only receives.
 int launch_dp_allreduce_sgd(const DpState& st, double* params, double* grads, double scale, cudaStream_t stream,
                             long long* cursor, long long batch, long long n_samples, const double* stats = nullptr,
-                            double* stats_ring = nullptr);
+                            double* stats_ring = nullptr, bool already_pushed = false);
 
 }  // namespace rcn

@@ -127,6 +127,8 @@ struct rcn_cuda_model {
     bool stats_valid = false;
     // data-parallel group (dp.cu) and the pipelined host-dataset loop (rcn_cuda_train_epoch_host)
     DpState dp;
+    bool dp_pushed = false;         // the last accumulate pushed its gradients to the peers itself (kernel B epilogue)
+    bool dp_push_suppress = false;  // warm-up launches must not push (a push is consumed by exactly one receive)
     OzakiWorkspace oz;              // tcgen05 integer-slice GEMM scratch (wide dense layers)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
@@ -177,6 +179,18 @@ struct DeviceGuard {
     if (!(h)) return fail(RCN_ERR_INVALID, "null model handle");                         \
     DeviceGuard _guard((h)->device);                                                     \
     if (!_guard.ok) return fail(RCN_ERR_CUDA, "cudaSetDevice(%d) failed", (h)->device);
+
+bool dp_fused_push_enabled() {
+    static const bool on = []() { const char* e = getenv("RCN_CUDA_DP_FUSED_PUSH"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+// Consumes the "already pushed" flag of the last accumulate: every push is matched by exactly one receive.
+bool take_dp_pushed(rcn_cuda_model* h) {
+    const bool p = h->dp_pushed;
+    h->dp_pushed = false;
+    return p;
+}
 
 int ensure_plan(rcn_cuda_model* h, size_t H, size_t W) {
     if (h->plan_valid && h->plan_H == H && h->plan_W == W) return RCN_OK;
@@ -239,6 +253,9 @@ int forward_dev(rcn_cuda_model* h, const double* feats, size_t B, const double* 
 int accumulate_dev(rcn_cuda_model* h, const double* feats, const double* onehot, const int64_t* labels, size_t B,
                    const SmallNetFront* front = nullptr) {
     const size_t n = h->rows.size();
+    if (h->dp_pushed)   // a pushed gradient must be received by the group's update before the next one is produced
+        return fail(RCN_ERR_STATE, "data-parallel group: the previous gradients were pushed to the peers but never applied "
+                                   "(every accumulate needs exactly one apply on every rank)");
     if (B == 0) {
         RCN_CUDA_TRY(cudaMemsetAsync(h->grads, 0, h->n_params * sizeof(double), h->stream));
         return RCN_OK;
@@ -247,9 +264,13 @@ int accumulate_dev(rcn_cuda_model* h, const double* feats, const double* onehot,
         RCN_TRY(h->acts.reserve(h->sum_rows * B * sizeof(double)));
         RCN_TRY(h->deltas.reserve(h->sum_rows * B * sizeof(double)));
         RCN_TRY(h->small.reserve(64));
+        DpPush push{};
+        const bool fuse_push = h->dp.connected && dp_fused_push_enabled() && !h->dp_push_suppress;
+        if (fuse_push) push = dp_push_desc(h->dp);
         RCN_TRY(launch_smallnet_backprop(h->small_desc, h->params.as<double>(), const_cast<double*>(feats), B, onehot,
                                          labels, h->acts.as<double>(), h->deltas.as<double>(), h->grads,
-                                         h->small.as<double>(), h->gemm_ws, front, h->stream));
+                                         h->small.as<double>(), h->gemm_ws, front, h->stream, fuse_push ? &push : nullptr));
+        h->dp_pushed = fuse_push;
         h->stats_valid = true;
         h->last_B = B;
         return RCN_OK;
@@ -733,7 +754,8 @@ int rcn_cuda_apply_gradients(rcn_cuda_handle h, double eta, size_t batch) {
     if (batch == 0) return RCN_OK;  // chunks_exact never yields an empty batch (rcn.rs:147)
     const double scale = eta / (double)batch;  // (eta / batch.len() as f64)  (rcn.rs:214)
     if (h->dp.connected)   // exchange over NVLink peer memory fused with the update (dp.cu)
-        return launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale, h->stream, nullptr, 0, 0);
+        return launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale, h->stream, nullptr, 0, 0, nullptr, nullptr,
+                                       take_dp_pushed(h));
     return launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale, h->stream);
 }
 
@@ -819,7 +841,7 @@ int rcn_cuda_epoch_apply(rcn_cuda_handle h, double eta, size_t global_batch) {
     const double scale = eta / (double)global_batch;
     if (h->dp.connected)
         return launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale, h->stream, h->ep_state.as<long long>(),
-                                       (long long)h->ep_B, (long long)h->ep_n);
+                                       (long long)h->ep_B, (long long)h->ep_n, nullptr, nullptr, take_dp_pushed(h));
     return launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale, h->stream, h->ep_state.as<long long>(),
                              (long long)h->ep_B, (long long)h->ep_n);
 }
@@ -909,7 +931,10 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
             if (!h->hs_graph || !(key == h->hs_key)) {
                 if (h->hs_graph) { cudaGraphExecDestroy(h->hs_graph); h->hs_graph = nullptr; }
                 // warm-up outside capture: reserves every scratch buffer and sets kernel attributes (no parameter update)
-                RCN_TRY(accumulate_images_dev(h, h->hs_ring.p, pixel_format, nullptr, B, H, W, &bi));
+                h->dp_push_suppress = true;
+                const int wrc = accumulate_images_dev(h, h->hs_ring.p, pixel_format, nullptr, B, H, W, &bi);
+                h->dp_push_suppress = false;
+                RCN_TRY(wrc);
                 RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
                 cudaGraph_t graph = nullptr;
                 RCN_CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -927,7 +952,7 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
                     if (cudaStreamWaitEvent(h->stream, h->hs_join, 0) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph join failed"); break; }
                     if (h->dp.connected)
                         rc = launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale_s, h->stream, st, (long long)B,
-                                                     (long long)(n_steps * B), h->small.as<double>(), h->stats_host);
+                                                     (long long)(n_steps * B), h->small.as<double>(), h->stats_host, take_dp_pushed(h));
                     else
                         rc = launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale_s, h->stream, st, (long long)B,
                                                (long long)(n_steps * B), h->small.as<double>(), h->stats_host);
@@ -975,7 +1000,8 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
         RCN_TRY(accumulate_images_dev(h, dst, pixel_format, labels_dev + k * B, B, H, W, nullptr));
         RCN_CUDA_TRY(cudaEventRecord(h->ev_consumed[slot], h->stream));
         if (h->dp.connected)
-            RCN_TRY(launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale, h->stream, nullptr, 0, 0));
+            RCN_TRY(launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale, h->stream, nullptr, 0, 0, nullptr, nullptr,
+                                            take_dp_pushed(h)));
         else
             RCN_TRY(launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale, h->stream));
         // D2H of this step's result (cost, hits evaluated with the pre-update parameters)
@@ -1050,6 +1076,7 @@ int rcn_cuda_dp_shutdown(rcn_cuda_handle h) {
     RCN_ENTER(h);
     RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
     dp_release(h->dp);
+    h->dp_pushed = false;
     return RCN_OK;
 }
 

@@ -19,6 +19,7 @@
 //        group to finish (atomic ticket) sums the K-split partials in a FIXED order into the flat gradient buffer
 //        (the all-reduce target) -- deterministic, unlike the reference's mutex-ordered sum (rcn.rs:190-205).
 #include "smallnet.cuh"
+#include "dp.cuh"
 
 #include "features_device.cuh"
 
@@ -321,13 +322,14 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
 // ------------------------------------------------------------------------------------------------
 constexpr int SNB_TILE = 32 * 64;   // padded partial tile: 32 rows x 64 columns
 
+template <bool DP>   // DP: also push the final values into the data-parallel peers' receive slots (dp.cu protocol)
 __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __grid_constant__ SmallNetDesc d,
                                                                      const double* __restrict__ feats,
                                                                      const double* __restrict__ small_partial,
                                                                      const double* __restrict__ deltas, int B, int ksplit,
                                                                      int col_groups, double* __restrict__ grads,
                                                                      const double* __restrict__ stats_partial, int n_stat,
-                                                                     double* __restrict__ stats) {
+                                                                     double* __restrict__ stats, const __grid_constant__ DpPush dp) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ __align__(16) double sD[2][64 * SN_DPITCH];   // double-buffered 64-sample delta_0 chunk (36 KB)
@@ -413,6 +415,9 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
     const int n_out = is_col ? SNB_TILE : n_small;
     const int per = (n_out + S - 1) / S;
     const int o_lo = rank * per, o_hi = min(n_out, o_lo + per);
+    // data-parallel group: the final values also go straight into the peers' receive slots (dp.cu protocol), so the
+    // exchange overlaps this kernel's tail and the launch of the update kernel
+    const size_t dp_par = DP ? dp_push_parity_offset(dp) : 0;
     for (int o = o_lo + tid; o < o_hi; o += SNB_THREADS) {
         double s = 0.0;
         for (int q = 0; q < S; ++q) {
@@ -421,9 +426,14 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
         }
         if (is_col) {
             const int m = o & 31, col = blockIdx.x * 64 + (o >> 5);
-            if (m < R0 && col < L) grads[d.w_off[0] + (size_t)col * R0 + m] = s;
+            if (m < R0 && col < L) {
+                const size_t gi = d.w_off[0] + (size_t)col * R0 + m;
+                grads[gi] = s;
+                if (DP) dp_push_value(dp, dp_par, gi, s);
+            }
         } else {
             grads[small_base + o] = s;
+            if (DP) dp_push_value(dp, dp_par, (size_t)(small_base + o), s);
         }
     }
     if (!is_col && rank == 0 && tid < 32 && stats) {
@@ -511,7 +521,7 @@ int launch_smallnet_forward(const SmallNetDesc& d, const double* params, double*
 
 int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double* feats, size_t B, const double* onehot,
                              const int64_t* labels, double* acts, double* deltas, double* grads, double* stats,
-                             DevBuf& workspace, const SmallNetFront* front, cudaStream_t stream) {
+                             DevBuf& workspace, const SmallNetFront* front, cudaStream_t stream, const DpPush* dp_push) {
     if (B == 0) return RCN_OK;
     if (B > smallnet_max_batch()) return fail(RCN_ERR_INVALID, "batch too large for the fused small-network path");
     int splits, ksplit;
@@ -526,9 +536,15 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
     RCN_TRY(launch_kernel_a(d, params, feats, B, onehot, labels, acts, deltas, stats_partial, small_partial, 1, front, stream));
 
     const size_t smem_b = (size_t)(n_small > SNB_TILE ? n_small : SNB_TILE) * sizeof(double);
-    static SmemAttrCache attr_b;
-    if (attr_b.need(smem_b))   // static 36 KB + dynamic tile exceeds the 48 KB default
-        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    DpPush push{};
+    push.world = 1;
+    if (dp_push) push = *dp_push;
+    const bool with_push = push.world > 1;
+    static SmemAttrCache attr_b[2];
+    if (attr_b[with_push].need(smem_b)) {  // static 36 KB + dynamic tile exceeds the 48 KB default
+        if (with_push) RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        else RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(col_groups + 1, splits, 1);
     cfg.blockDim = dim3(SNB_THREADS, 1, 1);
@@ -542,10 +558,17 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const int Bi = (int)B;
-    RCN_LAUNCH("smallnet_wgrad_kernel", stream,
-               cudaLaunchKernelEx(&cfg, smallnet_wgrad_kernel, d, (const double*)feats, (const double*)small_partial,
-                                  (const double*)deltas, Bi, ksplit, col_groups, grads, (const double*)stats_partial, n_tiles,
-                                  stats));
+    if (with_push) {
+        RCN_LAUNCH("smallnet_wgrad_kernel", stream,
+                   cudaLaunchKernelEx(&cfg, smallnet_wgrad_kernel<true>, d, (const double*)feats, (const double*)small_partial,
+                                      (const double*)deltas, Bi, ksplit, col_groups, grads, (const double*)stats_partial, n_tiles,
+                                      stats, push));
+    } else {
+        RCN_LAUNCH("smallnet_wgrad_kernel", stream,
+                   cudaLaunchKernelEx(&cfg, smallnet_wgrad_kernel<false>, d, (const double*)feats, (const double*)small_partial,
+                                      (const double*)deltas, Bi, ksplit, col_groups, grads, (const double*)stats_partial, n_tiles,
+                                      stats, push));
+    }
     return RCN_OK;
 }
 

@@ -5,6 +5,8 @@
 
 namespace rcn {
 
+struct DpPush;   // dp.cuh: peers' receive slots, when the weight-gradient kernel pushes the exchange itself
+
 constexpr int kSmallNetMaxLayers = 4;
 
 struct SmallNetDesc {
@@ -38,6 +40,7 @@ int launch_smallnet_forward(const SmallNetDesc& d, const double* params, double*
 // (quadratic cost, hit count as uint64 bits).
 int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double* feats, size_t B, const double* onehot,
                              const int64_t* labels, double* acts, double* deltas, double* grads, double* stats,
-                             DevBuf& workspace, const SmallNetFront* front, cudaStream_t stream);
+                             DevBuf& workspace, const SmallNetFront* front, cudaStream_t stream,
+                             const DpPush* dp_push = nullptr);
 
 }  // namespace rcn
