@@ -129,6 +129,41 @@ def test_features_u8_bit_exact(api, cfg, hw):
     assert bits_equal(model.flatten_feature_set(imgs.astype(np.float64)), want)
 
 
+@pytest.mark.parametrize("cfg", [[1, 3], [1, 3, 1, 3], [1, 3, 1, 3, 1, 3]])
+@pytest.mark.parametrize("hw", [(64, 64), (12, 20), (20, 12), (28, 28), (8, 4), (4, 4), (33, 32)])
+def test_features_staged_kernel_bit_exact(api, cfg, hw):
+    """The bulk-async staged kernel (u8, conv(Same)+pool stacks, W % 4 == 0): more images than resident CTAs so every
+    CTA walks several images through its double-buffered staging ring; with and without the standardise epilogue
+    (IEEE and host-verified fast division), contiguous and 1-byte-offset (non-bulk) sources."""
+    import torch
+    rng = np.random.default_rng(hw[0] * 1000 + hw[1] + len(cfg))
+    B = 2500 if hw[0] * hw[1] <= 1024 else 1300
+    imgs = rng.integers(0, 256, size=(B,) + hw, dtype=np.uint8)
+    imgs[0] = 255; imgs[1] = 0; imgs[2, ::2] = 255; imgs[2, 1::2] = 0
+    try:
+        want = O.features_u8(cfg, imgs)
+    except O.RefPanic:
+        model = api.RCN(10, layers(api, cfg), [30])
+        with pytest.raises(api.RcnCudaError):
+            model.flatten_feature_set(imgs)
+        return
+    model = api.RCN(10, layers(api, cfg), [30])
+    assert bits_equal(model.flatten_feature_set(imgs), want)
+    mean, sd = O.gen_scales(want)
+    if sd > 0:
+        model.scale_set = (mean, sd)
+        assert bits_equal(model.flatten_feature_set(imgs, standardise=True), O.standardise(want, mean, sd))
+        model.scale_set = (mean * 1.0000001, sd * 0.9999999)     # a pair the fast-division check may reject
+        assert bits_equal(model.flatten_feature_set(imgs, standardise=True),
+                          O.standardise(want, mean * 1.0000001, sd * 0.9999999))
+    # misaligned device source: the kernel falls back from bulk copies to plain loads into the same staging ring
+    flat = torch.zeros(imgs.size + 1, dtype=torch.uint8, device="cuda")
+    flat[1:] = torch.from_numpy(imgs.reshape(-1)).cuda()
+    shifted = flat[1:].view(B, *hw)
+    assert shifted.data_ptr() % 16 != 0
+    assert bits_equal(model.flatten_feature_set(shifted).cpu().numpy(), want)
+
+
 def test_features_f64_arbitrary_values(api):
     """Non-integer pixels: the f64 path keeps the reference's accumulation order, so it is still bit-exact."""
     rng = np.random.default_rng(17)
