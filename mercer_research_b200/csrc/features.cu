@@ -120,159 +120,7 @@ __global__ void __launch_bounds__(256) features_fused_kernel(const TIN* __restri
 // loads without a single bounds test; the only global traffic is the image read and the coalesced feature write.
 // Arithmetic is the same exact int32 closed form as conv_pool_same_int (bit-identical to the reference's f64).
 // ------------------------------------------------------------------------------------------------
-constexpr int kCpMaxStages = 8;
-struct CpStage {
-    int n_in, h, w;          // input maps of this stage
-    int hp, map_elems;       // padded column pitch (even), padded elements per map
-    int h_out, w_out;        // pooled output size
-    int off;                 // offset (ints) of this stage's input tile in shared memory
-    unsigned magic_hw, magic_h;   // ceil(2^32 / (h_out*w_out)), ceil(2^32 / h_out)
-};
-struct CpPlan {
-    CpStage s[kCpMaxStages];
-    int n;
-    int stage_bytes;         // one u8 staging buffer (H*W rounded up to 16)
-    int tile_ints;           // all padded tiles
-    unsigned magic_w4;       // ceil(2^32 / (W/4))
-};
-
-__host__ __device__ __forceinline__ int cp_pitch(int h) { return (h + 4) & ~1; }   // rows -2 .. h (+1 to stay even)
-__host__ __device__ __forceinline__ int cp_cols(int w) { return w + 3; }            // cols -2 .. w
-
-static unsigned cp_magic(unsigned d) { return d <= 1 ? 0u : (unsigned)(0xFFFFFFFFu / d) + 1u; }
-__device__ __forceinline__ int cp_div(int n, int d, unsigned magic) { return d == 1 ? n : (int)__umulhi((unsigned)n, magic); }
-
-namespace cpbulk {
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// 1-D bulk-async copy global -> shared, completion counted in bytes on `bar` (16-byte aligned, size % 16 == 0)
-__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-}  // namespace cpbulk
-
-// integer feature value -> f64 (exact: v < 2^31) -> optional standardise + clamp (rcn.rs:407-412)
-__device__ __forceinline__ double cp_finish(int v, const Standardise& sc) {
-    double d = __hiloint2double(0x43300000, v) - 4503599627370496.0;   // (2^52 + v) - 2^52 == (double)v for 0 <= v < 2^31
-    if (sc.mode == 1) {
-        d = (d - sc.mean) / sc.sd;
-        d = (d >= 0.0) ? d : 0.0;
-    } else if (sc.mode == 2) {   // host-verified exact Markstein division, see EmitFeatures
-        const double a = d - sc.mean;
-        const double q = __dmul_rn(a, sc.rcp);
-        const double rem = fma(-q, sc.sd, a);
-        d = fma(rem, sc.rcp, q);
-        d = (d >= 0.0) ? d : 0.0;
-    }
-    return d;
-}
-
-// One conv(Same)+pool stage over padded int32 tiles.  LAST: write standardised features to `gout` (flatten order
-// rcn.rs:350-355); otherwise write the next stage's padded tile `nxt` (its last column is left at zero).
-template <bool LAST>
-__device__ __forceinline__ void cp_run_stage(const CpStage& st, bool first, const int* __restrict__ in, int* __restrict__ nxt,
-                                             int nxt_hp, int nxt_map, double* __restrict__ gout, const Standardise& sc,
-                                             int tid, int nt) {
-    const int hw_out = st.h_out * st.w_out;
-    const int items = st.n_in * hw_out;
-    for (int it = tid; it < items; it += nt) {
-        const int i = cp_div(it, hw_out, st.magic_hw);
-        const int rem = it - i * hw_out;
-        const int x = cp_div(rem, st.h_out, st.magic_h);
-        const int y = rem - x * st.h_out;
-        // padded coordinates: image (row r, col c) sits at [(c + 2) * hp + r + 2]; the patch starts at (2y-2, 2x-2)
-        const int* f = in + i * st.map_elems + (2 * x) * st.hp + 2 * y;
-        int p[4][4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int2 a = *reinterpret_cast<const int2*>(f + k * st.hp);
-            const int2 b = *reinterpret_cast<const int2*>(f + k * st.hp + 2);
-            p[0][k] = a.x; p[1][k] = a.y; p[2][k] = b.x; p[3][k] = b.y;
-        }
-        // conv row 2y+a is zero for row 0 and beyond the map (the pool's zero padding, kernel.rs:253-261)
-        const bool rok0 = y > 0, rok1 = 2 * y + 1 < st.h;
-        const bool cok1 = 2 * x + 1 < st.w;
-        int tmax = 0, tmin = 0, lmax = 0, lmin = 0;
-#pragma unroll
-        for (int a = 0; a < 2; ++a) {
-            int vT[4], vS[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                vT[k] = p[a][k] - p[a + 2][k];
-                vS[k] = p[a][k] + 2 * p[a + 1][k] + p[a + 2][k];
-            }
-            const bool rok = a ? rok1 : rok0;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const bool ok = rok && (e ? cok1 : true);
-                const int T = ok ? vT[e] + 2 * vT[e + 1] + vT[e + 2] : 0;
-                const int L = ok ? vS[e] - vS[e + 2] : 0;
-                tmax = max(tmax, T); tmin = min(tmin, T);
-                lmax = max(lmax, L); lmin = min(lmin, L);
-            }
-        }
-        const int t = tmax, b = -tmin, l = lmax, r = -lmin;
-        int sT, sL, sR, sB;   // slot order rcn.rs:325-339
-        if (first) { sT = 0; sL = 1; sR = 2; sB = 3; }
-        else { sB = i; sT = st.n_in + 3 * i; sL = sT + 1; sR = sT + 2; }
-        if (LAST) {
-            const int o = x * st.h_out + y;
-            gout[sT * hw_out + o] = cp_finish(t, sc);
-            gout[sL * hw_out + o] = cp_finish(l, sc);
-            gout[sR * hw_out + o] = cp_finish(r, sc);
-            gout[sB * hw_out + o] = cp_finish(b, sc);
-        } else if (x < st.w_out - 1) {
-            const int o = (x + 2) * nxt_hp + y + 2;
-            nxt[sT * nxt_map + o] = t;
-            nxt[sL * nxt_map + o] = l;
-            nxt[sR * nxt_map + o] = r;
-            nxt[sB * nxt_map + o] = b;
-        }
-    }
-}
-
-// u8 row-major staging buffer -> padded int32 column-major tile (lib.rs:29-33 layout change).  Lane l of a warp task
-// takes row r0 + l and word (l + it) mod W/4 of that row: the 4-byte reads and the four column-strided writes are both
-// bank-conflict free.  Column W-1 is never read downstream and stays zero.
-__device__ __forceinline__ void cp_transpose_image(const uint8_t* __restrict__ stg, int* __restrict__ tile, int H, int W,
-                                                   int hp, unsigned magic_w4, int tid, int nt) {
-    const int W4 = W >> 2;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-    const int rgroups = (H + 31) >> 5;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(stg);
-    for (int task = warp; task < rgroups * W4; task += nwarps) {
-        const int rg = cp_div(task, W4, magic_w4);
-        const int it = task - rg * W4;
-        const int r = rg * 32 + lane;
-        int j = lane + it;
-        j -= cp_div(j, W4, magic_w4) * W4;
-        if (r < H) {
-            const uint32_t v = src[r * W4 + j];
-            int* dst = tile + (4 * j + 2) * hp + r + 2;
-            dst[0] = (int)(v & 0xffu);
-            dst[hp] = (int)((v >> 8) & 0xffu);
-            dst[2 * hp] = (int)((v >> 16) & 0xffu);
-            if (4 * j + 3 < W - 1) dst[3 * hp] = (int)(v >> 24);
-        }
-    }
-}
-
+template <int MODE>
 __global__ void __launch_bounds__(256) features_cp_kernel(const uint8_t* __restrict__ images, int B, int H, int W,
                                                          const __grid_constant__ CpPlan cp, double* __restrict__ out,
                                                          size_t L, const Standardise sc, const BatchIndex bi, int bulk) {
@@ -300,40 +148,53 @@ __global__ void __launch_bounds__(256) features_cp_kernel(const uint8_t* __restr
     for (int k = 0; img < B; img += gridDim.x, ++k) {
         const int s = k & 1;
         uint8_t* stg = s ? stg1 : stg0;
-        const size_t src = source_image(bi, (size_t)img);
-        if (tid == 0 && bi.labels_batch) bi.labels_batch[img] = bi.labels_all[src];
         if (bulk) {
             const int nimg = img + gridDim.x;
-            if (tid == 0 && nimg < B) {   // the other staging buffer was drained before the barriers of iteration k-1
-                const size_t nsrc = source_image(bi, (size_t)nimg);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads -> async-proxy overwrite
-                cpbulk::mbar_expect_tx(bar + (s ^ 1), img_bytes);
-                cpbulk::bulk_load(s ? stg0 : stg1, images + image_slot(bi, nsrc) * img_bytes, img_bytes, bar + (s ^ 1));
+            if (tid == 0) {
+                if (bi.labels_batch) bi.labels_batch[img] = bi.labels_all[source_image(bi, (size_t)img)];
+                if (nimg < B) {   // the other staging buffer was drained before the barriers of iteration k-1
+                    const size_t nsrc = source_image(bi, (size_t)nimg);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads -> async-proxy overwrite
+                    cpbulk::mbar_expect_tx(bar + (s ^ 1), img_bytes);
+                    cpbulk::bulk_load(s ? stg0 : stg1, images + image_slot(bi, nsrc) * img_bytes, img_bytes, bar + (s ^ 1));
+                }
             }
             cpbulk::mbar_wait(bar + s, (uint32_t)((k >> 1) & 1));
         } else {   // unaligned source: plain loads into the staging buffer
+            const size_t src = source_image(bi, (size_t)img);
+            if (tid == 0 && bi.labels_batch) bi.labels_batch[img] = bi.labels_all[src];
             const uint8_t* g = images + image_slot(bi, src) * img_bytes;
             for (int i = tid; i < (int)img_bytes; i += nt) stg[i] = g[i];
             __syncthreads();
         }
-        cp_transpose_image(stg, tiles + cp.s[0].off, H, W, cp.s[0].hp, cp.magic_w4, tid, nt);
+        cp_transpose_images(stg, 0, tiles, 0, 1, H, W, cp, tid, nt);
         __syncthreads();
-        double* gout = out + (size_t)img * L;
-        for (int q = 0; q < cp.n; ++q) {
-            const CpStage& st = cp.s[q];
-            if (q == cp.n - 1) {
-                cp_run_stage<true>(st, q == 0, tiles + st.off, nullptr, 0, 0, gout, sc, tid, nt);
-            } else {
+        CpSinkGlobal<MODE> sink{out + (size_t)img * L, sc};
+        if (cp.n == 1) {
+            for (int it = tid; it < cp.s[0].n_in * cp.s[0].h_out * cp.s[0].w_out; it += nt)
+                cp_item<true, true>(cp.s[0], tiles, it, nullptr, 0, 0, sink);
+        } else {
+            for (int it = tid; it < cp.s[0].h_out * cp.s[0].w_out; it += nt)
+                cp_item<false, true>(cp.s[0], tiles, it, tiles + cp.s[1].off, cp.s[1].hp, cp.s[1].map_elems, sink);
+            __syncthreads();
+            for (int q = 1; q < cp.n - 1; ++q) {
+                const CpStage& st = cp.s[q];
                 const CpStage& nx = cp.s[q + 1];
-                cp_run_stage<false>(st, q == 0, tiles + st.off, tiles + nx.off, nx.hp, nx.map_elems, nullptr, sc, tid, nt);
+                for (int it = tid; it < st.n_in * st.h_out * st.w_out; it += nt)
+                    cp_item<false, false>(st, tiles + st.off, it, tiles + nx.off, nx.hp, nx.map_elems, sink);
+                __syncthreads();   // the next stage reads what this one wrote
             }
-            __syncthreads();   // next stage reads what this one wrote; the next image's transpose reuses tile 0
+            const CpStage& st = cp.s[cp.n - 1];
+            for (int it = tid; it < st.n_in * st.h_out * st.w_out; it += nt)
+                cp_item<true, false>(st, tiles + st.off, it, nullptr, 0, 0, sink);
         }
+        __syncthreads();   // the next image's transpose reuses tile 0
     }
 }
 
 // Host: can this plan take the staged path, and with which geometry?
-static bool make_cp_plan(const FeaturePlan& plan, size_t H, size_t W, CpPlan* out) {
+static unsigned cp_magic(unsigned d) { return (unsigned)(0xFFFFFFFFu / d) + 1u; }   // d >= 2
+bool make_cp_plan(const FeaturePlan& plan, size_t H, size_t W, CpPlan* out) {
     const StageList& sl = plan.stages;
     if (sl.n < 1 || sl.n > kCpMaxStages || plan.n_conv > 10 || (W & 3) != 0) return false;
     CpPlan cp{};
@@ -348,14 +209,20 @@ static bool make_cp_plan(const FeaturePlan& plan, size_t H, size_t W, CpPlan* ou
         c.map_elems = c.hp * cp_cols(s.w_in);
         c.h_out = s.h_out; c.w_out = s.w_out;
         c.off = (int)off;
+        if (s.h_out < 2) return false;   // cp_div needs divisors >= 2; 1-row maps take the generic kernel
         c.magic_hw = cp_magic((unsigned)(s.h_out * s.w_out));
         c.magic_h = cp_magic((unsigned)s.h_out);
+        c.magic_items = cp_magic((unsigned)(c.n_in * s.h_out * s.w_out));
         off += (size_t)c.n_in * c.map_elems;
         if ((size_t)c.n_in * s.h_out * s.w_out >= (1u << 16) || off > (1u << 20)) return false;   // cp_div range
     }
     cp.tile_ints = (int)off;
     cp.stage_bytes = (int)((H * W + 127) / 128 * 128);
-    cp.magic_w4 = cp_magic((unsigned)(W / 4));
+    cp.magic_w4 = W / 4 >= 2 ? cp_magic((unsigned)(W / 4)) : 0;
+    const unsigned chunks = (unsigned)((W / 4 + kCpWordsPerTask - 1) / kCpWordsPerTask);
+    cp.magic_chunks = chunks >= 2 ? cp_magic(chunks) : 0;
+    cp.tasks_per_image = (int)(((H + 31) / 32) * chunks);
+    cp.magic_tasks = cp.tasks_per_image >= 2 ? cp_magic((unsigned)cp.tasks_per_image) : 0;
     *out = cp;
     return true;
 }
@@ -404,9 +271,10 @@ static bool try_launch_features_cp(const FeaturePlan& plan, const uint8_t* image
     const size_t smem = 2 * (size_t)cp.stage_bytes + (size_t)cp.tile_ints * sizeof(int);
     if (smem > kFusedSmemLimit) return false;
     auto launch = [&]() -> int {
-        static SmemAttrCache attr;
-        if (smem > 48 * 1024 && attr.need(smem))
-            RCN_CUDA_TRY(cudaFuncSetAttribute(features_cp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        auto kern = sc.mode == 0 ? features_cp_kernel<0> : sc.mode == 1 ? features_cp_kernel<1> : features_cp_kernel<2>;
+        static SmemAttrCache attr[3];
+        if (smem > 48 * 1024 && attr[sc.mode].need(smem))
+            RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         size_t per_sm = (220 * 1024) / (smem + 1024);
         if (per_sm > 8) per_sm = 8;
         if (per_sm < 1) per_sm = 1;
@@ -414,7 +282,7 @@ static bool try_launch_features_cp(const FeaturePlan& plan, const uint8_t* image
         if (grid > B) grid = B;
         const int bulk = ((H * W) % 16 == 0 && (reinterpret_cast<uintptr_t>(images) % 16) == 0) ? 1 : 0;
         RCN_LAUNCH("features_cp_kernel", stream,
-                   features_cp_kernel<<<(unsigned)grid, 256, smem, stream>>>(images, (int)B, (int)H, (int)W, cp, out, plan.L, sc, bi, bulk));
+                   kern<<<(unsigned)grid, 256, smem, stream>>>(images, (int)B, (int)H, (int)W, cp, out, plan.L, sc, bi, bulk));
         return RCN_OK;
     };
     *rc = launch();

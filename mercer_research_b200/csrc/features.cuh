@@ -29,6 +29,30 @@ struct FeaturePlan {
     int n_conv = 0;
 };
 
+// Geometry of the staged path (u8 images through [Convolve2D(Same), Pool2D(Max)]^n, W % 4 == 0): every stage input is a
+// set of int32 column-major tiles in shared memory with a zero frame (2 rows above / 2 columns left, >= 1 below / right,
+// and the never-read last column of SURVEY.md A.2 kept at zero).  Shared by features_cp_kernel and kernel A's front end.
+constexpr int kCpMaxStages = 8;
+struct CpStage {
+    int n_in, h, w;          // input maps of this stage
+    int hp, map_elems;       // padded column pitch (even), padded elements per map
+    int h_out, w_out;        // pooled output size
+    int off;                 // offset (ints) of this stage's input tiles within one image's tile block
+    unsigned magic_hw, magic_h, magic_items;   // ceil(2^32 / d) for d = h_out*w_out, h_out, n_in*h_out*w_out (all >= 2)
+};
+struct CpPlan {
+    CpStage s[kCpMaxStages];
+    int n;
+    int stage_bytes;         // one u8 staging buffer (H*W rounded up to 128)
+    int tile_ints;           // all padded tiles of one image
+    int tasks_per_image;     // transpose warp-tasks per image
+    unsigned magic_w4;       // ceil(2^32 / (W/4))            (0 when W/4 < 2)
+    unsigned magic_chunks;   // ceil(2^32 / chunks per row group)  (0 when < 2)
+    unsigned magic_tasks;    // ceil(2^32 / tasks_per_image)  (0 when < 2)
+};
+// false when the plan does not qualify (other layer kinds, W % 4 != 0, 1-row maps, > 10 conv layers).
+bool make_cp_plan(const FeaturePlan& plan, size_t H, size_t W, CpPlan* out);
+
 // Walks convpool_cfg for an H x W input; returns RCN_ERR_SHAPE / RCN_ERR_NOT_IMPLEMENTED where the
 // reference would panic.
 int plan_features(const int32_t* cfg, size_t n_cfg, size_t H, size_t W, FeaturePlan* plan);

@@ -216,6 +216,164 @@ __device__ __forceinline__ void load_image<double, double>(const double* __restr
     for (int i = tid; i < n; i += nthreads) dst[i] = src[i];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Staged path (CpPlan, features.cuh): device side.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int cp_pitch(int h) { return (h + 4) & ~1; }   // rows -2 .. h (+1 to stay even)
+__host__ __device__ __forceinline__ int cp_cols(int w) { return w + 3; }            // cols -2 .. w
+constexpr int kCpWordsPerTask = 4;
+
+__device__ __forceinline__ int cp_div(int n, unsigned magic) { return (int)__umulhi((unsigned)n, magic); }   // divisor >= 2
+__device__ __forceinline__ int cp_div1(int n, int d, unsigned magic) { return d == 1 ? n : cp_div(n, magic); }
+
+namespace cpbulk {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk-async copy global -> shared, completion counted in bytes on `bar` (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+}  // namespace cpbulk
+
+// integer feature value -> f64 (exact: 0 <= v < 2^31) -> optional standardise + clamp (rcn.rs:407-412)
+__device__ __forceinline__ double cp_finish(int mode, int v, const Standardise& sc) {
+    double d = __hiloint2double(0x43300000, v) - 4503599627370496.0;   // (2^52 + v) - 2^52 == (double)v
+    if (mode == 1) {
+        d = (d - sc.mean) / sc.sd;
+        d = (d >= 0.0) ? d : 0.0;
+    } else if (mode == 2) {   // host-verified exact Markstein division, see EmitFeatures
+        const double a = d - sc.mean;
+        const double q = __dmul_rn(a, sc.rcp);
+        const double rem = fma(-q, sc.sd, a);
+        d = fma(rem, sc.rcp, q);
+        d = (d >= 0.0) ? d : 0.0;
+    }
+    return d;
+}
+
+template <int MODE>
+struct CpSinkGlobal {   // flattened feature vector of one image in global memory (rcn.rs:350-355)
+    double* gout; Standardise sc;
+    __device__ __forceinline__ void operator()(int idx, int v) const { gout[idx] = cp_finish(MODE, v, sc); }
+};
+
+// One pooled output position of a conv(Same)+pool stage over padded int32 tiles: item `it` of one image =
+// (map i, column x, row y), y fastest.  LAST: the four operator responses go to `sink(feature index, value)`; otherwise
+// into the next stage's padded tiles `nxt` (whose last column stays zero).  Exact int32 closed form of
+// conv_pool_same_int without a single bounds test on the loads.
+template <bool LAST, bool FIRST, typename Sink>
+__device__ __forceinline__ void cp_item(const CpStage& st, const int* __restrict__ in, int it, int* __restrict__ nxt,
+                                        int nxt_hp, int nxt_map, const Sink& sink) {
+    const int hw_out = st.h_out * st.w_out;
+    const int hp = st.hp;
+    int i = 0, rem = it;
+    if (!FIRST) { i = cp_div(it, st.magic_hw); rem = it - i * hw_out; }
+    const int x = cp_div(rem, st.magic_h);
+    const int y = rem - x * st.h_out;
+    // padded coordinates: image (row r, col c) sits at [(c + 2) * hp + r + 2]; the patch starts at (2y-2, 2x-2)
+    const int* f = in + i * st.map_elems + (2 * x) * hp + 2 * y;
+    int p[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int2 a = *reinterpret_cast<const int2*>(f + k * hp);
+        const int2 b = *reinterpret_cast<const int2*>(f + k * hp + 2);
+        p[0][k] = a.x; p[1][k] = a.y; p[2][k] = b.x; p[3][k] = b.y;
+    }
+    // conv row 2y+a is zero for row 0 and beyond the map (the pool's zero padding, kernel.rs:253-261)
+    const bool rok0 = y > 0, rok1 = 2 * y + 1 < st.h;
+    const bool cok1 = 2 * x + 1 < st.w;
+    int tmax = 0, tmin = 0, lmax = 0, lmin = 0;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        int vT[4], vS[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            vT[k] = p[a][k] - p[a + 2][k];
+            vS[k] = p[a][k] + 2 * p[a + 1][k] + p[a + 2][k];
+        }
+        const bool rok = a ? rok1 : rok0;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const bool ok = rok && (e ? cok1 : true);
+            const int T = ok ? vT[e] + 2 * vT[e + 1] + vT[e + 2] : 0;
+            const int L = ok ? vS[e] - vS[e + 2] : 0;
+            tmax = max(tmax, T); tmin = min(tmin, T);
+            lmax = max(lmax, L); lmin = min(lmin, L);
+        }
+    }
+    const int t = tmax, b = -tmin, l = lmax, r = -lmin;
+    // slot order rcn.rs:325-339: first conv [T,L,R,B]; later convs put Bottom in slot i and T,L,R at n + 3i
+    const int sB = FIRST ? 3 : i;
+    const int sT = FIRST ? 0 : st.n_in + 3 * i;
+    if (LAST) {
+        const int o = sT * hw_out + rem;                  // rem == x * h_out + y
+        sink(o, t);
+        sink(o + hw_out, l);
+        sink(o + 2 * hw_out, r);
+        sink(sB * hw_out + rem, b);
+    } else if (x < st.w_out - 1) {
+        int* o = nxt + sT * nxt_map + (x + 2) * nxt_hp + y + 2;
+        o[0] = t;
+        o[nxt_map] = l;
+        o[2 * nxt_map] = r;
+        nxt[sB * nxt_map + (x + 2) * nxt_hp + y + 2] = b;
+    }
+}
+
+// u8 row-major staging buffers -> padded int32 column-major tiles of stage 0 (lib.rs:29-33 layout change) for G images
+// (image g: staging at stg + g*stg_stride bytes, tiles at tiles + g*tile_stride ints).  Lane l of a warp task takes
+// row r0 + l and walks words (l + it) mod W/4 of that row: the 4-byte reads and the four column-strided writes are both
+// bank-conflict free.  Column W-1 is never read downstream and stays zero.
+__device__ __forceinline__ void cp_transpose_images(const uint8_t* __restrict__ stg, int stg_stride, int* __restrict__ tiles,
+                                                    int tile_stride, int G, int H, int W, const CpPlan& cp, int tid, int nt) {
+    const int W4 = W >> 2;
+    const int hp = cp.s[0].hp;
+    const int chunks = (W4 + kCpWordsPerTask - 1) / kCpWordsPerTask;
+    const int tpi = cp.tasks_per_image;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    for (int task = warp; task < G * tpi; task += nwarps) {
+        const int g = cp_div1(task, tpi, cp.magic_tasks);
+        const int tl = task - g * tpi;
+        const int rg = cp_div1(tl, chunks, cp.magic_chunks);
+        const int it0 = (tl - rg * chunks) * kCpWordsPerTask;
+        const int r = rg * 32 + lane;
+        if (r >= H) continue;
+        int j = lane + it0;
+        if (W4 > 1) j -= cp_div(j, cp.magic_w4) * W4; else j = 0;
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(stg + (size_t)g * stg_stride) + r * W4;
+        int* col0 = tiles + g * tile_stride + 2 * hp + r + 2;
+        const int n = min(kCpWordsPerTask, W4 - it0);
+#pragma unroll
+        for (int u = 0; u < kCpWordsPerTask; ++u) {
+            if (u < n) {
+                const uint32_t v = row[j];
+                int* dst = col0 + 4 * j * hp;
+                dst[0] = (int)__byte_perm(v, 0, 0x4440);
+                dst[hp] = (int)__byte_perm(v, 0, 0x4441);
+                dst[2 * hp] = (int)__byte_perm(v, 0, 0x4442);
+                if (j != W4 - 1) dst[3 * hp] = (int)__byte_perm(v, 0, 0x4443);
+                j = (j + 1 == W4) ? 0 : j + 1;
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ size_t source_image(const BatchIndex& bi, size_t img) {
     if (!bi.cursor) return img;
     const long long pos = *bi.cursor + (long long)img;

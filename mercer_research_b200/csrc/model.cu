@@ -309,6 +309,7 @@ int accumulate_images_dev(rcn_cuda_model* h, const void* images, int fmt, const 
         fr.stages = h->plan.stages;
         fr.sc = make_standardise(h->plan, fmt, true, h->mean, h->sd);
         if (bi) fr.bi = *bi;
+        smallnet_front_select(h->plan, &fr);
         if (smallnet_front_fits(h->small_desc, fr))
             return accumulate_dev(h, h->feats.as<double>(), nullptr, step_labels, B, &fr);
     }

@@ -25,6 +25,8 @@
 
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 namespace rcn {
 
 __device__ __forceinline__ double sn_sigmoid(double z) { return 1.0 / (1.0 + exp(-z)); }  // rcn.rs:478-483
@@ -64,17 +66,31 @@ struct EmitTile {
     }
 };
 
+// staged front end: standardised feature -> shared tile + HBM
+struct CpSinkTile {
+    double* tile; double* gout; Standardise sc;
+    __device__ __forceinline__ void operator()(int idx, int v) const {
+        const double d = cp_finish(sc.mode, v, sc);
+        tile[idx] = d;
+        gout[idx] = d;
+    }
+};
+
+__device__ __forceinline__ unsigned char* sn_align128(void* p) {
+    return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 127) & ~(uintptr_t)127);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Kernel A
 // ------------------------------------------------------------------------------------------------
-template <bool FUSED>
+template <int FUSED>   // 0: features are an input; 1: generic fused front end; 2: staged front end (CpPlan)
 __global__ void __launch_bounds__(SNA_THREADS, 1)
 smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __restrict__ params,
                         double* __restrict__ feats, int B, const double* __restrict__ onehot,
                         const int64_t* __restrict__ labels, double* __restrict__ acts, double* __restrict__ deltas,
                         double* __restrict__ stats_partial, double* __restrict__ small_partial, int backward,
                         const __grid_constant__ SmallNetFront fr) {
-    extern __shared__ __align__(16) unsigned char sn_smem[];
+    extern __shared__ __align__(128) unsigned char sn_smem[];
     double* zpart = reinterpret_cast<double*>(sn_smem);                 // [16][32][8]
     double* s_small = zpart + SNA_WARPS * 32 * SN_TB;                   // params after W0: b0 | W1 | b1 | ...
     double* tile = s_small + SN_MAX_SMALL;                              // FUSED: [8][n_in + 4]
@@ -96,7 +112,61 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
     // prefetch biases + narrow-layer weights (overlaps with the front end / the DMMA phase)
     for (int i = tid; i < n_small; i += SNA_THREADS) s_small[i] = __ldg(params + small_base + i);
 
-    if (FUSED) {
+    if (FUSED == 2) {
+        // ---- staged front end: the 8 images arrive by bulk-async copies while the tiles' zero frames are written; then
+        // all 16 warps transpose and run the conv+pool stages over the 8 images together (features_device.cuh) ---------
+        __shared__ __align__(8) uint64_t s_bar;
+        unsigned char* stg = sn_align128(tile + SN_TB * pitch);
+        int* tiles = reinterpret_cast<int*>(stg + SN_TB * fr.cp.stage_bytes);
+        const int n_live = min(SN_TB, B - s0);
+        const uint32_t img_bytes = (uint32_t)(fr.H * fr.W);
+        if (warp == 0) {
+            if (lane == 0) {
+                cpbulk::mbar_init(&s_bar, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                cpbulk::mbar_expect_tx(&s_bar, img_bytes * (uint32_t)n_live);
+            }
+            __syncwarp();
+            if (lane < SN_TB) {
+                long long lab = -1;
+                if (lane < n_live) {
+                    const int sample = s0 + lane;
+                    const size_t src = source_image(fr.bi, (size_t)sample);
+                    cpbulk::bulk_load(stg + lane * fr.cp.stage_bytes, fr.images + image_slot(fr.bi, src) * img_bytes, img_bytes, &s_bar);
+                    lab = fr.bi.cursor ? fr.bi.labels_all[src] : (labels ? labels[sample] : 0);
+                    if (fr.bi.labels_batch) fr.bi.labels_batch[sample] = lab;
+                }
+                s_label[lane] = lab;
+            }
+        }
+        for (int i = tid; i < SN_TB * fr.cp.tile_ints; i += SNA_THREADS) tiles[i] = 0;
+        for (int i = n_live * pitch + tid; i < SN_TB * pitch; i += SNA_THREADS) tile[i] = 0.0;   // absent samples
+        __syncthreads();
+        cpbulk::mbar_wait(&s_bar, 0);
+        cp_transpose_images(stg, fr.cp.stage_bytes, tiles, fr.cp.tile_ints, n_live, fr.H, fr.W, fr.cp, tid, SNA_THREADS);
+        __syncthreads();
+        for (int q = 0; q < fr.cp.n; ++q) {
+            const CpStage& st = fr.cp.s[q];
+            const int items = st.n_in * st.h_out * st.w_out;
+            const bool last = q == fr.cp.n - 1;
+            const CpStage& nx = fr.cp.s[last ? q : q + 1];
+            for (int it = tid; it < n_live * items; it += SNA_THREADS) {
+                const int gi = cp_div(it, st.magic_items);
+                const int itl = it - gi * items;
+                const int* in = tiles + gi * fr.cp.tile_ints + st.off;
+                int* nxt = tiles + gi * fr.cp.tile_ints + nx.off;
+                CpSinkTile sink{tile + (size_t)gi * pitch, feats + (size_t)(s0 + gi) * L, fr.sc};
+                if (last) {
+                    if (q == 0) cp_item<true, true>(st, in, itl, nullptr, 0, 0, sink);
+                    else cp_item<true, false>(st, in, itl, nullptr, 0, 0, sink);
+                } else {
+                    if (q == 0) cp_item<false, true>(st, in, itl, nxt, nx.hp, nx.map_elems, sink);
+                    else cp_item<false, false>(st, in, itl, nxt, nx.hp, nx.map_elems, sink);
+                }
+            }
+            __syncthreads();
+        }
+    } else if (FUSED == 1) {
         // ---- fused front end: two warps per image --------------------------------------------------------------
         int* bufs = reinterpret_cast<int*>(tile + SN_TB * pitch);
         const int n_img = tid >> 6, lt = tid & 63;
@@ -483,11 +553,22 @@ size_t smallnet_max_batch() { return (size_t)1 << 22; }
 
 static size_t kernel_a_smem(const SmallNetDesc& d, const SmallNetFront* fr) {
     size_t bytes = ((size_t)SNA_WARPS * 32 * SN_TB + SN_MAX_SMALL) * sizeof(double);
-    if (fr) bytes += (size_t)SN_TB * (d.n_in + SN_TILE_PAD) * sizeof(double) + (size_t)SN_TB * 2 * fr->max_elems * sizeof(int);
+    if (fr) {
+        bytes += (size_t)SN_TB * (d.n_in + SN_TILE_PAD) * sizeof(double);
+        if (fr->use_cp) bytes += 128 + (size_t)SN_TB * ((size_t)fr->cp.stage_bytes + (size_t)fr->cp.tile_ints * sizeof(int));
+        else bytes += (size_t)SN_TB * 2 * fr->max_elems * sizeof(int);
+    }
     return bytes;
 }
 
 bool smallnet_front_fits(const SmallNetDesc& d, const SmallNetFront& fr) { return kernel_a_smem(d, &fr) <= 200 * 1024; }
+
+void smallnet_front_select(const FeaturePlan& plan, SmallNetFront* fr) {
+    static const bool off = []() { const char* e = getenv("RCN_CUDA_FEATURES_STAGED"); return e && e[0] == '0'; }();
+    fr->use_cp = 0;
+    if (off || (reinterpret_cast<uintptr_t>(fr->images) & 15) != 0 || ((size_t)fr->H * fr->W) % 16 != 0) return;
+    if (make_cp_plan(plan, (size_t)fr->H, (size_t)fr->W, &fr->cp)) fr->use_cp = 1;
+}
 
 static int launch_kernel_a(const SmallNetDesc& d, const double* params, double* feats, size_t B, const double* onehot,
                            const int64_t* labels, double* acts, double* deltas, double* stats_partial,
@@ -495,15 +576,22 @@ static int launch_kernel_a(const SmallNetDesc& d, const double* params, double* 
     const unsigned n_tiles = cdiv(B, SN_TB);
     const size_t smem = kernel_a_smem(d, fr);
     static SmallNetFront empty_front{};
-    if (fr) {
-        auto kern = smallnet_fwd_bwd_kernel<true>;
+    if (fr && fr->use_cp) {
+        auto kern = smallnet_fwd_bwd_kernel<2>;
+        static SmemAttrCache attr;
+        if (attr.need(smem)) RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RCN_LAUNCH("smallnet_fwd_bwd_kernel(fused features)", stream,
+                   kern<<<n_tiles, SNA_THREADS, smem, stream>>>(d, params, feats, (int)B, onehot, labels, acts, deltas,
+                                                               stats_partial, small_partial, backward, *fr));
+    } else if (fr) {
+        auto kern = smallnet_fwd_bwd_kernel<1>;
         static SmemAttrCache attr;
         if (attr.need(smem)) RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RCN_LAUNCH("smallnet_fwd_bwd_kernel(fused features)", stream,
                    kern<<<n_tiles, SNA_THREADS, smem, stream>>>(d, params, feats, (int)B, onehot, labels, acts, deltas,
                                                                stats_partial, small_partial, backward, *fr));
     } else {
-        auto kern = smallnet_fwd_bwd_kernel<false>;
+        auto kern = smallnet_fwd_bwd_kernel<0>;
         static SmemAttrCache attr;
         if (attr.need(smem)) RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RCN_LAUNCH("smallnet_fwd_bwd_kernel", stream,

@@ -26,7 +26,11 @@ struct SmallNetFront {
     StageList stages;
     Standardise sc;
     BatchIndex bi;
+    int use_cp;                        // staged front end (bulk-async image loads, zero-framed tiles): see CpPlan
+    CpPlan cp;
 };
+// Fills use_cp / cp: the staged front end needs a qualifying plan, 16-byte aligned images and H*W % 16 == 0.
+void smallnet_front_select(const FeaturePlan& plan, SmallNetFront* fr);
 
 bool smallnet_eligible(const SmallNetDesc& d);
 size_t smallnet_max_batch();

@@ -1,7 +1,7 @@
 """Feature-stage throughput (rcn_cuda_features: flatten_feature_set + standardise, rcn.rs:317-356,407-412) against
 the HBM roofline.  Algorithmic bytes per image = H*W (u8 read) + L*8 (f64 features written), SURVEY.md 8d.
 Inputs are device resident and larger than L2; CUDA events on the launching stream; JSON lines on stdout.
-Usage: python profiles/features_bench.py            (RCN_CUDA_FEATURES_STAGED=0 selects the one-image-per-CTA kernel)
+Usage: python profiles/features_bench.py [case-prefix]            (RCN_CUDA_FEATURES_STAGED=0 selects the one-image-per-CTA kernel)
 """
 import json
 import os
@@ -25,7 +25,10 @@ def main():
     except Exception:
         pass
     dev = torch.device("cuda", 0)
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
     for name, H, W, cfg, B in CASES:
+        if only and not name.startswith(only):
+            continue
         model = RCN(10, cfg, [30])
         L = model.feature_len(H, W)
         imgs = torch.randint(0, 256, (B, H, W), dtype=torch.uint8, device=dev)

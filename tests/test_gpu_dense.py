@@ -200,6 +200,30 @@ def test_full_pipeline_config_c2(api):
     assert_close(model.get_params(), thr_params, what="params vs threaded oracle")
 
 
+@pytest.mark.parametrize("cfg,hw,B", [([1, 3], (28, 28), 1021), ([1, 3, 1, 3], (28, 28), 203), ([1, 3, 1, 3, 1, 3], (32, 32), 64),
+                                       ([1, 3], (12, 20), 5), ([1, 3, 1, 3], (20, 12), 77), ([1, 3], (30, 28), 9)])
+def test_fused_front_end_variants(api, cfg, hw, B):
+    """Kernel A's staged front end (bulk-async image loads, zero-framed tiles) on stacks / sizes / ragged batches beyond the
+    canonical one; (30, 28) has H*W % 16 != 0 and takes the generic fused front end.  Features bit-exact, step <= 1e-9."""
+    rng = np.random.default_rng(B * 7 + hw[0])
+    imgs = rng.integers(0, 256, size=(B,) + hw, dtype=np.uint8)
+    labels = rng.integers(0, 10, B).astype(np.int64)
+    lay = [api.RCNLayer.Convolve2D(api.Padding.Same) if c == 1 else api.RCNLayer.Pool2D(api.Pooling.Max) for c in cfg]
+    model = api.RCN(10, lay, [30])
+    raw = O.features_u8(cfg, imgs)
+    mean, sd = O.gen_scales(raw)
+    model.scale_set = (mean, sd)
+    model.load_weights_and_bias(model.feature_len(*hw))
+    net = O.Net(model.layer_shapes)
+    params = np.random.default_rng(5).standard_normal(net.n_params) * 0.2
+    model.set_params(params)
+    X = O.standardise(raw, mean, sd)
+    want_params, want_grads = net.train_batch(params, X, np.eye(10)[labels], 3.0)
+    model.train_batch_images(imgs, labels, 3.0)
+    assert_close(model.get_gradients(), want_grads, what="grads")
+    assert_close(model.get_params(), want_params, what="params")
+
+
 def test_multi_step_training_tracks_oracle(api):
     """20 consecutive SGD steps: errors must not compound beyond tolerance."""
     model, net, params = make_model(api, [16], 4, 40, scale=0.3)
