@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -317,10 +318,13 @@ def run_gpu(args, wl, rank, world, local_rank):
     kernels_per_step = None
     if not args.no_graph:
         l_before = _lib.kernel_launches()
-        trainer.capture(warmup=3)
-        kernels_per_step = (_lib.kernel_launches() - l_before) // 4   # 3 warm-up steps + 1 captured step
+        spg = max(1, math.gcd(args.steps, args.steps_per_graph))     # the timed region is a whole number of replays
+        trainer.capture(warmup=3, steps_per_graph=spg)
+        kernels_per_step = (_lib.kernel_launches() - l_before) // (3 + spg)   # 3 warm-up steps + spg captured steps
+    else:
+        spg = 1
 
-    def step(i):
+    def step(i):                                # warm-up unit: one graph replay (= spg steps) or one eager step
         trainer.epoch_step()
 
     def barrier():
@@ -350,8 +354,7 @@ def run_gpu(args, wl, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clocks.mark_begin()
     e0.record(stream)
-    for i in range(args.steps):
-        step(args.warmup + i)
+    trainer.epoch_steps(args.steps)             # exactly K steps: K / spg replays of the spg-step graph
     e1.record(stream)
     barrier()
     clocks.mark_end()
@@ -449,6 +452,8 @@ def run_gpu(args, wl, rank, world, local_rank):
                                                     B * (48 * H * W + fwd + bwd_d)],
         "smallnet_fwd_bwd_kernel": ["hbm", B * (L * 8 + 8 + act_bytes) + n_params * 8, B * (fwd + bwd_d)],
         "smallnet_wgrad_kernel": ["hbm", B * (L + shapes[0][0]) * 8 + n_params * 8, B * bwd_w],
+        "smallnet_wgrad_kernel(+SGD update)": ["hbm", B * (L + shapes[0][0]) * 8 + 3 * n_params * 8, B * bwd_w + 2 * n_params],
+        "features_cp_kernel": ["hbm", B * (H * W * 1 + L * 8), B * 48 * H * W],
         "sgd_update_kernel": ["hbm", 3 * n_params * 8, 2 * n_params],
         "dp_allreduce_sgd_kernel": ["hbm", 3 * n_params * 8, 2 * n_params],
         "bias_grad_kernel": ["hbm", B * sum_rows * 8, B * sum_rows],
@@ -529,12 +534,12 @@ def run_gpu(args, wl, rank, world, local_rank):
 
     line = {
         "metric": "training images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": n_warm * spg, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["desc"], "batch_per_gpu": B, "global_batch": B * world, "pixels": "u8", "eta": ETA,
                    "params": n_params, "parallelism": f"dp{world}",
                    "l2_policy": f"inputs rotate over {n_batches} resident batches = {n_batches * B * H * W / 2 ** 20:.0f} MiB > 126 MB L2",
-                   "step": step_desc, "cuda_graph": not args.no_graph},
+                   "step": step_desc, "cuda_graph": not args.no_graph, "steps_per_graph": spg},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps, "host_buffers": "pinned",
@@ -559,6 +564,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--steps-per-graph", type=int, default=8, help="consecutive steps captured into one CUDA graph (the timed region replays it steps/this times)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
                     help="multi-GPU gradient exchange: fused NVLink peer-memory kernel, NCCL all-reduce, or by size")

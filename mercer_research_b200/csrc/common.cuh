@@ -127,6 +127,12 @@ struct ReduceScratch {
     double* partials() const { return reinterpret_cast<double*>(buf.as<char>() + kTicketBytes); }
 };
 
+// W <- W - (eta/B) * sum  (rcn.rs:214,221): the reference multiplies, rounds, then subtracts (Rust never contracts), so
+// the update is NOT a fused multiply-add here either -- given the same gradient sums the new weights are bit-identical.
+#ifdef __CUDACC__
+__device__ __forceinline__ double sgd_apply(double p, double scale, double g) { return __dsub_rn(p, __dmul_rn(scale, g)); }
+#endif
+
 constexpr int kNumSMs = 148;  // B200
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }

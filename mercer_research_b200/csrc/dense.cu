@@ -14,6 +14,7 @@
 // recomputes sigmoid(z) (rcn.rs:491) which is bitwise the same value, and it must NOT be rewritten
 // algebraically (1-a cancels for saturated units and parity depends on cancelling identically).
 #include "dense.cuh"
+#include "timeline.cuh"
 #include "gemm_f64.cuh"
 #include "opctx.cuh"
 #include "ozaki.cuh"
@@ -260,8 +261,9 @@ int launch_dense_backward_weight(const double* delta, const double* A_prev, size
 __global__ void sgd_update_kernel(double* __restrict__ p, const double* __restrict__ g, size_t n, double scale,
                                   long long* __restrict__ cursor, long long batch, long long n_samples,
                                   const double* __restrict__ stats, double* __restrict__ stats_ring) {
+    RCN_TL_BEGIN(0);
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        p[i] = p[i] - scale * g[i];  // &lw.0 - (eta / B) * w   (rcn.rs:214,221): product rounded, then subtracted
+        p[i] = sgd_apply(p[i], scale, g[i]);  // &lw.0 - (eta / B) * w   (rcn.rs:214,221): product rounded, then subtracted
     if (cursor && blockIdx.x == 0 && threadIdx.x == 0) {
         if (stats_ring) {   // this step's {cost, hits} straight into the (pinned host) result ring: one 16-byte write
             double* dst = stats_ring + 2 * (*cursor / batch);
@@ -273,6 +275,7 @@ __global__ void sgd_update_kernel(double* __restrict__ p, const double* __restri
         if (c + batch > n_samples) c = 0;
         *cursor = c;
     }
+    RCN_TL_END(0);
 }
 
 int launch_sgd_update(double* params, const double* grads, size_t n, double scale, cudaStream_t stream,
@@ -414,3 +417,8 @@ extern "C" int rcn_cuda_ext_gemm_f64(int device, void* cuda_stream, const double
     }
     return c.finish(C, c_dev, M * N * 8, host);
 }
+
+#ifdef RCN_TIMELINE
+extern "C" int rcn_cuda_debug_timeline_reset_dense() { return rcn_tl::reset_host(); }
+extern "C" int rcn_cuda_debug_timeline_read_dense(unsigned long long* out, unsigned* seq) { return rcn_tl::read_host(out, seq); }
+#endif

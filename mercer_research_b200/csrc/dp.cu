@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) dp_allreduce_sgd_kernel(const DpPeers pee
                 s = (q == 0) ? v : s + v;
             }
             grads[i] = s;                        // the gradient buffer ends up holding the global sum, like an all-reduce
-            params[i] = params[i] - scale * s;   // W -= (eta / B) * sum   (rcn.rs:214,221)
+            params[i] = sgd_apply(params[i], scale, s);   // W -= (eta / B) * sum   (rcn.rs:214,221)
         }
     }
     // ---- the last CTA to finish advances the device-side step counter (and the epoch cursor) ----------------------------

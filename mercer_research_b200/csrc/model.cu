@@ -61,20 +61,37 @@ LaunchScope::~LaunchScope() {
 }
 
 // ---- streaming from a pinned HOST dataset (rcn_cuda_train_epoch_host fast path) ---------------------------------------
-// State block in device memory: [0] cursor (samples, advanced by the update kernel), [1] n_steps, [2] host image base.
-// The prefetch kernel reads chunk k+1 = cursor/B + 1 straight from pinned host memory (zero-copy loads over PCIe, 16 B
-// per thread, coalesced) into ring slot (k+1) % 2 while the training kernels of chunk k run on the other graph branch.
-__global__ void __launch_bounds__(256) host_prefetch_kernel(const long long* __restrict__ state, unsigned char* __restrict__ ring,
+// State block in device memory: [0] cursor (samples, advanced by the update), [1] n_steps, [2] host image base,
+// [3] prefetch launches so far, [4] ticket of the running prefetch launch, [5] pad; the step's labels follow.
+// Launch k of the prefetch kernel (its own counter: it runs on a parallel graph branch and must not race with the
+// cursor update at the end of step k) reads chunk k+1 straight from pinned host memory (zero-copy loads over PCIe, 16 B
+// per thread, coalesced) into ring slot (k+1) % 2 while the training kernels of chunk k run on the other branch.
+constexpr int kHsStateSlots = 6;
+// consecutive steps captured into one CUDA graph by rcn_cuda_train_epoch_host (RCN_CUDA_HOST_STEPS_PER_GRAPH overrides)
+static int hs_steps_per_graph() {
+    static const int v = []() { const char* e = getenv("RCN_CUDA_HOST_STEPS_PER_GRAPH"); int n = e ? atoi(e) : 2; return n < 1 ? 1 : (n > 64 ? 64 : n); }();
+    return v;
+}
+__global__ void __launch_bounds__(256) host_prefetch_kernel(long long* __restrict__ state, unsigned char* __restrict__ ring,
                                                             long long B, long long img_bytes) {
-    const long long k1 = state[0] / B + 1;
-    if (k1 >= state[1]) return;
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(state[2]) + k1 * B * img_bytes;
-    unsigned char* dst = ring + ((k1 * B) % (2 * B)) * img_bytes;
-    const long long n16 = B * img_bytes / 16;
-    const uint4* s4 = reinterpret_cast<const uint4*>(src);
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
-        d4[i] = s4[i];
+    const long long k1 = *reinterpret_cast<volatile long long*>(state + 3) + 1;
+    if (k1 < state[1]) {
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(state[2]) + k1 * B * img_bytes;
+        unsigned char* dst = ring + ((k1 * B) % (2 * B)) * img_bytes;
+        const long long n16 = B * img_bytes / 16;
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
+            d4[i] = s4[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {   // the last CTA to finish publishes the counter: every CTA has read it by then
+        __threadfence();
+        if (atomicAdd(reinterpret_cast<unsigned long long*>(state + 4), 1ull) == gridDim.x - 1) {
+            state[4] = 0;
+            *reinterpret_cast<volatile long long*>(state + 3) = k1;
+        }
+    }
 }
 
 bool is_pinned_host_ptr(const void* p) {
@@ -127,6 +144,8 @@ struct rcn_cuda_model {
     bool stats_valid = false;
     // data-parallel group (dp.cu) and the pipelined host-dataset loop (rcn_cuda_train_epoch_host)
     DpState dp;
+    SnUpdate pending_upd{};         // set by the step entry points: the next small-network accumulate applies the update itself
+    bool upd_fused = false;         // ... and did (the standalone update kernel is then skipped)
     bool dp_pushed = false;         // the last accumulate pushed its gradients to the peers itself (kernel B epilogue)
     bool dp_push_suppress = false;  // warm-up launches must not push (a push is consumed by exactly one receive)
     OzakiWorkspace oz;              // tcgen05 integer-slice GEMM scratch (wide dense layers)
@@ -137,7 +156,8 @@ struct rcn_cuda_model {
     size_t stats_host_cap = 0;
     // streaming variant: the GPU pulls chunk k+1 from pinned host memory while it trains on chunk k; one graph per step
     DevBuf hs_ring, hs_state;
-    cudaGraphExec_t hs_graph = nullptr;
+    cudaGraphExec_t hs_graph = nullptr;     // hs_steps_per_graph() consecutive steps
+    cudaGraphExec_t hs_graph1 = nullptr;    // one step (the remainder of the epoch)
     cudaEvent_t hs_fork = nullptr, hs_join = nullptr;
     struct HsKey {
         size_t B = 0, H = 0, W = 0, n_steps = 0;
@@ -253,6 +273,9 @@ int forward_dev(rcn_cuda_model* h, const double* feats, size_t B, const double* 
 int accumulate_dev(rcn_cuda_model* h, const double* feats, const double* onehot, const int64_t* labels, size_t B,
                    const SmallNetFront* front = nullptr) {
     const size_t n = h->rows.size();
+    const SnUpdate upd = h->pending_upd;   // consumed by this call whichever path it takes
+    h->pending_upd = SnUpdate{};
+    h->upd_fused = false;
     if (h->dp_pushed)   // a pushed gradient must be received by the group's update before the next one is produced
         return fail(RCN_ERR_STATE, "data-parallel group: the previous gradients were pushed to the peers but never applied "
                                    "(every accumulate needs exactly one apply on every rank)");
@@ -269,8 +292,10 @@ int accumulate_dev(rcn_cuda_model* h, const double* feats, const double* onehot,
         if (fuse_push) push = dp_push_desc(h->dp);
         RCN_TRY(launch_smallnet_backprop(h->small_desc, h->params.as<double>(), const_cast<double*>(feats), B, onehot,
                                          labels, h->acts.as<double>(), h->deltas.as<double>(), h->grads,
-                                         h->small.as<double>(), h->gemm_ws, front, h->stream, fuse_push ? &push : nullptr));
+                                         h->small.as<double>(), h->gemm_ws, front, h->stream, fuse_push ? &push : nullptr,
+                                         (upd.params && !h->dp.connected) ? &upd : nullptr));
         h->dp_pushed = fuse_push;
+        h->upd_fused = upd.params && !h->dp.connected;
         h->stats_valid = true;
         h->last_B = B;
         return RCN_OK;
@@ -397,6 +422,7 @@ int rcn_cuda_destroy(rcn_cuda_handle h) {
     }
     if (h->stats_host) cudaFreeHost(h->stats_host);
     if (h->hs_graph) cudaGraphExecDestroy(h->hs_graph);
+    if (h->hs_graph1) cudaGraphExecDestroy(h->hs_graph1);
     if (h->hs_fork) cudaEventDestroy(h->hs_fork);
     if (h->hs_join) cudaEventDestroy(h->hs_join);
     h->hs_ring.release(); h->hs_state.release();
@@ -760,15 +786,42 @@ int rcn_cuda_apply_gradients(rcn_cuda_handle h, double eta, size_t batch) {
     return launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale, h->stream);
 }
 
+// Single-GPU steps of the fused small-network path let the weight-gradient kernel apply the update (SnUpdate): arm it
+// before the accumulate; if that accumulate took another path the standalone update kernel runs as before.
+static void arm_fused_update(rcn_cuda_model* h, double scale, long long* cursor, long long batch, long long n_samples,
+                             double* stats_ring) {
+    static const bool on = []() { const char* e = getenv("RCN_CUDA_FUSED_UPDATE"); return !(e && e[0] == '0'); }();
+    h->pending_upd = SnUpdate{};
+    if (!on || !h || !h->params_ready || !h->use_small || h->dp.connected) return;
+    h->pending_upd.params = h->params.as<double>();
+    h->pending_upd.scale = scale;
+    h->pending_upd.cursor = cursor;
+    h->pending_upd.batch = batch;
+    h->pending_upd.n_samples = n_samples;
+    h->pending_upd.stats_ring = stats_ring;
+}
+static bool take_upd_fused(rcn_cuda_model* h) {
+    const bool f = h->upd_fused;
+    h->upd_fused = false;
+    h->pending_upd = SnUpdate{};
+    return f;
+}
+
 int rcn_cuda_train_batch(rcn_cuda_handle h, const double* feats, const double* onehot, const int64_t* labels, size_t B,
                          double eta) {
-    RCN_TRY(rcn_cuda_accumulate_gradients(h, feats, onehot, labels, B));
+    if (h && B) arm_fused_update(h, eta / (double)B, nullptr, 0, 0, nullptr);
+    const int rc = rcn_cuda_accumulate_gradients(h, feats, onehot, labels, B);
+    if (rc != RCN_OK) { if (h) take_upd_fused(h); return rc; }
+    if (take_upd_fused(h)) return RCN_OK;
     return rcn_cuda_apply_gradients(h, eta, B);
 }
 
 int rcn_cuda_train_batch_images(rcn_cuda_handle h, const void* images, int pixel_format, const int64_t* labels, size_t B,
                                 size_t H, size_t W, double eta) {
-    RCN_TRY(rcn_cuda_accumulate_gradients_images(h, images, pixel_format, labels, B, H, W));
+    if (h && B) arm_fused_update(h, eta / (double)B, nullptr, 0, 0, nullptr);
+    const int rc = rcn_cuda_accumulate_gradients_images(h, images, pixel_format, labels, B, H, W);
+    if (rc != RCN_OK) { if (h) take_upd_fused(h); return rc; }
+    if (take_upd_fused(h)) return RCN_OK;
     return rcn_cuda_apply_gradients(h, eta, B);
 }
 
@@ -848,7 +901,11 @@ int rcn_cuda_epoch_apply(rcn_cuda_handle h, double eta, size_t global_batch) {
 }
 
 int rcn_cuda_epoch_step(rcn_cuda_handle h, double eta) {
-    RCN_TRY(rcn_cuda_epoch_accumulate(h));
+    if (h && h->ep_images && h->ep_B)
+        arm_fused_update(h, eta / (double)h->ep_B, h->ep_state.as<long long>(), (long long)h->ep_B, (long long)h->ep_n, nullptr);
+    const int rc = rcn_cuda_epoch_accumulate(h);
+    if (rc != RCN_OK) { if (h) take_upd_fused(h); return rc; }
+    if (take_upd_fused(h)) return RCN_OK;
     return rcn_cuda_epoch_apply(h, eta, h->ep_B);
 }
 
@@ -910,7 +967,7 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
                 h->stream = h->own_stream;
             }
             RCN_TRY(h->hs_ring.reserve(2 * img_bytes));
-            RCN_TRY(h->hs_state.reserve((4 + B) * sizeof(long long)));
+            RCN_TRY(h->hs_state.reserve((kHsStateSlots + B) * sizeof(long long)));
             RCN_TRY(h->tgt_stage.reserve(n_steps * B * sizeof(int64_t)));
             RCN_TRY(h->feats.reserve(h->plan.L * B * sizeof(double)));
             const double scale_s = eta / (double)global_batch;
@@ -918,10 +975,10 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
             BatchIndex bi;
             bi.cursor = st;
             bi.labels_all = h->tgt_stage.as<long long>();
-            bi.labels_batch = st + 4;
+            bi.labels_batch = st + kHsStateSlots;
             bi.window = (long long)(2 * B);
             // state, labels of the whole epoch and chunk 0 go up with plain copies; everything after that is graph replays
-            const long long init[4] = {0, (long long)n_steps, (long long)reinterpret_cast<uintptr_t>(images), 0};
+            const long long init[kHsStateSlots] = {0, (long long)n_steps, (long long)reinterpret_cast<uintptr_t>(images), 0, 0, 0};
             RCN_CUDA_TRY(cudaMemcpyAsync(st, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
             RCN_CUDA_TRY(cudaMemcpyAsync(h->tgt_stage.p, labels, n_steps * B * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
             RCN_CUDA_TRY(cudaMemcpyAsync(h->hs_ring.p, images, img_bytes, cudaMemcpyHostToDevice, h->stream));
@@ -929,45 +986,62 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
             key.B = B; key.H = H; key.W = W; key.n_steps = n_steps; key.scale = scale_s; key.labels = h->tgt_stage.p;
             key.stats = h->stats_host; key.ring = h->hs_ring.p; key.state = st; key.grads = h->grads; key.stream = h->stream;
             key.dp = h->dp.connected;
-            if (!h->hs_graph || !(key == h->hs_key)) {
+            if (!h->hs_graph || !h->hs_graph1 || !(key == h->hs_key)) {
                 if (h->hs_graph) { cudaGraphExecDestroy(h->hs_graph); h->hs_graph = nullptr; }
+                if (h->hs_graph1) { cudaGraphExecDestroy(h->hs_graph1); h->hs_graph1 = nullptr; }
                 // warm-up outside capture: reserves every scratch buffer and sets kernel attributes (no parameter update)
                 h->dp_push_suppress = true;
                 const int wrc = accumulate_images_dev(h, h->hs_ring.p, pixel_format, nullptr, B, H, W, &bi);
                 h->dp_push_suppress = false;
                 RCN_TRY(wrc);
                 RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
-                cudaGraph_t graph = nullptr;
-                RCN_CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-                int rc = RCN_OK;
-                do {
-                    if (cudaEventRecord(h->hs_fork, h->stream) != cudaSuccess || cudaStreamWaitEvent(h->copy_stream, h->hs_fork, 0) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph fork failed"); break; }
-                    {
-                        LaunchScope ls("host_prefetch_kernel", h->copy_stream);
-                        host_prefetch_kernel<<<32, 256, 0, h->copy_stream>>>(st, h->hs_ring.as<unsigned char>(), (long long)B, (long long)(H * W));
+                // `g` consecutive steps in ONE graph: a step is only tens of microseconds long, so the host's per-launch cost
+                // is spread over several of them; the remainder of the epoch replays the one-step graph.
+                auto capture_steps = [&](int g, cudaGraphExec_t* out) -> int {
+                    cudaGraph_t graph = nullptr;
+                    RCN_CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+                    int rc = RCN_OK;
+                    for (int q = 0; q < g && rc == RCN_OK; ++q) {
+                        if (cudaEventRecord(h->hs_fork, h->stream) != cudaSuccess || cudaStreamWaitEvent(h->copy_stream, h->hs_fork, 0) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph fork failed"); break; }
+                        {
+                            LaunchScope ls("host_prefetch_kernel", h->copy_stream);
+                            host_prefetch_kernel<<<32, 256, 0, h->copy_stream>>>(st, h->hs_ring.as<unsigned char>(), (long long)B, (long long)(H * W));
+                        }
+                        if (cudaPeekAtLastError() != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "prefetch kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+                        if (cudaEventRecord(h->hs_join, h->copy_stream) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph join failed"); break; }
+                        arm_fused_update(h, scale_s, st, (long long)B, (long long)(n_steps * B), h->stats_host);
+                        rc = accumulate_images_dev(h, h->hs_ring.p, pixel_format, nullptr, B, H, W, &bi);
+                        const bool fused = take_upd_fused(h);
+                        if (rc != RCN_OK) break;
+                        // the prefetch branch joins at the end of its step: the next step starts after both
+                        if (cudaStreamWaitEvent(h->stream, h->hs_join, 0) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph join failed"); break; }
+                        if (fused) continue;   // the weight-gradient kernel applied the update, advanced the cursor, wrote the result
+                        if (h->dp.connected)
+                            rc = launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale_s, h->stream, st, (long long)B,
+                                                         (long long)(n_steps * B), h->small.as<double>(), h->stats_host, take_dp_pushed(h));
+                        else
+                            rc = launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale_s, h->stream, st, (long long)B,
+                                                   (long long)(n_steps * B), h->small.as<double>(), h->stats_host);
                     }
-                    if (cudaPeekAtLastError() != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "prefetch kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
-                    if (cudaEventRecord(h->hs_join, h->copy_stream) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph join failed"); break; }
-                    rc = accumulate_images_dev(h, h->hs_ring.p, pixel_format, nullptr, B, H, W, &bi);
-                    if (rc != RCN_OK) break;
-                    if (cudaStreamWaitEvent(h->stream, h->hs_join, 0) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph join failed"); break; }
-                    if (h->dp.connected)
-                        rc = launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale_s, h->stream, st, (long long)B,
-                                                     (long long)(n_steps * B), h->small.as<double>(), h->stats_host, take_dp_pushed(h));
-                    else
-                        rc = launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale_s, h->stream, st, (long long)B,
-                                               (long long)(n_steps * B), h->small.as<double>(), h->stats_host);
-                } while (0);
-                cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-                if (rc != RCN_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
-                if (ce != cudaSuccess || !graph) return fail(RCN_ERR_CUDA, "stream capture of the training step failed: %s", cudaGetErrorString(ce));
-                ce = cudaGraphInstantiate(&h->hs_graph, graph, 0);
-                cudaGraphDestroy(graph);
-                if (ce != cudaSuccess) { h->hs_graph = nullptr; return fail(RCN_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
+                    cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+                    if (rc != RCN_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+                    if (ce != cudaSuccess || !graph) return fail(RCN_ERR_CUDA, "stream capture of the training step failed: %s", cudaGetErrorString(ce));
+                    ce = cudaGraphInstantiate(out, graph, 0);
+                    cudaGraphDestroy(graph);
+                    if (ce != cudaSuccess) { *out = nullptr; return fail(RCN_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
+                    return RCN_OK;
+                };
+                RCN_TRY(capture_steps(hs_steps_per_graph(), &h->hs_graph));
+                RCN_TRY(capture_steps(1, &h->hs_graph1));
                 h->hs_key = key;
             }
-            for (size_t k = 0; k < n_steps; ++k) RCN_CUDA_TRY(cudaGraphLaunch(h->hs_graph, h->stream));
-            g_launches.fetch_add((unsigned long long)n_steps * 4, std::memory_order_relaxed);   // prefetch + A + B + update per replay
+            {
+                size_t k = 0;
+                const size_t spg = (size_t)hs_steps_per_graph();
+                for (; k + spg <= n_steps; k += spg) RCN_CUDA_TRY(cudaGraphLaunch(h->hs_graph, h->stream));
+                for (; k < n_steps; ++k) RCN_CUDA_TRY(cudaGraphLaunch(h->hs_graph1, h->stream));
+            }
+            g_launches.fetch_add((unsigned long long)n_steps * (h->dp.connected ? 4 : 3), std::memory_order_relaxed);   // prefetch + A + B (+ exchange/update) per replay
             RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
             for (size_t k = 0; k < n_steps; ++k) {
                 if (cost_out) cost_out[k] = h->stats_host[2 * k];

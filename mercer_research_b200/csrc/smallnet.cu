@@ -22,6 +22,7 @@
 #include "dp.cuh"
 
 #include "features_device.cuh"
+#include "timeline.cuh"
 
 #include <cooperative_groups.h>
 
@@ -36,6 +37,15 @@ __device__ __forceinline__ void sn_dmma(double& c0, double& c1, double a, double
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
+
+// Optional phase clock (profiles/sn_phases.py builds a second library with -DRCN_SN_PHASES): thread 0 of every CTA of
+// kernel A stamps clock64() at the phase boundaries.  Compiled out of the product library.
+#ifdef RCN_SN_PHASES
+__device__ long long g_sn_phase[1024][8];
+#define SN_PHASE(k) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_sn_phase[blockIdx.x][k] = clock64(); } while (0)
+#else
+#define SN_PHASE(k) do { } while (0)
+#endif
 
 constexpr int SN_TB = 8;          // samples per CTA in kernel A (one DMMA n-fragment)
 constexpr int SNA_THREADS = 512;  // kernel A
@@ -105,6 +115,8 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
     const int s0 = blockIdx.x * SN_TB;
     const int L = d.n_in, R0 = d.rows[0];
     const int mf = (R0 + 7) >> 3;
+    SN_PHASE(0);
+    RCN_TL_BEGIN(0);
     const int pitch = L + SN_TILE_PAD;
     const int small_base = d.b_off[0];
     const int n_small = d.n_params - small_base;
@@ -143,8 +155,10 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
         for (int i = n_live * pitch + tid; i < SN_TB * pitch; i += SNA_THREADS) tile[i] = 0.0;   // absent samples
         __syncthreads();
         cpbulk::mbar_wait(&s_bar, 0);
+        SN_PHASE(1);
         cp_transpose_images(stg, fr.cp.stage_bytes, tiles, fr.cp.tile_ints, n_live, fr.H, fr.W, fr.cp, tid, SNA_THREADS);
         __syncthreads();
+        SN_PHASE(2);
         for (int q = 0; q < fr.cp.n; ++q) {
             const CpStage& st = fr.cp.s[q];
             const int items = st.n_in * st.h_out * st.w_out;
@@ -208,6 +222,7 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
         if (tid < SN_TB) s_label[tid] = (labels && s0 + tid < B) ? labels[s0 + tid] : -1;
     }
 
+    SN_PHASE(3);
     // ---- layer 0: z = W0 a0 on DMMA, K split across the 16 warps ----------------------------------------------------
     {
         const double* __restrict__ W0 = params + d.w_off[0];
@@ -251,6 +266,7 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
         }
     }
     __syncthreads();
+    SN_PHASE(4);
     if (tid >= 32 * SN_TB) return;   // the narrow part needs one thread per (sample, neuron); no barriers below use the rest
 
     // NOTE: only warps 0..7 continue; they synchronise with a named barrier of 256 threads.
@@ -288,6 +304,7 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
     }
     const int last = d.n_layers - 1;
     const int RL = d.rows[last];
+    SN_PHASE(5);
     // ---- activations out ---------------------------------------------------------------------------------------------
     {
         size_t off = 0;
@@ -296,7 +313,7 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
             off += d.rows[l];
         }
     }
-    if (!backward) return;
+    if (!backward) { RCN_TL_END(0); return; }
     // ---- output delta (rcn.rs:299) and batch statistics (rcn.rs:152-157) --------------------------------------------
     double y = 0.0;
     if (m < RL && live) y = onehot ? onehot[(size_t)sample * RL + m] : ((s_label[n] == (long long)m) ? 1.0 : 0.0);
@@ -349,6 +366,7 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
             off += d.rows[l];
         }
     }
+    SN_PHASE(6);
     if (tid == 0) {
         double c = 0.0;
         unsigned long long h = 0;
@@ -380,6 +398,8 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
             small_partial[(size_t)blockIdx.x * n_small + o] = acc;
         }
     }
+    SN_PHASE(7);
+    RCN_TL_END(0);
 #undef SN_BAR
 }
 
@@ -392,16 +412,22 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
 // ------------------------------------------------------------------------------------------------
 constexpr int SNB_TILE = 32 * 64;   // padded partial tile: 32 rows x 64 columns
 
-template <bool DP>   // DP: also push the final values into the data-parallel peers' receive slots (dp.cu protocol)
+// MODE 1: also push the final values into the data-parallel peers' receive slots (dp.cu protocol); MODE 2: single GPU,
+// apply the SGD update to the finished elements right here (SnUpdate); MODE 0: gradients only.
+template <int MODE>
 __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __grid_constant__ SmallNetDesc d,
                                                                      const double* __restrict__ feats,
                                                                      const double* __restrict__ small_partial,
                                                                      const double* __restrict__ deltas, int B, int ksplit,
                                                                      int col_groups, double* __restrict__ grads,
                                                                      const double* __restrict__ stats_partial, int n_stat,
-                                                                     double* __restrict__ stats, const __grid_constant__ DpPush dp) {
+                                                                     double* __restrict__ stats, const __grid_constant__ DpPush dp,
+                                                                     const __grid_constant__ SnUpdate upd) {
+    constexpr bool DP = MODE == 1;
+    constexpr bool UPD = MODE == 2;
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
+    RCN_TL_BEGIN(1);
     __shared__ __align__(16) double sD[2][64 * SN_DPITCH];   // double-buffered 64-sample delta_0 chunk (36 KB)
     extern __shared__ __align__(16) double sP[];              // partial tile: SNB_TILE (col CTAs) or n_small doubles
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -489,21 +515,25 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
     // exchange overlaps this kernel's tail and the launch of the update kernel
     const size_t dp_par = DP ? dp_push_parity_offset(dp) : 0;
     for (int o = o_lo + tid; o < o_hi; o += SNB_THREADS) {
+        // destination first: the old parameter value (fused update) is in flight while the peers' partials are read
+        long long gi = -1;
+        if (is_col) {
+            const int m = o & 31, col = blockIdx.x * 64 + (o >> 5);
+            if (m < R0 && col < L) gi = d.w_off[0] + (long long)col * R0 + m;
+        } else {
+            gi = small_base + o;
+        }
+        double pold = 0.0;
+        if (UPD && gi >= 0) pold = upd.params[gi];
         double s = 0.0;
         for (int q = 0; q < S; ++q) {
             const double* remote = cluster.map_shared_rank(sP, q);
             s += remote[o];
         }
-        if (is_col) {
-            const int m = o & 31, col = blockIdx.x * 64 + (o >> 5);
-            if (m < R0 && col < L) {
-                const size_t gi = d.w_off[0] + (size_t)col * R0 + m;
-                grads[gi] = s;
-                if (DP) dp_push_value(dp, dp_par, gi, s);
-            }
-        } else {
-            grads[small_base + o] = s;
-            if (DP) dp_push_value(dp, dp_par, (size_t)(small_base + o), s);
+        if (gi >= 0) {
+            grads[gi] = s;
+            if (DP) dp_push_value(dp, dp_par, (size_t)gi, s);
+            if (UPD) upd.params[gi] = sgd_apply(pold, upd.scale, s);
         }
     }
     if (!is_col && rank == 0 && tid < 32 && stats) {
@@ -523,9 +553,20 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
         if (tid == 0) {
             stats[0] = c;
             reinterpret_cast<unsigned long long*>(stats)[1] = h;
+            if (UPD && upd.cursor) {   // what sgd_update_kernel does on the side (kernel A of this step is long done)
+                if (upd.stats_ring) {
+                    double* dst = upd.stats_ring + 2 * (*upd.cursor / upd.batch);
+                    dst[0] = c;
+                    reinterpret_cast<unsigned long long*>(dst)[1] = h;
+                }
+                long long cur = *upd.cursor + upd.batch;   // next chunk of chunks_exact(batch) (rcn.rs:147), remainder dropped
+                if (cur + upd.batch > upd.n_samples) cur = 0;
+                *upd.cursor = cur;
+            }
         }
     }
     cluster.sync();   // nobody leaves while a peer may still read its tile
+    RCN_TL_END(1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -609,7 +650,8 @@ int launch_smallnet_forward(const SmallNetDesc& d, const double* params, double*
 
 int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double* feats, size_t B, const double* onehot,
                              const int64_t* labels, double* acts, double* deltas, double* grads, double* stats,
-                             DevBuf& workspace, const SmallNetFront* front, cudaStream_t stream, const DpPush* dp_push) {
+                             DevBuf& workspace, const SmallNetFront* front, cudaStream_t stream, const DpPush* dp_push,
+                             const SnUpdate* update) {
     if (B == 0) return RCN_OK;
     if (B > smallnet_max_batch()) return fail(RCN_ERR_INVALID, "batch too large for the fused small-network path");
     int splits, ksplit;
@@ -628,10 +670,15 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
     push.world = 1;
     if (dp_push) push = *dp_push;
     const bool with_push = push.world > 1;
-    static SmemAttrCache attr_b[2];
-    if (attr_b[with_push].need(smem_b)) {  // static 36 KB + dynamic tile exceeds the 48 KB default
-        if (with_push) RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-        else RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    SnUpdate upd{};
+    if (update && !with_push) upd = *update;
+    const int mode = with_push ? 1 : (upd.params ? 2 : 0);
+    static SmemAttrCache attr_b;
+    if (attr_b.need(smem_b)) {  // static 36 KB + dynamic tile exceeds the 48 KB default; all variants at once (a later
+                                // launch of another variant may happen inside a stream capture)
+        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(col_groups + 1, splits, 1);
@@ -646,18 +693,21 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const int Bi = (int)B;
-    if (with_push) {
-        RCN_LAUNCH("smallnet_wgrad_kernel", stream,
-                   cudaLaunchKernelEx(&cfg, smallnet_wgrad_kernel<true>, d, (const double*)feats, (const double*)small_partial,
-                                      (const double*)deltas, Bi, ksplit, col_groups, grads, (const double*)stats_partial, n_tiles,
-                                      stats, push));
-    } else {
-        RCN_LAUNCH("smallnet_wgrad_kernel", stream,
-                   cudaLaunchKernelEx(&cfg, smallnet_wgrad_kernel<false>, d, (const double*)feats, (const double*)small_partial,
-                                      (const double*)deltas, Bi, ksplit, col_groups, grads, (const double*)stats_partial, n_tiles,
-                                      stats, push));
-    }
+    auto kern = mode == 1 ? smallnet_wgrad_kernel<1> : mode == 2 ? smallnet_wgrad_kernel<2> : smallnet_wgrad_kernel<0>;
+    RCN_LAUNCH(mode == 2 ? "smallnet_wgrad_kernel(+SGD update)" : "smallnet_wgrad_kernel", stream,
+               cudaLaunchKernelEx(&cfg, kern, d, (const double*)feats, (const double*)small_partial, (const double*)deltas, Bi,
+                                  ksplit, col_groups, grads, (const double*)stats_partial, n_tiles, stats, push, upd));
     return RCN_OK;
 }
 
 }  // namespace rcn
+
+#ifdef RCN_TIMELINE
+extern "C" int rcn_cuda_debug_timeline_reset_smallnet() { return rcn_tl::reset_host(); }
+extern "C" int rcn_cuda_debug_timeline_read_smallnet(unsigned long long* out, unsigned* seq) { return rcn_tl::read_host(out, seq); }
+#endif
+#ifdef RCN_SN_PHASES
+extern "C" int rcn_cuda_debug_sn_phases(long long* out /* [1024][8] */) {
+    return cudaMemcpyFromSymbol(out, rcn::g_sn_phase, sizeof(rcn::g_sn_phase)) == cudaSuccess ? 0 : 4;
+}
+#endif

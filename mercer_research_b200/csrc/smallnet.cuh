@@ -32,6 +32,17 @@ struct SmallNetFront {
 // Fills use_cp / cp: the staged front end needs a qualifying plan, 16-byte aligned images and H*W % 16 == 0.
 void smallnet_front_select(const FeaturePlan& plan, SmallNetFront* fr);
 
+// Single-GPU steps fold the SGD update (rcn.rs:210-222) into the weight-gradient kernel: every CTA applies
+// W -= scale * sum to exactly the elements whose batch sum it has just finished (one kernel and one launch gap less per
+// step).  Also carries what sgd_update_kernel does on the side: the epoch cursor (rcn.rs:147) and the per-step result ring.
+struct SnUpdate {
+    double* params;          // nullptr = no fused update
+    double scale;            // eta / B
+    long long* cursor;       // optional epoch cursor, advanced by `batch` with chunks_exact wrap-around
+    long long batch, n_samples;
+    double* stats_ring;      // optional (pinned host) {cost, hits} per step
+};
+
 bool smallnet_eligible(const SmallNetDesc& d);
 size_t smallnet_max_batch();
 bool smallnet_front_fits(const SmallNetDesc& d, const SmallNetFront& fr);
@@ -45,6 +56,6 @@ int launch_smallnet_forward(const SmallNetDesc& d, const double* params, double*
 int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double* feats, size_t B, const double* onehot,
                              const int64_t* labels, double* acts, double* deltas, double* grads, double* stats,
                              DevBuf& workspace, const SmallNetFront* front, cudaStream_t stream,
-                             const DpPush* dp_push = nullptr);
+                             const DpPush* dp_push = nullptr, const SnUpdate* update = nullptr);
 
 }  // namespace rcn

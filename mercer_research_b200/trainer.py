@@ -65,6 +65,9 @@ class DataParallelTrainer:
 
     def step_images(self, images, labels):
         """images: this rank's shard, (B_local, H, W) uint8 / float64 (torch CUDA tensor or numpy); labels (B_local,)."""
+        if self.world == 1:   # one call: the library may fold the update into the weight-gradient kernel
+            self.model.train_batch_images(images, labels, self.eta)
+            return
         self.model.accumulate_gradients_images(images, labels)
         self._reduce_and_apply(int(images.shape[0]))
 
@@ -107,14 +110,19 @@ class DataParallelTrainer:
     def _epoch_step_eager(self):
         import torch
         self.model.set_stream(torch.cuda.current_stream().cuda_stream)
+        if self.world == 1:   # one call: the library may fold the update into the weight-gradient kernel
+            self.model.epoch_step(self.eta)
+            return
         self.model.epoch_accumulate()
         if self.world > 1 and not self.p2p:
             self.dist.all_reduce(self.grads, op=self.dist.ReduceOp.SUM, group=self.group)
         self.model.epoch_apply(self.eta, self.local_batch * self.world)
 
-    def capture(self, warmup: int = 3):
-        """Captures one epoch step (kernels + the NCCL all-reduce) into a CUDA graph; later epoch_step() calls replay
-        it. The batch selection lives in device memory, so the same graph serves every step of every epoch."""
+    def capture(self, warmup: int = 3, steps_per_graph: int = 1):
+        """Captures ``steps_per_graph`` consecutive epoch steps (kernels + the NCCL all-reduce) into ONE CUDA graph; later
+        epoch_step() / epoch_steps() calls replay it. The batch selection lives in device memory, so the same graph serves
+        every step of every epoch; several steps per graph take the host's per-launch cost off steps that are only a few
+        tens of microseconds long."""
         import torch
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -125,21 +133,35 @@ class DataParallelTrainer:
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self._epoch_step_eager()
+            for _ in range(max(1, int(steps_per_graph))):
+                self._epoch_step_eager()
         self.graph = graph
+        self.steps_per_graph = max(1, int(steps_per_graph))
         self.model.set_stream(torch.cuda.current_stream().cuda_stream)
         self.model.epoch_seek(0)
         return graph
 
     def epoch_step(self):
+        """One step (eager), or one replay of the captured graph (= ``steps_per_graph`` steps)."""
         if getattr(self, "graph", None) is not None:
             self.graph.replay()
         else:
             self._epoch_step_eager()
 
+    def epoch_steps(self, n: int):
+        """Exactly ``n`` steps: whole graph replays, the remainder eagerly."""
+        spg = getattr(self, "steps_per_graph", 1) if getattr(self, "graph", None) is not None else 0
+        if spg:
+            for _ in range(n // spg):
+                self.graph.replay()
+            n -= (n // spg) * spg
+        for _ in range(n):
+            self._epoch_step_eager()
+
     def describe(self) -> str:
         if self.world == 1:
-            ar = "none (1 GPU) -> SGD update"
+            ar = ("none (1 GPU) -> SGD update (narrow networks: applied by the weight-gradient kernel itself, "
+                  "no separate launch)")
         elif self.p2p:
             ar = (f"gradient exchange of {self.model.n_params} f64 over NVLink peer memory fused with the SGD update "
                   "(one kernel, rank-ordered sum)")
