@@ -53,6 +53,8 @@ constexpr int SNA_WARPS = 16;
 constexpr int SNB_THREADS = 256;  // kernel B
 constexpr int SN_TILE_PAD = 4;    // a0 tile row pitch = n_in + 4 doubles: conflict-free B-fragment reads
 constexpr int SN_DPITCH = 36;     // delta slice row pitch (doubles): conflict-free A-fragment reads
+constexpr int SN_U = 7;           // k-steps of W0 fragments a warp keeps in registers
+constexpr int SN_ZPITCH = 36;     // layer-0 partial sums [warp][sample][36]: conflict-free for the DMMA C fragments and the row reads
 constexpr int SN_MAX_SMALL = 32 + (kSmallNetMaxLayers - 1) * (32 * 32 + 32);  // params after W0
 
 // final-stage emit of the fused front end: standardised feature -> shared tile + HBM
@@ -101,8 +103,8 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
                         double* __restrict__ stats_partial, double* __restrict__ small_partial, int backward,
                         const __grid_constant__ SmallNetFront fr) {
     extern __shared__ __align__(128) unsigned char sn_smem[];
-    double* zpart = reinterpret_cast<double*>(sn_smem);                 // [16][32][8]
-    double* s_small = zpart + SNA_WARPS * 32 * SN_TB;                   // params after W0: b0 | W1 | b1 | ...
+    double* zpart = reinterpret_cast<double*>(sn_smem);                 // [16][8][36]
+    double* s_small = zpart + SNA_WARPS * SN_TB * SN_ZPITCH;                   // params after W0: b0 | W1 | b1 | ...
     double* tile = s_small + SN_MAX_SMALL;                              // FUSED: [8][n_in + 4]
     __shared__ double s_act[kSmallNetMaxLayers][SN_TB][33];
     __shared__ double s_del[kSmallNetMaxLayers][SN_TB][33];
@@ -121,15 +123,10 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
     const int small_base = d.b_off[0];
     const int n_small = d.n_params - small_base;
 
-    // prefetch biases + narrow-layer weights (overlaps with the front end / the DMMA phase)
-    for (int i = tid; i < n_small; i += SNA_THREADS) s_small[i] = __ldg(params + small_base + i);
-
+    // staged front end: the image loads go out before anything else asks the memory system for data
+    __shared__ __align__(8) uint64_t s_bar;
+    unsigned char* stg = sn_align128(tile + SN_TB * pitch);
     if (FUSED == 2) {
-        // ---- staged front end: the 8 images arrive by bulk-async copies while the tiles' zero frames are written; then
-        // all 16 warps transpose and run the conv+pool stages over the 8 images together (features_device.cuh) ---------
-        __shared__ __align__(8) uint64_t s_bar;
-        unsigned char* stg = sn_align128(tile + SN_TB * pitch);
-        int* tiles = reinterpret_cast<int*>(stg + SN_TB * fr.cp.stage_bytes);
         const int n_live = min(SN_TB, B - s0);
         const uint32_t img_bytes = (uint32_t)(fr.H * fr.W);
         if (warp == 0) {
@@ -151,6 +148,40 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
                 s_label[lane] = lab;
             }
         }
+    }
+    // prefetch biases + narrow-layer weights (overlaps with the front end / the DMMA phase)
+    for (int i = tid; i < n_small; i += SNA_THREADS) s_small[i] = __ldg(params + small_base + i);
+
+    // layer-0 weight fragments: each warp owns a K range of the n_in-deep contraction; its first SN_U k-steps go into
+    // registers NOW and the rest is prefetched into L1, so the L2 latency is hidden behind the front end
+    const double* __restrict__ W0 = params + d.w_off[0];
+    const int ksteps = (L + 3) >> 2;
+    const int per_warp = (ksteps + SNA_WARPS - 1) / SNA_WARPS;
+    const int ks_begin = warp * per_warp;
+    const int ks_end = min(ksteps, ks_begin + per_warp);
+    bool rowok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rowok[i] = (i < mf) && (i * 8 + g < R0);
+    double w_pre[SN_U][4];
+#pragma unroll
+    for (int u = 0; u < SN_U; ++u) {
+        const int k = (ks_begin + u) * 4 + t;
+        const bool kok = (ks_begin + u) < ks_end && k < L;
+        const double* wp = W0 + (size_t)k * R0 + g;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w_pre[u][i] = (kok && rowok[i]) ? __ldg(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
+    }
+    {
+        const long long lo = (long long)min((ks_begin + SN_U) * 4, L) * R0, hi = (long long)min(ks_end * 4, L) * R0;   // doubles
+        for (long long e = lo + lane * 16; e < hi; e += 32 * 16)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(W0 + e));
+    }
+
+    if (FUSED == 2) {
+        // ---- staged front end: the 8 images arrive by bulk-async copies while the tiles' zero frames are written; then
+        // all 16 warps transpose and run the conv+pool stages over the 8 images together (features_device.cuh) ---------
+        int* tiles = reinterpret_cast<int*>(stg + SN_TB * fr.cp.stage_bytes);
+        const int n_live = min(SN_TB, B - s0);
         for (int i = tid; i < SN_TB * fr.cp.tile_ints; i += SNA_THREADS) tiles[i] = 0;
         for (int i = n_live * pitch + tid; i < SN_TB * pitch; i += SNA_THREADS) tile[i] = 0.0;   // absent samples
         __syncthreads();
@@ -224,183 +255,198 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
 
     SN_PHASE(3);
     // ---- layer 0: z = W0 a0 on DMMA, K split across the 16 warps ----------------------------------------------------
+    // The first U k-steps of this warp's W0 fragments were loaded into registers at the very top (w_pre), the rest of
+    // its K range was prefetched into L1: the L2 round trips overlap the front end instead of following it.
     {
-        const double* __restrict__ W0 = params + d.w_off[0];
-        const int ksteps = (L + 3) >> 2;
-        const int per = (ksteps + SNA_WARPS - 1) / SNA_WARPS;
-        const int ks_begin = warp * per;
-        const int ks_end = min(ksteps, ks_begin + per);
         double acc[4][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.0;
-        bool rowok[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) rowok[i] = (i < mf) && (i * 8 + g < R0);
         const int sample = s0 + g;
         const bool sample_ok = sample < B;
         const double* __restrict__ frow = feats + (size_t)(sample_ok ? sample : 0) * L;
         const double* trow = tile + (size_t)g * pitch;
-        constexpr int U = 7;
-        for (int ks = ks_begin; ks < ks_end; ks += U) {
-            double af[U][4], bf[U];
+        {
+            double bf[SN_U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
+            for (int u = 0; u < SN_U; ++u) {
+                const int k = (ks_begin + u) * 4 + t;
+                const bool kok = (ks_begin + u) < ks_end && k < L;
+                if (FUSED) bf[u] = kok ? trow[k] : 0.0;                                        // B frag: row t (k), col g (sample)
+                else bf[u] = (kok && sample_ok) ? __ldg(frow + k) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < SN_U; ++u)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < mf) sn_dmma(acc[i][0], acc[i][1], w_pre[u][i], bf[u]);
+        }
+        for (int ks = ks_begin + SN_U; ks < ks_end; ks += SN_U) {
+            double af[SN_U][4], bf[SN_U];
+#pragma unroll
+            for (int u = 0; u < SN_U; ++u) {
                 const int k = (ks + u) * 4 + t;
                 const bool kok = (ks + u) < ks_end && k < L;
                 const double* wp = W0 + (size_t)k * R0 + g;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) af[u][i] = (kok && rowok[i]) ? __ldg(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
-                if (FUSED) bf[u] = kok ? trow[k] : 0.0;                                        // B frag: row t (k), col g (sample)
+                if (FUSED) bf[u] = kok ? trow[k] : 0.0;
                 else bf[u] = (kok && sample_ok) ? __ldg(frow + k) : 0.0;
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u)
+            for (int u = 0; u < SN_U; ++u)
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     if (i < mf) sn_dmma(acc[i][0], acc[i][1], af[u][i], bf[u]);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {  // C frag: row g (m), cols 2t, 2t+1 (sample)
-            zpart[(warp * 32 + i * 8 + g) * SN_TB + 2 * t] = acc[i][0];
-            zpart[(warp * 32 + i * 8 + g) * SN_TB + 2 * t + 1] = acc[i][1];
+        for (int i = 0; i < 4; ++i) {  // C frag: row g (m), cols 2t, 2t+1 (sample); [warp][sample][36]: conflict-free both ways
+            zpart[(warp * SN_TB + 2 * t) * SN_ZPITCH + i * 8 + g] = acc[i][0];
+            zpart[(warp * SN_TB + 2 * t + 1) * SN_ZPITCH + i * 8 + g] = acc[i][1];
         }
     }
     __syncthreads();
     SN_PHASE(4);
-    if (tid >= 32 * SN_TB) return;   // the narrow part needs one thread per (sample, neuron); no barriers below use the rest
-
-    // NOTE: only warps 0..7 continue; they synchronise with a named barrier of 256 threads.
-#define SN_BAR() asm volatile("bar.sync 1, 256;" ::: "memory")
-    const int n = tid >> 5;       // sample within the tile
-    const int m = tid & 31;       // neuron
-    const int sample = s0 + n;
-    const bool live = sample < B;
-    {
-        double z = 0.0;
-#pragma unroll
-        for (int w = 0; w < SNA_WARPS; ++w) z += zpart[(w * 32 + m) * SN_TB + n];
-        if (m < R0) {
-            z = z + s_small[m];                         // w * a + b      (rcn.rs:287)
-            s_act[0][n][m] = sn_sigmoid(z);             // sigmoid(&z)    (rcn.rs:289)
-        }
-    }
-    SN_BAR();
-    // ---- narrow layers ---------------------------------------------------------------------------------------------
-    for (int l = 1; l < d.n_layers; ++l) {
-        const int R = d.rows[l], C = d.rows[l - 1];
-        if (m < R) {
-            const double* W = s_small + (d.w_off[l] - small_base);
-            double z0 = 0.0, z1 = 0.0;
-            int k = 0;
-            for (; k + 1 < C; k += 2) {
-                z0 = fma(W[k * R + m], s_act[l - 1][n][k], z0);
-                z1 = fma(W[(k + 1) * R + m], s_act[l - 1][n][k + 1], z1);
-            }
-            if (k < C) z0 = fma(W[k * R + m], s_act[l - 1][n][k], z0);
-            const double z = (z0 + z1) + s_small[d.b_off[l] - small_base + m];
-            s_act[l][n][m] = sn_sigmoid(z);
-        }
-        SN_BAR();
-    }
     const int last = d.n_layers - 1;
     const int RL = d.rows[last];
-    SN_PHASE(5);
-    // ---- activations out ---------------------------------------------------------------------------------------------
-    {
-        size_t off = 0;
-        for (int l = 0; l < d.n_layers; ++l) {
-            if (live && m < d.rows[l]) acts[off * B + (size_t)sample * d.rows[l] + m] = s_act[l][n][m];
-            off += d.rows[l];
+    // ---- narrow part: warp n owns sample n from here to its deltas (lane = neuron), so the layers only need warp-level
+    // synchronisation; warps 8..15 rejoin for the gradient partials.
+    if (warp < SN_TB) {
+        const int n = warp;           // sample within the tile
+        const int m = lane;           // neuron
+        const int sample = s0 + n;
+        const bool live = sample < B;
+        {
+            double zp[SNA_WARPS];
+#pragma unroll
+            for (int w = 0; w < SNA_WARPS; ++w) zp[w] = zpart[(w * SN_TB + n) * SN_ZPITCH + m];
+#pragma unroll
+            for (int o = 1; o < SNA_WARPS; o <<= 1)      // fixed pairwise tree over the 16 K-splits
+#pragma unroll
+                for (int w = 0; w < SNA_WARPS; w += 2 * o) zp[w] += zp[w + o];
+            if (m < R0) {
+                const double z = zp[0] + s_small[m];            // w * a + b      (rcn.rs:287)
+                s_act[0][n][m] = sn_sigmoid(z);                 // sigmoid(&z)    (rcn.rs:289)
+            }
+        }
+        __syncwarp();
+        // ---- narrow layers -----------------------------------------------------------------------------------------
+        for (int l = 1; l < d.n_layers; ++l) {
+            const int R = d.rows[l], C = d.rows[l - 1];
+            if (m < R) {
+                const double* W = s_small + (d.w_off[l] - small_base);
+                double z0 = 0.0, z1 = 0.0;
+                int k = 0;
+                for (; k + 1 < C; k += 2) {
+                    z0 = fma(W[k * R + m], s_act[l - 1][n][k], z0);
+                    z1 = fma(W[(k + 1) * R + m], s_act[l - 1][n][k + 1], z1);
+                }
+                if (k < C) z0 = fma(W[k * R + m], s_act[l - 1][n][k], z0);
+                const double z = (z0 + z1) + s_small[d.b_off[l] - small_base + m];
+                s_act[l][n][m] = sn_sigmoid(z);
+            }
+            __syncwarp();
+        }
+        SN_PHASE(5);
+        // ---- activations out ---------------------------------------------------------------------------------------
+        {
+            size_t off = 0;
+            for (int l = 0; l < d.n_layers; ++l) {
+                if (live && m < d.rows[l]) acts[off * B + (size_t)sample * d.rows[l] + m] = s_act[l][n][m];
+                off += d.rows[l];
+            }
+        }
+        if (backward) {
+            // ---- output delta (rcn.rs:299) and batch statistics (rcn.rs:152-157) ---------------------------------------
+            const bool out = m < RL;
+            double y = 0.0;
+            if (out && live) y = onehot ? onehot[(size_t)sample * RL + m] : ((s_label[n] == (long long)m) ? 1.0 : 0.0);
+            const double a = out ? s_act[last][n][m] : 0.0;
+            if (out) s_del[last][n][m] = (a - y) * (a * (1.0 - a));
+            {
+                double mx = out ? a : -1.0;                        // activations are in (0, 1)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                const bool ok = __all_sync(0xffffffffu, !out || (((a == mx) ? 1.0 : 0.0) == y));
+                const double df = a - y;
+                const double sq = df * df;
+                double cost = 0.0;
+                for (int i = 0; i < RL; ++i) cost += __shfl_sync(0xffffffffu, sq, i);   // neuron order, like the serial sum
+                if (m == 0) {
+                    s_cost[n] = live ? cost * 0.5 : 0.0;
+                    s_hit[n] = (live && ok) ? 1ull : 0ull;
+                }
+            }
+            __syncwarp();
+            // ---- backward-data chain (rcn.rs:305-309) -------------------------------------------------------------------
+            for (int l = last - 1; l >= 0; --l) {
+                const int R = d.rows[l], Ru = d.rows[l + 1];
+                if (m < R) {
+                    const double* Wu = s_small + (d.w_off[l + 1] - small_base);  // Ru x R column-major: (k, m) at m*Ru + k
+                    double v0 = 0.0, v1 = 0.0;
+                    int k = 0;
+                    for (; k + 1 < Ru; k += 2) {
+                        v0 = fma(Wu[m * Ru + k], s_del[l + 1][n][k], v0);
+                        v1 = fma(Wu[m * Ru + k + 1], s_del[l + 1][n][k + 1], v1);
+                    }
+                    if (k < Ru) v0 = fma(Wu[m * Ru + k], s_del[l + 1][n][k], v0);
+                    const double al = s_act[l][n][m];
+                    s_del[l][n][m] = (v0 + v1) * (al * (1.0 - al));
+                }
+                __syncwarp();
+            }
+            size_t off = 0;
+            for (int l = 0; l < d.n_layers; ++l) {
+                if (live && m < d.rows[l]) deltas[off * B + (size_t)sample * d.rows[l] + m] = s_del[l][n][m];
+                off += d.rows[l];
+            }
         }
     }
     if (!backward) { RCN_TL_END(0); return; }
-    // ---- output delta (rcn.rs:299) and batch statistics (rcn.rs:152-157) --------------------------------------------
-    double y = 0.0;
-    if (m < RL && live) y = onehot ? onehot[(size_t)sample * RL + m] : ((s_label[n] == (long long)m) ? 1.0 : 0.0);
-    if (m < RL) {
-        const double a = s_act[last][n][m];
-        s_del[last][n][m] = (a - y) * (a * (1.0 - a));
-    }
-    if (m == 0) {
-        double cost = 0.0;
-        unsigned long long hit = 0;
-        if (live) {
-            double mx = s_act[last][n][0];
-            for (int i = 1; i < RL; ++i) mx = fmax(mx, s_act[last][n][i]);
-            bool ok = true;
-            for (int i = 0; i < RL; ++i) {
-                const double yi = onehot ? onehot[(size_t)sample * RL + i] : ((s_label[n] == (long long)i) ? 1.0 : 0.0);
-                const double a = s_act[last][n][i];
-                const double df = a - yi;
-                cost += df * df;
-                ok = ok && (((a == mx) ? 1.0 : 0.0) == yi);
-            }
-            cost *= 0.5;
-            hit = ok ? 1ull : 0ull;
-        }
-        s_cost[n] = cost;
-        s_hit[n] = hit;
-    }
-    SN_BAR();
-    // ---- backward-data chain (rcn.rs:305-309) -------------------------------------------------------------------------
-    for (int l = last - 1; l >= 0; --l) {
-        const int R = d.rows[l], Ru = d.rows[l + 1];
-        if (m < R) {
-            const double* Wu = s_small + (d.w_off[l + 1] - small_base);  // Ru x R column-major: (k, m) at m*Ru + k
-            double v0 = 0.0, v1 = 0.0;
-            int k = 0;
-            for (; k + 1 < Ru; k += 2) {
-                v0 = fma(Wu[m * Ru + k], s_del[l + 1][n][k], v0);
-                v1 = fma(Wu[m * Ru + k + 1], s_del[l + 1][n][k + 1], v1);
-            }
-            if (k < Ru) v0 = fma(Wu[m * Ru + k], s_del[l + 1][n][k], v0);
-            const double a = s_act[l][n][m];
-            s_del[l][n][m] = (v0 + v1) * (a * (1.0 - a));
-        }
-        SN_BAR();
-    }
-    {
-        size_t off = 0;
-        for (int l = 0; l < d.n_layers; ++l) {
-            if (live && m < d.rows[l]) deltas[off * B + (size_t)sample * d.rows[l] + m] = s_del[l][n][m];
-            off += d.rows[l];
-        }
-    }
+    __syncthreads();
     SN_PHASE(6);
-    if (tid == 0) {
+    if (tid == SNA_THREADS - 32) {   // a warp with the fewest partial tasks below
         double c = 0.0;
         unsigned long long h = 0;
+#pragma unroll
         for (int i = 0; i < SN_TB; ++i) { c += s_cost[i]; h += s_hit[i]; }
         stats_partial[2 * blockIdx.x] = c;
         reinterpret_cast<unsigned long long*>(stats_partial)[2 * blockIdx.x + 1] = h;
     }
     // ---- this tile's share of db_l (all layers) and dW_l (narrow layers): everything is already in shared memory.
-    // One value per entry of the "small" parameter block b0|W1|b1|...; kernel B sums the tiles in index order.
+    // One value per entry of the "small" parameter block b0|W1|b1|...; kernel B sums the tiles in index order.  A task is
+    // one bias vector or one column k of a dW_l (lane = row), dealt round-robin to the 16 warps; samples added in order.
     {
         const int n_live = min(SN_TB, B - s0);
-        for (int o = tid; o < n_small; o += 32 * SN_TB) {
-            const int p = o + small_base;
-            double acc = 0.0;
-            for (int l = 0; l < d.n_layers; ++l) {
-                const int R = d.rows[l];
-                if (p >= d.b_off[l] && p < d.b_off[l] + R) {                 // db_l = sum_b delta_l      (rcn.rs:302,309)
-                    const int mr = p - d.b_off[l];
-                    for (int b = 0; b < n_live; ++b) acc += s_del[l][b][mr];
-                    break;
-                }
-                if (l >= 1 && p >= d.w_off[l] && p < d.b_off[l]) {           // dW_l = sum_b delta_l a_{l-1}^T (rcn.rs:303,310)
-                    const int q = p - d.w_off[l];
-                    const int mr = q % R, k = q / R;
-                    for (int b = 0; b < n_live; ++b) acc = fma(s_del[l][b][mr], s_act[l - 1][b][k], acc);
-                    break;
-                }
+        double* sp = small_partial + (size_t)blockIdx.x * n_small;
+        int task = 0;
+        for (int l = 0; l < d.n_layers; ++l) {
+            const int R = d.rows[l];
+            if ((task++ & (SNA_WARPS - 1)) == warp && lane < R) {        // db_l = sum_b delta_l      (rcn.rs:302,309)
+                double v[SN_TB];
+#pragma unroll
+                for (int b = 0; b < SN_TB; ++b) v[b] = s_del[l][b][lane];
+                double acc = 0.0;
+#pragma unroll
+                for (int b = 0; b < SN_TB; ++b) if (b < n_live) acc += v[b];
+                sp[d.b_off[l] - small_base + lane] = acc;
             }
-            small_partial[(size_t)blockIdx.x * n_small + o] = acc;
+            if (l >= 1) {
+                const int C = d.rows[l - 1];
+                for (int k = 0; k < C; ++k)
+                    if ((task++ & (SNA_WARPS - 1)) == warp && lane < R) {   // dW_l = sum_b delta_l a_{l-1}^T (rcn.rs:303,310)
+                        double v[SN_TB], a[SN_TB];
+#pragma unroll
+                        for (int b = 0; b < SN_TB; ++b) { v[b] = s_del[l][b][lane]; a[b] = s_act[l - 1][b][k]; }
+                        double acc = 0.0;
+#pragma unroll
+                        for (int b = 0; b < SN_TB; ++b) if (b < n_live) acc = fma(v[b], a[b], acc);
+                        sp[d.w_off[l] - small_base + k * R + lane] = acc;
+                    }
+            }
         }
     }
     SN_PHASE(7);
     RCN_TL_END(0);
-#undef SN_BAR
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -593,7 +639,7 @@ static void smallnet_splits(size_t B, int* splits, int* ksplit) {
 size_t smallnet_max_batch() { return (size_t)1 << 22; }
 
 static size_t kernel_a_smem(const SmallNetDesc& d, const SmallNetFront* fr) {
-    size_t bytes = ((size_t)SNA_WARPS * 32 * SN_TB + SN_MAX_SMALL) * sizeof(double);
+    size_t bytes = ((size_t)SNA_WARPS * SN_TB * SN_ZPITCH + SN_MAX_SMALL) * sizeof(double);
     if (fr) {
         bytes += (size_t)SN_TB * (d.n_in + SN_TILE_PAD) * sizeof(double);
         if (fr->use_cp) bytes += 128 + (size_t)SN_TB * ((size_t)fr->cp.stage_bytes + (size_t)fr->cp.tile_ints * sizeof(int));
