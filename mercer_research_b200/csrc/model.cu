@@ -67,6 +67,9 @@ LaunchScope::~LaunchScope() {
 // cursor update at the end of step k) reads chunk k+1 straight from pinned host memory (zero-copy loads over PCIe, 16 B
 // per thread, coalesced) into ring slot (k+1) % 2 while the training kernels of chunk k run on the other branch.
 constexpr int kHsStateSlots = 6;
+// the streamed epoch's cursor never wraps (every call re-initialises the state block), so the captured graphs are independent
+// of the epoch length and serve every later call with the same batch shape
+constexpr long long kHsNoWrap = 1ll << 62;
 // consecutive steps captured into one CUDA graph by rcn_cuda_train_epoch_host (RCN_CUDA_HOST_STEPS_PER_GRAPH overrides)
 static int hs_steps_per_graph() {
     static const int v = []() { const char* e = getenv("RCN_CUDA_HOST_STEPS_PER_GRAPH"); int n = e ? atoi(e) : 2; return n < 1 ? 1 : (n > 64 ? 64 : n); }();
@@ -983,7 +986,7 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
             RCN_CUDA_TRY(cudaMemcpyAsync(h->tgt_stage.p, labels, n_steps * B * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
             RCN_CUDA_TRY(cudaMemcpyAsync(h->hs_ring.p, images, img_bytes, cudaMemcpyHostToDevice, h->stream));
             rcn_cuda_model::HsKey key;
-            key.B = B; key.H = H; key.W = W; key.n_steps = n_steps; key.scale = scale_s; key.labels = h->tgt_stage.p;
+            key.B = B; key.H = H; key.W = W; key.n_steps = 0; key.scale = scale_s;   // the graphs do not depend on the epoch length key.labels = h->tgt_stage.p;
             key.stats = h->stats_host; key.ring = h->hs_ring.p; key.state = st; key.grads = h->grads; key.stream = h->stream;
             key.dp = h->dp.connected;
             if (!h->hs_graph || !h->hs_graph1 || !(key == h->hs_key)) {
@@ -1009,7 +1012,7 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
                         }
                         if (cudaPeekAtLastError() != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "prefetch kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
                         if (cudaEventRecord(h->hs_join, h->copy_stream) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph join failed"); break; }
-                        arm_fused_update(h, scale_s, st, (long long)B, (long long)(n_steps * B), h->stats_host);
+                        arm_fused_update(h, scale_s, st, (long long)B, kHsNoWrap, h->stats_host);
                         rc = accumulate_images_dev(h, h->hs_ring.p, pixel_format, nullptr, B, H, W, &bi);
                         const bool fused = take_upd_fused(h);
                         if (rc != RCN_OK) break;
@@ -1018,10 +1021,10 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
                         if (fused) continue;   // the weight-gradient kernel applied the update, advanced the cursor, wrote the result
                         if (h->dp.connected)
                             rc = launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale_s, h->stream, st, (long long)B,
-                                                         (long long)(n_steps * B), h->small.as<double>(), h->stats_host, take_dp_pushed(h));
+                                                         kHsNoWrap, h->small.as<double>(), h->stats_host, take_dp_pushed(h));
                         else
                             rc = launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale_s, h->stream, st, (long long)B,
-                                                   (long long)(n_steps * B), h->small.as<double>(), h->stats_host);
+                                                   kHsNoWrap, h->small.as<double>(), h->stats_host);
                     }
                     cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
                     if (rc != RCN_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
