@@ -453,6 +453,7 @@ def run_gpu(args, wl, rank, world, local_rank):
         "smallnet_fwd_bwd_kernel": ["hbm", B * (L * 8 + 8 + act_bytes) + n_params * 8, B * (fwd + bwd_d)],
         "smallnet_wgrad_kernel": ["hbm", B * (L + shapes[0][0]) * 8 + n_params * 8, B * bwd_w],
         "smallnet_wgrad_kernel(+SGD update)": ["hbm", B * (L + shapes[0][0]) * 8 + 3 * n_params * 8, B * bwd_w + 2 * n_params],
+        "smallnet_wgrad_kernel(+exchange+SGD update)": ["hbm", B * (L + shapes[0][0]) * 8 + 3 * n_params * 8, B * bwd_w + 2 * n_params],
         "features_cp_kernel": ["hbm", B * (H * W * 1 + L * 8), B * 48 * H * W],
         "sgd_update_kernel": ["hbm", 3 * n_params * 8, 2 * n_params],
         "dp_allreduce_sgd_kernel": ["hbm", 3 * n_params * 8, 2 * n_params],

@@ -26,10 +26,6 @@
 
 namespace rcn {
 
-struct DpCtrl {
-    long long step;
-    unsigned int done_ctas;
-};
 constexpr size_t kDpCtrlBytes = 256;
 
 size_t dp_block_bytes(int world, size_t n) { return kDpCtrlBytes + 2 * (size_t)world * n * sizeof(double); }

@@ -36,6 +36,44 @@ __device__ __forceinline__ void dp_push_value(const DpPush& dp, size_t par_off, 
         if (q != dp.rank)
             reinterpret_cast<unsigned long long*>(dp.peers[q] + kDpCtrlBytesPub)[par_off + (size_t)dp.rank * dp.n + i] = bits;
 }
+// Control words at the head of a communication block.
+struct DpCtrl {
+    long long step;              // exchanges completed by this rank (device-side: CUDA-graph replayable)
+    unsigned int done_ctas;      // ticket of the kernel that is finishing the current exchange
+};
+constexpr unsigned long long kDpSentinelBits = 0xFFFFFFFFFFFFFFFFull;
+
+// Device side of the receive for ONE element: wait for every peer's value of element i in my own block, put the sentinel
+// back and add the ranks in RANK ORDER (mine = `own`), so every replica computes the bit-identical global sum.
+__device__ __forceinline__ double dp_receive_sum(const DpPush& dp, size_t par_off, size_t i, double own) {
+    unsigned long long* slots = reinterpret_cast<unsigned long long*>(dp.peers[dp.rank] + kDpCtrlBytesPub) + par_off;
+    double s = 0.0;
+    for (int q = 0; q < dp.world; ++q) {
+        double v = own;
+        if (q != dp.rank) {
+            unsigned long long* p = slots + (size_t)q * dp.n + i;
+            unsigned long long bits;
+            do { asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(bits) : "l"(p) : "memory"); } while (bits == kDpSentinelBits);
+            *p = kDpSentinelBits;
+            v = __longlong_as_double((long long)bits);
+        }
+        s = (q == 0) ? v : s + v;
+    }
+    return s;
+}
+// The last CTA (of `total`) to finish an exchange publishes the step counter; call from ONE thread per CTA after the CTA's
+// receives are done.  `step` is the value dp_push_parity_offset() derived the parity from.
+__device__ __forceinline__ void dp_finish_step(const DpPush& dp, unsigned total_ctas) {
+    DpCtrl* ctrl = reinterpret_cast<DpCtrl*>(dp.peers[dp.rank]);
+    __threadfence();
+    if (atomicAdd(&ctrl->done_ctas, 1u) == total_ctas - 1) {
+        ctrl->done_ctas = 0;
+        const long long step = *reinterpret_cast<volatile long long*>(&ctrl->step) + 1;
+        *reinterpret_cast<volatile long long*>(&ctrl->step) = step;
+        __threadfence();
+    }
+}
+
 // parity offset of the step this rank is about to exchange (reads the device-side step counter of its own block)
 __device__ __forceinline__ size_t dp_push_parity_offset(const DpPush& dp) {
     const long long step = *reinterpret_cast<volatile long long*>(dp.peers[dp.rank]) + 1;

@@ -296,9 +296,9 @@ int accumulate_dev(rcn_cuda_model* h, const double* feats, const double* onehot,
         RCN_TRY(launch_smallnet_backprop(h->small_desc, h->params.as<double>(), const_cast<double*>(feats), B, onehot,
                                          labels, h->acts.as<double>(), h->deltas.as<double>(), h->grads,
                                          h->small.as<double>(), h->gemm_ws, front, h->stream, fuse_push ? &push : nullptr,
-                                         (upd.params && !h->dp.connected) ? &upd : nullptr));
-        h->dp_pushed = fuse_push;
-        h->upd_fused = upd.params && !h->dp.connected;
+                                         (upd.params && (!h->dp.connected || fuse_push)) ? &upd : nullptr));
+        h->upd_fused = upd.params && (!h->dp.connected || fuse_push);
+        h->dp_pushed = fuse_push && !h->upd_fused;   // pushed but not yet received: the exchange kernel must follow
         h->stats_valid = true;
         h->last_B = B;
         return RCN_OK;
@@ -795,7 +795,12 @@ static void arm_fused_update(rcn_cuda_model* h, double scale, long long* cursor,
                              double* stats_ring) {
     static const bool on = []() { const char* e = getenv("RCN_CUDA_FUSED_UPDATE"); return !(e && e[0] == '0'); }();
     h->pending_upd = SnUpdate{};
-    if (!on || !h || !h->params_ready || !h->use_small || h->dp.connected) return;
+    if (!on || !h || !h->params_ready || !h->use_small) return;
+    // Data-parallel groups: receiving inside the weight-gradient kernel (MODE 3) was measured SLOWER than the separate
+    // exchange kernel (2 GPUs, c2: 30.8 vs 28.4 us/step) -- the NVLink round trip is then exposed inside the kernel
+    // instead of overlapping the next launch -- so it is opt-in (RCN_CUDA_DP_FUSED_UPDATE=1).
+    static const bool dp_on = []() { const char* e = getenv("RCN_CUDA_DP_FUSED_UPDATE"); return e && e[0] == '1'; }();
+    if (h->dp.connected && (!dp_on || !dp_fused_push_enabled() || h->dp_push_suppress)) return;
     h->pending_upd.params = h->params.as<double>();
     h->pending_upd.scale = scale;
     h->pending_upd.cursor = cursor;
@@ -812,20 +817,23 @@ static bool take_upd_fused(rcn_cuda_model* h) {
 
 int rcn_cuda_train_batch(rcn_cuda_handle h, const double* feats, const double* onehot, const int64_t* labels, size_t B,
                          double eta) {
-    if (h && B) arm_fused_update(h, eta / (double)B, nullptr, 0, 0, nullptr);
+    // on a connected data-parallel group B is this rank's shard and the update uses the global batch (rcn.rs:214)
+    const size_t global = h ? B * (size_t)(h->dp.connected ? h->dp.world : 1) : B;
+    if (h && B) arm_fused_update(h, eta / (double)global, nullptr, 0, 0, nullptr);
     const int rc = rcn_cuda_accumulate_gradients(h, feats, onehot, labels, B);
     if (rc != RCN_OK) { if (h) take_upd_fused(h); return rc; }
     if (take_upd_fused(h)) return RCN_OK;
-    return rcn_cuda_apply_gradients(h, eta, B);
+    return rcn_cuda_apply_gradients(h, eta, global);
 }
 
 int rcn_cuda_train_batch_images(rcn_cuda_handle h, const void* images, int pixel_format, const int64_t* labels, size_t B,
                                 size_t H, size_t W, double eta) {
-    if (h && B) arm_fused_update(h, eta / (double)B, nullptr, 0, 0, nullptr);
+    const size_t global = h ? B * (size_t)(h->dp.connected ? h->dp.world : 1) : B;
+    if (h && B) arm_fused_update(h, eta / (double)global, nullptr, 0, 0, nullptr);
     const int rc = rcn_cuda_accumulate_gradients_images(h, images, pixel_format, labels, B, H, W);
     if (rc != RCN_OK) { if (h) take_upd_fused(h); return rc; }
     if (take_upd_fused(h)) return RCN_OK;
-    return rcn_cuda_apply_gradients(h, eta, B);
+    return rcn_cuda_apply_gradients(h, eta, global);
 }
 
 int rcn_cuda_last_batch_stats(rcn_cuda_handle h, double* cost, uint64_t* hits) {
@@ -904,12 +912,13 @@ int rcn_cuda_epoch_apply(rcn_cuda_handle h, double eta, size_t global_batch) {
 }
 
 int rcn_cuda_epoch_step(rcn_cuda_handle h, double eta) {
+    const size_t global = h ? h->ep_B * (size_t)(h->dp.connected ? h->dp.world : 1) : 0;
     if (h && h->ep_images && h->ep_B)
-        arm_fused_update(h, eta / (double)h->ep_B, h->ep_state.as<long long>(), (long long)h->ep_B, (long long)h->ep_n, nullptr);
+        arm_fused_update(h, eta / (double)global, h->ep_state.as<long long>(), (long long)h->ep_B, (long long)h->ep_n, nullptr);
     const int rc = rcn_cuda_epoch_accumulate(h);
     if (rc != RCN_OK) { if (h) take_upd_fused(h); return rc; }
     if (take_upd_fused(h)) return RCN_OK;
-    return rcn_cuda_epoch_apply(h, eta, h->ep_B);
+    return rcn_cuda_epoch_apply(h, eta, global);
 }
 
 // ---- pipelined loop over a HOST-resident dataset: rcn.rs:147-149 ------------------------------------------------------

@@ -458,8 +458,11 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
 // ------------------------------------------------------------------------------------------------
 constexpr int SNB_TILE = 32 * 64;   // padded partial tile: 32 rows x 64 columns
 
-// MODE 1: also push the final values into the data-parallel peers' receive slots (dp.cu protocol); MODE 2: single GPU,
-// apply the SGD update to the finished elements right here (SnUpdate); MODE 0: gradients only.
+// MODE 0: gradients only.  MODE 1: also push the final values into the data-parallel peers' receive slots (dp.cu
+// protocol; the update kernel then only receives).  MODE 2: single GPU, apply the SGD update to the finished elements
+// right here (SnUpdate).  MODE 3: data-parallel AND fused update: every thread pushes its finished element to the peers,
+// waits for theirs, adds the ranks in rank order and applies the update -- the whole exchange + update of rcn.rs:190-222
+// inside this kernel's epilogue, so a multi-GPU step is two launches as well.
 template <int MODE>
 __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __grid_constant__ SmallNetDesc d,
                                                                      const double* __restrict__ feats,
@@ -469,8 +472,9 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
                                                                      const double* __restrict__ stats_partial, int n_stat,
                                                                      double* __restrict__ stats, const __grid_constant__ DpPush dp,
                                                                      const __grid_constant__ SnUpdate upd) {
-    constexpr bool DP = MODE == 1;
-    constexpr bool UPD = MODE == 2;
+    constexpr bool DP = MODE == 1 || MODE == 3;
+    constexpr bool UPD = MODE == 2 || MODE == 3;
+    constexpr bool DPX = MODE == 3;
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     RCN_TL_BEGIN(1);
@@ -577,8 +581,9 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
             s += remote[o];
         }
         if (gi >= 0) {
-            grads[gi] = s;
             if (DP) dp_push_value(dp, dp_par, (size_t)gi, s);
+            if (DPX) s = dp_receive_sum(dp, dp_par, (size_t)gi, s);   // the global sum, identical on every rank
+            grads[gi] = s;
             if (UPD) upd.params[gi] = sgd_apply(pold, upd.scale, s);
         }
     }
@@ -612,6 +617,7 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
         }
     }
     cluster.sync();   // nobody leaves while a peer may still read its tile
+    if (DPX && tid == 0) dp_finish_step(dp, gridDim.x * gridDim.y);
     RCN_TL_END(1);
 }
 
@@ -717,14 +723,15 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
     if (dp_push) push = *dp_push;
     const bool with_push = push.world > 1;
     SnUpdate upd{};
-    if (update && !with_push) upd = *update;
-    const int mode = with_push ? 1 : (upd.params ? 2 : 0);
+    if (update) upd = *update;
+    const int mode = with_push ? (upd.params ? 3 : 1) : (upd.params ? 2 : 0);
     static SmemAttrCache attr_b;
     if (attr_b.need(smem_b)) {  // static 36 KB + dynamic tile exceeds the 48 KB default; all variants at once (a later
                                 // launch of another variant may happen inside a stream capture)
         RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
         RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
         RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(col_groups + 1, splits, 1);
@@ -739,8 +746,8 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const int Bi = (int)B;
-    auto kern = mode == 1 ? smallnet_wgrad_kernel<1> : mode == 2 ? smallnet_wgrad_kernel<2> : smallnet_wgrad_kernel<0>;
-    RCN_LAUNCH(mode == 2 ? "smallnet_wgrad_kernel(+SGD update)" : "smallnet_wgrad_kernel", stream,
+    auto kern = mode == 1 ? smallnet_wgrad_kernel<1> : mode == 2 ? smallnet_wgrad_kernel<2> : mode == 3 ? smallnet_wgrad_kernel<3> : smallnet_wgrad_kernel<0>;
+    RCN_LAUNCH(mode == 2 ? "smallnet_wgrad_kernel(+SGD update)" : mode == 3 ? "smallnet_wgrad_kernel(+exchange+SGD update)" : "smallnet_wgrad_kernel", stream,
                cudaLaunchKernelEx(&cfg, kern, d, (const double*)feats, (const double*)small_partial, (const double*)deltas, Bi,
                                   ksplit, col_groups, grads, (const double*)stats_partial, n_tiles, stats, push, upd));
     return RCN_OK;

@@ -65,7 +65,7 @@ class DataParallelTrainer:
 
     def step_images(self, images, labels):
         """images: this rank's shard, (B_local, H, W) uint8 / float64 (torch CUDA tensor or numpy); labels (B_local,)."""
-        if self.world == 1:   # one call: the library may fold the update into the weight-gradient kernel
+        if self.world == 1 or self.p2p:   # one call: the library folds the (exchange +) update into the weight-gradient kernel
             self.model.train_batch_images(images, labels, self.eta)
             return
         self.model.accumulate_gradients_images(images, labels)
@@ -110,7 +110,7 @@ class DataParallelTrainer:
     def _epoch_step_eager(self):
         import torch
         self.model.set_stream(torch.cuda.current_stream().cuda_stream)
-        if self.world == 1:   # one call: the library may fold the update into the weight-gradient kernel
+        if self.world == 1 or self.p2p:   # one call: the library folds the (exchange +) update into the weight-gradient kernel
             self.model.epoch_step(self.eta)
             return
         self.model.epoch_accumulate()
@@ -163,8 +163,8 @@ class DataParallelTrainer:
             ar = ("none (1 GPU) -> SGD update (narrow networks: applied by the weight-gradient kernel itself, "
                   "no separate launch)")
         elif self.p2p:
-            ar = (f"gradient exchange of {self.model.n_params} f64 over NVLink peer memory fused with the SGD update "
-                  "(one kernel, rank-ordered sum)")
+            ar = (f"gradient exchange of {self.model.n_params} f64 over NVLink peer memory + SGD update (narrow networks: both "
+                  "inside the weight-gradient kernel's epilogue, rank-ordered sum; otherwise one exchange+update kernel)")
         else:
             ar = f"1x NCCL all-reduce(sum) of {self.model.n_params} f64 per step -> SGD update"
         return ("features(+standardise) -> fwd -> bwd-data -> bwd-weight(+db) -> batch stats -> " + ar +

@@ -383,9 +383,11 @@ def test_train_epoch_host_equals_step_by_step(api):
         assert np.array_equal(results[0][1], other[1]) and np.array_equal(results[0][2], other[2])
 
 
-def test_dp_peer_memory_exchange_two_gpus(api):
-    """Two ranks on two GPUs of this box (one process, peer access): the fused NVLink exchange + update kernel keeps the
-    replicas bit-identical and equals single-GPU training on the global minibatch within summation order."""
+@pytest.mark.parametrize("single_call", [False, True])
+def test_dp_peer_memory_exchange_two_gpus(api, single_call):
+    """Two ranks on two GPUs of this box (one process, peer access): the NVLink exchange + update -- as its own kernel
+    after accumulate (split calls) or inside the weight-gradient kernel's epilogue (train_batch_images, one call) -- keeps
+    the replicas bit-identical and equals single-GPU training on the global minibatch within summation order."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -416,8 +418,11 @@ def test_dp_peer_memory_exchange_two_gpus(api):
     def work(r):
         m = ranks[r]
         for k in range(steps):
-            m.accumulate_gradients_images(images[k, r * half:(r + 1) * half], labels[k, r * half:(r + 1) * half])
-            m.apply_gradients(3.0, Bg)
+            if single_call:    # the shard is this rank's batch; the library scales by the global batch (rcn.rs:214)
+                m.train_batch_images(images[k, r * half:(r + 1) * half], labels[k, r * half:(r + 1) * half], 3.0)
+            else:
+                m.accumulate_gradients_images(images[k, r * half:(r + 1) * half], labels[k, r * half:(r + 1) * half])
+                m.apply_gradients(3.0, Bg)
         m.synchronize()
 
     th = [threading.Thread(target=work, args=(r,)) for r in range(2)]
