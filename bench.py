@@ -359,8 +359,9 @@ def run_gpu(args, wl, rank, world, local_rank):
     barrier()
     clocks.mark_end()
     launches = _lib.kernel_launches() - l0
-    if kernels_per_step is not None:
-        launches = kernels_per_step * args.steps   # graph replays re-launch the captured kernels
+    if kernels_per_step is not None and launches == 0:
+        launches = kernels_per_step * args.steps   # graph replays re-launch the captured kernels (the counter only sees
+                                                   # launches made through the library, e.g. the persistent step kernel)
     ms_total = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)

@@ -153,6 +153,10 @@ int rcn_cuda_epoch_position(rcn_cuda_handle h, size_t* position); /* synchronise
 int rcn_cuda_epoch_accumulate(rcn_cuda_handle h);
 int rcn_cuda_epoch_apply(rcn_cuda_handle h, double eta, size_t global_batch);
 int rcn_cuda_epoch_step(rcn_cuda_handle h, double eta); /* accumulate + apply with global_batch = B */
+/* n_steps consecutive epoch steps (rcn.rs:147-149: n_steps iterations of the chunks_exact loop). On one GPU with the
+ * canonical narrow network and u8 images they run as ONE persistent cooperative launch (phase A, phase B + update, next
+ * step ... separated by grid-wide barriers instead of kernel boundaries); otherwise as n_steps rcn_cuda_epoch_step calls. */
+int rcn_cuda_epoch_run(rcn_cuda_handle h, double eta, size_t n_steps);
 
 /* The same loop over a HOST-resident (already shuffled) dataset: `for batch in training_set.chunks_exact(B) {
  * train_batch(batch, eta) }` (rcn.rs:147-149). The host->device transfer of chunk k+1 overlaps the kernels of chunk k:

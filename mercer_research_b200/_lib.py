@@ -63,6 +63,7 @@ SIGNATURES = {
     "rcn_cuda_epoch_accumulate": [_vp],
     "rcn_cuda_epoch_apply": [_vp, _d, _sz],
     "rcn_cuda_epoch_step": [_vp, _d],
+    "rcn_cuda_epoch_run": [_vp, _d, _sz],
     "rcn_cuda_train_epoch_host": [_vp, _vp, _i, _vp, _sz, _sz, _sz, _sz, _d, _sz, _vp, _vp, _szp],
     "rcn_cuda_dp_init": [_vp, _i, _i, _vp],
     "rcn_cuda_dp_connect_ipc": [_vp, _vp],

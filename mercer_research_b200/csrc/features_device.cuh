@@ -376,7 +376,7 @@ __device__ __forceinline__ void cp_transpose_images(const uint8_t* __restrict__ 
 
 __device__ __forceinline__ size_t source_image(const BatchIndex& bi, size_t img) {
     if (!bi.cursor) return img;
-    const long long pos = *bi.cursor + (long long)img;
+    const long long pos = __ldcg(bi.cursor) + (long long)img;   // L2: a persistent kernel advances the cursor between steps
     return (size_t)(bi.perm ? bi.perm[pos] : pos);
 }
 // where that image's pixels live: the dataset itself, or a ring of `window` slots when streaming from the host

@@ -147,6 +147,8 @@ struct rcn_cuda_model {
     bool stats_valid = false;
     // data-parallel group (dp.cu) and the pipelined host-dataset loop (rcn_cuda_train_epoch_host)
     DpState dp;
+    DevBuf persist_ws;              // barrier counter + per-tile partials of the persistent step kernel
+    bool persist_failed = false;    // the cooperative launch was refused once: stay on the per-step kernels
     SnUpdate pending_upd{};         // set by the step entry points: the next small-network accumulate applies the update itself
     bool upd_fused = false;         // ... and did (the standalone update kernel is then skipped)
     bool dp_pushed = false;         // the last accumulate pushed its gradients to the peers itself (kernel B epilogue)
@@ -428,7 +430,7 @@ int rcn_cuda_destroy(rcn_cuda_handle h) {
     if (h->hs_graph1) cudaGraphExecDestroy(h->hs_graph1);
     if (h->hs_fork) cudaEventDestroy(h->hs_fork);
     if (h->hs_join) cudaEventDestroy(h->hs_join);
-    h->hs_ring.release(); h->hs_state.release();
+    h->hs_ring.release(); h->hs_state.release(); h->persist_ws.release();
     dp_release(h->dp);
     h->oz.release();
     DevBuf* bufs[] = {&h->params, &h->grads_own, &h->in_stage, &h->tgt_stage, &h->feats, &h->acts, &h->deltas,
@@ -919,6 +921,56 @@ int rcn_cuda_epoch_step(rcn_cuda_handle h, double eta) {
     if (rc != RCN_OK) { if (h) take_upd_fused(h); return rc; }
     if (take_upd_fused(h)) return RCN_OK;
     return rcn_cuda_epoch_apply(h, eta, global);
+}
+
+int rcn_cuda_epoch_run(rcn_cuda_handle h, double eta, size_t n_steps) {
+    RCN_ENTER(h);
+    RCN_TRY(require_params(h));
+    if (!h->ep_images) return fail(RCN_ERR_STATE, "no dataset bound: call rcn_cuda_epoch_bind first");
+    if (n_steps == 0) return RCN_OK;
+    if (n_steps > (size_t)1 << 30) return fail(RCN_ERR_INVALID, "too many steps in one call");
+    const size_t B = h->ep_B;
+    if (h->use_small && !h->dp.connected && !h->persist_failed && h->ep_fmt == RCN_PIXELS_U8_ROWMAJOR && h->plan.L > 0 &&
+        h->plan.n_conv <= 10 && B <= smallnet_max_batch()) {
+        if (h->dp_pushed) return fail(RCN_ERR_STATE, "data-parallel group: pushed gradients were never applied");
+        SmallNetFront fr{};
+        fr.images = (const uint8_t*)h->ep_images;
+        fr.H = (int)h->ep_H; fr.W = (int)h->ep_W;
+        fr.max_elems = (int)h->plan.max_elems;
+        fr.stages = h->plan.stages;
+        fr.sc = make_standardise(h->plan, h->ep_fmt, true, h->mean, h->sd);
+        fr.bi.cursor = h->ep_state.as<long long>();
+        fr.bi.perm = (const long long*)h->ep_perm;
+        fr.bi.labels_all = (const long long*)h->ep_labels;
+        fr.bi.labels_batch = h->ep_state.as<long long>() + 2;
+        smallnet_front_select(h->plan, &fr);
+        if (smallnet_persistent_eligible(h->small_desc, fr, B)) {
+            RCN_TRY(h->feats.reserve(h->plan.L * B * sizeof(double)));
+            RCN_TRY(h->acts.reserve(h->sum_rows * B * sizeof(double)));
+            RCN_TRY(h->deltas.reserve(h->sum_rows * B * sizeof(double)));
+            RCN_TRY(h->small.reserve(64));
+            SnUpdate upd{};
+            upd.params = h->params.as<double>();
+            upd.scale = eta / (double)B;                 // (eta / batch.len() as f64)  (rcn.rs:214)
+            upd.cursor = h->ep_state.as<long long>();
+            upd.batch = (long long)B;
+            upd.n_samples = (long long)h->ep_n;
+            const int rc = launch_smallnet_persistent(h->small_desc, h->params.as<double>(), h->feats.as<double>(), B,
+                                                      h->acts.as<double>(), h->deltas.as<double>(), h->grads, h->small.as<double>(),
+                                                      h->persist_ws, fr, upd, (int)n_steps, h->stream);
+            if (rc == RCN_OK) {
+                h->stats_valid = true;
+                h->last_B = B;
+                return RCN_OK;
+            }
+            // e.g. the cooperative launch does not fit this device partition: never try again, take the per-step path
+            if (getenv("RCN_CUDA_DEBUG")) fprintf(stderr, "[rcn_cuda] persistent launch refused: %s\n", rcn_cuda_last_error());
+            h->persist_failed = true;
+            cudaGetLastError();
+        }
+    }
+    for (size_t k = 0; k < n_steps; ++k) RCN_TRY(rcn_cuda_epoch_step(h, eta));
+    return RCN_OK;
 }
 
 // ---- pipelined loop over a HOST-resident dataset: rcn.rs:147-149 ------------------------------------------------------

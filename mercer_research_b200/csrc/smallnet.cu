@@ -42,10 +42,17 @@ __device__ __forceinline__ void sn_dmma(double& c0, double& c1, double a, double
 // kernel A stamps clock64() at the phase boundaries.  Compiled out of the product library.
 #ifdef RCN_SN_PHASES
 __device__ long long g_sn_phase[1024][8];
+__device__ long long g_snp_stamp[1024][8];
 #define SN_PHASE(k) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_sn_phase[blockIdx.x][k] = clock64(); } while (0)
 #else
 #define SN_PHASE(k) do { } while (0)
 #endif
+
+// Loads of data that OTHER CTAs rewrite while a persistent kernel is running (parameters, features, deltas, partials, the
+// epoch cursor) must not be served from this SM's L1: ld.global.cg reads L2.  One-launch-per-phase kernels keep the
+// read-only path.
+template <bool PERSIST>
+__device__ __forceinline__ double sn_ld(const double* p) { return PERSIST ? __ldcg(p) : __ldg(p); }
 
 constexpr int SN_TB = 8;          // samples per CTA in kernel A (one DMMA n-fragment)
 constexpr int SNA_THREADS = 512;  // kernel A
@@ -95,14 +102,15 @@ __device__ __forceinline__ unsigned char* sn_align128(void* p) {
 // ------------------------------------------------------------------------------------------------
 // Kernel A
 // ------------------------------------------------------------------------------------------------
-template <int FUSED>   // 0: features are an input; 1: generic fused front end; 2: staged front end (CpPlan)
-__global__ void __launch_bounds__(SNA_THREADS, 1)
-smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __restrict__ params,
-                        double* __restrict__ feats, int B, const double* __restrict__ onehot,
-                        const int64_t* __restrict__ labels, double* __restrict__ acts, double* __restrict__ deltas,
-                        double* __restrict__ stats_partial, double* __restrict__ small_partial, int backward,
-                        const __grid_constant__ SmallNetFront fr) {
-    extern __shared__ __align__(128) unsigned char sn_smem[];
+// FUSED 0: features are an input; 1: generic fused front end; 2: staged front end (CpPlan).  PERSIST: called once per step
+// from the persistent step kernel (`step` = iteration; the image mbarrier is initialised once and waited by parity).
+template <int FUSED, bool PERSIST>
+__device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* __restrict__ params,
+                                           double* __restrict__ feats, int B, const double* __restrict__ onehot,
+                                           const int64_t* __restrict__ labels, double* __restrict__ acts,
+                                           double* __restrict__ deltas, double* __restrict__ stats_partial,
+                                           double* __restrict__ small_partial, int backward, const SmallNetFront& fr,
+                                           const int tile_idx, unsigned char* sn_smem, const int step) {
     double* zpart = reinterpret_cast<double*>(sn_smem);                 // [16][8][36]
     double* s_small = zpart + SNA_WARPS * SN_TB * SN_ZPITCH;                   // params after W0: b0 | W1 | b1 | ...
     double* tile = s_small + SN_MAX_SMALL;                              // FUSED: [8][n_in + 4]
@@ -114,7 +122,7 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int s0 = blockIdx.x * SN_TB;
+    const int s0 = tile_idx * SN_TB;
     const int L = d.n_in, R0 = d.rows[0];
     const int mf = (R0 + 7) >> 3;
     SN_PHASE(0);
@@ -131,8 +139,12 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
         const uint32_t img_bytes = (uint32_t)(fr.H * fr.W);
         if (warp == 0) {
             if (lane == 0) {
-                cpbulk::mbar_init(&s_bar, 1);
-                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                if (step == 0) {
+                    cpbulk::mbar_init(&s_bar, 1);
+                    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                } else {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // last step's generic reads -> async overwrite
+                }
                 cpbulk::mbar_expect_tx(&s_bar, img_bytes * (uint32_t)n_live);
             }
             __syncwarp();
@@ -150,7 +162,7 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
         }
     }
     // prefetch biases + narrow-layer weights (overlaps with the front end / the DMMA phase)
-    for (int i = tid; i < n_small; i += SNA_THREADS) s_small[i] = __ldg(params + small_base + i);
+    for (int i = tid; i < n_small; i += SNA_THREADS) s_small[i] = sn_ld<PERSIST>(params + small_base + i);
 
     // layer-0 weight fragments: each warp owns a K range of the n_in-deep contraction; its first SN_U k-steps go into
     // registers NOW and the rest is prefetched into L1, so the L2 latency is hidden behind the front end
@@ -169,12 +181,13 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
         const bool kok = (ks_begin + u) < ks_end && k < L;
         const double* wp = W0 + (size_t)k * R0 + g;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) w_pre[u][i] = (kok && rowok[i]) ? __ldg(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
+        for (int i = 0; i < 4; ++i) w_pre[u][i] = (kok && rowok[i]) ? sn_ld<PERSIST>(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
     }
     {
         const long long lo = (long long)min((ks_begin + SN_U) * 4, L) * R0, hi = (long long)min(ks_end * 4, L) * R0;   // doubles
-        for (long long e = lo + lane * 16; e < hi; e += 32 * 16)
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(W0 + e));
+        if (!PERSIST)   // (a persistent kernel must not keep parameters in L1 across steps)
+            for (long long e = lo + lane * 16; e < hi; e += 32 * 16)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(W0 + e));
     }
 
     if (FUSED == 2) {
@@ -185,7 +198,7 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
         for (int i = tid; i < SN_TB * fr.cp.tile_ints; i += SNA_THREADS) tiles[i] = 0;
         for (int i = n_live * pitch + tid; i < SN_TB * pitch; i += SNA_THREADS) tile[i] = 0.0;   // absent samples
         __syncthreads();
-        cpbulk::mbar_wait(&s_bar, 0);
+        cpbulk::mbar_wait(&s_bar, (uint32_t)(step & 1));
         SN_PHASE(1);
         cp_transpose_images(stg, fr.cp.stage_bytes, tiles, fr.cp.tile_ints, n_live, fr.H, fr.W, fr.cp, tid, SNA_THREADS);
         __syncthreads();
@@ -288,7 +301,7 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
                 const bool kok = (ks + u) < ks_end && k < L;
                 const double* wp = W0 + (size_t)k * R0 + g;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) af[u][i] = (kok && rowok[i]) ? __ldg(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
+                for (int i = 0; i < 4; ++i) af[u][i] = (kok && rowok[i]) ? sn_ld<PERSIST>(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
                 if (FUSED) bf[u] = kok ? trow[k] : 0.0;
                 else bf[u] = (kok && sample_ok) ? __ldg(frow + k) : 0.0;
             }
@@ -409,15 +422,15 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
         unsigned long long h = 0;
 #pragma unroll
         for (int i = 0; i < SN_TB; ++i) { c += s_cost[i]; h += s_hit[i]; }
-        stats_partial[2 * blockIdx.x] = c;
-        reinterpret_cast<unsigned long long*>(stats_partial)[2 * blockIdx.x + 1] = h;
+        stats_partial[2 * tile_idx] = c;
+        reinterpret_cast<unsigned long long*>(stats_partial)[2 * tile_idx + 1] = h;
     }
     // ---- this tile's share of db_l (all layers) and dW_l (narrow layers): everything is already in shared memory.
     // One value per entry of the "small" parameter block b0|W1|b1|...; kernel B sums the tiles in index order.  A task is
     // one bias vector or one column k of a dW_l (lane = row), dealt round-robin to the 16 warps; samples added in order.
     {
         const int n_live = min(SN_TB, B - s0);
-        double* sp = small_partial + (size_t)blockIdx.x * n_small;
+        double* sp = small_partial + (size_t)tile_idx * n_small;
         int task = 0;
         for (int l = 0; l < d.n_layers; ++l) {
             const int R = d.rows[l];
@@ -449,6 +462,18 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
     RCN_TL_END(0);
 }
 
+template <int FUSED>
+__global__ void __launch_bounds__(SNA_THREADS, 1)
+smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __restrict__ params,
+                        double* __restrict__ feats, int B, const double* __restrict__ onehot,
+                        const int64_t* __restrict__ labels, double* __restrict__ acts, double* __restrict__ deltas,
+                        double* __restrict__ stats_partial, double* __restrict__ small_partial, int backward,
+                        const __grid_constant__ SmallNetFront fr) {
+    extern __shared__ __align__(128) unsigned char sn_smem[];
+    sn_phase_a<FUSED, false>(d, params, feats, B, onehot, labels, acts, deltas, stats_partial, small_partial, backward, fr,
+                             (int)blockIdx.x, sn_smem, 0);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Kernel B: dW/db.  grid = (col_groups + 1, S) launched as thread-block CLUSTERS of (1, S, 1): the S CTAs of a
 // cluster own the same 64 columns of dW0 (or, for blockIdx.x == col_groups, db0 + the narrow layers) and one K-split
@@ -463,51 +488,58 @@ constexpr int SNB_TILE = 32 * 64;   // padded partial tile: 32 rows x 64 columns
 // right here (SnUpdate).  MODE 3: data-parallel AND fused update: every thread pushes its finished element to the peers,
 // waits for theirs, adds the ranks in rank order and applies the update -- the whole exchange + update of rcn.rs:190-222
 // inside this kernel's epilogue, so a multi-GPU step is two launches as well.
-template <int MODE>
-__global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __grid_constant__ SmallNetDesc d,
-                                                                     const double* __restrict__ feats,
-                                                                     const double* __restrict__ small_partial,
-                                                                     const double* __restrict__ deltas, int B, int ksplit,
-                                                                     int col_groups, double* __restrict__ grads,
-                                                                     const double* __restrict__ stats_partial, int n_stat,
-                                                                     double* __restrict__ stats, const __grid_constant__ DpPush dp,
-                                                                     const __grid_constant__ SnUpdate upd) {
+// PERSIST: called from the persistent step kernel with 512 threads per CTA: threads >= SNB_THREADS only take part in the
+// cluster barriers, the working threads synchronise on a named barrier.
+// CW: columns of dW0 per CTA: 64 (one warp per 8 columns) or 32 (two warps per 8 columns, each taking half of every
+// 64-sample chunk; their two partial tiles are added, in order, by the reduction).
+template <int MODE, bool PERSIST, int CW>
+__device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* __restrict__ feats,
+                                           const double* __restrict__ small_partial, const double* __restrict__ deltas,
+                                           int B, int ksplit, int col_groups, double* __restrict__ grads,
+                                           const double* __restrict__ stats_partial, int n_stat, double* __restrict__ stats,
+                                           const DpPush& dp, const SnUpdate& upd, const int cg_idx, const int rank, const int S,
+                                           double* sP, double* sD /* [2][64 * SN_DPITCH]: double-buffered 64-sample delta_0 chunk */,
+                                           const unsigned total_ctas) {
     constexpr bool DP = MODE == 1 || MODE == 3;
     constexpr bool UPD = MODE == 2 || MODE == 3;
     constexpr bool DPX = MODE == 3;
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     RCN_TL_BEGIN(1);
-    __shared__ __align__(16) double sD[2][64 * SN_DPITCH];   // double-buffered 64-sample delta_0 chunk (36 KB)
-    extern __shared__ __align__(16) double sP[];              // partial tile: SNB_TILE (col CTAs) or n_small doubles
+    if (PERSIST && threadIdx.x >= SNB_THREADS) {             // spectators of the DSMEM reduction
+        cluster.sync();
+        cluster.sync();
+        return;
+    }
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int L = d.n_in, R0 = d.rows[0];
-    const int S = gridDim.y;
-    const int rank = blockIdx.y;                               // == cluster.block_rank() for cluster dims (1, S, 1)
     const int b_begin = rank * ksplit;
     const int b_end = min(B, b_begin + ksplit);
-    const bool is_col = (int)blockIdx.x < col_groups;
+    const bool is_col = cg_idx < col_groups;
     const int small_base = d.b_off[0];
     const int n_small = d.n_params - small_base;
 
     if (is_col) {
         const int mf = (R0 + 7) >> 3;
-        const int col = blockIdx.x * 64 + warp * 8 + g;     // B frag column (feature index)
+        constexpr int NWC = CW / 8;                          // warps across the columns
+        constexpr int KQ = 8 / NWC;                          // warps sharing a column octet (each 64 / KQ samples of a chunk)
+        const int oct = warp % NWC, kq = warp / NWC;
+        const int col = cg_idx * CW + oct * 8 + g;          // B frag column (feature index)
         const bool col_ok = col < L;
-        constexpr int U = 16;                                // 64 samples per chunk
+        constexpr int U = 16 / KQ;                           // k-steps per warp per 64-sample chunk
         double acc[4][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.0;
         int buf = 0;
-        for (int c0 = b_begin; c0 < b_end; c0 += 4 * U, buf ^= 1) {
+        for (int c0 = b_begin; c0 < b_end; c0 += 64, buf ^= 1) {
             double bf[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {                    // 16 A0 loads in flight per lane
-                const int b = c0 + u * 4 + t;
-                bf[u] = (b < b_end && col_ok) ? feats[(size_t)b * L + col] : 0.0;   // B frag: row t (sample), col g (feature)
+            for (int u = 0; u < U; ++u) {                    // U A0 loads in flight per lane
+                const int b = c0 + kq * (64 / KQ) + u * 4 + t;
+                bf[u] = (b < b_end && col_ok) ? (PERSIST ? __ldcg(feats + (size_t)b * L + col) : feats[(size_t)b * L + col]) : 0.0;   // B frag: row t (sample), col g (feature)
             }
-            double* sd = sD[buf];
+            double* sd = sD + buf * (64 * SN_DPITCH);
             {
                 double vd[8];
 #pragma unroll
@@ -515,7 +547,7 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
                     const int idx = u * SNB_THREADS + tid;
                     const int kk = idx >> 5, mm = idx & 31;
                     const int b = c0 + kk;
-                    vd[u] = (mm < R0 && b < b_end) ? deltas[(size_t)b * R0 + mm] : 0.0;
+                    vd[u] = (mm < R0 && b < b_end) ? (PERSIST ? __ldcg(deltas + (size_t)b * R0 + mm) : deltas[(size_t)b * R0 + mm]) : 0.0;
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -523,16 +555,16 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
                     sd[(idx >> 5) * SN_DPITCH + (idx & 31)] = vd[u];
                 }
             }
-            __syncthreads();   // chunk staged; the other buffer is free again because everyone passed this barrier
+            if (PERSIST) asm volatile("bar.sync 2, 256;" ::: "memory"); else __syncthreads();   // chunk staged; the other buffer is free again because everyone passed this barrier
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int kk = u * 4 + t;
+                const int kk = kq * (64 / KQ) + u * 4 + t;
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     if (i < mf) sn_dmma(acc[i][0], acc[i][1], sd[kk * SN_DPITCH + i * 8 + g], bf[u]);  // A frag: row g (m), col t
             }
         }
-        const int cl = warp * 8 + 2 * t;                    // C frag: row g (m), cols 2t, 2t+1
+        const int cl = kq * CW + oct * 8 + 2 * t;           // C frag: row g (m), cols 2t, 2t+1; one CW x 32 tile per kq
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             sP[cl * 32 + i * 8 + g] = acc[i][0];
@@ -548,7 +580,7 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
             for (int tb = t_begin; tb < t_end; tb += 8) {
                 double v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = (tb + u < t_end) ? small_partial[(size_t)(tb + u) * n_small + o] : 0.0;
+                for (int u = 0; u < 8; ++u) v[u] = (tb + u < t_end) ? (PERSIST ? __ldcg(small_partial + (size_t)(tb + u) * n_small + o) : small_partial[(size_t)(tb + u) * n_small + o]) : 0.0;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) s += v[u];
             }
@@ -558,7 +590,7 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
 
     // ---- cross-split reduction through distributed shared memory, rank order ----------------------------------------
     cluster.sync();
-    const int n_out = is_col ? SNB_TILE : n_small;
+    const int n_out = is_col ? CW * 32 : n_small;
     const int per = (n_out + S - 1) / S;
     const int o_lo = rank * per, o_hi = min(n_out, o_lo + per);
     // data-parallel group: the final values also go straight into the peers' receive slots (dp.cu protocol), so the
@@ -568,17 +600,18 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
         // destination first: the old parameter value (fused update) is in flight while the peers' partials are read
         long long gi = -1;
         if (is_col) {
-            const int m = o & 31, col = blockIdx.x * 64 + (o >> 5);
+            const int m = o & 31, col = cg_idx * CW + (o >> 5);
             if (m < R0 && col < L) gi = d.w_off[0] + (long long)col * R0 + m;
         } else {
             gi = small_base + o;
         }
         double pold = 0.0;
-        if (UPD && gi >= 0) pold = upd.params[gi];
+        if (UPD && gi >= 0) pold = PERSIST ? __ldcg(upd.params + gi) : upd.params[gi];
         double s = 0.0;
         for (int q = 0; q < S; ++q) {
             const double* remote = cluster.map_shared_rank(sP, q);
             s += remote[o];
+            if (is_col && CW == 32) s += remote[CW * 32 + o];   // the second warp's half of every chunk
         }
         if (gi >= 0) {
             if (DP) dp_push_value(dp, dp_par, (size_t)gi, s);
@@ -593,8 +626,8 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
         double c = 0.0;
         unsigned long long h = 0;
         for (int i = tid * per_l; i < min(n_stat, (tid + 1) * per_l); ++i) {
-            c += stats_partial[2 * i];
-            h += reinterpret_cast<const unsigned long long*>(stats_partial)[2 * i + 1];
+            c += PERSIST ? __ldcg(stats_partial + 2 * i) : stats_partial[2 * i];
+            h += PERSIST ? __ldcg(reinterpret_cast<const unsigned long long*>(stats_partial) + 2 * i + 1) : reinterpret_cast<const unsigned long long*>(stats_partial)[2 * i + 1];
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -605,20 +638,104 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
             stats[0] = c;
             reinterpret_cast<unsigned long long*>(stats)[1] = h;
             if (UPD && upd.cursor) {   // what sgd_update_kernel does on the side (kernel A of this step is long done)
+                const long long cur0 = PERSIST ? __ldcg(upd.cursor) : *upd.cursor;
                 if (upd.stats_ring) {
-                    double* dst = upd.stats_ring + 2 * (*upd.cursor / upd.batch);
+                    double* dst = upd.stats_ring + 2 * (cur0 / upd.batch);
                     dst[0] = c;
                     reinterpret_cast<unsigned long long*>(dst)[1] = h;
                 }
-                long long cur = *upd.cursor + upd.batch;   // next chunk of chunks_exact(batch) (rcn.rs:147), remainder dropped
+                long long cur = cur0 + upd.batch;   // next chunk of chunks_exact(batch) (rcn.rs:147), remainder dropped
                 if (cur + upd.batch > upd.n_samples) cur = 0;
                 *upd.cursor = cur;
             }
         }
     }
     cluster.sync();   // nobody leaves while a peer may still read its tile
-    if (DPX && tid == 0) dp_finish_step(dp, gridDim.x * gridDim.y);
+    if (DPX && tid == 0) dp_finish_step(dp, total_ctas);
     RCN_TL_END(1);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __grid_constant__ SmallNetDesc d,
+                                                                     const double* __restrict__ feats,
+                                                                     const double* __restrict__ small_partial,
+                                                                     const double* __restrict__ deltas, int B, int ksplit,
+                                                                     int col_groups, double* __restrict__ grads,
+                                                                     const double* __restrict__ stats_partial, int n_stat,
+                                                                     double* __restrict__ stats, const __grid_constant__ DpPush dp,
+                                                                     const __grid_constant__ SnUpdate upd) {
+    extern __shared__ __align__(16) double sP_dyn[];          // partial tile: SNB_TILE (col CTAs) or n_small doubles
+    __shared__ __align__(16) double sD_static[2 * 64 * SN_DPITCH];   // 36 KB
+    // grid (col_groups + 1, S) in clusters of (1, S, 1): blockIdx.y == cluster.block_rank()
+    sn_phase_b<MODE, false, 64>(d, feats, small_partial, deltas, B, ksplit, col_groups, grads, stats_partial, n_stat, stats, dp, upd,
+                            (int)blockIdx.x, (int)blockIdx.y, (int)gridDim.y, sP_dyn, sD_static, gridDim.x * gridDim.y);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent step kernel (single GPU, canonical network, staged front end): the kernel boundaries of a step cost
+// 2.5-3 us each on B200 (measured with the device-side timeline, profiles/sn_phases.py) against ~20 us of work, so
+// phase A, phase B (+ SGD update) and the NEXT steps run inside ONE cooperative launch of n_tiles CTAs in clusters of 4,
+// separated by grid-wide barriers (one atomic arrival + an acquire poll per CTA) instead of launches.  Cluster c takes
+// column group c of phase B (the DSMEM reduction needs its 4 K-split CTAs in one cluster), CTA i tile i of phase A.
+// Data other CTAs rewrite during the kernel is read with ld.global.cg (L1 is not coherent); the epoch cursor lives in
+// device memory as before, so n_steps consecutive steps of rcn.rs:147-149 are one launch.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sn_grid_barrier(unsigned* counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned v, spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (++spins > (1u << 27)) __trap();   // a lost CTA must fail the launch, not hang the device
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+constexpr int SNP_CLUSTER = 4;    // 8-CTA clusters: only 15 of the 16 needed are co-resident on B200 (GPC sizes); 4-CTA ones fit
+constexpr int SNP_CW = 32;        // so phase B runs 32-column groups x 4 K-splits instead of 64 x 8
+
+__global__ void __launch_bounds__(SNA_THREADS, 1)
+smallnet_persistent_kernel(const __grid_constant__ SmallNetDesc d, double* __restrict__ params, double* __restrict__ feats,
+                           int B, double* __restrict__ acts, double* __restrict__ deltas, double* __restrict__ stats_partial,
+                           double* __restrict__ small_partial, const __grid_constant__ SmallNetFront fr, int ksplit,
+                           int col_groups, double* __restrict__ grads, double* __restrict__ stats,
+                           const __grid_constant__ SnUpdate upd, int n_steps, unsigned* __restrict__ gbar) {
+    extern __shared__ __align__(128) unsigned char sn_smem[];
+    const int n_tiles = (B + SN_TB - 1) / SN_TB;
+    const int cid = (int)blockIdx.x / SNP_CLUSTER;
+    const int rank = (int)blockIdx.x % SNP_CLUSTER;             // == cluster.block_rank() for cluster dims (4, 1, 1)
+    DpPush nodp{};
+    nodp.world = 1;
+    unsigned arrivals = 0;
+#ifdef RCN_SN_PHASES
+#define SNP_STAMP(k) do { if (threadIdx.x == 0 && blockIdx.x < 1024) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_snp_stamp[blockIdx.x][k] = (long long)_t; } } while (0)
+#else
+#define SNP_STAMP(k) do { } while (0)
+#endif
+    for (int step = 0; step < n_steps; ++step) {
+        SNP_STAMP(0);
+        if ((int)blockIdx.x < n_tiles)
+            sn_phase_a<2, true>(d, params, feats, B, nullptr, nullptr, acts, deltas, stats_partial, small_partial, 1, fr,
+                                (int)blockIdx.x, sn_smem, step);
+        SNP_STAMP(1);
+        arrivals += gridDim.x;
+        sn_grid_barrier(gbar, arrivals);                          // every tile's features / deltas / partials are in L2
+        SNP_STAMP(2);
+        if (cid <= col_groups)
+            sn_phase_b<2, true, 32>(d, feats, small_partial, deltas, B, ksplit, col_groups, grads, stats_partial, n_tiles, stats, nodp,
+                                upd, cid, rank, SNP_CLUSTER, reinterpret_cast<double*>(sn_smem),
+                                reinterpret_cast<double*>(sn_smem) + SNA_WARPS * SN_TB * SN_ZPITCH, 0u);   // sP | sD alias phase A's buffers
+        SNP_STAMP(3);
+        if (step + 1 < n_steps) {
+            arrivals += gridDim.x;
+            sn_grid_barrier(gbar, arrivals);                      // the updated parameters and the cursor are in L2
+        }
+        SNP_STAMP(4);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -753,6 +870,77 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
     return RCN_OK;
 }
 
+// Can `n_steps` steps of this shape run as one persistent launch?  Needs the staged front end, 8 K-splits (= the cluster
+// size), every tile and every column-group cluster co-resident (one CTA per SM).
+static void smallnet_persistent_plan(const SmallNetDesc& d, size_t B, int* splits, int* ksplit, int* col_groups, int* grid) {
+    size_t ks = (B + SNP_CLUSTER - 1) / SNP_CLUSTER;
+    ks = (ks + 63) / 64 * 64;                                   // whole 64-sample chunks
+    *ksplit = (int)ks;
+    *splits = (int)((B + ks - 1) / ks);
+    *col_groups = (int)cdiv(d.n_in, SNP_CW);
+    const size_t n_tiles = cdiv(B, SN_TB);
+    size_t g = n_tiles > (size_t)SNP_CLUSTER * (*col_groups + 1) ? n_tiles : (size_t)SNP_CLUSTER * (*col_groups + 1);
+    *grid = (int)((g + SNP_CLUSTER - 1) / SNP_CLUSTER * SNP_CLUSTER);
+}
+
+bool smallnet_persistent_eligible(const SmallNetDesc& d, const SmallNetFront& fr, size_t B) {
+    // Opt-in (RCN_CUDA_PERSISTENT=1, read per call): measured on B200 the grid barrier costs ~1.3 us against ~2.7 us for a
+    // kernel boundary, but without L1-resident weights and with 4 instead of 8 K-splits the phases themselves are slower,
+    // and the step comes out at 25.6 us against 24.4 us for the two-kernel graph (profiles/sn_phases.py persistent).
+    const char* env = getenv("RCN_CUDA_PERSISTENT");
+    if (!(env && env[0] == '1') || !fr.use_cp || B == 0 || B > smallnet_max_batch()) return false;
+    int splits, ksplit, col_groups, grid;
+    smallnet_persistent_plan(d, B, &splits, &ksplit, &col_groups, &grid);
+    const size_t n_small = (size_t)(d.n_params - d.b_off[0]);
+    if (splits != SNP_CLUSTER || n_small > (size_t)SNA_WARPS * SN_TB * SN_ZPITCH) return false;
+    const size_t smem = kernel_a_smem(d, &fr);   // phase B's partial tile and delta chunks alias phase A's dynamic buffers
+    if (smem < ((size_t)SNA_WARPS * SN_TB * SN_ZPITCH + 2 * 64 * SN_DPITCH) * sizeof(double) || smem > 200 * 1024) return false;
+    return grid <= 144;                          // one CTA per SM, all co-resident (the cooperative launch checks again)
+}
+
+int launch_smallnet_persistent(const SmallNetDesc& d, double* params, double* feats, size_t B, double* acts, double* deltas,
+                               double* grads, double* stats, DevBuf& workspace, const SmallNetFront& front,
+                               const SnUpdate& update, int n_steps, cudaStream_t stream) {
+    if (n_steps <= 0) return RCN_OK;
+    int splits, ksplit, col_groups, grid;
+    smallnet_persistent_plan(d, B, &splits, &ksplit, &col_groups, &grid);
+    const int n_tiles = (int)cdiv(B, SN_TB);
+    const int n_small = d.n_params - d.b_off[0];
+    // workspace: [barrier counter (256 B)] | per-tile statistics partials | per-tile small-parameter gradient partials
+    RCN_TRY(workspace.reserve(256 + (2 + (size_t)n_small) * (size_t)n_tiles * sizeof(double)));
+    unsigned* gbar = workspace.as<unsigned>();
+    double* stats_partial = reinterpret_cast<double*>(workspace.as<char>() + 256);
+    double* small_partial = stats_partial + 2 * (size_t)n_tiles;
+    RCN_CUDA_TRY(cudaMemsetAsync(gbar, 0, 256, stream));
+    const size_t smem = kernel_a_smem(d, &front);
+    static SmemAttrCache attr;
+    if (attr.need(smem)) RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(SNA_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = SNP_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident, or the launch fails: the barriers cannot deadlock
+    at[1].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 2;
+    const int Bi = (int)B;
+    static const bool debug = []() { const char* e = getenv("RCN_CUDA_DEBUG"); return e && e[0] == '1'; }();
+    if (debug) {
+        int n_clusters = -1;
+        cudaError_t oe = cudaOccupancyMaxActiveClusters(&n_clusters, smallnet_persistent_kernel, &cfg);
+        fprintf(stderr, "[rcn_cuda] persistent kernel: grid %d CTAs (%d clusters of %d), smem %zu B, max active clusters %d (%s)\n",
+                grid, grid / SNP_CLUSTER, SNP_CLUSTER, smem, n_clusters, cudaGetErrorString(oe));
+    }
+    RCN_LAUNCH("smallnet_persistent_kernel", stream,
+               cudaLaunchKernelEx(&cfg, smallnet_persistent_kernel, d, params, feats, Bi, acts, deltas, stats_partial, small_partial,
+                                  front, ksplit, col_groups, grads, stats, update, n_steps, gbar));
+    return RCN_OK;
+}
+
 }  // namespace rcn
 
 #ifdef RCN_TIMELINE
@@ -760,6 +948,9 @@ extern "C" int rcn_cuda_debug_timeline_reset_smallnet() { return rcn_tl::reset_h
 extern "C" int rcn_cuda_debug_timeline_read_smallnet(unsigned long long* out, unsigned* seq) { return rcn_tl::read_host(out, seq); }
 #endif
 #ifdef RCN_SN_PHASES
+extern "C" int rcn_cuda_debug_snp_stamps(long long* out /* [1024][8] */) {
+    return cudaMemcpyFromSymbol(out, rcn::g_snp_stamp, sizeof(rcn::g_snp_stamp)) == cudaSuccess ? 0 : 4;
+}
 extern "C" int rcn_cuda_debug_sn_phases(long long* out /* [1024][8] */) {
     return cudaMemcpyFromSymbol(out, rcn::g_sn_phase, sizeof(rcn::g_sn_phase)) == cudaSuccess ? 0 : 4;
 }

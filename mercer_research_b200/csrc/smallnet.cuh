@@ -58,4 +58,11 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
                              DevBuf& workspace, const SmallNetFront* front, cudaStream_t stream,
                              const DpPush* dp_push = nullptr, const SnUpdate* update = nullptr);
 
+// n_steps consecutive single-GPU steps (kernel A, kernel B + SGD update, epoch cursor) as ONE persistent cooperative launch
+// with grid-wide barriers instead of kernel boundaries; `update` must carry params / scale (and the cursor in epoch mode).
+bool smallnet_persistent_eligible(const SmallNetDesc& d, const SmallNetFront& fr, size_t B);
+int launch_smallnet_persistent(const SmallNetDesc& d, double* params, double* feats, size_t B, double* acts, double* deltas,
+                               double* grads, double* stats, DevBuf& workspace, const SmallNetFront& front,
+                               const SnUpdate& update, int n_steps, cudaStream_t stream);
+
 }  // namespace rcn

@@ -413,6 +413,11 @@ class RCN:
     def epoch_step(self, eta: float):
         _lib.check(self._lib.rcn_cuda_epoch_step(self._h, float(eta)))
 
+    def epoch_run(self, eta: float, n_steps: int):
+        """``n_steps`` iterations of ``for batch in training_set.chunks_exact(batch) { train_batch(batch, eta) }``
+        (rcn.rs:147-149) over the bound dataset; one persistent launch where the shape allows it."""
+        _lib.check(self._lib.rcn_cuda_epoch_run(self._h, float(eta), int(n_steps)))
+
     def train_epoch_host(self, images, labels, batch: int, eta: float, global_batch: int = 0):
         """``for batch in training_set.chunks_exact(batch) { train_batch(batch, eta) }`` (rcn.rs:147-149) over a HOST
         dataset (numpy, already shuffled; pin it for copy/compute overlap). The copy of chunk k+1 overlaps the kernels of

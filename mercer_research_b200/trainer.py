@@ -150,6 +150,13 @@ class DataParallelTrainer:
 
     def epoch_steps(self, n: int):
         """Exactly ``n`` steps: whole graph replays, the remainder eagerly."""
+        import os
+        if self.world == 1 and os.environ.get("RCN_CUDA_PERSISTENT") == "1":
+            # opt-in: the library runs all n steps as ONE persistent cooperative launch where the shape allows it
+            import torch
+            self.model.set_stream(torch.cuda.current_stream().cuda_stream)
+            self.model.epoch_run(self.eta, n)
+            return
         spg = getattr(self, "steps_per_graph", 1) if getattr(self, "graph", None) is not None else 0
         if spg:
             for _ in range(n // spg):

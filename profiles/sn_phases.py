@@ -96,7 +96,35 @@ def timeline(B=1024, steps=40):
         print(f"  {name:45s} {np.median(v):8.0f} {v.min():8.0f} {v.max():8.0f}")
 
 
+def persistent(B=1024, steps=50):
+    """Phase spans inside the persistent step kernel (rcn_cuda_epoch_run), %globaltimer stamps of the second-to-last step."""
+    dev = torch.device("cuda", 0)
+    model = RCN(10, [RCNLayer.Convolve2D(Padding.Same), RCNLayer.Pool2D(Pooling.Max)], [30])
+    model.load_weights_and_bias(784)
+    model.set_params(np.random.default_rng(1).standard_normal(model.n_params) * 0.1)
+    N = B * 64
+    imgs = torch.randint(0, 256, (N, 28, 28), dtype=torch.uint8, device=dev)
+    labels = (torch.arange(N, device=dev) % 10).to(torch.int64)
+    model.gen_scales(model.flatten_feature_set(imgs[:4096]))
+    model.epoch_bind(imgs, labels, B)
+    model.epoch_run(3.0, steps)
+    torch.cuda.synchronize()
+    out = np.zeros((1024, 8), dtype=np.int64)
+    assert model._lib.rcn_cuda_debug_snp_stamps(out.ctypes.data_as(C.c_void_p)) == 0
+    n = (B + 7) // 8
+    t = out[:n, :5]
+    t0 = t[:, 0].min()
+    print(f"persistent kernel, last step, {n} CTAs; ns relative to the first CTA's step start (min / median / max over CTAs)")
+    for k, name in enumerate(["step start", "phase A done", "barrier 1 passed", "phase B done", "step end"]):
+        v = t[:, k] - t0
+        print(f"  {name:20s} {v.min():8d} {int(np.median(v)):8d} {v.max():8d}")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "persistent":
+        persistent(int(sys.argv[2]) if len(sys.argv) > 2 else 1024)
+        sys.exit(0)
+
     if len(sys.argv) > 1 and sys.argv[1] == "timeline":
         timeline(int(sys.argv[2]) if len(sys.argv) > 2 else 1024)
         sys.exit(0)

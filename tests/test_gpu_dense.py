@@ -342,6 +342,54 @@ def test_epoch_mode_and_cuda_graph(api):
     assert graphed.epoch_position() == 3 * B
 
 
+@pytest.mark.parametrize("B,N,n_steps", [(1024, 5000, 7), (512, 2100, 9), (96, 1000, 5)])
+def test_epoch_run_persistent_kernel_equals_steps(api, monkeypatch, B, N, n_steps):
+    """rcn_cuda_epoch_run: n steps as ONE persistent cooperative launch (grid barriers instead of kernel boundaries; B = 96
+    does not qualify and takes the per-step path) must equal n epoch_step calls -- same arithmetic; the weight-gradient
+    sum is split 4 x 2 ways over the batch instead of 8, so agreement is to summation order -- including the cursor
+    wrap-around, the last step's statistics and a second call that continues; and both must track the oracle."""
+    import torch
+    monkeypatch.setenv("RCN_CUDA_PERSISTENT", "1")      # opt-in: read by the library on every rcn_cuda_epoch_run call
+    rng = np.random.default_rng(B + n_steps)
+    imgs = rng.integers(0, 256, size=(N, 28, 28), dtype=np.uint8)
+    labels = rng.integers(0, 10, N).astype(np.int64)
+    perm = rng.permutation(N).astype(np.int64)
+    cfg = [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max)]
+    d_imgs, d_labels, d_perm = torch.from_numpy(imgs).cuda(), torch.from_numpy(labels).cuda(), torch.from_numpy(perm).cuda()
+
+    def fresh():
+        m = api.RCN(10, cfg, [30])
+        m.scale_set = (20.0, 35.0)
+        m.load_weights_and_bias(784)
+        m.set_params(np.random.default_rng(3).standard_normal(m.n_params) * 0.05)
+        m.epoch_bind(d_imgs, d_labels, B, perm=d_perm)
+        return m
+
+    stepwise = fresh()
+    for k in range(n_steps + 2):
+        stepwise.epoch_step(3.0)
+    want_stats = stepwise.last_batch_stats()
+    run = fresh()
+    run.epoch_run(3.0, n_steps)
+    run.epoch_run(3.0, 2)
+    assert run.epoch_position() == stepwise.epoch_position()
+    assert_close(run.get_params(), stepwise.get_params(), rtol=1e-11, what="params: persistent launch vs per-step kernels")
+    assert_close(run.get_gradients(), stepwise.get_gradients(), rtol=1e-9, what="last gradients")
+    got_stats = run.last_batch_stats()
+    assert got_stats[1] == want_stats[1] and abs(got_stats[0] - want_stats[0]) <= 1e-11 * abs(want_stats[0])
+    # the oracle's literal loop over the same chunks (rcn.rs:147-149)
+    raw = O.features_u8(CP, imgs)
+    X = O.standardise(raw, 20.0, 35.0)
+    net = O.Net([(30, 784), (10, 30)])
+    p = np.random.default_rng(3).standard_normal(net.n_params) * 0.05
+    pos = 0
+    for k in range(n_steps + 2):
+        idx = perm[pos:pos + B]
+        p, _ = net.train_batch(p, X[idx], np.eye(10)[labels[idx]], 3.0)
+        pos = pos + B if pos + 2 * B <= N else 0
+    assert_close(run.get_params(), p, rtol=1e-9, what="params vs oracle epoch loop")
+
+
 def test_train_epoch_host_equals_step_by_step(api):
     """The pipelined host-dataset loop (double-buffered H2D on a copy stream) == train_batch_images chunk by chunk,
     remainder dropped like chunks_exact (rcn.rs:147-149); per-step (cost, hits) equal last_batch_stats."""
