@@ -459,6 +459,10 @@ def run_gpu(args, wl, rank, world, local_rank):
         "sgd_update_kernel": ["hbm", 3 * n_params * 8, 2 * n_params],
         "dp_allreduce_sgd_kernel": ["hbm", 3 * n_params * 8, 2 * n_params],
         "bias_grad_kernel": ["hbm", B * sum_rows * 8, B * sum_rows],
+        # skinny output layer (rows <= 16 behind a wide layer): each kernel streams the wide activation matrix once
+        "skinny_forward_kernel": ["hbm", B * (shapes[-1][1] + 2 * shapes[-1][0]) * 8, 2 * B * shapes[-1][0] * shapes[-1][1]],
+        "skinny_backward_data_kernel": ["hbm", B * (2 * shapes[-1][1] + shapes[-1][0]) * 8, 2 * B * shapes[-1][0] * shapes[-1][1]],
+        "skinny_backward_weight_kernel": ["hbm", B * (shapes[-1][1] + shapes[-1][0]) * 8, 2 * B * shapes[-1][0] * shapes[-1][1]],
     }
     for tag in ("forward", "backward_data", "backward_weight"):
         for suffix in ("", "(tcgen05 int8 slices)"):

@@ -113,11 +113,217 @@ static int effective_splits(size_t K, int splits) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Skinny output layers (rows <= 16, e.g. the 10 classes behind a 4096-wide hidden layer): 20 flop per 8-byte element of
+// the wide activation matrix, i.e. HBM-bound streaming work, not a GEMM worth tiling for tensor cores.  Each kernel
+// reads the K x N activation matrix exactly once, coalesced, with many independent loads in flight:
+//   forward        z = W a + b, sigmoid (+ output delta)     DMMA: a warp owns a K range for 32 samples, W from L2
+//   backward-data  delta = (W^T delta_up) .* a (1 - a)       thread = feature, W^T column in registers, 16 samples in flight
+//   backward-wt    dW = delta a^T                            thread = feature, 16 accumulators, batch split across CTAs
+// ------------------------------------------------------------------------------------------------
+constexpr int SK_MAX_ROWS = 16;
+constexpr int SK_FWD_SAMPLES = 32;    // samples per CTA of the forward kernel (4 DMMA n-fragments)
+
+__device__ __forceinline__ void sk_dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// grid = ceil(N / 32); 256 threads: warp w contracts k in [w*K/8, (w+1)*K/8) for the CTA's 32 samples.  A lane loads
+// 4 consecutive k of one sample as two 16-byte loads (k = kb + 4t + j, j = 0..3): DMMA k-step j then uses element j of
+// every lane, i.e. the k set {kb + 4t + j}, and the W fragment is read at the same k.  Requires K % 128 == 0.
+__global__ void __launch_bounds__(256) skinny_forward_kernel(const double* __restrict__ W, const double* __restrict__ bias,
+                                                             const double* __restrict__ A_in, int M, int K, int N,
+                                                             double* __restrict__ A_out, double* __restrict__ delta_out,
+                                                             const double* __restrict__ onehot, const int64_t* __restrict__ labels) {
+    __shared__ double part[8][SK_FWD_SAMPLES][SK_MAX_ROWS + 1];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int n0 = blockIdx.x * SK_FWD_SAMPLES;
+    const int kw = K / 8;
+    const int k_lo = warp * kw, k_hi = k_lo + kw;
+    double acc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const double* arow[4];
+    bool aok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = n0 + 8 * j + g;
+        aok[j] = n < N;
+        arow[j] = A_in + (size_t)(aok[j] ? n : 0) * K + 4 * t;
+    }
+    const bool m0ok = g < M, m1ok = g + 8 < M;
+    double2 a[2][4][2];          // two register stages: the loads of block kb + 16 are in flight under the DMMAs of block kb
+    double w[2][4][2];
+    auto load_block = [&](int st, int kb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {               // B fragments: 32 bytes per lane and sample
+            const double2* p = reinterpret_cast<const double2*>(arow[j] + kb);
+            a[st][j][0] = aok[j] ? __ldcs(p) : make_double2(0.0, 0.0);
+            a[st][j][1] = aok[j] ? __ldcs(p + 1) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {               // A fragments: W[m, kb + 4t + q], L2 resident
+            const double* wp = W + (size_t)(kb + 4 * t + q) * M + g;
+            w[st][q][0] = m0ok ? __ldg(wp) : 0.0;
+            w[st][q][1] = m1ok ? __ldg(wp + 8) : 0.0;
+        }
+    };
+    auto mma_block = [&](int st) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sk_dmma(acc[0][j][0], acc[0][j][1], w[st][0][0], a[st][j][0].x);
+            sk_dmma(acc[1][j][0], acc[1][j][1], w[st][0][1], a[st][j][0].x);
+            sk_dmma(acc[0][j][0], acc[0][j][1], w[st][1][0], a[st][j][0].y);
+            sk_dmma(acc[1][j][0], acc[1][j][1], w[st][1][1], a[st][j][0].y);
+            sk_dmma(acc[0][j][0], acc[0][j][1], w[st][2][0], a[st][j][1].x);
+            sk_dmma(acc[1][j][0], acc[1][j][1], w[st][2][1], a[st][j][1].x);
+            sk_dmma(acc[0][j][0], acc[0][j][1], w[st][3][0], a[st][j][1].y);
+            sk_dmma(acc[1][j][0], acc[1][j][1], w[st][3][1], a[st][j][1].y);
+        }
+    };
+    load_block(0, k_lo);
+    for (int kb = k_lo; kb < k_hi; kb += 32) {      // K / 8 is a multiple of 16; blocks are taken in pairs (stage 0, stage 1)
+        if (kb + 16 < k_hi) load_block(1, kb + 16);
+        mma_block(0);
+        if (kb + 16 < k_hi) {
+            if (kb + 32 < k_hi) load_block(0, kb + 32);
+            mma_block(1);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)                     // C fragment: row g (+8i), samples 8j + 2t, 2t + 1
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            part[warp][8 * j + 2 * t][8 * i + g] = acc[i][j][0];
+            part[warp][8 * j + 2 * t + 1][8 * i + g] = acc[i][j][1];
+        }
+    __syncthreads();
+    for (int o = tid; o < SK_FWD_SAMPLES * M; o += 256) {
+        const int s = o / M, m = o - s * M;
+        const int n = n0 + s;
+        if (n >= N) continue;
+        double v = part[0][s][m];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) v += part[q][s][m];          // K ranges in ascending order
+        const double z = v + bias[m];                            // w * a + b           (rcn.rs:287)
+        const double act = sigmoid1(z);                          // sigmoid(&z)         (rcn.rs:289)
+        const size_t idx = (size_t)n * M + m;
+        A_out[idx] = act;
+        if (delta_out) {                                         // (a_L - y) .* sigmoid_prime(z_L)   (rcn.rs:299)
+            const double y = onehot ? onehot[idx] : ((labels[n] == (int64_t)m) ? 1.0 : 0.0);
+            delta_out[idx] = (act - y) * (act * (1.0 - act));
+        }
+    }
+}
+
+// delta_out[k, n] = (sum_m W_up[m, k] delta_up[m, n]) * a (1 - a), a = A[k, n].  grid (ceil(K / 256), ceil(N / 16)).
+template <int MR>
+__global__ void __launch_bounds__(256) skinny_backward_data_kernel(const double* __restrict__ W_up, const double* __restrict__ delta_up,
+                                                                   const double* __restrict__ A, int K, int N,
+                                                                   double* __restrict__ delta_out) {
+    constexpr int NS = 16;
+    constexpr int MP = (MR + 1) & ~1;               // rows padded to an even count: 16-byte shared loads
+    __shared__ __align__(16) double sd[NS][MP];
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    const int n0 = blockIdx.y * NS;
+    for (int i = threadIdx.x; i < NS * MP; i += 256) {
+        const int s = i / MP, m = i - s * MP;
+        sd[s][m] = (m < MR && n0 + s < N) ? delta_up[(size_t)(n0 + s) * MR + m] : 0.0;
+    }
+    double w[MR];
+    if (k < K) {
+#pragma unroll
+        for (int m = 0; m < MR; ++m) w[m] = __ldg(W_up + (size_t)k * MR + m);
+    }
+    __syncthreads();
+    if (k >= K) return;
+    double a[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) a[s] = (n0 + s < N) ? __ldcs(A + (size_t)(n0 + s) * K + k) : 0.0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        if (n0 + s < N) {
+            double v = 0.0;
+#pragma unroll
+            for (int m = 0; m < MR; m += 2) {                               // W^T delta, m ascending
+                const double2 dd = *reinterpret_cast<const double2*>(&sd[s][m]);
+                v = fma(w[m], dd.x, v);
+                if (m + 1 < MR) v = fma(w[m + 1], dd.y, v);
+            }
+            __stcs(delta_out + (size_t)(n0 + s) * K + k, v * (a[s] * (1.0 - a[s])));   // .* sigmoid_prime(z)  (rcn.rs:306-308)
+        }
+    }
+}
+
+// partial[split][m + k*MR] = sum over this split's samples of delta[m, n] * A_prev[k, n].  grid (ceil(K / 256), splits).
+template <int MR>
+__global__ void __launch_bounds__(256) skinny_backward_weight_kernel(const double* __restrict__ delta, const double* __restrict__ A_prev,
+                                                                     int K, int N, int n_per_split, double* __restrict__ partial) {
+    constexpr int NS = 16;
+    constexpr int MP = (MR + 1) & ~1;
+    __shared__ __align__(16) double sd[2][NS][MP];
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    const int n_lo = blockIdx.y * n_per_split, n_hi = min(N, n_lo + n_per_split);
+    const bool kok = k < K;
+    double acc[MR];
+#pragma unroll
+    for (int m = 0; m < MR; ++m) acc[m] = 0.0;
+    // (a two-stage register pipeline over the chunks was measured slower here: 126 registers, 83.7 vs 75.7 us on c5)
+    int buf = 0;
+    for (int nb = n_lo; nb < n_hi; nb += NS, buf ^= 1) {
+        for (int i = threadIdx.x; i < NS * MP; i += 256) {
+            const int s = i / MP, m = i - s * MP;
+            sd[buf][s][m] = (m < MR && nb + s < n_hi) ? delta[(size_t)(nb + s) * MR + m] : 0.0;
+        }
+        double a[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) a[s] = (kok && nb + s < n_hi) ? __ldcs(A_prev + (size_t)(nb + s) * K + k) : 0.0;
+        __syncthreads();   // this chunk's deltas are staged; the other buffer is free again
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int m = 0; m < MR; m += 2) {                                         // samples in ascending order
+                const double2 dd = *reinterpret_cast<const double2*>(&sd[buf][s][m]);
+                acc[m] = fma(dd.x, a[s], acc[m]);
+                if (m + 1 < MR) acc[m + 1] = fma(dd.y, a[s], acc[m + 1]);
+            }
+    }
+    if (kok) {
+        double* out = partial + (size_t)blockIdx.y * K * MR + (size_t)k * MR;
+#pragma unroll
+        for (int m = 0; m < MR; ++m) out[m] = acc[m];
+    }
+}
+
+static bool skinny_layer(size_t M, size_t K) {
+    static const bool off = []() { const char* e = getenv("RCN_CUDA_SKINNY"); return e && e[0] == '0'; }();
+    return !off && gemm_impl() == GEMM_AUTO && M >= 1 && M <= (size_t)SK_MAX_ROWS && K >= 512 && K % 128 == 0;
+}
+
+template <int MR>
+static int launch_skinny_bwd_t(const double* W_up, const double* delta_up, const double* A, size_t M, size_t K, size_t N,
+                               double* delta_out, cudaStream_t stream) {
+    RCN_LAUNCH("skinny_backward_data_kernel", stream,
+               skinny_backward_data_kernel<MR><<<dim3(cdiv(M, 256), cdiv(N, 16)), 256, 0, stream>>>(W_up, delta_up, A, (int)M, (int)N, delta_out));
+    return RCN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Layer entry points
 // ------------------------------------------------------------------------------------------------
 int launch_dense_forward(const double* W, const double* b, const double* A_in, size_t M, size_t K, size_t N,
                          double* A_out, double* delta_out, const double* onehot, const int64_t* labels,
                          cudaStream_t stream, OzakiWorkspace* oz) {
+    if (N > 0 && skinny_layer(M, K)) {
+        RCN_LAUNCH("skinny_forward_kernel", stream,
+                   skinny_forward_kernel<<<cdiv(N, SK_FWD_SAMPLES), 256, 0, stream>>>(W, b, A_in, (int)M, (int)K, (int)N, A_out, delta_out,
+                                                                                      onehot, labels));
+        return RCN_OK;
+    }
     EpiForward epi{b, A_out, delta_out, onehot, labels, (int)M};
     const bool tc = use_tensor_cores(M, N, K, oz);
     return launch_gemm<false, true, EpiForward>(tc ? "dense_forward_gemm(tcgen05 int8 slices)" : "dense_forward_gemm", W, (int)M, A_in,
@@ -126,6 +332,16 @@ int launch_dense_forward(const double* W, const double* b, const double* A_in, s
 
 int launch_dense_backward_data(const double* W_up, const double* delta_up, const double* A, size_t M, size_t K,
                                size_t N, double* delta_out, cudaStream_t stream, OzakiWorkspace* oz) {
+    // here M = width of the layer below (features), K = rows of the upper layer (the contraction)
+    if (N > 0 && M > 0 && skinny_layer(K, M)) {
+        switch (K) {
+#define RCN_SK_CASE(R) case R: return launch_skinny_bwd_t<R>(W_up, delta_up, A, M, K, N, delta_out, stream);
+            RCN_SK_CASE(1) RCN_SK_CASE(2) RCN_SK_CASE(3) RCN_SK_CASE(4) RCN_SK_CASE(5) RCN_SK_CASE(6) RCN_SK_CASE(7) RCN_SK_CASE(8)
+            RCN_SK_CASE(9) RCN_SK_CASE(10) RCN_SK_CASE(11) RCN_SK_CASE(12) RCN_SK_CASE(13) RCN_SK_CASE(14) RCN_SK_CASE(15) RCN_SK_CASE(16)
+#undef RCN_SK_CASE
+            default: break;
+        }
+    }
     EpiBackData epi{A, delta_out, (int)M};
     // A(m,k) = W_up[k, m]; W_up is K x M column-major => k-contiguous with lda = K.
     const bool tc = use_tensor_cores(M, N, K, oz);
@@ -155,12 +371,12 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const double* __restrict
     const int n_lo = blockIdx.y * n_per_split, n_hi = min(N, n_lo + n_per_split);
     double acc = 0.0;
     if (m < M) {
-        for (int n = n_lo + w; n < n_hi; n += 32) {
-            double v[4];
+        for (int n = n_lo + w; n < n_hi; n += 128) {
+            double v[16];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = (n + 8 * u < n_hi) ? delta[(size_t)(n + 8 * u) * M + m] : 0.0;
+            for (int u = 0; u < 16; ++u) v[u] = (n + 8 * u < n_hi) ? __ldcs(delta + (size_t)(n + 8 * u) * M + m) : 0.0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) acc += v[u];
+            for (int u = 0; u < 16; ++u) acc += v[u];
         }
     }
     sm[w][lane] = acc;
@@ -189,6 +405,44 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const double* __restrict
     }
 }
 
+// Wide layers (M >= 256): thread = row, a CTA owns 256 consecutive rows (2 KB contiguous per column: whole DRAM bursts
+// instead of 256-byte islands 8 * M bytes apart) and a column range, 16 loads in flight per thread; per-CTA partials are
+// added in split order by the last CTA of the row block to arrive (deterministic).
+__global__ void __launch_bounds__(256) bias_grad_wide_kernel(const double* __restrict__ delta, int M, int N, int n_per_split,
+                                                             double* __restrict__ db, double* __restrict__ partial,
+                                                             unsigned* __restrict__ tickets) {
+    __shared__ bool s_last;
+    const int m = blockIdx.x * 256 + threadIdx.x;
+    const int S = gridDim.y;
+    const int n_lo = blockIdx.y * n_per_split, n_hi = min(N, n_lo + n_per_split);
+    double acc = 0.0;
+    if (m < M) {
+        for (int n = n_lo; n < n_hi; n += 16) {
+            double v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = (n + u < n_hi) ? __ldcs(delta + (size_t)(n + u) * M + m) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc += v[u];
+        }
+        if (S == 1) db[m] = acc; else partial[(size_t)blockIdx.y * M + m] = acc;
+    }
+    if (S == 1) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(tickets + blockIdx.x, 1u);
+        s_last = (t == (unsigned)S - 1);
+        if (s_last) tickets[blockIdx.x] = 0;
+    }
+    __syncthreads();
+    if (s_last && m < M) {
+        __threadfence();
+        double s = 0.0;
+        for (int q = 0; q < S; ++q) s += __ldcg(partial + (size_t)q * M + m);
+        db[m] = s;
+    }
+}
+
 int launch_reduce_splits(const double* partials, int splits, size_t n, double* out, cudaStream_t stream) {
     unsigned grid = cdiv(n, 256);
     if (grid > kNumSMs * 8) grid = kNumSMs * 8;
@@ -198,6 +452,21 @@ int launch_reduce_splits(const double* partials, int splits, size_t n, double* o
 
 int launch_bias_grad(const double* delta, size_t M, size_t N, double* db, ReduceScratch& rs, cudaStream_t stream) {
     if (M == 0) return RCN_OK;
+    if (M >= 256 && cdiv(M, 256) <= 1023) {
+        const unsigned rb = cdiv(M, 256);
+        unsigned S = (4 * kNumSMs + rb - 1) / rb;
+        const unsigned max_s = (unsigned)((N + 63) / 64);
+        if (S > max_s) S = max_s;
+        if (S < 1) S = 1;
+        int n_per_split = (int)((N + S - 1) / S);
+        n_per_split = (n_per_split + 15) / 16 * 16;
+        S = (unsigned)((N + n_per_split - 1) / n_per_split);
+        if (S < 1) S = 1;
+        RCN_TRY(rs.ensure((size_t)S * M * sizeof(double), stream));
+        RCN_LAUNCH("bias_grad_kernel", stream,
+                   bias_grad_wide_kernel<<<dim3(rb, S), 256, 0, stream>>>(delta, (int)M, (int)N, n_per_split, db, rs.partials(), rs.tickets()));
+        return RCN_OK;
+    }
     const unsigned row_blocks = cdiv(M, 32);
     if (row_blocks > 1023) return fail(RCN_ERR_INVALID, "layer too wide for the bias-gradient reduction");
     // enough column splits to cover the machine a few times over, each at least 256 columns deep
@@ -218,6 +487,28 @@ int launch_bias_grad(const double* delta, size_t M, size_t N, double* db, Reduce
 int launch_dense_backward_weight(const double* delta, const double* A_prev, size_t M, size_t N, size_t Kb, double* dW,
                                  double* db, DevBuf& workspace, ReduceScratch& rs, cudaStream_t stream, OzakiWorkspace* oz) {
     if (M == 0) return RCN_OK;
+    if (N > 0 && Kb > 0 && skinny_layer(M, N)) {
+        // thread = input feature, batch split across CTAs; the partials are added in split order (deterministic)
+        int splits = (int)((4 * (size_t)kNumSMs + cdiv(N, 256) - 1) / cdiv(N, 256));
+        const int max_splits = (int)((Kb + 63) / 64);
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+        int n_per_split = (int)((Kb + splits - 1) / splits);
+        n_per_split = (n_per_split + 15) / 16 * 16;
+        splits = (int)((Kb + n_per_split - 1) / n_per_split);
+        RCN_TRY(workspace.reserve((size_t)splits * M * N * sizeof(double)));
+        double* part = workspace.as<double>();
+        const dim3 grid(cdiv(N, 256), splits);
+        switch (M) {
+#define RCN_SK_CASE(R) case R: RCN_LAUNCH("skinny_backward_weight_kernel", stream, skinny_backward_weight_kernel<R><<<grid, 256, 0, stream>>>(delta, A_prev, (int)N, (int)Kb, n_per_split, part)); break;
+            RCN_SK_CASE(1) RCN_SK_CASE(2) RCN_SK_CASE(3) RCN_SK_CASE(4) RCN_SK_CASE(5) RCN_SK_CASE(6) RCN_SK_CASE(7) RCN_SK_CASE(8)
+            RCN_SK_CASE(9) RCN_SK_CASE(10) RCN_SK_CASE(11) RCN_SK_CASE(12) RCN_SK_CASE(13) RCN_SK_CASE(14) RCN_SK_CASE(15) RCN_SK_CASE(16)
+#undef RCN_SK_CASE
+            default: return fail(RCN_ERR_INVALID, "internal: skinny layer with %zu rows", M);
+        }
+        RCN_TRY(launch_reduce_splits(part, splits, M * N, dW, stream));
+        return launch_bias_grad(delta, M, Kb, db, rs, stream);
+    }
     if (N > 0 && use_tensor_cores(M, N, Kb, oz)) {
         // enough output tiles to fill the machine without splitting the batch: one exact pass, deterministic by construction
         EpiStore epi{dW, (int)M, 0};

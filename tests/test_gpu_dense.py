@@ -71,6 +71,9 @@ SHAPES = [
     (12, [7, 5], 3, 1),           # single sample
     (300, [129, 65, 33], 17, 200),
     (640, [384, 256], 10, 2048),  # exercises the 128x128 tiles and split-K
+    (200, [640], 10, 333),        # 640 -> 10: the skinny output-layer kernels (rows <= 16, K % 128 == 0), ragged batch
+    (96, [512], 16, 1000),        # 512 -> 16: skinny kernels at their row limit
+    (64, [1024], 3, 50),          # 1024 -> 3: fewer samples than one forward CTA holds
 ]
 
 
