@@ -11,6 +11,6 @@ $CMD > $OUT/bench_${TAG}_${WL}_plain.json 2> $OUT/bench_${TAG}_${WL}_plain.err |
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_${TAG}_${WL}.csv \
     $CMD > $OUT/ncu_${TAG}_${WL}.log 2>&1
 python profiles/run_step.py $WL 4 > $OUT/run_step_${TAG}_${WL}.log 2>&1 || { echo "run_step failed"; exit 1; }
-ncu --set full --clock-control none --import-source on -k "regex:^(smallnet|features_|gemm_f64|sgd_update|bias_grad|reduce_splits|batch_stats|rcn_)" \
+ncu --set full --clock-control none --import-source on -k "regex:^(smallnet|features_|gemm_f64|sgd_update|bias_grad|reduce_splits|batch_stats|skinny_|rcn_)" \
     -s 3 -c 9 -f -o $OUT/full_${TAG}_${WL} python profiles/run_step.py $WL 4 > $OUT/ncu_full_${TAG}_${WL}.log 2>&1
 ls -la $OUT | tail -8

@@ -21,7 +21,10 @@ M = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", 
      "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
      "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
      "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]
-NAMES = {"smallnet_fwd_bwd_kernel<1>": "smallnet_fwd_bwd_kernel(fused features)", "smallnet_fwd_bwd_kernel<0>": "smallnet_fwd_bwd_kernel"}
+NAMES = {"smallnet_fwd_bwd_kernel<1>": "smallnet_fwd_bwd_kernel(fused features)", "smallnet_fwd_bwd_kernel<2>": "smallnet_fwd_bwd_kernel(fused features)",
+         "smallnet_fwd_bwd_kernel<0>": "smallnet_fwd_bwd_kernel", "smallnet_wgrad_kernel<2>": "smallnet_wgrad_kernel(+SGD update)",
+         "smallnet_wgrad_kernel<0>": "smallnet_wgrad_kernel", "smallnet_wgrad_kernel<1>": "smallnet_wgrad_kernel",
+         "smallnet_wgrad_kernel<3>": "smallnet_wgrad_kernel(+exchange+SGD update)"}
 
 
 def to_bytes(v, unit):
