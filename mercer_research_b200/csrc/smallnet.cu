@@ -531,31 +531,32 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
         double acc[4][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.0;
-        int buf = 0;
-        for (int c0 = b_begin; c0 < b_end; c0 += 64, buf ^= 1) {
-            double bf[U];
+        // Chunks are taken in PAIRS: both chunks' A0 fragments (2 x U loads per lane) and both delta slices are requested
+        // before the one barrier, so a K-split of 128 samples (the canonical case) pays ONE L2 round trip, not two.
+        auto load_feats = [&](double (&bf)[U], int c0) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {                    // U A0 loads in flight per lane
+            for (int u = 0; u < U; ++u) {
                 const int b = c0 + kq * (64 / KQ) + u * 4 + t;
                 bf[u] = (b < b_end && col_ok) ? (PERSIST ? __ldcg(feats + (size_t)b * L + col) : feats[(size_t)b * L + col]) : 0.0;   // B frag: row t (sample), col g (feature)
             }
-            double* sd = sD + buf * (64 * SN_DPITCH);
-            {
-                double vd[8];
+        };
+        auto load_delta = [&](double (&vd)[8], int c0) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {            // 64 x 32 slice = 8 elements per thread, all loads first
-                    const int idx = u * SNB_THREADS + tid;
-                    const int kk = idx >> 5, mm = idx & 31;
-                    const int b = c0 + kk;
-                    vd[u] = (mm < R0 && b < b_end) ? (PERSIST ? __ldcg(deltas + (size_t)b * R0 + mm) : deltas[(size_t)b * R0 + mm]) : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int idx = u * SNB_THREADS + tid;
-                    sd[(idx >> 5) * SN_DPITCH + (idx & 31)] = vd[u];
-                }
+            for (int u = 0; u < 8; ++u) {            // 64 x 32 slice = 8 elements per thread
+                const int idx = u * SNB_THREADS + tid;
+                const int kk = idx >> 5, mm = idx & 31;
+                const int b = c0 + kk;
+                vd[u] = (mm < R0 && b < b_end) ? (PERSIST ? __ldcg(deltas + (size_t)b * R0 + mm) : deltas[(size_t)b * R0 + mm]) : 0.0;
             }
-            if (PERSIST) asm volatile("bar.sync 2, 256;" ::: "memory"); else __syncthreads();   // chunk staged; the other buffer is free again because everyone passed this barrier
+        };
+        auto store_delta = [&](const double (&vd)[8], double* sd) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = u * SNB_THREADS + tid;
+                sd[(idx >> 5) * SN_DPITCH + (idx & 31)] = vd[u];
+            }
+        };
+        auto mma_chunk = [&](const double (&bf)[U], const double* sd) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int kk = kq * (64 / KQ) + u * 4 + t;
@@ -563,6 +564,19 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
                 for (int i = 0; i < 4; ++i)
                     if (i < mf) sn_dmma(acc[i][0], acc[i][1], sd[kk * SN_DPITCH + i * 8 + g], bf[u]);  // A frag: row g (m), col t
             }
+        };
+        for (int c0 = b_begin; c0 < b_end; c0 += 128) {
+            const bool two = c0 + 64 < b_end;
+            double bf0[U], bf1[U], vd0[8], vd1[8];
+            load_feats(bf0, c0);
+            load_delta(vd0, c0);
+            if (two) { load_feats(bf1, c0 + 64); load_delta(vd1, c0 + 64); }
+            store_delta(vd0, sD);
+            if (two) store_delta(vd1, sD + 64 * SN_DPITCH);
+            if (PERSIST) asm volatile("bar.sync 2, 256;" ::: "memory"); else __syncthreads();   // both slices staged
+            mma_chunk(bf0, sD);
+            if (two) mma_chunk(bf1, sD + 64 * SN_DPITCH);
+            if (c0 + 128 < b_end) { if (PERSIST) asm volatile("bar.sync 2, 256;" ::: "memory"); else __syncthreads(); }   // before the slices are overwritten
         }
         const int cl = kq * CW + oct * 8 + 2 * t;           // C frag: row g (m), cols 2t, 2t+1; one CW x 32 tile per kq
 #pragma unroll
