@@ -161,8 +161,6 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
             }
         }
     }
-    // prefetch biases + narrow-layer weights (overlaps with the front end / the DMMA phase)
-    for (int i = tid; i < n_small; i += SNA_THREADS) s_small[i] = sn_ld<PERSIST>(params + small_base + i);
 
     // layer-0 weight fragments: each warp owns a K range of the n_in-deep contraction; its first SN_U k-steps go into
     // registers NOW and the rest is prefetched into L1, so the L2 latency is hidden behind the front end
@@ -183,6 +181,8 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
 #pragma unroll
         for (int i = 0; i < 4; ++i) w_pre[u][i] = (kok && rowok[i]) ? sn_ld<PERSIST>(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
     }
+    // biases + narrow-layer weights into shared memory (after the register loads above: the store waits for its load)
+    for (int i = tid; i < n_small; i += SNA_THREADS) s_small[i] = sn_ld<PERSIST>(params + small_base + i);
     {
         const long long lo = (long long)min((ks_begin + SN_U) * 4, L) * R0, hi = (long long)min(ks_end * 4, L) * R0;   // doubles
         if (!PERSIST)   // (a persistent kernel must not keep parameters in L1 across steps)
