@@ -41,7 +41,7 @@ __device__ __forceinline__ void sn_dmma(double& c0, double& c1, double a, double
 // Optional phase clock (profiles/sn_phases.py builds a second library with -DRCN_SN_PHASES): thread 0 of every CTA of
 // kernel A stamps clock64() at the phase boundaries.  Compiled out of the product library.
 #ifdef RCN_SN_PHASES
-__device__ long long g_sn_phase[1024][8];
+__device__ long long g_sn_phase[1024][16];
 __device__ long long g_snp_stamp[1024][8];
 #define SN_PHASE(k) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_sn_phase[blockIdx.x][k] = clock64(); } while (0)
 #else
@@ -148,20 +148,24 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
                 cpbulk::mbar_expect_tx(&s_bar, img_bytes * (uint32_t)n_live);
             }
             __syncwarp();
-            if (lane < SN_TB) {
-                long long lab = -1;
-                if (lane < n_live) {
-                    const int sample = s0 + lane;
-                    const size_t src = source_image(fr.bi, (size_t)sample);
-                    cpbulk::bulk_load(stg + lane * fr.cp.stage_bytes, fr.images + image_slot(fr.bi, src) * img_bytes, img_bytes, &s_bar);
-                    lab = fr.bi.cursor ? fr.bi.labels_all[src] : (labels ? labels[sample] : 0);
-                    if (fr.bi.labels_batch) fr.bi.labels_batch[sample] = lab;
-                }
-                s_label[lane] = lab;
+            if (lane < n_live) {
+                const size_t src = source_image(fr.bi, (size_t)(s0 + lane));
+                cpbulk::bulk_load(stg + lane * fr.cp.stage_bytes, fr.images + image_slot(fr.bi, src) * img_bytes, img_bytes, &s_bar);
             }
+        } else if (warp == SNA_WARPS - 1 && lane < SN_TB) {
+            // the labels take a second dependent global load: another warp fetches them, off warp 0's critical path
+            long long lab = -1;
+            if (lane < n_live) {
+                const int sample = s0 + lane;
+                const size_t src = source_image(fr.bi, (size_t)sample);
+                lab = fr.bi.cursor ? fr.bi.labels_all[src] : (labels ? labels[sample] : 0);
+                if (fr.bi.labels_batch) fr.bi.labels_batch[sample] = lab;
+            }
+            s_label[lane] = lab;
         }
     }
 
+    SN_PHASE(8);
     // layer-0 weight fragments: each warp owns a K range of the n_in-deep contraction; its first SN_U k-steps go into
     // registers NOW and the rest is prefetched into L1, so the L2 latency is hidden behind the front end
     const double* __restrict__ W0 = params + d.w_off[0];
@@ -181,8 +185,17 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
 #pragma unroll
         for (int i = 0; i < 4; ++i) w_pre[u][i] = (kok && rowok[i]) ? sn_ld<PERSIST>(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
     }
+    SN_PHASE(9);
     // biases + narrow-layer weights into shared memory (after the register loads above: the store waits for its load)
-    for (int i = tid; i < n_small; i += SNA_THREADS) s_small[i] = sn_ld<PERSIST>(params + small_base + i);
+    if (PERSIST) {
+        for (int i = tid; i < n_small; i += SNA_THREADS) s_small[i] = sn_ld<true>(params + small_base + i);
+    } else {   // asynchronous copies: no register dependency, so no warp waits an L2 round trip here
+        for (int i = tid; i < n_small; i += SNA_THREADS) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(s_small + i);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(params + small_base + i) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     {
         const long long lo = (long long)min((ks_begin + SN_U) * 4, L) * R0, hi = (long long)min(ks_end * 4, L) * R0;   // doubles
         if (!PERSIST)   // (a persistent kernel must not keep parameters in L1 across steps)
@@ -195,9 +208,12 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
         // all 16 warps transpose and run the conv+pool stages over the 8 images together (features_device.cuh) ---------
         int* tiles = reinterpret_cast<int*>(stg + SN_TB * fr.cp.stage_bytes);
         const int n_live = min(SN_TB, B - s0);
+        SN_PHASE(10);
         for (int i = tid; i < SN_TB * fr.cp.tile_ints; i += SNA_THREADS) tiles[i] = 0;
         for (int i = n_live * pitch + tid; i < SN_TB * pitch; i += SNA_THREADS) tile[i] = 0.0;   // absent samples
+        SN_PHASE(11);
         __syncthreads();
+        SN_PHASE(12);
         cpbulk::mbar_wait(&s_bar, (uint32_t)(step & 1));
         SN_PHASE(1);
         cp_transpose_images(stg, fr.cp.stage_bytes, tiles, fr.cp.tile_ints, n_live, fr.H, fr.W, fr.cp, tid, SNA_THREADS);
@@ -317,6 +333,7 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
             zpart[(warp * SN_TB + 2 * t + 1) * SN_ZPITCH + i * 8 + g] = acc[i][1];
         }
     }
+    if (!PERSIST) asm volatile("cp.async.wait_all;" ::: "memory");   // this thread's share of the small parameters has landed
     __syncthreads();
     SN_PHASE(4);
     const int last = d.n_layers - 1;
@@ -470,6 +487,10 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
                         double* __restrict__ stats_partial, double* __restrict__ small_partial, int backward,
                         const __grid_constant__ SmallNetFront fr) {
     extern __shared__ __align__(128) unsigned char sn_smem[];
+    // programmatic dependent launch (when the host asked for it; no-ops otherwise): let the next kernel's launch proceed
+    // under this one, and wait here until the previous kernel has completed and flushed before touching global memory
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     sn_phase_a<FUSED, false>(d, params, feats, B, onehot, labels, acts, deltas, stats_partial, small_partial, backward, fr,
                              (int)blockIdx.x, sn_smem, 0);
 }
@@ -681,6 +702,8 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
     extern __shared__ __align__(16) double sP_dyn[];          // partial tile: SNB_TILE (col CTAs) or n_small doubles
     __shared__ __align__(16) double sD_static[2 * 64 * SN_DPITCH];   // 36 KB
     // grid (col_groups + 1, S) in clusters of (1, S, 1): blockIdx.y == cluster.block_rank()
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     sn_phase_b<MODE, false, 64>(d, feats, small_partial, deltas, B, ksplit, col_groups, grads, stats_partial, n_stat, stats, dp, upd,
                             (int)blockIdx.x, (int)blockIdx.y, (int)gridDim.y, sP_dyn, sD_static, gridDim.x * gridDim.y);
 }
@@ -775,6 +798,13 @@ static void smallnet_splits(size_t B, int* splits, int* ksplit) {
 
 size_t smallnet_max_batch() { return (size_t)1 << 22; }
 
+// Programmatic dependent launch between the step's kernels: the launch latency of kernel N+1 overlaps kernel N
+// (RCN_CUDA_PDL=0 turns it off; measured on c2: gap A->B 2.9 -> 1.8 us, B->A 2.3 -> 1.95 us, step 22.25 -> 21.77 us).
+static bool sn_pdl_enabled() {
+    static const bool on = []() { const char* e = getenv("RCN_CUDA_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 static size_t kernel_a_smem(const SmallNetDesc& d, const SmallNetFront* fr) {
     size_t bytes = ((size_t)SNA_WARPS * SN_TB * SN_ZPITCH + SN_MAX_SMALL) * sizeof(double);
     if (fr) {
@@ -800,27 +830,32 @@ static int launch_kernel_a(const SmallNetDesc& d, const double* params, double* 
     const unsigned n_tiles = cdiv(B, SN_TB);
     const size_t smem = kernel_a_smem(d, fr);
     static SmallNetFront empty_front{};
+    const int Bi = (int)B;
+    auto launch = [&](auto kern, SmemAttrCache& attr, const char* name, const SmallNetFront& front) -> int {
+        if (attr.need(smem)) RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(n_tiles, 1, 1);
+        cfg.blockDim = dim3(SNA_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = sn_pdl_enabled() ? 1 : 0;
+        RCN_LAUNCH(name, stream, cudaLaunchKernelEx(&cfg, kern, d, params, feats, Bi, onehot, labels, acts, deltas, stats_partial,
+                                                    small_partial, backward, front));
+        return RCN_OK;
+    };
     if (fr && fr->use_cp) {
-        auto kern = smallnet_fwd_bwd_kernel<2>;
         static SmemAttrCache attr;
-        if (attr.need(smem)) RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RCN_LAUNCH("smallnet_fwd_bwd_kernel(fused features)", stream,
-                   kern<<<n_tiles, SNA_THREADS, smem, stream>>>(d, params, feats, (int)B, onehot, labels, acts, deltas,
-                                                               stats_partial, small_partial, backward, *fr));
+        RCN_TRY(launch(smallnet_fwd_bwd_kernel<2>, attr, "smallnet_fwd_bwd_kernel(fused features)", *fr));
     } else if (fr) {
-        auto kern = smallnet_fwd_bwd_kernel<1>;
         static SmemAttrCache attr;
-        if (attr.need(smem)) RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RCN_LAUNCH("smallnet_fwd_bwd_kernel(fused features)", stream,
-                   kern<<<n_tiles, SNA_THREADS, smem, stream>>>(d, params, feats, (int)B, onehot, labels, acts, deltas,
-                                                               stats_partial, small_partial, backward, *fr));
+        RCN_TRY(launch(smallnet_fwd_bwd_kernel<1>, attr, "smallnet_fwd_bwd_kernel(fused features)", *fr));
     } else {
-        auto kern = smallnet_fwd_bwd_kernel<0>;
         static SmemAttrCache attr;
-        if (attr.need(smem)) RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RCN_LAUNCH("smallnet_fwd_bwd_kernel", stream,
-                   kern<<<n_tiles, SNA_THREADS, smem, stream>>>(d, params, feats, (int)B, onehot, labels, acts, deltas,
-                                                               stats_partial, small_partial, backward, empty_front));
+        RCN_TRY(launch(smallnet_fwd_bwd_kernel<0>, attr, "smallnet_fwd_bwd_kernel", empty_front));
     }
     return RCN_OK;
 }
@@ -869,13 +904,15 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
     cfg.blockDim = dim3(SNB_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem_b;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = splits;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = sn_pdl_enabled() ? 2 : 1;
     const int Bi = (int)B;
     auto kern = mode == 1 ? smallnet_wgrad_kernel<1> : mode == 2 ? smallnet_wgrad_kernel<2> : mode == 3 ? smallnet_wgrad_kernel<3> : smallnet_wgrad_kernel<0>;
     RCN_LAUNCH(mode == 2 ? "smallnet_wgrad_kernel(+SGD update)" : mode == 3 ? "smallnet_wgrad_kernel(+exchange+SGD update)" : "smallnet_wgrad_kernel", stream,
@@ -965,7 +1002,7 @@ extern "C" int rcn_cuda_debug_timeline_read_smallnet(unsigned long long* out, un
 extern "C" int rcn_cuda_debug_snp_stamps(long long* out /* [1024][8] */) {
     return cudaMemcpyFromSymbol(out, rcn::g_snp_stamp, sizeof(rcn::g_snp_stamp)) == cudaSuccess ? 0 : 4;
 }
-extern "C" int rcn_cuda_debug_sn_phases(long long* out /* [1024][8] */) {
+extern "C" int rcn_cuda_debug_sn_phases(long long* out /* [1024][16] */) {
     return cudaMemcpyFromSymbol(out, rcn::g_sn_phase, sizeof(rcn::g_sn_phase)) == cudaSuccess ? 0 : 4;
 }
 #endif

@@ -29,11 +29,16 @@ def main():
     for _ in range(5):
         model.train_batch_images(imgs, labels, 3.0)
     torch.cuda.synchronize()
-    out = np.zeros((1024, 8), dtype=np.int64)
-    rc = model._lib.rcn_cuda_debug_sn_phases(out.ctypes.data_as(C.c_void_p))
+    full = np.zeros((1024, 16), dtype=np.int64)
+    rc = model._lib.rcn_cuda_debug_sn_phases(full.ctypes.data_as(C.c_void_p))
     assert rc == 0
+    out = full[:, :8]
     n = (B + 7) // 8
     d = np.diff(out[:n], axis=1) / 1.965   # ns at 1965 MHz
+    sub = full[:n, [0, 8, 9, 10, 11, 12, 1]]
+    ds = np.diff(sub, axis=1) / 1.965
+    print("  head of kernel A (thread 0): " + ", ".join(f"{nm} {ds[:, k].mean():.0f}" for k, nm in enumerate(
+        ["bulk-load issue + labels", "W fragment loads issued", "small params staged", "zero frames", "barrier", "mbarrier wait"])))
     print(f"kernel A, B={B}, {n} CTAs; per-phase ns (mean / min / max over CTAs)")
     for k, name in enumerate(NAMES):
         print(f"  {name:45s} {d[:, k].mean():8.0f} {d[:, k].min():8.0f} {d[:, k].max():8.0f}")
