@@ -41,7 +41,7 @@ __device__ __forceinline__ void sn_dmma(double& c0, double& c1, double a, double
 // Optional phase clock (profiles/sn_phases.py builds a second library with -DRCN_SN_PHASES): thread 0 of every CTA of
 // kernel A stamps clock64() at the phase boundaries.  Compiled out of the product library.
 #ifdef RCN_SN_PHASES
-__device__ long long g_sn_phase[1024][16];
+__device__ long long g_sn_phase[1024][32];
 __device__ long long g_snp_stamp[1024][8];
 #define SN_PHASE(k) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_sn_phase[blockIdx.x][k] = clock64(); } while (0)
 #else
@@ -353,11 +353,13 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
             for (int o = 1; o < SNA_WARPS; o <<= 1)      // fixed pairwise tree over the 16 K-splits
 #pragma unroll
                 for (int w = 0; w < SNA_WARPS; w += 2 * o) zp[w] += zp[w + o];
+            SN_PHASE(16);
             if (m < R0) {
                 const double z = zp[0] + s_small[m];            // w * a + b      (rcn.rs:287)
                 s_act[0][n][m] = sn_sigmoid(z);                 // sigmoid(&z)    (rcn.rs:289)
             }
         }
+        SN_PHASE(17);
         __syncwarp();
         // ---- narrow layers -----------------------------------------------------------------------------------------
         for (int l = 1; l < d.n_layers; ++l) {
@@ -385,6 +387,7 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
                 off += d.rows[l];
             }
         }
+        SN_PHASE(18);
         if (backward) {
             // ---- output delta (rcn.rs:299) and batch statistics (rcn.rs:152-157) ---------------------------------------
             const bool out = m < RL;
@@ -406,6 +409,7 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
                     s_hit[n] = (live && ok) ? 1ull : 0ull;
                 }
             }
+            SN_PHASE(19);
             __syncwarp();
             // ---- backward-data chain (rcn.rs:305-309) -------------------------------------------------------------------
             for (int l = last - 1; l >= 0; --l) {
@@ -424,6 +428,7 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
                 }
                 __syncwarp();
             }
+            SN_PHASE(20);
             size_t off = 0;
             for (int l = 0; l < d.n_layers; ++l) {
                 if (live && m < d.rows[l]) deltas[off * B + (size_t)sample * d.rows[l] + m] = s_del[l][n][m];
@@ -431,6 +436,7 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
             }
         }
     }
+    SN_PHASE(21);
     if (!backward) { RCN_TL_END(0); return; }
     __syncthreads();
     SN_PHASE(6);
@@ -448,10 +454,20 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
     {
         const int n_live = min(SN_TB, B - s0);
         double* sp = small_partial + (size_t)tile_idx * n_small;
-        int task = 0;
-        for (int l = 0; l < d.n_layers; ++l) {
+        int total = 0;                                  // layer l owns 1 task (db_l) + rows[l-1] tasks (columns of dW_l, l >= 1)
+        for (int l = 0; l < d.n_layers; ++l) total += 1 + (l >= 1 ? d.rows[l - 1] : 0);
+        for (int tsk = warp; tsk < total; tsk += SNA_WARPS) {   // each warp decodes only ITS tasks (no shared dealing loop)
+            int l = 0, base = 0;
+            for (;;) {
+                const int cnt = 1 + (l >= 1 ? d.rows[l - 1] : 0);
+                if (tsk < base + cnt) break;
+                base += cnt;
+                ++l;
+            }
+            const int j = tsk - base;
             const int R = d.rows[l];
-            if ((task++ & (SNA_WARPS - 1)) == warp && lane < R) {        // db_l = sum_b delta_l      (rcn.rs:302,309)
+            if (lane >= R) continue;
+            if (j == 0) {                                                    // db_l = sum_b delta_l      (rcn.rs:302,309)
                 double v[SN_TB];
 #pragma unroll
                 for (int b = 0; b < SN_TB; ++b) v[b] = s_del[l][b][lane];
@@ -459,19 +475,15 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
 #pragma unroll
                 for (int b = 0; b < SN_TB; ++b) if (b < n_live) acc += v[b];
                 sp[d.b_off[l] - small_base + lane] = acc;
-            }
-            if (l >= 1) {
-                const int C = d.rows[l - 1];
-                for (int k = 0; k < C; ++k)
-                    if ((task++ & (SNA_WARPS - 1)) == warp && lane < R) {   // dW_l = sum_b delta_l a_{l-1}^T (rcn.rs:303,310)
-                        double v[SN_TB], a[SN_TB];
+            } else {                                                         // dW_l = sum_b delta_l a_{l-1}^T (rcn.rs:303,310)
+                const int k = j - 1;
+                double v[SN_TB], a[SN_TB];
 #pragma unroll
-                        for (int b = 0; b < SN_TB; ++b) { v[b] = s_del[l][b][lane]; a[b] = s_act[l - 1][b][k]; }
-                        double acc = 0.0;
+                for (int b = 0; b < SN_TB; ++b) { v[b] = s_del[l][b][lane]; a[b] = s_act[l - 1][b][k]; }
+                double acc = 0.0;
 #pragma unroll
-                        for (int b = 0; b < SN_TB; ++b) if (b < n_live) acc = fma(v[b], a[b], acc);
-                        sp[d.w_off[l] - small_base + k * R + lane] = acc;
-                    }
+                for (int b = 0; b < SN_TB; ++b) if (b < n_live) acc = fma(v[b], a[b], acc);
+                sp[d.w_off[l] - small_base + k * R + lane] = acc;
             }
         }
     }
@@ -1002,7 +1014,7 @@ extern "C" int rcn_cuda_debug_timeline_read_smallnet(unsigned long long* out, un
 extern "C" int rcn_cuda_debug_snp_stamps(long long* out /* [1024][8] */) {
     return cudaMemcpyFromSymbol(out, rcn::g_snp_stamp, sizeof(rcn::g_snp_stamp)) == cudaSuccess ? 0 : 4;
 }
-extern "C" int rcn_cuda_debug_sn_phases(long long* out /* [1024][16] */) {
+extern "C" int rcn_cuda_debug_sn_phases(long long* out /* [1024][32] */) {
     return cudaMemcpyFromSymbol(out, rcn::g_sn_phase, sizeof(rcn::g_sn_phase)) == cudaSuccess ? 0 : 4;
 }
 #endif

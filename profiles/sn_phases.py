@@ -29,7 +29,7 @@ def main():
     for _ in range(5):
         model.train_batch_images(imgs, labels, 3.0)
     torch.cuda.synchronize()
-    full = np.zeros((1024, 16), dtype=np.int64)
+    full = np.zeros((1024, 32), dtype=np.int64)
     rc = model._lib.rcn_cuda_debug_sn_phases(full.ctypes.data_as(C.c_void_p))
     assert rc == 0
     out = full[:, :8]
@@ -39,6 +39,11 @@ def main():
     ds = np.diff(sub, axis=1) / 1.965
     print("  head of kernel A (thread 0): " + ", ".join(f"{nm} {ds[:, k].mean():.0f}" for k, nm in enumerate(
         ["bulk-load issue + labels", "W fragment loads issued", "small params staged", "zero frames", "barrier", "mbarrier wait"])))
+    tail = full[:n, [4, 16, 17, 5, 18, 19, 20, 21, 6, 7]]
+    dt = np.diff(tail, axis=1) / 1.965
+    print("  tail of kernel A (thread 0): " + ", ".join(f"{nm} {dt[:, k].mean():.0f}" for k, nm in enumerate(
+        ["partial-sum tree", "bias + sigmoid", "narrow layers", "activations out", "delta + statistics", "backward chain", "deltas out",
+         "block barrier", "gradient partials"])))
     print(f"kernel A, B={B}, {n} CTAs; per-phase ns (mean / min / max over CTAs)")
     for k, name in enumerate(NAMES):
         print(f"  {name:45s} {d[:, k].mean():8.0f} {d[:, k].min():8.0f} {d[:, k].max():8.0f}")
