@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) dp_allreduce_sgd_kernel(const DpPeers pee
                                                                double* __restrict__ params, double* __restrict__ grads,
                                                                double scale, long long* __restrict__ cursor, long long batch,
                                                                long long n_samples, const double* __restrict__ stats,
-                                                               double* __restrict__ stats_ring, int already_pushed) {
+                                                               double* __restrict__ stats_ring, int already_pushed, int pipe) {
     const int world = WORLD ? WORLD : world_rt;
     char* self = peers.p[rank];
     DpCtrl* ctrl = reinterpret_cast<DpCtrl*>(self);
@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(256) dp_allreduce_sgd_kernel(const DpPeers pee
                 long long cc = *cursor + batch;
                 if (cc + batch > n_samples) cc = 0;
                 *cursor = cc;
+                if (pipe) cursor[1] += 1;   // pipelined epoch mode: training steps done
             }
             __threadfence();
         }
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(256) dp_allreduce_sgd_kernel(const DpPeers pee
 
 int launch_dp_allreduce_sgd(const DpState& st, double* params, double* grads, double scale, cudaStream_t stream,
                             long long* cursor, long long batch, long long n_samples, const double* stats, double* stats_ring,
-                            bool already_pushed) {
+                            bool already_pushed, bool pipe) {
     if (!st.connected) return fail(RCN_ERR_STATE, "data-parallel group is not connected");
     if (st.n == 0) return RCN_OK;
     DpPeers pp{};
@@ -165,7 +166,7 @@ int launch_dp_allreduce_sgd(const DpState& st, double* params, double* grads, do
 #define RCN_DP_LAUNCH(W)                                                                                                       \
     RCN_LAUNCH("dp_allreduce_sgd_kernel", stream,                                                                              \
                dp_allreduce_sgd_kernel<W><<<grid, 256, 0, stream>>>(pp, st.world, st.rank, st.n, params, grads, scale, cursor, \
-                                                                   batch, n_samples, stats, stats_ring, already_pushed ? 1 : 0))
+                                                                   batch, n_samples, stats, stats_ring, already_pushed ? 1 : 0, pipe ? 1 : 0))
     switch (st.world) {
         case 2: RCN_DP_LAUNCH(2); break;
         case 4: RCN_DP_LAUNCH(4); break;

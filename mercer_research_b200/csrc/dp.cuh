@@ -89,6 +89,6 @@ void dp_release(DpState& st);
 // already_pushed: the gradient kernel pushed this step's values itself (DpPush); the kernel then only receives.
 int launch_dp_allreduce_sgd(const DpState& st, double* params, double* grads, double scale, cudaStream_t stream,
                             long long* cursor, long long batch, long long n_samples, const double* stats = nullptr,
-                            double* stats_ring = nullptr, bool already_pushed = false);
+                            double* stats_ring = nullptr, bool already_pushed = false, bool pipe = false);
 
 }  // namespace rcn

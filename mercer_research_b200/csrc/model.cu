@@ -142,7 +142,11 @@ struct rcn_cuda_model {
     const int64_t* ep_perm = nullptr;
     int ep_fmt = 0;
     size_t ep_n = 0, ep_H = 0, ep_W = 0, ep_B = 0;
-    DevBuf ep_state;            // [cursor (int64) | pad | labels_batch (B x int64)]
+    DevBuf ep_state;            // kEpSlots int64 state words (features.cuh: cursor, steps, feature cursor, ...) | labels_batch [2][B]
+    DevBuf ep_feats;            // pipelined epoch mode: [2][L x B] feature double buffer (never used as scratch by other calls)
+    bool pipe_step = false;     // the accumulate in flight is a pipelined epoch step (kernel B gets the state block)
+    bool ep_pipe = false;       // pipelined epoch mode: the feature kernel of step k+1 runs beside step k (double-buffered feats)
+    cudaEvent_t ep_fork = nullptr, ep_join = nullptr;
     size_t last_B = 0;          // batch of the last accumulate call (taps)
     bool stats_valid = false;
     // data-parallel group (dp.cu) and the pipelined host-dataset loop (rcn_cuda_train_epoch_host)
@@ -298,7 +302,8 @@ int accumulate_dev(rcn_cuda_model* h, const double* feats, const double* onehot,
         RCN_TRY(launch_smallnet_backprop(h->small_desc, h->params.as<double>(), const_cast<double*>(feats), B, onehot,
                                          labels, h->acts.as<double>(), h->deltas.as<double>(), h->grads,
                                          h->small.as<double>(), h->gemm_ws, front, h->stream, fuse_push ? &push : nullptr,
-                                         (upd.params && (!h->dp.connected || fuse_push)) ? &upd : nullptr));
+                                         (upd.params && (!h->dp.connected || fuse_push)) ? &upd : nullptr,
+                                         h->pipe_step ? h->ep_state.as<long long>() : nullptr, h->pipe_step ? h->ep_fork : nullptr));
         h->upd_fused = upd.params && (!h->dp.connected || fuse_push);
         h->dp_pushed = fuse_push && !h->upd_fused;   // pushed but not yet received: the exchange kernel must follow
         h->stats_valid = true;
@@ -428,9 +433,11 @@ int rcn_cuda_destroy(rcn_cuda_handle h) {
     if (h->stats_host) cudaFreeHost(h->stats_host);
     if (h->hs_graph) cudaGraphExecDestroy(h->hs_graph);
     if (h->hs_graph1) cudaGraphExecDestroy(h->hs_graph1);
+    if (h->ep_fork) cudaEventDestroy(h->ep_fork);
+    if (h->ep_join) cudaEventDestroy(h->ep_join);
     if (h->hs_fork) cudaEventDestroy(h->hs_fork);
     if (h->hs_join) cudaEventDestroy(h->hs_join);
-    h->hs_ring.release(); h->hs_state.release(); h->persist_ws.release();
+    h->hs_ring.release(); h->hs_state.release(); h->persist_ws.release(); h->ep_feats.release();
     dp_release(h->dp);
     h->oz.release();
     DevBuf* bufs[] = {&h->params, &h->grads_own, &h->in_stage, &h->tgt_stage, &h->feats, &h->acts, &h->deltas,
@@ -613,9 +620,13 @@ int rcn_cuda_get_params(rcn_cuda_handle h, double* flat, size_t n) {
     return deliver(h, flat, h->params.p, n * sizeof(double));
 }
 
+static int epoch_reprime(rcn_cuda_model* h);   // pipelined epoch mode: prefetched features depend on (mean, sd)
+
 int rcn_cuda_set_scale(rcn_cuda_handle h, double mean, double sd) {
     RCN_ENTER(h);
+    const bool changed = mean != h->mean || sd != h->sd;
     h->mean = mean; h->sd = sd;
+    if (changed && h->ep_pipe && h->ep_images) return epoch_reprime(h);
     return RCN_OK;
 }
 
@@ -652,9 +663,11 @@ int rcn_cuda_gen_scales(rcn_cuda_handle h, const double* feats, size_t L, size_t
     double host[2];
     RCN_CUDA_TRY(cudaMemcpyAsync(host, res, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
     RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const bool changed = host[0] != h->mean || host[1] != h->sd;
     h->mean = host[0]; h->sd = host[1];  // self.scale_set = (mean, sd)  (rcn.rs:249-250)
     if (mean) *mean = host[0];
     if (sd) *sd = host[1];
+    if (changed && h->ep_pipe && h->ep_images) return epoch_reprime(h);
     return RCN_OK;
 }
 
@@ -809,6 +822,7 @@ static void arm_fused_update(rcn_cuda_model* h, double scale, long long* cursor,
     h->pending_upd.batch = batch;
     h->pending_upd.n_samples = n_samples;
     h->pending_upd.stats_ring = stats_ring;
+    h->pending_upd.pipe = (cursor && cursor == h->ep_state.as<long long>() && h->ep_pipe) ? 1 : 0;
 }
 static bool take_upd_fused(rcn_cuda_model* h) {
     const bool f = h->upd_fused;
@@ -849,6 +863,59 @@ int rcn_cuda_last_batch_stats(rcn_cuda_handle h, double* cost, uint64_t* hits) {
     return RCN_OK;
 }
 
+// ---- pipelined epoch mode ---------------------------------------------------------------------------------------------
+// The convpool front end of a step does not depend on the parameters, only on which images come next.  With a bound
+// device dataset, the canonical narrow network and u8 images the feature kernel of step k+1 therefore runs on a PARALLEL
+// branch (own stream, own device-side cursor) while kernels A and B of step k train; kernel A drops its front end and
+// reads the features / labels of its step from the half of a double buffer selected by a device-side step counter
+// (the branch forks after kernel A, so the feature kernel shares the machine with kernel B's small CTAs).  The
+// invariant "half (steps done & 1) holds the features of the batch at the cursor" is (re-)established by epoch_prime
+// after every bind / seek / scale change, so eager calls and replayed CUDA graphs of any length can be mixed freely.
+static bool epoch_pipe_eligible(rcn_cuda_model* h) {
+    // Opt-in (RCN_CUDA_EPOCH_PIPELINE=1, read at every bind): measured on c2 the cross-stream fork / join inside the step graph
+    // and the contention for SMs cost more than the hidden front end saves (26.2 us/step with the feature kernel beside
+    // kernel A, 26.9 us beside kernel B only, against 20.5 us for the fused kernel A).
+    const char* env = getenv("RCN_CUDA_EPOCH_PIPELINE");
+    const bool on = env && env[0] == '1';
+    const char* staged = getenv("RCN_CUDA_FEATURES_STAGED");
+    if (!on || (staged && staged[0] == '0') || !h->use_small || h->ep_fmt != RCN_PIXELS_U8_ROWMAJOR || h->plan.L == 0 || h->plan.n_conv > 10) return false;
+    if (h->ep_B > smallnet_max_batch() || (reinterpret_cast<uintptr_t>(h->ep_images) & 15) != 0 || (h->ep_H * h->ep_W) % 16 != 0) return false;
+    CpPlan cp;
+    return make_cp_plan(h->plan, h->ep_H, h->ep_W, &cp);   // the staged feature kernel implements the pipe protocol
+}
+
+static BatchIndex epoch_pipe_index(rcn_cuda_model* h) {
+    BatchIndex bi;
+    bi.cursor = h->ep_state.as<long long>() + kEpFpos;
+    bi.perm = (const long long*)h->ep_perm;
+    bi.labels_all = (const long long*)h->ep_labels;
+    bi.labels_batch = h->ep_state.as<long long>() + kEpSlots;
+    bi.pipe = h->ep_state.as<long long>();
+    bi.batch = (long long)h->ep_B;
+    bi.n_samples = (long long)h->ep_n;
+    return bi;
+}
+
+// state <- {cursor = pos, 0 steps done, feature cursor = pos, 0 feature steps}; then one feature launch on the model's
+// stream fills half 0 and moves the feature cursor one chunk ahead
+static int epoch_prime(rcn_cuda_model* h, long long pos) {
+    long long init[kEpSlots] = {};
+    init[kEpCursor] = pos;
+    init[kEpFpos] = pos;
+    RCN_CUDA_TRY(cudaMemcpyAsync(h->ep_state.p, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+    RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));   // `init` lives on this stack frame
+    const BatchIndex bi = epoch_pipe_index(h);
+    return launch_features(h->plan, h->ep_images, h->ep_fmt, h->ep_B, h->ep_H, h->ep_W, true, h->mean, h->sd, h->ep_feats.as<double>(),
+                           h->fscratch, h->stream, &bi);
+}
+
+static int epoch_reprime(rcn_cuda_model* h) {
+    long long pos = 0;
+    RCN_CUDA_TRY(cudaMemcpyAsync(&pos, h->ep_state.p, sizeof(pos), cudaMemcpyDeviceToHost, h->stream));
+    RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return epoch_prime(h, pos);
+}
+
 int rcn_cuda_epoch_bind(rcn_cuda_handle h, const void* images, int pixel_format, const int64_t* labels,
                         const int64_t* perm, size_t n_samples, size_t H, size_t W, size_t B) {
     RCN_ENTER(h);
@@ -860,11 +927,16 @@ int rcn_cuda_epoch_bind(rcn_cuda_handle h, const void* images, int pixel_format,
         return fail(RCN_ERR_INVALID, "unknown pixel format %d", pixel_format);
     RCN_TRY(ensure_plan(h, H, W));
     RCN_TRY(check_feature_width(h, h->plan.L));
-    RCN_TRY(h->ep_state.reserve((2 + B) * sizeof(int64_t)));
-    RCN_CUDA_TRY(cudaMemsetAsync(h->ep_state.p, 0, (2 + B) * sizeof(int64_t), h->stream));
+    RCN_TRY(h->ep_state.reserve((kEpSlots + 2 * B) * sizeof(int64_t)));
+    RCN_CUDA_TRY(cudaMemsetAsync(h->ep_state.p, 0, (kEpSlots + 2 * B) * sizeof(int64_t), h->stream));
     RCN_TRY(h->feats.reserve(h->plan.L * B * sizeof(double)));
     h->ep_images = images; h->ep_labels = labels; h->ep_perm = perm; h->ep_fmt = pixel_format;
     h->ep_n = n_samples; h->ep_H = H; h->ep_W = W; h->ep_B = B;
+    h->ep_pipe = epoch_pipe_eligible(h);
+    if (h->ep_pipe) {
+        RCN_TRY(h->ep_feats.reserve(2 * h->plan.L * B * sizeof(double)));
+        RCN_TRY(epoch_prime(h, 0));
+    }
     return RCN_OK;
 }
 
@@ -873,6 +945,7 @@ int rcn_cuda_epoch_seek(rcn_cuda_handle h, size_t position) {
     if (!h->ep_images) return fail(RCN_ERR_STATE, "no dataset bound: call rcn_cuda_epoch_bind first");
     if (position + h->ep_B > h->ep_n) return fail(RCN_ERR_INVALID, "position %zu leaves fewer than B samples", position);
     const long long pos = (long long)position;
+    if (h->ep_pipe) return epoch_prime(h, pos);   // also recomputes the prefetched features (new perm / position)
     RCN_CUDA_TRY(cudaMemcpyAsync(h->ep_state.p, &pos, sizeof(pos), cudaMemcpyHostToDevice, h->stream));
     RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
     return RCN_OK;
@@ -892,11 +965,36 @@ int rcn_cuda_epoch_accumulate(rcn_cuda_handle h) {
     RCN_ENTER(h);
     RCN_TRY(require_params(h));
     if (!h->ep_images) return fail(RCN_ERR_STATE, "no dataset bound: call rcn_cuda_epoch_bind first");
+    if (h->ep_pipe) {
+        // fork: the feature kernel of the NEXT step on a parallel branch (own cursor, other half of the double buffer)
+        if (!h->copy_stream) RCN_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        if (!h->ep_fork) {
+            RCN_CUDA_TRY(cudaEventCreateWithFlags(&h->ep_fork, cudaEventDisableTiming));
+            RCN_CUDA_TRY(cudaEventCreateWithFlags(&h->ep_join, cudaEventDisableTiming));
+        }
+        // this step: kernels A (no front end) and B on the half the step counter selects; ep_fork is recorded between them
+        SmallNetFront fr{};
+        fr.pipe_only = 1;
+        fr.bi.pipe = h->ep_state.as<long long>();
+        h->pipe_step = true;
+        const int rc = accumulate_dev(h, h->ep_feats.as<double>(), nullptr, nullptr, h->ep_B, &fr);
+        h->pipe_step = false;
+        RCN_TRY(rc);
+        // fork after kernel A: the feature kernel of the NEXT step shares the machine with kernel B (small CTAs on both sides;
+        // beside kernel A, whose CTAs need a whole SM each, it was measured to delay the step instead)
+        RCN_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ep_fork, 0));
+        const BatchIndex fbi = epoch_pipe_index(h);
+        RCN_TRY(launch_features(h->plan, h->ep_images, h->ep_fmt, h->ep_B, h->ep_H, h->ep_W, true, h->mean, h->sd,
+                                h->ep_feats.as<double>(), h->fscratch, h->copy_stream, &fbi));
+        RCN_CUDA_TRY(cudaEventRecord(h->ep_join, h->copy_stream));
+        RCN_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ep_join, 0));   // join: the next step's kernel A needs those features
+        return RCN_OK;
+    }
     BatchIndex bi;
     bi.cursor = h->ep_state.as<long long>();
     bi.perm = (const long long*)h->ep_perm;
     bi.labels_all = (const long long*)h->ep_labels;
-    bi.labels_batch = h->ep_state.as<long long>() + 2;
+    bi.labels_batch = h->ep_state.as<long long>() + kEpSlots;
     return accumulate_images_dev(h, h->ep_images, h->ep_fmt, nullptr, h->ep_B, h->ep_H, h->ep_W, &bi);
 }
 
@@ -908,9 +1006,9 @@ int rcn_cuda_epoch_apply(rcn_cuda_handle h, double eta, size_t global_batch) {
     const double scale = eta / (double)global_batch;
     if (h->dp.connected)
         return launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale, h->stream, h->ep_state.as<long long>(),
-                                       (long long)h->ep_B, (long long)h->ep_n, nullptr, nullptr, take_dp_pushed(h));
+                                       (long long)h->ep_B, (long long)h->ep_n, nullptr, nullptr, take_dp_pushed(h), h->ep_pipe);
     return launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale, h->stream, h->ep_state.as<long long>(),
-                             (long long)h->ep_B, (long long)h->ep_n);
+                             (long long)h->ep_B, (long long)h->ep_n, nullptr, nullptr, h->ep_pipe);
 }
 
 int rcn_cuda_epoch_step(rcn_cuda_handle h, double eta) {
@@ -930,7 +1028,7 @@ int rcn_cuda_epoch_run(rcn_cuda_handle h, double eta, size_t n_steps) {
     if (n_steps == 0) return RCN_OK;
     if (n_steps > (size_t)1 << 30) return fail(RCN_ERR_INVALID, "too many steps in one call");
     const size_t B = h->ep_B;
-    if (h->use_small && !h->dp.connected && !h->persist_failed && h->ep_fmt == RCN_PIXELS_U8_ROWMAJOR && h->plan.L > 0 &&
+    if (h->use_small && !h->ep_pipe && !h->dp.connected && !h->persist_failed && h->ep_fmt == RCN_PIXELS_U8_ROWMAJOR && h->plan.L > 0 &&
         h->plan.n_conv <= 10 && B <= smallnet_max_batch()) {
         if (h->dp_pushed) return fail(RCN_ERR_STATE, "data-parallel group: pushed gradients were never applied");
         SmallNetFront fr{};
@@ -942,7 +1040,7 @@ int rcn_cuda_epoch_run(rcn_cuda_handle h, double eta, size_t n_steps) {
         fr.bi.cursor = h->ep_state.as<long long>();
         fr.bi.perm = (const long long*)h->ep_perm;
         fr.bi.labels_all = (const long long*)h->ep_labels;
-        fr.bi.labels_batch = h->ep_state.as<long long>() + 2;
+        fr.bi.labels_batch = h->ep_state.as<long long>() + kEpSlots;
         smallnet_front_select(h->plan, &fr);
         if (smallnet_persistent_eligible(h->small_desc, fr, B)) {
             RCN_TRY(h->feats.reserve(h->plan.L * B * sizeof(double)));
@@ -992,8 +1090,8 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
     RCN_TRY(check_feature_width(h, h->plan.L));
     if (global_batch == 0) global_batch = B * (size_t)(h->dp.connected ? h->dp.world : 1);
     const size_t img_bytes = B * H * W * pixel_bytes(pixel_format);
-    if (!h->copy_stream) {
-        RCN_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->copy_stream) RCN_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->hs_fork) {   // (the stream may already exist: the pipelined epoch mode shares it)
         for (int i = 0; i < 2; ++i) {
             RCN_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
             RCN_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming));

@@ -120,6 +120,12 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
     __shared__ unsigned long long s_hit[SN_TB];
     __shared__ long long s_label[SN_TB];
 
+    if (FUSED == 0 && fr.pipe_only) {   // pipelined epoch mode: this step's half of the feature / label double buffer
+        const long long par = __ldcg(fr.bi.pipe + kEpAstep) & 1;
+        feats += (size_t)par * (size_t)B * d.n_in;
+        labels = reinterpret_cast<const int64_t*>(fr.bi.pipe + kEpSlots + par * (long long)B);
+        if (tile_idx == 0 && threadIdx.x == 0) fr.bi.pipe[kEpCurPar] = par;   // kernel B reads the same half
+    }
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int s0 = tile_idx * SN_TB;
@@ -532,7 +538,8 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
                                            const double* __restrict__ stats_partial, int n_stat, double* __restrict__ stats,
                                            const DpPush& dp, const SnUpdate& upd, const int cg_idx, const int rank, const int S,
                                            double* sP, double* sD /* [2][64 * SN_DPITCH]: double-buffered 64-sample delta_0 chunk */,
-                                           const unsigned total_ctas) {
+                                           const unsigned total_ctas, const long long* pipe) {
+    if (pipe) feats += (size_t)__ldcg(pipe + kEpCurPar) * (size_t)B * d.n_in;   // the half kernel A used (pipelined epoch mode)
     constexpr bool DP = MODE == 1 || MODE == 3;
     constexpr bool UPD = MODE == 2 || MODE == 3;
     constexpr bool DPX = MODE == 3;
@@ -694,6 +701,7 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
                 long long cur = cur0 + upd.batch;   // next chunk of chunks_exact(batch) (rcn.rs:147), remainder dropped
                 if (cur + upd.batch > upd.n_samples) cur = 0;
                 *upd.cursor = cur;
+                if (upd.pipe) upd.cursor[kEpAstep] += 1;
             }
         }
     }
@@ -710,14 +718,14 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
                                                                      int col_groups, double* __restrict__ grads,
                                                                      const double* __restrict__ stats_partial, int n_stat,
                                                                      double* __restrict__ stats, const __grid_constant__ DpPush dp,
-                                                                     const __grid_constant__ SnUpdate upd) {
+                                                                     const __grid_constant__ SnUpdate upd, const long long* __restrict__ pipe) {
     extern __shared__ __align__(16) double sP_dyn[];          // partial tile: SNB_TILE (col CTAs) or n_small doubles
     __shared__ __align__(16) double sD_static[2 * 64 * SN_DPITCH];   // 36 KB
     // grid (col_groups + 1, S) in clusters of (1, S, 1): blockIdx.y == cluster.block_rank()
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     sn_phase_b<MODE, false, 64>(d, feats, small_partial, deltas, B, ksplit, col_groups, grads, stats_partial, n_stat, stats, dp, upd,
-                            (int)blockIdx.x, (int)blockIdx.y, (int)gridDim.y, sP_dyn, sD_static, gridDim.x * gridDim.y);
+                            (int)blockIdx.x, (int)blockIdx.y, (int)gridDim.y, sP_dyn, sD_static, gridDim.x * gridDim.y, pipe);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -777,7 +785,7 @@ smallnet_persistent_kernel(const __grid_constant__ SmallNetDesc d, double* __res
         if (cid <= col_groups)
             sn_phase_b<2, true, 32>(d, feats, small_partial, deltas, B, ksplit, col_groups, grads, stats_partial, n_tiles, stats, nodp,
                                 upd, cid, rank, SNP_CLUSTER, reinterpret_cast<double*>(sn_smem),
-                                reinterpret_cast<double*>(sn_smem) + SNA_WARPS * SN_TB * SN_ZPITCH, 0u);   // sP | sD alias phase A's buffers
+                                reinterpret_cast<double*>(sn_smem) + SNA_WARPS * SN_TB * SN_ZPITCH, 0u, nullptr);   // sP | sD alias phase A's buffers
         SNP_STAMP(3);
         if (step + 1 < n_steps) {
             arrivals += gridDim.x;
@@ -817,6 +825,14 @@ static bool sn_pdl_enabled() {
     return on;
 }
 
+// Highest launch priority for the training kernels: when the pipelined epoch mode runs the next step's feature kernel on
+// a parallel branch, pending CTAs of kernels A / B must win the SMs (kernel A needs a whole SM per CTA), the feature
+// kernel fills what is left.
+static int sn_high_priority() {
+    static const int prio = []() { int least = 0, greatest = 0; if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { cudaGetLastError(); return 0; } return greatest; }();
+    return prio;
+}
+
 static size_t kernel_a_smem(const SmallNetDesc& d, const SmallNetFront* fr) {
     size_t bytes = ((size_t)SNA_WARPS * SN_TB * SN_ZPITCH + SN_MAX_SMALL) * sizeof(double);
     if (fr) {
@@ -840,7 +856,7 @@ static int launch_kernel_a(const SmallNetDesc& d, const double* params, double* 
                            const int64_t* labels, double* acts, double* deltas, double* stats_partial,
                            double* small_partial, int backward, const SmallNetFront* fr, cudaStream_t stream) {
     const unsigned n_tiles = cdiv(B, SN_TB);
-    const size_t smem = kernel_a_smem(d, fr);
+    const size_t smem = kernel_a_smem(d, (fr && fr->pipe_only) ? nullptr : fr);
     static SmallNetFront empty_front{};
     const int Bi = (int)B;
     auto launch = [&](auto kern, SmemAttrCache& attr, const char* name, const SmallNetFront& front) -> int {
@@ -850,15 +866,19 @@ static int launch_kernel_a(const SmallNetDesc& d, const double* params, double* 
         cfg.blockDim = dim3(SNA_THREADS, 1, 1);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributePriority;
+        at[0].val.priority = sn_high_priority();
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at;
-        cfg.numAttrs = sn_pdl_enabled() ? 1 : 0;
+        cfg.numAttrs = sn_pdl_enabled() ? 2 : 1;
         RCN_LAUNCH(name, stream, cudaLaunchKernelEx(&cfg, kern, d, params, feats, Bi, onehot, labels, acts, deltas, stats_partial,
                                                     small_partial, backward, front));
         return RCN_OK;
     };
+    const SmallNetFront* pipe_front = (fr && fr->pipe_only) ? fr : nullptr;
+    if (pipe_front) fr = nullptr;   // no front end inside the kernel
     if (fr && fr->use_cp) {
         static SmemAttrCache attr;
         RCN_TRY(launch(smallnet_fwd_bwd_kernel<2>, attr, "smallnet_fwd_bwd_kernel(fused features)", *fr));
@@ -867,7 +887,7 @@ static int launch_kernel_a(const SmallNetDesc& d, const double* params, double* 
         RCN_TRY(launch(smallnet_fwd_bwd_kernel<1>, attr, "smallnet_fwd_bwd_kernel(fused features)", *fr));
     } else {
         static SmemAttrCache attr;
-        RCN_TRY(launch(smallnet_fwd_bwd_kernel<0>, attr, "smallnet_fwd_bwd_kernel", empty_front));
+        RCN_TRY(launch(smallnet_fwd_bwd_kernel<0>, attr, "smallnet_fwd_bwd_kernel", pipe_front ? *pipe_front : empty_front));
     }
     return RCN_OK;
 }
@@ -881,7 +901,7 @@ int launch_smallnet_forward(const SmallNetDesc& d, const double* params, double*
 int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double* feats, size_t B, const double* onehot,
                              const int64_t* labels, double* acts, double* deltas, double* grads, double* stats,
                              DevBuf& workspace, const SmallNetFront* front, cudaStream_t stream, const DpPush* dp_push,
-                             const SnUpdate* update) {
+                             const SnUpdate* update, const long long* pipe, cudaEvent_t after_a) {
     if (B == 0) return RCN_OK;
     if (B > smallnet_max_batch()) return fail(RCN_ERR_INVALID, "batch too large for the fused small-network path");
     int splits, ksplit;
@@ -894,6 +914,7 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
     double* stats_partial = workspace.as<double>();
     double* small_partial = stats_partial + 2 * (size_t)n_tiles;
     RCN_TRY(launch_kernel_a(d, params, feats, B, onehot, labels, acts, deltas, stats_partial, small_partial, 1, front, stream));
+    if (after_a) RCN_CUDA_TRY(cudaEventRecord(after_a, stream));   // a parallel branch may start once kernel A is done
 
     const size_t smem_b = (size_t)(n_small > SNB_TILE ? n_small : SNB_TILE) * sizeof(double);
     DpPush push{};
@@ -916,20 +937,22 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
     cfg.blockDim = dim3(SNB_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem_b;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[3];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = splits;
     attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributePriority;
+    attr[1].val.priority = sn_high_priority();
+    attr[2].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[2].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = sn_pdl_enabled() ? 2 : 1;
+    cfg.numAttrs = sn_pdl_enabled() ? 3 : 2;
     const int Bi = (int)B;
     auto kern = mode == 1 ? smallnet_wgrad_kernel<1> : mode == 2 ? smallnet_wgrad_kernel<2> : mode == 3 ? smallnet_wgrad_kernel<3> : smallnet_wgrad_kernel<0>;
     RCN_LAUNCH(mode == 2 ? "smallnet_wgrad_kernel(+SGD update)" : mode == 3 ? "smallnet_wgrad_kernel(+exchange+SGD update)" : "smallnet_wgrad_kernel", stream,
                cudaLaunchKernelEx(&cfg, kern, d, (const double*)feats, (const double*)small_partial, (const double*)deltas, Bi,
-                                  ksplit, col_groups, grads, (const double*)stats_partial, n_tiles, stats, push, upd));
+                                  ksplit, col_groups, grads, (const double*)stats_partial, n_tiles, stats, push, upd, pipe));
     return RCN_OK;
 }
 

@@ -26,6 +26,8 @@ struct SmallNetFront {
     StageList stages;
     Standardise sc;
     BatchIndex bi;
+    int pipe_only;                     // no front end in the kernel: the features / labels come from the pipelined epoch
+                                       // mode's double buffer (bi.pipe = epoch state block, half = pipe[kEpAstep] & 1)
     int use_cp;                        // staged front end (bulk-async image loads, zero-framed tiles): see CpPlan
     CpPlan cp;
 };
@@ -41,6 +43,7 @@ struct SnUpdate {
     long long* cursor;       // optional epoch cursor, advanced by `batch` with chunks_exact wrap-around
     long long batch, n_samples;
     double* stats_ring;      // optional (pinned host) {cost, hits} per step
+    int pipe;                // pipelined epoch mode: also count the step (cursor[kEpAstep]++)
 };
 
 bool smallnet_eligible(const SmallNetDesc& d);
@@ -56,7 +59,8 @@ int launch_smallnet_forward(const SmallNetDesc& d, const double* params, double*
 int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double* feats, size_t B, const double* onehot,
                              const int64_t* labels, double* acts, double* deltas, double* grads, double* stats,
                              DevBuf& workspace, const SmallNetFront* front, cudaStream_t stream,
-                             const DpPush* dp_push = nullptr, const SnUpdate* update = nullptr);
+                             const DpPush* dp_push = nullptr, const SnUpdate* update = nullptr,
+                             const long long* pipe = nullptr, cudaEvent_t after_a = nullptr /* recorded between kernels A and B */);
 
 // n_steps consecutive single-GPU steps (kernel A, kernel B + SGD update, epoch cursor) as ONE persistent cooperative launch
 // with grid-wide barriers instead of kernel boundaries; `update` must carry params / scale (and the cursor in epoch mode).

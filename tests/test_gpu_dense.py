@@ -393,6 +393,61 @@ def test_epoch_run_persistent_kernel_equals_steps(api, monkeypatch, B, N, n_step
     assert_close(run.get_params(), p, rtol=1e-9, what="params vs oracle epoch loop")
 
 
+def test_epoch_pipeline_opt_in_equals_fused_steps(api, monkeypatch):
+    """RCN_CUDA_EPOCH_PIPELINE=1: the feature kernel of step k+1 runs on a parallel branch while step k trains (double-
+    buffered features, device-side cursors / step parity).  Same arithmetic as the fused kernel A, so parameters are
+    BIT-identical -- across the wrap-around, a mid-epoch seek, a scale change, an interleaved classify call (which must
+    not disturb the prefetched half) and a replayed CUDA graph with an odd number of steps."""
+    import torch
+    rng = np.random.default_rng(99)
+    N, B = 3000, 512
+    imgs = rng.integers(0, 256, size=(N, 28, 28), dtype=np.uint8)
+    labels = rng.integers(0, 10, N).astype(np.int64)
+    perm = rng.permutation(N).astype(np.int64)
+    cfg = [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max)]
+    d_imgs, d_labels, d_perm = torch.from_numpy(imgs).cuda(), torch.from_numpy(labels).cuda(), torch.from_numpy(perm).cuda()
+
+    def run(pipelined):
+        if pipelined:
+            monkeypatch.setenv("RCN_CUDA_EPOCH_PIPELINE", "1")
+        else:
+            monkeypatch.delenv("RCN_CUDA_EPOCH_PIPELINE", raising=False)
+        m = api.RCN(10, cfg, [30])
+        m.scale_set = (20.0, 35.0)
+        m.load_weights_and_bias(784)
+        m.set_params(np.random.default_rng(3).standard_normal(m.n_params) * 0.05)
+        m.epoch_bind(d_imgs, d_labels, B, perm=d_perm)
+        for _ in range(7):                       # 5 chunks per epoch: wraps
+            m.epoch_step(3.0)
+        m.classify_images(imgs[:300])            # uses the model's scratch feature buffer
+        m.epoch_step(3.0)
+        m.epoch_seek(2 * B)
+        m.epoch_step(3.0)
+        m.scale_set = (21.0, 34.0)               # prefetched features depend on the scale
+        m.epoch_step(3.0)
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            m.set_stream(side.cuda_stream)
+            m.epoch_step(3.0)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            m.set_stream(torch.cuda.current_stream().cuda_stream)
+            for _ in range(3):
+                m.epoch_step(3.0)
+        g.replay(); g.replay()
+        torch.cuda.synchronize()
+        m.set_stream(torch.cuda.current_stream().cuda_stream)
+        return m.get_params(), m.epoch_position(), m.last_batch_stats()
+
+    p_ref, pos_ref, st_ref = run(False)
+    p_pipe, pos_pipe, st_pipe = run(True)
+    assert pos_pipe == pos_ref and st_pipe == st_ref
+    assert np.array_equal(p_pipe.view(np.uint64), p_ref.view(np.uint64))
+
+
 def test_train_epoch_host_equals_step_by_step(api):
     """The pipelined host-dataset loop (double-buffered H2D on a copy stream) == train_batch_images chunk by chunk,
     remainder dropped like chunks_exact (rcn.rs:147-149); per-step (cost, hits) equal last_batch_stats."""
