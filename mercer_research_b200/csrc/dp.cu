@@ -24,6 +24,8 @@
 // buffers (e.g. the 268 MB of the 4096-wide MLP) are bandwidth-bound and stay on NCCL (trainer.py picks by size).
 #include "dp.cuh"
 
+#include <cstdlib>
+
 namespace rcn {
 
 constexpr size_t kDpCtrlBytes = 256;
@@ -82,6 +84,10 @@ __global__ void __launch_bounds__(256) dp_allreduce_sgd_kernel(const DpPeers pee
                                                                double scale, long long* __restrict__ cursor, long long batch,
                                                                long long n_samples, const double* __restrict__ stats,
                                                                double* __restrict__ stats_ring, int already_pushed, int pipe) {
+    // programmatic dependent launch (no-ops unless the host asked for it): the next kernel's launch may proceed under this
+    // one; this one waits for the gradient kernel to complete before it touches global memory
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int world = WORLD ? WORLD : world_rt;
     char* self = peers.p[rank];
     DpCtrl* ctrl = reinterpret_cast<DpCtrl*>(self);
@@ -163,10 +169,22 @@ int launch_dp_allreduce_sgd(const DpState& st, double* params, double* grads, do
     DpPeers pp{};
     for (int q = 0; q < st.world; ++q) pp.p[q] = (char*)st.peers[q];
     const unsigned grid = (unsigned)st.n_chunks;
+    static const bool pdl = []() { const char* e = getenv("RCN_CUDA_PDL"); return !(e && e[0] == '0'); }();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const int world_i = st.world, rank_i = st.rank, pushed_i = already_pushed ? 1 : 0, pipe_i = pipe ? 1 : 0;
+    const size_t n_i = st.n;
 #define RCN_DP_LAUNCH(W)                                                                                                       \
     RCN_LAUNCH("dp_allreduce_sgd_kernel", stream,                                                                              \
-               dp_allreduce_sgd_kernel<W><<<grid, 256, 0, stream>>>(pp, st.world, st.rank, st.n, params, grads, scale, cursor, \
-                                                                   batch, n_samples, stats, stats_ring, already_pushed ? 1 : 0, pipe ? 1 : 0))
+               cudaLaunchKernelEx(&cfg, dp_allreduce_sgd_kernel<W>, pp, world_i, rank_i, n_i, params, grads, scale, cursor, batch, \
+                                  n_samples, stats, stats_ring, pushed_i, pipe_i))
     switch (st.world) {
         case 2: RCN_DP_LAUNCH(2); break;
         case 4: RCN_DP_LAUNCH(4); break;
