@@ -75,6 +75,11 @@ static int hs_steps_per_graph() {
     static const int v = []() { const char* e = getenv("RCN_CUDA_HOST_STEPS_PER_GRAPH"); int n = e ? atoi(e) : 2; return n < 1 ? 1 : (n > 64 ? 64 : n); }();
     return v;
 }
+// PCIe pulls are latency-bound per request: every thread first issues ALL the 16-byte loads of its round (U independent
+// zero-copy reads in flight, the whole 0.8 MB chunk of the canonical config in one round trip) and only then stores them.
+// (Written as `d4[i] = s4[i]` the compiler must keep load/store pairs in order -- source and ring may alias as far as it
+// knows -- which leaves ONE load in flight per thread and costs a PCIe round trip per 128 KB.)
+template <int U>
 __global__ void __launch_bounds__(256) host_prefetch_kernel(long long* __restrict__ state, unsigned char* __restrict__ ring,
                                                             long long B, long long img_bytes) {
     const long long k1 = *reinterpret_cast<volatile long long*>(state + 3) + 1;
@@ -84,8 +89,16 @@ __global__ void __launch_bounds__(256) host_prefetch_kernel(long long* __restric
         const long long n16 = B * img_bytes / 16;
         const uint4* s4 = reinterpret_cast<const uint4*>(src);
         uint4* d4 = reinterpret_cast<uint4*>(dst);
-        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
-            d4[i] = s4[i];
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        for (long long base = blockIdx.x * (long long)blockDim.x + threadIdx.x; base < n16; base += stride * U) {
+            uint4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (base + u * stride < n16) v[u] = s4[base + u * stride];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (base + u * stride < n16) d4[base + u * stride] = v[u];
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {   // the last CTA to finish publishes the counter: every CTA has read it by then
@@ -94,6 +107,24 @@ __global__ void __launch_bounds__(256) host_prefetch_kernel(long long* __restric
             state[4] = 0;
             *reinterpret_cast<volatile long long*>(state + 3) = k1;
         }
+    }
+}
+// RCN_CUDA_PREFETCH_UNROLL = loads in flight per thread (1 = the load/store-paired loop, default 8);
+// RCN_CUDA_PREFETCH_CTAS = grid size (default 32: the SMs the 128-CTA step kernels leave free, and then some)
+static int prefetch_unroll() {
+    static const int v = []() { const char* e = getenv("RCN_CUDA_PREFETCH_UNROLL"); int n = e ? atoi(e) : 8; return n <= 1 ? 1 : (n <= 4 ? 4 : 8); }();
+    return v;
+}
+static int prefetch_ctas() {
+    static const int v = []() { const char* e = getenv("RCN_CUDA_PREFETCH_CTAS"); int n = e ? atoi(e) : 32; return n < 1 ? 1 : (n > 1024 ? 1024 : n); }();
+    return v;
+}
+static void launch_host_prefetch(long long* state, unsigned char* ring, long long B, long long img_bytes, cudaStream_t s) {
+    const int g = prefetch_ctas();
+    switch (prefetch_unroll()) {
+        case 1: host_prefetch_kernel<1><<<g, 256, 0, s>>>(state, ring, B, img_bytes); break;
+        case 4: host_prefetch_kernel<4><<<g, 256, 0, s>>>(state, ring, B, img_bytes); break;
+        default: host_prefetch_kernel<8><<<g, 256, 0, s>>>(state, ring, B, img_bytes); break;
     }
 }
 
@@ -1167,7 +1198,7 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
                         if (cudaEventRecord(h->hs_fork, h->stream) != cudaSuccess || cudaStreamWaitEvent(h->copy_stream, h->hs_fork, 0) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph fork failed"); break; }
                         {
                             LaunchScope ls("host_prefetch_kernel", h->copy_stream);
-                            host_prefetch_kernel<<<32, 256, 0, h->copy_stream>>>(st, h->hs_ring.as<unsigned char>(), (long long)B, (long long)(H * W));
+                            launch_host_prefetch(st, h->hs_ring.as<unsigned char>(), (long long)B, (long long)(H * W), h->copy_stream);
                         }
                         if (cudaPeekAtLastError() != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "prefetch kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
                         if (cudaEventRecord(h->hs_join, h->copy_stream) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph join failed"); break; }

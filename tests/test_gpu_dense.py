@@ -489,6 +489,34 @@ def test_train_epoch_host_equals_step_by_step(api):
         assert np.array_equal(results[0][1], other[1]) and np.array_equal(results[0][2], other[2])
 
 
+def test_train_epoch_host_streaming_large_chunks(api):
+    """Same equality at a chunk size where every prefetch thread carries several 16-byte loads and the last round is
+    ragged (B=1000: 49 000 uint4 per chunk over 8192 threads)."""
+    import torch
+    rng = np.random.default_rng(23)
+    B, N = 1000, 1000 * 4 + 123
+    images = torch.from_numpy(rng.integers(0, 256, size=(N, 28, 28), dtype=np.uint8)).pin_memory()
+    labels = torch.from_numpy(rng.integers(0, 10, size=N).astype(np.int64)).pin_memory()
+    cfg = [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max)]
+    out = []
+    for mode in ("loop", "epoch-pinned"):
+        model = api.RCN(10, cfg, [30])
+        model.load_weights_and_bias(784)
+        model.set_params(np.random.default_rng(24).standard_normal(model.n_params) * 0.1)
+        model.scale_set = (40.0, 60.0)
+        if mode == "loop":
+            stats = []
+            for k in range(N // B):
+                model.train_batch_images(images.numpy()[k * B:(k + 1) * B], labels.numpy()[k * B:(k + 1) * B], 3.0)
+                stats.append(model.last_batch_stats())
+            cost = np.array([s[0] for s in stats]); hits = np.array([s[1] for s in stats], dtype=np.uint64)
+        else:
+            cost, hits = model.train_epoch_host(images.numpy(), labels.numpy(), B, 3.0)
+        out.append((model.get_params(), cost, hits))
+    assert np.array_equal(out[0][0].view(np.uint64), out[1][0].view(np.uint64))
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+
+
 @pytest.mark.parametrize("single_call", [False, True])
 def test_dp_peer_memory_exchange_two_gpus(api, single_call):
     """Two ranks on two GPUs of this box (one process, peer access): the NVLink exchange + update -- as its own kernel
