@@ -75,6 +75,7 @@ SIGNATURES = {
     "rcn_cuda_get_activations": [_vp, _sz, _vp],
     "rcn_cuda_get_deltas": [_vp, _sz, _vp],
     "rcn_cuda_kernel_launches": [C.POINTER(C.c_uint64)],
+    "rcn_cuda_allocation_generation": [C.POINTER(C.c_uint64)],
     "rcn_cuda_profile_enable": [_i],
     "rcn_cuda_profile_report": [C.c_char_p, _sz],
     "rcn_cuda_convolve_2d": [_i, _vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _vp],
@@ -137,6 +138,14 @@ def kernel_launches() -> int:
     """Kernels launched by librcn_cuda in this process (bench.py's gpu_launches)."""
     n = C.c_uint64()
     check(load().rcn_cuda_kernel_launches(C.byref(n)))
+    return n.value
+
+
+def allocation_generation() -> int:
+    """Changes whenever the library (re)allocates one of its device buffers: a captured CUDA graph of library calls is
+    only valid while this value is the one seen at capture time."""
+    n = C.c_uint64()
+    check(load().rcn_cuda_allocation_generation(C.byref(n)))
     return n.value
 
 

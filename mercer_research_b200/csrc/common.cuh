@@ -3,6 +3,8 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -69,11 +71,19 @@ inline bool is_device_ptr(const void* p) {
 }
 
 // Grow-only device buffer: steady-state training does no allocation (CUDA-graph friendly).
+// Bumped whenever a grow-only device buffer is (re)allocated or released: anything that has baked device pointers into a
+// CUDA graph (the host-streaming step graphs, a caller's captured step) compares generations before replaying it.
+inline std::atomic<unsigned long long>& alloc_generation() {
+    static std::atomic<unsigned long long> g{1};
+    return g;
+}
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     int reserve(size_t bytes) {
         if (bytes <= cap) return RCN_OK;
+        alloc_generation().fetch_add(1, std::memory_order_relaxed);
         if (p) { cudaFree(p); p = nullptr; cap = 0; }
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
@@ -81,7 +91,7 @@ struct DevBuf {
         cap = want;
         return RCN_OK;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) { cudaFree(p); alloc_generation().fetch_add(1, std::memory_order_relaxed); } p = nullptr; cap = 0; }
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 

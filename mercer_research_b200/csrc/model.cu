@@ -201,12 +201,13 @@ struct rcn_cuda_model {
     cudaEvent_t hs_fork = nullptr, hs_join = nullptr;
     struct HsKey {
         size_t B = 0, H = 0, W = 0, n_steps = 0;
+        unsigned long long alloc_gen = 0;   // no device buffer has moved since the capture (common.cuh)
         double scale = 0.0;
         const void *labels = nullptr, *stats = nullptr, *ring = nullptr, *state = nullptr, *grads = nullptr;
         cudaStream_t stream = nullptr;
         bool dp = false;
         bool operator==(const HsKey& o) const {
-            return B == o.B && H == o.H && W == o.W && n_steps == o.n_steps && scale == o.scale && labels == o.labels &&
+            return B == o.B && H == o.H && W == o.W && n_steps == o.n_steps && alloc_gen == o.alloc_gen && scale == o.scale && labels == o.labels &&
                    stats == o.stats && ring == o.ring && state == o.state && grads == o.grads && stream == o.stream && dp == o.dp;
         }
     } hs_key;
@@ -1176,7 +1177,9 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
             RCN_CUDA_TRY(cudaMemcpyAsync(h->tgt_stage.p, labels, n_steps * B * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
             RCN_CUDA_TRY(cudaMemcpyAsync(h->hs_ring.p, images, img_bytes, cudaMemcpyHostToDevice, h->stream));
             rcn_cuda_model::HsKey key;
-            key.B = B; key.H = H; key.W = W; key.n_steps = 0; key.scale = scale_s;   // the graphs do not depend on the epoch length key.labels = h->tgt_stage.p;
+            key.B = B; key.H = H; key.W = W; key.n_steps = 0; key.scale = scale_s;   // the graphs do not depend on the epoch length
+            key.labels = h->tgt_stage.p;   // (grows with the epoch length: a longer epoch than any before re-captures)
+            key.alloc_gen = alloc_generation().load(std::memory_order_relaxed);
             key.stats = h->stats_host; key.ring = h->hs_ring.p; key.state = st; key.grads = h->grads; key.stream = h->stream;
             key.dp = h->dp.connected;
             if (!h->hs_graph || !h->hs_graph1 || !(key == h->hs_key)) {
@@ -1226,6 +1229,7 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
                 };
                 RCN_TRY(capture_steps(hs_steps_per_graph(), &h->hs_graph));
                 RCN_TRY(capture_steps(1, &h->hs_graph1));
+                key.alloc_gen = alloc_generation().load(std::memory_order_relaxed);   // the warm-up may have grown scratch buffers
                 h->hs_key = key;
             }
             {
@@ -1399,6 +1403,12 @@ int rcn_cuda_get_deltas(rcn_cuda_handle h, size_t layer, double* out) {
 int rcn_cuda_kernel_launches(uint64_t* count) {
     if (!count) return fail(RCN_ERR_INVALID, "null count");
     *count = g_launches.load();
+    return RCN_OK;
+}
+
+int rcn_cuda_allocation_generation(uint64_t* generation) {
+    if (!generation) return fail(RCN_ERR_INVALID, "null generation");
+    *generation = alloc_generation().load(std::memory_order_relaxed);
     return RCN_OK;
 }
 

@@ -545,17 +545,24 @@ class RCN:
                     self.set_stream(side.cuda_stream)
                     self.epoch_accumulate()                   # warm-up launch outside capture (allocations, attributes)
                 stream.wait_stream(side)
-                torch.cuda.synchronize(dev)
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    self.set_stream(torch.cuda.current_stream(dev).cuda_stream)
-                    self.epoch_step(eta)
-                self.set_stream(stream.cuda_stream)
+
+                def capture_step():
+                    torch.cuda.synchronize(dev)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+                        self.epoch_step(eta)
+                    self.set_stream(stream.cuda_stream)
+                    return g, _lib.allocation_generation()
+
+                graph, graph_gen = capture_step()
         for e in range(epochs):
             if n_steps:
                 perm.copy_(torch.as_tensor(rng.permutation(n)), non_blocking=False)   # training_set.shuffle (rcn.rs:146)
                 self.scale_set = tr_stats
                 self.epoch_seek(0)
+                if graph is not None and _lib.allocation_generation() != graph_gen:
+                    graph, graph_gen = capture_step()         # the evaluation below grew a library buffer: pointers moved
                 for _ in range(n_steps):                      # chunks_exact(batch_size) (rcn.rs:147-149)
                     if graph is not None:
                         graph.replay()

@@ -131,20 +131,36 @@ class DataParallelTrainer:
                 self._epoch_step_eager()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        self.steps_per_graph = max(1, int(steps_per_graph))
+        self._capture_graph()
+        self.model.epoch_seek(0)
+        return self.graph
+
+    def _capture_graph(self):
+        """Captures ``steps_per_graph`` steps without executing any (capture does not run the kernels, and the cursor and
+        the parameters live in device memory): used by capture() after its warm-up and by _replay() when a library buffer
+        has moved since (some call in between needed more scratch: the old graph holds freed pointers)."""
+        import torch
+        from . import _lib
+        torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            for _ in range(max(1, int(steps_per_graph))):
+            for _ in range(self.steps_per_graph):
                 self._epoch_step_eager()
         self.graph = graph
-        self.steps_per_graph = max(1, int(steps_per_graph))
+        self._graph_generation = _lib.allocation_generation()
         self.model.set_stream(torch.cuda.current_stream().cuda_stream)
-        self.model.epoch_seek(0)
-        return graph
+
+    def _replay(self):
+        from . import _lib
+        if _lib.allocation_generation() != self._graph_generation:
+            self._capture_graph()
+        self.graph.replay()
 
     def epoch_step(self):
         """One step (eager), or one replay of the captured graph (= ``steps_per_graph`` steps)."""
         if getattr(self, "graph", None) is not None:
-            self.graph.replay()
+            self._replay()
         else:
             self._epoch_step_eager()
 
@@ -160,7 +176,7 @@ class DataParallelTrainer:
         spg = getattr(self, "steps_per_graph", 1) if getattr(self, "graph", None) is not None else 0
         if spg:
             for _ in range(n // spg):
-                self.graph.replay()
+                self._replay()
             n -= (n // spg) * spg
         for _ in range(n):
             self._epoch_step_eager()

@@ -40,6 +40,7 @@ us = np.array([r[1] for r in rows])
 b, a = np.polyfit(ns, us, 1)
 print(json.dumps({"workload": "c2", "unroll": os.environ.get("RCN_CUDA_PREFETCH_UNROLL", "default"),
                   "ctas": os.environ.get("RCN_CUDA_PREFETCH_CTAS", "default"),
+                  "host_steps_per_graph": os.environ.get("RCN_CUDA_HOST_STEPS_PER_GRAPH", "default"),
                   "calls": [{"steps": n, "median_us": round(m, 1), "min_us": round(lo, 1), "us_per_step": round(m / n, 2)}
                             for n, m, lo in rows],
                   "fit": {"fixed_us": round(float(a), 1), "us_per_step": round(float(b), 3)}}))

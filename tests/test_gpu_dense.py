@@ -626,6 +626,68 @@ def test_train_arrays_matches_oracle_epoch_loop(api, graph):
     assert abs(gm - mte[0]) <= 1e-12 * mte[0] and abs(gs - mte[1]) <= 1e-12 * mte[1]
 
 
+def test_cached_step_graphs_survive_buffer_growth(api):
+    """Device pointers are baked into the cached step graphs (the library's host-streaming graphs, the trainer's captured
+    step). When a later call needs more scratch than any call before it (a longer epoch: the label stage grows; a bigger
+    inference batch: features / activations grow) the grow-only buffers move and the graphs must be re-captured, not
+    replayed with freed pointers. Results stay bit-identical to chunk-by-chunk training."""
+    import torch
+    from mercer_research_b200 import _lib
+    from mercer_research_b200.trainer import DataParallelTrainer
+    rng = np.random.default_rng(31)
+    B, N = 64, 64 * 40
+    images = torch.from_numpy(rng.integers(0, 256, size=(N, 28, 28), dtype=np.uint8)).pin_memory()
+    labels = torch.from_numpy(rng.integers(0, 10, size=N).astype(np.int64)).pin_memory()
+    big = rng.integers(0, 256, size=(6000, 28, 28), dtype=np.uint8)
+    cfg = [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max)]
+    hi, hl = images.numpy(), labels.numpy()
+
+    def fresh():
+        m = api.RCN(10, cfg, [30])
+        m.load_weights_and_bias(784)
+        m.set_params(np.random.default_rng(32).standard_normal(m.n_params) * 0.1)
+        m.scale_set = (40.0, 60.0)
+        return m
+
+    ref = fresh()
+    for k in range(2 + 40 + 3):                  # the three epochs below, chunk by chunk
+        j = k if k < 2 else (k - 2 if k < 42 else k - 42)
+        ref.train_batch_images(hi[j * B:(j + 1) * B], hl[j * B:(j + 1) * B], 3.0)
+        if k == 41:
+            want_pred = ref.classify_images(big)  # labels under the parameters after the first two epochs
+    want = ref.get_params()
+
+    model = fresh()
+    g0 = _lib.allocation_generation()
+    model.train_epoch_host(hi[:2 * B], hl[:2 * B], B, 3.0)        # short epoch: graphs captured, small label stage
+    assert _lib.allocation_generation() > g0
+    model.train_epoch_host(hi, hl, B, 3.0)                        # 20x longer epoch: the label stage moves
+    pred = model.classify_images(big)                             # much bigger batch: features / activations move
+    model.train_epoch_host(hi[:3 * B], hl[:3 * B], B, 3.0)
+    assert np.array_equal(model.get_params().view(np.uint64), want.view(np.uint64))
+    assert np.array_equal(pred, want_pred)
+
+    # the trainer's captured epoch step: replay, grow a buffer in between, replay again
+    d_imgs, d_labels = images.cuda(), labels.cuda()
+    ref2 = fresh()
+    for k in range(6):
+        ref2.train_batch_images(hi[k * B:(k + 1) * B], hl[k * B:(k + 1) * B], 3.0)
+    graphed = fresh()
+    tr = DataParallelTrainer(graphed, eta=3.0)
+    tr.bind_dataset(d_imgs, d_labels, B)
+    tr.capture(warmup=1, steps_per_graph=2)
+    graphed.set_params(np.random.default_rng(32).standard_normal(graphed.n_params) * 0.1)   # undo the warm-up step
+    tr.epoch_steps(2)
+    gen = tr._graph_generation
+    graphed.classify_images(torch.from_numpy(big).cuda())         # grows the model's feature / activation buffers
+    assert _lib.allocation_generation() != gen
+    tr.epoch_steps(4)
+    torch.cuda.synchronize()
+    assert tr._graph_generation == _lib.allocation_generation()   # re-captured
+    assert graphed.epoch_position() == 6 * B
+    assert np.array_equal(graphed.get_params().view(np.uint64), ref2.get_params().view(np.uint64))
+
+
 def test_train_epoch_host_contract(api):
     """Argument contract of the host-dataset loop: chunks_exact drops a short tail entirely (rcn.rs:147), device buffers are
     rejected, a wrong feature width is the reference's dimension-mismatch panic, state errors come back as status codes."""
