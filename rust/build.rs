@@ -37,5 +37,9 @@ fn main() {
     assert!(ok, "link failed");
     println!("cargo:rustc-link-search=native={}", out.display());
     println!("cargo:rustc-link-lib=dylib=rcn_cuda");
+    // src/cuda.rs binds a handful of libcudart entry points directly (device / pinned buffers)
+    let cuda_lib = env::var("CUDA_LIB_DIR").unwrap_or_else(|_| "/usr/local/cuda/lib64".into());
+    println!("cargo:rustc-link-search=native={cuda_lib}");
+    println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rerun-if-changed={}", root.join("include").join("rcn_cuda.h").display());
 }

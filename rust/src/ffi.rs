@@ -9,8 +9,13 @@ pub struct rcn_cuda_model {
 pub type rcn_cuda_handle = *mut rcn_cuda_model;
 
 pub const RCN_OK: c_int = 0;
+pub const RCN_ERR_INVALID: c_int = 1;
 pub const RCN_ERR_SHAPE: c_int = 2;
 pub const RCN_ERR_NOT_IMPLEMENTED: c_int = 3;
+pub const RCN_ERR_CUDA: c_int = 4;
+pub const RCN_ERR_STATE: c_int = 5;
+pub const RCN_ERR_OUT_OF_BOUNDS: c_int = 6;
+pub const RCN_ERR_NAN: c_int = 7;
 pub const RCN_PIXELS_U8_ROWMAJOR: c_int = 0;
 pub const RCN_PIXELS_F64_COLMAJOR: c_int = 1;
 
@@ -80,6 +85,39 @@ extern "C" {
     pub fn rcn_cuda_ext_gemm_f64(device: c_int, stream: *mut c_void, A: *const c_double, lda: usize, a_kcontig: c_int,
                                  B: *const c_double, ldb: usize, b_kcontig: c_int, M: usize, N: usize, K: usize, impl_: c_int,
                                  C: *mut c_double) -> c_int;
+    // ---- library / stream ------------------------------------------------------------------------------------------
+    pub fn rcn_cuda_version() -> c_int;
+    pub fn rcn_cuda_device_count(count: *mut c_int) -> c_int;
+    pub fn rcn_cuda_set_stream(h: rcn_cuda_handle, cuda_stream: *mut c_void) -> c_int;
+    pub fn rcn_cuda_synchronize(h: rcn_cuda_handle) -> c_int;
+    // ---- flat parameter / gradient views (serialization.rs:19-22 order) ------------------------------------------------
+    pub fn rcn_cuda_param_count(h: rcn_cuda_handle, n: *mut usize) -> c_int;
+    pub fn rcn_cuda_set_params(h: rcn_cuda_handle, flat: *const c_double, n: usize) -> c_int;
+    pub fn rcn_cuda_get_params(h: rcn_cuda_handle, flat: *mut c_double, n: usize) -> c_int;
+    pub fn rcn_cuda_bind_gradient_buffer(h: rcn_cuda_handle, device_ptr: *mut c_double, n: usize) -> c_int;
+    pub fn rcn_cuda_gradient_buffer(h: rcn_cuda_handle, device_ptr: *mut *mut c_double, n: *mut usize) -> c_int;
+    pub fn rcn_cuda_get_gradients(h: rcn_cuda_handle, flat: *mut c_double, n: usize) -> c_int;
+    pub fn rcn_cuda_get_activations(h: rcn_cuda_handle, layer: usize, out: *mut c_double) -> c_int;
+    pub fn rcn_cuda_get_deltas(h: rcn_cuda_handle, layer: usize, out: *mut c_double) -> c_int;
+    // ---- classify_test argmax / backprop sums on features (rcn.rs:92-97, 190-205) --------------------------------------
+    pub fn rcn_cuda_classify_features(h: rcn_cuda_handle, feats: *const c_double, B: usize, labels_out: *mut i64) -> c_int;
+    pub fn rcn_cuda_accumulate_gradients(h: rcn_cuda_handle, feats: *const c_double, onehot: *const c_double,
+                                         labels: *const i64, B: usize) -> c_int;
+    // ---- epoch mode: chunks_exact loop over a dataset resident in HBM (rcn.rs:144-149) --------------------------------
+    pub fn rcn_cuda_epoch_bind(h: rcn_cuda_handle, images: *const c_void, pixel_format: c_int, labels: *const i64,
+                               perm: *const i64, n_samples: usize, H: usize, W: usize, B: usize) -> c_int;
+    pub fn rcn_cuda_epoch_seek(h: rcn_cuda_handle, position: usize) -> c_int;
+    pub fn rcn_cuda_epoch_position(h: rcn_cuda_handle, position: *mut usize) -> c_int;
+    pub fn rcn_cuda_epoch_accumulate(h: rcn_cuda_handle) -> c_int;
+    pub fn rcn_cuda_epoch_apply(h: rcn_cuda_handle, eta: c_double, global_batch: usize) -> c_int;
+    pub fn rcn_cuda_epoch_step(h: rcn_cuda_handle, eta: c_double) -> c_int;
+    pub fn rcn_cuda_epoch_run(h: rcn_cuda_handle, eta: c_double, n_steps: usize) -> c_int;
+    // ---- accounting ----------------------------------------------------------------------------------------------------
+    pub fn rcn_cuda_kernel_launches(count: *mut u64) -> c_int;
+    pub fn rcn_cuda_allocation_generation(generation: *mut u64) -> c_int;
+    pub fn rcn_cuda_profile_enable(on: c_int) -> c_int;
+    pub fn rcn_cuda_profile_report(json_out: *mut c_char, capacity: usize) -> c_int;
+    // ---- op-level API: traits Convolve2D / Pool2D (kernel.rs:61-100, 219-236) ------------------------------------------
     pub fn rcn_cuda_convolve_2d(device: c_int, stream: *mut c_void, m: *const c_double, H: usize, W: usize,
                                 kernel: *const c_double, kh: usize, kw: usize, padding: c_int, out: *mut c_double) -> c_int;
     pub fn rcn_cuda_convolve_2d_separated(device: c_int, stream: *mut c_void, m: *const c_double, H: usize, W: usize,

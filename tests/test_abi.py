@@ -29,6 +29,26 @@ def test_binding_covers_header(built_library):
     assert set(_lib.SIGNATURES) | {"rcn_cuda_last_error"} == set(declared_symbols())
 
 
+def test_rust_extern_block_covers_header():
+    """rust/src/ffi.rs (the binding a maintainer adds to rcn) declares every header entry point
+    with the header's parameter count; it cannot be compiled here (no rustc), so at least keep it in step textually."""
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "rcn_cuda.h")).read(), flags=re.S)
+    rust = re.sub(r"//.*", "", open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read())
+
+    def arity(text, pattern):
+        out = {}
+        for name, args in re.findall(pattern, text, flags=re.S):
+            args = args.strip()
+            out[name] = 0 if args in ("", "void") else args.count(",") + 1
+        return out
+
+    c = arity(header, r"\b(rcn_cuda_[a-z0-9_]+)\s*\(([^)]*)\)\s*;")
+    r = arity(rust, r"pub fn (rcn_cuda_[a-z0-9_]+)\s*\(([^)]*)\)")
+    assert set(c) == set(declared_symbols())
+    assert set(r) == set(c), (sorted(set(c) - set(r)), sorted(set(r) - set(c)))
+    assert {k: v for k, v in r.items() if c[k] != v} == {}
+
+
 def test_version_and_error_string(built_library):
     assert built_library.rcn_cuda_version() >= 100
     assert isinstance(built_library.rcn_cuda_last_error(), bytes)
