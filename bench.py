@@ -549,6 +549,9 @@ def run_gpu(args, wl, rank, world, local_rank):
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps, "host_buffers": "pinned",
+                # PCIe bytes per second this rank pulled inside the timed region (the e2e path's own bound: SM-issued
+                # zero-copy reads reach ~38 GB/s on this pool's boxes, profiles/r1s_full_host_prefetch.txt)
+                "h2d_GBps_per_gpu": h2d / (e2e_ms / args.steps * 1e-3) * 1e-9,
                 "api": "rcn_cuda_train_epoch_host (chunks_exact loop over a pinned host dataset: the GPU pulls chunk k+1 over PCIe "
                        "while chunk k trains, one CUDA graph launch per step, per-step cost/hits written back to host memory)"},
         "gpu_launches": int(launches),
