@@ -318,7 +318,8 @@ def run_gpu(args, wl, rank, world, local_rank):
     kernels_per_step = None
     if not args.no_graph:
         l_before = _lib.kernel_launches()
-        spg = max(1, math.gcd(args.steps, args.steps_per_graph))     # the timed region is a whole number of replays
+        # the timed region is a whole number of replays: the largest divisor of K that is <= --steps-per-graph
+        spg = max(d for d in range(1, max(1, min(args.steps_per_graph, args.steps)) + 1) if args.steps % d == 0)
         trainer.capture(warmup=3, steps_per_graph=spg)
         kernels_per_step = (_lib.kernel_launches() - l_before) // (3 + spg)   # 3 warm-up steps + spg captured steps
     else:
@@ -573,7 +574,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--steps-per-graph", type=int, default=8, help="consecutive steps captured into one CUDA graph (the timed region replays it steps/this times)")
+    ap.add_argument("--steps-per-graph", type=int, default=16, help="consecutive steps captured into one CUDA graph (the timed region replays it steps/this times)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
                     help="multi-GPU gradient exchange: fused NVLink peer-memory kernel, NCCL all-reduce, or by size")
