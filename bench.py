@@ -319,9 +319,10 @@ def run_gpu(args, wl, rank, world, local_rank):
     if not args.no_graph:
         l_before = _lib.kernel_launches()
         # the timed region is a whole number of replays: the largest divisor of K that is <= --steps-per-graph
-        # (multi-GPU runs were validated with at most 8 steps per graph on this pool: keep that cap there)
-        cap = args.steps_per_graph if world == 1 else min(args.steps_per_graph, 8)
-        spg = max(d for d in range(1, max(1, min(cap, args.steps)) + 1) if args.steps % d == 0)
+        if world == 1:
+            spg = max(d for d in range(1, max(1, min(args.steps_per_graph, args.steps)) + 1) if args.steps % d == 0)
+        else:   # multi-GPU runs keep the graph shapes they were validated with on this pool (gcd with at most 8)
+            spg = max(1, math.gcd(args.steps, min(args.steps_per_graph, 8)))
         trainer.capture(warmup=3, steps_per_graph=spg)
         kernels_per_step = (_lib.kernel_launches() - l_before) // (3 + spg)   # 3 warm-up steps + spg captured steps
     else:
