@@ -204,7 +204,8 @@ int rcn_cuda_kernel_launches(uint64_t* count);
 /* Generation of the library's grow-only device buffers: changes whenever one of them is (re)allocated, i.e. whenever a
  * call needed more scratch than any call before it.  A caller that has captured library calls into its own CUDA graph
  * (device pointers baked in) compares the value from capture time before each replay and re-captures on a change; the
- * library's own step graphs (rcn_cuda_train_epoch_host) do the same internally. */
+ * library's own step graphs (rcn_cuda_train_epoch_host) do the same internally.  scale_set is the other thing a captured
+ * step holds BY VALUE (kernel arguments): re-capture after rcn_cuda_set_scale / rcn_cuda_gen_scales changed it. */
 int rcn_cuda_allocation_generation(uint64_t* generation);
 /* on != 0: start bracketing every kernel launch with CUDA events on its stream (clears old records);
  * on == 0: stop.  Adds two event records per launch -- never enable inside a timed region. */

@@ -202,12 +202,14 @@ struct rcn_cuda_model {
     struct HsKey {
         size_t B = 0, H = 0, W = 0, n_steps = 0;
         unsigned long long alloc_gen = 0;   // no device buffer has moved since the capture (common.cuh)
+        uint64_t mean_bits = 0, sd_bits = 0; // scale_set travels BY VALUE in the captured kernel arguments
         double scale = 0.0;
         const void *labels = nullptr, *stats = nullptr, *ring = nullptr, *state = nullptr, *grads = nullptr;
         cudaStream_t stream = nullptr;
         bool dp = false;
         bool operator==(const HsKey& o) const {
-            return B == o.B && H == o.H && W == o.W && n_steps == o.n_steps && alloc_gen == o.alloc_gen && scale == o.scale && labels == o.labels &&
+            return B == o.B && H == o.H && W == o.W && n_steps == o.n_steps && alloc_gen == o.alloc_gen && mean_bits == o.mean_bits &&
+                   sd_bits == o.sd_bits && scale == o.scale && labels == o.labels &&
                    stats == o.stats && ring == o.ring && state == o.state && grads == o.grads && stream == o.stream && dp == o.dp;
         }
     } hs_key;
@@ -1180,6 +1182,8 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
             key.B = B; key.H = H; key.W = W; key.n_steps = 0; key.scale = scale_s;   // the graphs do not depend on the epoch length
             key.labels = h->tgt_stage.p;   // (grows with the epoch length: a longer epoch than any before re-captures)
             key.alloc_gen = alloc_generation().load(std::memory_order_relaxed);
+            memcpy(&key.mean_bits, &h->mean, sizeof(double));   // a set_scale / gen_scales since the capture re-captures
+            memcpy(&key.sd_bits, &h->sd, sizeof(double));
             key.stats = h->stats_host; key.ring = h->hs_ring.p; key.state = st; key.grads = h->grads; key.stream = h->stream;
             key.dp = h->dp.connected;
             if (!h->hs_graph || !h->hs_graph1 || !(key == h->hs_key)) {

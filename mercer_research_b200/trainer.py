@@ -149,11 +149,12 @@ class DataParallelTrainer:
                 self._epoch_step_eager()
         self.graph = graph
         self._graph_generation = _lib.allocation_generation()
+        self._graph_scale = self.model.scale_set          # (mean, sd) travel by value in the captured kernel arguments
         self.model.set_stream(torch.cuda.current_stream().cuda_stream)
 
     def _replay(self):
         from . import _lib
-        if _lib.allocation_generation() != self._graph_generation:
+        if _lib.allocation_generation() != self._graph_generation or self.model.scale_set != self._graph_scale:
             self._capture_graph()
         self.graph.replay()
 

@@ -688,6 +688,51 @@ def test_cached_step_graphs_survive_buffer_growth(api):
     assert np.array_equal(graphed.get_params().view(np.uint64), ref2.get_params().view(np.uint64))
 
 
+def test_cached_step_graphs_follow_scale_set(api):
+    """scale_set travels by value in the captured kernel arguments: after set_scale / gen_scales changed it, the cached
+    host-streaming graphs and the trainer's captured step must be re-captured (rcn.rs:406-412 standardises with the
+    CURRENT scale_set), not replayed with the old (mean, sd)."""
+    import torch
+    from mercer_research_b200.trainer import DataParallelTrainer
+    rng = np.random.default_rng(41)
+    B, N = 64, 64 * 6
+    images = torch.from_numpy(rng.integers(0, 256, size=(N, 28, 28), dtype=np.uint8)).pin_memory()
+    labels = torch.from_numpy(rng.integers(0, 10, size=N).astype(np.int64)).pin_memory()
+    hi, hl = images.numpy(), labels.numpy()
+    cfg = [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max)]
+
+    def fresh():
+        m = api.RCN(10, cfg, [30])
+        m.load_weights_and_bias(784)
+        m.set_params(np.random.default_rng(42).standard_normal(m.n_params) * 0.1)
+        return m
+
+    ref = fresh()
+    for scale in ((40.0, 60.0), (25.0, 45.0)):
+        ref.scale_set = scale
+        for k in range(N // B):
+            ref.train_batch_images(hi[k * B:(k + 1) * B], hl[k * B:(k + 1) * B], 3.0)
+    want = ref.get_params()
+
+    model = fresh()
+    for scale in ((40.0, 60.0), (25.0, 45.0)):
+        model.scale_set = scale
+        model.train_epoch_host(hi, hl, B, 3.0)
+    assert np.array_equal(model.get_params().view(np.uint64), want.view(np.uint64))
+
+    graphed = fresh()
+    graphed.scale_set = (40.0, 60.0)
+    tr = DataParallelTrainer(graphed, eta=3.0)
+    tr.bind_dataset(images.cuda(), labels.cuda(), B)
+    tr.capture(warmup=1, steps_per_graph=3)
+    graphed.set_params(np.random.default_rng(42).standard_normal(graphed.n_params) * 0.1)   # undo the warm-up step
+    tr.epoch_steps(6)
+    graphed.scale_set = (25.0, 45.0)
+    tr.epoch_steps(6)
+    torch.cuda.synchronize()
+    assert np.array_equal(graphed.get_params().view(np.uint64), want.view(np.uint64))
+
+
 def test_train_epoch_host_contract(api):
     """Argument contract of the host-dataset loop: chunks_exact drops a short tail entirely (rcn.rs:147), device buffers are
     rejected, a wrong feature width is the reference's dimension-mismatch panic, state errors come back as status codes."""
