@@ -105,3 +105,54 @@ def test_dp_two_ranks_equals_single_process(tmp_path):
         params, _ = net.train_batch(params, X, np.eye(10)[labels], 3.0)
     err = np.max(np.abs(p0 - params)) / np.max(np.abs(params))
     assert err < 1e-12, err   # only the summation order differs
+
+
+def test_captured_step_is_recaptured_when_its_baked_in_state_moved(monkeypatch):
+    """Host logic of DataParallelTrainer._replay (no GPU): a captured step holds device pointers and scale_set by value,
+    so it is re-captured when the library's allocation generation or the model's scale_set differ from capture time, and
+    only then; epoch_steps() = whole replays + an eager remainder."""
+    from mercer_research_b200 import _lib
+    from mercer_research_b200.trainer import DataParallelTrainer
+
+    class Graph:
+        def __init__(self, log):
+            self.log = log
+
+        def replay(self):
+            self.log.append("replay")
+
+    class Model:
+        scale_set = (1.0, 1.0)
+
+    gen = {"v": 7}
+    monkeypatch.setattr(_lib, "allocation_generation", lambda: gen["v"])
+    log = []
+    tr = DataParallelTrainer.__new__(DataParallelTrainer)
+    tr.model, tr.world, tr.p2p = Model(), 1, False
+
+    def capture():
+        log.append("capture")
+        tr.graph = Graph(log)
+        tr._graph_generation = _lib.allocation_generation()
+        tr._graph_scale = tr.model.scale_set
+
+    monkeypatch.setattr(tr, "_capture_graph", capture)
+    monkeypatch.setattr(tr, "_epoch_step_eager", lambda: log.append("eager"))
+    tr.steps_per_graph = 4
+    capture()
+    del log[:]
+    tr.epoch_steps(8)
+    assert log == ["replay", "replay"]
+    gen["v"] = 8                                   # a library buffer moved
+    del log[:]
+    tr.epoch_step()
+    tr.epoch_step()
+    assert log == ["capture", "replay", "replay"]
+    tr.model.scale_set = (2.0, 3.0)                # scale_set changed
+    del log[:]
+    tr.epoch_steps(10)                             # 2 replays + 2 eager steps
+    assert log == ["capture", "replay", "replay", "eager", "eager"]
+    tr.graph = None
+    del log[:]
+    tr.epoch_steps(3)
+    assert log == ["eager"] * 3
