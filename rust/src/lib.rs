@@ -202,9 +202,12 @@ pub mod rcn {
         pub(crate) fn raw(&self) -> ffi::rcn_cuda_handle { self.handle }
         pub fn device(&self) -> i32 { self.device }
 
+        /// Number of dense layers; 0 while the model has no parameters yet (`layer_weights.is_empty()`, rcn.rs:139).
         fn num_layers(&self) -> usize {
             let mut n = 0usize;
-            check(unsafe { ffi::rcn_cuda_num_layers(self.handle, &mut n) });
+            let rc = unsafe { ffi::rcn_cuda_num_layers(self.handle, &mut n) };
+            if rc == ffi::RCN_ERR_STATE { return 0; }
+            check(rc);
             n
         }
 
