@@ -17,7 +17,7 @@ def host_test(built_library):
     deps = [SRC, os.path.join(ROOT, "include", "rcn.hpp"), os.path.join(ROOT, "include", "rcn_cuda.h")]
     if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
         os.makedirs(BUILD, exist_ok=True)
-        cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), SRC,
+        cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), SRC,
                "-L", os.path.join(ROOT, "mercer_research_b200"), "-lrcn_cuda",
                "-Wl,-rpath,$ORIGIN/../../../mercer_research_b200", "-o", EXE]
         r = subprocess.run(cmd, capture_output=True, text=True)
