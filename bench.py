@@ -544,12 +544,14 @@ def run_gpu(args, wl, rank, world, local_rank):
 
     line = {
         "metric": "training images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": n_warm * spg, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["desc"], "batch_per_gpu": B, "global_batch": B * world, "pixels": "u8", "eta": ETA,
                    "params": n_params, "parallelism": f"dp{world}",
                    "l2_policy": f"inputs rotate over {n_batches} resident batches = {n_batches * B * H * W / 2 ** 20:.0f} MiB > 126 MB L2",
-                   "step": step_desc, "cuda_graph": not args.no_graph, "steps_per_graph": spg},
+                   "step": step_desc, "cuda_graph": not args.no_graph, "steps_per_graph": spg,
+                   # the W requested warm-up steps plus ~0.3 s of the same load so that clocks have ramped
+                   "warmup_steps_run": n_warm * spg},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps, "host_buffers": "pinned",
