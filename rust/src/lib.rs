@@ -95,7 +95,8 @@ pub mod rcn {
     use serde::{de::Deserializer, ser::Serializer, Deserialize, Serialize};
     use std::os::raw::c_void;
     use std::sync::Mutex;
-    use std::{fs, path::PathBuf, ptr};
+    use std::path::{Path, PathBuf};
+    use std::{fs, ptr};
 
     /// rcn.rs:35-38
     #[derive(Clone, Copy, Serialize, Deserialize)]
@@ -286,32 +287,42 @@ pub mod rcn {
             maps * mh * mw
         }
 
-        /// rcn.rs:367-415: sorted class directories, `class_size_limit` files drawn without replacement per class,
-        /// decoded to grayscale; then gen_scales over the raw features of the whole set (stored as scale_set).
+        /// rcn.rs:367-415: class directories in sorted order, `class_size_limit` files per class drawn uniformly without
+        /// replacement, decoded to grayscale; then gen_scales over the raw features of the whole set (stored as scale_set).
+        /// All pixels of the set land in ONE page-locked buffer so that the GPU can stream it.
         fn load_data(&mut self, path: &str, class_size_limit: usize) -> HostSet {
-            let mut classes: Vec<PathBuf> = fs::read_dir(path).unwrap().map(|f| f.unwrap().path()).collect();
-            classes.sort();
-            let mut bytes: Vec<u8> = Vec::new();
+            fn entries(dir: &Path) -> Vec<PathBuf> {
+                let mut v: Vec<PathBuf> = fs::read_dir(dir)
+                    .unwrap_or_else(|e| panic!("cannot read {}: {e}", dir.display()))
+                    .map(|entry| entry.expect("directory entry").path())
+                    .collect();
+                v.sort();
+                v
+            }
+            let mut rng = rand::thread_rng();
+            let mut staged: Vec<u8> = Vec::new();
             let mut labels: Vec<i64> = Vec::new();
-            let (mut h, mut w) = (0usize, 0usize);
-            for (i, class) in classes.iter().enumerate() {
-                let mut paths: Vec<PathBuf> = fs::read_dir(class).unwrap().map(|f| f.unwrap().path()).collect();
-                if class_size_limit > paths.len() {
-                    panic!("provided class_size_limit for {} too large! expected {} <= {}", path, class_size_limit, paths.len());
+            let mut dims: Option<(usize, usize)> = None;
+            for (class_index, dir) in entries(Path::new(path)).iter().enumerate() {
+                let mut files = entries(dir);
+                if class_size_limit > files.len() {
+                    // same message as the reference's panic (rcn.rs:383-390)
+                    panic!("provided class_size_limit for {} too large! expected {} <= {}", path, class_size_limit, files.len());
                 }
-                for _ in 0..class_size_limit {
-                    let idx = rand::thread_rng().gen_range(0..paths.len());
-                    let img = ImageReader::open(paths.remove(idx)).unwrap().decode().unwrap().grayscale();
-                    let (px, ih, iw) = luma_bytes(img).unwrap();
-                    if labels.is_empty() { h = ih; w = iw; }
+                let (chosen, _rest) = files.partial_shuffle(&mut rng, class_size_limit);
+                for file in chosen.iter() {
+                    let decoded = ImageReader::open(file).unwrap().decode().unwrap().grayscale();
+                    let (px, ih, iw) = luma_bytes(decoded).unwrap();
+                    let (h, w) = *dims.get_or_insert((ih, iw));
                     assert!(ih == h && iw == w, "all images of a data set must have the same size ({h}x{w}), got {ih}x{iw}");
-                    bytes.extend_from_slice(&px);
-                    labels.push(i as i64);
+                    staged.extend_from_slice(&px);
+                    labels.push(class_index as i64);
                 }
             }
+            let (h, w) = dims.expect("empty data set");
             let n = labels.len();
-            let mut pixels = PinnedBuffer::<u8>::new(bytes.len());
-            pixels.as_mut_slice().copy_from_slice(&bytes);
+            let mut pixels = PinnedBuffer::<u8>::new(staged.len());
+            pixels.as_mut_slice().copy_from_slice(&staged);
             // gen_scales (rcn.rs:230-251) on the device: raw features of the whole set, then mean / population sd
             let l = self.feature_len(h, w);
             let mut feats = DeviceBuffer::<f64>::new(self.device, l * n);
