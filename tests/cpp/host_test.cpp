@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <sstream>
 #include <string>
 
@@ -69,6 +70,28 @@ static int run_cpu() {
     EXPECT(status_of([] { DMatrix(2, 2).convolve_2d(DMatrix(3, 3), Padding::None); }) == RCN_ERR_SHAPE);                       // kernel.rs:123-128
     EXPECT(status_of([] { DMatrix(8, 8).convolve_2d(DMatrix(5, 5), Padding::Same); }) == RCN_ERR_OUT_OF_BOUNDS);               // kernel.rs:156
     EXPECT(rcn::RCNLayer::Convolve2D(Padding::Same).code == RCN_LAYER_CONV_SAME && rcn::RCNLayer::Pool2D(Pooling::Max).code == RCN_LAYER_POOL_MAX);
+    // column-major storage and the row-iterator constructor (lib.rs:29-33 builds the pixel matrix the same way)
+    {
+        const DMatrix m = DMatrix::from_row_slice(2, 3, {1, 2, 3, 4, 5, 6});
+        EXPECT(m(0, 2) == 3 && m(1, 0) == 4 && m.as_slice() == std::vector<double>({1, 4, 2, 5, 3, 6}));
+        EXPECT(DMatrix::from_vec(2, 3, {1, 4, 2, 5, 3, 6}) == m && m.shape() == std::make_pair(size_t{2}, size_t{3}));
+    }
+    // the one image format the header decodes itself: binary PGM, comments allowed, 16-bit and truncated files rejected
+    {
+        const std::string path = "/tmp/rcn_host_test.pgm";
+        { std::ofstream f(path, std::ios::binary); f << "P5\n# a comment\n3 2\n255\n"; f.write("\x00\x01\x02\xfd\xfe\xff", 6); }
+        std::vector<uint8_t> px;
+        size_t h = 0, w = 0;
+        EXPECT(rcn::read_pgm(path, &px, &h, &w) && h == 2 && w == 3 && px == std::vector<uint8_t>({0, 1, 2, 253, 254, 255}));
+        { std::ofstream f(path, std::ios::binary); f << "P5\n3 2\n65535\n"; f.write("\0\0\0\0\0\0\0\0\0\0\0\0", 12); }
+        EXPECT(!rcn::read_pgm(path, &px, &h, &w));
+        { std::ofstream f(path, std::ios::binary); f << "P5\n3 2\n255\n"; f.write("\x00\x01", 2); }
+        EXPECT(!rcn::read_pgm(path, &px, &h, &w));
+        { std::ofstream f(path, std::ios::binary); f << "P2\n3 2\n255\n1 2 3 4 5 6\n"; }
+        EXPECT(!rcn::read_pgm(path, &px, &h, &w));
+        EXPECT(!rcn::read_pgm("/tmp/rcn_host_test_missing.pgm", &px, &h, &w));
+        std::remove(path.c_str());
+    }
     if (!g_failed) std::printf("cpu ok\n");
     return g_failed ? 1 : 0;
 }
