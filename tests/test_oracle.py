@@ -260,3 +260,63 @@ def test_golden_dense():
     db, dw, zs, acts, deltas = N.backprop(ws, bs, g["X"][0], Y[0])
     assert np.array_equal(np.concatenate(zs), g["sample0_zs"])
     assert np.array_equal(np.concatenate(deltas), g["sample0_deltas"])
+
+
+# ---- randomised cross-checks of the two restatements (hypothesis): shapes and configurations nobody hand-picked ---------
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+_SLOW_OK = settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+
+
+@_SLOW_OK
+@given(h=st.integers(3, 17), w=st.integers(3, 17), cfg=st.lists(st.sampled_from([0, 1, 3]), max_size=4), seed=st.integers(0, 2 ** 31))
+def test_cross_flatten_random(h, w, cfg, seed):
+    """C++ oracle == numpy twin, bit for bit, on random image sizes and convpool stacks (valid / SAME convolutions, max
+    pools in any order); a stack that shrinks a map below what the next layer accepts must panic in both."""
+    img = np.random.default_rng(seed).integers(0, 256, (h, w)).astype(float)
+    try:
+        want = N.flatten_feature_set(cfg, img)
+    except N.RefPanic:
+        with pytest.raises(O.RefPanic):
+            O.flatten_feature_set(cfg, img)
+        return
+    got = O.flatten_feature_set(cfg, img)
+    assert np.array_equal(got, want)
+    n, fh, fw = O.feature_shape(cfg, h, w)
+    assert got.size == n * fh * fw
+
+
+@_SLOW_OK
+@given(sizes=st.lists(st.integers(1, 9), min_size=2, max_size=5), batch=st.integers(1, 7), seed=st.integers(0, 2 ** 31),
+       eta=st.sampled_from([0.1, 0.5, 3.0]))
+def test_cross_train_batch_random(sizes, batch, seed, eta):
+    """backprop + minibatch sum + SGD step: C++ oracle == numpy twin, bit for bit, on random layer stacks (incl. width-1
+    layers and single-sample batches) with unscaled N(0, 1) parameters like the reference's initialisation."""
+    rng = np.random.default_rng(seed)
+    shapes = [(sizes[i + 1], sizes[i]) for i in range(len(sizes) - 1)]
+    net = O.Net(shapes)
+    ws = [rng.standard_normal(s) for s in shapes]
+    bs = [rng.standard_normal(s[0]) for s in shapes]
+    X = np.maximum(rng.standard_normal((batch, sizes[0])), 0)
+    labels = rng.integers(0, sizes[-1], batch)
+    Y = np.eye(sizes[-1])[labels]
+    newp, g = net.train_batch(net.pack(ws, bs), X, Y, eta)
+    nw, nb, gw, gb = N.train_batch(ws, bs, list(X), list(Y), eta)
+    w2, b2 = net.unpack(newp)
+    gw2, gb2 = net.unpack(g)
+    for a, b in zip(w2 + b2 + gw2 + gb2, nw + nb + gw + gb):
+        assert np.array_equal(a, b)
+    acts = net.forward(net.pack(ws, bs), X)
+    assert O.argmax_last(acts).tolist() == [N.argmax_last(a) for a in acts]
+    assert O.accuracy(acts, labels) == sum(N.accuracy_hit(a, l) for a, l in zip(acts, labels))
+
+
+@_SLOW_OK
+@given(h=st.integers(2, 12), w=st.integers(2, 12), pad=st.sampled_from([0, 1]), seed=st.integers(0, 2 ** 31), ties=st.booleans())
+def test_cross_pool_random(h, w, pad, seed, ties):
+    """max pool values and the last-max-wins argmax on random maps, with many ties when asked for (small value range)."""
+    rng = np.random.default_rng(seed)
+    x = rng.integers(0, 3 if ties else 256, (h, w)).astype(float)
+    a, ai = O.pool_2d(x, pad, O.POOL_MAX, return_argmax=True)
+    b, bi = N.pool_2d(x, pad, O.POOL_MAX, return_argmax=True)
+    assert np.array_equal(a, b) and np.array_equal(ai, bi)
