@@ -39,6 +39,7 @@ int dp_alloc(DpState& st, int world, int rank, size_t n, cudaStream_t stream) {
     st.n_chunks = (n + kDpChunk - 1) / kDpChunk;
     st.bytes = dp_block_bytes(world, n);
     RCN_CUDA_TRY(cudaMalloc(&st.block, st.bytes));
+    alloc_generation().fetch_add(1, std::memory_order_relaxed);   // peer pointers are baked into captured step graphs too
     RCN_CUDA_TRY(cudaMemsetAsync(st.block, 0xFF, st.bytes, stream));      // every receive slot = sentinel
     RCN_CUDA_TRY(cudaMemsetAsync(st.block, 0, kDpCtrlBytes, stream));
     RCN_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -51,7 +52,7 @@ void dp_release(DpState& st) {
         if (st.imported[q] && st.peers[q]) cudaIpcCloseMemHandle(st.peers[q]);
         st.peers[q] = nullptr; st.imported[q] = false;
     }
-    if (st.block) cudaFree(st.block);
+    if (st.block) { cudaFree(st.block); alloc_generation().fetch_add(1, std::memory_order_relaxed); }
     st.block = nullptr; st.connected = false; st.world = 1; st.rank = 0;
     cudaGetLastError();
 }
