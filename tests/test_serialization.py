@@ -68,3 +68,30 @@ def test_malformed_checkpoints_are_rejected():
         S.decode_state(bytes(bad_variant))
     with pytest.raises(ValueError):
         S.encode_state(dict(classes=2, convpool_cfg=[9], feedforward_cfg=[], weights=[], biases=[], scale_set=(1, 1)))
+
+
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+@given(classes=st.integers(1, 50), cfg=st.lists(st.integers(0, 3), max_size=6), widths=st.lists(st.integers(1, 12), min_size=1, max_size=4),
+       trained=st.booleans(), seed=st.integers(0, 2 ** 31), tr=st.text(max_size=20), te=st.text(max_size=20))
+def test_round_trip_random_states(classes, cfg, widths, trained, seed, tr, te):
+    """encode -> decode -> encode is the identity on random models (any layer stack, any widths, untrained or trained,
+    non-ASCII paths): the byte layout has no state-dependent ambiguity."""
+    rng = np.random.default_rng(seed)
+    sizes = [int(rng.integers(1, 40))] + widths + [classes]
+    ws = [rng.standard_normal((sizes[i + 1], sizes[i])) for i in range(len(sizes) - 1)] if trained else []
+    bs = [rng.standard_normal(w.shape[0]) for w in ws]
+    state = dict(classes=classes, convpool_cfg=cfg, feedforward_cfg=widths, weights=ws, biases=bs,
+                 scale_set=(float(rng.standard_normal()), float(abs(rng.standard_normal()) + 0.1)), training_path=tr, testing_path=te)
+    blob = S.encode_state(state)
+    back = S.decode_state(blob)
+    assert S.encode_state(back) == blob
+    assert back["classes"] == classes and back["convpool_cfg"] == cfg and back["feedforward_cfg"] == widths
+    assert back["training_path"] == tr and back["testing_path"] == te and back["scale_set"] == state["scale_set"]
+    assert len(back["weights"]) == len(ws) and all(np.array_equal(a, b) for a, b in zip(back["weights"], ws))
+    for cut in sorted({0, 1, len(blob) // 2, len(blob) - 1}):
+        if cut < len(blob):
+            with pytest.raises(ValueError):
+                S.decode_state(blob[:cut])                      # a truncated file never decodes silently
