@@ -265,7 +265,7 @@ def test_golden_dense():
 # ---- randomised cross-checks of the two restatements (hypothesis): shapes and configurations nobody hand-picked ---------
 from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
 
-_SLOW_OK = settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+_SLOW_OK = settings(max_examples=40, deadline=None, derandomize=True, database=None, suppress_health_check=list(HealthCheck))
 
 
 @_SLOW_OK

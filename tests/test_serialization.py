@@ -73,7 +73,7 @@ def test_malformed_checkpoints_are_rejected():
 from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
 
 
-@settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=60, deadline=None, derandomize=True, database=None, suppress_health_check=list(HealthCheck))
 @given(classes=st.integers(1, 50), cfg=st.lists(st.integers(0, 3), max_size=6), widths=st.lists(st.integers(1, 12), min_size=1, max_size=4),
        trained=st.booleans(), seed=st.integers(0, 2 ** 31), tr=st.text(max_size=20), te=st.text(max_size=20))
 def test_round_trip_random_states(classes, cfg, widths, trained, seed, tr, te):
