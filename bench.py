@@ -254,6 +254,32 @@ def run_reference(args, wl, rank, world):
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
+_WC_KEEP = []   # write-combined allocations stay alive for the life of the process
+
+
+def _wc_pinned_copy(a):
+    """numpy array -> the same bytes in cudaHostAllocWriteCombined memory (viewed as a numpy array), or None if the CUDA
+    runtime cannot be reached from here. CPU reads of such memory are slow; the bench only writes it once."""
+    import ctypes
+    try:
+        import torch
+        rt = ctypes.CDLL(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_runtime", "lib", "libcudart.so.12"))
+    except OSError:
+        try:
+            rt = ctypes.CDLL("libcudart.so.12")
+        except OSError:
+            return None
+    p = ctypes.c_void_p()
+    rt.cudaHostAlloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t, ctypes.c_uint]
+    if rt.cudaHostAlloc(ctypes.byref(p), a.nbytes, 0x01 | 0x04) != 0 or not p.value:   # portable | write-combined
+        return None
+    buf = (ctypes.c_uint8 * a.nbytes).from_address(p.value)
+    out = np.frombuffer(buf, dtype=a.dtype).reshape(a.shape)
+    out[...] = a
+    _WC_KEEP.append((rt, p, buf))
+    return out
+
+
 def measure_fp64_peak(torch, dev):
     """cuBLAS DGEMM 8192^3 via torch.matmul -- the f64 denominator MEASURED_PEAKS.json lacks."""
     n = 8192
@@ -380,6 +406,14 @@ def run_gpu(args, wl, rank, world, local_rank):
     h_images = torch.randint(0, 256, (n_host * B, H, W), dtype=torch.uint8).pin_memory()
     h_labels = (torch.arange(n_host * B) % wl["classes"]).to(torch.int64).pin_memory()
     hi, hl = h_images.numpy(), h_labels.numpy()
+    host_alloc = "pinned"
+    if args.host_alloc == "wc":
+        # opt-in experiment: the same dataset in WRITE-COMBINED pinned memory (cudaHostAllocWriteCombined). The e2e path is
+        # bound by the rate at which the GPU can read host memory (38 GB/s from ordinary pinned pages);
+        # write-combined pages are not snooped in the CPU caches on the way out. Not the default until it is measured.
+        wc = _wc_pinned_copy(hi)
+        if wc is not None:
+            hi, host_alloc = wc, "pinned, write-combined"
 
     def e2e_steps(n):
         done = 0
@@ -554,7 +588,7 @@ def run_gpu(args, wl, rank, world, local_rank):
                    "warmup_steps_run": n_warm * spg},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / args.steps, "host_buffers": "pinned",
+                "ms_per_step": e2e_ms / args.steps, "host_buffers": host_alloc,
                 # PCIe bytes per second this rank pulled inside the timed region (the e2e path's own bound: SM-issued
                 # zero-copy reads reach ~38 GB/s on this pool's boxes, profiles/r1s_full_host_prefetch.txt)
                 "h2d_GBps_per_gpu": h2d / (e2e_ms / args.steps * 1e-3) * 1e-9,
@@ -581,6 +615,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--steps-per-graph", type=int, default=16, help="consecutive steps captured into one CUDA graph (the timed region replays it steps/this times)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--host-alloc", default="pinned", choices=["pinned", "wc"],
+                    help="e2e leg: ordinary pinned host memory (default) or write-combined pinned memory (experiment)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
                     help="multi-GPU gradient exchange: fused NVLink peer-memory kernel, NCCL all-reduce, or by size")
     args = ap.parse_args()
