@@ -506,6 +506,8 @@ namespace {
 // Installs explicit layer shapes (rows[i] x cols[i]), allocates zeroed parameters / gradients, picks the fused path.
 int install_shapes(rcn_cuda_model* h, const std::vector<size_t>& rows, const std::vector<size_t>& cols) {
     const size_t n = rows.size();
+    // a captured step holds the layer shapes by value (SmallNetDesc): new shapes invalidate it like a moved buffer does
+    alloc_generation().fetch_add(1, std::memory_order_relaxed);
     h->rows.clear(); h->cols.clear(); h->w_off.clear(); h->b_off.clear();
     size_t off = 0, sum_rows = 0;
     for (size_t i = 0; i < n; ++i) {
