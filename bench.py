@@ -575,6 +575,8 @@ def run_gpu(args, wl, rank, world, local_rank):
     # ---- CPU baseline on this box's host cores (bounded sample, ~10-20 s) ------------------------------------------
     Bs = cpu_sample_batch(wl, os.cpu_count() or 1)
     cpu_ips, cpu_ms, cpu_done, cores, Bs = cpu_train_steps(wl, steps=10 ** 6, warmup=2, max_seconds=12.0, batch=Bs)
+    # BASELINE.json configs[0] (the reference's own CPU-runnable case: the same network at batch 32), ~3 s more
+    c1_ips, _, c1_done, _, _ = cpu_train_steps(WORKLOADS["c1"], steps=10 ** 6, warmup=2, max_seconds=3.0)
 
     line = {
         "metric": "training images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
@@ -598,7 +600,9 @@ def run_gpu(args, wl, rank, world, local_rank):
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_ips, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": f"{cpu_done} steps of batch {Bs} (features+fwd+bwd+SGD) on {cores} host threads, "
-                                   "oracle/rcn_oracle.cpp (C++ restatement of rcn's CPU path, not rustc output)"},
+                                   "oracle/rcn_oracle.cpp (C++ restatement of rcn's CPU path, not rustc output)",
+                         "configs0_batch32": {"value": c1_ips, "unit": "images/s", "cores": cores,
+                                              "sample": f"{c1_done} steps of batch 32, same network, same {cores} host threads"}},
     }
     emit_result(line)
     if world > 1:
