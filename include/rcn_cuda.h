@@ -153,9 +153,7 @@ int rcn_cuda_epoch_position(rcn_cuda_handle h, size_t* position); /* synchronise
 int rcn_cuda_epoch_accumulate(rcn_cuda_handle h);
 int rcn_cuda_epoch_apply(rcn_cuda_handle h, double eta, size_t global_batch);
 int rcn_cuda_epoch_step(rcn_cuda_handle h, double eta); /* accumulate + apply with global_batch = B */
-/* n_steps consecutive epoch steps (rcn.rs:147-149: n_steps iterations of the chunks_exact loop). On one GPU with the
- * canonical narrow network and u8 images they run as ONE persistent cooperative launch (phase A, phase B + update, next
- * step ... separated by grid-wide barriers instead of kernel boundaries); otherwise as n_steps rcn_cuda_epoch_step calls. */
+/* n_steps consecutive epoch steps (rcn.rs:147-149: n_steps iterations of the chunks_exact loop) in one call. */
 int rcn_cuda_epoch_run(rcn_cuda_handle h, double eta, size_t n_steps);
 
 /* The same loop over a HOST-resident (already shuffled) dataset: `for batch in training_set.chunks_exact(B) {
@@ -183,11 +181,23 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
  *   dp_connect_local group = world handles living in THIS process (one per device; peer access is enabled).
  * Every rank must execute the same sequence of apply calls, and in a connected group every accumulate must be followed by
  * exactly one apply before the next accumulate (the fused small-network kernels already push their gradients to the peers
- * at the end of accumulate, so that the exchange overlaps the launch of the update). */
+ * at the end of accumulate, so that the exchange overlaps the launch of the update).
+ * A receive never waits forever: a peer that stays silent for RCN_CUDA_DP_TIMEOUT_MS (default 10 000) sets a sticky error
+ * word in this rank's block, the affected sums become NaN, and rcn_cuda_dp_error (which synchronises the stream) returns
+ * RCN_ERR_STATE with *error = 1 -- the reference's equivalent is a poisoned mutex panic (rcn.rs:192-193). */
 int rcn_cuda_dp_init(rcn_cuda_handle h, int world, int rank, void* ipc_handle_out);
 int rcn_cuda_dp_connect_ipc(rcn_cuda_handle h, const void* all_handles);
 int rcn_cuda_dp_connect_local(rcn_cuda_handle h, const rcn_cuda_handle* group);
 int rcn_cuda_dp_shutdown(rcn_cuda_handle h);
+int rcn_cuda_dp_error(rcn_cuda_handle h, int* error);
+
+/* Device-side launch timeline of the fused step kernels (kernel 0 = forward/backward kernel A, 1 = weight-gradient kernel
+ * B, 2 = data-parallel exchange kernel): per launch the earliest CTA start and the latest CTA end in %globaltimer
+ * nanoseconds, kept for the last 64 launches -- the durations of, and gaps between, the kernels of a REPLAYED CUDA graph.
+ * enable(1) allocates and clears the block (steps captured before the call must be re-captured: the allocation generation
+ * is bumped); read: stamps = [2][4][64] uint64 (starts, then ends; slot = launch index % 64), launches = [4] uint32. */
+int rcn_cuda_timeline_enable(rcn_cuda_handle h, int on);
+int rcn_cuda_timeline_read(rcn_cuda_handle h, uint64_t* stamps, uint32_t* launches);
 
 /* Gradient buffer access for the data-parallel trainer. bind: use caller-owned DEVICE memory (e.g. a torch
  * tensor that NCCL all-reduces) as the flat gradient buffer; NULL restores the internal one. */

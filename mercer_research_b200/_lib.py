@@ -69,6 +69,9 @@ SIGNATURES = {
     "rcn_cuda_dp_connect_ipc": [_vp, _vp],
     "rcn_cuda_dp_connect_local": [_vp, _vp],
     "rcn_cuda_dp_shutdown": [_vp],
+    "rcn_cuda_dp_error": [_vp, _vp],
+    "rcn_cuda_timeline_enable": [_vp, _i],
+    "rcn_cuda_timeline_read": [_vp, _vp, _vp],
     "rcn_cuda_bind_gradient_buffer": [_vp, _vp, _sz],
     "rcn_cuda_gradient_buffer": [_vp, C.POINTER(_vp), _szp],
     "rcn_cuda_get_gradients": [_vp, _vp, _sz],

@@ -14,7 +14,6 @@
 // recomputes sigmoid(z) (rcn.rs:491) which is bitwise the same value, and it must NOT be rewritten
 // algebraically (1-a cancels for saturated units and parity depends on cancelling identically).
 #include "dense.cuh"
-#include "timeline.cuh"
 #include "gemm_f64.cuh"
 #include "opctx.cuh"
 #include "ozaki.cuh"
@@ -551,8 +550,7 @@ int launch_dense_backward_weight(const double* delta, const double* A_prev, size
 // ------------------------------------------------------------------------------------------------
 __global__ void sgd_update_kernel(double* __restrict__ p, const double* __restrict__ g, size_t n, double scale,
                                   long long* __restrict__ cursor, long long batch, long long n_samples,
-                                  const double* __restrict__ stats, double* __restrict__ stats_ring, int pipe) {
-    RCN_TL_BEGIN(0);
+                                  const double* __restrict__ stats, double* __restrict__ stats_ring) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         p[i] = sgd_apply(p[i], scale, g[i]);  // &lw.0 - (eta / B) * w   (rcn.rs:214,221): product rounded, then subtracted
     if (cursor && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -565,18 +563,16 @@ __global__ void sgd_update_kernel(double* __restrict__ p, const double* __restri
         long long c = *cursor + batch;
         if (c + batch > n_samples) c = 0;
         *cursor = c;
-        if (pipe) cursor[1] += 1;   // pipelined epoch mode: training steps done (kEpAstep)
     }
-    RCN_TL_END(0);
 }
 
 int launch_sgd_update(double* params, const double* grads, size_t n, double scale, cudaStream_t stream,
-                      long long* cursor, long long batch, long long n_samples, const double* stats, double* stats_ring, bool pipe) {
+                      long long* cursor, long long batch, long long n_samples, const double* stats, double* stats_ring) {
     if (n == 0) return RCN_OK;
     unsigned grid = cdiv(n, 256);
     if (grid > kNumSMs * 8) grid = kNumSMs * 8;
     RCN_LAUNCH("sgd_update_kernel", stream,
-               sgd_update_kernel<<<grid, 256, 0, stream>>>(params, grads, n, scale, cursor, batch, n_samples, stats, stats_ring, pipe ? 1 : 0));
+               sgd_update_kernel<<<grid, 256, 0, stream>>>(params, grads, n, scale, cursor, batch, n_samples, stats, stats_ring));
     return RCN_OK;
 }
 
@@ -710,7 +706,4 @@ extern "C" int rcn_cuda_ext_gemm_f64(int device, void* cuda_stream, const double
     return c.finish(C, c_dev, M * N * 8, host);
 }
 
-#ifdef RCN_TIMELINE
-extern "C" int rcn_cuda_debug_timeline_reset_dense() { return rcn_tl::reset_host(); }
-extern "C" int rcn_cuda_debug_timeline_read_dense(unsigned long long* out, unsigned* seq) { return rcn_tl::read_host(out, seq); }
-#endif
+

@@ -40,7 +40,7 @@ int launch_bias_grad(const double* delta, size_t M, size_t N, double* db, Reduce
 // (pinned host memory in rcn_cuda_train_epoch_host) before the cursor advances.
 int launch_sgd_update(double* params, const double* grads, size_t n, double scale, cudaStream_t stream,
                       long long* cursor = nullptr, long long batch = 0, long long n_samples = 0, const double* stats = nullptr,
-                      double* stats_ring = nullptr, bool pipe = false /* pipelined epoch mode: cursor[1]++ as well */);
+                      double* stats_ring = nullptr);
 
 // labels[b] = argmax_i acts[i, b], last maximal element wins (rcn.rs:92-97)
 int launch_argmax_last(const double* acts, size_t n, size_t B, int64_t* labels, cudaStream_t stream);

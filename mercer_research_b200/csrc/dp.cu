@@ -17,6 +17,11 @@
 //   * the same thread then polls its elements of the peers' slots in ITS OWN block until they differ from the sentinel,
 //     puts the sentinel back, adds the ranks in RANK ORDER (so all replicas compute bit-identical sums and stay
 //     bit-identical to each other) and applies the update.  Latency = one NVLink traversal + a few L2 polls.
+// All of a thread's peer slots are requested before any is tested (one L2 round trip, not world - 1 dependent ones) and
+// every wait is BOUNDED (dp_wait_slot: a silent peer sets a sticky error word and yields NaN instead of hanging the
+// device).  The kernel runs as a FEW FAT CTAs (<= 20 x 1024 threads, grid-stride): beside rcn's canonical step its
+// successor, kernel A of the next step (128 CTAs that each need a whole SM), then finds its SMs free and can run its
+// parameter-independent front end while this kernel waits for the NVLink traffic (smallnet.cu).
 // Threads are independent: no grid-wide, CTA-wide or end-of-kernel barrier.  The receive slots are double buffered by
 // step parity: a peer can only push step s+2 into the parity that held step s after it has received every rank's
 // step s+1 push, which a rank issues only after its step-s kernel (reads and sentinel resets included) has finished.
@@ -36,7 +41,6 @@ int dp_alloc(DpState& st, int world, int rank, size_t n, cudaStream_t stream) {
     if (world < 1 || world > kDpMaxWorld || rank < 0 || rank >= world) return fail(RCN_ERR_INVALID, "bad world / rank (%d / %d)", world, rank);
     dp_release(st);
     st.world = world; st.rank = rank; st.n = n;
-    st.n_chunks = (n + kDpChunk - 1) / kDpChunk;
     st.bytes = dp_block_bytes(world, n);
     RCN_CUDA_TRY(cudaMalloc(&st.block, st.bytes));
     alloc_generation().fetch_add(1, std::memory_order_relaxed);   // peer pointers are baked into captured step graphs too
@@ -58,89 +62,68 @@ void dp_release(DpState& st) {
 }
 
 static_assert(kDpCtrlBytes == kDpCtrlBytesPub, "slot offset mismatch");
+static_assert(sizeof(DpCtrl) <= kDpCtrlBytes, "control words must fit the block header");
+
+static unsigned long long dp_timeout_ns() {
+    static const unsigned long long ns = []() {
+        const char* e = getenv("RCN_CUDA_DP_TIMEOUT_MS");
+        const long long ms = e ? atoll(e) : 10000;
+        return (unsigned long long)(ms > 0 ? ms : 10000) * 1000000ull;
+    }();
+    return ns;
+}
 
 DpPush dp_push_desc(const DpState& st) {
     DpPush d{};
     d.world = st.connected ? st.world : 1;
     d.rank = st.rank;
     d.n = st.n;
+    d.timeout_ns = dp_timeout_ns();
     for (int q = 0; q < st.world && q < kDpMaxWorld; ++q) d.peers[q] = (char*)st.peers[q];
     return d;
 }
 
-struct DpPeers { char* p[kDpMaxWorld]; };
-
-constexpr unsigned long long kDpSentinel = 0xFFFFFFFFFFFFFFFFull;
-constexpr unsigned long long kDpQuietNaN = 0x7FF8000000000000ull;
-
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
+int dp_read_error(const DpState& st, cudaStream_t stream, unsigned* error) {
+    *error = 0;
+    if (!st.block) return RCN_OK;
+    DpCtrl c{};
+    RCN_CUDA_TRY(cudaMemcpyAsync(&c, st.block, sizeof(c), cudaMemcpyDeviceToHost, stream));
+    RCN_CUDA_TRY(cudaStreamSynchronize(stream));
+    *error = c.error;
+    return RCN_OK;
 }
 
 template <int WORLD>   // 0 = runtime world size
-__global__ void __launch_bounds__(256) dp_allreduce_sgd_kernel(const DpPeers peers, int world_rt, int rank, size_t n,
-                                                               double* __restrict__ params, double* __restrict__ grads,
-                                                               double scale, long long* __restrict__ cursor, long long batch,
-                                                               long long n_samples, const double* __restrict__ stats,
-                                                               double* __restrict__ stats_ring, int already_pushed, int pipe) {
-    // programmatic dependent launch (no-ops unless the host asked for it): the next kernel's launch may proceed under this
-    // one; this one waits for the gradient kernel to complete before it touches global memory
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+__global__ void __launch_bounds__(kDpThreads, 1) dp_allreduce_sgd_kernel(const __grid_constant__ DpPush dp, double* __restrict__ params,
+                                                                          double* __restrict__ grads, double scale,
+                                                                          long long* __restrict__ cursor, long long batch,
+                                                                          long long n_samples, const double* __restrict__ stats,
+                                                                          double* __restrict__ stats_ring, int already_pushed) {
+    // programmatic dependent launch (no-ops unless the host asked for it): wait for the gradient kernel to complete, THEN
+    // let the next kernel's launch proceed under this one (its pre-wait part may rely on everything up to the gradient
+    // kernel being complete, see smallnet.cu)
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int world = WORLD ? WORLD : world_rt;
-    char* self = peers.p[rank];
-    DpCtrl* ctrl = reinterpret_cast<DpCtrl*>(self);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    RCN_TL_BEGIN(dp.tl, 2);
+    DpCtrl* ctrl = reinterpret_cast<DpCtrl*>(dp.peers[dp.rank]);
     const long long step = *reinterpret_cast<volatile long long*>(&ctrl->step) + 1;
-    const size_t par_off = (size_t)(step & 1) * world * n;
-    const int tid = threadIdx.x;
-    const size_t lo = (size_t)blockIdx.x * kDpChunk;
-    const size_t hi = lo + kDpChunk < n ? lo + kDpChunk : n;
-    constexpr int E = kDpChunk / 256;            // elements per thread
-    double g[E];
+    const size_t n = dp.n;
+    const size_t par_off = (size_t)(step & 1) * (WORLD ? WORLD : dp.world) * n;
+    const size_t stride = (size_t)gridDim.x * kDpThreads;
+    const size_t first = (size_t)blockIdx.x * kDpThreads + threadIdx.x;
     // ---- push my elements of the local gradient sums into my slot on every peer (stores travel over NVLink) ---------
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const size_t i = lo + tid + (size_t)e * 256;
-        g[e] = 0.0;
-        if (i < hi) {
-            g[e] = grads[i];
-            if (!already_pushed) {
-                unsigned long long bits = (unsigned long long)__double_as_longlong(g[e]);
-                if (bits == kDpSentinel) bits = kDpQuietNaN;          // a NaN either way; never send the sentinel itself
-                for (int q = 0; q < world; ++q)
-                    if (q != rank)
-                        reinterpret_cast<unsigned long long*>(peers.p[q] + kDpCtrlBytes)[par_off + (size_t)rank * n + i] = bits;
-            }
-        }
-    }
-    // ---- receive: poll my elements of every peer's slot in my own block, restore the sentinel, add in rank order ------
-    unsigned long long* slots = reinterpret_cast<unsigned long long*>(self + kDpCtrlBytes) + par_off;
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const size_t i = lo + tid + (size_t)e * 256;
-        if (i < hi) {
-            double s = 0.0;
-            for (int q = 0; q < world; ++q) {
-                double v;
-                if (q == rank) v = g[e];
-                else {
-                    unsigned long long* p = slots + (size_t)q * n + i;
-                    unsigned long long bits;
-                    while ((bits = ld_volatile_u64(p)) == kDpSentinel) { }
-                    *p = kDpSentinel;
-                    v = __longlong_as_double((long long)bits);
-                }
-                s = (q == 0) ? v : s + v;
-            }
-            grads[i] = s;                        // the gradient buffer ends up holding the global sum, like an all-reduce
-            params[i] = sgd_apply(params[i], scale, s);   // W -= (eta / B) * sum   (rcn.rs:214,221)
-        }
+    if (!already_pushed)
+        for (size_t i = first; i < n; i += stride) dp_push_value(dp, par_off, i, grads[i]);
+    // ---- receive: my elements of every peer's slot in my own block, sentinel restored, ranks added in rank order --------
+    for (size_t i = first; i < n; i += stride) {
+        const double pold = params[i];
+        const double s = dp_receive_sum<WORLD>(dp, par_off, i, grads[i]);
+        grads[i] = s;                            // the gradient buffer ends up holding the global sum, like an all-reduce
+        params[i] = sgd_apply(pold, scale, s);   // W -= (eta / B) * sum   (rcn.rs:214,221)
     }
     // ---- the last CTA to finish advances the device-side step counter (and the epoch cursor) ----------------------------
     __syncthreads();
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         __threadfence();
         const unsigned int t = atomicAdd(&ctrl->done_ctas, 1u);
         if (t == gridDim.x - 1) {
@@ -155,37 +138,37 @@ __global__ void __launch_bounds__(256) dp_allreduce_sgd_kernel(const DpPeers pee
                 long long cc = *cursor + batch;
                 if (cc + batch > n_samples) cc = 0;
                 *cursor = cc;
-                if (pipe) cursor[1] += 1;   // pipelined epoch mode: training steps done
             }
             __threadfence();
         }
     }
+    RCN_TL_END(dp.tl, 2);
 }
 
 int launch_dp_allreduce_sgd(const DpState& st, double* params, double* grads, double scale, cudaStream_t stream,
                             long long* cursor, long long batch, long long n_samples, const double* stats, double* stats_ring,
-                            bool already_pushed, bool pipe) {
+                            bool already_pushed, Timeline* tl) {
     if (!st.connected) return fail(RCN_ERR_STATE, "data-parallel group is not connected");
     if (st.n == 0) return RCN_OK;
-    DpPeers pp{};
-    for (int q = 0; q < st.world; ++q) pp.p[q] = (char*)st.peers[q];
-    const unsigned grid = (unsigned)st.n_chunks;
+    DpPush pp = dp_push_desc(st);
+    pp.tl = tl;
+    unsigned grid = cdiv(st.n, kDpThreads);
+    if (grid > (unsigned)kDpMaxCtas) grid = kDpMaxCtas;
     static const bool pdl = []() { const char* e = getenv("RCN_CUDA_PDL"); return !(e && e[0] == '0'); }();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid, 1, 1);
-    cfg.blockDim = dim3(256, 1, 1);
+    cfg.blockDim = dim3(kDpThreads, 1, 1);
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl ? 1 : 0;
-    const int world_i = st.world, rank_i = st.rank, pushed_i = already_pushed ? 1 : 0, pipe_i = pipe ? 1 : 0;
-    const size_t n_i = st.n;
+    const int pushed_i = already_pushed ? 1 : 0;
 #define RCN_DP_LAUNCH(W)                                                                                                       \
     RCN_LAUNCH("dp_allreduce_sgd_kernel", stream,                                                                              \
-               cudaLaunchKernelEx(&cfg, dp_allreduce_sgd_kernel<W>, pp, world_i, rank_i, n_i, params, grads, scale, cursor, batch, \
-                                  n_samples, stats, stats_ring, pushed_i, pipe_i))
+               cudaLaunchKernelEx(&cfg, dp_allreduce_sgd_kernel<W>, pp, params, grads, scale, cursor, batch, n_samples, stats,  \
+                                  stats_ring, pushed_i))
     switch (st.world) {
         case 2: RCN_DP_LAUNCH(2); break;
         case 4: RCN_DP_LAUNCH(4); break;

@@ -123,16 +123,7 @@ __global__ void __launch_bounds__(256) features_fused_kernel(const TIN* __restri
 template <int MODE>
 __global__ void __launch_bounds__(256) features_cp_kernel(const uint8_t* __restrict__ images, int B, int H, int W,
                                                          const __grid_constant__ CpPlan cp, double* __restrict__ out,
-                                                         size_t L, const Standardise sc, const BatchIndex bi_in, int bulk) {
-    BatchIndex bi = bi_in;
-    long long pipe_pos = 0, pipe_step = 0;
-    if (bi.pipe) {   // pipelined epoch mode: own cursor, output half by own step parity (see BatchIndex)
-        pipe_pos = __ldcg(bi.pipe + kEpFpos);
-        pipe_step = __ldcg(bi.pipe + kEpFstep);
-        bi.cursor = bi.pipe + kEpFpos;
-        out += (size_t)(pipe_step & 1) * (size_t)B * L;
-        bi.labels_batch = bi.pipe + kEpSlots + (pipe_step & 1) * (long long)B;
-    }
+                                                         size_t L, const Standardise sc, const BatchIndex bi, int bulk) {
     extern __shared__ __align__(128) unsigned char cp_smem[];
     __shared__ __align__(8) uint64_t bar[2];
     uint8_t* stg0 = cp_smem;
@@ -198,20 +189,6 @@ __global__ void __launch_bounds__(256) features_cp_kernel(const uint8_t* __restr
                 cp_item<true, false>(st, tiles + st.off, it, nullptr, 0, 0, sink);
         }
         __syncthreads();   // the next image's transpose reuses tile 0
-    }
-    if (bi.pipe) {   // the last CTA to finish advances the feature cursor and the step parity (every CTA has read them by then)
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            if (atomicAdd(reinterpret_cast<unsigned long long*>(bi.pipe + kEpFticket), 1ull) == gridDim.x - 1) {
-                bi.pipe[kEpFticket] = 0;
-                long long nxt = pipe_pos + bi.batch;
-                if (nxt + bi.batch > bi.n_samples) nxt = 0;
-                *reinterpret_cast<volatile long long*>(bi.pipe + kEpFpos) = nxt;
-                *reinterpret_cast<volatile long long*>(bi.pipe + kEpFstep) = pipe_step + 1;
-                __threadfence();
-            }
-        }
     }
 }
 

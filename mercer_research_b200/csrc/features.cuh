@@ -80,16 +80,12 @@ struct BatchIndex {
     // Streaming from a HOST dataset (rcn_cuda_train_epoch_host): `images` is a ring of `window` image slots and image
     // i of the walk lives in slot i % window (labels are still indexed by i).  0 = images hold the whole dataset.
     long long window = 0;
-    // Pipelined epoch mode (model.cu, kEp* slots): the feature kernel of step k+1 runs on a parallel branch while step k
-    // trains.  `pipe` is the epoch state block; the kernel then walks its OWN cursor pipe[kEpFpos], writes features and
-    // labels into the half selected by pipe[kEpFstep] & 1 and, as its last CTA, advances both (chunks_exact wrap-around
-    // with `batch` / `n_samples`).  nullptr: `cursor` / `labels_batch` above are used as they are.
-    long long* pipe = nullptr;
+    // Epoch mode: how the cursor advances after this step (chunks_exact wrap-around, rcn.rs:147) -- lets a kernel ask L2 for
+    // the NEXT step's images ahead of time.  0 = unknown (no prefetch).
     long long batch = 0, n_samples = 0;
 };
-// epoch state block (int64 slots): training cursor, training steps done, feature cursor, feature steps done, feature-kernel
-// ticket, the half kernel A read (for kernel B); the two label halves follow
-constexpr int kEpCursor = 0, kEpAstep = 1, kEpFpos = 2, kEpFstep = 3, kEpFticket = 4, kEpCurPar = 5, kEpSlots = 8;
+// epoch state block (int64 slots): the training cursor, padding; this step's labels follow
+constexpr int kEpCursor = 0, kEpSlots = 8;
 
 // Epilogue descriptor for a batch: picks the host-verified exact fast division when the input is u8.
 Standardise make_standardise(const FeaturePlan& plan, int pixel_format, bool standardise, double mean, double sd);

@@ -173,21 +173,20 @@ struct rcn_cuda_model {
     const int64_t* ep_perm = nullptr;
     int ep_fmt = 0;
     size_t ep_n = 0, ep_H = 0, ep_W = 0, ep_B = 0;
-    DevBuf ep_state;            // kEpSlots int64 state words (features.cuh: cursor, steps, feature cursor, ...) | labels_batch [2][B]
-    DevBuf ep_feats;            // pipelined epoch mode: [2][L x B] feature double buffer (never used as scratch by other calls)
-    bool pipe_step = false;     // the accumulate in flight is a pipelined epoch step (kernel B gets the state block)
-    bool ep_pipe = false;       // pipelined epoch mode: the feature kernel of step k+1 runs beside step k (double-buffered feats)
-    cudaEvent_t ep_fork = nullptr, ep_join = nullptr;
+    DevBuf ep_state;            // kEpSlots int64 state words (features.cuh: the cursor) | labels_batch [B]
     size_t last_B = 0;          // batch of the last accumulate call (taps)
     bool stats_valid = false;
     // data-parallel group (dp.cu) and the pipelined host-dataset loop (rcn_cuda_train_epoch_host)
     DpState dp;
-    DevBuf persist_ws;              // barrier counter + per-tile partials of the persistent step kernel
-    bool persist_failed = false;    // the cooperative launch was refused once: stay on the per-step kernels
     SnUpdate pending_upd{};         // set by the step entry points: the next small-network accumulate applies the update itself
     bool upd_fused = false;         // ... and did (the standalone update kernel is then skipped)
+    bool cursor_fused = false;      // ... or at least advanced the cursor / wrote the result ring (data-parallel groups)
+    bool x_owns_cursor = false;     // an exchange kernel that advances a cursor may be in flight: kernel A must not read the
+                                    // cursor ahead of its griddepcontrol.wait (cleared wherever the stream is drained)
     bool dp_pushed = false;         // the last accumulate pushed its gradients to the peers itself (kernel B epilogue)
     bool dp_push_suppress = false;  // warm-up launches must not push (a push is consumed by exactly one receive)
+    DevBuf timeline;                // device-side launch timeline (timeline.cuh), allocated by rcn_cuda_timeline_enable
+    bool tl_on = false;
     OzakiWorkspace oz;              // tcgen05 integer-slice GEMM scratch (wide dense layers)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
@@ -336,9 +335,9 @@ int accumulate_dev(rcn_cuda_model* h, const double* feats, const double* onehot,
         RCN_TRY(launch_smallnet_backprop(h->small_desc, h->params.as<double>(), const_cast<double*>(feats), B, onehot,
                                          labels, h->acts.as<double>(), h->deltas.as<double>(), h->grads,
                                          h->small.as<double>(), h->gemm_ws, front, h->stream, fuse_push ? &push : nullptr,
-                                         (upd.params && (!h->dp.connected || fuse_push)) ? &upd : nullptr,
-                                         h->pipe_step ? h->ep_state.as<long long>() : nullptr, h->pipe_step ? h->ep_fork : nullptr));
+                                         ((upd.params || upd.cursor) && (!h->dp.connected || fuse_push)) ? &upd : nullptr));
         h->upd_fused = upd.params && (!h->dp.connected || fuse_push);
+        h->cursor_fused = upd.cursor && (!h->dp.connected || fuse_push);
         h->dp_pushed = fuse_push && !h->upd_fused;   // pushed but not yet received: the exchange kernel must follow
         h->stats_valid = true;
         h->last_B = B;
@@ -379,6 +378,14 @@ int accumulate_images_dev(rcn_cuda_model* h, const void* images, int fmt, const 
         fr.sc = make_standardise(h->plan, fmt, true, h->mean, h->sd);
         if (bi) fr.bi = *bi;
         smallnet_front_select(h->plan, &fr);
+        // Data-parallel step behind the exchange kernel: kernel A may run its front end ahead of griddepcontrol.wait
+        // (smallnet.cu) when this step's kernel B pushes to the peers (so the exchange kernel X precedes the next kernel
+        // A), the update is not folded into kernel B, and any device-side cursor it reads is advanced by kernel B -- this
+        // step's and the previous one's (x_owns_cursor) -- not by X, which may still be running then.
+        static const bool prewait_env = []() { const char* e = getenv("RCN_CUDA_DP_PREWAIT"); return !(e && e[0] == '0'); }();
+        const bool fuse_push = h->dp.connected && dp_fused_push_enabled() && !h->dp_push_suppress;
+        fr.prewait = (prewait_env && fr.use_cp && fuse_push && !h->pending_upd.params && !h->x_owns_cursor &&
+                      (!fr.bi.cursor || h->pending_upd.cursor == fr.bi.cursor)) ? 1 : 0;
         if (smallnet_front_fits(h->small_desc, fr))
             return accumulate_dev(h, h->feats.as<double>(), nullptr, step_labels, B, &fr);
     }
@@ -467,11 +474,9 @@ int rcn_cuda_destroy(rcn_cuda_handle h) {
     if (h->stats_host) cudaFreeHost(h->stats_host);
     if (h->hs_graph) cudaGraphExecDestroy(h->hs_graph);
     if (h->hs_graph1) cudaGraphExecDestroy(h->hs_graph1);
-    if (h->ep_fork) cudaEventDestroy(h->ep_fork);
-    if (h->ep_join) cudaEventDestroy(h->ep_join);
     if (h->hs_fork) cudaEventDestroy(h->hs_fork);
     if (h->hs_join) cudaEventDestroy(h->hs_join);
-    h->hs_ring.release(); h->hs_state.release(); h->persist_ws.release(); h->ep_feats.release();
+    h->hs_ring.release(); h->hs_state.release(); 
     dp_release(h->dp);
     h->oz.release();
     DevBuf* bufs[] = {&h->params, &h->grads_own, &h->in_stage, &h->tgt_stage, &h->feats, &h->acts, &h->deltas,
@@ -487,9 +492,12 @@ int rcn_cuda_set_stream(rcn_cuda_handle h, void* cuda_stream) {
     return RCN_OK;
 }
 
+static void stream_drained(rcn_cuda_model* h);
+
 int rcn_cuda_synchronize(rcn_cuda_handle h) {
     RCN_ENTER(h);
     RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    stream_drained(h);
     return RCN_OK;
 }
 
@@ -528,7 +536,7 @@ int install_shapes(rcn_cuda_model* h, const std::vector<size_t>& rows, const std
             for (size_t i = 0; i < n; ++i) { d.rows[i] = (int)h->rows[i]; d.w_off[i] = (int)h->w_off[i]; d.b_off[i] = (int)h->b_off[i]; }
             bool ok = true;
             for (size_t i = 0; i < n; ++i) ok = ok && h->rows[i] <= 32;
-            if (ok && smallnet_eligible(d)) { h->small_desc = d; h->use_small = true; }
+            if (ok && smallnet_eligible(d)) { h->small_desc = d; h->small_desc.tl = h->tl_on ? h->timeline.as<Timeline>() : nullptr; h->use_small = true; }
         }
     }
     RCN_TRY(h->params.reserve(off * sizeof(double)));
@@ -656,13 +664,9 @@ int rcn_cuda_get_params(rcn_cuda_handle h, double* flat, size_t n) {
     return deliver(h, flat, h->params.p, n * sizeof(double));
 }
 
-static int epoch_reprime(rcn_cuda_model* h);   // pipelined epoch mode: prefetched features depend on (mean, sd)
-
 int rcn_cuda_set_scale(rcn_cuda_handle h, double mean, double sd) {
     RCN_ENTER(h);
-    const bool changed = mean != h->mean || sd != h->sd;
     h->mean = mean; h->sd = sd;
-    if (changed && h->ep_pipe && h->ep_images) return epoch_reprime(h);
     return RCN_OK;
 }
 
@@ -699,11 +703,9 @@ int rcn_cuda_gen_scales(rcn_cuda_handle h, const double* feats, size_t L, size_t
     double host[2];
     RCN_CUDA_TRY(cudaMemcpyAsync(host, res, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
     RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    const bool changed = host[0] != h->mean || host[1] != h->sd;
     h->mean = host[0]; h->sd = host[1];  // self.scale_set = (mean, sd)  (rcn.rs:249-250)
     if (mean) *mean = host[0];
     if (sd) *sd = host[1];
-    if (changed && h->ep_pipe && h->ep_images) return epoch_reprime(h);
     return RCN_OK;
 }
 
@@ -836,9 +838,12 @@ int rcn_cuda_apply_gradients(rcn_cuda_handle h, double eta, size_t batch) {
     const double scale = eta / (double)batch;  // (eta / batch.len() as f64)  (rcn.rs:214)
     if (h->dp.connected)   // exchange over NVLink peer memory fused with the update (dp.cu)
         return launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale, h->stream, nullptr, 0, 0, nullptr, nullptr,
-                                       take_dp_pushed(h));
+                                       take_dp_pushed(h), h->small_desc.tl);
     return launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale, h->stream);
 }
+
+// Every entry point that drains the model's stream ends the hazard x_owns_cursor guards against.
+static void stream_drained(rcn_cuda_model* h) { h->x_owns_cursor = false; }
 
 // Single-GPU steps of the fused small-network path let the weight-gradient kernel apply the update (SnUpdate): arm it
 // before the accumulate; if that accumulate took another path the standalone update kernel runs as before.
@@ -849,20 +854,22 @@ static void arm_fused_update(rcn_cuda_model* h, double scale, long long* cursor,
     if (!on || !h || !h->params_ready || !h->use_small) return;
     // Data-parallel groups: receiving inside the weight-gradient kernel (MODE 3) was measured SLOWER than the separate
     // exchange kernel (2 GPUs, c2: 30.8 vs 28.4 us/step) -- the NVLink round trip is then exposed inside the kernel
-    // instead of overlapping the next launch -- so it is opt-in (RCN_CUDA_DP_FUSED_UPDATE=1).
+    // instead of overlapping the next launch -- so it is opt-in (RCN_CUDA_DP_FUSED_UPDATE=1).  By default kernel B only
+    // takes over the cursor / result ring there (params stays null) and the exchange kernel applies the update.
     static const bool dp_on = []() { const char* e = getenv("RCN_CUDA_DP_FUSED_UPDATE"); return e && e[0] == '1'; }();
-    if (h->dp.connected && (!dp_on || !dp_fused_push_enabled() || h->dp_push_suppress)) return;
-    h->pending_upd.params = h->params.as<double>();
+    if (h->dp.connected && (!dp_fused_push_enabled() || h->dp_push_suppress)) return;
+    if (!h->dp.connected || dp_on) h->pending_upd.params = h->params.as<double>();
     h->pending_upd.scale = scale;
     h->pending_upd.cursor = cursor;
     h->pending_upd.batch = batch;
     h->pending_upd.n_samples = n_samples;
     h->pending_upd.stats_ring = stats_ring;
-    h->pending_upd.pipe = (cursor && cursor == h->ep_state.as<long long>() && h->ep_pipe) ? 1 : 0;
 }
-static bool take_upd_fused(rcn_cuda_model* h) {
-    const bool f = h->upd_fused;
+// What the accumulate did with the armed update: bit 0 = parameters updated, bit 1 = cursor advanced / result ring written.
+static int take_upd_fused(rcn_cuda_model* h) {
+    const int f = (h->upd_fused ? 1 : 0) | (h->cursor_fused ? 2 : 0);
     h->upd_fused = false;
+    h->cursor_fused = false;
     h->pending_upd = SnUpdate{};
     return f;
 }
@@ -874,7 +881,7 @@ int rcn_cuda_train_batch(rcn_cuda_handle h, const double* feats, const double* o
     if (h && B) arm_fused_update(h, eta / (double)global, nullptr, 0, 0, nullptr);
     const int rc = rcn_cuda_accumulate_gradients(h, feats, onehot, labels, B);
     if (rc != RCN_OK) { if (h) take_upd_fused(h); return rc; }
-    if (take_upd_fused(h)) return RCN_OK;
+    if (take_upd_fused(h) & 1) return RCN_OK;
     return rcn_cuda_apply_gradients(h, eta, global);
 }
 
@@ -884,7 +891,7 @@ int rcn_cuda_train_batch_images(rcn_cuda_handle h, const void* images, int pixel
     if (h && B) arm_fused_update(h, eta / (double)global, nullptr, 0, 0, nullptr);
     const int rc = rcn_cuda_accumulate_gradients_images(h, images, pixel_format, labels, B, H, W);
     if (rc != RCN_OK) { if (h) take_upd_fused(h); return rc; }
-    if (take_upd_fused(h)) return RCN_OK;
+    if (take_upd_fused(h) & 1) return RCN_OK;
     return rcn_cuda_apply_gradients(h, eta, global);
 }
 
@@ -899,59 +906,7 @@ int rcn_cuda_last_batch_stats(rcn_cuda_handle h, double* cost, uint64_t* hits) {
     return RCN_OK;
 }
 
-// ---- pipelined epoch mode ---------------------------------------------------------------------------------------------
-// The convpool front end of a step does not depend on the parameters, only on which images come next.  With a bound
-// device dataset, the canonical narrow network and u8 images the feature kernel of step k+1 therefore runs on a PARALLEL
-// branch (own stream, own device-side cursor) while kernels A and B of step k train; kernel A drops its front end and
-// reads the features / labels of its step from the half of a double buffer selected by a device-side step counter
-// (the branch forks after kernel A, so the feature kernel shares the machine with kernel B's small CTAs).  The
-// invariant "half (steps done & 1) holds the features of the batch at the cursor" is (re-)established by epoch_prime
-// after every bind / seek / scale change, so eager calls and replayed CUDA graphs of any length can be mixed freely.
-static bool epoch_pipe_eligible(rcn_cuda_model* h) {
-    // Opt-in (RCN_CUDA_EPOCH_PIPELINE=1, read at every bind): measured on c2 the cross-stream fork / join inside the step graph
-    // and the contention for SMs cost more than the hidden front end saves (26.2 us/step with the feature kernel beside
-    // kernel A, 26.9 us beside kernel B only, against 20.5 us for the fused kernel A).
-    const char* env = getenv("RCN_CUDA_EPOCH_PIPELINE");
-    const bool on = env && env[0] == '1';
-    const char* staged = getenv("RCN_CUDA_FEATURES_STAGED");
-    if (!on || (staged && staged[0] == '0') || !h->use_small || h->ep_fmt != RCN_PIXELS_U8_ROWMAJOR || h->plan.L == 0 || h->plan.n_conv > 10) return false;
-    if (h->ep_B > smallnet_max_batch() || (reinterpret_cast<uintptr_t>(h->ep_images) & 15) != 0 || (h->ep_H * h->ep_W) % 16 != 0) return false;
-    CpPlan cp;
-    return make_cp_plan(h->plan, h->ep_H, h->ep_W, &cp);   // the staged feature kernel implements the pipe protocol
-}
-
-static BatchIndex epoch_pipe_index(rcn_cuda_model* h) {
-    BatchIndex bi;
-    bi.cursor = h->ep_state.as<long long>() + kEpFpos;
-    bi.perm = (const long long*)h->ep_perm;
-    bi.labels_all = (const long long*)h->ep_labels;
-    bi.labels_batch = h->ep_state.as<long long>() + kEpSlots;
-    bi.pipe = h->ep_state.as<long long>();
-    bi.batch = (long long)h->ep_B;
-    bi.n_samples = (long long)h->ep_n;
-    return bi;
-}
-
-// state <- {cursor = pos, 0 steps done, feature cursor = pos, 0 feature steps}; then one feature launch on the model's
-// stream fills half 0 and moves the feature cursor one chunk ahead
-static int epoch_prime(rcn_cuda_model* h, long long pos) {
-    long long init[kEpSlots] = {};
-    init[kEpCursor] = pos;
-    init[kEpFpos] = pos;
-    RCN_CUDA_TRY(cudaMemcpyAsync(h->ep_state.p, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
-    RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));   // `init` lives on this stack frame
-    const BatchIndex bi = epoch_pipe_index(h);
-    return launch_features(h->plan, h->ep_images, h->ep_fmt, h->ep_B, h->ep_H, h->ep_W, true, h->mean, h->sd, h->ep_feats.as<double>(),
-                           h->fscratch, h->stream, &bi);
-}
-
-static int epoch_reprime(rcn_cuda_model* h) {
-    long long pos = 0;
-    RCN_CUDA_TRY(cudaMemcpyAsync(&pos, h->ep_state.p, sizeof(pos), cudaMemcpyDeviceToHost, h->stream));
-    RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return epoch_prime(h, pos);
-}
-
+// ---- epoch mode: rcn.rs:144-149 over a dataset resident in device memory ---------------------------------------------
 int rcn_cuda_epoch_bind(rcn_cuda_handle h, const void* images, int pixel_format, const int64_t* labels,
                         const int64_t* perm, size_t n_samples, size_t H, size_t W, size_t B) {
     RCN_ENTER(h);
@@ -963,16 +918,13 @@ int rcn_cuda_epoch_bind(rcn_cuda_handle h, const void* images, int pixel_format,
         return fail(RCN_ERR_INVALID, "unknown pixel format %d", pixel_format);
     RCN_TRY(ensure_plan(h, H, W));
     RCN_TRY(check_feature_width(h, h->plan.L));
-    RCN_TRY(h->ep_state.reserve((kEpSlots + 2 * B) * sizeof(int64_t)));
-    RCN_CUDA_TRY(cudaMemsetAsync(h->ep_state.p, 0, (kEpSlots + 2 * B) * sizeof(int64_t), h->stream));
+    RCN_TRY(h->ep_state.reserve((kEpSlots + B) * sizeof(int64_t)));
+    RCN_CUDA_TRY(cudaMemsetAsync(h->ep_state.p, 0, (kEpSlots + B) * sizeof(int64_t), h->stream));
     RCN_TRY(h->feats.reserve(h->plan.L * B * sizeof(double)));
     h->ep_images = images; h->ep_labels = labels; h->ep_perm = perm; h->ep_fmt = pixel_format;
     h->ep_n = n_samples; h->ep_H = H; h->ep_W = W; h->ep_B = B;
-    h->ep_pipe = epoch_pipe_eligible(h);
-    if (h->ep_pipe) {
-        RCN_TRY(h->ep_feats.reserve(2 * h->plan.L * B * sizeof(double)));
-        RCN_TRY(epoch_prime(h, 0));
-    }
+    RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));   // the cursor is zero before any step kernel can look at it
+    stream_drained(h);
     return RCN_OK;
 }
 
@@ -981,9 +933,9 @@ int rcn_cuda_epoch_seek(rcn_cuda_handle h, size_t position) {
     if (!h->ep_images) return fail(RCN_ERR_STATE, "no dataset bound: call rcn_cuda_epoch_bind first");
     if (position + h->ep_B > h->ep_n) return fail(RCN_ERR_INVALID, "position %zu leaves fewer than B samples", position);
     const long long pos = (long long)position;
-    if (h->ep_pipe) return epoch_prime(h, pos);   // also recomputes the prefetched features (new perm / position)
     RCN_CUDA_TRY(cudaMemcpyAsync(h->ep_state.p, &pos, sizeof(pos), cudaMemcpyHostToDevice, h->stream));
     RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    stream_drained(h);
     return RCN_OK;
 }
 
@@ -993,6 +945,7 @@ int rcn_cuda_epoch_position(rcn_cuda_handle h, size_t* position) {
     long long pos = 0;
     RCN_CUDA_TRY(cudaMemcpyAsync(&pos, h->ep_state.p, sizeof(pos), cudaMemcpyDeviceToHost, h->stream));
     RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    stream_drained(h);
     *position = (size_t)pos;
     return RCN_OK;
 }
@@ -1001,50 +954,34 @@ int rcn_cuda_epoch_accumulate(rcn_cuda_handle h) {
     RCN_ENTER(h);
     RCN_TRY(require_params(h));
     if (!h->ep_images) return fail(RCN_ERR_STATE, "no dataset bound: call rcn_cuda_epoch_bind first");
-    if (h->ep_pipe) {
-        // fork: the feature kernel of the NEXT step on a parallel branch (own cursor, other half of the double buffer)
-        if (!h->copy_stream) RCN_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        if (!h->ep_fork) {
-            RCN_CUDA_TRY(cudaEventCreateWithFlags(&h->ep_fork, cudaEventDisableTiming));
-            RCN_CUDA_TRY(cudaEventCreateWithFlags(&h->ep_join, cudaEventDisableTiming));
-        }
-        // this step: kernels A (no front end) and B on the half the step counter selects; ep_fork is recorded between them
-        SmallNetFront fr{};
-        fr.pipe_only = 1;
-        fr.bi.pipe = h->ep_state.as<long long>();
-        h->pipe_step = true;
-        const int rc = accumulate_dev(h, h->ep_feats.as<double>(), nullptr, nullptr, h->ep_B, &fr);
-        h->pipe_step = false;
-        RCN_TRY(rc);
-        // fork after kernel A: the feature kernel of the NEXT step shares the machine with kernel B (small CTAs on both sides;
-        // beside kernel A, whose CTAs need a whole SM each, it was measured to delay the step instead)
-        RCN_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ep_fork, 0));
-        const BatchIndex fbi = epoch_pipe_index(h);
-        RCN_TRY(launch_features(h->plan, h->ep_images, h->ep_fmt, h->ep_B, h->ep_H, h->ep_W, true, h->mean, h->sd,
-                                h->ep_feats.as<double>(), h->fscratch, h->copy_stream, &fbi));
-        RCN_CUDA_TRY(cudaEventRecord(h->ep_join, h->copy_stream));
-        RCN_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ep_join, 0));   // join: the next step's kernel A needs those features
-        return RCN_OK;
-    }
     BatchIndex bi;
     bi.cursor = h->ep_state.as<long long>();
     bi.perm = (const long long*)h->ep_perm;
     bi.labels_all = (const long long*)h->ep_labels;
     bi.labels_batch = h->ep_state.as<long long>() + kEpSlots;
+    bi.batch = (long long)h->ep_B;
+    bi.n_samples = (long long)h->ep_n;
     return accumulate_images_dev(h, h->ep_images, h->ep_fmt, nullptr, h->ep_B, h->ep_H, h->ep_W, &bi);
+}
+
+static int epoch_apply_impl(rcn_cuda_model* h, double eta, size_t global_batch, bool cursor_done) {
+    if (global_batch == 0) return fail(RCN_ERR_INVALID, "global batch is zero");
+    const double scale = eta / (double)global_batch;
+    long long* cursor = cursor_done ? nullptr : h->ep_state.as<long long>();   // kernel B already advanced it
+    if (h->dp.connected) {
+        if (cursor) h->x_owns_cursor = true;
+        return launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale, h->stream, cursor, (long long)h->ep_B,
+                                       (long long)h->ep_n, nullptr, nullptr, take_dp_pushed(h), h->small_desc.tl);
+    }
+    return launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale, h->stream, cursor, (long long)h->ep_B,
+                             (long long)h->ep_n, nullptr, nullptr);
 }
 
 int rcn_cuda_epoch_apply(rcn_cuda_handle h, double eta, size_t global_batch) {
     RCN_ENTER(h);
     RCN_TRY(require_params(h));
     if (!h->ep_images) return fail(RCN_ERR_STATE, "no dataset bound: call rcn_cuda_epoch_bind first");
-    if (global_batch == 0) return fail(RCN_ERR_INVALID, "global batch is zero");
-    const double scale = eta / (double)global_batch;
-    if (h->dp.connected)
-        return launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale, h->stream, h->ep_state.as<long long>(),
-                                       (long long)h->ep_B, (long long)h->ep_n, nullptr, nullptr, take_dp_pushed(h), h->ep_pipe);
-    return launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale, h->stream, h->ep_state.as<long long>(),
-                             (long long)h->ep_B, (long long)h->ep_n, nullptr, nullptr, h->ep_pipe);
+    return epoch_apply_impl(h, eta, global_batch, false);
 }
 
 int rcn_cuda_epoch_step(rcn_cuda_handle h, double eta) {
@@ -1053,56 +990,17 @@ int rcn_cuda_epoch_step(rcn_cuda_handle h, double eta) {
         arm_fused_update(h, eta / (double)global, h->ep_state.as<long long>(), (long long)h->ep_B, (long long)h->ep_n, nullptr);
     const int rc = rcn_cuda_epoch_accumulate(h);
     if (rc != RCN_OK) { if (h) take_upd_fused(h); return rc; }
-    if (take_upd_fused(h)) return RCN_OK;
-    return rcn_cuda_epoch_apply(h, eta, global);
+    const int fused = take_upd_fused(h);
+    if (fused & 1) return RCN_OK;
+    RCN_ENTER(h);
+    return epoch_apply_impl(h, eta, global, (fused & 2) != 0);
 }
 
 int rcn_cuda_epoch_run(rcn_cuda_handle h, double eta, size_t n_steps) {
     RCN_ENTER(h);
     RCN_TRY(require_params(h));
     if (!h->ep_images) return fail(RCN_ERR_STATE, "no dataset bound: call rcn_cuda_epoch_bind first");
-    if (n_steps == 0) return RCN_OK;
     if (n_steps > (size_t)1 << 30) return fail(RCN_ERR_INVALID, "too many steps in one call");
-    const size_t B = h->ep_B;
-    if (h->use_small && !h->ep_pipe && !h->dp.connected && !h->persist_failed && h->ep_fmt == RCN_PIXELS_U8_ROWMAJOR && h->plan.L > 0 &&
-        h->plan.n_conv <= 10 && B <= smallnet_max_batch()) {
-        if (h->dp_pushed) return fail(RCN_ERR_STATE, "data-parallel group: pushed gradients were never applied");
-        SmallNetFront fr{};
-        fr.images = (const uint8_t*)h->ep_images;
-        fr.H = (int)h->ep_H; fr.W = (int)h->ep_W;
-        fr.max_elems = (int)h->plan.max_elems;
-        fr.stages = h->plan.stages;
-        fr.sc = make_standardise(h->plan, h->ep_fmt, true, h->mean, h->sd);
-        fr.bi.cursor = h->ep_state.as<long long>();
-        fr.bi.perm = (const long long*)h->ep_perm;
-        fr.bi.labels_all = (const long long*)h->ep_labels;
-        fr.bi.labels_batch = h->ep_state.as<long long>() + kEpSlots;
-        smallnet_front_select(h->plan, &fr);
-        if (smallnet_persistent_eligible(h->small_desc, fr, B)) {
-            RCN_TRY(h->feats.reserve(h->plan.L * B * sizeof(double)));
-            RCN_TRY(h->acts.reserve(h->sum_rows * B * sizeof(double)));
-            RCN_TRY(h->deltas.reserve(h->sum_rows * B * sizeof(double)));
-            RCN_TRY(h->small.reserve(64));
-            SnUpdate upd{};
-            upd.params = h->params.as<double>();
-            upd.scale = eta / (double)B;                 // (eta / batch.len() as f64)  (rcn.rs:214)
-            upd.cursor = h->ep_state.as<long long>();
-            upd.batch = (long long)B;
-            upd.n_samples = (long long)h->ep_n;
-            const int rc = launch_smallnet_persistent(h->small_desc, h->params.as<double>(), h->feats.as<double>(), B,
-                                                      h->acts.as<double>(), h->deltas.as<double>(), h->grads, h->small.as<double>(),
-                                                      h->persist_ws, fr, upd, (int)n_steps, h->stream);
-            if (rc == RCN_OK) {
-                h->stats_valid = true;
-                h->last_B = B;
-                return RCN_OK;
-            }
-            // e.g. the cooperative launch does not fit this device partition: never try again, take the per-step path
-            if (getenv("RCN_CUDA_DEBUG")) fprintf(stderr, "[rcn_cuda] persistent launch refused: %s\n", rcn_cuda_last_error());
-            h->persist_failed = true;
-            cudaGetLastError();
-        }
-    }
     for (size_t k = 0; k < n_steps; ++k) RCN_TRY(rcn_cuda_epoch_step(h, eta));
     return RCN_OK;
 }
@@ -1127,7 +1025,7 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
     if (global_batch == 0) global_batch = B * (size_t)(h->dp.connected ? h->dp.world : 1);
     const size_t img_bytes = B * H * W * pixel_bytes(pixel_format);
     if (!h->copy_stream) RCN_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    if (!h->hs_fork) {   // (the stream may already exist: the pipelined epoch mode shares it)
+    if (!h->hs_fork) {
         for (int i = 0; i < 2; ++i) {
             RCN_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
             RCN_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming));
@@ -1213,17 +1111,28 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
                         if (cudaEventRecord(h->hs_join, h->copy_stream) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph join failed"); break; }
                         arm_fused_update(h, scale_s, st, (long long)B, kHsNoWrap, h->stats_host);
                         rc = accumulate_images_dev(h, h->hs_ring.p, pixel_format, nullptr, B, H, W, &bi);
-                        const bool fused = take_upd_fused(h);
+                        const int fused = take_upd_fused(h);
                         if (rc != RCN_OK) break;
-                        // the prefetch branch joins at the end of its step: the next step starts after both
-                        if (cudaStreamWaitEvent(h->stream, h->hs_join, 0) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph join failed"); break; }
-                        if (fused) continue;   // the weight-gradient kernel applied the update, advanced the cursor, wrote the result
-                        if (h->dp.connected)
-                            rc = launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale_s, h->stream, st, (long long)B,
-                                                         kHsNoWrap, h->small.as<double>(), h->stats_host, take_dp_pushed(h));
-                        else
-                            rc = launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale_s, h->stream, st, (long long)B,
+                        if (fused & 1) {   // the weight-gradient kernel applied the update, advanced the cursor, wrote the result
+                            // the prefetch branch joins at the end of its step: the next step starts after both
+                            if (cudaStreamWaitEvent(h->stream, h->hs_join, 0) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph join failed"); break; }
+                            continue;
+                        }
+                        // (fused & 2: kernel B advanced the cursor and wrote the result; the update kernel gets no cursor)
+                        long long* cur = (fused & 2) ? nullptr : st;
+                        if (h->dp.connected) {
+                            if (cur) h->x_owns_cursor = true;
+                            rc = launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale_s, h->stream, cur, (long long)B,
+                                                         kHsNoWrap, h->small.as<double>(), h->stats_host, take_dp_pushed(h), h->small_desc.tl);
+                        } else {
+                            rc = launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale_s, h->stream, cur, (long long)B,
                                                    kHsNoWrap, h->small.as<double>(), h->stats_host);
+                        }
+                        if (rc != RCN_OK) break;
+                        // the prefetch branch joins AFTER the exchange / update kernel was enqueued: the next step's kernel A
+                        // then directly follows that kernel in the stream (its programmatic dependent) and also waits for
+                        // the prefetched chunk
+                        if (cudaStreamWaitEvent(h->stream, h->hs_join, 0) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph join failed"); break; }
                     }
                     cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
                     if (rc != RCN_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
@@ -1246,6 +1155,7 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
             }
             g_launches.fetch_add((unsigned long long)n_steps * (h->dp.connected ? 4 : 3), std::memory_order_relaxed);   // prefetch + A + B (+ exchange/update) per replay
             RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+            stream_drained(h);
             for (size_t k = 0; k < n_steps; ++k) {
                 if (cost_out) cost_out[k] = h->stats_host[2 * k];
                 if (hits_out) memcpy(&hits_out[k], &h->stats_host[2 * k + 1], sizeof(uint64_t));
@@ -1279,7 +1189,7 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
         RCN_CUDA_TRY(cudaEventRecord(h->ev_consumed[slot], h->stream));
         if (h->dp.connected)
             RCN_TRY(launch_dp_allreduce_sgd(h->dp, h->params.as<double>(), h->grads, scale, h->stream, nullptr, 0, 0, nullptr, nullptr,
-                                            take_dp_pushed(h)));
+                                            take_dp_pushed(h), h->small_desc.tl));
         else
             RCN_TRY(launch_sgd_update(h->params.as<double>(), h->grads, h->n_params, scale, h->stream));
         // D2H of this step's result (cost, hits evaluated with the pre-update parameters)
@@ -1353,8 +1263,58 @@ int rcn_cuda_dp_connect_local(rcn_cuda_handle h, const rcn_cuda_handle* group) {
 int rcn_cuda_dp_shutdown(rcn_cuda_handle h) {
     RCN_ENTER(h);
     RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    stream_drained(h);
     dp_release(h->dp);
     h->dp_pushed = false;
+    return RCN_OK;
+}
+
+static int timeline_reset(rcn_cuda_model* h) {
+    static Timeline init;   // 4.3 KB: too large for the stack of a small thread
+    memset(&init, 0, sizeof(init));
+    memset(init.t0, 0xff, sizeof(init.t0));
+    RCN_CUDA_TRY(cudaMemcpyAsync(h->timeline.p, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+    RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return RCN_OK;
+}
+
+int rcn_cuda_timeline_enable(rcn_cuda_handle h, int on) {
+    RCN_ENTER(h);
+    RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    stream_drained(h);
+    if (on) {
+        RCN_TRY(h->timeline.reserve(sizeof(Timeline)));
+        RCN_TRY(timeline_reset(h));
+    }
+    if ((on != 0) != h->tl_on) alloc_generation().fetch_add(1, std::memory_order_relaxed);   // captured steps hold the pointer by value
+    h->tl_on = on != 0;
+    h->small_desc.tl = h->tl_on ? h->timeline.as<Timeline>() : nullptr;
+    return RCN_OK;
+}
+
+int rcn_cuda_timeline_read(rcn_cuda_handle h, uint64_t* stamps, uint32_t* launches) {
+    RCN_ENTER(h);
+    if (!h->tl_on) return fail(RCN_ERR_STATE, "the timeline is not enabled");
+    if (!stamps || !launches) return fail(RCN_ERR_INVALID, "null output");
+    static Timeline host;
+    RCN_CUDA_TRY(cudaMemcpyAsync(&host, h->timeline.p, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+    RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    stream_drained(h);
+    memcpy(stamps, host.t0, sizeof(host.t0));
+    memcpy(stamps + kTlKernels * kTlRing, host.t1, sizeof(host.t1));
+    for (int k = 0; k < kTlKernels; ++k) launches[k] = host.seq[k];
+    return RCN_OK;
+}
+
+int rcn_cuda_dp_error(rcn_cuda_handle h, int* error) {
+    RCN_ENTER(h);
+    if (!error) return fail(RCN_ERR_INVALID, "null output");
+    unsigned e = 0;
+    RCN_TRY(dp_read_error(h->dp, h->stream, &e));
+    stream_drained(h);
+    *error = (int)e;
+    if (e) return fail(RCN_ERR_STATE, "data-parallel group: a gradient exchange timed out waiting for a peer (a rank died, raised before "
+                                      "its launch, or ran a different number of steps); the parameters of this replica are NaN");
     return RCN_OK;
 }
 

@@ -39,12 +39,26 @@ __device__ __forceinline__ void slice6(double x, double inv, int8_t (&q)[OZ_S]) 
 }
 
 // row scale from the row maximum: amax = f * 2^e, f in [0.5, 1)  =>  |x| * 2^-e < 1
+// A row that holds a NaN / Inf (amax arrives as NaN, see amax_fold) or a magnitude the digit scaling cannot represent gets
+// all-zero planes and scale = NaN: the epilogue's `acc * scale_a * scale_b` then yields NaN for every output that row
+// touches, like the f64 DMMA / SIMT paths and the reference (NaN * x = NaN), instead of a silently finite result.
 __device__ __forceinline__ void row_scale(double amax, double& inv, double& scale) {
-    if (!(amax > 1e-290) || !(amax < 1e290)) { inv = 0.0; scale = 0.0; return; }   // zero / denormal / non-finite row: all-zero planes
+    if (!(amax < 1e290)) { inv = 0.0; scale = __longlong_as_double(0x7FF8000000000000ll); return; }   // NaN / Inf / overflow-range row
+    if (!(amax > 1e-290)) { inv = 0.0; scale = 0.0; return; }                                          // zero / denormal row: all-zero planes
     int e;
     frexp(amax, &e);
     inv = ldexp(1.0, 6 - e);
     scale = ldexp(1.0, e - 6);
+}
+
+// Row-maximum accumulation that does not lose non-finite values: fmax() drops NaN operands, so a NaN or Inf element turns
+// the running maximum into +Inf (sticky under fmax); amax_finish() maps that to NaN for row_scale.
+__device__ __forceinline__ double amax_fold(double amax, double v) {
+    const double a = fabs(v);
+    return (a <= 1.7976931348623157e308) ? fmax(amax, a) : __longlong_as_double(0x7FF0000000000000ll);
+}
+__device__ __forceinline__ double amax_finish(double amax) {
+    return (amax <= 1.7976931348623157e308) ? amax : __longlong_as_double(0x7FF8000000000000ll);
 }
 
 // One row of a k-contiguous operand: a strided matrix row, or the im2col row of one grid pixel (gathered, zero padded).
@@ -81,11 +95,11 @@ __global__ void __launch_bounds__(256) ozaki_slice_kmajor_kernel(const OzOperand
     if (r >= R) return;
     const RowReader row(op, r);
     double amax = 0.0;
-    for (int k = lane; k < K; k += 32) amax = fmax(amax, fabs(row.at(k)));
+    for (int k = lane; k < K; k += 32) amax = amax_fold(amax, row.at(k));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));   // +Inf marks a non-finite element
     double inv, sc;
-    row_scale(amax, inv, sc);
+    row_scale(amax_finish(amax), inv, sc);
     if (lane == 0) scale[r] = sc;
     const size_t plane = (size_t)R * Kp;
     for (int k4 = lane * 4; k4 < Kp; k4 += 128) {
@@ -153,16 +167,16 @@ __global__ void __launch_bounds__(256) ozaki_amax_rmajor_kernel(const OzOperand 
 #pragma unroll
             for (int u = 0; u < 8; ++u) v[u] = (k + 8 * u < k_hi) ? col.at(k + 8 * u) : 0.0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) amax = fmax(amax, fabs(v[u]));
+            for (int u = 0; u < 8; ++u) amax = amax_fold(amax, v[u]);
         }
     }
     red[warp][lane] = amax;
     __syncthreads();
     if (warp == 0 && r < R) {
 #pragma unroll
-        for (int w = 1; w < 8; ++w) amax = fmax(amax, red[w][lane]);
-        if (amax == amax) atomicMax(amax_bits + r, (unsigned long long)__double_as_longlong(amax));
-        else atomicMax(amax_bits + r, 0x7FF8000000000000ull);    // NaN poisons the row (row_scale zeroes it)
+        for (int w = 1; w < 8; ++w) amax = fmax(amax, red[w][lane]);   // +Inf (a non-finite element) is sticky
+        // bit order == value order for |x| >= 0; the quiet-NaN pattern sorts above +Inf, so it poisons the row for good
+        atomicMax(amax_bits + r, (unsigned long long)__double_as_longlong(amax_finish(amax)));
     }
 }
 
@@ -220,13 +234,10 @@ __global__ void __launch_bounds__(256) ozaki_slice_rmajor_kernel(const OzOperand
 // ---- whole-tensor slicing (one scale): convolution inputs whose im2col is done by TMA -------------------------------
 __global__ void __launch_bounds__(256) ozaki_amax_tensor_kernel(const double* __restrict__ x, size_t n, unsigned long long* __restrict__ amax_bits) {
     double amax = 0.0;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) amax = fmax(amax, fabs(x[i]));
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) amax = amax_fold(amax, x[i]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    if ((threadIdx.x & 31) == 0) {
-        if (amax == amax) atomicMax(amax_bits, (unsigned long long)__double_as_longlong(amax));
-        else atomicMax(amax_bits, 0x7FF8000000000000ull);
-    }
+    if ((threadIdx.x & 31) == 0) atomicMax(amax_bits, (unsigned long long)__double_as_longlong(amax_finish(amax)));
 }
 
 __global__ void __launch_bounds__(256) ozaki_slice_tensor_kernel(const double* __restrict__ x, size_t n, const unsigned long long* __restrict__ amax_bits,

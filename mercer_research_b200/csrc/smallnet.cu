@@ -18,6 +18,14 @@
 //        again; one extra CTA per K-split does db1 and the narrow layers' dW/db.  The last CTA of each column
 //        group to finish (atomic ticket) sums the K-split partials in a FIXED order into the flat gradient buffer
 //        (the all-reduce target) -- deterministic, unlike the reference's mutex-ordered sum (rcn.rs:190-205).
+//
+// Data-parallel groups (dp.cu): kernel B pushes its finished sums to the peers, a small exchange kernel X receives, adds and
+// updates.  Kernel A of the NEXT step is launched as X's programmatic dependent and runs its whole parameter-independent
+// front end (image loads, transpose, conv+pool, feature stores) BEFORE griddepcontrol.wait, i.e. while X is still waiting
+// for the NVLink traffic: the exchange leaves the step's critical path.  That is safe because (i) X triggers its
+// dependents only after its own wait, so kernel B of the previous step -- the last reader of the feature buffer and the
+// writer of the epoch cursor -- has completed and flushed before kernel A's first instruction; (ii) X touches only
+// parameters, gradients and its communication block; (iii) X runs as <= 20 fat CTAs, so kernel A's 128 CTAs find an SM each.
 #include "smallnet.cuh"
 #include "dp.cuh"
 
@@ -48,11 +56,7 @@ __device__ long long g_snp_stamp[1024][8];
 #define SN_PHASE(k) do { } while (0)
 #endif
 
-// Loads of data that OTHER CTAs rewrite while a persistent kernel is running (parameters, features, deltas, partials, the
-// epoch cursor) must not be served from this SM's L1: ld.global.cg reads L2.  One-launch-per-phase kernels keep the
-// read-only path.
-template <bool PERSIST>
-__device__ __forceinline__ double sn_ld(const double* p) { return PERSIST ? __ldcg(p) : __ldg(p); }
+__device__ __forceinline__ double sn_ld(const double* p) { return __ldg(p); }
 
 constexpr int SN_TB = 8;          // samples per CTA in kernel A (one DMMA n-fragment)
 constexpr int SNA_THREADS = 512;  // kernel A
@@ -102,15 +106,16 @@ __device__ __forceinline__ unsigned char* sn_align128(void* p) {
 // ------------------------------------------------------------------------------------------------
 // Kernel A
 // ------------------------------------------------------------------------------------------------
-// FUSED 0: features are an input; 1: generic fused front end; 2: staged front end (CpPlan).  PERSIST: called once per step
-// from the persistent step kernel (`step` = iteration; the image mbarrier is initialised once and waited by parity).
-template <int FUSED, bool PERSIST>
+// FUSED 0: features are an input; 1: generic fused front end; 2: staged front end (CpPlan).
+// PREWAIT (FUSED == 2, data-parallel groups): the whole front end runs before griddepcontrol.wait -- under the previous
+// step's exchange kernel -- and only the parameter loads wait for it (see the file header for why that is safe).
+template <int FUSED, bool PREWAIT>
 __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* __restrict__ params,
                                            double* __restrict__ feats, int B, const double* __restrict__ onehot,
                                            const int64_t* __restrict__ labels, double* __restrict__ acts,
                                            double* __restrict__ deltas, double* __restrict__ stats_partial,
                                            double* __restrict__ small_partial, int backward, const SmallNetFront& fr,
-                                           const int tile_idx, unsigned char* sn_smem, const int step) {
+                                           const int tile_idx, unsigned char* sn_smem) {
     double* zpart = reinterpret_cast<double*>(sn_smem);                 // [16][8][36]
     double* s_small = zpart + SNA_WARPS * SN_TB * SN_ZPITCH;                   // params after W0: b0 | W1 | b1 | ...
     double* tile = s_small + SN_MAX_SMALL;                              // FUSED: [8][n_in + 4]
@@ -120,19 +125,19 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
     __shared__ unsigned long long s_hit[SN_TB];
     __shared__ long long s_label[SN_TB];
 
-    if (FUSED == 0 && fr.pipe_only) {   // pipelined epoch mode: this step's half of the feature / label double buffer
-        const long long par = __ldcg(fr.bi.pipe + kEpAstep) & 1;
-        feats += (size_t)par * (size_t)B * d.n_in;
-        labels = reinterpret_cast<const int64_t*>(fr.bi.pipe + kEpSlots + par * (long long)B);
-        if (tile_idx == 0 && threadIdx.x == 0) fr.bi.pipe[kEpCurPar] = par;   // kernel B reads the same half
-    }
+    // programmatic dependent launch (when the host asked for it; no-ops otherwise): let the next kernel's launch proceed
+    // under this one, and wait until the previous kernel has completed and flushed before touching global memory
+    // (a forward-only launch keeps the implicit trigger at its completion: its successor may be a PREWAIT kernel A, whose
+    // early part writes the feature buffer)
+    if (backward) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!PREWAIT) asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int s0 = tile_idx * SN_TB;
     const int L = d.n_in, R0 = d.rows[0];
     const int mf = (R0 + 7) >> 3;
     SN_PHASE(0);
-    RCN_TL_BEGIN(0);
+    RCN_TL_BEGIN(d.tl, 0);
     const int pitch = L + SN_TILE_PAD;
     const int small_base = d.b_off[0];
     const int n_small = d.n_params - small_base;
@@ -145,12 +150,8 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
         const uint32_t img_bytes = (uint32_t)(fr.H * fr.W);
         if (warp == 0) {
             if (lane == 0) {
-                if (step == 0) {
-                    cpbulk::mbar_init(&s_bar, 1);
-                    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-                } else {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // last step's generic reads -> async overwrite
-                }
+                cpbulk::mbar_init(&s_bar, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
                 cpbulk::mbar_expect_tx(&s_bar, img_bytes * (uint32_t)n_live);
             }
             __syncwarp();
@@ -173,7 +174,8 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
 
     SN_PHASE(8);
     // layer-0 weight fragments: each warp owns a K range of the n_in-deep contraction; its first SN_U k-steps go into
-    // registers NOW and the rest is prefetched into L1, so the L2 latency is hidden behind the front end
+    // registers NOW and the rest is prefetched into L1, so the L2 latency is hidden behind the front end (PREWAIT: the
+    // parameters are not final yet -- the same loads are issued right after the wait below instead)
     const double* __restrict__ W0 = params + d.w_off[0];
     const int ksteps = (L + 3) >> 2;
     const int per_warp = (ksteps + SNA_WARPS - 1) / SNA_WARPS;
@@ -183,31 +185,28 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
 #pragma unroll
     for (int i = 0; i < 4; ++i) rowok[i] = (i < mf) && (i * 8 + g < R0);
     double w_pre[SN_U][4];
+    auto load_params = [&]() {
 #pragma unroll
-    for (int u = 0; u < SN_U; ++u) {
-        const int k = (ks_begin + u) * 4 + t;
-        const bool kok = (ks_begin + u) < ks_end && k < L;
-        const double* wp = W0 + (size_t)k * R0 + g;
+        for (int u = 0; u < SN_U; ++u) {
+            const int k = (ks_begin + u) * 4 + t;
+            const bool kok = (ks_begin + u) < ks_end && k < L;
+            const double* wp = W0 + (size_t)k * R0 + g;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) w_pre[u][i] = (kok && rowok[i]) ? sn_ld<PERSIST>(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
-    }
-    SN_PHASE(9);
-    // biases + narrow-layer weights into shared memory (after the register loads above: the store waits for its load)
-    if (PERSIST) {
-        for (int i = tid; i < n_small; i += SNA_THREADS) s_small[i] = sn_ld<true>(params + small_base + i);
-    } else {   // asynchronous copies: no register dependency, so no warp waits an L2 round trip here
+            for (int i = 0; i < 4; ++i) w_pre[u][i] = (kok && rowok[i]) ? sn_ld(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
+        }
+        SN_PHASE(9);
+        // biases + narrow-layer weights into shared memory (after the register loads above), as asynchronous copies: no
+        // register dependency, so no warp waits an L2 round trip here
         for (int i = tid; i < n_small; i += SNA_THREADS) {
             const unsigned dst = (unsigned)__cvta_generic_to_shared(s_small + i);
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(params + small_base + i) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    {
         const long long lo = (long long)min((ks_begin + SN_U) * 4, L) * R0, hi = (long long)min(ks_end * 4, L) * R0;   // doubles
-        if (!PERSIST)   // (a persistent kernel must not keep parameters in L1 across steps)
-            for (long long e = lo + lane * 16; e < hi; e += 32 * 16)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(W0 + e));
-    }
+        for (long long e = lo + lane * 16; e < hi; e += 32 * 16)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(W0 + e));
+    };
+    if (!PREWAIT) load_params();
 
     if (FUSED == 2) {
         // ---- staged front end: the 8 images arrive by bulk-async copies while the tiles' zero frames are written; then
@@ -220,7 +219,7 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
         SN_PHASE(11);
         __syncthreads();
         SN_PHASE(12);
-        cpbulk::mbar_wait(&s_bar, (uint32_t)(step & 1));
+        cpbulk::mbar_wait(&s_bar, 0u);
         SN_PHASE(1);
         cp_transpose_images(stg, fr.cp.stage_bytes, tiles, fr.cp.tile_ints, n_live, fr.H, fr.W, fr.cp, tid, SNA_THREADS);
         __syncthreads();
@@ -288,6 +287,10 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
         if (tid < SN_TB) s_label[tid] = (labels && s0 + tid < B) ? labels[s0 + tid] : -1;
     }
 
+    if (PREWAIT) {   // everything above ran under the previous step's exchange kernel; the parameters are final from here on
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        load_params();
+    }
     SN_PHASE(3);
     // ---- layer 0: z = W0 a0 on DMMA, K split across the 16 warps ----------------------------------------------------
     // The first U k-steps of this warp's W0 fragments were loaded into registers at the very top (w_pre), the rest of
@@ -323,7 +326,7 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
                 const bool kok = (ks + u) < ks_end && k < L;
                 const double* wp = W0 + (size_t)k * R0 + g;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) af[u][i] = (kok && rowok[i]) ? sn_ld<PERSIST>(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
+                for (int i = 0; i < 4; ++i) af[u][i] = (kok && rowok[i]) ? sn_ld(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
                 if (FUSED) bf[u] = kok ? trow[k] : 0.0;
                 else bf[u] = (kok && sample_ok) ? __ldg(frow + k) : 0.0;
             }
@@ -339,7 +342,7 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
             zpart[(warp * SN_TB + 2 * t + 1) * SN_ZPITCH + i * 8 + g] = acc[i][1];
         }
     }
-    if (!PERSIST) asm volatile("cp.async.wait_all;" ::: "memory");   // this thread's share of the small parameters has landed
+    asm volatile("cp.async.wait_all;" ::: "memory");   // this thread's share of the small parameters has landed
     __syncthreads();
     SN_PHASE(4);
     const int last = d.n_layers - 1;
@@ -443,7 +446,7 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
         }
     }
     SN_PHASE(21);
-    if (!backward) { RCN_TL_END(0); return; }
+    if (!backward) { RCN_TL_END(d.tl, 0); return; }
     __syncthreads();
     SN_PHASE(6);
     if (tid == SNA_THREADS - 32) {   // a warp with the fewest partial tasks below
@@ -493,11 +496,22 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
             }
         }
     }
+    // ---- epoch mode: ask L2 for the images this tile will load in the NEXT step (same tile index, cursor advanced like the
+    // update does, rcn.rs:147): 20 us from now their bulk loads hit L2 instead of paying an HBM round trip at the head of
+    // the step's critical path.  Nobody waits for these requests.
+    if (FUSED == 2 && warp == 1 && lane < SN_TB && fr.bi.cursor && !fr.bi.window && fr.bi.batch > 0 && s0 + lane < B) {
+        long long nx = __ldcg(fr.bi.cursor) + fr.bi.batch;
+        if (nx + fr.bi.batch > fr.bi.n_samples) nx = 0;
+        const long long pos = nx + s0 + lane;
+        const size_t src = (size_t)(fr.bi.perm ? fr.bi.perm[pos] : pos);
+        const uint32_t img_bytes = (uint32_t)(fr.H * fr.W);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(fr.images + src * img_bytes), "r"(img_bytes) : "memory");
+    }
     SN_PHASE(7);
-    RCN_TL_END(0);
+    RCN_TL_END(d.tl, 0);
 }
 
-template <int FUSED>
+template <int FUSED, bool PREWAIT>
 __global__ void __launch_bounds__(SNA_THREADS, 1)
 smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __restrict__ params,
                         double* __restrict__ feats, int B, const double* __restrict__ onehot,
@@ -505,12 +519,8 @@ smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __
                         double* __restrict__ stats_partial, double* __restrict__ small_partial, int backward,
                         const __grid_constant__ SmallNetFront fr) {
     extern __shared__ __align__(128) unsigned char sn_smem[];
-    // programmatic dependent launch (when the host asked for it; no-ops otherwise): let the next kernel's launch proceed
-    // under this one, and wait here until the previous kernel has completed and flushed before touching global memory
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    sn_phase_a<FUSED, false>(d, params, feats, B, onehot, labels, acts, deltas, stats_partial, small_partial, backward, fr,
-                             (int)blockIdx.x, sn_smem, 0);
+    sn_phase_a<FUSED, PREWAIT>(d, params, feats, B, onehot, labels, acts, deltas, stats_partial, small_partial, backward, fr,
+                               (int)blockIdx.x, sn_smem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -527,30 +537,25 @@ constexpr int SNB_TILE = 32 * 64;   // padded partial tile: 32 rows x 64 columns
 // right here (SnUpdate).  MODE 3: data-parallel AND fused update: every thread pushes its finished element to the peers,
 // waits for theirs, adds the ranks in rank order and applies the update -- the whole exchange + update of rcn.rs:190-222
 // inside this kernel's epilogue, so a multi-GPU step is two launches as well.
-// PERSIST: called from the persistent step kernel with 512 threads per CTA: threads >= SNB_THREADS only take part in the
-// cluster barriers, the working threads synchronise on a named barrier.
+// Whatever the mode, when `upd.cursor` is set the statistics thread also advances the epoch cursor and writes the per-step
+// result ring (on a data-parallel group that makes the cursor final BEFORE the exchange kernel runs, which is what lets the
+// next step's kernel A read it ahead of its griddepcontrol.wait).
 // CW: columns of dW0 per CTA: 64 (one warp per 8 columns) or 32 (two warps per 8 columns, each taking half of every
 // 64-sample chunk; their two partial tiles are added, in order, by the reduction).
-template <int MODE, bool PERSIST, int CW>
+template <int MODE, int CW>
 __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* __restrict__ feats,
                                            const double* __restrict__ small_partial, const double* __restrict__ deltas,
                                            int B, int ksplit, int col_groups, double* __restrict__ grads,
                                            const double* __restrict__ stats_partial, int n_stat, double* __restrict__ stats,
                                            const DpPush& dp, const SnUpdate& upd, const int cg_idx, const int rank, const int S,
                                            double* sP, double* sD /* [2][64 * SN_DPITCH]: double-buffered 64-sample delta_0 chunk */,
-                                           const unsigned total_ctas, const long long* pipe) {
-    if (pipe) feats += (size_t)__ldcg(pipe + kEpCurPar) * (size_t)B * d.n_in;   // the half kernel A used (pipelined epoch mode)
+                                           const unsigned total_ctas) {
     constexpr bool DP = MODE == 1 || MODE == 3;
     constexpr bool UPD = MODE == 2 || MODE == 3;
     constexpr bool DPX = MODE == 3;
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
-    RCN_TL_BEGIN(1);
-    if (PERSIST && threadIdx.x >= SNB_THREADS) {             // spectators of the DSMEM reduction
-        cluster.sync();
-        cluster.sync();
-        return;
-    }
+    RCN_TL_BEGIN(d.tl, 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int L = d.n_in, R0 = d.rows[0];
@@ -577,7 +582,7 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int b = c0 + kq * (64 / KQ) + u * 4 + t;
-                bf[u] = (b < b_end && col_ok) ? (PERSIST ? __ldcg(feats + (size_t)b * L + col) : feats[(size_t)b * L + col]) : 0.0;   // B frag: row t (sample), col g (feature)
+                bf[u] = (b < b_end && col_ok) ? feats[(size_t)b * L + col] : 0.0;   // B frag: row t (sample), col g (feature)
             }
         };
         auto load_delta = [&](double (&vd)[8], int c0) {
@@ -586,7 +591,7 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
                 const int idx = u * SNB_THREADS + tid;
                 const int kk = idx >> 5, mm = idx & 31;
                 const int b = c0 + kk;
-                vd[u] = (mm < R0 && b < b_end) ? (PERSIST ? __ldcg(deltas + (size_t)b * R0 + mm) : deltas[(size_t)b * R0 + mm]) : 0.0;
+                vd[u] = (mm < R0 && b < b_end) ? deltas[(size_t)b * R0 + mm] : 0.0;
             }
         };
         auto store_delta = [&](const double (&vd)[8], double* sd) {
@@ -613,10 +618,10 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
             if (two) { load_feats(bf1, c0 + 64); load_delta(vd1, c0 + 64); }
             store_delta(vd0, sD);
             if (two) store_delta(vd1, sD + 64 * SN_DPITCH);
-            if (PERSIST) asm volatile("bar.sync 2, 256;" ::: "memory"); else __syncthreads();   // both slices staged
+            __syncthreads();   // both slices staged
             mma_chunk(bf0, sD);
             if (two) mma_chunk(bf1, sD + 64 * SN_DPITCH);
-            if (c0 + 128 < b_end) { if (PERSIST) asm volatile("bar.sync 2, 256;" ::: "memory"); else __syncthreads(); }   // before the slices are overwritten
+            if (c0 + 128 < b_end) __syncthreads();   // before the slices are overwritten
         }
         const int cl = kq * CW + oct * 8 + 2 * t;           // C frag: row g (m), cols 2t, 2t+1; one CW x 32 tile per kq
 #pragma unroll
@@ -634,7 +639,7 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
             for (int tb = t_begin; tb < t_end; tb += 8) {
                 double v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = (tb + u < t_end) ? (PERSIST ? __ldcg(small_partial + (size_t)(tb + u) * n_small + o) : small_partial[(size_t)(tb + u) * n_small + o]) : 0.0;
+                for (int u = 0; u < 8; ++u) v[u] = (tb + u < t_end) ? small_partial[(size_t)(tb + u) * n_small + o] : 0.0;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) s += v[u];
             }
@@ -660,16 +665,29 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
             gi = small_base + o;
         }
         double pold = 0.0;
-        if (UPD && gi >= 0) pold = PERSIST ? __ldcg(upd.params + gi) : upd.params[gi];
+        if (UPD && gi >= 0) pold = upd.params[gi];
+        // all S remote reads are issued before the first add (one DSMEM round trip, not S dependent ones; S <= 8)
+        double rv[8], rw[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            rv[q] = 0.0; rw[q] = 0.0;
+            if (q < S) {
+                const double* remote = cluster.map_shared_rank(sP, q);
+                rv[q] = remote[o];
+                if (is_col && CW == 32) rw[q] = remote[CW * 32 + o];   // the second warp's half of every chunk
+            }
+        }
         double s = 0.0;
-        for (int q = 0; q < S; ++q) {
-            const double* remote = cluster.map_shared_rank(sP, q);
-            s += remote[o];
-            if (is_col && CW == 32) s += remote[CW * 32 + o];   // the second warp's half of every chunk
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (q < S) {
+                s += rv[q];
+                if (is_col && CW == 32) s += rw[q];
+            }
         }
         if (gi >= 0) {
             if (DP) dp_push_value(dp, dp_par, (size_t)gi, s);
-            if (DPX) s = dp_receive_sum(dp, dp_par, (size_t)gi, s);   // the global sum, identical on every rank
+            if (DPX) s = dp_receive_sum<0>(dp, dp_par, (size_t)gi, s);   // the global sum, identical on every rank
             grads[gi] = s;
             if (UPD) upd.params[gi] = sgd_apply(pold, upd.scale, s);
         }
@@ -680,8 +698,8 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
         double c = 0.0;
         unsigned long long h = 0;
         for (int i = tid * per_l; i < min(n_stat, (tid + 1) * per_l); ++i) {
-            c += PERSIST ? __ldcg(stats_partial + 2 * i) : stats_partial[2 * i];
-            h += PERSIST ? __ldcg(reinterpret_cast<const unsigned long long*>(stats_partial) + 2 * i + 1) : reinterpret_cast<const unsigned long long*>(stats_partial)[2 * i + 1];
+            c += stats_partial[2 * i];
+            h += reinterpret_cast<const unsigned long long*>(stats_partial)[2 * i + 1];
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -691,8 +709,8 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
         if (tid == 0) {
             stats[0] = c;
             reinterpret_cast<unsigned long long*>(stats)[1] = h;
-            if (UPD && upd.cursor) {   // what sgd_update_kernel does on the side (kernel A of this step is long done)
-                const long long cur0 = PERSIST ? __ldcg(upd.cursor) : *upd.cursor;
+            if (upd.cursor) {   // what sgd_update_kernel does on the side (kernel A of this step is long done)
+                const long long cur0 = *upd.cursor;
                 if (upd.stats_ring) {
                     double* dst = upd.stats_ring + 2 * (cur0 / upd.batch);
                     dst[0] = c;
@@ -701,13 +719,12 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
                 long long cur = cur0 + upd.batch;   // next chunk of chunks_exact(batch) (rcn.rs:147), remainder dropped
                 if (cur + upd.batch > upd.n_samples) cur = 0;
                 *upd.cursor = cur;
-                if (upd.pipe) upd.cursor[kEpAstep] += 1;
             }
         }
     }
     cluster.sync();   // nobody leaves while a peer may still read its tile
     if (DPX && tid == 0) dp_finish_step(dp, total_ctas);
-    RCN_TL_END(1);
+    RCN_TL_END(d.tl, 1);
 }
 
 template <int MODE>
@@ -718,81 +735,16 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
                                                                      int col_groups, double* __restrict__ grads,
                                                                      const double* __restrict__ stats_partial, int n_stat,
                                                                      double* __restrict__ stats, const __grid_constant__ DpPush dp,
-                                                                     const __grid_constant__ SnUpdate upd, const long long* __restrict__ pipe) {
+                                                                     const __grid_constant__ SnUpdate upd) {
     extern __shared__ __align__(16) double sP_dyn[];          // partial tile: SNB_TILE (col CTAs) or n_small doubles
     __shared__ __align__(16) double sD_static[2 * 64 * SN_DPITCH];   // 36 KB
     // grid (col_groups + 1, S) in clusters of (1, S, 1): blockIdx.y == cluster.block_rank()
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // On a data-parallel group the successor may be a PREWAIT kernel A that writes the feature buffer this kernel reads:
+    // no early trigger there (the implicit one at completion stands); a single GPU keeps the early trigger.
+    if (dp.world <= 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    sn_phase_b<MODE, false, 64>(d, feats, small_partial, deltas, B, ksplit, col_groups, grads, stats_partial, n_stat, stats, dp, upd,
-                            (int)blockIdx.x, (int)blockIdx.y, (int)gridDim.y, sP_dyn, sD_static, gridDim.x * gridDim.y, pipe);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Persistent step kernel (single GPU, canonical network, staged front end): the kernel boundaries of a step cost
-// 2.5-3 us each on B200 (measured with the device-side timeline, profiles/sn_phases.py) against ~20 us of work, so
-// phase A, phase B (+ SGD update) and the NEXT steps run inside ONE cooperative launch of n_tiles CTAs in clusters of 4,
-// separated by grid-wide barriers (one atomic arrival + an acquire poll per CTA) instead of launches.  Cluster c takes
-// column group c of phase B (the DSMEM reduction needs its 4 K-split CTAs in one cluster), CTA i tile i of phase A.
-// Data other CTAs rewrite during the kernel is read with ld.global.cg (L1 is not coherent); the epoch cursor lives in
-// device memory as before, so n_steps consecutive steps of rcn.rs:147-149 are one launch.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void sn_grid_barrier(unsigned* counter, unsigned target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        unsigned v, spins = 0;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-            if (++spins > (1u << 27)) __trap();   // a lost CTA must fail the launch, not hang the device
-        } while (v < target);
-        __threadfence();
-    }
-    __syncthreads();
-}
-
-constexpr int SNP_CLUSTER = 4;    // 8-CTA clusters: only 15 of the 16 needed are co-resident on B200 (GPC sizes); 4-CTA ones fit
-constexpr int SNP_CW = 32;        // so phase B runs 32-column groups x 4 K-splits instead of 64 x 8
-
-__global__ void __launch_bounds__(SNA_THREADS, 1)
-smallnet_persistent_kernel(const __grid_constant__ SmallNetDesc d, double* __restrict__ params, double* __restrict__ feats,
-                           int B, double* __restrict__ acts, double* __restrict__ deltas, double* __restrict__ stats_partial,
-                           double* __restrict__ small_partial, const __grid_constant__ SmallNetFront fr, int ksplit,
-                           int col_groups, double* __restrict__ grads, double* __restrict__ stats,
-                           const __grid_constant__ SnUpdate upd, int n_steps, unsigned* __restrict__ gbar) {
-    extern __shared__ __align__(128) unsigned char sn_smem[];
-    const int n_tiles = (B + SN_TB - 1) / SN_TB;
-    const int cid = (int)blockIdx.x / SNP_CLUSTER;
-    const int rank = (int)blockIdx.x % SNP_CLUSTER;             // == cluster.block_rank() for cluster dims (4, 1, 1)
-    DpPush nodp{};
-    nodp.world = 1;
-    unsigned arrivals = 0;
-#ifdef RCN_SN_PHASES
-#define SNP_STAMP(k) do { if (threadIdx.x == 0 && blockIdx.x < 1024) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_snp_stamp[blockIdx.x][k] = (long long)_t; } } while (0)
-#else
-#define SNP_STAMP(k) do { } while (0)
-#endif
-    for (int step = 0; step < n_steps; ++step) {
-        SNP_STAMP(0);
-        if ((int)blockIdx.x < n_tiles)
-            sn_phase_a<2, true>(d, params, feats, B, nullptr, nullptr, acts, deltas, stats_partial, small_partial, 1, fr,
-                                (int)blockIdx.x, sn_smem, step);
-        SNP_STAMP(1);
-        arrivals += gridDim.x;
-        sn_grid_barrier(gbar, arrivals);                          // every tile's features / deltas / partials are in L2
-        SNP_STAMP(2);
-        if (cid <= col_groups)
-            sn_phase_b<2, true, 32>(d, feats, small_partial, deltas, B, ksplit, col_groups, grads, stats_partial, n_tiles, stats, nodp,
-                                upd, cid, rank, SNP_CLUSTER, reinterpret_cast<double*>(sn_smem),
-                                reinterpret_cast<double*>(sn_smem) + SNA_WARPS * SN_TB * SN_ZPITCH, 0u, nullptr);   // sP | sD alias phase A's buffers
-        SNP_STAMP(3);
-        if (step + 1 < n_steps) {
-            arrivals += gridDim.x;
-            sn_grid_barrier(gbar, arrivals);                      // the updated parameters and the cursor are in L2
-        }
-        SNP_STAMP(4);
-    }
+    sn_phase_b<MODE, 64>(d, feats, small_partial, deltas, B, ksplit, col_groups, grads, stats_partial, n_stat, stats, dp, upd,
+                         (int)blockIdx.x, (int)blockIdx.y, (int)gridDim.y, sP_dyn, sD_static, gridDim.x * gridDim.y);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -825,9 +777,8 @@ static bool sn_pdl_enabled() {
     return on;
 }
 
-// Highest launch priority for the training kernels: when the pipelined epoch mode runs the next step's feature kernel on
-// a parallel branch, pending CTAs of kernels A / B must win the SMs (kernel A needs a whole SM per CTA), the feature
-// kernel fills what is left.
+// Highest launch priority for the training kernels: pending CTAs of kernels A / B must win the SMs (kernel A needs a whole
+// SM per CTA) against anything a parallel branch runs (the host-dataset loop's prefetch kernel).
 static int sn_high_priority() {
     static const int prio = []() { int least = 0, greatest = 0; if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { cudaGetLastError(); return 0; } return greatest; }();
     return prio;
@@ -856,7 +807,7 @@ static int launch_kernel_a(const SmallNetDesc& d, const double* params, double* 
                            const int64_t* labels, double* acts, double* deltas, double* stats_partial,
                            double* small_partial, int backward, const SmallNetFront* fr, cudaStream_t stream) {
     const unsigned n_tiles = cdiv(B, SN_TB);
-    const size_t smem = kernel_a_smem(d, (fr && fr->pipe_only) ? nullptr : fr);
+    const size_t smem = kernel_a_smem(d, fr);
     static SmallNetFront empty_front{};
     const int Bi = (int)B;
     auto launch = [&](auto kern, SmemAttrCache& attr, const char* name, const SmallNetFront& front) -> int {
@@ -877,17 +828,18 @@ static int launch_kernel_a(const SmallNetDesc& d, const double* params, double* 
                                                     small_partial, backward, front));
         return RCN_OK;
     };
-    const SmallNetFront* pipe_front = (fr && fr->pipe_only) ? fr : nullptr;
-    if (pipe_front) fr = nullptr;   // no front end inside the kernel
-    if (fr && fr->use_cp) {
+    if (fr && fr->use_cp && fr->prewait && backward && sn_pdl_enabled()) {
         static SmemAttrCache attr;
-        RCN_TRY(launch(smallnet_fwd_bwd_kernel<2>, attr, "smallnet_fwd_bwd_kernel(fused features)", *fr));
+        RCN_TRY(launch(smallnet_fwd_bwd_kernel<2, true>, attr, "smallnet_fwd_bwd_kernel(fused features, front end ahead of the exchange)", *fr));
+    } else if (fr && fr->use_cp) {
+        static SmemAttrCache attr;
+        RCN_TRY(launch(smallnet_fwd_bwd_kernel<2, false>, attr, "smallnet_fwd_bwd_kernel(fused features)", *fr));
     } else if (fr) {
         static SmemAttrCache attr;
-        RCN_TRY(launch(smallnet_fwd_bwd_kernel<1>, attr, "smallnet_fwd_bwd_kernel(fused features)", *fr));
+        RCN_TRY(launch(smallnet_fwd_bwd_kernel<1, false>, attr, "smallnet_fwd_bwd_kernel(fused features)", *fr));
     } else {
         static SmemAttrCache attr;
-        RCN_TRY(launch(smallnet_fwd_bwd_kernel<0>, attr, "smallnet_fwd_bwd_kernel", pipe_front ? *pipe_front : empty_front));
+        RCN_TRY(launch(smallnet_fwd_bwd_kernel<0, false>, attr, "smallnet_fwd_bwd_kernel", empty_front));
     }
     return RCN_OK;
 }
@@ -901,7 +853,7 @@ int launch_smallnet_forward(const SmallNetDesc& d, const double* params, double*
 int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double* feats, size_t B, const double* onehot,
                              const int64_t* labels, double* acts, double* deltas, double* grads, double* stats,
                              DevBuf& workspace, const SmallNetFront* front, cudaStream_t stream, const DpPush* dp_push,
-                             const SnUpdate* update, const long long* pipe, cudaEvent_t after_a) {
+                             const SnUpdate* update) {
     if (B == 0) return RCN_OK;
     if (B > smallnet_max_batch()) return fail(RCN_ERR_INVALID, "batch too large for the fused small-network path");
     int splits, ksplit;
@@ -914,7 +866,6 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
     double* stats_partial = workspace.as<double>();
     double* small_partial = stats_partial + 2 * (size_t)n_tiles;
     RCN_TRY(launch_kernel_a(d, params, feats, B, onehot, labels, acts, deltas, stats_partial, small_partial, 1, front, stream));
-    if (after_a) RCN_CUDA_TRY(cudaEventRecord(after_a, stream));   // a parallel branch may start once kernel A is done
 
     const size_t smem_b = (size_t)(n_small > SNB_TILE ? n_small : SNB_TILE) * sizeof(double);
     DpPush push{};
@@ -952,87 +903,12 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
     auto kern = mode == 1 ? smallnet_wgrad_kernel<1> : mode == 2 ? smallnet_wgrad_kernel<2> : mode == 3 ? smallnet_wgrad_kernel<3> : smallnet_wgrad_kernel<0>;
     RCN_LAUNCH(mode == 2 ? "smallnet_wgrad_kernel(+SGD update)" : mode == 3 ? "smallnet_wgrad_kernel(+exchange+SGD update)" : "smallnet_wgrad_kernel", stream,
                cudaLaunchKernelEx(&cfg, kern, d, (const double*)feats, (const double*)small_partial, (const double*)deltas, Bi,
-                                  ksplit, col_groups, grads, (const double*)stats_partial, n_tiles, stats, push, upd, pipe));
-    return RCN_OK;
-}
-
-// Can `n_steps` steps of this shape run as one persistent launch?  Needs the staged front end, 8 K-splits (= the cluster
-// size), every tile and every column-group cluster co-resident (one CTA per SM).
-static void smallnet_persistent_plan(const SmallNetDesc& d, size_t B, int* splits, int* ksplit, int* col_groups, int* grid) {
-    size_t ks = (B + SNP_CLUSTER - 1) / SNP_CLUSTER;
-    ks = (ks + 63) / 64 * 64;                                   // whole 64-sample chunks
-    *ksplit = (int)ks;
-    *splits = (int)((B + ks - 1) / ks);
-    *col_groups = (int)cdiv(d.n_in, SNP_CW);
-    const size_t n_tiles = cdiv(B, SN_TB);
-    size_t g = n_tiles > (size_t)SNP_CLUSTER * (*col_groups + 1) ? n_tiles : (size_t)SNP_CLUSTER * (*col_groups + 1);
-    *grid = (int)((g + SNP_CLUSTER - 1) / SNP_CLUSTER * SNP_CLUSTER);
-}
-
-bool smallnet_persistent_eligible(const SmallNetDesc& d, const SmallNetFront& fr, size_t B) {
-    // Opt-in (RCN_CUDA_PERSISTENT=1, read per call): measured on B200 the grid barrier costs ~1.3 us against ~2.7 us for a
-    // kernel boundary, but without L1-resident weights and with 4 instead of 8 K-splits the phases themselves are slower,
-    // and the step comes out at 25.6 us against 24.4 us for the two-kernel graph (profiles/sn_phases.py persistent).
-    const char* env = getenv("RCN_CUDA_PERSISTENT");
-    if (!(env && env[0] == '1') || !fr.use_cp || B == 0 || B > smallnet_max_batch()) return false;
-    int splits, ksplit, col_groups, grid;
-    smallnet_persistent_plan(d, B, &splits, &ksplit, &col_groups, &grid);
-    const size_t n_small = (size_t)(d.n_params - d.b_off[0]);
-    if (splits != SNP_CLUSTER || n_small > (size_t)SNA_WARPS * SN_TB * SN_ZPITCH) return false;
-    const size_t smem = kernel_a_smem(d, &fr);   // phase B's partial tile and delta chunks alias phase A's dynamic buffers
-    if (smem < ((size_t)SNA_WARPS * SN_TB * SN_ZPITCH + 2 * 64 * SN_DPITCH) * sizeof(double) || smem > 200 * 1024) return false;
-    return grid <= 144;                          // one CTA per SM, all co-resident (the cooperative launch checks again)
-}
-
-int launch_smallnet_persistent(const SmallNetDesc& d, double* params, double* feats, size_t B, double* acts, double* deltas,
-                               double* grads, double* stats, DevBuf& workspace, const SmallNetFront& front,
-                               const SnUpdate& update, int n_steps, cudaStream_t stream) {
-    if (n_steps <= 0) return RCN_OK;
-    int splits, ksplit, col_groups, grid;
-    smallnet_persistent_plan(d, B, &splits, &ksplit, &col_groups, &grid);
-    const int n_tiles = (int)cdiv(B, SN_TB);
-    const int n_small = d.n_params - d.b_off[0];
-    // workspace: [barrier counter (256 B)] | per-tile statistics partials | per-tile small-parameter gradient partials
-    RCN_TRY(workspace.reserve(256 + (2 + (size_t)n_small) * (size_t)n_tiles * sizeof(double)));
-    unsigned* gbar = workspace.as<unsigned>();
-    double* stats_partial = reinterpret_cast<double*>(workspace.as<char>() + 256);
-    double* small_partial = stats_partial + 2 * (size_t)n_tiles;
-    RCN_CUDA_TRY(cudaMemsetAsync(gbar, 0, 256, stream));
-    const size_t smem = kernel_a_smem(d, &front);
-    static SmemAttrCache attr;
-    if (attr.need(smem)) RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid, 1, 1);
-    cfg.blockDim = dim3(SNA_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = SNP_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    at[1].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident, or the launch fails: the barriers cannot deadlock
-    at[1].val.cooperative = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 2;
-    const int Bi = (int)B;
-    static const bool debug = []() { const char* e = getenv("RCN_CUDA_DEBUG"); return e && e[0] == '1'; }();
-    if (debug) {
-        int n_clusters = -1;
-        cudaError_t oe = cudaOccupancyMaxActiveClusters(&n_clusters, smallnet_persistent_kernel, &cfg);
-        fprintf(stderr, "[rcn_cuda] persistent kernel: grid %d CTAs (%d clusters of %d), smem %zu B, max active clusters %d (%s)\n",
-                grid, grid / SNP_CLUSTER, SNP_CLUSTER, smem, n_clusters, cudaGetErrorString(oe));
-    }
-    RCN_LAUNCH("smallnet_persistent_kernel", stream,
-               cudaLaunchKernelEx(&cfg, smallnet_persistent_kernel, d, params, feats, Bi, acts, deltas, stats_partial, small_partial,
-                                  front, ksplit, col_groups, grads, stats, update, n_steps, gbar));
+                                  ksplit, col_groups, grads, (const double*)stats_partial, n_tiles, stats, push, upd));
     return RCN_OK;
 }
 
 }  // namespace rcn
 
-#ifdef RCN_TIMELINE
-extern "C" int rcn_cuda_debug_timeline_reset_smallnet() { return rcn_tl::reset_host(); }
-extern "C" int rcn_cuda_debug_timeline_read_smallnet(unsigned long long* out, unsigned* seq) { return rcn_tl::read_host(out, seq); }
-#endif
 #ifdef RCN_SN_PHASES
 extern "C" int rcn_cuda_debug_snp_stamps(long long* out /* [1024][8] */) {
     return cudaMemcpyFromSymbol(out, rcn::g_snp_stamp, sizeof(rcn::g_snp_stamp)) == cudaSuccess ? 0 : 4;

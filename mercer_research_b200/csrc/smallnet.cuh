@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "features.cuh"
+#include "timeline.cuh"
 
 namespace rcn {
 
@@ -16,6 +17,7 @@ struct SmallNetDesc {
     int w_off[kSmallNetMaxLayers];     // offsets into the flat [W0|b0|W1|b1|...] buffer
     int b_off[kSmallNetMaxLayers];
     int n_params;
+    Timeline* tl;                      // device-side launch timeline (timeline.cuh), null = off
 };
 
 // Optional fused front end of kernel A: u8 images -> convpool stack -> standardised features, in shared memory.
@@ -26,14 +28,16 @@ struct SmallNetFront {
     StageList stages;
     Standardise sc;
     BatchIndex bi;
-    int pipe_only;                     // no front end in the kernel: the features / labels come from the pipelined epoch
-                                       // mode's double buffer (bi.pipe = epoch state block, half = pipe[kEpAstep] & 1)
+    int prewait;                       // data-parallel step behind the exchange kernel: run the front end ahead of
+                                       // griddepcontrol.wait (smallnet.cu; needs use_cp and a cursor the previous kernel B advanced)
     int use_cp;                        // staged front end (bulk-async image loads, zero-framed tiles): see CpPlan
     CpPlan cp;
 };
 // Fills use_cp / cp: the staged front end needs a qualifying plan, 16-byte aligned images and H*W % 16 == 0.
 void smallnet_front_select(const FeaturePlan& plan, SmallNetFront* fr);
 
+// `params` may be null with `cursor` set: the kernel then only advances the cursor / writes the result ring (data-parallel
+// groups, where the exchange kernel applies the update).
 // Single-GPU steps fold the SGD update (rcn.rs:210-222) into the weight-gradient kernel: every CTA applies
 // W -= scale * sum to exactly the elements whose batch sum it has just finished (one kernel and one launch gap less per
 // step).  Also carries what sgd_update_kernel does on the side: the epoch cursor (rcn.rs:147) and the per-step result ring.
@@ -43,7 +47,6 @@ struct SnUpdate {
     long long* cursor;       // optional epoch cursor, advanced by `batch` with chunks_exact wrap-around
     long long batch, n_samples;
     double* stats_ring;      // optional (pinned host) {cost, hits} per step
-    int pipe;                // pipelined epoch mode: also count the step (cursor[kEpAstep]++)
 };
 
 bool smallnet_eligible(const SmallNetDesc& d);
@@ -59,14 +62,6 @@ int launch_smallnet_forward(const SmallNetDesc& d, const double* params, double*
 int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double* feats, size_t B, const double* onehot,
                              const int64_t* labels, double* acts, double* deltas, double* grads, double* stats,
                              DevBuf& workspace, const SmallNetFront* front, cudaStream_t stream,
-                             const DpPush* dp_push = nullptr, const SnUpdate* update = nullptr,
-                             const long long* pipe = nullptr, cudaEvent_t after_a = nullptr /* recorded between kernels A and B */);
-
-// n_steps consecutive single-GPU steps (kernel A, kernel B + SGD update, epoch cursor) as ONE persistent cooperative launch
-// with grid-wide barriers instead of kernel boundaries; `update` must carry params / scale (and the cursor in epoch mode).
-bool smallnet_persistent_eligible(const SmallNetDesc& d, const SmallNetFront& fr, size_t B);
-int launch_smallnet_persistent(const SmallNetDesc& d, double* params, double* feats, size_t B, double* acts, double* deltas,
-                               double* grads, double* stats, DevBuf& workspace, const SmallNetFront& front,
-                               const SnUpdate& update, int n_steps, cudaStream_t stream);
+                             const DpPush* dp_push = nullptr, const SnUpdate* update = nullptr);
 
 }  // namespace rcn

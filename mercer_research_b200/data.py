@@ -27,11 +27,37 @@ def get_pixel_matrix(image) -> np.ndarray:
     raise InvalidGrayscaleImageError()
 
 
+def grayscale_u8(im) -> np.ndarray:
+    """``DynamicImage::grayscale()`` followed by ``get_pixel_matrix`` (rcn.rs:83,398 + lib.rs:27-41) for a decoded Pillow
+    image -> (H, W) uint8.
+
+    The ``image`` crate (0.24, rcn/Cargo.toml; not vendored -- formula from its published source, unverifiable here) turns
+    Rgb8 / Rgba8 into Luma8 / LumaA8 with the integer sRGB luminance ``(2126 R + 7152 G + 722 B) / 10000`` (truncating
+    division), NOT the Rec.601 weights of Pillow's ``convert("L")``; palette PNGs decode to RGB(A) first; 1-bit grey decodes
+    to 0 / 255. 16-bit (and any other) colour types stay 16-bit through ``grayscale()``, which ``get_pixel_matrix``
+    rejects with ``InvalidGrayscaleImageError`` (lib.rs:39) -- same here instead of a silent clip."""
+    mode = im.mode
+    if mode == "P":
+        im = im.convert("RGBA" if "transparency" in im.info else "RGB")
+        mode = im.mode
+    if mode == "1":
+        im = im.convert("L")
+        mode = "L"
+    if mode == "L":
+        return np.asarray(im, dtype=np.uint8)
+    if mode == "LA":
+        return np.ascontiguousarray(np.asarray(im, dtype=np.uint8)[:, :, 0])
+    if mode in ("RGB", "RGBA"):
+        a = np.asarray(im, dtype=np.uint8).astype(np.uint32)
+        return ((2126 * a[..., 0] + 7152 * a[..., 1] + 722 * a[..., 2]) // 10000).astype(np.uint8)
+    raise InvalidGrayscaleImageError()
+
+
 def load_grayscale(path: str) -> np.ndarray:
-    """``ImageReader::open(path)?.decode()?.grayscale()`` (rcn.rs:83,394-398) -> (H, W) uint8."""
+    """``ImageReader::open(path)?.decode()?.grayscale()`` + ``get_pixel_matrix`` (rcn.rs:83,394-400) -> (H, W) uint8."""
     from PIL import Image
     with Image.open(path) as im:
-        return np.asarray(im.convert("L"), dtype=np.uint8)
+        return grayscale_u8(im)
 
 
 def load_data(path: str, class_size_limit: int, rng: np.random.Generator):

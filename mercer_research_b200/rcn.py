@@ -415,7 +415,7 @@ class RCN:
 
     def epoch_run(self, eta: float, n_steps: int):
         """``n_steps`` iterations of ``for batch in training_set.chunks_exact(batch) { train_batch(batch, eta) }``
-        (rcn.rs:147-149) over the bound dataset; one persistent launch where the shape allows it."""
+        (rcn.rs:147-149) over the bound dataset, one library call."""
         _lib.check(self._lib.rcn_cuda_epoch_run(self._h, float(eta), int(n_steps)))
 
     def train_epoch_host(self, images, labels, batch: int, eta: float, global_batch: int = 0):
@@ -460,6 +460,24 @@ class RCN:
 
     def dp_shutdown(self):
         _lib.check(self._lib.rcn_cuda_dp_shutdown(self._h))
+
+    def timeline_enable(self, on: bool = True):
+        """Device-side launch timeline of the fused step kernels (csrc/timeline.cuh); captured steps must be re-captured."""
+        _lib.check(self._lib.rcn_cuda_timeline_enable(self._h, 1 if on else 0))
+
+    def timeline_read(self):
+        """(starts, ends, launches): starts / ends are (4, 64) uint64 %globaltimer ns (slot = launch index % 64) for kernel
+        A, kernel B, the exchange kernel; launches (4,) uint32."""
+        stamps = np.zeros((2, 4, 64), dtype=np.uint64)
+        n = np.zeros(4, dtype=np.uint32)
+        _lib.check(self._lib.rcn_cuda_timeline_read(self._h, stamps.ctypes.data, n.ctypes.data))
+        return stamps[0], stamps[1], n
+
+    def dp_check(self):
+        """Synchronises and raises if a gradient exchange timed out waiting for a peer (the device never hangs on a dead
+        or desynchronised rank: the receive is bounded, RCN_CUDA_DP_TIMEOUT_MS)."""
+        e = C.c_int()
+        _lib.check(self._lib.rcn_cuda_dp_error(self._h, C.byref(e)))
 
     def last_batch_stats(self) -> Tuple[float, int]:
         """(quadratic cost, hits) of the last accumulated batch, evaluated with the pre-update parameters."""

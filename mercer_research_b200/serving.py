@@ -25,6 +25,8 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
+from .data import grayscale_u8
+
 
 class ClassifyBatcher:
     """Coalesces concurrent ``classify`` requests into batched device calls.
@@ -146,7 +148,7 @@ class RCNState:
             path = self.image_paths[self.rng.randrange(len(self.image_paths))]
         with Image.open(path) as im:
             im.load()
-            pixels = np.asarray(im.convert("L"), dtype=np.uint8)   # .grayscale() of rcn.rs:83
+            pixels = grayscale_u8(im)                               # .grayscale() of rcn.rs:83 (image-crate luma weights)
             buf = io.BytesIO()
             im.save(buf, format="PNG")                              # img.write_to(.., Png) of main.rs:33-35
         output = self.batcher.classify(pixels)

@@ -57,6 +57,9 @@ extern "C" {
     pub fn rcn_cuda_dp_connect_ipc(h: rcn_cuda_handle, all_handles: *const c_void) -> c_int;
     pub fn rcn_cuda_dp_connect_local(h: rcn_cuda_handle, group: *const rcn_cuda_handle) -> c_int;
     pub fn rcn_cuda_dp_shutdown(h: rcn_cuda_handle) -> c_int;
+    pub fn rcn_cuda_dp_error(h: rcn_cuda_handle, error: *mut c_int) -> c_int;
+    pub fn rcn_cuda_timeline_enable(h: rcn_cuda_handle, on: c_int) -> c_int;
+    pub fn rcn_cuda_timeline_read(h: rcn_cuda_handle, stamps: *mut u64, launches: *mut u32) -> c_int;
     pub fn rcn_cuda_init_params_shapes(h: rcn_cuda_handle, rows: *const usize, cols: *const usize, n_layers: usize) -> c_int;
     pub fn rcn_cuda_accumulate_gradients_images(h: rcn_cuda_handle, images: *const c_void, pixel_format: c_int,
                                                 labels: *const i64, B: usize, H: usize, W: usize) -> c_int;

@@ -62,3 +62,27 @@ def test_load_data_limit_too_large_is_the_reference_panic(tree):
     with pytest.raises(ValueError) as e:
         D.load_data(path, 6, np.random.default_rng(0))
     assert str(e.value) == f"provided class_size_limit for {path} too large! expected 6 <= 5"   # rcn.rs:383-390
+
+
+def test_grayscale_uses_the_image_crates_integer_luma_not_rec601(tmp_path):
+    """`.grayscale()` of the `image` crate (rcn.rs:83,398): (2126 R + 7152 G + 722 B) / 10000, truncating -- a colour PNG
+    must give the reference's pixels, not Pillow's Rec.601 convert("L"); 16-bit input is the reference's error."""
+    rng = np.random.default_rng(3)
+    rgb = rng.integers(0, 256, size=(5, 6, 3), dtype=np.uint8)
+    r32 = rgb.astype(np.uint32)
+    want = ((2126 * r32[..., 0] + 7152 * r32[..., 1] + 722 * r32[..., 2]) // 10000).astype(np.uint8)
+    Image.fromarray(rgb, mode="RGB").save(tmp_path / "c.png")
+    got = D.load_grayscale(str(tmp_path / "c.png"))
+    assert np.array_equal(got, want)
+    assert not np.array_equal(got, np.asarray(Image.fromarray(rgb, mode="RGB").convert("L")))   # Rec.601 differs
+    rgba = np.concatenate([rgb, rng.integers(0, 256, size=(5, 6, 1), dtype=np.uint8)], axis=-1)
+    Image.fromarray(rgba, mode="RGBA").save(tmp_path / "a.png")
+    assert np.array_equal(D.load_grayscale(str(tmp_path / "a.png")), want)                      # alpha ignored (lib.rs:34-38)
+    pal = Image.fromarray(rgb, mode="RGB").quantize(8)
+    pal.save(tmp_path / "p.png")
+    p_rgb = np.asarray(pal.convert("RGB"), dtype=np.uint32)
+    assert np.array_equal(D.load_grayscale(str(tmp_path / "p.png")),
+                          ((2126 * p_rgb[..., 0] + 7152 * p_rgb[..., 1] + 722 * p_rgb[..., 2]) // 10000).astype(np.uint8))
+    Image.fromarray(rng.integers(0, 65536, size=(4, 4), dtype=np.uint16)).save(tmp_path / "s.png")   # 16-bit grey
+    with pytest.raises(D.InvalidGrayscaleImageError):
+        D.load_grayscale(str(tmp_path / "s.png"))

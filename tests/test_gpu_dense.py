@@ -337,7 +337,7 @@ def test_epoch_mode_and_cuda_graph(api):
     tr = DataParallelTrainer(graphed, eta=3.0)
     tr.bind_dataset(d_imgs, d_labels, B, perm=d_perm)
     tr.capture(warmup=2)
-    graphed.set_params(np.random.default_rng(3).standard_normal(graphed.n_params) * 0.05)   # undo the warm-up steps
+    # (capture() restores parameters and cursor after its own warm-up steps)
     for k in range(n_steps):
         tr.epoch_step()
     torch.cuda.synchronize()
@@ -345,14 +345,11 @@ def test_epoch_mode_and_cuda_graph(api):
     assert graphed.epoch_position() == 3 * B
 
 
-@pytest.mark.parametrize("B,N,n_steps", [(1024, 5000, 7), (512, 2100, 9), (96, 1000, 5)])
-def test_epoch_run_persistent_kernel_equals_steps(api, monkeypatch, B, N, n_steps):
-    """rcn_cuda_epoch_run: n steps as ONE persistent cooperative launch (grid barriers instead of kernel boundaries; B = 96
-    does not qualify and takes the per-step path) must equal n epoch_step calls -- same arithmetic; the weight-gradient
-    sum is split 4 x 2 ways over the batch instead of 8, so agreement is to summation order -- including the cursor
-    wrap-around, the last step's statistics and a second call that continues; and both must track the oracle."""
+@pytest.mark.parametrize("B,N,n_steps", [(1024, 5000, 7), (96, 1000, 5)])
+def test_epoch_run_equals_steps_and_oracle(api, B, N, n_steps):
+    """rcn_cuda_epoch_run (n iterations of the chunks_exact loop, rcn.rs:147-149, in one call) == n epoch_step calls, bit
+    for bit, including the cursor wrap-around and a second call that continues; and both track the oracle's literal loop."""
     import torch
-    monkeypatch.setenv("RCN_CUDA_PERSISTENT", "1")      # opt-in: read by the library on every rcn_cuda_epoch_run call
     rng = np.random.default_rng(B + n_steps)
     imgs = rng.integers(0, 256, size=(N, 28, 28), dtype=np.uint8)
     labels = rng.integers(0, 10, N).astype(np.int64)
@@ -371,16 +368,12 @@ def test_epoch_run_persistent_kernel_equals_steps(api, monkeypatch, B, N, n_step
     stepwise = fresh()
     for k in range(n_steps + 2):
         stepwise.epoch_step(3.0)
-    want_stats = stepwise.last_batch_stats()
     run = fresh()
     run.epoch_run(3.0, n_steps)
     run.epoch_run(3.0, 2)
     assert run.epoch_position() == stepwise.epoch_position()
-    assert_close(run.get_params(), stepwise.get_params(), rtol=1e-11, what="params: persistent launch vs per-step kernels")
-    assert_close(run.get_gradients(), stepwise.get_gradients(), rtol=1e-9, what="last gradients")
-    got_stats = run.last_batch_stats()
-    assert got_stats[1] == want_stats[1] and abs(got_stats[0] - want_stats[0]) <= 1e-11 * abs(want_stats[0])
-    # the oracle's literal loop over the same chunks (rcn.rs:147-149)
+    assert np.array_equal(run.get_params(), stepwise.get_params())
+    assert run.last_batch_stats() == stepwise.last_batch_stats()
     raw = O.features_u8(CP, imgs)
     X = O.standardise(raw, 20.0, 35.0)
     net = O.Net([(30, 784), (10, 30)])
@@ -391,61 +384,6 @@ def test_epoch_run_persistent_kernel_equals_steps(api, monkeypatch, B, N, n_step
         p, _ = net.train_batch(p, X[idx], np.eye(10)[labels[idx]], 3.0)
         pos = pos + B if pos + 2 * B <= N else 0
     assert_close(run.get_params(), p, rtol=1e-9, what="params vs oracle epoch loop")
-
-
-def test_epoch_pipeline_opt_in_equals_fused_steps(api, monkeypatch):
-    """RCN_CUDA_EPOCH_PIPELINE=1: the feature kernel of step k+1 runs on a parallel branch while step k trains (double-
-    buffered features, device-side cursors / step parity).  Same arithmetic as the fused kernel A, so parameters are
-    BIT-identical -- across the wrap-around, a mid-epoch seek, a scale change, an interleaved classify call (which must
-    not disturb the prefetched half) and a replayed CUDA graph with an odd number of steps."""
-    import torch
-    rng = np.random.default_rng(99)
-    N, B = 3000, 512
-    imgs = rng.integers(0, 256, size=(N, 28, 28), dtype=np.uint8)
-    labels = rng.integers(0, 10, N).astype(np.int64)
-    perm = rng.permutation(N).astype(np.int64)
-    cfg = [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max)]
-    d_imgs, d_labels, d_perm = torch.from_numpy(imgs).cuda(), torch.from_numpy(labels).cuda(), torch.from_numpy(perm).cuda()
-
-    def run(pipelined):
-        if pipelined:
-            monkeypatch.setenv("RCN_CUDA_EPOCH_PIPELINE", "1")
-        else:
-            monkeypatch.delenv("RCN_CUDA_EPOCH_PIPELINE", raising=False)
-        m = api.RCN(10, cfg, [30])
-        m.scale_set = (20.0, 35.0)
-        m.load_weights_and_bias(784)
-        m.set_params(np.random.default_rng(3).standard_normal(m.n_params) * 0.05)
-        m.epoch_bind(d_imgs, d_labels, B, perm=d_perm)
-        for _ in range(7):                       # 5 chunks per epoch: wraps
-            m.epoch_step(3.0)
-        m.classify_images(imgs[:300])            # uses the model's scratch feature buffer
-        m.epoch_step(3.0)
-        m.epoch_seek(2 * B)
-        m.epoch_step(3.0)
-        m.scale_set = (21.0, 34.0)               # prefetched features depend on the scale
-        m.epoch_step(3.0)
-        g = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            m.set_stream(side.cuda_stream)
-            m.epoch_step(3.0)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        with torch.cuda.graph(g):
-            m.set_stream(torch.cuda.current_stream().cuda_stream)
-            for _ in range(3):
-                m.epoch_step(3.0)
-        g.replay(); g.replay()
-        torch.cuda.synchronize()
-        m.set_stream(torch.cuda.current_stream().cuda_stream)
-        return m.get_params(), m.epoch_position(), m.last_batch_stats()
-
-    p_ref, pos_ref, st_ref = run(False)
-    p_pipe, pos_pipe, st_pipe = run(True)
-    assert pos_pipe == pos_ref and st_pipe == st_ref
-    assert np.array_equal(p_pipe.view(np.uint64), p_ref.view(np.uint64))
 
 
 def test_train_epoch_host_equals_step_by_step(api):
@@ -517,17 +455,20 @@ def test_train_epoch_host_streaming_large_chunks(api):
     assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
 
 
-@pytest.mark.parametrize("single_call", [False, True])
-def test_dp_peer_memory_exchange_two_gpus(api, single_call):
-    """Two ranks on two GPUs of this box (one process, peer access): the NVLink exchange + update -- as its own kernel
-    after accumulate (split calls) or inside the weight-gradient kernel's epilogue (train_batch_images, one call) -- keeps
-    the replicas bit-identical and equals single-GPU training on the global minibatch within summation order."""
+@pytest.mark.parametrize("same_device", [True, False])
+@pytest.mark.parametrize("single_call", [True, False])
+def test_dp_peer_memory_exchange_two_ranks(api, single_call, same_device):
+    """Two ranks in one process -- on two GPUs of this box (peer access over NVLink) or BOTH ON DEVICE 0 (the protocol is
+    the same: receive slots, sentinels, step parity, rank-ordered sum; this variant runs on a 1-GPU lease): the exchange +
+    update -- as its own kernel after accumulate (split calls) or behind the weight-gradient kernel's pushes
+    (train_batch_images, one call) -- keeps the replicas bit-identical and equals single-GPU training on the global minibatch
+    within summation order (rcn.rs:190-222)."""
     import torch
-    if torch.cuda.device_count() < 2:
+    if not same_device and torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import threading
     rng = np.random.default_rng(23)
-    Bg, steps = 128, 4
+    Bg, steps = 128, 6
     images = rng.integers(0, 256, size=(steps, Bg, 28, 28), dtype=np.uint8)
     labels = rng.integers(0, 10, size=(steps, Bg)).astype(np.int64)
     cfg = [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max)]
@@ -540,7 +481,7 @@ def test_dp_peer_memory_exchange_two_gpus(api, single_call):
     want = ref.get_params()
     ranks = []
     for r in range(2):
-        m = api.RCN(10, cfg, [30], device=r)
+        m = api.RCN(10, cfg, [30], device=0 if same_device else r)
         m.load_weights_and_bias(784)
         m.set_params(params); m.scale_set = (40.0, 60.0)
         m.dp_init(2, r)
@@ -548,21 +489,27 @@ def test_dp_peer_memory_exchange_two_gpus(api, single_call):
     for m in ranks:
         m.dp_connect_local(ranks)
     half = Bg // 2
+    errors = []
 
     def work(r):
-        m = ranks[r]
-        for k in range(steps):
-            if single_call:    # the shard is this rank's batch; the library scales by the global batch (rcn.rs:214)
-                m.train_batch_images(images[k, r * half:(r + 1) * half], labels[k, r * half:(r + 1) * half], 3.0)
-            else:
-                m.accumulate_gradients_images(images[k, r * half:(r + 1) * half], labels[k, r * half:(r + 1) * half])
-                m.apply_gradients(3.0, Bg)
-        m.synchronize()
+        try:
+            m = ranks[r]
+            for k in range(steps):
+                if single_call:    # the shard is this rank's batch; the library scales by the global batch (rcn.rs:214)
+                    m.train_batch_images(images[k, r * half:(r + 1) * half], labels[k, r * half:(r + 1) * half], 3.0)
+                else:
+                    m.accumulate_gradients_images(images[k, r * half:(r + 1) * half], labels[k, r * half:(r + 1) * half])
+                    m.apply_gradients(3.0, Bg)
+            m.synchronize()
+            m.dp_check()
+        except Exception as e:   # noqa: BLE001
+            errors.append((r, repr(e)))
 
     th = [threading.Thread(target=work, args=(r,)) for r in range(2)]
     [t.start() for t in th]
-    [t.join(timeout=60) for t in th]
+    [t.join(timeout=90) for t in th]
     assert not any(t.is_alive() for t in th), "ranks did not finish (exchange deadlock?)"
+    assert not errors, errors
     p0, p1 = ranks[0].get_params(), ranks[1].get_params()
     assert np.array_equal(p0, p1), "replicas must stay bit-identical"
     assert_close(p0, want, rtol=1e-9, what="2-rank parameters vs single GPU")
@@ -570,6 +517,138 @@ def test_dp_peer_memory_exchange_two_gpus(api, single_call):
     assert np.array_equal(g0, g1), "gradient buffers hold the same global sum on every rank"
     for m in ranks:
         m.dp_shutdown()
+
+
+def test_dp_epoch_graph_two_ranks_same_device_prewait(api):
+    """The data-parallel EPOCH step as the bench runs it -- device cursor, kernel B pushing to the peer and advancing the
+    cursor, the small exchange kernel, and the next step's kernel A running its front end ahead of griddepcontrol.wait --
+    captured into one CUDA graph per rank (4 steps each) and replayed; two ranks on device 0, each on its own stream.
+    Replicas bit-identical, parameters equal to single-GPU training on the concatenated global batches, cursor wraps."""
+    import threading
+    import torch
+    rng = np.random.default_rng(77)
+    B, n_chunks, steps = 64, 5, 12            # per-rank batch; 5 chunks per epoch -> the cursor wraps twice
+    N = B * n_chunks + 17                      # chunks_exact drops the remainder
+    shard = [rng.integers(0, 256, size=(N, 28, 28), dtype=np.uint8) for _ in range(2)]
+    shard_labels = [rng.integers(0, 10, size=N).astype(np.int64) for _ in range(2)]
+    cfg = [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max)]
+    params = np.random.default_rng(78).standard_normal(23860) * 0.05
+    ref = api.RCN(10, cfg, [30], device=0)
+    ref.load_weights_and_bias(784); ref.set_params(params); ref.scale_set = (40.0, 60.0)
+    pos = 0
+    for k in range(steps):
+        gi = np.concatenate([shard[0][pos:pos + B], shard[1][pos:pos + B]])
+        gl = np.concatenate([shard_labels[0][pos:pos + B], shard_labels[1][pos:pos + B]])
+        ref.train_batch_images(gi, gl, 3.0)
+        pos = pos + B if pos + 2 * B <= N else 0
+    want = ref.get_params()
+    ranks, streams, graphs, data = [], [], [], []
+    for r in range(2):
+        m = api.RCN(10, cfg, [30], device=0)
+        m.load_weights_and_bias(784); m.set_params(params); m.scale_set = (40.0, 60.0)
+        m.dp_init(2, r)
+        ranks.append(m)
+    for m in ranks:
+        m.dp_connect_local(ranks)
+    for r, m in enumerate(ranks):
+        st = torch.cuda.Stream()
+        streams.append(st)
+        di, dl = torch.from_numpy(shard[r]).cuda(), torch.from_numpy(shard_labels[r]).cuda()
+        data.append((di, dl))
+        m.set_stream(st.cuda_stream)
+        m.epoch_bind(di, dl, B)
+    torch.cuda.synchronize()
+    errors = []
+
+    def warm(r):   # one eager step per rank sizes every buffer (no allocation may happen inside a capture)
+        try:
+            ranks[r].epoch_step(3.0)
+            ranks[r].synchronize()
+        except Exception as e:   # noqa: BLE001
+            errors.append((r, repr(e)))
+
+    th = [threading.Thread(target=warm, args=(r,)) for r in range(2)]
+    [t.start() for t in th]
+    [t.join(timeout=90) for t in th]
+    assert not any(t.is_alive() for t in th) and not errors, errors
+    for m in ranks:
+        m.set_params(params)
+        m.epoch_seek(0)
+    # capture 4 steps per rank (capture executes nothing); both graphs are then replayed 3 times from two host threads
+    for r, m in enumerate(ranks):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=streams[r]):
+            m.set_stream(streams[r].cuda_stream)
+            for _ in range(4):
+                m.epoch_step(3.0)
+        graphs.append(g)
+
+    def work(r):
+        try:
+            with torch.cuda.stream(streams[r]):
+                for _ in range(steps // 4):
+                    graphs[r].replay()
+            streams[r].synchronize()
+            ranks[r].dp_check()
+        except Exception as e:   # noqa: BLE001
+            errors.append((r, repr(e)))
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+    [t.start() for t in th]
+    [t.join(timeout=90) for t in th]
+    assert not any(t.is_alive() for t in th), "ranks did not finish (exchange deadlock?)"
+    assert not errors, errors
+    p0, p1 = ranks[0].get_params(), ranks[1].get_params()
+    assert np.array_equal(p0, p1), "replicas must stay bit-identical"
+    assert_close(p0, want, rtol=1e-9, what="2-rank graph-replayed epoch steps vs single GPU")
+    assert ranks[0].epoch_position() == pos and ranks[1].epoch_position() == pos
+    for m in ranks:
+        m.dp_shutdown()
+
+
+DP_TIMEOUT_SCRIPT = r"""
+import json, sys, time
+import numpy as np
+sys.path.insert(0, %(root)r)
+from mercer_research_b200 import RCN, Padding, Pooling, RCNLayer, _lib
+cfg = [RCNLayer.Convolve2D(Padding.Same), RCNLayer.Pool2D(Pooling.Max)]
+ranks = []
+for r in range(2):
+    m = RCN(10, cfg, [30], device=0)
+    m.load_weights_and_bias(784)
+    m.set_params(np.random.default_rng(1).standard_normal(m.n_params) * 0.05)
+    m.dp_init(2, r)
+    ranks.append(m)
+for m in ranks:
+    m.dp_connect_local(ranks)
+rng = np.random.default_rng(2)
+images = rng.integers(0, 256, size=(32, 28, 28), dtype=np.uint8)
+labels = rng.integers(0, 10, size=32)
+t0 = time.time()
+ranks[0].train_batch_images(images, labels, 3.0)        # rank 1 never steps: its pushes never arrive
+raised = ""
+try:
+    ranks[0].dp_check()
+except _lib.RcnCudaError as e:
+    raised = str(e)
+print(json.dumps({"seconds": time.time() - t0, "raised": raised, "params_nan": bool(np.isnan(ranks[0].get_params()).any())}))
+"""
+
+
+def test_dp_exchange_times_out_instead_of_hanging(built_library):
+    """a rank whose peer never pushes (died, raised before its launch, ran fewer steps) must not spin in a GPU
+    kernel forever: the receive is bounded, sets the block's error word, and the host gets RCN_ERR_STATE."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RCN_CUDA_DP_TIMEOUT_MS="300")
+    out = subprocess.run([sys.executable, "-c", DP_TIMEOUT_SCRIPT % {"root": root}], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert "timed out" in r["raised"], r
+    assert r["params_nan"], r
+    assert r["seconds"] < 60, r
 
 
 def test_checkpoint_round_trip_on_device(api, tmp_path):
@@ -676,7 +755,7 @@ def test_cached_step_graphs_survive_buffer_growth(api):
     tr = DataParallelTrainer(graphed, eta=3.0)
     tr.bind_dataset(d_imgs, d_labels, B)
     tr.capture(warmup=1, steps_per_graph=2)
-    graphed.set_params(np.random.default_rng(32).standard_normal(graphed.n_params) * 0.1)   # undo the warm-up step
+    # (capture() restores parameters and cursor after its own warm-up steps)
     tr.epoch_steps(2)
     gen = tr._graph_generation
     graphed.classify_images(torch.from_numpy(big).cuda())         # grows the model's feature / activation buffers
@@ -725,7 +804,7 @@ def test_cached_step_graphs_follow_scale_set(api):
     tr = DataParallelTrainer(graphed, eta=3.0)
     tr.bind_dataset(images.cuda(), labels.cuda(), B)
     tr.capture(warmup=1, steps_per_graph=3)
-    graphed.set_params(np.random.default_rng(42).standard_normal(graphed.n_params) * 0.1)   # undo the warm-up step
+    # (capture() restores parameters and cursor after its own warm-up steps)
     tr.epoch_steps(6)
     graphed.scale_set = (25.0, 45.0)
     tr.epoch_steps(6)
@@ -796,3 +875,59 @@ def test_wide_layer_beyond_exact_int32_range_stays_on_dmma(api):
     with pytest.raises(api.RcnCudaError) as e:
         ext.gemm_f64(a, b, impl=1)
     assert e.value.status == 1 and "exact int32" in e.value.message
+
+
+def _nccl_numpy_worker(rank, world, port, out_dir):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import torch
+    import torch.distributed as dist
+    import mercer_research_b200 as m
+    from mercer_research_b200.trainer import DataParallelTrainer, shard_bounds
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    rng = np.random.default_rng(51)
+    Bg, steps = 256, 5
+    images = rng.integers(0, 256, size=(steps, Bg, 28, 28), dtype=np.uint8)
+    labels = rng.integers(0, 10, size=(steps, Bg)).astype(np.int64)
+    cfg = [m.RCNLayer.Convolve2D(m.Padding.Same), m.RCNLayer.Pool2D(m.Pooling.Max)]
+    model = m.RCN(10, cfg, [30], device=rank)
+    model.load_weights_and_bias(784)
+    model.set_params(np.random.default_rng(52).standard_normal(model.n_params) * 0.05)
+    model.scale_set = (40.0, 60.0)
+    trainer = DataParallelTrainer(model, eta=3.0, exchange="nccl")
+    assert not trainer.p2p
+    lo, hi = shard_bounds(Bg, rank, world)
+    for k in range(steps):   # numpy (host) inputs: the library used to run these on its private stream, unordered with NCCL
+        trainer.step_images_host(images[k, lo:hi], labels[k, lo:hi])
+    torch.cuda.synchronize()
+    np.save(os.path.join(out_dir, f"nccl_params_{rank}.npy"), model.get_params())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_nccl_exchange_with_host_inputs_two_gpus(api, tmp_path):
+    """the NCCL path with numpy inputs must order the library's kernels, the all-reduce and the update on one
+    stream (DataParallelTrainer binds the model to torch's current stream before every sequence). 2 processes x 1 GPU."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_nccl_numpy_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    p0, p1 = np.load(tmp_path / "nccl_params_0.npy"), np.load(tmp_path / "nccl_params_1.npy")
+    assert np.array_equal(p0, p1), "replicas must stay bit-identical"
+    rng = np.random.default_rng(51)
+    images = rng.integers(0, 256, size=(5, 256, 28, 28), dtype=np.uint8)
+    labels = rng.integers(0, 10, size=(5, 256)).astype(np.int64)
+    cfg = [api.RCNLayer.Convolve2D(api.Padding.Same), api.RCNLayer.Pool2D(api.Pooling.Max)]
+    ref = api.RCN(10, cfg, [30], device=0)
+    ref.load_weights_and_bias(784)
+    ref.set_params(np.random.default_rng(52).standard_normal(ref.n_params) * 0.05)
+    ref.scale_set = (40.0, 60.0)
+    for k in range(5):
+        ref.train_batch_images(images[k], labels[k], 3.0)
+    assert_close(p0, ref.get_params(), rtol=1e-9, what="2-GPU NCCL (host inputs) vs single GPU")
