@@ -242,7 +242,7 @@ def run_reference(args, wl, rank, world):
         "impl": "reference", "metric": "training images/sec", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": done, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "batch_per_step": Bs, "pixels": "u8", "eta": ETA,
+        "config": {"workload": wl["desc"], "batch_per_step": Bs, "batch_per_gpu": wl["batch"], "pixels": "u8", "eta": ETA,
                    "note": "C++ restatement of rcn's CPU path (oracle/rcn_oracle.cpp: per-sample matvec backprop, worker threads "
                            "+ mutex-ordered gradient sum as rcn.rs:176-223); the Rust crate cannot be built here (no rustc)"},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
@@ -296,203 +296,69 @@ def measure_fp64_peak(torch, dev):
     return 2 * n ** 3 / (best * 1e-3) / 1e12
 
 
-def run_gpu(args, wl, rank, world, local_rank):
-    import torch
-    import torch.distributed as dist
+def measure_int8_peak(torch, dev):
+    """cuBLASLt IGEMM 8192^3 (s8 x s8 -> s32, torch._int_mm): the int8 tensor-pipe denominator of the tcgen05 integer-slice
+    GEMMs, MEASURED on this box (round 1 assumed 2 x the bf16 figure). Returns (TOP/s, how) or (None, why)."""
+    try:
+        n = 8192
+        a = torch.randint(-128, 128, (n, n), dtype=torch.int8, device=dev)
+        b = torch.randint(-128, 128, (n, n), dtype=torch.int8, device=dev)
+        torch._int_mm(a, b)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch._int_mm(a, b); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        del a, b
+        return 2 * n ** 3 / (best * 1e-3) / 1e12, "torch._int_mm (cuBLASLt IGEMM s8*s8->s32) 8192^3, best of 5, measured in this run"
+    except Exception as e:  # noqa: BLE001
+        return None, f"int8 IGEMM probe failed ({type(e).__name__}: {e})"
 
-    from mercer_research_b200 import RCN, _lib
-    from mercer_research_b200.trainer import DataParallelTrainer
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    B, H, W = wl["batch"], wl["H"], wl["W"]
-    shapes = layer_shapes(wl)
+class Ctx:
+    pass
+
+
+def _barrier(ctx):
+    ctx.torch.cuda.synchronize()
+    if ctx.world > 1:
+        ctx.dist.barrier()
+    ctx.torch.cuda.synchronize()
+
+
+def _max_over_ranks(ctx, x):
+    if ctx.world == 1:
+        return x
+    t = ctx.torch.tensor([x], dtype=ctx.torch.float64, device=ctx.dev)
+    ctx.dist.all_reduce(t, op=ctx.dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def on_tc(M, N, K):                                   # mirrors use_tensor_cores() in csrc/dense.cu
+    tiles = -(-M // 128) * -(-N // 96)
+    return M >= 256 and N >= 256 and K >= 512 and K <= 16384 and tiles >= 74 and float(M) * N * K >= 4.0e9
+
+
+def kernel_rooflines(wl, B, shapes, prof, prof_steps, pk, fp64_peak, int8_peak):
+    """Per-kernel achieved rates from the eager per-launch CUDA-event pass (`prof`: name -> launches, total_ms) against the
+    algorithmic work of DESIGN.md section 4. Returns (kernels dict, name of the kernel with the largest share)."""
+    H, W = wl["H"], wl["W"]
     L = shapes[0][1]
     n_params = sum(r * c + r for r, c in shapes)
-
-    model = RCN(wl["classes"], wl["cfg"], wl["ff"], device=local_rank)
-    assert model.feature_len(H, W) == L
-    model.load_weights_and_bias(L)
-    assert model.layer_shapes == shapes
-    model.set_params(np.random.default_rng(PARAM_SEED).standard_normal(n_params))   # same replica on every rank
-    trainer = DataParallelTrainer(model, eta=ETA, exchange=args.exchange)
-
-    # synthetic dataset resident in HBM, larger than L2 (126 MB) so that consecutive steps never hit in L2
-    pool_bytes = 192 << 20
-    n_batches = max(4, -(-pool_bytes // (B * H * W)))
-    g = torch.Generator(device=dev); g.manual_seed(DATA_SEED + rank)
-    images = torch.randint(0, 256, (n_batches, B, H, W), dtype=torch.uint8, device=dev, generator=g)
-    labels = (torch.arange(B, device=dev) % wl["classes"]).to(torch.int64)
-    raw = model.flatten_feature_set(images[0][:min(B, 1024)])
-    model.gen_scales(raw)                       # (mean, sd) are fixed inputs on the streaming path
-    if world > 1:                               # every replica must use the same scale_set
-        ms = torch.tensor(model.scale_set, dtype=torch.float64, device=dev)
-        dist.broadcast(ms, 0)
-        model.scale_set = tuple(ms.tolist())
-    del raw
-
-    stream = torch.cuda.current_stream(dev)
-    model.set_stream(stream.cuda_stream)
-
-    # epoch mode: the resident dataset is walked in chunks_exact(B) steps by a device-side cursor (rcn.rs:144-149),
-    # so ONE captured CUDA graph (all kernels + the all-reduce) replays for every step.
-    all_labels = labels.repeat(n_batches)
-    trainer.bind_dataset(images.view(n_batches * B, H, W), all_labels, B)
-    step_desc = trainer.describe()
-    kernels_per_step = None
-    if not args.no_graph:
-        l_before = _lib.kernel_launches()
-        # the timed region is a whole number of replays: the largest divisor of K that is <= --steps-per-graph
-        if world == 1:
-            spg = max(d for d in range(1, max(1, min(args.steps_per_graph, args.steps)) + 1) if args.steps % d == 0)
-        else:   # multi-GPU runs keep the graph shapes they were validated with on this pool (gcd with at most 8)
-            spg = max(1, math.gcd(args.steps, min(args.steps_per_graph, 8)))
-        trainer.capture(warmup=3, steps_per_graph=spg)
-        kernels_per_step = (_lib.kernel_launches() - l_before) // (3 + spg)   # 3 warm-up steps + spg captured steps
-    else:
-        spg = 1
-
-    def step(i):                                # warm-up unit: one graph replay (= spg steps) or one eager step
-        trainer.epoch_step()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    # warm-up: at least W steps and at least ~0.3 s of the same load, so clocks have ramped before the timed region
-    n_warm = max(args.warmup, 3)
-    t_w = time.perf_counter()
-    for i in range(n_warm):
-        step(i)
-    torch.cuda.synchronize()
-    per_step = max((time.perf_counter() - t_w) / n_warm, 1e-6)
-    extra = torch.tensor([min(200000, int(0.3 / per_step))], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.broadcast(extra, 0)            # every rank must run the same number of (all-reducing) steps
-    for i in range(int(extra.item())):
-        step(n_warm + i)
-    n_warm += int(extra.item())
-    barrier()
-    l0 = _lib.kernel_launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clocks.mark_begin()
-    e0.record(stream)
-    trainer.epoch_steps(args.steps)             # exactly K steps: K / spg replays of the spg-step graph
-    e1.record(stream)
-    barrier()
-    clocks.mark_end()
-    launches = _lib.kernel_launches() - l0
-    if kernels_per_step is not None and launches == 0:
-        launches = kernels_per_step * args.steps   # graph replays re-launch the captured kernels (the counter only sees
-                                                   # launches made through the library, e.g. the persistent step kernel)
-    ms_total = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = world * B / (ms_step * 1e-3)
-
-    # ---- e2e: the reference-facing call with HOST buffers (pinned): the chunks_exact loop of rcn.rs:147-149 over a
-    # host-resident dataset; every step's H2D copy and the D2H read of its (cost, hits) are inside the timed region -----
-    n_host = max(2, min(args.steps, (512 << 20) // (B * H * W)))
-    h_images = torch.randint(0, 256, (n_host * B, H, W), dtype=torch.uint8).pin_memory()
-    h_labels = (torch.arange(n_host * B) % wl["classes"]).to(torch.int64).pin_memory()
-    hi, hl = h_images.numpy(), h_labels.numpy()
-    host_alloc = "pinned"
-    if args.host_alloc == "wc":
-        # opt-in experiment: the same dataset in WRITE-COMBINED pinned memory (cudaHostAllocWriteCombined). The e2e path is
-        # bound by the rate at which the GPU can read host memory (38 GB/s from ordinary pinned pages);
-        # write-combined pages are not snooped in the CPU caches on the way out. Not the default until it is measured.
-        wc = _wc_pinned_copy(hi)
-        if wc is not None:
-            hi, host_alloc = wc, "pinned, write-combined"
-
-    def e2e_steps(n):
-        done = 0
-        while done < n:
-            m = min(n_host, n - done)
-            cost, hits = trainer.train_epoch_host(hi[:m * B], hl[:m * B], B)
-            assert len(cost) == m
-            done += m
-
-    e2e_steps(min(n_host, args.steps))          # warm-up at the timed call's size: buffers sized, step graphs captured
-    barrier()
-    clocks.mark_begin()
-    e0.record(stream)
-    e2e_steps(args.steps)
-    e1.record(stream)
-    barrier()
-    clocks.mark_end()
-    clk = clocks.stop() if rank == 0 else None
-    e2e_ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_value = world * B / (e2e_ms / args.steps * 1e-3)
-    h2d = B * H * W + B * 8
-    d2h = 16
-
-    # ---- per-kernel durations (CUDA events on the launching stream) for the roofline; separate eager pass that EVERY
-    # rank runs (the exchange kernel / all-reduce needs all of them); rank 0 reports its own records ------------------
-    prof_steps = min(args.steps, 50)
-    barrier()
-    _lib.profile_enable(True)
-    for i in range(prof_steps):
-        trainer.step_images(images[i % n_batches], labels)
-    torch.cuda.synchronize()
-    prof = _lib.profile_report()
-    _lib.profile_enable(False)
-    barrier()
-
-    # every collective is done: tear the process group down on ALL ranks together, then rank 0 alone continues with
-    # the single-GPU profiling pass and the CPU baseline (nothing below uses torch.distributed)
-    if world > 1:
-        trainer.graph = None            # the captured graph holds NCCL work: drop it before leaving the group
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        if trainer.p2p:                 # rank 0's profiling pass below must not wait for peers that have left
-            model.dp_shutdown()
-            trainer.p2p = False
-            dist.barrier()
-        if rank != 0:
-            # destroy_process_group() was seen to block with a captured NCCL graph on this stack (torch 2.11 / NCCL
-            # 2.28): leave without running the destructors; every collective has completed at the barrier above.
-            sys.stdout.flush(); sys.stderr.flush()
-            os._exit(0)
-    if rank != 0:
-        return
-
-    print("[bench] rank 0: collective phases done", file=sys.stderr, flush=True)
-    pk = peaks()
     fwd, bwd_d, bwd_w = dense_flops_per_image(shapes)
     sum_rows = sum(r for r, _ in shapes)
     act_bytes = 2 * sum_rows * 8                      # a_l and delta_l written once per sample
-    int8_peak = 2.0 * (pk["bf16_tflops"] or 1590.0)   # kind::i8 issues at twice the bf16 rate; bf16 is the measured figure
-
-    def on_tc(M, N, K):                               # mirrors use_tensor_cores() in csrc/dense.cu
-        tiles = -(-M // 128) * -(-N // 96)
-        return M >= 256 and N >= 256 and K >= 512 and K <= 16384 and tiles >= 74 and float(M) * N * K >= 4.0e9
-
-    # algorithmic work per step of each kernel NAME: name -> [bound, bytes, flops]; the per-launch
-    # figure is this divided by the launches per step the profiler counted
     alg = {
         "features_fused_kernel": ["hbm", B * (H * W * 1 + L * 8), B * 48 * H * W],
-        "smallnet_fwd_bwd_kernel(fused features)": ["hbm", B * (H * W * 1 + 8 + L * 8 + act_bytes) + n_params * 8,
+        "smallnet_fwd_bwd_kernel(fused features)": ["fp64", B * (H * W * 1 + 8 + L * 8 + act_bytes) + n_params * 8,
                                                     B * (48 * H * W + fwd + bwd_d)],
-        "smallnet_fwd_bwd_kernel": ["hbm", B * (L * 8 + 8 + act_bytes) + n_params * 8, B * (fwd + bwd_d)],
-        "smallnet_wgrad_kernel": ["hbm", B * (L + shapes[0][0]) * 8 + n_params * 8, B * bwd_w],
-        "smallnet_wgrad_kernel(+SGD update)": ["hbm", B * (L + shapes[0][0]) * 8 + 3 * n_params * 8, B * bwd_w + 2 * n_params],
-        "smallnet_wgrad_kernel(+exchange+SGD update)": ["hbm", B * (L + shapes[0][0]) * 8 + 3 * n_params * 8, B * bwd_w + 2 * n_params],
+        "smallnet_fwd_bwd_kernel(fused features, front end ahead of the exchange)": ["fp64", B * (H * W * 1 + 8 + L * 8 + act_bytes) + n_params * 8,
+                                                                                      B * (48 * H * W + fwd + bwd_d)],
+        "smallnet_fwd_bwd_kernel": ["fp64", B * (L * 8 + 8 + act_bytes) + n_params * 8, B * (fwd + bwd_d)],
+        "smallnet_wgrad_kernel": ["fp64", B * (L + shapes[0][0]) * 8 + n_params * 8, B * bwd_w],
+        "smallnet_wgrad_kernel(+SGD update)": ["fp64", B * (L + shapes[0][0]) * 8 + 3 * n_params * 8, B * bwd_w + 2 * n_params],
+        "smallnet_wgrad_kernel(+exchange+SGD update)": ["fp64", B * (L + shapes[0][0]) * 8 + 3 * n_params * 8, B * bwd_w + 2 * n_params],
         "features_cp_kernel": ["hbm", B * (H * W * 1 + L * 8), B * 48 * H * W],
         "sgd_update_kernel": ["hbm", 3 * n_params * 8, 2 * n_params],
         "dp_allreduce_sgd_kernel": ["hbm", 3 * n_params * 8, 2 * n_params],
@@ -520,15 +386,14 @@ def run_gpu(args, wl, rank, world, local_rank):
     alg["ozaki_slice"] = ["hbm", slice_bytes, 0]      # both slicing kernels together: 8 B read + 5 B written per element
     kernels = {k: {"launches_per_step": v["launches"] / prof_steps, "avg_us": v["total_ms"] / v["launches"] * 1e3,
                    "share": None} for k, v in prof.items()}
-    tot = sum(v["total_ms"] for v in prof.values())
-    fp64_peak = measure_fp64_peak(torch, dev)
+    tot = sum(v["total_ms"] for v in prof.values()) or 1.0
     for k, v in prof.items():
         kernels[k]["share"] = round(v["total_ms"] / tot, 4)
-        key = "ozaki_slice" if k.startswith("ozaki_slice") else k
+        key = "ozaki_slice" if k.startswith("ozaki_slice") or k.startswith("ozaki_amax") else k
         if key in alg:
             d_s = v["total_ms"] / prof_steps * 1e-3          # seconds of this kernel name per step
             if key == "ozaki_slice":
-                d_s = sum(x["total_ms"] for n_, x in prof.items() if n_.startswith("ozaki_slice")) / prof_steps * 1e-3
+                d_s = sum(x["total_ms"] for n_, x in prof.items() if n_.startswith("ozaki_slice") or n_.startswith("ozaki_amax")) / prof_steps * 1e-3
             bnd, nbytes, nflops = alg[key]
             kernels[k]["bound"] = bnd
             if nbytes:
@@ -541,35 +406,394 @@ def run_gpu(args, wl, rank, world, local_rank):
             elif nflops:
                 kernels[k]["TFLOPs_f64"] = round(nflops / d_s / 1e12, 3)
                 kernels[k]["frac_fp64"] = round(nflops / d_s / 1e12 / fp64_peak, 4)
-    top = max(prof, key=lambda k: prof[k]["total_ms"])
-    bound, nbytes, nflops = alg.get(top, ("hbm", 0, 0))
-    dur_s = prof[top]["total_ms"] / prof_steps * 1e-3        # all launches of the top kernel in one step
-    peak_source = pk["source"]
-    if bound == "hbm":
-        achieved, peak, unit = nbytes / dur_s / 1e9, pk["hbm_gbs"], "GB/s"
-    elif "tcgen05" in top:
-        achieved, peak, unit = 15 * nflops / dur_s / 1e12, int8_peak, "TFLOP/s"
-        peak_source = ("int8 tensor peak taken as 2 x the measured bf16 cuBLAS figure of MEASURED_PEAKS.json (kind::i8 issues at twice "
-                       "the bf16 rate; nominal 4500); achieved = 15 exact int8 digit-plane products per f64 product, in int8 TOP/s")
+    top = max(prof, key=lambda k: prof[k]["total_ms"]) if prof else None
+    return kernels, top, alg
+
+
+def run_leg(ctx, name, wl, B, steps, warmup, exchange, *, main, steps_per_graph=16, no_graph=False, host_alloc="pinned"):
+    """One workload on this rank: device-resident `value` leg (epoch mode, CUDA graph), host-buffer `e2e` leg, eager per-kernel
+    profile; the main leg (c2) additionally reads the in-graph device timeline. Collective on every rank; returns a dict
+    (rank 0's view; timings are max over ranks)."""
+    torch, dist, dev, rank, world = ctx.torch, ctx.dist, ctx.dev, ctx.rank, ctx.world
+    from mercer_research_b200 import RCN, _lib
+    from mercer_research_b200.trainer import DataParallelTrainer
+    H, W = wl["H"], wl["W"]
+    shapes = layer_shapes(wl)
+    L = shapes[0][1]
+    n_params = sum(r * c + r for r, c in shapes)
+    model = RCN(wl["classes"], wl["cfg"], wl["ff"], device=ctx.local_rank)
+    assert model.feature_len(H, W) == L
+    model.load_weights_and_bias(L)
+    assert model.layer_shapes == shapes
+    scale = 1.0 if L <= 1024 else 1.0 / 64.0        # the 4096-wide layers: N(0,1)/64 keeps the sigmoids out of saturation
+    model.set_params(np.random.default_rng(PARAM_SEED).standard_normal(n_params) * scale)   # same replica on every rank
+    trainer = DataParallelTrainer(model, eta=ETA, exchange=exchange)
+
+    # synthetic dataset resident in HBM, larger than L2 (126 MB) so that consecutive steps never hit in L2
+    pool_bytes = 192 << 20
+    n_batches = max(4, -(-pool_bytes // (B * H * W)))
+    g = torch.Generator(device=dev); g.manual_seed(DATA_SEED + rank)
+    images = torch.randint(0, 256, (n_batches, B, H, W), dtype=torch.uint8, device=dev, generator=g)
+    labels = (torch.arange(B, device=dev) % wl["classes"]).to(torch.int64)
+    raw = model.flatten_feature_set(images[0][:min(B, 1024)])
+    model.gen_scales(raw)                       # (mean, sd) are fixed inputs on the streaming path (SURVEY.md 8a a6)
+    if world > 1:                               # every replica must use the same scale_set
+        ms = torch.tensor(model.scale_set, dtype=torch.float64, device=dev)
+        dist.broadcast(ms, 0)
+        model.scale_set = tuple(ms.tolist())
+    del raw
+    stream = torch.cuda.current_stream(dev)
+    model.set_stream(stream.cuda_stream)
+    use_timeline = main and not no_graph
+
+    # epoch mode: the resident dataset is walked in chunks_exact(B) steps by a device-side cursor (rcn.rs:144-149),
+    # so ONE captured CUDA graph (all kernels + the exchange) replays for every step.
+    all_labels = labels.repeat(n_batches)
+    trainer.bind_dataset(images.view(n_batches * B, H, W), all_labels, B)
+    step_desc = trainer.describe()
+    graph_ok = not no_graph and (world == 1 or trainer.p2p)   # the NCCL all-reduce is issued eagerly (a captured NCCL
+                                                              # graph blocked destroy_process_group on this stack)
+    kernels_per_step = None
+    if graph_ok:
+        l_before = _lib.kernel_launches()
+        # the timed region is a whole number of replays: the largest divisor of K that is <= --steps-per-graph
+        spg = max(d for d in range(1, max(1, min(steps_per_graph, steps)) + 1) if steps % d == 0)
+        trainer.capture(warmup=3, steps_per_graph=spg)
+        kernels_per_step = (_lib.kernel_launches() - l_before) // (3 + spg)   # 3 warm-up steps + spg captured steps
     else:
-        achieved, peak, unit = nflops / dur_s / 1e12, fp64_peak, "TFLOP/s"
-        peak_source = "torch.matmul f64 8192^3 measured in this run (f64 DMMA path; MEASURED_PEAKS.json has no f64 figure)"
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed `ncu --set full` capture
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.workload, {}).get(top)
+        spg = 1
+        l_before = _lib.kernel_launches()
+        for _ in range(2):
+            trainer.epoch_step()
+        torch.cuda.synchronize()
+        kernels_per_step = (_lib.kernel_launches() - l_before) // 2
+
+    clocks = ClockSampler(ctx.local_rank)
+    if rank == 0:
+        clocks.start()
+    # warm-up: at least W steps and at least ~0.3 s of the same load, so clocks have ramped before the timed region
+    n_warm = max(warmup, 3)
+    t_w = time.perf_counter()
+    for i in range(n_warm):
+        trainer.epoch_step()
+    torch.cuda.synchronize()
+    per_step = max((time.perf_counter() - t_w) / n_warm, 1e-6)
+    extra = torch.tensor([min(200000, int(0.3 / per_step))], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(extra, 0)            # every rank must run the same number of (exchanging) steps
+    for i in range(int(extra.item())):
+        trainer.epoch_step()
+    n_warm += int(extra.item())
+    _barrier(ctx)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.mark_begin()
+    e0.record(stream)
+    trainer.epoch_steps(steps)              # exactly K steps: K / spg replays of the spg-step graph
+    e1.record(stream)
+    _barrier(ctx)
+    clocks.mark_end()
+    trainer.check()
+    launches = kernels_per_step * steps
+    ms_step = _max_over_ranks(ctx, e0.elapsed_time(e1)) / steps
+    value = world * B / (ms_step * 1e-3)
+
+    # ---- in-graph device timeline of the step kernels (durations inside the replayed graph, and the gaps between them) ----
+    # A SEPARATE pass after the timed region (the stamps cost atomics and fences inside the kernels): enabling the timeline
+    # bumps the allocation generation, so the trainer re-captures its graph with the timeline pointer baked in.
+    timeline = None
+    if use_timeline and graph_ok:
+        model.timeline_enable(True)
+        trainer.epoch_steps(4 * spg if spg >= 16 else 64 // spg * spg)
+        torch.cuda.synchronize()
+        trainer.check()
+    if use_timeline and graph_ok and rank == 0:
+        t0, t1, n_l = model.timeline_read()
+        tl = {}
+        names = {0: "kernel A (features+fwd+bwd-data)", 1: "kernel B (bwd-weight + update / push)", 2: "exchange+update kernel"}
+        spans = {}
+        for k in (0, 1, 2):
+            n = int(n_l[k])
+            if n < 8:
+                continue
+            idx = [(n - 1 - j) % 64 for j in range(min(48, n - 1))]       # the most recent launches (all inside the timed replays)
+            d = (t1[k, idx].astype(np.int64) - t0[k, idx].astype(np.int64)) * 1e-3
+            spans[k] = (t0[k, idx].astype(np.int64), t1[k, idx].astype(np.int64))
+            tl[names[k]] = {"us_mean": float(d.mean()), "us_min": float(d.min()), "us_max": float(d.max()), "launches_seen": n}
+        if 0 in spans and 1 in spans:
+            a0, a1 = spans[0]; b0, b1 = spans[1]
+            gap_ab = (b0 - a1) * 1e-3                                     # same index = same step
+            tl["gap A->B us"] = float(np.median(gap_ab))
+            last = spans[2][1] if 2 in spans else b1                      # what precedes the next kernel A
+            nxt = np.array([a0[j - 1] - last[j] for j in range(1, len(a0))]) * 1e-3   # idx is newest first: a0[j-1] is the later step
+            tl["gap (end of step k) -> kernel A(k+1) us"] = float(np.median(nxt))
+        timeline = tl
+    if use_timeline and graph_ok:
+        model.timeline_enable(False)
+        _barrier(ctx)
+
+    # ---- e2e: the reference-facing call with HOST buffers (pinned): the chunks_exact loop of rcn.rs:147-149 over a
+    # host-resident dataset; every step's H2D copy and the D2H read of its (cost, hits) are inside the timed region -----
+    e2e_steps_n = steps
+    n_host = max(2, min(e2e_steps_n, (512 << 20) // (B * H * W)))
+    h_images = torch.randint(0, 256, (n_host * B, H, W), dtype=torch.uint8).pin_memory()
+    h_labels = (torch.arange(n_host * B) % wl["classes"]).to(torch.int64).pin_memory()
+    hi, hl = h_images.numpy(), h_labels.numpy()
+    if host_alloc == "wc":
+        # opt-in experiment: the same dataset in WRITE-COMBINED pinned memory (cudaHostAllocWriteCombined)
+        wc = _wc_pinned_copy(hi)
+        if wc is not None:
+            hi, host_alloc = wc, "pinned, write-combined"
+
+    def e2e_run(n):
+        done = 0
+        while done < n:
+            m = min(n_host, n - done)
+            cost, hits = trainer.train_epoch_host(hi[:m * B], hl[:m * B], B)
+            assert len(cost) == m
+            done += m
+
+    e2e_run(min(n_host, e2e_steps_n))           # warm-up at the timed call's size: buffers sized, step graphs captured
+    _barrier(ctx)
+    clocks.mark_begin()
+    e0.record(stream)
+    e2e_run(e2e_steps_n)
+    e1.record(stream)
+    _barrier(ctx)
+    clocks.mark_end()
+    trainer.check()
+    clk = clocks.stop() if rank == 0 else None
+    e2e_ms = _max_over_ranks(ctx, e0.elapsed_time(e1))
+    e2e_value = world * B / (e2e_ms / e2e_steps_n * 1e-3)
+    h2d = B * H * W + B * 8
+    d2h = 16
+
+    # ---- per-kernel durations (CUDA events on the launching stream): separate eager pass that EVERY rank runs ------------
+    prof_steps = min(steps, 50)
+    _barrier(ctx)
+    _lib.profile_enable(True)
+    for i in range(prof_steps):
+        trainer.step_images(images[i % n_batches], labels)
+    torch.cuda.synchronize()
+    prof = _lib.profile_report()
+    _lib.profile_enable(False)
+    trainer.check()
+    _barrier(ctx)
+
+    # ---- data-parallel parity self-check (world > 1): 3 steps from fixed parameters on fixed global batches; rank 0 later
+    # repeats them on ONE GPU and through the oracle ----------------------------------------------------------------------
+    parity = None
+    if world > 1 and main:
+        p0 = np.random.default_rng(PARAM_SEED + 1).standard_normal(n_params) * 0.05
+        model.set_params(p0)
+        prng = np.random.default_rng(DATA_SEED + 99)
+        pg_images = prng.integers(0, 256, size=(3, world * B, H, W), dtype=np.uint8)
+        pg_labels = prng.integers(0, wl["classes"], size=(3, world * B)).astype(np.int64)
+        for k in range(3):
+            trainer.step_images(torch.from_numpy(pg_images[k, rank * B:(rank + 1) * B]).to(dev),
+                                torch.from_numpy(pg_labels[k, rank * B:(rank + 1) * B]).to(dev))
+        torch.cuda.synchronize()
+        trainer.check()
+        mine = torch.from_numpy(model.get_params()).to(dev)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        if rank == 0:
+            allp = [t.cpu().numpy() for t in gathered]
+            parity = {"steps": 3, "global_batch": world * B,
+                      "replicas_bit_identical": bool(all(np.array_equal(allp[0].view(np.uint64), q.view(np.uint64)) for q in allp[1:])),
+                      "_p0": p0, "_images": pg_images, "_labels": pg_labels, "_dp_params": allp[0], "_scale": model.scale_set}
+
+    out = {"name": name, "wl": wl, "B": B, "shapes": shapes, "n_params": n_params, "n_batches": n_batches, "value": value,
+           "ms_step": ms_step, "steps": steps, "spg": spg, "graph": graph_ok, "n_warm": n_warm * spg, "launches": int(launches),
+           "step_desc": step_desc, "clocks": clk, "e2e_value": e2e_value, "e2e_ms_step": e2e_ms / e2e_steps_n, "h2d": h2d, "d2h": d2h,
+           "host_alloc": host_alloc, "prof": prof, "prof_steps": prof_steps, "timeline": timeline, "parity": parity,
+           "p2p": trainer.p2p, "scale_set": model.scale_set}
+    # leave the group state clean for the next leg
+    if world > 1:
+        trainer.graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        if trainer.p2p:
+            model.dp_shutdown()
+            trainer.p2p = False
+            dist.barrier()
+    model.close()
+    del trainer, model, images, h_images, h_labels
+    torch.cuda.empty_cache()
+    return out
+
+
+def leg_roofline(leg, pk, fp64_peak, int8_peak, int8_how, traffic_all, workload_key):
+    """Roofline record of one leg."""
+    wl, B, shapes = leg["wl"], leg["B"], leg["shapes"]
+    H, W = wl["H"], wl["W"]
+    n_params = leg["n_params"]
+    fwd, bwd_d, bwd_w = dense_flops_per_image(shapes)
+    kernels, top, alg = kernel_rooflines(wl, B, shapes, leg["prof"], leg["prof_steps"], pk, fp64_peak, int8_peak)
+    ms_step = leg["ms_step"]
     step_bytes = B * (H * W + 8) + 3 * n_params * 8           # compulsory HBM traffic of a whole step (intermediates on chip / in L2)
+    # SURVEY.md 8d per-image figures: feature stage 12 MAC/px/op x 4 ops (48 flop/px incl. zero taps) + dense fwd / bwd-data / bwd-weight
     step_flops = B * (48 * H * W + fwd + bwd_d + bwd_w)
-    roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-                "frac": achieved / peak if peak else None, "traffic": traffic,
-                "peak_source": peak_source,
-                "precision": "f64", "fp64_dgemm_tflops_measured": fp64_peak,
-                "durations": "CUDA events around every launch on the launching stream, separate eager pass of "
-                             f"{prof_steps} steps (the timed region replays a CUDA graph)",
-                "whole_step": {"ms": ms_step, "compulsory_GBps": step_bytes / (ms_step * 1e-3) / 1e9,
-                               "TFLOPs_f64": step_flops / (ms_step * 1e-3) / 1e12,
-                               "frac_fp64": step_flops / (ms_step * 1e-3) / 1e12 / fp64_peak},
-                "kernels": kernels}
+    dense_flops = B * (fwd + bwd_d + bwd_w)
+    whole = {"ms": ms_step, "compulsory_GBps": step_bytes / (ms_step * 1e-3) / 1e9,
+             "frac_hbm_compulsory": step_bytes / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"],
+             "TFLOPs_f64": step_flops / (ms_step * 1e-3) / 1e12, "frac_fp64": step_flops / (ms_step * 1e-3) / 1e12 / fp64_peak,
+             "TFLOPs_f64_dense_only": dense_flops / (ms_step * 1e-3) / 1e12,
+             "frac_fp64_dense_only": dense_flops / (ms_step * 1e-3) / 1e12 / fp64_peak}
+    traffic = (traffic_all.get(workload_key, {}) or {}).get(top) if top else None
+    small = top is not None and top.startswith("smallnet")
+    if small:
+        # the fused narrow-network step: two kernels that are ONE dependent chain; 99 flop per compulsory byte against an FP64
+        # ridge of ~5 flop/B => FP64-pipe-bound in the limit. The fraction is the WHOLE step (kernel A + kernel B + the
+        # boundaries, timed in the replayed graph) against the DGEMM peak measured in this run; per-kernel durations come
+        # from the in-graph device timeline.
+        rl = {"kernel": "fused step = " + " + ".join(sorted(k for k in leg["prof"] if k.startswith("smallnet"))),
+              "bound": "fp64", "achieved": whole["TFLOPs_f64"], "peak": fp64_peak, "unit": "TFLOP/s", "frac": whole["frac_fp64"],
+              "traffic": traffic,
+              "peak_source": "torch.matmul f64 8192^3 (cuBLAS DGEMM) measured in this run; MEASURED_PEAKS.json has no f64 figure",
+              "achieved_is": "SURVEY 8d algorithmic flops of one step (48 flop/px feature stage + dense fwd/bwd-data/bwd-weight) / "
+                             "the step's duration in the timed, graph-replayed region (CUDA events, max over ranks)",
+              "hbm": {"achieved_GBps": whole["compulsory_GBps"], "peak_GBps": pk["hbm_gbs"], "frac": whole["frac_hbm_compulsory"],
+                      "note": "compulsory bytes of the step (u8 images + labels + 3 x parameters); secondary: the step is not HBM-bound"}}
+        if leg["timeline"]:
+            tl = leg["timeline"]
+            rl["in_graph_timeline"] = tl
+            a = tl.get("kernel A (features+fwd+bwd-data)")
+            b = tl.get("kernel B (bwd-weight + update / push)")
+            if a:
+                fa = B * (48 * H * W + fwd + bwd_d)
+                rl["kernel_A"] = {"us": a["us_mean"], "TFLOPs_f64": fa / (a["us_mean"] * 1e-6) / 1e12,
+                                  "frac_fp64": fa / (a["us_mean"] * 1e-6) / 1e12 / fp64_peak}
+            if b:
+                fb = B * bwd_w
+                rl["kernel_B"] = {"us": b["us_mean"], "TFLOPs_f64": fb / (b["us_mean"] * 1e-6) / 1e12,
+                                  "frac_fp64": fb / (b["us_mean"] * 1e-6) / 1e12 / fp64_peak}
+    else:
+        bound, nbytes, nflops = alg.get(top, ("hbm", 0, 0)) if top else ("hbm", 0, 0)
+        dur_s = leg["prof"][top]["total_ms"] / leg["prof_steps"] * 1e-3 if top else 1.0
+        peak_source = pk["source"]
+        if bound == "hbm":
+            achieved, peak, unit = nbytes / dur_s / 1e9, pk["hbm_gbs"], "GB/s"
+        elif top and "tcgen05" in top:
+            achieved, peak, unit = 15 * nflops / dur_s / 1e12, int8_peak, "TFLOP/s"
+            peak_source = "int8 tensor peak: " + int8_how + "; achieved = 15 exact int8 digit-plane products per f64 product, in int8 TOP/s"
+        else:
+            achieved, peak, unit = nflops / dur_s / 1e12, fp64_peak, "TFLOP/s"
+            peak_source = "torch.matmul f64 8192^3 measured in this run (f64 DMMA path; MEASURED_PEAKS.json has no f64 figure)"
+        rl = {"kernel": top, "bound": "tensor" if bound == "fp64" else bound, "achieved": achieved, "peak": peak, "unit": unit,
+              "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_source}
+    rl.update({"precision": "f64", "fp64_dgemm_tflops_measured": fp64_peak, "int8_tops_measured": int8_peak, "int8_peak_how": int8_how,
+               "durations": "per-kernel: CUDA events around every launch on the launching stream, separate eager pass of "
+                            f"{leg['prof_steps']} steps (shares); fused c2 step: in-graph device timeline (%globaltimer stamps, "
+                            "rcn_cuda_timeline_read) + the timed region itself",
+               "whole_step": whole, "kernels": kernels})
+    return rl
+
+
+def _teardown_group(ctx):
+    """destroy_process_group() on every rank; it was seen to block on this stack (torch 2.11 / NCCL 2.28) after NCCL work
+    had been captured into a CUDA graph, so it runs under a watchdog: if it has not returned after 20 s the process leaves
+    without it (every collective has completed at the barrier before)."""
+    if ctx.world == 1:
+        return
+    ctx.torch.cuda.synchronize()
+    ctx.dist.barrier()
+    done = threading.Event()
+
+    def destroy():
+        try:
+            ctx.dist.destroy_process_group()
+        finally:
+            done.set()
+
+    th = threading.Thread(target=destroy, daemon=True)
+    th.start()
+    if not done.wait(20.0):
+        print(f"[bench] rank {ctx.rank}: destroy_process_group() did not return within 20 s; leaving without it", file=sys.stderr, flush=True)
+        ctx.hung_teardown = True
+
+
+def run_gpu(args, wl, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    ctx = Ctx()
+    ctx.torch, ctx.dist, ctx.rank, ctx.world, ctx.local_rank = torch, dist, rank, world, local_rank
+    ctx.dev = torch.device("cuda", local_rank)
+    ctx.hung_teardown = False
+    if world > 1:
+        dist.init_process_group("nccl", device_id=ctx.dev)
+
+    # ---- main leg: BASELINE configs[1] (or --workload), per-GPU batch fixed (weak scaling) --------------------------------
+    main = run_leg(ctx, args.workload, wl, wl["batch"], args.steps, args.warmup, args.exchange, main=True,
+                   steps_per_graph=args.steps_per_graph, no_graph=args.no_graph, host_alloc=args.host_alloc)
+    # ---- extra legs in the same invocation: c3 (STRONG scaling: global batch 4096 split over the ranks, SURVEY 8e) and c5
+    # (weak, NCCL all-reduce of the 268.8 MB gradient buffer at N > 1) -----------------------------------------------------
+    legs = {}
+    if args.workload == "c2" and not args.no_extra:
+        for key in [k for k in args.extra.split(",") if k]:
+            w2 = WORKLOADS[key]
+            if key == "c3":
+                if w2["batch"] % world:
+                    continue
+                B2, st2, ex2, scaling = w2["batch"] // world, max(16, min(args.steps, 320) // 16 * 16), "auto", "strong"
+            else:
+                B2, st2, ex2, scaling = w2["batch"], max(4, min(args.steps, 12)), ("nccl" if world > 1 else "auto"), "weak"
+            try:
+                leg = run_leg(ctx, key, w2, B2, st2, min(args.warmup, 3), ex2, main=False, steps_per_graph=16)
+                leg["scaling"] = scaling
+                legs[key] = leg
+            except Exception as e:  # noqa: BLE001  -- an extra leg must never cost the main line
+                if world > 1:
+                    raise
+                legs[key] = {"error": f"{type(e).__name__}: {e}"}
+                print(f"[bench] extra leg {key} failed: {e}", file=sys.stderr, flush=True)
+
+    _teardown_group(ctx)
+    if rank != 0:
+        sys.stdout.flush(); sys.stderr.flush()
+        if ctx.hung_teardown:
+            os._exit(0)
+        return
+
+    print("[bench] rank 0: collective phases done", file=sys.stderr, flush=True)
+    pk = peaks()
+    fp64_peak = measure_fp64_peak(torch, ctx.dev)
+    int8_peak, int8_how = measure_int8_peak(torch, ctx.dev)
+    if int8_peak is None:
+        int8_how = int8_how + "; FALLBACK: 2 x the measured bf16 cuBLAS figure of MEASURED_PEAKS.json"
+        int8_peak = 2.0 * (pk["bf16_tflops"] or 1590.0)
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed `ncu --set full` capture
+    traffic_all = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    roofline = leg_roofline(main, pk, fp64_peak, int8_peak, int8_how, traffic_all, args.workload)
+
+    # ---- data-parallel parity: the 3 fixed steps again on ONE GPU and through the oracle ------------------------------------
+    parity = None
+    if main["parity"]:
+        import oracle as O
+        from mercer_research_b200 import RCN
+        pr = main["parity"]
+        single = RCN(wl["classes"], wl["cfg"], wl["ff"], device=local_rank)
+        single.load_weights_and_bias(main["shapes"][0][1])
+        single.set_params(pr["_p0"])
+        single.scale_set = pr["_scale"]
+        net = O.Net(main["shapes"])
+        p_or = pr["_p0"].copy()
+        mean, sd = pr["_scale"]
+        for k in range(3):
+            single.train_batch_images(pr["_images"][k], pr["_labels"][k], ETA)
+            X = O.standardise(O.features_u8(wl["cfg"], pr["_images"][k]), mean, sd)
+            p_or, _ = net.train_batch(p_or, X, np.eye(wl["classes"])[pr["_labels"][k]], ETA, n_threads=os.cpu_count() or 1)
+        p_single = single.get_params()
+        single.close()
+
+        def max_rel(a, b):
+            return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+        parity = {"steps": 3, "global_batch": pr["global_batch"], "replicas_bit_identical": pr["replicas_bit_identical"],
+                  "max_rel_vs_single_gpu": max_rel(pr["_dp_params"], p_single), "max_rel_vs_oracle": max_rel(pr["_dp_params"], p_or),
+                  "single_gpu_max_rel_vs_oracle": max_rel(p_single, p_or), "tolerance": 1e-9,
+                  "what": "post-step parameters after 3 SGD steps from fixed parameters on fixed global batches (rcn.rs:190-222), "
+                          "element-wise relative; oracle = C++ restatement (parity unpinned by the reference's own tests)"}
 
     print("[bench] rank 0: cpu baseline", file=sys.stderr, flush=True)
     # ---- CPU baseline on this box's host cores (bounded sample, ~10-20 s) ------------------------------------------
@@ -578,35 +802,59 @@ def run_gpu(args, wl, rank, world, local_rank):
     # BASELINE.json configs[0] (the reference's own CPU-runnable case: the same network at batch 32), ~3 s more
     c1_ips, _, c1_done, _, _ = cpu_train_steps(WORKLOADS["c1"], steps=10 ** 6, warmup=2, max_seconds=3.0)
 
+    B, H, W = main["B"], wl["H"], wl["W"]
+    workloads = {}
+    for key, leg in legs.items():
+        if "error" in leg:
+            workloads[key] = leg
+            continue
+        w2 = leg["wl"]
+        rl2 = leg_roofline(leg, pk, fp64_peak, int8_peak, int8_how, traffic_all, key)
+        workloads[key] = {
+            "workload": w2["desc"], "value": leg["value"], "unit": "images/s", "ms_per_step": leg["ms_step"], "steps": leg["steps"],
+            "scaling": leg["scaling"], "batch_per_gpu": leg["B"], "global_batch": leg["B"] * world, "params": leg["n_params"],
+            "exchange": ("none (1 GPU)" if world == 1 else ("NVLink peer-memory exchange kernel" if leg["p2p"] else "NCCL all-reduce (eager)")),
+            "cuda_graph": leg["graph"], "steps_per_graph": leg["spg"], "gpu_launches": leg["launches"],
+            "e2e": {"value": leg["e2e_value"], "unit": "images/s", "ms_per_step": leg["e2e_ms_step"],
+                    "h2d_bytes_per_step": leg["h2d"], "d2h_bytes_per_step": leg["d2h"]},
+            "clocks": leg["clocks"], "roofline": rl2,
+        }
+
     line = {
-        "metric": "training images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": "training images/sec", "value": main["value"], "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": main["ms_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "batch_per_gpu": B, "global_batch": B * world, "pixels": "u8", "eta": ETA,
-                   "params": n_params, "parallelism": f"dp{world}",
-                   "l2_policy": f"inputs rotate over {n_batches} resident batches = {n_batches * B * H * W / 2 ** 20:.0f} MiB > 126 MB L2",
-                   "step": step_desc, "cuda_graph": not args.no_graph, "steps_per_graph": spg,
+        "config": {"workload": wl["desc"], "batch_per_gpu": B, "batch_per_step": B, "global_batch": B * world, "pixels": "u8", "eta": ETA,
+                   "params": main["n_params"], "parallelism": f"dp{world}",
+                   "l2_policy": f"inputs rotate over {main['n_batches']} resident batches = {main['n_batches'] * B * H * W / 2 ** 20:.0f} MiB > 126 MB L2 "
+                                "(each step's kernel A asks L2 for the NEXT step's images ahead of time; every image still comes from HBM once per step)",
+                   "step": main["step_desc"], "cuda_graph": main["graph"], "steps_per_graph": main["spg"],
                    # the W requested warm-up steps plus ~0.3 s of the same load so that clocks have ramped
-                   "warmup_steps_run": n_warm * spg},
-        "clocks": clk,
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / args.steps, "host_buffers": host_alloc,
+                   "warmup_steps_run": main["n_warm"]},
+        "clocks": main["clocks"],
+        "e2e": {"value": main["e2e_value"], "unit": "images/s", "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": main["d2h"],
+                "ms_per_step": main["e2e_ms_step"], "host_buffers": main["host_alloc"],
                 # PCIe bytes per second this rank pulled inside the timed region (the e2e path's own bound: SM-issued
                 # zero-copy reads reach ~38 GB/s on this pool's boxes, profiles/r1s_full_host_prefetch.txt)
-                "h2d_GBps_per_gpu": h2d / (e2e_ms / args.steps * 1e-3) * 1e-9,
+                "h2d_GBps_per_gpu": main["h2d"] / (main["e2e_ms_step"] * 1e-3) * 1e-9,
                 "api": "rcn_cuda_train_epoch_host (chunks_exact loop over a pinned host dataset: the GPU pulls chunk k+1 over PCIe "
-                       "while chunk k trains, one CUDA graph launch per step, per-step cost/hits written back to host memory)"},
-        "gpu_launches": int(launches),
+                       "while chunk k trains, one CUDA graph launch per two steps, per-step cost/hits written back to host memory)"},
+        "gpu_launches": int(main["launches"]),
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_ips, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": f"{cpu_done} steps of batch {Bs} (features+fwd+bwd+SGD) on {cores} host threads, "
                                    "oracle/rcn_oracle.cpp (C++ restatement of rcn's CPU path, not rustc output)",
                          "configs0_batch32": {"value": c1_ips, "unit": "images/s", "cores": cores,
                                               "sample": f"{c1_done} steps of batch 32, same network, same {cores} host threads"}},
+        "parity_note": "parity unpinned: the oracle is a C++ restatement of rcn (no Rust toolchain); only kernel.rs:400-441 pin it",
     }
+    if parity:
+        line["parity"] = parity
+    if workloads:
+        line["workloads"] = workloads
     emit_result(line)
-    if world > 1:
-        sys.stdout.flush(); sys.stderr.flush()
+    sys.stdout.flush(); sys.stderr.flush()
+    if ctx.hung_teardown:
         os._exit(0)
 
 
@@ -623,6 +871,8 @@ def main():
                     help="e2e leg: ordinary pinned host memory (default) or write-combined pinned memory (experiment)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
                     help="multi-GPU gradient exchange: fused NVLink peer-memory kernel, NCCL all-reduce, or by size")
+    ap.add_argument("--extra", default="c3,c5", help="extra workloads measured after the main one in the same run (parsed.workloads)")
+    ap.add_argument("--no-extra", action="store_true", help="main workload only")
     args = ap.parse_args()
     # stdout must carry exactly ONE JSON line: route everything else that writes to fd 1 (e.g. NCCL's version banner)
     # to stderr and keep the real stdout for the result line.

@@ -152,8 +152,11 @@ int launch_dp_allreduce_sgd(const DpState& st, double* params, double* grads, do
     if (st.n == 0) return RCN_OK;
     DpPush pp = dp_push_desc(st);
     pp.tl = tl;
+    // rcn's canonical network (23 860 parameters): <= 20 fat CTAs, so that kernel A of the next step (128 CTAs, a whole SM
+    // each) runs beside this kernel; larger buffers are bandwidth work and spread over the machine
     unsigned grid = cdiv(st.n, kDpThreads);
-    if (grid > (unsigned)kDpMaxCtas) grid = kDpMaxCtas;
+    if (grid <= 2u * kDpMaxCtas) { if (grid > (unsigned)kDpMaxCtas) grid = kDpMaxCtas; }
+    else if (grid > 2u * kNumSMs) grid = 2u * kNumSMs;
     static const bool pdl = []() { const char* e = getenv("RCN_CUDA_PDL"); return !(e && e[0] == '0'); }();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid, 1, 1);

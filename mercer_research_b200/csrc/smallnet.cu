@@ -540,6 +540,8 @@ constexpr int SNB_TILE = 32 * 64;   // padded partial tile: 32 rows x 64 columns
 // Whatever the mode, when `upd.cursor` is set the statistics thread also advances the epoch cursor and writes the per-step
 // result ring (on a data-parallel group that makes the cursor final BEFORE the exchange kernel runs, which is what lets the
 // next step's kernel A read it ahead of its griddepcontrol.wait).
+// (Measured and dropped, round 2: 48 columns per CTA = 17 column groups x 8 K-splits + 8 = 144 CTAs "one per SM" ran 11.2 us
+// instead of 6.1 -- B200 co-schedules only ~15 clusters of 8 CTAs, so 18 clusters take two waves.)
 // CW: columns of dW0 per CTA: 64 (one warp per 8 columns) or 32 (two warps per 8 columns, each taking half of every
 // 64-sample chunk; their two partial tiles are added, in order, by the reduction).
 template <int MODE, int CW>
@@ -722,12 +724,16 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
             }
         }
     }
-    cluster.sync();   // nobody leaves while a peer may still read its tile
+    // nobody leaves while a peer may still read its tile.  RELAXED arrive: this barrier orders no memory (a peer arrives after
+    // it has consumed the values it read from my tile), so it must not wait for this CTA's global stores to drain the way
+    // the release fence of cluster.sync() does (ncu: 9 % of the kernel's samples sat in that membar).
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
     if (DPX && tid == 0) dp_finish_step(dp, total_ctas);
     RCN_TL_END(d.tl, 1);
 }
 
-template <int MODE>
+template <int MODE, int CW>
 __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __grid_constant__ SmallNetDesc d,
                                                                      const double* __restrict__ feats,
                                                                      const double* __restrict__ small_partial,
@@ -743,7 +749,7 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
     // no early trigger there (the implicit one at completion stands); a single GPU keeps the early trigger.
     if (dp.world <= 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    sn_phase_b<MODE, 64>(d, feats, small_partial, deltas, B, ksplit, col_groups, grads, stats_partial, n_stat, stats, dp, upd,
+    sn_phase_b<MODE, CW>(d, feats, small_partial, deltas, B, ksplit, col_groups, grads, stats_partial, n_stat, stats, dp, upd,
                          (int)blockIdx.x, (int)blockIdx.y, (int)gridDim.y, sP_dyn, sD_static, gridDim.x * gridDim.y);
 }
 
@@ -878,10 +884,11 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
     static SmemAttrCache attr_b;
     if (attr_b.need(smem_b)) {  // static 36 KB + dynamic tile exceeds the 48 KB default; all variants at once (a later
                                 // launch of another variant may happen inside a stream capture)
-        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(col_groups + 1, splits, 1);
@@ -900,7 +907,7 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
     cfg.attrs = attr;
     cfg.numAttrs = sn_pdl_enabled() ? 3 : 2;
     const int Bi = (int)B;
-    auto kern = mode == 1 ? smallnet_wgrad_kernel<1> : mode == 2 ? smallnet_wgrad_kernel<2> : mode == 3 ? smallnet_wgrad_kernel<3> : smallnet_wgrad_kernel<0>;
+    auto kern = mode == 1 ? smallnet_wgrad_kernel<1, 64> : mode == 2 ? smallnet_wgrad_kernel<2, 64> : mode == 3 ? smallnet_wgrad_kernel<3, 64> : smallnet_wgrad_kernel<0, 64>;
     RCN_LAUNCH(mode == 2 ? "smallnet_wgrad_kernel(+SGD update)" : mode == 3 ? "smallnet_wgrad_kernel(+exchange+SGD update)" : "smallnet_wgrad_kernel", stream,
                cudaLaunchKernelEx(&cfg, kern, d, (const double*)feats, (const double*)small_partial, (const double*)deltas, Bi,
                                   ksplit, col_groups, grads, (const double*)stats_partial, n_tiles, stats, push, upd));

@@ -31,7 +31,7 @@ def shard_bounds(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
 
 # One-shot exchange over NVLink peer memory (csrc/dp.cu) is used while every rank pushes at most this many bytes per
 # step; above it the exchange is bandwidth-bound and NCCL's all-reduce (ring / NVLS in-switch reduction) wins.
-P2P_MAX_PUSH_BYTES = 8 << 20
+P2P_MAX_PUSH_BYTES = 16 << 20
 
 
 class DataParallelTrainer:

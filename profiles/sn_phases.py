@@ -77,64 +77,29 @@ def timeline(B=1024, steps=40):
     for _ in range(5):
         g.replay()
     torch.cuda.synchronize()
-    lib = model._lib
-    assert lib.rcn_cuda_debug_timeline_reset_smallnet() == 0 and lib.rcn_cuda_debug_timeline_reset_dense() == 0
-    for _ in range(steps // 8):
+    model.timeline_enable(True)          # bumps the allocation generation: capture again with the timeline pointer baked in
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        model.set_stream(torch.cuda.current_stream().cuda_stream)
+        for _ in range(8):
+            model.epoch_step(3.0)
+    for _ in range(max(1, steps // 8)):
         g.replay()
     torch.cuda.synchronize()
-    K, R = 4, 64
-    a = np.zeros((2, K, R), dtype=np.uint64); sa = np.zeros(K, dtype=np.uint32)
-    d = np.zeros((2, K, R), dtype=np.uint64); sd = np.zeros(K, dtype=np.uint32)
-    assert lib.rcn_cuda_debug_timeline_read_smallnet(a.ctypes.data_as(C.c_void_p), sa.ctypes.data_as(C.c_void_p)) == 0
-    assert lib.rcn_cuda_debug_timeline_read_dense(d.ctypes.data_as(C.c_void_p), sd.ctypes.data_as(C.c_void_p)) == 0
-    fused = int(sd[0]) == 0   # the weight-gradient kernel applied the update: no sgd_update launches
-    n = int(min(sa[0], sa[1])) if fused else int(min(sa[0], sa[1], sd[0]))
-    A0, A1 = a[0, 0, :n].astype(np.int64), a[1, 0, :n].astype(np.int64)
-    B0, B1 = a[0, 1, :n].astype(np.int64), a[1, 1, :n].astype(np.int64)
-    sl = slice(5, n - 1)
-    rows = [("kernel A  first CTA start -> last CTA end", (A1 - A0)[sl]), ("gap A -> B", (B0 - A1)[sl]),
-            ("kernel B  span", (B1 - B0)[sl])]
-    if fused:
-        rows += [("gap B(+update) -> next kernel A", (A0[1:] - B1[:-1])[5:n - 2])]
-    else:
-        S0, S1 = d[0, 0, :n].astype(np.int64), d[1, 0, :n].astype(np.int64)
-        rows += [("gap B -> sgd_update", (S0 - B1)[sl]), ("sgd_update span", (S1 - S0)[sl]),
-                 ("gap sgd_update -> next kernel A", (A0[1:] - S1[:-1])[5:n - 2])]
-    rows += [("step period (A start to A start)", np.diff(A0)[5:n - 2])]
+    t0, t1, n_l = model.timeline_read()
+    n = int(min(n_l[0], n_l[1], 56))
+    order = [(int(n_l[0]) - n + j) % 64 for j in range(n)]          # oldest -> newest of the last n launches
+    A0, A1 = t0[0, order].astype(np.int64), t1[0, order].astype(np.int64)
+    orderb = [(int(n_l[1]) - n + j) % 64 for j in range(n)]
+    B0, B1 = t0[1, orderb].astype(np.int64), t1[1, orderb].astype(np.int64)
+    rows = [("kernel A  first CTA start -> last CTA end", (A1 - A0)), ("gap A -> B", (B0 - A1)), ("kernel B  span", (B1 - B0)),
+            ("gap B(+update) -> next kernel A", (A0[1:] - B1[:-1])), ("step period (A start to A start)", np.diff(A0))]
     print(f"graph-replayed c2 step, B={B}: {n} steps recorded; ns (median / min / max)")
     for name, v in rows:
         print(f"  {name:45s} {np.median(v):8.0f} {v.min():8.0f} {v.max():8.0f}")
 
 
-def persistent(B=1024, steps=50):
-    """Phase spans inside the persistent step kernel (rcn_cuda_epoch_run), %globaltimer stamps of the second-to-last step."""
-    dev = torch.device("cuda", 0)
-    model = RCN(10, [RCNLayer.Convolve2D(Padding.Same), RCNLayer.Pool2D(Pooling.Max)], [30])
-    model.load_weights_and_bias(784)
-    model.set_params(np.random.default_rng(1).standard_normal(model.n_params) * 0.1)
-    N = B * 64
-    imgs = torch.randint(0, 256, (N, 28, 28), dtype=torch.uint8, device=dev)
-    labels = (torch.arange(N, device=dev) % 10).to(torch.int64)
-    model.gen_scales(model.flatten_feature_set(imgs[:4096]))
-    model.epoch_bind(imgs, labels, B)
-    model.epoch_run(3.0, steps)
-    torch.cuda.synchronize()
-    out = np.zeros((1024, 8), dtype=np.int64)
-    assert model._lib.rcn_cuda_debug_snp_stamps(out.ctypes.data_as(C.c_void_p)) == 0
-    n = (B + 7) // 8
-    t = out[:n, :5]
-    t0 = t[:, 0].min()
-    print(f"persistent kernel, last step, {n} CTAs; ns relative to the first CTA's step start (min / median / max over CTAs)")
-    for k, name in enumerate(["step start", "phase A done", "barrier 1 passed", "phase B done", "step end"]):
-        v = t[:, k] - t0
-        print(f"  {name:20s} {v.min():8d} {int(np.median(v)):8d} {v.max():8d}")
-
-
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "persistent":
-        persistent(int(sys.argv[2]) if len(sys.argv) > 2 else 1024)
-        sys.exit(0)
-
     if len(sys.argv) > 1 and sys.argv[1] == "timeline":
         timeline(int(sys.argv[2]) if len(sys.argv) > 2 else 1024)
         sys.exit(0)

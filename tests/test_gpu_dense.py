@@ -519,13 +519,20 @@ def test_dp_peer_memory_exchange_two_ranks(api, single_call, same_device):
         m.dp_shutdown()
 
 
-def test_dp_epoch_graph_two_ranks_same_device_prewait(api):
+@pytest.mark.parametrize("graph", [False, True])
+def test_dp_epoch_steps_two_ranks_prewait(api, graph):
     """The data-parallel EPOCH step as the bench runs it -- device cursor, kernel B pushing to the peer and advancing the
     cursor, the small exchange kernel, and the next step's kernel A running its front end ahead of griddepcontrol.wait --
-    captured into one CUDA graph per rank (4 steps each) and replayed; two ranks on device 0, each on its own stream.
-    Replicas bit-identical, parameters equal to single-GPU training on the concatenated global batches, cursor wraps."""
+    queued back to back without any host synchronisation in between (so consecutive steps really overlap).  graph=False:
+    eager launches, two ranks on device 0, each on its own stream and host thread (runs on a 1-GPU lease).  graph=True: 4
+    steps per CUDA graph, replayed; needs two GPUs (two graphs replayed on ONE device were observed to run one after the
+    other, which starves the exchange).  Replicas bit-identical, parameters equal to single-GPU training on the concatenated
+    global batches, cursor wraps."""
     import threading
     import torch
+    if graph and torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    devs = (0, 1) if graph else (0, 0)
     rng = np.random.default_rng(77)
     B, n_chunks, steps = 64, 5, 12            # per-rank batch; 5 chunks per epoch -> the cursor wraps twice
     N = B * n_chunks + 17                      # chunks_exact drops the remainder
@@ -544,20 +551,21 @@ def test_dp_epoch_graph_two_ranks_same_device_prewait(api):
     want = ref.get_params()
     ranks, streams, graphs, data = [], [], [], []
     for r in range(2):
-        m = api.RCN(10, cfg, [30], device=0)
+        m = api.RCN(10, cfg, [30], device=devs[r])
         m.load_weights_and_bias(784); m.set_params(params); m.scale_set = (40.0, 60.0)
         m.dp_init(2, r)
         ranks.append(m)
     for m in ranks:
         m.dp_connect_local(ranks)
     for r, m in enumerate(ranks):
-        st = torch.cuda.Stream()
+        st = torch.cuda.Stream(device=devs[r])
         streams.append(st)
-        di, dl = torch.from_numpy(shard[r]).cuda(), torch.from_numpy(shard_labels[r]).cuda()
+        di, dl = torch.from_numpy(shard[r]).cuda(devs[r]), torch.from_numpy(shard_labels[r]).cuda(devs[r])
         data.append((di, dl))
         m.set_stream(st.cuda_stream)
         m.epoch_bind(di, dl, B)
-    torch.cuda.synchronize()
+    for d in set(devs):
+        torch.cuda.synchronize(d)
     errors = []
 
     def warm(r):   # one eager step per rank sizes every buffer (no allocation may happen inside a capture)
@@ -574,20 +582,27 @@ def test_dp_epoch_graph_two_ranks_same_device_prewait(api):
     for m in ranks:
         m.set_params(params)
         m.epoch_seek(0)
-    # capture 4 steps per rank (capture executes nothing); both graphs are then replayed 3 times from two host threads
+    # graph=True: capture 4 steps per rank (capture executes nothing); both graphs are then replayed 3 times from two threads
     for r, m in enumerate(ranks):
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=streams[r]):
-            m.set_stream(streams[r].cuda_stream)
-            for _ in range(4):
-                m.epoch_step(3.0)
+        if not graph:
+            break
+        with torch.cuda.device(devs[r]):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=streams[r]):
+                m.set_stream(streams[r].cuda_stream)
+                for _ in range(4):
+                    m.epoch_step(3.0)
         graphs.append(g)
 
     def work(r):
         try:
-            with torch.cuda.stream(streams[r]):
-                for _ in range(steps // 4):
-                    graphs[r].replay()
+            with torch.cuda.device(devs[r]), torch.cuda.stream(streams[r]):
+                if graph:
+                    for _ in range(steps // 4):
+                        graphs[r].replay()
+                else:
+                    for _ in range(steps):          # no host synchronisation between the steps
+                        ranks[r].epoch_step(3.0)
             streams[r].synchronize()
             ranks[r].dp_check()
         except Exception as e:   # noqa: BLE001
