@@ -40,6 +40,13 @@ WORKLOADS = {
     # configs[4]: 64x64 [C,P] -> 4096 feats -> 4096-4096-4096-10
     "c5": dict(desc="dense-heavy head 64x64 [C,P] 4096-4096-4096-10, batch 8192 per GPU",
                H=64, W=64, cfg=[1, 3], ff=[4096, 4096], classes=10, batch=8192),
+    # configs[3] in reference semantics: the "wide conv stack" is four stacked Convolve2D(Same) layers on 64x64 inputs -- the
+    # reference's convolution has no channel contraction, every layer fans each map out x4: 4 -> 16 -> 64 -> 256 maps of 64x64
+    # (SURVEY.md 8d C4).  Feature stage only (flatten_feature_set + standardise): 2 MiB x 4 of f64 features per image make a
+    # dense head meaningless; HBM-bound integer/byte work.  (The learned-convolution reading of this config is the (X)
+    # extension, profiles/conv_bench.py.)
+    "c4": dict(desc="wide conv stack 64x64 [Conv(Same)]x4 -> 256 maps of 64x64 (feature stage only), batch 128 per GPU",
+               H=64, W=64, cfg=[1, 1, 1, 1], ff=[30], classes=10, batch=128),
 }
 _RESULT_FD = 1
 
@@ -579,8 +586,10 @@ def run_leg(ctx, name, wl, B, steps, warmup, exchange, *, main, steps_per_graph=
     trainer.check()
     _barrier(ctx)
 
-    # ---- data-parallel parity self-check (world > 1): 3 steps from fixed parameters on fixed global batches; rank 0 later
-    # repeats them on ONE GPU and through the oracle ----------------------------------------------------------------------
+    # ---- data-parallel parity self-check (world > 1), through the SAME path the timed region uses: fixed parameters, a fixed
+    # 3-chunk dataset bound in epoch mode, 3 steps per captured CUDA graph, two replays back to back (6 SGD steps, the cursor
+    # wraps once; kernel B advances the cursor, the exchange kernel runs under the next step's front end).  Rank 0 later
+    # repeats the 6 global minibatches on ONE GPU and through the oracle ---------------------------------------------------
     parity = None
     if world > 1 and main:
         p0 = np.random.default_rng(PARAM_SEED + 1).standard_normal(n_params) * 0.05
@@ -588,9 +597,12 @@ def run_leg(ctx, name, wl, B, steps, warmup, exchange, *, main, steps_per_graph=
         prng = np.random.default_rng(DATA_SEED + 99)
         pg_images = prng.integers(0, 256, size=(3, world * B, H, W), dtype=np.uint8)
         pg_labels = prng.integers(0, wl["classes"], size=(3, world * B)).astype(np.int64)
-        for k in range(3):
-            trainer.step_images(torch.from_numpy(pg_images[k, rank * B:(rank + 1) * B]).to(dev),
-                                torch.from_numpy(pg_labels[k, rank * B:(rank + 1) * B]).to(dev))
+        d_pi = torch.from_numpy(np.ascontiguousarray(pg_images[:, rank * B:(rank + 1) * B]).reshape(3 * B, H, W)).to(dev)
+        d_pl = torch.from_numpy(np.ascontiguousarray(pg_labels[:, rank * B:(rank + 1) * B]).reshape(3 * B)).to(dev)
+        trainer.bind_dataset(d_pi, d_pl, B)
+        if graph_ok:
+            trainer.capture(warmup=1, steps_per_graph=3)     # restores parameters and cursor after its warm-up step
+        trainer.epoch_steps(6)
         torch.cuda.synchronize()
         trainer.check()
         mine = torch.from_numpy(model.get_params()).to(dev)
@@ -598,8 +610,10 @@ def run_leg(ctx, name, wl, B, steps, warmup, exchange, *, main, steps_per_graph=
         dist.all_gather(gathered, mine)
         if rank == 0:
             allp = [t.cpu().numpy() for t in gathered]
-            parity = {"steps": 3, "global_batch": world * B,
+            parity = {"steps": 6, "global_batch": world * B,
                       "replicas_bit_identical": bool(all(np.array_equal(allp[0].view(np.uint64), q.view(np.uint64)) for q in allp[1:])),
+                      "path": ("epoch mode, 3 steps per CUDA graph, 2 replays" if graph_ok else "epoch mode, eager steps") +
+                              (", NVLink peer-memory exchange" if trainer.p2p else ", NCCL all-reduce"),
                       "_p0": p0, "_images": pg_images, "_labels": pg_labels, "_dp_params": allp[0], "_scale": model.scale_set}
 
     out = {"name": name, "wl": wl, "B": B, "shapes": shapes, "n_params": n_params, "n_batches": n_batches, "value": value,
@@ -620,6 +634,53 @@ def run_leg(ctx, name, wl, B, steps, warmup, exchange, *, main, steps_per_graph=
     del trainer, model, images, h_images, h_labels
     torch.cuda.empty_cache()
     return out
+
+
+def run_features_leg(ctx, name, wl, B, steps):
+    """BASELINE configs[3] in reference semantics: throughput of the feature stage alone (rcn_cuda_features) on every rank
+    (independent replicas: the stage has no exchange step). Device-resident inputs; the 1 GiB output per call exceeds L2."""
+    torch, dev, rank, world = ctx.torch, ctx.dev, ctx.rank, ctx.world
+    from mercer_research_b200 import RCN, _lib
+    H, W = wl["H"], wl["W"]
+    model = RCN(wl["classes"], wl["cfg"], wl["ff"], device=ctx.local_rank)
+    L = model.feature_len(H, W)
+    g = torch.Generator(device=dev); g.manual_seed(DATA_SEED + 7 + rank)
+    images = torch.randint(0, 256, (4, B, H, W), dtype=torch.uint8, device=dev, generator=g)
+    out = torch.empty((B, L), dtype=torch.float64, device=dev)
+    model.scale_set = (100.0, 50.0)
+    stream = torch.cuda.current_stream(dev)
+    model.set_stream(stream.cuda_stream)
+    for i in range(3):
+        model.flatten_feature_set(images[i % 4], standardise=True, out=out)
+    _barrier(ctx)
+    clocks = ClockSampler(ctx.local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = _lib.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.mark_begin()
+    e0.record(stream)
+    for i in range(steps):
+        model.flatten_feature_set(images[i % 4], standardise=True, out=out)
+    e1.record(stream)
+    _barrier(ctx)
+    clocks.mark_end()
+    launches = _lib.kernel_launches() - l0
+    clk = clocks.stop() if rank == 0 else None
+    ms_step = _max_over_ranks(ctx, e0.elapsed_time(e1)) / steps
+    _lib.profile_enable(True)
+    for i in range(min(steps, 10)):
+        model.flatten_feature_set(images[i % 4], standardise=True, out=out)
+    torch.cuda.synchronize()
+    prof = _lib.profile_report()
+    _lib.profile_enable(False)
+    model.close()
+    del images, out
+    torch.cuda.empty_cache()
+    nbytes = B * (H * W + L * 8)
+    return {"workload": wl["desc"], "value": world * B / (ms_step * 1e-3), "unit": "images/s", "ms_per_step": ms_step, "steps": steps,
+            "scaling": "weak (independent replicas: no exchange step)", "batch_per_gpu": B, "feature_len": L, "gpu_launches": int(launches),
+            "clocks": clk, "_nbytes": nbytes, "_prof": prof, "_prof_steps": min(steps, 10)}
 
 
 def leg_roofline(leg, pk, fp64_peak, int8_peak, int8_how, traffic_all, workload_key):
@@ -733,6 +794,9 @@ def run_gpu(args, wl, rank, world, local_rank):
     if args.workload == "c2" and not args.no_extra:
         for key in [k for k in args.extra.split(",") if k]:
             w2 = WORKLOADS[key]
+            if key == "c4":
+                legs[key] = run_features_leg(ctx, key, w2, w2["batch"], max(4, min(args.steps, 20)))
+                continue
             if key == "c3":
                 if w2["batch"] % world:
                     continue
@@ -780,7 +844,7 @@ def run_gpu(args, wl, rank, world, local_rank):
         net = O.Net(main["shapes"])
         p_or = pr["_p0"].copy()
         mean, sd = pr["_scale"]
-        for k in range(3):
+        for k in (0, 1, 2, 0, 1, 2):                        # the 3-chunk epoch walked twice (chunks_exact + wrap, rcn.rs:144-149)
             single.train_batch_images(pr["_images"][k], pr["_labels"][k], ETA)
             X = O.standardise(O.features_u8(wl["cfg"], pr["_images"][k]), mean, sd)
             p_or, _ = net.train_batch(p_or, X, np.eye(wl["classes"])[pr["_labels"][k]], ETA, n_threads=os.cpu_count() or 1)
@@ -789,10 +853,10 @@ def run_gpu(args, wl, rank, world, local_rank):
 
         def max_rel(a, b):
             return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
-        parity = {"steps": 3, "global_batch": pr["global_batch"], "replicas_bit_identical": pr["replicas_bit_identical"],
+        parity = {"steps": pr["steps"], "global_batch": pr["global_batch"], "path": pr["path"], "replicas_bit_identical": pr["replicas_bit_identical"],
                   "max_rel_vs_single_gpu": max_rel(pr["_dp_params"], p_single), "max_rel_vs_oracle": max_rel(pr["_dp_params"], p_or),
                   "single_gpu_max_rel_vs_oracle": max_rel(p_single, p_or), "tolerance": 1e-9,
-                  "what": "post-step parameters after 3 SGD steps from fixed parameters on fixed global batches (rcn.rs:190-222), "
+                  "what": "parameters after 6 SGD steps from fixed parameters on fixed global batches (rcn.rs:144-149,190-222), "
                           "element-wise relative; oracle = C++ restatement (parity unpinned by the reference's own tests)"}
 
     print("[bench] rank 0: cpu baseline", file=sys.stderr, flush=True)
@@ -806,6 +870,17 @@ def run_gpu(args, wl, rank, world, local_rank):
     workloads = {}
     for key, leg in legs.items():
         if "error" in leg:
+            workloads[key] = leg
+            continue
+        if "_nbytes" in leg:     # feature-stage-only leg (c4)
+            nbytes, prof, psteps = leg.pop("_nbytes"), leg.pop("_prof"), leg.pop("_prof_steps")
+            gbs = nbytes / (leg["ms_per_step"] * 1e-3) / 1e9
+            tot = sum(v["total_ms"] for v in prof.values()) or 1.0
+            leg["roofline"] = {"kernel": max(prof, key=lambda k: prof[k]["total_ms"]) if prof else None, "bound": "hbm", "achieved": gbs,
+                               "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                               "achieved_is": "algorithmic bytes (H*W u8 read + L*8 f64 features written per image, SURVEY 8d) / duration of one call",
+                               "kernels": {k: {"launches_per_step": v["launches"] / psteps, "avg_us": v["total_ms"] / v["launches"] * 1e3,
+                                               "share": round(v["total_ms"] / tot, 4)} for k, v in prof.items()}}
             workloads[key] = leg
             continue
         w2 = leg["wl"]
@@ -871,7 +946,7 @@ def main():
                     help="e2e leg: ordinary pinned host memory (default) or write-combined pinned memory (experiment)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
                     help="multi-GPU gradient exchange: fused NVLink peer-memory kernel, NCCL all-reduce, or by size")
-    ap.add_argument("--extra", default="c3,c5", help="extra workloads measured after the main one in the same run (parsed.workloads)")
+    ap.add_argument("--extra", default="c3,c4,c5", help="extra workloads measured after the main one in the same run (parsed.workloads)")
     ap.add_argument("--no-extra", action="store_true", help="main workload only")
     args = ap.parse_args()
     # stdout must carry exactly ONE JSON line: route everything else that writes to fd 1 (e.g. NCCL's version banner)

@@ -959,8 +959,11 @@ int rcn_cuda_epoch_accumulate(rcn_cuda_handle h) {
     bi.perm = (const long long*)h->ep_perm;
     bi.labels_all = (const long long*)h->ep_labels;
     bi.labels_batch = h->ep_state.as<long long>() + kEpSlots;
-    bi.batch = (long long)h->ep_B;
-    bi.n_samples = (long long)h->ep_n;
+    static const bool l2_prefetch = []() { const char* e = getenv("RCN_CUDA_L2_PREFETCH"); return !(e && e[0] == '0'); }();
+    if (l2_prefetch) {   // lets kernel A ask L2 for the next step's images (smallnet.cu)
+        bi.batch = (long long)h->ep_B;
+        bi.n_samples = (long long)h->ep_n;
+    }
     return accumulate_images_dev(h, h->ep_images, h->ep_fmt, nullptr, h->ep_B, h->ep_H, h->ep_W, &bi);
 }
 

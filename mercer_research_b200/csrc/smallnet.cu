@@ -114,7 +114,7 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
                                            double* __restrict__ feats, int B, const double* __restrict__ onehot,
                                            const int64_t* __restrict__ labels, double* __restrict__ acts,
                                            double* __restrict__ deltas, double* __restrict__ stats_partial,
-                                           double* __restrict__ small_partial, int backward, const SmallNetFront& fr,
+                                           int backward, const SmallNetFront& fr,
                                            const int tile_idx, unsigned char* sn_smem) {
     double* zpart = reinterpret_cast<double*>(sn_smem);                 // [16][8][36]
     double* s_small = zpart + SNA_WARPS * SN_TB * SN_ZPITCH;                   // params after W0: b0 | W1 | b1 | ...
@@ -370,30 +370,43 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
         }
         SN_PHASE(17);
         __syncwarp();
-        // ---- narrow layers -----------------------------------------------------------------------------------------
-        for (int l = 1; l < d.n_layers; ++l) {
-            const int R = d.rows[l], C = d.rows[l - 1];
-            if (m < R) {
-                const double* W = s_small + (d.w_off[l] - small_base);
-                double z0 = 0.0, z1 = 0.0;
-                int k = 0;
-                for (; k + 1 < C; k += 2) {
-                    z0 = fma(W[k * R + m], s_act[l - 1][n][k], z0);
-                    z1 = fma(W[(k + 1) * R + m], s_act[l - 1][n][k + 1], z1);
+        // ---- narrow layers.  Every layer loop below is unrolled over kSmallNetMaxLayers with a guard, so the descriptor
+        // fields (rows / offsets) are read with STATIC constant-bank offsets -- an operand of the instruction -- instead of a
+        // dependent LDC per use, and the k loops run on four independent FMA chains ------------------------------------
+#pragma unroll
+        for (int l = 1; l < kSmallNetMaxLayers; ++l) {
+            if (l < d.n_layers) {
+                const int R = d.rows[l], C = d.rows[l - 1];
+                if (m < R) {
+                    const double* W = s_small + (d.w_off[l] - small_base) + m;
+                    const double* av = &s_act[l - 1][n][0];
+                    double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
+                    int k = 0;
+#pragma unroll 2
+                    for (; k + 3 < C; k += 4) {
+                        z0 = fma(W[k * R], av[k], z0);
+                        z1 = fma(W[(k + 1) * R], av[k + 1], z1);
+                        z2 = fma(W[(k + 2) * R], av[k + 2], z2);
+                        z3 = fma(W[(k + 3) * R], av[k + 3], z3);
+                    }
+                    for (; k < C; ++k) z0 = fma(W[k * R], av[k], z0);
+                    const double z = ((z0 + z1) + (z2 + z3)) + s_small[d.b_off[l] - small_base + m];
+                    s_act[l][n][m] = sn_sigmoid(z);
                 }
-                if (k < C) z0 = fma(W[k * R + m], s_act[l - 1][n][k], z0);
-                const double z = (z0 + z1) + s_small[d.b_off[l] - small_base + m];
-                s_act[l][n][m] = sn_sigmoid(z);
+                __syncwarp();
             }
-            __syncwarp();
         }
         SN_PHASE(5);
         // ---- activations out ---------------------------------------------------------------------------------------
         {
-            size_t off = 0;
-            for (int l = 0; l < d.n_layers; ++l) {
-                if (live && m < d.rows[l]) acts[off * B + (size_t)sample * d.rows[l] + m] = s_act[l][n][m];
-                off += d.rows[l];
+            int off = 0;
+#pragma unroll
+            for (int l = 0; l < kSmallNetMaxLayers; ++l) {
+                if (l < d.n_layers) {
+                    const int R = d.rows[l];
+                    if (live && m < R) acts[(size_t)off * B + (size_t)sample * R + m] = s_act[l][n][m];
+                    off += R;
+                }
             }
         }
         SN_PHASE(18);
@@ -406,13 +419,14 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
             if (out) s_del[last][n][m] = (a - y) * (a * (1.0 - a));
             {
                 double mx = out ? a : -1.0;                        // activations are in (0, 1)
+                const double df = a - y;                           // 0 for lanes beyond the output layer
+                double cost = out ? df * df : 0.0;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                for (int o = 16; o > 0; o >>= 1) {                 // both butterflies in one pass: fixed order, deterministic
+                    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    cost += __shfl_xor_sync(0xffffffffu, cost, o);
+                }
                 const bool ok = __all_sync(0xffffffffu, !out || (((a == mx) ? 1.0 : 0.0) == y));
-                const double df = a - y;
-                const double sq = df * df;
-                double cost = 0.0;
-                for (int i = 0; i < RL; ++i) cost += __shfl_sync(0xffffffffu, sq, i);   // neuron order, like the serial sum
                 if (m == 0) {
                     s_cost[n] = live ? cost * 0.5 : 0.0;
                     s_hit[n] = (live && ok) ? 1ull : 0ull;
@@ -421,27 +435,38 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
             SN_PHASE(19);
             __syncwarp();
             // ---- backward-data chain (rcn.rs:305-309) -------------------------------------------------------------------
-            for (int l = last - 1; l >= 0; --l) {
-                const int R = d.rows[l], Ru = d.rows[l + 1];
-                if (m < R) {
-                    const double* Wu = s_small + (d.w_off[l + 1] - small_base);  // Ru x R column-major: (k, m) at m*Ru + k
-                    double v0 = 0.0, v1 = 0.0;
-                    int k = 0;
-                    for (; k + 1 < Ru; k += 2) {
-                        v0 = fma(Wu[m * Ru + k], s_del[l + 1][n][k], v0);
-                        v1 = fma(Wu[m * Ru + k + 1], s_del[l + 1][n][k + 1], v1);
+#pragma unroll
+            for (int l = kSmallNetMaxLayers - 2; l >= 0; --l) {
+                if (l < last) {
+                    const int R = d.rows[l], Ru = d.rows[l + 1];
+                    if (m < R) {
+                        const double* Wu = s_small + (d.w_off[l + 1] - small_base) + m * Ru;  // Ru x R column-major: (k, m) at m*Ru + k
+                        const double* dv = &s_del[l + 1][n][0];
+                        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+                        int k = 0;
+#pragma unroll 2
+                        for (; k + 3 < Ru; k += 4) {
+                            v0 = fma(Wu[k], dv[k], v0);
+                            v1 = fma(Wu[k + 1], dv[k + 1], v1);
+                            v2 = fma(Wu[k + 2], dv[k + 2], v2);
+                            v3 = fma(Wu[k + 3], dv[k + 3], v3);
+                        }
+                        for (; k < Ru; ++k) v0 = fma(Wu[k], dv[k], v0);
+                        const double al = s_act[l][n][m];
+                        s_del[l][n][m] = ((v0 + v1) + (v2 + v3)) * (al * (1.0 - al));
                     }
-                    if (k < Ru) v0 = fma(Wu[m * Ru + k], s_del[l + 1][n][k], v0);
-                    const double al = s_act[l][n][m];
-                    s_del[l][n][m] = (v0 + v1) * (al * (1.0 - al));
+                    __syncwarp();
                 }
-                __syncwarp();
             }
             SN_PHASE(20);
-            size_t off = 0;
-            for (int l = 0; l < d.n_layers; ++l) {
-                if (live && m < d.rows[l]) deltas[off * B + (size_t)sample * d.rows[l] + m] = s_del[l][n][m];
-                off += d.rows[l];
+            int off = 0;
+#pragma unroll
+            for (int l = 0; l < kSmallNetMaxLayers; ++l) {
+                if (l < d.n_layers) {
+                    const int R = d.rows[l];
+                    if (live && m < R) deltas[(size_t)off * B + (size_t)sample * R + m] = s_del[l][n][m];
+                    off += R;
+                }
             }
         }
     }
@@ -449,52 +474,13 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
     if (!backward) { RCN_TL_END(d.tl, 0); return; }
     __syncthreads();
     SN_PHASE(6);
-    if (tid == SNA_THREADS - 32) {   // a warp with the fewest partial tasks below
+    if (tid == SNA_THREADS - 32) {
         double c = 0.0;
         unsigned long long h = 0;
 #pragma unroll
         for (int i = 0; i < SN_TB; ++i) { c += s_cost[i]; h += s_hit[i]; }
         stats_partial[2 * tile_idx] = c;
         reinterpret_cast<unsigned long long*>(stats_partial)[2 * tile_idx + 1] = h;
-    }
-    // ---- this tile's share of db_l (all layers) and dW_l (narrow layers): everything is already in shared memory.
-    // One value per entry of the "small" parameter block b0|W1|b1|...; kernel B sums the tiles in index order.  A task is
-    // one bias vector or one column k of a dW_l (lane = row), dealt round-robin to the 16 warps; samples added in order.
-    {
-        const int n_live = min(SN_TB, B - s0);
-        double* sp = small_partial + (size_t)tile_idx * n_small;
-        int total = 0;                                  // layer l owns 1 task (db_l) + rows[l-1] tasks (columns of dW_l, l >= 1)
-        for (int l = 0; l < d.n_layers; ++l) total += 1 + (l >= 1 ? d.rows[l - 1] : 0);
-        for (int tsk = warp; tsk < total; tsk += SNA_WARPS) {   // each warp decodes only ITS tasks (no shared dealing loop)
-            int l = 0, base = 0;
-            for (;;) {
-                const int cnt = 1 + (l >= 1 ? d.rows[l - 1] : 0);
-                if (tsk < base + cnt) break;
-                base += cnt;
-                ++l;
-            }
-            const int j = tsk - base;
-            const int R = d.rows[l];
-            if (lane >= R) continue;
-            if (j == 0) {                                                    // db_l = sum_b delta_l      (rcn.rs:302,309)
-                double v[SN_TB];
-#pragma unroll
-                for (int b = 0; b < SN_TB; ++b) v[b] = s_del[l][b][lane];
-                double acc = 0.0;
-#pragma unroll
-                for (int b = 0; b < SN_TB; ++b) if (b < n_live) acc += v[b];
-                sp[d.b_off[l] - small_base + lane] = acc;
-            } else {                                                         // dW_l = sum_b delta_l a_{l-1}^T (rcn.rs:303,310)
-                const int k = j - 1;
-                double v[SN_TB], a[SN_TB];
-#pragma unroll
-                for (int b = 0; b < SN_TB; ++b) { v[b] = s_del[l][b][lane]; a[b] = s_act[l - 1][b][k]; }
-                double acc = 0.0;
-#pragma unroll
-                for (int b = 0; b < SN_TB; ++b) if (b < n_live) acc = fma(v[b], a[b], acc);
-                sp[d.w_off[l] - small_base + k * R + lane] = acc;
-            }
-        }
     }
     // ---- epoch mode: ask L2 for the images this tile will load in the NEXT step (same tile index, cursor advanced like the
     // update does, rcn.rs:147): 20 us from now their bulk loads hit L2 instead of paying an HBM round trip at the head of
@@ -516,16 +502,15 @@ __global__ void __launch_bounds__(SNA_THREADS, 1)
 smallnet_fwd_bwd_kernel(const __grid_constant__ SmallNetDesc d, const double* __restrict__ params,
                         double* __restrict__ feats, int B, const double* __restrict__ onehot,
                         const int64_t* __restrict__ labels, double* __restrict__ acts, double* __restrict__ deltas,
-                        double* __restrict__ stats_partial, double* __restrict__ small_partial, int backward,
-                        const __grid_constant__ SmallNetFront fr) {
+                        double* __restrict__ stats_partial, int backward, const __grid_constant__ SmallNetFront fr) {
     extern __shared__ __align__(128) unsigned char sn_smem[];
-    sn_phase_a<FUSED, PREWAIT>(d, params, feats, B, onehot, labels, acts, deltas, stats_partial, small_partial, backward, fr,
+    sn_phase_a<FUSED, PREWAIT>(d, params, feats, B, onehot, labels, acts, deltas, stats_partial, backward, fr,
                                (int)blockIdx.x, sn_smem);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Kernel B: dW/db.  grid = (col_groups + 1, S) launched as thread-block CLUSTERS of (1, S, 1): the S CTAs of a
-// cluster own the same 64 columns of dW0 (or, for blockIdx.x == col_groups, db0 + the narrow layers) and one K-split
+// Kernel B: dW/db.  grid = (col_groups + small_groups, S) launched as thread-block CLUSTERS of (1, S, 1): the S CTAs of a
+// cluster own the same 64 columns of dW0 (or, for blockIdx.x >= col_groups, a share of db0 + the narrow layers) and one K-split
 // of the batch each.  Every CTA leaves its partial tile in its own shared memory; after a cluster barrier each rank
 // sums 1/S of the tile over all S ranks through distributed shared memory, in rank order (deterministic), and
 // writes the flat gradient buffer.  No partials ever touch L2/HBM.
@@ -546,10 +531,11 @@ constexpr int SNB_TILE = 32 * 64;   // padded partial tile: 32 rows x 64 columns
 // 64-sample chunk; their two partial tiles are added, in order, by the reduction).
 template <int MODE, int CW>
 __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* __restrict__ feats,
-                                           const double* __restrict__ small_partial, const double* __restrict__ deltas,
+                                           const double* __restrict__ acts, const double* __restrict__ deltas,
                                            int B, int ksplit, int col_groups, double* __restrict__ grads,
                                            const double* __restrict__ stats_partial, int n_stat, double* __restrict__ stats,
-                                           const DpPush& dp, const SnUpdate& upd, const int cg_idx, const int rank, const int S,
+                                           const DpPush& dp, const SnUpdate& upd, const int chunk /* samples per staging pass of the small CTA */,
+                                           const int cg_idx, const int rank, const int S,
                                            double* sP, double* sD /* [2][64 * SN_DPITCH]: double-buffered 64-sample delta_0 chunk */,
                                            const unsigned total_ctas) {
     constexpr bool DP = MODE == 1 || MODE == 3;
@@ -564,6 +550,11 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
     const int b_begin = rank * ksplit;
     const int b_end = min(B, b_begin + ksplit);
     const bool is_col = cg_idx < col_groups;
+    // the "small" parameter block b0|W1|b1|... is dealt to the (gridDim.x - col_groups) small column groups in contiguous halves
+    const int small_groups = (int)gridDim.x - col_groups;
+    const int e_per = (d.n_params - d.b_off[0] + small_groups - 1) / small_groups;
+    const int e_lo = is_col ? 0 : (cg_idx - col_groups) * e_per;
+    const int e_hi = is_col ? 0 : min(d.n_params - d.b_off[0], e_lo + e_per);
     const int small_base = d.b_off[0];
     const int n_small = d.n_params - small_base;
 
@@ -632,26 +623,91 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
             sP[(cl + 1) * 32 + i * 8 + g] = acc[i][1];
         }
     } else {
-        // ---- db_l (all layers) and dW_l (narrow layers): kernel A left one partial per 8-sample tile; sum this
-        // rank's tiles in index order (8 loads in flight per thread).
-        const int t_begin = b_begin / SN_TB;
-        const int t_end = (b_end + SN_TB - 1) / SN_TB;
-        for (int o = tid; o < n_small; o += SNB_THREADS) {
-            double s = 0.0;
-            for (int tb = t_begin; tb < t_end; tb += 8) {
-                double v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = (tb + u < t_end) ? small_partial[(size_t)(tb + u) * n_small + o] : 0.0;
-#pragma unroll
-                for (int u = 0; u < 8; ++u) s += v[u];
+        // ---- db_l (all layers) and dW_l = sum_b delta_l a_{l-1}^T (narrow layers, rcn.rs:302-303,309-310) for this K-split:
+        // the split's activations (layers 0 .. n-2) and deltas (all layers) are staged in shared memory chunk by chunk --
+        // per layer one contiguous, coalesced block [sample][rows_l], exactly as it lies in global memory -- and every
+        // thread owns the entries o = tid, tid + 256, ... of the "small" parameter block b0|W1|b1|..., adding the samples in
+        // index order on two interleaved chains (even / odd samples; deterministic).  This CTA would otherwise idle while
+        // the column CTAs run their DMMAs, and kernel A no longer spends its tail on per-tile partial sums.
+        double* stg = sP + ((n_small + 1) & ~1);                 // staging area behind the partial tile (dynamic smem)
+        int per_sample = 0;                                       // doubles per sample in a chunk: a_0..a_{n-2} | delta_0..delta_{n-1}
+        for (int l = 0; l + 1 < d.n_layers; ++l) per_sample += d.rows[l];
+        const int act_doubles = per_sample;
+        for (int l = 0; l < d.n_layers; ++l) per_sample += d.rows[l];
+        for (int o = tid; o < e_hi - e_lo; o += SNB_THREADS) sP[o] = 0.0;
+        for (int c0 = b_begin; c0 < b_end; c0 += chunk) {
+            const int cn = min(chunk, b_end - c0);
+            __syncthreads();                                      // sP zeroed / the previous chunk consumed
+            {   // asynchronous copies: no register dependency, every request of the chunk is in flight at once (one L2 round trip)
+                auto stage = [&](const double* src, int n, int soff) {
+                    for (int i = tid; i < n; i += SNB_THREADS) {
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(stg + soff + i);
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + i) : "memory");
+                    }
+                };
+                size_t goff = 0;
+                int soff = 0;
+                for (int l = 0; l + 1 < d.n_layers; ++l) {        // activations of layers 0 .. n-2
+                    const int R = d.rows[l];
+                    stage(acts + goff * B + (size_t)c0 * R, cn * R, soff);
+                    goff += R; soff += chunk * R;
+                }
+                goff = 0;
+                for (int l = 0; l < d.n_layers; ++l) {            // deltas of every layer
+                    const int R = d.rows[l];
+                    stage(deltas + goff * B + (size_t)c0 * R, cn * R, soff);
+                    goff += R; soff += chunk * R;
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_all;" ::: "memory");
             }
-            sP[o] = s;
+            __syncthreads();
+            for (int o = e_lo + tid; o < e_hi; o += SNB_THREADS) {
+                // decode o -> layer l, row m, and (for a weight entry) column k
+                int a_blk = 0, d_blk = act_doubles;               // per-sample offsets of a_{l-1} / delta_l
+                const double* dp_ = nullptr;
+                const double* ap_ = nullptr;
+                int dR = 0, aR = 0;
+                for (int l = 0; l < d.n_layers; ++l) {
+                    const int R = d.rows[l];
+                    const int bo = d.b_off[l] - small_base;
+                    if (o >= bo && o < bo + R) { dp_ = stg + d_blk * chunk + (o - bo); dR = R; break; }
+                    if (l >= 1) {
+                        const int C = d.rows[l - 1];
+                        const int wo = d.w_off[l] - small_base;
+                        if (o >= wo && o < wo + R * C) {
+                            const int k = (o - wo) / R, m = (o - wo) - k * R;
+                            dp_ = stg + d_blk * chunk + m; dR = R;
+                            ap_ = stg + a_blk * chunk + k; aR = C;
+                            break;
+                        }
+                        a_blk += C;
+                    }
+                    d_blk += R;
+                }
+                if (!dp_) continue;
+                double s0 = 0.0, s1 = 0.0;
+                int b = 0;
+                if (ap_) {
+#pragma unroll 4
+                    for (; b + 1 < cn; b += 2) {                  // 16 shared loads in flight per thread
+                        s0 = fma(dp_[b * dR], ap_[b * aR], s0);
+                        s1 = fma(dp_[(b + 1) * dR], ap_[(b + 1) * aR], s1);
+                    }
+                    if (b < cn) s0 = fma(dp_[b * dR], ap_[b * aR], s0);
+                } else {
+#pragma unroll 4
+                    for (; b + 1 < cn; b += 2) { s0 += dp_[b * dR]; s1 += dp_[(b + 1) * dR]; }
+                    if (b < cn) s0 += dp_[b * dR];
+                }
+                sP[o - e_lo] += s0 + s1;
+            }
         }
     }
 
     // ---- cross-split reduction through distributed shared memory, rank order ----------------------------------------
     cluster.sync();
-    const int n_out = is_col ? CW * 32 : n_small;
+    const int n_out = is_col ? CW * 32 : e_hi - e_lo;
     const int per = (n_out + S - 1) / S;
     const int o_lo = rank * per, o_hi = min(n_out, o_lo + per);
     // data-parallel group: the final values also go straight into the peers' receive slots (dp.cu protocol), so the
@@ -664,7 +720,7 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
             const int m = o & 31, col = cg_idx * CW + (o >> 5);
             if (m < R0 && col < L) gi = d.w_off[0] + (long long)col * R0 + m;
         } else {
-            gi = small_base + o;
+            gi = small_base + e_lo + o;
         }
         double pold = 0.0;
         if (UPD && gi >= 0) pold = upd.params[gi];
@@ -694,7 +750,7 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
             if (UPD) upd.params[gi] = sgd_apply(pold, upd.scale, s);
         }
     }
-    if (!is_col && rank == 0 && tid < 32 && stats) {
+    if (!is_col && cg_idx == col_groups && rank == 0 && tid < 32 && stats) {
         // 32 lanes, each a contiguous chunk in order, then a fixed-order shuffle tree => deterministic
         const int per_l = (n_stat + 31) / 32;
         double c = 0.0;
@@ -736,20 +792,20 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
 template <int MODE, int CW>
 __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __grid_constant__ SmallNetDesc d,
                                                                      const double* __restrict__ feats,
-                                                                     const double* __restrict__ small_partial,
+                                                                     const double* __restrict__ acts,
                                                                      const double* __restrict__ deltas, int B, int ksplit,
                                                                      int col_groups, double* __restrict__ grads,
                                                                      const double* __restrict__ stats_partial, int n_stat,
                                                                      double* __restrict__ stats, const __grid_constant__ DpPush dp,
-                                                                     const __grid_constant__ SnUpdate upd) {
-    extern __shared__ __align__(16) double sP_dyn[];          // partial tile: SNB_TILE (col CTAs) or n_small doubles
+                                                                     const __grid_constant__ SnUpdate upd, int chunk) {
+    extern __shared__ __align__(16) double sP_dyn[];          // partial tile: SNB_TILE (col CTAs) or n_small doubles + the small CTA's staging area
     __shared__ __align__(16) double sD_static[2 * 64 * SN_DPITCH];   // 36 KB
     // grid (col_groups + 1, S) in clusters of (1, S, 1): blockIdx.y == cluster.block_rank()
     // On a data-parallel group the successor may be a PREWAIT kernel A that writes the feature buffer this kernel reads:
     // no early trigger there (the implicit one at completion stands); a single GPU keeps the early trigger.
     if (dp.world <= 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    sn_phase_b<MODE, CW>(d, feats, small_partial, deltas, B, ksplit, col_groups, grads, stats_partial, n_stat, stats, dp, upd,
+    sn_phase_b<MODE, CW>(d, feats, acts, deltas, B, ksplit, col_groups, grads, stats_partial, n_stat, stats, dp, upd, chunk,
                          (int)blockIdx.x, (int)blockIdx.y, (int)gridDim.y, sP_dyn, sD_static, gridDim.x * gridDim.y);
 }
 
@@ -786,7 +842,13 @@ static bool sn_pdl_enabled() {
 // Highest launch priority for the training kernels: pending CTAs of kernels A / B must win the SMs (kernel A needs a whole
 // SM per CTA) against anything a parallel branch runs (the host-dataset loop's prefetch kernel).
 static int sn_high_priority() {
-    static const int prio = []() { int least = 0, greatest = 0; if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { cudaGetLastError(); return 0; } return greatest; }();
+    static const int prio = []() {
+        const char* e = getenv("RCN_CUDA_LAUNCH_PRIORITY");
+        if (e && e[0] == '0') return 0;
+        int least = 0, greatest = 0;
+        if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { cudaGetLastError(); return 0; }
+        return greatest;
+    }();
     return prio;
 }
 
@@ -811,13 +873,20 @@ void smallnet_front_select(const FeaturePlan& plan, SmallNetFront* fr) {
 
 static int launch_kernel_a(const SmallNetDesc& d, const double* params, double* feats, size_t B, const double* onehot,
                            const int64_t* labels, double* acts, double* deltas, double* stats_partial,
-                           double* small_partial, int backward, const SmallNetFront* fr, cudaStream_t stream) {
+                           int backward, const SmallNetFront* fr, cudaStream_t stream) {
     const unsigned n_tiles = cdiv(B, SN_TB);
     const size_t smem = kernel_a_smem(d, fr);
     static SmallNetFront empty_front{};
     const int Bi = (int)B;
     auto launch = [&](auto kern, SmemAttrCache& attr, const char* name, const SmallNetFront& front) -> int {
-        if (attr.need(smem)) RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (attr.need(smem)) {
+            RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // every kernel of the step asks for the SAME shared-memory / L1 split (all shared): an SM whose split has to change
+            // between two kernels is reconfigured at the boundary, and a kernel that needs another split than the one a
+            // concurrently RUNNING kernel holds was observed to wait for that kernel (two ranks on one device: kernel A
+            // could not finish while the peer's exchange kernel was spinning)
+            RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        }
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(n_tiles, 1, 1);
         cfg.blockDim = dim3(SNA_THREADS, 1, 1);
@@ -831,7 +900,7 @@ static int launch_kernel_a(const SmallNetDesc& d, const double* params, double* 
         cfg.attrs = at;
         cfg.numAttrs = sn_pdl_enabled() ? 2 : 1;
         RCN_LAUNCH(name, stream, cudaLaunchKernelEx(&cfg, kern, d, params, feats, Bi, onehot, labels, acts, deltas, stats_partial,
-                                                    small_partial, backward, front));
+                                                    backward, front));
         return RCN_OK;
     };
     if (fr && fr->use_cp && fr->prewait && backward && sn_pdl_enabled()) {
@@ -853,7 +922,7 @@ static int launch_kernel_a(const SmallNetDesc& d, const double* params, double* 
 int launch_smallnet_forward(const SmallNetDesc& d, const double* params, double* feats, size_t B, double* acts,
                             const SmallNetFront* front, cudaStream_t stream) {
     if (B == 0) return RCN_OK;
-    return launch_kernel_a(d, params, feats, B, nullptr, nullptr, acts, nullptr, nullptr, nullptr, 0, front, stream);
+    return launch_kernel_a(d, params, feats, B, nullptr, nullptr, acts, nullptr, nullptr, 0, front, stream);
 }
 
 int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double* feats, size_t B, const double* onehot,
@@ -867,13 +936,22 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
     const int n_tiles = (int)cdiv(B, SN_TB);
     const int col_groups = (int)cdiv(d.n_in, 64);
     const int n_small = d.n_params - d.b_off[0];
-    // workspace: per-tile statistics partials [n_tiles][2] | per-tile small-parameter gradient partials [n_tiles][n_small]
-    RCN_TRY(workspace.reserve((2 + (size_t)n_small) * (size_t)n_tiles * sizeof(double)));
+    // workspace: per-tile statistics partials [n_tiles][2]
+    RCN_TRY(workspace.reserve(2 * (size_t)n_tiles * sizeof(double)));
     double* stats_partial = workspace.as<double>();
-    double* small_partial = stats_partial + 2 * (size_t)n_tiles;
-    RCN_TRY(launch_kernel_a(d, params, feats, B, onehot, labels, acts, deltas, stats_partial, small_partial, 1, front, stream));
+    RCN_TRY(launch_kernel_a(d, params, feats, B, onehot, labels, acts, deltas, stats_partial, 1, front, stream));
 
-    const size_t smem_b = (size_t)(n_small > SNB_TILE ? n_small : SNB_TILE) * sizeof(double);
+    // dynamic smem of kernel B: the partial tile, and behind it the small CTA's staging area for `chunk` samples of the
+    // narrow layers' activations and deltas (a whole K-split when it fits 96 KB: one pass, one L2 round trip)
+    int per_sample = 0;
+    for (int l = 0; l + 1 < d.n_layers; ++l) per_sample += d.rows[l];
+    for (int l = 0; l < d.n_layers; ++l) per_sample += d.rows[l];
+    int chunk = (int)((96 * 1024 / sizeof(double)) / (size_t)per_sample);
+    if (chunk > ksplit) chunk = ksplit;
+    if (chunk < 1) chunk = 1;
+    const size_t tile_doubles = (size_t)(((n_small + 1) & ~1) > SNB_TILE ? ((n_small + 1) & ~1) : SNB_TILE);
+    const size_t stg_doubles = (size_t)((n_small + 1) & ~1) + (size_t)chunk * per_sample;
+    const size_t smem_b = (tile_doubles > stg_doubles ? tile_doubles : stg_doubles) * sizeof(double);
     DpPush push{};
     push.world = 1;
     if (dp_push) push = *dp_push;
@@ -888,10 +966,17 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
         RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
         RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
         RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<0, 64>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<1, 64>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<2, 64>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<3, 64>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
 
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(col_groups + 1, splits, 1);
+    // one or two "small" column groups (db_l, dW_l of the narrow layers): two when there are more entries than threads and the
+    // extra cluster still fits the single wave of ~15 eight-CTA clusters B200 co-schedules
+    const int small_groups = (n_small > SNB_THREADS && (col_groups + 2) * splits <= 120) ? 2 : 1;
+    cfg.gridDim = dim3(col_groups + small_groups, splits, 1);
     cfg.blockDim = dim3(SNB_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem_b;
     cfg.stream = stream;
@@ -909,8 +994,8 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
     const int Bi = (int)B;
     auto kern = mode == 1 ? smallnet_wgrad_kernel<1, 64> : mode == 2 ? smallnet_wgrad_kernel<2, 64> : mode == 3 ? smallnet_wgrad_kernel<3, 64> : smallnet_wgrad_kernel<0, 64>;
     RCN_LAUNCH(mode == 2 ? "smallnet_wgrad_kernel(+SGD update)" : mode == 3 ? "smallnet_wgrad_kernel(+exchange+SGD update)" : "smallnet_wgrad_kernel", stream,
-               cudaLaunchKernelEx(&cfg, kern, d, (const double*)feats, (const double*)small_partial, (const double*)deltas, Bi,
-                                  ksplit, col_groups, grads, (const double*)stats_partial, n_tiles, stats, push, upd));
+               cudaLaunchKernelEx(&cfg, kern, d, (const double*)feats, (const double*)acts, (const double*)deltas, Bi,
+                                  ksplit, col_groups, grads, (const double*)stats_partial, n_tiles, stats, push, upd, chunk));
     return RCN_OK;
 }
 

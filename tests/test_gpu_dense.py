@@ -523,16 +523,17 @@ def test_dp_peer_memory_exchange_two_ranks(api, single_call, same_device):
 def test_dp_epoch_steps_two_ranks_prewait(api, graph):
     """The data-parallel EPOCH step as the bench runs it -- device cursor, kernel B pushing to the peer and advancing the
     cursor, the small exchange kernel, and the next step's kernel A running its front end ahead of griddepcontrol.wait --
-    queued back to back without any host synchronisation in between (so consecutive steps really overlap).  graph=False:
-    eager launches, two ranks on device 0, each on its own stream and host thread (runs on a 1-GPU lease).  graph=True: 4
-    steps per CUDA graph, replayed; needs two GPUs (two graphs replayed on ONE device were observed to run one after the
-    other, which starves the exchange).  Replicas bit-identical, parameters equal to single-GPU training on the concatenated
-    global batches, cursor wraps."""
+    queued back to back without any host synchronisation in between (so consecutive steps really overlap), eagerly or as 4
+    steps per CUDA graph.  Needs TWO GPUs: with both ranks on ONE device the peer's weight-gradient kernel (a thread-block-
+    cluster launch) was measured NOT to start while this rank's exchange kernel is resident (device timeline, round 2: it
+    started 5 us after the spinning kernel gave up), so a rank that runs ahead starves the other -- an artefact of sharing a
+    device, which one process per GPU never does.  (bench.py checks the same path across processes in its `parity` block.)
+    Replicas bit-identical, parameters equal to single-GPU training on the concatenated global batches, cursor wraps."""
     import threading
     import torch
-    if graph and torch.cuda.device_count() < 2:
+    if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    devs = (0, 1) if graph else (0, 0)
+    devs = (0, 1)
     rng = np.random.default_rng(77)
     B, n_chunks, steps = 64, 5, 12            # per-rank batch; 5 chunks per epoch -> the cursor wraps twice
     N = B * n_chunks + 17                      # chunks_exact drops the remainder
@@ -558,19 +559,33 @@ def test_dp_epoch_steps_two_ranks_prewait(api, graph):
     for m in ranks:
         m.dp_connect_local(ranks)
     for r, m in enumerate(ranks):
-        st = torch.cuda.Stream(device=devs[r])
+        # graph=True captures on a torch stream (one per device).  The eager variant keeps each model on the non-blocking
+        # stream it created itself: two MORE streams on this one device can end up sharing a hardware queue with the other
+        # rank's (CUDA_DEVICE_MAX_CONNECTIONS = 8), and a queue shared by both ranks serialises the peer behind a spinning
+        # exchange kernel -- a one-process artefact (one process per GPU, the deployed shape, has a queue set per rank).
+        st = torch.cuda.Stream(device=devs[r]) if graph else None
         streams.append(st)
         di, dl = torch.from_numpy(shard[r]).cuda(devs[r]), torch.from_numpy(shard_labels[r]).cuda(devs[r])
         data.append((di, dl))
-        m.set_stream(st.cuda_stream)
+        if graph:
+            m.set_stream(st.cuda_stream)
         m.epoch_bind(di, dl, B)
     for d in set(devs):
         torch.cuda.synchronize(d)
     errors = []
 
-    def warm(r):   # one eager step per rank sizes every buffer (no allocation may happen inside a capture)
+    # Warm-up with SPLIT calls and a host barrier in between: the first step sizes every scratch buffer, and a cudaMalloc /
+    # cudaFree synchronises the whole device -- on which, in this one-process test, the peer's exchange kernel may already
+    # be spinning for our pushes (one process per GPU, the deployed shape, has no such coupling).  After the warm-up no call
+    # allocates, so the steps below run back to back.
+    gate = threading.Barrier(2)
+
+    def warm(r):
         try:
-            ranks[r].epoch_step(3.0)
+            ranks[r].epoch_accumulate()
+            ranks[r].synchronize()
+            gate.wait(timeout=60)
+            ranks[r].epoch_apply(3.0, 2 * B)
             ranks[r].synchronize()
         except Exception as e:   # noqa: BLE001
             errors.append((r, repr(e)))
@@ -596,14 +611,15 @@ def test_dp_epoch_steps_two_ranks_prewait(api, graph):
 
     def work(r):
         try:
-            with torch.cuda.device(devs[r]), torch.cuda.stream(streams[r]):
-                if graph:
+            if graph:
+                with torch.cuda.device(devs[r]), torch.cuda.stream(streams[r]):
                     for _ in range(steps // 4):
                         graphs[r].replay()
-                else:
-                    for _ in range(steps):          # no host synchronisation between the steps
-                        ranks[r].epoch_step(3.0)
-            streams[r].synchronize()
+                streams[r].synchronize()
+            else:
+                for _ in range(steps):              # no host synchronisation between the steps
+                    ranks[r].epoch_step(3.0)
+                ranks[r].synchronize()
             ranks[r].dp_check()
         except Exception as e:   # noqa: BLE001
             errors.append((r, repr(e)))
