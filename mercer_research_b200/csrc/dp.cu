@@ -168,14 +168,6 @@ int launch_dp_allreduce_sgd(const DpState& st, double* params, double* grads, do
     cfg.attrs = at;
     cfg.numAttrs = pdl ? 1 : 0;
     const int pushed_i = already_pushed ? 1 : 0;
-    // same shared-memory / L1 split as the step kernels it runs beside (see launch_kernel_a in smallnet.cu)
-    static SmemAttrCache carve;
-    if (carve.need(1)) {
-        RCN_CUDA_TRY(cudaFuncSetAttribute(dp_allreduce_sgd_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        RCN_CUDA_TRY(cudaFuncSetAttribute(dp_allreduce_sgd_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        RCN_CUDA_TRY(cudaFuncSetAttribute(dp_allreduce_sgd_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        RCN_CUDA_TRY(cudaFuncSetAttribute(dp_allreduce_sgd_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-    }
 #define RCN_DP_LAUNCH(W)                                                                                                       \
     RCN_LAUNCH("dp_allreduce_sgd_kernel", stream,                                                                              \
                cudaLaunchKernelEx(&cfg, dp_allreduce_sgd_kernel<W>, pp, params, grads, scale, cursor, batch, n_samples, stats,  \

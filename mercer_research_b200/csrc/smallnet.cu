@@ -56,7 +56,19 @@ __device__ long long g_snp_stamp[1024][8];
 #define SN_PHASE(k) do { } while (0)
 #endif
 
-__device__ __forceinline__ double sn_ld(const double* p) { return __ldg(p); }
+// Parameter loads.  The default is the read-only path (ld.global.nc).  A PREWAIT kernel is ALIVE while the previous step's
+// exchange kernel still rewrites the parameters, which breaks the contract of ld.global.nc ("not modified during the
+// kernel's lifetime") -- and ptxas does hoist such loads above griddepcontrol.wait (seen in SASS, round 2: two
+// LDG.E.64.CONSTANT of W0 sat in front of ACQBULK and read stale weights; caught by bench.py's graph-replayed parity block).
+// There the parameters are read with volatile ld.global.cg: coherent at L2, never served from this SM's L1, and the
+// compiler may not move them across the wait.
+template <bool COHERENT>
+__device__ __forceinline__ double sn_ld(const double* p) {
+    if (!COHERENT) return __ldg(p);
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
 
 constexpr int SN_TB = 8;          // samples per CTA in kernel A (one DMMA n-fragment)
 constexpr int SNA_THREADS = 512;  // kernel A
@@ -192,19 +204,24 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
             const bool kok = (ks_begin + u) < ks_end && k < L;
             const double* wp = W0 + (size_t)k * R0 + g;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) w_pre[u][i] = (kok && rowok[i]) ? sn_ld(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
+            for (int i = 0; i < 4; ++i) w_pre[u][i] = (kok && rowok[i]) ? sn_ld<PREWAIT>(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
         }
         SN_PHASE(9);
         // biases + narrow-layer weights into shared memory (after the register loads above), as asynchronous copies: no
-        // register dependency, so no warp waits an L2 round trip here
-        for (int i = tid; i < n_small; i += SNA_THREADS) {
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(s_small + i);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(params + small_base + i) : "memory");
+        // register dependency, so no warp waits an L2 round trip here (PREWAIT: through registers, coherent at L2)
+        if (PREWAIT) {
+            for (int i = tid; i < n_small; i += SNA_THREADS) s_small[i] = sn_ld<true>(params + small_base + i);
+        } else {
+            for (int i = tid; i < n_small; i += SNA_THREADS) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(s_small + i);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(params + small_base + i) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            // the rest of this warp's K range of W0 into L1 (PREWAIT reads it from L2: L1 must not keep parameters there)
+            const long long lo = (long long)min((ks_begin + SN_U) * 4, L) * R0, hi = (long long)min(ks_end * 4, L) * R0;   // doubles
+            for (long long e = lo + lane * 16; e < hi; e += 32 * 16)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(W0 + e));
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        const long long lo = (long long)min((ks_begin + SN_U) * 4, L) * R0, hi = (long long)min(ks_end * 4, L) * R0;   // doubles
-        for (long long e = lo + lane * 16; e < hi; e += 32 * 16)
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(W0 + e));
     };
     if (!PREWAIT) load_params();
 
@@ -326,7 +343,7 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
                 const bool kok = (ks + u) < ks_end && k < L;
                 const double* wp = W0 + (size_t)k * R0 + g;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) af[u][i] = (kok && rowok[i]) ? sn_ld(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
+                for (int i = 0; i < 4; ++i) af[u][i] = (kok && rowok[i]) ? sn_ld<PREWAIT>(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
                 if (FUSED) bf[u] = kok ? trow[k] : 0.0;
                 else bf[u] = (kok && sample_ok) ? __ldg(frow + k) : 0.0;
             }
@@ -801,9 +818,11 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
     extern __shared__ __align__(16) double sP_dyn[];          // partial tile: SNB_TILE (col CTAs) or n_small doubles + the small CTA's staging area
     __shared__ __align__(16) double sD_static[2 * 64 * SN_DPITCH];   // 36 KB
     // grid (col_groups + 1, S) in clusters of (1, S, 1): blockIdx.y == cluster.block_rank()
-    // On a data-parallel group the successor may be a PREWAIT kernel A that writes the feature buffer this kernel reads:
-    // no early trigger there (the implicit one at completion stands); a single GPU keeps the early trigger.
-    if (dp.world <= 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // Early trigger (the successor's CTAs are scheduled under this kernel and wait in griddepcontrol.wait): on one GPU, and on
+    // a data-parallel group when this kernel pushed to the peers (MODE 1) -- its successor is then the exchange kernel, which
+    // waits for this kernel's completion before it lets the next kernel A start.  Not in the other group modes: their
+    // successor may be a PREWAIT kernel A, whose early part overwrites the feature buffer this kernel reads.
+    if (dp.world <= 1 || MODE == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     sn_phase_b<MODE, CW>(d, feats, acts, deltas, B, ksplit, col_groups, grads, stats_partial, n_stat, stats, dp, upd, chunk,
                          (int)blockIdx.x, (int)blockIdx.y, (int)gridDim.y, sP_dyn, sD_static, gridDim.x * gridDim.y);
@@ -879,14 +898,9 @@ static int launch_kernel_a(const SmallNetDesc& d, const double* params, double* 
     static SmallNetFront empty_front{};
     const int Bi = (int)B;
     auto launch = [&](auto kern, SmemAttrCache& attr, const char* name, const SmallNetFront& front) -> int {
-        if (attr.need(smem)) {
-            RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            // every kernel of the step asks for the SAME shared-memory / L1 split (all shared): an SM whose split has to change
-            // between two kernels is reconfigured at the boundary, and a kernel that needs another split than the one a
-            // concurrently RUNNING kernel holds was observed to wait for that kernel (two ranks on one device: kernel A
-            // could not finish while the peer's exchange kernel was spinning)
-            RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        }
+        // (Measured and dropped, round 2: asking for the all-shared L1 split on every step kernel -- so that no SM is
+        // reconfigured at a kernel boundary -- made the step 0.6 us SLOWER: kernel A's tail of W0 is prefetched into L1.)
+        if (attr.need(smem)) RCN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(n_tiles, 1, 1);
         cfg.blockDim = dim3(SNA_THREADS, 1, 1);
@@ -966,10 +980,7 @@ int launch_smallnet_backprop(const SmallNetDesc& d, const double* params, double
         RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
         RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
         RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<0, 64>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<1, 64>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<2, 64>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        RCN_CUDA_TRY(cudaFuncSetAttribute(smallnet_wgrad_kernel<3, 64>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+
 
     }
     cudaLaunchConfig_t cfg{};
