@@ -350,8 +350,14 @@ int launch_dense_backward_data(const double* W_up, const double* delta_up, const
 
 __global__ void reduce_splits_kernel(const double* __restrict__ part, int splits, size_t n, double* __restrict__ out) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        double s = part[i];
-        for (int p = 1; p < splits; ++p) s += part[(size_t)p * n + i];
+        double s = 0.0;
+        for (int p0 = 0; p0 < splits; p0 += 8) {          // 8 loads in flight, added in split order (deterministic)
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (p0 + u < splits) ? __ldcs(part + (size_t)(p0 + u) * n + i) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (p0 + u < splits) s = (p0 + u == 0) ? v[u] : s + v[u];
+        }
         out[i] = s;
     }
 }
@@ -399,7 +405,13 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const double* __restrict
     if (s_last && w == 0 && m < M) {
         __threadfence();
         double s = 0.0;
-        for (int q = 0; q < S; ++q) s += __ldcg(partial + (size_t)q * M + m);
+        for (int q0 = 0; q0 < S; q0 += 8) {               // 8 loads in flight, added in split order (deterministic)
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (q0 + u < S) ? __ldcg(partial + (size_t)(q0 + u) * M + m) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (q0 + u < S) s += v[u];
+        }
         db[m] = s;
     }
 }
@@ -437,7 +449,13 @@ __global__ void __launch_bounds__(256) bias_grad_wide_kernel(const double* __res
     if (s_last && m < M) {
         __threadfence();
         double s = 0.0;
-        for (int q = 0; q < S; ++q) s += __ldcg(partial + (size_t)q * M + m);
+        for (int q0 = 0; q0 < S; q0 += 8) {               // 8 loads in flight, added in split order (deterministic)
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (q0 + u < S) ? __ldcg(partial + (size_t)(q0 + u) * M + m) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (q0 + u < S) s += v[u];
+        }
         db[m] = s;
     }
 }
