@@ -417,7 +417,7 @@ def kernel_rooflines(wl, B, shapes, prof, prof_steps, pk, fp64_peak, int8_peak):
     return kernels, top, alg
 
 
-def run_leg(ctx, name, wl, B, steps, warmup, exchange, *, main, steps_per_graph=16, no_graph=False, host_alloc="pinned"):
+def run_leg(ctx, name, wl, B, steps, warmup, exchange, *, main, steps_per_graph=5, no_graph=False, host_alloc="pinned"):
     """One workload on this rank: device-resident `value` leg (epoch mode, CUDA graph), host-buffer `e2e` leg, eager per-kernel
     profile; the main leg (c2) additionally reads the in-graph device timeline. Collective on every rank; returns a dict
     (rank 0's view; timings are max over ranks)."""
@@ -510,7 +510,7 @@ def run_leg(ctx, name, wl, B, steps, warmup, exchange, *, main, steps_per_graph=
     timeline = None
     if use_timeline and graph_ok:
         model.timeline_enable(True)
-        trainer.epoch_steps(4 * spg if spg >= 16 else 64 // spg * spg)
+        trainer.epoch_steps(-(-64 // spg) * spg)
         torch.cuda.synchronize()
         trainer.check()
     if use_timeline and graph_ok and rank == 0:
@@ -551,19 +551,20 @@ def run_leg(ctx, name, wl, B, steps, warmup, exchange, *, main, steps_per_graph=
         if wc is not None:
             hi, host_alloc = wc, "pinned, write-combined"
 
-    def e2e_run(n):
+    def e2e_run(n, verify):
         done = 0
         while done < n:
             m = min(n_host, n - done)
-            cost, hits = trainer.train_epoch_host(hi[:m * B], hl[:m * B], B)
+            cost, hits = trainer.train_epoch_host(hi[:m * B], hl[:m * B], B, verify_steps=verify)
             assert len(cost) == m
             done += m
 
-    e2e_run(min(n_host, e2e_steps_n))           # warm-up at the timed call's size: buffers sized, step graphs captured
+    e2e_run(e2e_steps_n, True)                  # warm-up = the timed call sequence itself: buffers sized, step graphs captured,
+                                                # the per-call step counts agreed on across ranks (not repeated in the timed region)
     _barrier(ctx)
     clocks.mark_begin()
     e0.record(stream)
-    e2e_run(e2e_steps_n)
+    e2e_run(e2e_steps_n, False)
     e1.record(stream)
     _barrier(ctx)
     clocks.mark_end()
@@ -804,7 +805,7 @@ def run_gpu(args, wl, rank, world, local_rank):
             else:
                 B2, st2, ex2, scaling = w2["batch"], max(4, min(args.steps, 12)), ("nccl" if world > 1 else "auto"), "weak"
             try:
-                leg = run_leg(ctx, key, w2, B2, st2, min(args.warmup, 3), ex2, main=False, steps_per_graph=16)
+                leg = run_leg(ctx, key, w2, B2, st2, min(args.warmup, 3), ex2, main=False, steps_per_graph=4)
                 leg["scaling"] = scaling
                 legs[key] = leg
             except Exception as e:  # noqa: BLE001  -- an extra leg must never cost the main line
@@ -940,7 +941,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--steps-per-graph", type=int, default=16, help="consecutive steps captured into one CUDA graph (the timed region replays it steps/this times)")
+    ap.add_argument("--steps-per-graph", type=int, default=5,
+                    help="consecutive steps captured into one CUDA graph (the timed region replays it steps/this times). Small graphs on "
+                         "purpose: the timed region starts on an idle GPU, a graph's launch latency grows with its node count (measured: "
+                         "~38 us for 20 steps, ~12 us for 5) and only the FIRST launch is exposed -- the host enqueues the others while "
+                         "the GPU works")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--host-alloc", default="pinned", choices=["pinned", "wc"],
                     help="e2e leg: ordinary pinned host memory (default) or write-combined pinned memory (experiment)")

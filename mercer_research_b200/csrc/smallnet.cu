@@ -60,13 +60,16 @@ __device__ long long g_snp_stamp[1024][8];
 // exchange kernel still rewrites the parameters, which breaks the contract of ld.global.nc ("not modified during the
 // kernel's lifetime") -- and ptxas does hoist such loads above griddepcontrol.wait (seen in SASS, round 2: two
 // LDG.E.64.CONSTANT of W0 sat in front of ACQBULK and read stale weights; caught by bench.py's graph-replayed parity block).
-// There the parameters are read with volatile ld.global.cg: coherent at L2, never served from this SM's L1, and the
-// compiler may not move them across the wait.
-template <bool COHERENT>
+// There the parameters are read with VOLATILE loads the compiler may not move across the wait: ld.global.cg (L2) for what is
+// consumed at once, ld.global.ca for the part of W0 that was prefetched into L1 AFTER the wait (this SM's L1 was
+// invalidated when the CTA started and no parameter line entered it before the wait, so it cannot hold a stale one).
+// MODE 0: read-only path; 1: volatile .cg; 2: volatile .ca.
+template <int MODE>
 __device__ __forceinline__ double sn_ld(const double* p) {
-    if (!COHERENT) return __ldg(p);
+    if (MODE == 0) return __ldg(p);
     double v;
-    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    if (MODE == 1) asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    else asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -204,24 +207,24 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
             const bool kok = (ks_begin + u) < ks_end && k < L;
             const double* wp = W0 + (size_t)k * R0 + g;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) w_pre[u][i] = (kok && rowok[i]) ? sn_ld<PREWAIT>(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
+            for (int i = 0; i < 4; ++i) w_pre[u][i] = (kok && rowok[i]) ? sn_ld<PREWAIT ? 1 : 0>(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
         }
         SN_PHASE(9);
         // biases + narrow-layer weights into shared memory (after the register loads above), as asynchronous copies: no
         // register dependency, so no warp waits an L2 round trip here (PREWAIT: through registers, coherent at L2)
         if (PREWAIT) {
-            for (int i = tid; i < n_small; i += SNA_THREADS) s_small[i] = sn_ld<true>(params + small_base + i);
+            for (int i = tid; i < n_small; i += SNA_THREADS) s_small[i] = sn_ld<1>(params + small_base + i);
         } else {
             for (int i = tid; i < n_small; i += SNA_THREADS) {
                 const unsigned dst = (unsigned)__cvta_generic_to_shared(s_small + i);
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(params + small_base + i) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
-            // the rest of this warp's K range of W0 into L1 (PREWAIT reads it from L2: L1 must not keep parameters there)
-            const long long lo = (long long)min((ks_begin + SN_U) * 4, L) * R0, hi = (long long)min(ks_end * 4, L) * R0;   // doubles
-            for (long long e = lo + lane * 16; e < hi; e += 32 * 16)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(W0 + e));
         }
+        // the rest of this warp's K range of W0 into L1
+        const long long lo = (long long)min((ks_begin + SN_U) * 4, L) * R0, hi = (long long)min(ks_end * 4, L) * R0;   // doubles
+        for (long long e = lo + lane * 16; e < hi; e += 32 * 16)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(W0 + e) : "memory");
     };
     if (!PREWAIT) load_params();
 
@@ -343,7 +346,7 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
                 const bool kok = (ks + u) < ks_end && k < L;
                 const double* wp = W0 + (size_t)k * R0 + g;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) af[u][i] = (kok && rowok[i]) ? sn_ld<PREWAIT>(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
+                for (int i = 0; i < 4; ++i) af[u][i] = (kok && rowok[i]) ? sn_ld<PREWAIT ? 2 : 0>(wp + i * 8) : 0.0;  // A frag: row g (m), col t (k)
                 if (FUSED) bf[u] = kok ? trow[k] : 0.0;
                 else bf[u] = (kok && sample_ok) ? __ldg(frow + k) : 0.0;
             }

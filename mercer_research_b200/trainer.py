@@ -118,12 +118,15 @@ class DataParallelTrainer:
         self._reduce_and_apply(int(images.shape[0]))
         return self.model.last_batch_stats()
 
-    def train_epoch_host(self, images, labels, batch: int):
+    def train_epoch_host(self, images, labels, batch: int, verify_steps: bool = True):
         """This rank's shard of a host-resident dataset walked in ``chunks_exact(batch)`` steps (rcn.rs:147-149) with the
         H2D copy of the next chunk overlapping the current step; returns per-step (cost, hits) of this rank's shard.
-        With the NCCL exchange the loop is driven step by step from here (the collective is a host call)."""
+        With the NCCL exchange the loop is driven step by step from here (the collective is a host call).
+        ``verify_steps``: agree on the step count across ranks first (one small collective + a host sync); a caller that
+        repeats an epoch shape every rank has already agreed on may pass False on ALL ranks."""
         n_steps = int(images.shape[0]) // int(batch)
-        self._same_on_all_ranks(n_steps, "the number of chunks_exact steps of this epoch")
+        if verify_steps:
+            self._same_on_all_ranks(n_steps, "the number of chunks_exact steps of this epoch")
         self._bind_stream()
         if self.world == 1 or self.p2p:
             return self.model.train_epoch_host(images, labels, batch, self.eta, batch * self.world)
