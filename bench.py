@@ -561,6 +561,19 @@ def run_leg(ctx, name, wl, B, steps, warmup, exchange, *, main, steps_per_graph=
 
     e2e_run(e2e_steps_n, True)                  # warm-up = the timed call sequence itself: buffers sized, step graphs captured,
                                                 # the per-call step counts agreed on across ranks (not repeated in the timed region)
+    # ... and, like the device-resident leg, ~0.3 s of the same load: the timed region of a short run (the driver's K = 20 is
+    # half a millisecond) must not start on a GPU / PCIe link that idled down while the host buffers were being built
+    # (measured: 18-31 M images/s without this, against 39-43 M)
+    torch.cuda.synchronize()
+    t_w = time.perf_counter()
+    e2e_run(e2e_steps_n, False)
+    torch.cuda.synchronize()
+    per_call = max(time.perf_counter() - t_w, 1e-5)
+    reps = torch.tensor([min(2000, int(0.3 / per_call))], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(reps, 0)
+    for _ in range(int(reps.item())):
+        e2e_run(e2e_steps_n, False)
     _barrier(ctx)
     clocks.mark_begin()
     e0.record(stream)
@@ -703,6 +716,10 @@ def leg_roofline(leg, pk, fp64_peak, int8_peak, int8_how, traffic_all, workload_
              "frac_fp64_dense_only": dense_flops / (ms_step * 1e-3) / 1e12 / fp64_peak}
     traffic = (traffic_all.get(workload_key, {}) or {}).get(top) if top else None
     small = top is not None and top.startswith("smallnet")
+    if small:   # the fused step = kernel A + kernel B: DRAM bytes of both launches
+        tw = traffic_all.get(workload_key, {}) or {}
+        parts = [v for k, v in tw.items() if k.startswith("smallnet") and isinstance(v, (int, float))]
+        traffic = float(sum(parts)) if parts else None
     if small:
         # the fused narrow-network step: two kernels that are ONE dependent chain; 99 flop per compulsory byte against an FP64
         # ridge of ~5 flop/B => FP64-pipe-bound in the limit. The fraction is the WHOLE step (kernel A + kernel B + the

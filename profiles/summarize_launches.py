@@ -16,9 +16,12 @@ def main(path):
         a[0] += 1
         a[1] += v
     tot = sum(a[1] for a in agg.values())
-    print(f"{'n':>5} {'mean_ns':>10} {'share':>6}  grid / block / kernel")
+    own = sum(a[1] for k, a in agg.items() if "rcn::" in k)
+    print(f"{'n':>5} {'mean_ns':>10} {'share':>6} {'of rcn':>7}  grid / block / kernel   (rcn:: = this repo's kernels; the rest is torch set-up "
+          "and the DGEMM / IGEMM peak probes of bench.py)")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print(f"{a[0]:5d} {a[1] / a[0]:10.1f} {a[1] / tot:6.3f}  {a[2]} {a[3]} {k}")
+        mine = f"{a[1] / own:7.3f}" if "rcn::" in k else "      -"
+        print(f"{a[0]:5d} {a[1] / a[0]:10.1f} {a[1] / tot:6.3f} {mine}  {a[2]} {a[3]} {k}")
 
 
 if __name__ == "__main__":

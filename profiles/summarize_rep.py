@@ -21,10 +21,11 @@ M = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", 
      "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
      "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
      "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]
-NAMES = {"smallnet_fwd_bwd_kernel<1>": "smallnet_fwd_bwd_kernel(fused features)", "smallnet_fwd_bwd_kernel<2>": "smallnet_fwd_bwd_kernel(fused features)",
-         "smallnet_fwd_bwd_kernel<0>": "smallnet_fwd_bwd_kernel", "smallnet_wgrad_kernel<2>": "smallnet_wgrad_kernel(+SGD update)",
-         "smallnet_wgrad_kernel<0>": "smallnet_wgrad_kernel", "smallnet_wgrad_kernel<1>": "smallnet_wgrad_kernel",
-         "smallnet_wgrad_kernel<3>": "smallnet_wgrad_kernel(+exchange+SGD update)"}
+NAMES = {"smallnet_fwd_bwd_kernel<1, 0>": "smallnet_fwd_bwd_kernel(fused features)", "smallnet_fwd_bwd_kernel<2, 0>": "smallnet_fwd_bwd_kernel(fused features)",
+         "smallnet_fwd_bwd_kernel<2, 1>": "smallnet_fwd_bwd_kernel(fused features, front end ahead of the exchange)",
+         "smallnet_fwd_bwd_kernel<0, 0>": "smallnet_fwd_bwd_kernel", "smallnet_wgrad_kernel<2, 64>": "smallnet_wgrad_kernel(+SGD update)",
+         "smallnet_wgrad_kernel<0, 64>": "smallnet_wgrad_kernel", "smallnet_wgrad_kernel<1, 64>": "smallnet_wgrad_kernel",
+         "smallnet_wgrad_kernel<3, 64>": "smallnet_wgrad_kernel(+exchange+SGD update)"}
 
 
 def to_bytes(v, unit):
@@ -47,10 +48,14 @@ def main(rep, workload, out_txt):
                 cands = [h for h in hdr if h.endswith(m)]
                 if cands:
                     col[m] = col[cands[0]]
-            if m in col and r[col[m]] not in ("", "n/a"):
+            if m in col and r[col[m]] not in ("", "n/a", "no data"):
                 v = r[col[m]]
-                rec[m].append(to_bytes(v, units[col[m]]) if "bytes" in m else float(v.replace(",", "")))
-    lines = [f"# {os.path.basename(rep)}  (ncu --set full --clock-control none; warm L2 between replays -> DRAM bytes are a lower bound)"]
+                try:
+                    rec[m].append(to_bytes(v, units[col[m]]) if "bytes" in m else float(v.replace(",", "")))
+                except ValueError:
+                    pass
+    note = sys.argv[4] if len(sys.argv) > 4 else "ncu --set full --clock-control none"
+    lines = [f"# {os.path.basename(rep)}  ({note})"]
     traffic = {}
     for name, rec in agg.items():
         n = len(rec["gpu__time_duration.sum"])
