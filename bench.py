@@ -464,7 +464,10 @@ def run_leg(ctx, name, wl, B, steps, warmup, exchange, *, main, steps_per_graph=
     if graph_ok:
         l_before = _lib.kernel_launches()
         # the timed region is a whole number of replays: the largest divisor of K that is <= --steps-per-graph
-        spg = max(d for d in range(1, max(1, min(steps_per_graph, steps)) + 1) if steps % d == 0)
+        # (data-parallel groups take graphs twice as long: a graph boundary is a full dependency, so the first kernel A of a
+        # graph cannot run its front end under the previous graph's last exchange kernel -- ~4 us lost per boundary at N = 8)
+        spg_cap = steps_per_graph * (2 if world > 1 else 1)
+        spg = max(d for d in range(1, max(1, min(spg_cap, steps)) + 1) if steps % d == 0)
         trainer.capture(warmup=3, steps_per_graph=spg)
         kernels_per_step = (_lib.kernel_launches() - l_before) // (3 + spg)   # 3 warm-up steps + spg captured steps
     else:
@@ -962,7 +965,8 @@ def main():
                     help="consecutive steps captured into one CUDA graph (the timed region replays it steps/this times). Small graphs on "
                          "purpose: the timed region starts on an idle GPU, a graph's launch latency grows with its node count (measured: "
                          "~38 us for 20 steps, ~12 us for 5) and only the FIRST launch is exposed -- the host enqueues the others while "
-                         "the GPU works")
+                         "the GPU works. (A 2-step head graph followed by 9-step graphs was measured WORSE at K = 20: 22-31 us/step, the "
+                         "head is too short to cover the host's launch of the first long graph.)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--host-alloc", default="pinned", choices=["pinned", "wc"],
                     help="e2e leg: ordinary pinned host memory (default) or write-combined pinned memory (experiment)")
