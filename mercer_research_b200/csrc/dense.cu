@@ -547,6 +547,16 @@ int launch_dense_backward_weight(const double* delta, const double* A_prev, size
         const int max_splits = (int)(Kb / 64) > 0 ? (int)(Kb / 64) : 1;
         if (splits > max_splits) splits = max_splits;
         if (splits > 64) splits = 64;
+        // Few 128 x 128 tiles but a deep batch (c3: dW0 is 256 x 1024 over 4096 samples = 16 tiles): ONE wave of the big tile
+        // -- one CTA per SM, 32 DMMAs per 12 fragment loads; 0.86 of the DGEMM peak at one CTA per SM on the c5 shapes --
+        // with the batch split floor(148 / tiles) ways beats two waves of 64 x 64 tiles (ncu, c3: 20 % warps active, 0.52 of peak).
+        // launch_gemm_tiles takes the big tile when tiles x splits covers at least 7/8 of the SMs.
+        const size_t big = M > 32 ? (size_t)cdiv(M, 128) * cdiv(N, 128) : 0;
+        static const bool big_on = []() { const char* e = getenv("RCN_CUDA_WGRAD_BIG_TILE"); return !(e && e[0] == '0'); }();
+        if (big_on && big > 0 && big < (size_t)kNumSMs) {
+            const int s_big = (int)((size_t)kNumSMs / big);
+            if (s_big >= 2 && Kb / (size_t)s_big >= 256 && big * (size_t)s_big >= (size_t)kNumSMs * 7 / 8) splits = s_big;
+        }
     }
     splits = effective_splits(Kb, splits);
     if (N > 0) {

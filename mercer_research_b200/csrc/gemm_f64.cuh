@@ -195,7 +195,7 @@ static int launch_gemm_tiles(const char* name, const ALoad& la, const BLoad& lb,
                              int k_per_split, const Epi& epi, cudaStream_t stream) {
     if (M <= 32) return launch_dmma<32, 128, 32, 16, ALoad, BLoad, Epi>(name, la, lb, M, N, K, splits, k_per_split, epi, stream);
     const size_t big_tiles = (size_t)cdiv(M, 128) * cdiv(N, 128) * splits;
-    if (big_tiles >= (size_t)kNumSMs)
+    if (big_tiles >= (size_t)kNumSMs * 7 / 8)   // (almost) one CTA per SM is enough for the big tile: it is the efficient one
         return launch_dmma<128, 128, 64, 32, ALoad, BLoad, Epi>(name, la, lb, M, N, K, splits, k_per_split, epi, stream);
     return launch_dmma<64, 64, 32, 16, ALoad, BLoad, Epi>(name, la, lb, M, N, K, splits, k_per_split, epi, stream);
 }
