@@ -4,6 +4,8 @@
 // memory, the only global traffic is the image read and the feature write (H*W*s_in + L*8 B).
 #include "features.cuh"
 
+#include <type_traits>
+
 #include <cmath>
 #include <cstdlib>
 
@@ -260,6 +262,96 @@ __global__ void __launch_bounds__(256) stage_final_kernel(const __grid_constant_
     }
 }
 
+// Convolve2D(Same) WITHOUT a pool, exact int32 maps (the wide conv stacks of BASELINE config 4: 64x64 maps fanned out x4 per
+// layer stay too large for shared memory, so the stage streams HBM -> HBM).  One CTA = one input map of one image; a thread
+// owns output row y and slides a three-column window along x: the vertical passes [1,0,-1] / [1,2,1] of a column are computed
+// once and reused by the three outputs that read it, so a pixel costs 3 coalesced loads (lanes = consecutive rows of the
+// column-major map) and ~12 integer operations instead of the 9 bounds-tested loads and two integer divisions of the generic
+// item loop.  Same closed form as sobel4<int, true> (response centred at (y-1, x-1), row 0 zero, last input
+// column never read), so the result is bit-identical.
+template <typename Emit>
+__device__ __forceinline__ void conv_same_strips(const Stage& st, const int* __restrict__ f, int i, const Emit& emit, int tid) {
+    const int h = st.h_in, w = st.w_in;
+    const int rows = min(h, 256);
+    const int n_strips = max(1, 256 / rows);
+    const int sw = (w + n_strips - 1) / n_strips;
+    const int yl = tid % rows, sidx = tid / rows;
+    if (sidx >= n_strips) return;
+    const int xa = sidx * sw, xb = min(w, xa + sw);
+    int sT, sL, sR, sB;   // slot order rcn.rs:325-339
+    if (st.first) { sT = 0; sL = 1; sR = 2; sB = 3; }
+    else { sB = i; sT = st.n_in + 3 * i; sL = sT + 1; sR = sT + 2; }
+    for (int y = yl; y < h; y += rows) {
+        if (y == 0) {
+            for (int x = xa; x < xb; ++x) { emit(sT, 0, x, 0); emit(sL, 0, x, 0); emit(sR, 0, x, 0); emit(sB, 0, x, 0); }
+            continue;
+        }
+        const int rr = y - 1;
+        auto column = [&](int j, int& ct, int& cs) {
+            if (j >= 0 && j <= w - 2) {
+                const int* col = f + (size_t)j * h + rr;
+                const int a = (rr >= 1) ? col[-1] : 0, b = col[0], c = col[1];
+                ct = a - c;            // [1, 0, -1]
+                cs = a + 2 * b + c;    // [1, 2, 1]
+            } else {
+                ct = 0; cs = 0;
+            }
+        };
+        int ct0, cs0, ct1, cs1;
+        column(xa - 2, ct0, cs0);
+        column(xa - 1, ct1, cs1);
+#pragma unroll 2   // (unroll 4 cost 128 registers = two CTAs per SM: 22 % warps active, slower than the generic loop)
+        for (int x = xa; x < xb; ++x) {
+            int ct2, cs2;
+            column(x, ct2, cs2);
+            const int t = ct0 + 2 * ct1 + ct2;   // Top; Bottom is its negation
+            const int l = cs0 - cs2;             // Left; Right is its negation
+            emit(sT, y, x, max(t, 0));
+            emit(sL, y, x, max(l, 0));
+            emit(sR, y, x, max(-l, 0));
+            emit(sB, y, x, max(-t, 0));
+            ct0 = ct1; cs0 = cs1; ct1 = ct2; cs1 = cs2;
+        }
+    }
+}
+
+// The CTA's input map is first copied into shared memory (when it fits: `staged`; 16-byte loads, every request of the map
+// in flight at once), so the HBM / L2 latency is paid once per map instead of once per pixel (ncu of the first version:
+// 57 % of the samples were long-scoreboard waits on the three loads of a pixel).
+__device__ __forceinline__ const int* conv_same_stage_map(const int* __restrict__ g, int n, int staged, int* s_map) {
+    if (!staged) return g;
+    __syncthreads();   // the previous image's map has been consumed
+    const int4* g4 = reinterpret_cast<const int4*>(g);
+    int4* s4 = reinterpret_cast<int4*>(s_map);
+    for (int k = threadIdx.x; k < n / 4; k += 256) s4[k] = g4[k];
+    __syncthreads();
+    return s_map;
+}
+
+__global__ void __launch_bounds__(256, 4) conv_same_maps_kernel(const __grid_constant__ Stage st, const int* __restrict__ in,
+                                                            size_t in_stride, int* __restrict__ out, size_t out_stride, size_t B,
+                                                            int staged) {
+    extern __shared__ __align__(16) int s_map[];
+    const int i = blockIdx.x;
+    for (size_t img = blockIdx.y; img < B; img += gridDim.y) {
+        EmitMaps<int> e{out + img * out_stride, st.h_out, st.h_out * st.w_out};
+        const int* f = conv_same_stage_map(in + img * in_stride + (size_t)i * st.h_in * st.w_in, st.h_in * st.w_in, staged, s_map);
+        conv_same_strips(st, f, i, e, threadIdx.x);
+    }
+}
+
+__global__ void __launch_bounds__(256, 4) conv_same_final_kernel(const __grid_constant__ Stage st, const int* __restrict__ in,
+                                                             size_t in_stride, double* __restrict__ out, size_t L,
+                                                             const Standardise sc, size_t B, int staged) {
+    extern __shared__ __align__(16) int s_map[];
+    const int i = blockIdx.x;
+    for (size_t img = blockIdx.y; img < B; img += gridDim.y) {
+        EmitFeatures<int> e{out + img * L, st.h_out, st.h_out * st.w_out, sc};
+        const int* f = conv_same_stage_map(in + img * in_stride + (size_t)i * st.h_in * st.w_in, st.h_in * st.w_in, staged, s_map);
+        conv_same_strips(st, f, i, e, threadIdx.x);
+    }
+}
+
 constexpr size_t kFusedSmemLimit = 200 * 1024;
 
 // u8 images through conv(Same)+pool stacks: the staged kernel above.  Returns false when the plan does not qualify.
@@ -329,6 +421,27 @@ static int launch_features_t(const FeaturePlan& plan, const TIN* images, size_t 
         const size_t items = (size_t)st.n_in * st.h_out * st.w_out;
         dim3 grid(cdiv(items, 256), (unsigned)(B > 32768 ? 32768 : B));
         if (grid.x > 1024) grid.x = 1024;
+        if (std::is_same<T, int>::value && st.kind == 0 && st.same && st.h_in >= 2) {   // streaming strip kernels (see above)
+            static const bool strips = []() { const char* e = getenv("RCN_CUDA_CONV_STRIPS"); return !(e && e[0] == '0'); }();
+            if (strips) {
+                const dim3 sgrid((unsigned)st.n_in, grid.y);
+                const int* cin = reinterpret_cast<const int*>(cur);
+                // the map goes through shared memory when it fits the default 48 KB and 16-byte loads are possible
+                const size_t map_elems = (size_t)st.h_in * st.w_in;
+                const int staged = (map_elems * sizeof(int) <= 48 * 1024 && map_elems % 4 == 0 && cur_stride % 4 == 0 &&
+                                    (reinterpret_cast<uintptr_t>(cin) & 15) == 0) ? 1 : 0;
+                const size_t ssmem = staged ? map_elems * sizeof(int) : 0;
+                if (s == sl.n - 1) {
+                    RCN_LAUNCH("conv_same_final_kernel", stream, conv_same_final_kernel<<<sgrid, 256, ssmem, stream>>>(st, cin, cur_stride, out, plan.L, sc, B, staged));
+                } else {
+                    const size_t out_stride = (size_t)st.n_out * st.h_out * st.w_out;
+                    RCN_LAUNCH("conv_same_maps_kernel", stream, conv_same_maps_kernel<<<sgrid, 256, ssmem, stream>>>(st, cin, cur_stride, reinterpret_cast<int*>(nxt), out_stride, B, staged));
+                    T* tmp = cur; cur = nxt; nxt = tmp;
+                    cur_stride = out_stride;
+                }
+                continue;
+            }
+        }
         if (s == sl.n - 1) {
             RCN_LAUNCH("stage_final_kernel", stream, stage_final_kernel<T><<<grid, 256, 0, stream>>>(st, cur, cur_stride, out, plan.L, sc, B));
         } else {
