@@ -794,7 +794,41 @@ def _teardown_group(ctx):
         ctx.hung_teardown = True
 
 
+def _bind_near_gpu(local_rank):
+    """Run this rank's host threads on the CPUs NVML names as closest to its GPU (same socket / NUMA node): launches,
+    doorbells and the pinned buffers this process first touches then stay local to the GPU's PCIe root.  Measured need: on
+    two-socket boxes the device-resident K = 20 region was bimodal per PROCESS (435 vs 575 us) depending on where the
+    scheduler had put it.  Returns (description, original affinity) -- the CPU baseline leg restores the original set."""
+    try:
+        orig = os.sched_getaffinity(0)
+    except (AttributeError, OSError):
+        return "unchanged (no sched_getaffinity)", None
+    if os.environ.get("RCN_BENCH_AFFINITY", "1") == "0":
+        return "unchanged (RCN_BENCH_AFFINITY=0)", orig
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        idx = local_rank
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local_rank < len(ids) and ids[local_rank].isdigit():
+                idx = int(ids[local_rank])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_words = (max(orig | {os.cpu_count() or 1}) + 64) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        ideal = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        want = ideal & orig
+        if not want or want == orig:
+            return f"unchanged ({len(orig)} cpus; NVML ideal set covers them all or none)", orig
+        os.sched_setaffinity(0, want)
+        return f"NVML ideal CPUs of the GPU ({len(want)} of {len(orig)} cpus)", orig
+    except Exception as e:  # noqa: BLE001 -- affinity is an optimisation, never a failure
+        return f"unchanged ({type(e).__name__})", orig
+
+
 def run_gpu(args, wl, rank, world, local_rank):
+    affinity, orig_affinity = _bind_near_gpu(local_rank)
     import torch
     import torch.distributed as dist
 
@@ -883,6 +917,11 @@ def run_gpu(args, wl, rank, world, local_rank):
     print("[bench] rank 0: cpu baseline", file=sys.stderr, flush=True)
     # ---- CPU baseline on this box's host cores (bounded sample, ~10-20 s) ------------------------------------------
     Bs = cpu_sample_batch(wl, os.cpu_count() or 1)
+    if orig_affinity:
+        try:
+            os.sched_setaffinity(0, orig_affinity)   # the CPU baseline gets every host core
+        except OSError:
+            pass
     cpu_ips, cpu_ms, cpu_done, cores, Bs = cpu_train_steps(wl, steps=10 ** 6, warmup=2, max_seconds=12.0, batch=Bs)
     # BASELINE.json configs[0] (the reference's own CPU-runnable case: the same network at batch 32), ~3 s more
     c1_ips, _, c1_done, _, _ = cpu_train_steps(WORKLOADS["c1"], steps=10 ** 6, warmup=2, max_seconds=3.0)
@@ -925,16 +964,18 @@ def run_gpu(args, wl, rank, world, local_rank):
                    "l2_policy": f"inputs rotate over {main['n_batches']} resident batches = {main['n_batches'] * B * H * W / 2 ** 20:.0f} MiB > 126 MB L2 "
                                 "(each step's kernel A asks L2 for the NEXT step's images ahead of time; every image still comes from HBM once per step)",
                    "step": main["step_desc"], "cuda_graph": main["graph"], "steps_per_graph": main["spg"],
+                   "host_cpu_affinity": affinity,
                    # the W requested warm-up steps plus ~0.3 s of the same load so that clocks have ramped
                    "warmup_steps_run": main["n_warm"]},
         "clocks": main["clocks"],
         "e2e": {"value": main["e2e_value"], "unit": "images/s", "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": main["d2h"],
                 "ms_per_step": main["e2e_ms_step"], "host_buffers": main["host_alloc"],
-                # PCIe bytes per second this rank pulled inside the timed region (the e2e path's own bound: SM-issued
-                # zero-copy reads reach ~38 GB/s on this pool's boxes, profiles/r1s_full_host_prefetch.txt)
+                # PCIe bytes per second this rank moved inside the timed region (the link: 43.6-55 GB/s for copy-engine
+                # transfers of 0.8-64 MB, profiles/r2_pcie_dma.json; 38 GB/s for SM-issued zero-copy reads)
                 "h2d_GBps_per_gpu": main["h2d"] / (main["e2e_ms_step"] * 1e-3) * 1e-9,
-                "api": "rcn_cuda_train_epoch_host (chunks_exact loop over a pinned host dataset: the GPU pulls chunk k+1 over PCIe "
-                       "while chunk k trains, one CUDA graph launch per two steps, per-step cost/hits written back to host memory)"},
+                "api": "rcn_cuda_train_epoch_host (chunks_exact loop over a pinned host dataset: the copy engine streams the chunks "
+                       "into a device ring ahead of the steps, kernel A waits on an arrival counter, 20 steps per CUDA graph launch, "
+                       "per-step cost/hits written back to host memory; RCN_CUDA_HOST_COPY=pull = round 1's SM-issued zero-copy loads)"},
         "gpu_launches": int(main["launches"]),
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_ips, "unit": "images/s", "cores": cores, "kind": "port",

@@ -80,6 +80,9 @@ struct BatchIndex {
     // Streaming from a HOST dataset (rcn_cuda_train_epoch_host): `images` is a ring of `window` image slots and image
     // i of the walk lives in slot i % window (labels are still indexed by i).  0 = images hold the whole dataset.
     long long window = 0;
+    // ... filled by the copy engine: `*arrived` = how many images of the walk have landed in the ring so far (written by a
+    // stream memory operation behind each copy).  A kernel reading image i first waits for *arrived > i.  nullptr = no wait.
+    const long long* arrived = nullptr;
     // Epoch mode: how the cursor advances after this step (chunks_exact wrap-around, rcn.rs:147) -- lets a kernel ask L2 for
     // the NEXT step's images ahead of time.  0 = unknown (no prefetch).
     long long batch = 0, n_samples = 0;

@@ -379,6 +379,26 @@ __device__ __forceinline__ size_t source_image(const BatchIndex& bi, size_t img)
     const long long pos = __ldcg(bi.cursor) + (long long)img;   // L2: a persistent kernel advances the cursor between steps
     return (size_t)(bi.perm ? bi.perm[pos] : pos);
 }
+// Streamed epoch, copy-engine mode: block until image `src` of the walk has landed in the ring (BatchIndex::arrived).  The
+// counter is written by the copy stream right behind the copy that carried the image, so an acquire load that sees it also
+// orders the image bytes; the proxy fence extends that to the bulk-async loads issued next.  A copy that has not arrived after
+// 20 s is a broken copy stream: trap (the host call then fails with the CUDA error instead of training on garbage).
+__device__ __forceinline__ void wait_arrived(const BatchIndex& bi, size_t src) {
+    if (!bi.arrived) return;
+    long long a;
+    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(a) : "l"(bi.arrived) : "memory");
+    if (a <= (long long)src) {
+        unsigned long long t0, t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        do {
+            __nanosleep(200);
+            asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(a) : "l"(bi.arrived) : "memory");
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > 20000000000ull) __trap();
+        } while (a <= (long long)src);
+    }
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
 // where that image's pixels live: the dataset itself, or a ring of `window` slots when streaming from the host
 __device__ __forceinline__ size_t image_slot(const BatchIndex& bi, size_t src) {
     return bi.window ? (size_t)((unsigned)src % (unsigned)bi.window) : src;   // 32-bit: a streamed epoch has < 2^32 samples

@@ -1,6 +1,8 @@
 // model.cu -- the C ABI of librcn_cuda.so (include/rcn_cuda.h): model handle, device buffers, host<->device
 // staging, and the layer dispatch that replaces rcn's per-sample CPU loops (rcn/src/rcn.rs) with batched
 // kernels (features.cu, dense.cu).
+#include <cuda.h>
+#include <algorithm>
 #include <atomic>
 #include <map>
 #include <memory>
@@ -71,9 +73,57 @@ constexpr int kHsStateSlots = 6;
 // of the epoch length and serve every later call with the same batch shape
 constexpr long long kHsNoWrap = 1ll << 62;
 // consecutive steps captured into one CUDA graph by rcn_cuda_train_epoch_host (RCN_CUDA_HOST_STEPS_PER_GRAPH overrides)
-static int hs_steps_per_graph() {
-    static const int v = []() { const char* e = getenv("RCN_CUDA_HOST_STEPS_PER_GRAPH"); int n = e ? atoi(e) : 2; return n < 1 ? 1 : (n > 64 ? 64 : n); }();
+// Default: 2 in pull mode (every step joins its prefetch branch anyway), 20 in dma mode -- the steps inside a graph follow each
+// other without the host or the PCIe link in between, while every graph boundary cost 4-5 us (and now and then 27 us) with
+// copies in flight on the link (profiles/r2_e2e_timeline.txt): 24.8 / 23.4 / 22.3 / 21.8 us per step at 5 / 10 / 20 / 40.
+static int hs_steps_per_graph(bool dma) {
+    static const int v = []() { const char* e = getenv("RCN_CUDA_HOST_STEPS_PER_GRAPH"); int n = e ? atoi(e) : 0; return n < 1 ? 0 : (n > 64 ? 64 : n); }();
+    return v ? v : (dma ? 20 : 2);
+}
+// How the images of the streamed epoch cross PCIe (RCN_CUDA_HOST_COPY = dma | pull):
+//  dma  (default) the copy engine.  The copy stream walks the dataset with back-to-back cudaMemcpyAsync calls into a ring of
+//       `kHsRingSteps` chunks, an event behind each; a second stream waits for each event and publishes, with an 8-byte copy
+//       from a pinned table, how many images have landed (state[3]).  Kernel A's image-loading lanes wait for their own image on
+//       that counter (wait_arrived), so the compute stream carries nothing but back-to-back graph launches -- no events, no
+//       per-step join.  Once per quarter of the ring the copy stream waits (cuStreamWaitValue64) until the training cursor
+//       (state[0]) has passed the quarter's previous occupants.  Copies ramp 1 ... 2 ... 4 ... 8 chunks: the first step starts
+//       after ONE chunk has crossed the link, later copies run at the link's large-transfer rate.  Measured on a warm link
+//       (profiles/r2_pcie_dma.json): 43.6 GB/s for one 0.8 MB chunk, 48.7 for two, 53.6 for eight, against 38 GB/s for
+//       SM-issued zero-copy loads; and no CTA of the step's kernels shares its SM with a copy kernel.  (Publishing the counter
+//       on the copy stream itself -- cuStreamWriteValue64 or the 8-byte copy -- put ~22 us between consecutive data copies,
+//       which then no longer pipeline: a one-chunk copy took 40 us instead of 18 and the copy stream became the bottleneck.)
+//  pull the prefetch kernel below on a parallel branch of the step's graph (round 1's design; also the fallback when the
+//       driver has no 64-bit stream memory operations or the staged front end is not the one selected).
+static bool hs_dma_env() {
+    static const bool v = []() { const char* e = getenv("RCN_CUDA_HOST_COPY"); return !(e && (e[0] == 'p' || e[0] == 'P')); }();
     return v;
+}
+constexpr size_t kHsRingSteps = 64;   // dma: chunks the ring holds
+constexpr size_t kHsQuarter = kHsRingSteps / 4;   // dma: granularity of the copy stream's wait for free ring slots
+constexpr size_t kHsMaxCopy = 8;      // dma: chunks per cudaMemcpyAsync once the ramp is over (divides kHsQuarter)
+constexpr int kHsEvents = 64;         // dma: one event behind each copy, reused round robin
+struct StreamMemOps {
+    CUresult (*wait64)(CUstream, CUdeviceptr, cuuint64_t, unsigned int) = nullptr;
+
+    bool ok = false;
+};
+static const StreamMemOps& stream_mem_ops(int device) {
+    static const StreamMemOps ops = [device]() {
+        StreamMemOps o;
+        auto entry = [](const char* name) -> void* {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+            return p;
+        };
+        auto get_attr = reinterpret_cast<CUresult (*)(int*, CUdevice_attribute, CUdevice)>(entry("cuDeviceGetAttribute"));
+        o.wait64 = reinterpret_cast<decltype(o.wait64)>(entry("cuStreamWaitValue64"));
+
+        int can = 0;
+        o.ok = get_attr && o.wait64 && get_attr(&can, CU_DEVICE_ATTRIBUTE_CAN_USE_64_BIT_STREAM_MEM_OPS, device) == CUDA_SUCCESS && can;
+        return o;
+    }();
+    return ops;
 }
 // PCIe pulls are latency-bound per request: every thread first issues ALL the 16-byte loads of its round (U independent
 // zero-copy reads in flight, the whole 0.8 MB chunk of the canonical config in one round trip) and only then stores them.
@@ -195,8 +245,11 @@ struct rcn_cuda_model {
     size_t stats_host_cap = 0;
     // streaming variant: the GPU pulls chunk k+1 from pinned host memory while it trains on chunk k; one graph per step
     DevBuf hs_ring, hs_state;
-    cudaGraphExec_t hs_graph = nullptr;     // hs_steps_per_graph() consecutive steps
-    cudaGraphExec_t hs_graph1 = nullptr;    // one step (the remainder of the epoch)
+    cudaStream_t flag_stream = nullptr;     // dma mode: publishes the arrival counter behind each copy
+    cudaEvent_t hs_ev[kHsEvents] = {};
+    long long* hs_counts = nullptr;         // pinned: "images arrived" value behind each copy of the streamed epoch (dma mode)
+    size_t hs_counts_cap = 0;
+    std::map<int, cudaGraphExec_t> hs_graphs;   // streamed epoch: g consecutive steps per graph, captured on first use
     cudaEvent_t hs_fork = nullptr, hs_join = nullptr;
     struct HsKey {
         size_t B = 0, H = 0, W = 0, n_steps = 0;
@@ -206,10 +259,11 @@ struct rcn_cuda_model {
         const void *labels = nullptr, *stats = nullptr, *ring = nullptr, *state = nullptr, *grads = nullptr;
         cudaStream_t stream = nullptr;
         bool dp = false;
+        long long window = 0;               // ring size in images (captured in kernel A's arguments)
         bool operator==(const HsKey& o) const {
             return B == o.B && H == o.H && W == o.W && n_steps == o.n_steps && alloc_gen == o.alloc_gen && mean_bits == o.mean_bits &&
                    sd_bits == o.sd_bits && scale == o.scale && labels == o.labels &&
-                   stats == o.stats && ring == o.ring && state == o.state && grads == o.grads && stream == o.stream && dp == o.dp;
+                   stats == o.stats && ring == o.ring && state == o.state && grads == o.grads && stream == o.stream && dp == o.dp && window == o.window;
         }
     } hs_key;
 
@@ -363,12 +417,16 @@ int accumulate_dev(rcn_cuda_model* h, const double* feats, const double* onehot,
 // images (DEVICE) -> gradient sums.  The canonical narrow network with u8 pixels runs the convpool stack inside
 // kernel A (smallnet.cu); everything else runs the feature kernel(s) first.  `bi` (optional) is the epoch-mode
 // device-side batch selection; without it `labels` are this batch's labels.
+static bool fused_front_enabled() {
+    static const bool v = []() { const char* e = getenv("RCN_CUDA_FUSED_FRONT"); return !(e && e[0] == '0'); }();
+    return v;
+}
+
 int accumulate_images_dev(rcn_cuda_model* h, const void* images, int fmt, const int64_t* labels, size_t B, size_t H,
                           size_t W, const BatchIndex* bi) {
     RCN_TRY(h->feats.reserve(h->plan.L * B * sizeof(double)));
     const int64_t* step_labels = bi ? (const int64_t*)bi->labels_batch : labels;
-    static const bool fuse_env = []() { const char* e = getenv("RCN_CUDA_FUSED_FRONT"); return !(e && e[0] == '0'); }();
-    if (fuse_env && h->use_small && B <= smallnet_max_batch() && fmt == RCN_PIXELS_U8_ROWMAJOR && h->plan.n_conv <= 10 &&
+    if (fused_front_enabled() && h->use_small && B <= smallnet_max_batch() && fmt == RCN_PIXELS_U8_ROWMAJOR && h->plan.n_conv <= 10 &&
         h->plan.L > 0) {
         SmallNetFront fr{};
         fr.images = (const uint8_t*)images;
@@ -472,11 +530,16 @@ int rcn_cuda_destroy(rcn_cuda_handle h) {
         h->host_slot[i].release();
     }
     if (h->stats_host) cudaFreeHost(h->stats_host);
-    if (h->hs_graph) cudaGraphExecDestroy(h->hs_graph);
-    if (h->hs_graph1) cudaGraphExecDestroy(h->hs_graph1);
+    for (auto& kv : h->hs_graphs) cudaGraphExecDestroy(kv.second);
     if (h->hs_fork) cudaEventDestroy(h->hs_fork);
     if (h->hs_join) cudaEventDestroy(h->hs_join);
-    h->hs_ring.release(); h->hs_state.release(); 
+
+    h->hs_ring.release(); h->hs_state.release();
+    if (h->hs_counts) cudaFreeHost(h->hs_counts);
+    if (h->flag_stream) cudaStreamDestroy(h->flag_stream);
+    for (int i = 0; i < kHsEvents; ++i)
+        if (h->hs_ev[i]) cudaEventDestroy(h->hs_ev[i]);
+
     dp_release(h->dp);
     h->oz.release();
     DevBuf* bufs[] = {&h->params, &h->grads_own, &h->in_stage, &h->tgt_stage, &h->feats, &h->acts, &h->deltas,
@@ -1065,7 +1128,23 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
                 RCN_CUDA_TRY(cudaStreamWaitEvent(h->own_stream, h->hs_fork, 0));
                 h->stream = h->own_stream;
             }
-            RCN_TRY(h->hs_ring.reserve(2 * img_bytes));
+            RCN_TRY(h->hs_ring.reserve(kHsRingSteps * img_bytes));
+            // copy-engine mode needs the staged front end (its image-loading lanes do the waiting) and stream memory operations
+            bool dma = hs_dma_env() && fused_front_enabled() && kHsRingSteps * B < (1ull << 31) && stream_mem_ops(h->device).ok;
+            if (dma) {
+                probe.images = h->hs_ring.as<uint8_t>();
+                smallnet_front_select(h->plan, &probe);
+                dma = probe.use_cp != 0;
+            }
+            const size_t spg = (size_t)hs_steps_per_graph(dma);
+            const size_t ring_steps = dma ? kHsRingSteps : 2;
+            // the epoch as a sequence of graph launches: as many `spg`-step graphs as fit, then (dma) 5-step graphs, then single steps
+            std::vector<int> plan_g;
+            for (size_t left = n_steps; left;) {
+                const size_t g = left >= spg ? spg : (dma && left >= 5 && spg > 5 ? 5 : 1);
+                plan_g.push_back((int)g);
+                left -= g;
+            }
             RCN_TRY(h->hs_state.reserve((kHsStateSlots + B) * sizeof(long long)));
             RCN_TRY(h->tgt_stage.reserve(n_steps * B * sizeof(int64_t)));
             RCN_TRY(h->feats.reserve(h->plan.L * B * sizeof(double)));
@@ -1075,12 +1154,13 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
             bi.cursor = st;
             bi.labels_all = h->tgt_stage.as<long long>();
             bi.labels_batch = st + kHsStateSlots;
-            bi.window = (long long)(2 * B);
-            // state, labels of the whole epoch and chunk 0 go up with plain copies; everything after that is graph replays
+            bi.window = (long long)(ring_steps * B);
+            bi.arrived = dma ? st + 3 : nullptr;
+            // state, labels of the whole epoch (and, pull mode, chunk 0) go up with plain copies; after that graph replays
             const long long init[kHsStateSlots] = {0, (long long)n_steps, (long long)reinterpret_cast<uintptr_t>(images), 0, 0, 0};
             RCN_CUDA_TRY(cudaMemcpyAsync(st, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
             RCN_CUDA_TRY(cudaMemcpyAsync(h->tgt_stage.p, labels, n_steps * B * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-            RCN_CUDA_TRY(cudaMemcpyAsync(h->hs_ring.p, images, img_bytes, cudaMemcpyHostToDevice, h->stream));
+            if (!dma) RCN_CUDA_TRY(cudaMemcpyAsync(h->hs_ring.p, images, img_bytes, cudaMemcpyHostToDevice, h->stream));
             rcn_cuda_model::HsKey key;
             key.B = B; key.H = H; key.W = W; key.n_steps = 0; key.scale = scale_s;   // the graphs do not depend on the epoch length
             key.labels = h->tgt_stage.p;   // (grows with the epoch length: a longer epoch than any before re-captures)
@@ -1089,15 +1169,22 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
             memcpy(&key.sd_bits, &h->sd, sizeof(double));
             key.stats = h->stats_host; key.ring = h->hs_ring.p; key.state = st; key.grads = h->grads; key.stream = h->stream;
             key.dp = h->dp.connected;
-            if (!h->hs_graph || !h->hs_graph1 || !(key == h->hs_key)) {
-                if (h->hs_graph) { cudaGraphExecDestroy(h->hs_graph); h->hs_graph = nullptr; }
-                if (h->hs_graph1) { cudaGraphExecDestroy(h->hs_graph1); h->hs_graph1 = nullptr; }
+            key.window = dma ? -bi.window : bi.window;   // (sign: the pull graphs carry the prefetch branch, the dma graphs do not)
+            if (h->hs_graphs.empty() || !(key == h->hs_key)) {
+                for (auto& kv : h->hs_graphs) cudaGraphExecDestroy(kv.second);
+                h->hs_graphs.clear();
                 // warm-up outside capture: reserves every scratch buffer and sets kernel attributes (no parameter update)
                 h->dp_push_suppress = true;
-                const int wrc = accumulate_images_dev(h, h->hs_ring.p, pixel_format, nullptr, B, H, W, &bi);
+                BatchIndex bi_warm = bi;
+                bi_warm.arrived = nullptr;   // nothing has been copied yet: the warm-up trains on whatever the ring holds
+                const int wrc = accumulate_images_dev(h, h->hs_ring.p, pixel_format, nullptr, B, H, W, &bi_warm);
                 h->dp_push_suppress = false;
                 RCN_TRY(wrc);
                 RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
+                key.alloc_gen = alloc_generation().load(std::memory_order_relaxed);   // the warm-up may have grown scratch buffers
+                h->hs_key = key;
+            }
+            {
                 // `g` consecutive steps in ONE graph: a step is only tens of microseconds long, so the host's per-launch cost
                 // is spread over several of them; the remainder of the epoch replays the one-step graph.
                 auto capture_steps = [&](int g, cudaGraphExec_t* out) -> int {
@@ -1105,6 +1192,7 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
                     RCN_CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
                     int rc = RCN_OK;
                     for (int q = 0; q < g && rc == RCN_OK; ++q) {
+                        if (!dma) {
                         if (cudaEventRecord(h->hs_fork, h->stream) != cudaSuccess || cudaStreamWaitEvent(h->copy_stream, h->hs_fork, 0) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph fork failed"); break; }
                         {
                             LaunchScope ls("host_prefetch_kernel", h->copy_stream);
@@ -1112,13 +1200,14 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
                         }
                         if (cudaPeekAtLastError() != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "prefetch kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
                         if (cudaEventRecord(h->hs_join, h->copy_stream) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph join failed"); break; }
+                        }
                         arm_fused_update(h, scale_s, st, (long long)B, kHsNoWrap, h->stats_host);
                         rc = accumulate_images_dev(h, h->hs_ring.p, pixel_format, nullptr, B, H, W, &bi);
                         const int fused = take_upd_fused(h);
                         if (rc != RCN_OK) break;
                         if (fused & 1) {   // the weight-gradient kernel applied the update, advanced the cursor, wrote the result
                             // the prefetch branch joins at the end of its step: the next step starts after both
-                            if (cudaStreamWaitEvent(h->stream, h->hs_join, 0) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph join failed"); break; }
+                            if (!dma && cudaStreamWaitEvent(h->stream, h->hs_join, 0) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph join failed"); break; }
                             continue;
                         }
                         // (fused & 2: kernel B advanced the cursor and wrote the result; the update kernel gets no cursor)
@@ -1135,7 +1224,7 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
                         // the prefetch branch joins AFTER the exchange / update kernel was enqueued: the next step's kernel A
                         // then directly follows that kernel in the stream (its programmatic dependent) and also waits for
                         // the prefetched chunk
-                        if (cudaStreamWaitEvent(h->stream, h->hs_join, 0) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph join failed"); break; }
+                        if (!dma && cudaStreamWaitEvent(h->stream, h->hs_join, 0) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph join failed"); break; }
                     }
                     cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
                     if (rc != RCN_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
@@ -1145,18 +1234,69 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
                     if (ce != cudaSuccess) { *out = nullptr; return fail(RCN_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
                     return RCN_OK;
                 };
-                RCN_TRY(capture_steps(hs_steps_per_graph(), &h->hs_graph));
-                RCN_TRY(capture_steps(1, &h->hs_graph1));
-                key.alloc_gen = alloc_generation().load(std::memory_order_relaxed);   // the warm-up may have grown scratch buffers
-                h->hs_key = key;
+                for (int g : plan_g) {
+                    if (h->hs_graphs.count(g)) continue;
+                    cudaGraphExec_t ge = nullptr;
+                    RCN_TRY(capture_steps(g, &ge));
+                    h->hs_graphs[g] = ge;
+                }
             }
-            {
-                size_t k = 0;
-                const size_t spg = (size_t)hs_steps_per_graph();
-                for (; k + spg <= n_steps; k += spg) RCN_CUDA_TRY(cudaGraphLaunch(h->hs_graph, h->stream));
-                for (; k < n_steps; ++k) RCN_CUDA_TRY(cudaGraphLaunch(h->hs_graph1, h->stream));
+            if (!dma) {
+                for (int g : plan_g) RCN_CUDA_TRY(cudaGraphLaunch(h->hs_graphs[g], h->stream));
+            } else {
+                // Copies first (the driver queues them; each waits on the device for its ring slots), then the graph launches.
+                const StreamMemOps& mo = stream_mem_ops(h->device);
+                const CUdeviceptr cursor_dev = (CUdeviceptr)reinterpret_cast<uintptr_t>(st);
+                const char* src = static_cast<const char*>(images);
+                if (h->hs_counts_cap < n_steps) {   // pinned table of the counter values, one per copy
+                    if (h->hs_counts) cudaFreeHost(h->hs_counts);
+                    h->hs_counts = nullptr; h->hs_counts_cap = 0;
+                    RCN_CUDA_TRY(cudaHostAlloc((void**)&h->hs_counts, n_steps * sizeof(long long), cudaHostAllocDefault));
+                    h->hs_counts_cap = n_steps;
+                }
+                if (!h->flag_stream) {
+                    RCN_CUDA_TRY(cudaStreamCreateWithFlags(&h->flag_stream, cudaStreamNonBlocking));
+                    for (int i = 0; i < kHsEvents; ++i) RCN_CUDA_TRY(cudaEventCreateWithFlags(&h->hs_ev[i], cudaEventDisableTiming));
+                }
+                // the state block (cursor 0, arrived 0) must be in place before the first counter copy can land
+                RCN_CUDA_TRY(cudaEventRecord(h->hs_fork, h->stream));
+                RCN_CUDA_TRY(cudaStreamWaitEvent(h->flag_stream, h->hs_fork, 0));
+                size_t a = 0, k = 0, n_copy = 0;
+                auto enqueue_copy = [&]() -> int {
+                    // ramp: while the copies are only a few chunks ahead of the training steps a long copy would hold back the
+                    // steps waiting for its first chunk (the counter moves when a copy has landed completely)
+                    size_t g = a < 2 ? 1 : (a < 16 ? 2 : (a < 32 ? 4 : kHsMaxCopy));
+                    g = std::min(g, n_steps - a);
+                    g = std::min(g, kHsQuarter - a % kHsQuarter);                      // never across a quarter of the ring
+                    if (a >= ring_steps && a % kHsQuarter == 0) {
+                        // entering a quarter whose slots held steps [a - ring, a + quarter - ring): all of them must have trained
+                        if (mo.wait64(h->copy_stream, cursor_dev, (cuuint64_t)((a + kHsQuarter - ring_steps) * B), CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                            return fail(RCN_ERR_CUDA, "cuStreamWaitValue64 failed");
+                    }
+                    RCN_CUDA_TRY(cudaMemcpyAsync(h->hs_ring.as<char>() + (a % ring_steps) * img_bytes, src + a * img_bytes, g * img_bytes,
+                                                 cudaMemcpyHostToDevice, h->copy_stream));
+                    a += g;
+                    h->hs_counts[n_copy] = (long long)(a * B);
+                    cudaEvent_t ev = h->hs_ev[n_copy % kHsEvents];
+                    RCN_CUDA_TRY(cudaEventRecord(ev, h->copy_stream));
+                    RCN_CUDA_TRY(cudaStreamWaitEvent(h->flag_stream, ev, 0));
+                    // (cuStreamWriteValue64 here instead measured the same: 476 vs 478 us for a 20-step epoch)
+                    RCN_CUDA_TRY(cudaMemcpyAsync(st + 3, h->hs_counts + n_copy, sizeof(long long), cudaMemcpyHostToDevice, h->flag_stream));
+                    ++n_copy;
+                    return RCN_OK;
+                };
+                // One chunk's copy, then the first graph launch (its launch latency passes while the chunk crosses the link; kernel
+                // A waits on the device for whatever has not arrived yet), then copies and launches interleaved, the copies
+                // enqueued half a ring ahead of the launches.
+                RCN_TRY(enqueue_copy());
+                for (int g : plan_g) {
+                    RCN_CUDA_TRY(cudaGraphLaunch(h->hs_graphs[g], h->stream));
+                    k += (size_t)g;
+                    while (a < n_steps && a < k + ring_steps / 2) RCN_TRY(enqueue_copy());
+                }
             }
-            g_launches.fetch_add((unsigned long long)n_steps * (h->dp.connected ? 4 : 3), std::memory_order_relaxed);   // prefetch + A + B (+ exchange/update) per replay
+            // (pull: prefetch +) A + B (+ exchange/update) per replayed step
+            g_launches.fetch_add((unsigned long long)n_steps * ((dma ? 2 : 3) + (h->dp.connected ? 1 : 0)), std::memory_order_relaxed);
             RCN_CUDA_TRY(cudaStreamSynchronize(h->stream));
             stream_drained(h);
             for (size_t k = 0; k < n_steps; ++k) {

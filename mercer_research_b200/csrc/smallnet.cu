@@ -172,6 +172,7 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
             __syncwarp();
             if (lane < n_live) {
                 const size_t src = source_image(fr.bi, (size_t)(s0 + lane));
+                wait_arrived(fr.bi, src);
                 cpbulk::bulk_load(stg + lane * fr.cp.stage_bytes, fr.images + image_slot(fr.bi, src) * img_bytes, img_bytes, &s_bar);
             }
         } else if (warp == SNA_WARPS - 1 && lane < SN_TB) {

@@ -455,6 +455,55 @@ def test_train_epoch_host_streaming_large_chunks(api):
     assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
 
 
+HOST_COPY_SCRIPT = r'''
+import numpy as np, sys, torch
+sys.path.insert(0, %(root)r)
+import mercer_research_b200 as m
+rng = np.random.default_rng(31)
+B, steps = 16, 151
+N = B * steps + 5
+images = torch.from_numpy(rng.integers(0, 256, size=(N, 28, 28), dtype=np.uint8)).pin_memory()
+labels = torch.from_numpy(rng.integers(0, 10, size=N).astype(np.int64)).pin_memory()
+cfg = [m.RCNLayer.Convolve2D(m.Padding.Same), m.RCNLayer.Pool2D(m.Pooling.Max)]
+out = []
+for mode in ("loop", "epoch", "epoch-again"):
+    model = m.RCN(10, cfg, [30]); model.load_weights_and_bias(784)
+    model.set_params(np.random.default_rng(32).standard_normal(model.n_params) * 0.1)
+    model.scale_set = (40.0, 60.0)
+    if mode == "loop":
+        st = []
+        for k in range(steps):
+            model.train_batch_images(images.numpy()[k * B:(k + 1) * B], labels.numpy()[k * B:(k + 1) * B], 3.0)
+            st.append(model.last_batch_stats())
+        cost = np.array([x[0] for x in st]); hits = np.array([x[1] for x in st], dtype=np.uint64)
+    else:
+        if mode == "epoch-again":
+            model.train_epoch_host(images.numpy()[:7 * B], labels.numpy()[:7 * B], B, 3.0)
+            model.set_params(np.random.default_rng(32).standard_normal(model.n_params) * 0.1)
+        cost, hits = model.train_epoch_host(images.numpy(), labels.numpy(), B, 3.0)
+        assert len(cost) == steps
+    out.append((model.get_params(), cost, hits))
+for o in out[1:]:
+    assert np.array_equal(out[0][0].view(np.uint64), o[0].view(np.uint64)), "parameters differ"
+    assert np.array_equal(out[0][1], o[1]) and np.array_equal(out[0][2], o[2]), "per-step results differ"
+print("ok")
+'''
+
+
+@pytest.mark.parametrize("copy_mode,spg", [("dma", "0"), ("dma", "1"), ("dma", "7"), ("pull", "0"), ("pull", "3")])
+def test_train_epoch_host_copy_modes(api, copy_mode, spg):
+    """Both ways the streamed epoch moves its images over PCIe (copy engine into a 64-chunk ring with an arrival counter
+    kernel A waits on / SM-issued zero-copy loads on a graph branch), at several steps per graph ("0" = the mode's default:
+    20 / 2): 151 steps wrap the ring twice and leave a remainder of 5-step and single-step launches; bit-identical to train_batch_images chunk by chunk
+    (rcn.rs:147-149)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RCN_CUDA_HOST_COPY=copy_mode, RCN_CUDA_HOST_STEPS_PER_GRAPH=spg)
+    r = subprocess.run([sys.executable, "-c", HOST_COPY_SCRIPT % {"root": root}], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("same_device", [True, False])
 @pytest.mark.parametrize("single_call", [True, False])
 def test_dp_peer_memory_exchange_two_ranks(api, single_call, same_device):
