@@ -98,7 +98,12 @@ class ClockSampler:
 
     NVML is polled in-process every few ms (a timed region of this workload can be shorter than one `nvidia-smi -lms`
     period); samples carry a host timestamp and only those inside [mark_begin, mark_end] are reported. Falls back to an
-    `nvidia-smi -lms 100` subprocess when pynvml is unavailable."""
+    `nvidia-smi -lms 100` subprocess when pynvml is unavailable.
+
+    A timed region expected to be shorter than 50 ms (the driver's K = 20 is half a millisecond, an eighth of the polling
+    period) additionally gets one sample immediately before it and one immediately after it, taken from the timing thread (an
+    NVML query takes 4-5 us on this pool's boxes; RCN_BENCH_CLOCK_QUIET=1 pauses the poller inside such a region -- measured:
+    no difference, 47-49 M images/s either way)."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
@@ -109,6 +114,7 @@ class ClockSampler:
         self.thread = None
         self.max_mhz = None
         self.mode = None
+        self.paused, self.in_call, self.adjacent, self.query_s = False, False, [], []
 
     def start(self):
         try:
@@ -138,18 +144,28 @@ class ClockSampler:
             except Exception:
                 self.mode = None
 
-    def _poll_nvml(self):
+    def _sample_nvml(self):
         nv = self.nv
-        while not self.stop_flag:
+        t = time.perf_counter()
+        try:
+            sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
             try:
-                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                except Exception:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                self.samples.append((time.perf_counter(), sm, mask))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
             except Exception:
-                pass
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            self.samples.append((t, sm, mask))
+            self.query_s.append(time.perf_counter() - t)
+        except Exception:
+            pass
+
+    def _poll_nvml(self):
+        while not self.stop_flag:
+            if self.paused:
+                time.sleep(0.0005)
+                continue
+            self.in_call = True
+            self._sample_nvml()
+            self.in_call = False
             time.sleep(self.period)
 
     def _poll_smi(self):
@@ -166,11 +182,24 @@ class ClockSampler:
                     mask |= bit
             self.samples.append((time.perf_counter(), sm, mask))
 
-    def mark_begin(self):
+    def mark_begin(self, expected_s=None):
+        short = self.mode == "nvml" and expected_s is not None and expected_s < 0.05
+        if short:
+            if os.environ.get("RCN_BENCH_CLOCK_QUIET", "0") == "1":
+                self.paused = True
+                while self.in_call:             # a query already in flight finishes first
+                    time.sleep(0.0002)
+            self._sample_nvml()                 # ... immediately before the region, from this thread
+            self.adjacent.append(len(self.samples) - 1)
+        self._short = short
         self._t0 = time.perf_counter()
 
     def mark_end(self):
         self.windows.append((self._t0, time.perf_counter()))
+        if getattr(self, "_short", False):
+            self._sample_nvml()                 # ... and immediately after it
+            self.adjacent.append(len(self.samples) - 1)
+            self.paused = False
 
     def stop(self):
         if self.mode is None:
@@ -181,6 +210,10 @@ class ClockSampler:
             self.proc.terminate()
         inside = [x for x in self.samples if any(a <= x[0] <= b for a, b in self.windows)]
         note = "samples inside the timed regions"
+        if self.adjacent:
+            inside = inside + [self.samples[i] for i in self.adjacent if i < len(self.samples)]
+            note = ("samples inside the timed regions plus, for regions shorter than 50 ms, one immediately before and one immediately "
+                    "after each (an NVML query takes %.0f us here)" % (1e6 * float(np.median(self.query_s)) if self.query_s else 0.0))
         if not inside and self.windows:      # region shorter than one sampling period: nearest samples under the same load
             a, b = self.windows[0][0], self.windows[-1][1]
             inside = [x for x in self.samples if a - 0.25 <= x[0] <= b + 0.05]
@@ -496,7 +529,7 @@ def run_leg(ctx, name, wl, B, steps, warmup, exchange, *, main, steps_per_graph=
     n_warm += int(extra.item())
     _barrier(ctx)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clocks.mark_begin()
+    clocks.mark_begin(expected_s=per_step * steps)
     e0.record(stream)
     trainer.epoch_steps(steps)              # exactly K steps: K / spg replays of the spg-step graph
     e1.record(stream)
@@ -578,7 +611,7 @@ def run_leg(ctx, name, wl, B, steps, warmup, exchange, *, main, steps_per_graph=
     for _ in range(int(reps.item())):
         e2e_run(e2e_steps_n, False)
     _barrier(ctx)
-    clocks.mark_begin()
+    clocks.mark_begin(expected_s=per_call)
     e0.record(stream)
     e2e_run(e2e_steps_n, False)
     e1.record(stream)
@@ -974,7 +1007,7 @@ def run_gpu(args, wl, rank, world, local_rank):
                 # transfers of 0.8-64 MB, profiles/r2_pcie_dma.json; 38 GB/s for SM-issued zero-copy reads)
                 "h2d_GBps_per_gpu": main["h2d"] / (main["e2e_ms_step"] * 1e-3) * 1e-9,
                 "api": "rcn_cuda_train_epoch_host (chunks_exact loop over a pinned host dataset: the copy engine streams the chunks "
-                       "into a device ring ahead of the steps, kernel A waits on an arrival counter, 20 steps per CUDA graph launch, "
+                       "into a device ring ahead of the steps, kernel A waits on an arrival counter, up to 40 steps per CUDA graph launch, "
                        "per-step cost/hits written back to host memory; RCN_CUDA_HOST_COPY=pull = round 1's SM-issued zero-copy loads)"},
         "gpu_launches": int(main["launches"]),
         "roofline": roofline,

@@ -73,12 +73,12 @@ constexpr int kHsStateSlots = 6;
 // of the epoch length and serve every later call with the same batch shape
 constexpr long long kHsNoWrap = 1ll << 62;
 // consecutive steps captured into one CUDA graph by rcn_cuda_train_epoch_host (RCN_CUDA_HOST_STEPS_PER_GRAPH overrides)
-// Default: 2 in pull mode (every step joins its prefetch branch anyway), 20 in dma mode -- the steps inside a graph follow each
+// Default: 2 in pull mode (every step joins its prefetch branch anyway), 40 in dma mode -- the steps inside a graph follow each
 // other without the host or the PCIe link in between, while every graph boundary cost 4-5 us (and now and then 27 us) with
 // copies in flight on the link (profiles/r2_e2e_timeline.txt): 24.8 / 23.4 / 22.3 / 21.8 us per step at 5 / 10 / 20 / 40.
 static int hs_steps_per_graph(bool dma) {
     static const int v = []() { const char* e = getenv("RCN_CUDA_HOST_STEPS_PER_GRAPH"); int n = e ? atoi(e) : 0; return n < 1 ? 0 : (n > 64 ? 64 : n); }();
-    return v ? v : (dma ? 20 : 2);
+    return v ? v : (dma ? 40 : 2);
 }
 // How the images of the streamed epoch cross PCIe (RCN_CUDA_HOST_COPY = dma | pull):
 //  dma  (default) the copy engine.  The copy stream walks the dataset with back-to-back cudaMemcpyAsync calls into a ring of
@@ -1138,10 +1138,17 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
             }
             const size_t spg = (size_t)hs_steps_per_graph(dma);
             const size_t ring_steps = dma ? kHsRingSteps : 2;
-            // the epoch as a sequence of graph launches: as many `spg`-step graphs as fit, then (dma) 5-step graphs, then single steps
+            // The epoch as a sequence of graph launches: as many `spg`-step graphs as fit, then (dma) the largest of 20 / 10 / 5 / 2 /
+            // 1 steps that still fits -- as few launches as possible: with copies on the link a graph boundary costs 4-5 us and
+            // now and then 27 us (a short FIRST graph to get going sooner measured worse for that reason: 507-519 us against 479
+            // for a 20-step epoch; its launch latency passes while the first chunk crosses the link anyway).
             std::vector<int> plan_g;
             for (size_t left = n_steps; left;) {
-                const size_t g = left >= spg ? spg : (dma && left >= 5 && spg > 5 ? 5 : 1);
+                size_t g = 1;
+                if (left >= spg) g = spg;
+                else if (dma)
+                    for (size_t c : {(size_t)20, (size_t)10, (size_t)5, (size_t)2})
+                        if (c < spg && left >= c) { g = c; break; }
                 plan_g.push_back((int)g);
                 left -= g;
             }

@@ -494,7 +494,7 @@ print("ok")
 def test_train_epoch_host_copy_modes(api, copy_mode, spg):
     """Both ways the streamed epoch moves its images over PCIe (copy engine into a 64-chunk ring with an arrival counter
     kernel A waits on / SM-issued zero-copy loads on a graph branch), at several steps per graph ("0" = the mode's default:
-    20 / 2): 151 steps wrap the ring twice and leave a remainder of 5-step and single-step launches; bit-identical to train_batch_images chunk by chunk
+    40 / 2): 151 steps wrap the ring twice and leave a remainder of 20-, 10- and single-step launches; bit-identical to train_batch_images chunk by chunk
     (rcn.rs:147-149)."""
     import subprocess
     import sys
