@@ -395,6 +395,8 @@ def kernel_rooflines(wl, B, shapes, prof, prof_steps, pk, fp64_peak, int8_peak):
                                                     B * (48 * H * W + fwd + bwd_d)],
         "smallnet_fwd_bwd_kernel(fused features, front end ahead of the exchange)": ["fp64", B * (H * W * 1 + 8 + L * 8 + act_bytes) + n_params * 8,
                                                                                       B * (48 * H * W + fwd + bwd_d)],
+        "smallnet_fwd_bwd_kernel(fused features, front end ahead of the wait)": ["fp64", B * (H * W * 1 + 8 + L * 8 + act_bytes) + n_params * 8,
+                                                                                  B * (48 * H * W + fwd + bwd_d)],
         "smallnet_fwd_bwd_kernel": ["fp64", B * (L * 8 + 8 + act_bytes) + n_params * 8, B * (fwd + bwd_d)],
         "smallnet_wgrad_kernel": ["fp64", B * (L + shapes[0][0]) * 8 + n_params * 8, B * bwd_w],
         "smallnet_wgrad_kernel(+SGD update)": ["fp64", B * (L + shapes[0][0]) * 8 + 3 * n_params * 8, B * bwd_w + 2 * n_params],

@@ -444,6 +444,12 @@ int accumulate_images_dev(rcn_cuda_model* h, const void* images, int fmt, const 
         const bool fuse_push = h->dp.connected && dp_fused_push_enabled() && !h->dp_push_suppress;
         fr.prewait = (prewait_env && fr.use_cp && fuse_push && !h->pending_upd.params && !h->x_owns_cursor &&
                       (!fr.bi.cursor || h->pending_upd.cursor == fr.bi.cursor)) ? 1 : 0;
+        // One GPU: the same front end under the tail of the previous step's kernel B (which triggers its dependents early).
+        // Safe whatever precedes this launch: a kernel that does not trigger early has completed before kernel A starts; kernel B
+        // advances a device-side cursor before it triggers, and the only buffer both touch -- the features -- is written by
+        // this kernel A after its wait.
+        static const bool prewait1_env = []() { const char* e = getenv("RCN_CUDA_PREWAIT"); return !(e && e[0] == '0'); }();
+        if (!h->dp.connected && prewait1_env && fr.use_cp) fr.prewait = 2;
         if (smallnet_front_fits(h->small_desc, fr))
             return accumulate_dev(h, h->feats.as<double>(), nullptr, step_labels, B, &fr);
     }

@@ -106,11 +106,11 @@ struct EmitTile {
 
 // staged front end: standardised feature -> shared tile + HBM
 struct CpSinkTile {
-    double* tile; double* gout; Standardise sc;
+    double* tile; double* gout; Standardise sc;   // gout == nullptr: the HBM copy is written later, from the tile (prewait 2)
     __device__ __forceinline__ void operator()(int idx, int v) const {
         const double d = cp_finish(sc.mode, v, sc);
         tile[idx] = d;
-        gout[idx] = d;
+        if (gout) gout[idx] = d;
     }
 };
 
@@ -255,7 +255,7 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
                 const int itl = it - gi * items;
                 const int* in = tiles + gi * fr.cp.tile_ints + st.off;
                 int* nxt = tiles + gi * fr.cp.tile_ints + nx.off;
-                CpSinkTile sink{tile + (size_t)gi * pitch, feats + (size_t)(s0 + gi) * L, fr.sc};
+                CpSinkTile sink{tile + (size_t)gi * pitch, (PREWAIT && fr.prewait == 2) ? nullptr : feats + (size_t)(s0 + gi) * L, fr.sc};
                 if (last) {
                     if (q == 0) cp_item<true, true>(st, in, itl, nullptr, 0, 0, sink);
                     else cp_item<true, false>(st, in, itl, nullptr, 0, 0, sink);
@@ -308,9 +308,19 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
         if (tid < SN_TB) s_label[tid] = (labels && s0 + tid < B) ? labels[s0 + tid] : -1;
     }
 
-    if (PREWAIT) {   // everything above ran under the previous step's exchange kernel; the parameters are final from here on
+    if (PREWAIT) {   // everything above ran under the previous step's exchange kernel (prewait 1) or under the tail of its
+                     // weight-gradient kernel (prewait 2); the parameters are final from here on
         asm volatile("griddepcontrol.wait;" ::: "memory");
         load_params();
+        if (FUSED == 2 && fr.prewait == 2) {
+            // the previous step's kernel B was still reading the feature buffer until now: this tile's rows go out from shared memory
+            const int n_live = min(SN_TB, B - s0);
+            for (int gi = 0; gi < n_live; ++gi) {
+                double* __restrict__ dst = feats + (size_t)(s0 + gi) * L;
+                const double* src = tile + (size_t)gi * pitch;
+                for (int k = tid; k < L; k += SNA_THREADS) dst[k] = src[k];
+            }
+        }
     }
     SN_PHASE(3);
     // ---- layer 0: z = W0 a0 on DMMA, K split across the 16 warps ----------------------------------------------------
@@ -558,7 +568,7 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
                                            const DpPush& dp, const SnUpdate& upd, const int chunk /* samples per staging pass of the small CTA */,
                                            const int cg_idx, const int rank, const int S,
                                            double* sP, double* sD /* [2][64 * SN_DPITCH]: double-buffered 64-sample delta_0 chunk */,
-                                           const unsigned total_ctas) {
+                                           const unsigned total_ctas, const long long cur0_early /* >= 0: the cursor was advanced at the top */) {
     constexpr bool DP = MODE == 1 || MODE == 3;
     constexpr bool UPD = MODE == 2 || MODE == 3;
     constexpr bool DPX = MODE == 3;
@@ -789,15 +799,17 @@ __device__ __forceinline__ void sn_phase_b(const SmallNetDesc& d, const double* 
             stats[0] = c;
             reinterpret_cast<unsigned long long*>(stats)[1] = h;
             if (upd.cursor) {   // what sgd_update_kernel does on the side (kernel A of this step is long done)
-                const long long cur0 = *upd.cursor;
+                const long long cur0 = cur0_early >= 0 ? cur0_early : *upd.cursor;
                 if (upd.stats_ring) {
                     double* dst = upd.stats_ring + 2 * (cur0 / upd.batch);
                     dst[0] = c;
                     reinterpret_cast<unsigned long long*>(dst)[1] = h;
                 }
-                long long cur = cur0 + upd.batch;   // next chunk of chunks_exact(batch) (rcn.rs:147), remainder dropped
-                if (cur + upd.batch > upd.n_samples) cur = 0;
-                *upd.cursor = cur;
+                if (cur0_early < 0) {
+                    long long cur = cur0 + upd.batch;   // next chunk of chunks_exact(batch) (rcn.rs:147), remainder dropped
+                    if (cur + upd.batch > upd.n_samples) cur = 0;
+                    *upd.cursor = cur;
+                }
             }
         }
     }
@@ -826,10 +838,32 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
     // a data-parallel group when this kernel pushed to the peers (MODE 1) -- its successor is then the exchange kernel, which
     // waits for this kernel's completion before it lets the next kernel A start.  Not in the other group modes: their
     // successor may be a PREWAIT kernel A, whose early part overwrites the feature buffer this kernel reads.
-    if (dp.world <= 1 || MODE == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    //
+    // One GPU with a device-side cursor: the next kernel A may read the cursor BEFORE its own griddepcontrol.wait (prewait 2: its
+    // front end runs under this kernel's tail), so the cursor is advanced before this kernel lets it start -- the statistics CTA
+    // first waits for this step's kernel A (the cursor's last reader), advances the cursor, and only then triggers; the launch
+    // of the dependents needs every CTA's trigger, so it cannot overtake that store.
+    long long cur0_early = -1;
+    if (dp.world <= 1 && upd.cursor && blockIdx.x == (unsigned)col_groups && blockIdx.y == 0) {
+        __shared__ long long s_cur0;
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (threadIdx.x == 0) {
+            const long long c0 = *upd.cursor;
+            long long cur = c0 + upd.batch;   // next chunk of chunks_exact(batch) (rcn.rs:147), remainder dropped
+            if (cur + upd.batch > upd.n_samples) cur = 0;
+            *upd.cursor = cur;
+            s_cur0 = c0;
+            __threadfence();
+        }
+        __syncthreads();
+        cur0_early = s_cur0;
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    } else {
+        if (dp.world <= 1 || MODE == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     sn_phase_b<MODE, CW>(d, feats, acts, deltas, B, ksplit, col_groups, grads, stats_partial, n_stat, stats, dp, upd, chunk,
-                         (int)blockIdx.x, (int)blockIdx.y, (int)gridDim.y, sP_dyn, sD_static, gridDim.x * gridDim.y);
+                         (int)blockIdx.x, (int)blockIdx.y, (int)gridDim.y, sP_dyn, sD_static, gridDim.x * gridDim.y, cur0_early);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -923,7 +957,9 @@ static int launch_kernel_a(const SmallNetDesc& d, const double* params, double* 
     };
     if (fr && fr->use_cp && fr->prewait && backward && sn_pdl_enabled()) {
         static SmemAttrCache attr;
-        RCN_TRY(launch(smallnet_fwd_bwd_kernel<2, true>, attr, "smallnet_fwd_bwd_kernel(fused features, front end ahead of the exchange)", *fr));
+        RCN_TRY(launch(smallnet_fwd_bwd_kernel<2, true>, attr,
+                       fr->prewait == 2 ? "smallnet_fwd_bwd_kernel(fused features, front end ahead of the wait)"
+                                        : "smallnet_fwd_bwd_kernel(fused features, front end ahead of the exchange)", *fr));
     } else if (fr && fr->use_cp) {
         static SmemAttrCache attr;
         RCN_TRY(launch(smallnet_fwd_bwd_kernel<2, false>, attr, "smallnet_fwd_bwd_kernel(fused features)", *fr));

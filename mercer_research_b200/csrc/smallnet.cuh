@@ -28,8 +28,10 @@ struct SmallNetFront {
     StageList stages;
     Standardise sc;
     BatchIndex bi;
-    int prewait;                       // data-parallel step behind the exchange kernel: run the front end ahead of
-                                       // griddepcontrol.wait (smallnet.cu; needs use_cp and a cursor the previous kernel B advanced)
+    int prewait;                       // run the front end ahead of griddepcontrol.wait (smallnet.cu; needs use_cp).  1: data-parallel
+                                       // step behind the exchange kernel (needs a cursor the previous kernel B advanced);
+                                       // 2: one GPU, under the tail of the previous step's kernel B, which still reads the
+                                       // feature buffer -- the features stay in the tile until the wait has passed
     int use_cp;                        // staged front end (bulk-async image loads, zero-framed tiles): see CpPlan
     CpPlan cp;
 };

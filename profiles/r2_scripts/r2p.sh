@@ -1,16 +1,22 @@
 #!/bin/bash
-# 8 GPUs, final code: the driver's command line (K=20, W=5, all legs) and the steady-state c2 line (2000 steps)
+# single-GPU prewait (kernel A's front end under the tail of the previous kernel B): parity tests, then A/B of the bench line
 set -u
 OUT=gpurun_out
-show() { python - <<PY
+timeout 900 python -m pytest tests/test_gpu_dense.py tests/test_gpu_configs.py -m gpu -q -x -k "c2 or c3 or epoch or host or generation or graph or smallnet or fused" 2>&1 | tail -3
+for pw in 1 0 1 0; do
+RCN_CUDA_PREWAIT=$pw timeout 300 python bench.py --steps 20 --warmup 5 --no-extra > $OUT/r2p_${pw}.json 2> $OUT/r2p_${pw}.err
+python - <<PY
 import json
-d = json.load(open("gpurun_out/$1"))
-print("$1", round(d["value"] / 1e6, 2), "M img/s", round(d["ms_per_step"] * 1e3, 2), "us; e2e", round(d["e2e"]["value"] / 1e6, 2), "M", round(d["e2e"]["ms_per_step"] * 1e3, 2), "us", round(d["e2e"]["h2d_GBps_per_gpu"], 1), "GB/s", (d.get("parity") or {}))
-print("    ", d["roofline"].get("in_graph_timeline"))
-for k, v in d.get("workloads", {}).items():
-    print("    ", k, round(v["value"] / 1e6, 3) if "value" in v else v, round(v.get("ms_per_step", 0), 4), v.get("exchange"))
+d = json.load(open("gpurun_out/r2p_${pw}.json"))
+tl = d["roofline"].get("in_graph_timeline") or {}
+print("prewait=$pw K=20", round(d["value"] / 1e6, 2), "M", round(d["ms_per_step"] * 1e3, 2), "us  e2e", round(d["e2e"]["value"] / 1e6, 2), "M |", {k: (round(v["us_mean"], 2) if isinstance(v, dict) else v) for k, v in tl.items()})
 PY
-}
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511"
-timeout 600 $TR bench.py --gpus 8 --steps 20 --warmup 5 > $OUT/r2p_n8_driver_cmd.json 2> $OUT/r2p_n8_driver_cmd.err; echo "rc=$?"; show r2p_n8_driver_cmd.json
-timeout 600 $TR bench.py --gpus 8 --no-extra > $OUT/r2p_n8_2000.json 2> $OUT/r2p_n8_2000.err; echo "rc=$?"; show r2p_n8_2000.json
+done
+for pw in 1 0; do
+RCN_CUDA_PREWAIT=$pw timeout 300 python bench.py --steps 2000 --warmup 20 --no-extra > $OUT/r2p_${pw}_long.json 2> $OUT/r2p_${pw}_long.err
+python - <<PY
+import json
+d = json.load(open("gpurun_out/r2p_${pw}_long.json"))
+print("prewait=$pw K=2000", round(d["value"] / 1e6, 2), "M", round(d["ms_per_step"] * 1e3, 2), "us  e2e", round(d["e2e"]["value"] / 1e6, 2), "M")
+PY
+done
