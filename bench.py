@@ -971,8 +971,11 @@ def run_gpu(args, wl, rank, world, local_rank):
             nbytes, prof, psteps = leg.pop("_nbytes"), leg.pop("_prof"), leg.pop("_prof_steps")
             gbs = nbytes / (leg["ms_per_step"] * 1e-3) / 1e9
             tot = sum(v["total_ms"] for v in prof.values()) or 1.0
+            tw = traffic_all.get(key, {}) or {}   # dram bytes of one call: per-launch ncu figures x launches per call
+            parts = [tw[k] * v["launches"] / psteps for k, v in prof.items() if isinstance(tw.get(k), (int, float))]
             leg["roofline"] = {"kernel": max(prof, key=lambda k: prof[k]["total_ms"]) if prof else None, "bound": "hbm", "achieved": gbs,
-                               "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                               "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                               "traffic": float(sum(parts)) if parts else None, "peak_source": pk["source"],
                                "achieved_is": "algorithmic bytes (H*W u8 read + L*8 f64 features written per image, SURVEY 8d) / duration of one call",
                                "kernels": {k: {"launches_per_step": v["launches"] / psteps, "avg_us": v["total_ms"] / v["launches"] * 1e3,
                                                "share": round(v["total_ms"] / tot, 4)} for k, v in prof.items()}}

@@ -15,7 +15,9 @@ from mercer_research_b200 import RCN, Padding, Pooling, RCNLayer  # noqa: E402
 
 CP = [RCNLayer.Convolve2D(Padding.Same), RCNLayer.Pool2D(Pooling.Max)]
 CASES = [("c2 28x28 [C,P]", 28, 28, CP, 131072), ("c3 32x32 [C,P]x3", 32, 32, CP * 3, 65536),
-         ("c5 64x64 [C,P]", 64, 64, CP, 16384), ("28x28 [C,P]x2", 28, 28, CP * 2, 131072)]
+         ("c5 64x64 [C,P]", 64, 64, CP, 16384), ("28x28 [C,P]x2", 28, 28, CP * 2, 131072),
+         # BASELINE config 4's conv stack: four Same convolutions, 256 maps of 64x64 per image (the layered path's strip kernels)
+         ("c4 64x64 [C]x4", 64, 64, [RCNLayer.Convolve2D(Padding.Same)] * 4, 128)]
 
 
 def main():
