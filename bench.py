@@ -778,8 +778,12 @@ def leg_roofline(leg, pk, fp64_peak, int8_peak, int8_how, traffic_all, workload_
             b = tl.get("kernel B (bwd-weight + update / push)")
             if a:
                 fa = B * (48 * H * W + fwd + bwd_d)
-                rl["kernel_A"] = {"us": a["us_mean"], "TFLOPs_f64": fa / (a["us_mean"] * 1e-6) / 1e12,
-                                  "frac_fp64": fa / (a["us_mean"] * 1e-6) / 1e12 / fp64_peak}
+                # Kernel A starts its front end under the previous step's kernel B / exchange kernel (prewait): its span then
+                # begins BEFORE that kernel ends (negative gap).  Its own share of the step is the span minus that overlap.
+                overlap = max(0.0, -float(tl.get("gap (end of step k) -> kernel A(k+1) us", 0.0) or 0.0))
+                us_a = max(a["us_mean"] - overlap, 1e-3)
+                rl["kernel_A"] = {"us": us_a, "span_us": a["us_mean"], "overlap_with_previous_step_us": overlap,
+                                  "TFLOPs_f64": fa / (us_a * 1e-6) / 1e12, "frac_fp64": fa / (us_a * 1e-6) / 1e12 / fp64_peak}
             if b:
                 fb = B * bwd_w
                 rl["kernel_B"] = {"us": b["us_mean"], "TFLOPs_f64": fb / (b["us_mean"] * 1e-6) / 1e12,

@@ -417,6 +417,16 @@ int accumulate_dev(rcn_cuda_model* h, const double* feats, const double* onehot,
 // images (DEVICE) -> gradient sums.  The canonical narrow network with u8 pixels runs the convpool stack inside
 // kernel A (smallnet.cu); everything else runs the feature kernel(s) first.  `bi` (optional) is the epoch-mode
 // device-side batch selection; without it `labels` are this batch's labels.
+// How far the single-GPU prewait goes (kernel A's front end ahead of griddepcontrol.wait, under the previous kernel B's tail;
+// RCN_CUDA_PREWAIT): 0 = nowhere, 1 = in the streamed host epoch only (default), 2 = in every training step.  Measured: the host
+// epoch gains 3-6 % (the arrival-counter wait and the ring loads move under kernel B); the device-resident step does not (kernel
+// A needs a whole SM's registers, so all but ~26 of its CTAs start only when kernel B's CTAs leave, and its parameter loads are
+// no longer hidden behind the front end).
+static int prewait_mode() {
+    static const int v = []() { const char* e = getenv("RCN_CUDA_PREWAIT"); return e ? atoi(e) : 1; }();
+    return v;
+}
+
 static bool fused_front_enabled() {
     static const bool v = []() { const char* e = getenv("RCN_CUDA_FUSED_FRONT"); return !(e && e[0] == '0'); }();
     return v;
@@ -448,8 +458,7 @@ int accumulate_images_dev(rcn_cuda_model* h, const void* images, int fmt, const 
         // Safe whatever precedes this launch: a kernel that does not trigger early has completed before kernel A starts; kernel B
         // advances a device-side cursor before it triggers, and the only buffer both touch -- the features -- is written by
         // this kernel A after its wait.
-        static const bool prewait1_env = []() { const char* e = getenv("RCN_CUDA_PREWAIT"); return !(e && e[0] == '0'); }();
-        if (!h->dp.connected && prewait1_env && fr.use_cp) fr.prewait = 2;
+        if (!h->dp.connected && fr.use_cp && (prewait_mode() == 2 || (prewait_mode() == 1 && fr.bi.window != 0))) fr.prewait = 2;
         if (smallnet_front_fits(h->small_desc, fr))
             return accumulate_dev(h, h->feats.as<double>(), nullptr, step_labels, B, &fr);
     }
@@ -917,7 +926,7 @@ static void stream_drained(rcn_cuda_model* h) { h->x_owns_cursor = false; }
 // Single-GPU steps of the fused small-network path let the weight-gradient kernel apply the update (SnUpdate): arm it
 // before the accumulate; if that accumulate took another path the standalone update kernel runs as before.
 static void arm_fused_update(rcn_cuda_model* h, double scale, long long* cursor, long long batch, long long n_samples,
-                             double* stats_ring) {
+                             double* stats_ring, bool streamed = false) {
     static const bool on = []() { const char* e = getenv("RCN_CUDA_FUSED_UPDATE"); return !(e && e[0] == '0'); }();
     h->pending_upd = SnUpdate{};
     if (!on || !h || !h->params_ready || !h->use_small) return;
@@ -933,6 +942,7 @@ static void arm_fused_update(rcn_cuda_model* h, double scale, long long* cursor,
     h->pending_upd.batch = batch;
     h->pending_upd.n_samples = n_samples;
     h->pending_upd.stats_ring = stats_ring;
+    h->pending_upd.early_cursor = (!h->dp.connected && (prewait_mode() == 2 || (prewait_mode() == 1 && streamed))) ? 1 : 0;
 }
 // What the accumulate did with the armed update: bit 0 = parameters updated, bit 1 = cursor advanced / result ring written.
 static int take_upd_fused(rcn_cuda_model* h) {
@@ -1214,7 +1224,7 @@ int rcn_cuda_train_epoch_host(rcn_cuda_handle h, const void* images, int pixel_f
                         if (cudaPeekAtLastError() != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "prefetch kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
                         if (cudaEventRecord(h->hs_join, h->copy_stream) != cudaSuccess) { rc = fail(RCN_ERR_CUDA, "graph join failed"); break; }
                         }
-                        arm_fused_update(h, scale_s, st, (long long)B, kHsNoWrap, h->stats_host);
+                        arm_fused_update(h, scale_s, st, (long long)B, kHsNoWrap, h->stats_host, true);
                         rc = accumulate_images_dev(h, h->hs_ring.p, pixel_format, nullptr, B, H, W, &bi);
                         const int fused = take_upd_fused(h);
                         if (rc != RCN_OK) break;

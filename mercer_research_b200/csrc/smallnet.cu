@@ -105,12 +105,15 @@ struct EmitTile {
 };
 
 // staged front end: standardised feature -> shared tile + HBM
+// DEFER (the PREWAIT kernels): only the tile is written here; the HBM copy goes out from the tile once griddepcontrol.wait has
+// passed -- until then the previous step's kernel B may still be reading the feature buffer.
+template <bool DEFER>
 struct CpSinkTile {
-    double* tile; double* gout; Standardise sc;   // gout == nullptr: the HBM copy is written later, from the tile (prewait 2)
+    double* tile; double* gout; Standardise sc;
     __device__ __forceinline__ void operator()(int idx, int v) const {
         const double d = cp_finish(sc.mode, v, sc);
         tile[idx] = d;
-        if (gout) gout[idx] = d;
+        if (!DEFER) gout[idx] = d;
     }
 };
 
@@ -255,7 +258,7 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
                 const int itl = it - gi * items;
                 const int* in = tiles + gi * fr.cp.tile_ints + st.off;
                 int* nxt = tiles + gi * fr.cp.tile_ints + nx.off;
-                CpSinkTile sink{tile + (size_t)gi * pitch, (PREWAIT && fr.prewait == 2) ? nullptr : feats + (size_t)(s0 + gi) * L, fr.sc};
+                CpSinkTile<PREWAIT> sink{tile + (size_t)gi * pitch, feats + (size_t)(s0 + gi) * L, fr.sc};
                 if (last) {
                     if (q == 0) cp_item<true, true>(st, in, itl, nullptr, 0, 0, sink);
                     else cp_item<true, false>(st, in, itl, nullptr, 0, 0, sink);
@@ -312,8 +315,8 @@ __device__ __forceinline__ void sn_phase_a(const SmallNetDesc& d, const double* 
                      // weight-gradient kernel (prewait 2); the parameters are final from here on
         asm volatile("griddepcontrol.wait;" ::: "memory");
         load_params();
-        if (FUSED == 2 && fr.prewait == 2) {
-            // the previous step's kernel B was still reading the feature buffer until now: this tile's rows go out from shared memory
+        if (FUSED == 2) {
+            // the previous step's kernel B may have been reading the feature buffer until now: this tile's rows go out from shared memory
             const int n_live = min(SN_TB, B - s0);
             for (int gi = 0; gi < n_live; ++gi) {
                 double* __restrict__ dst = feats + (size_t)(s0 + gi) * L;
@@ -844,7 +847,7 @@ __global__ void __launch_bounds__(SNB_THREADS) smallnet_wgrad_kernel(const __gri
     // first waits for this step's kernel A (the cursor's last reader), advances the cursor, and only then triggers; the launch
     // of the dependents needs every CTA's trigger, so it cannot overtake that store.
     long long cur0_early = -1;
-    if (dp.world <= 1 && upd.cursor && blockIdx.x == (unsigned)col_groups && blockIdx.y == 0) {
+    if (dp.world <= 1 && upd.cursor && upd.early_cursor && blockIdx.x == (unsigned)col_groups && blockIdx.y == 0) {
         __shared__ long long s_cur0;
         asm volatile("griddepcontrol.wait;" ::: "memory");
         if (threadIdx.x == 0) {

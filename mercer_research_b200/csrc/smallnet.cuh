@@ -49,6 +49,8 @@ struct SnUpdate {
     long long* cursor;       // optional epoch cursor, advanced by `batch` with chunks_exact wrap-around
     long long batch, n_samples;
     double* stats_ring;      // optional (pinned host) {cost, hits} per step
+    int early_cursor;        // one GPU: advance the cursor BEFORE this kernel lets its dependents start (the next kernel A reads
+                             // it ahead of its griddepcontrol.wait: SmallNetFront::prewait == 2)
 };
 
 bool smallnet_eligible(const SmallNetDesc& d);
