@@ -756,7 +756,7 @@ def leg_roofline(leg, pk, fp64_peak, int8_peak, int8_how, traffic_all, workload_
     small = top is not None and top.startswith("smallnet")
     if small:   # the fused step = kernel A + kernel B: DRAM bytes of both launches
         tw = traffic_all.get(workload_key, {}) or {}
-        parts = [v for k, v in tw.items() if k.startswith("smallnet") and isinstance(v, (int, float))]
+        parts = [v for k, v in tw.items() if k.startswith("smallnet") and k in leg["prof"] and isinstance(v, (int, float))]   # the kernels this leg ran
         traffic = float(sum(parts)) if parts else None
     if small:
         # the fused narrow-network step: two kernels that are ONE dependent chain; 99 flop per compulsory byte against an FP64
