@@ -12,6 +12,7 @@ A "step" is one pass of the hot path over one minibatch: u8 images -> Sobel/ReLU
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import math
 import os
@@ -529,14 +530,19 @@ def run_leg(ctx, name, wl, B, steps, warmup, exchange, *, main, steps_per_graph=
     for i in range(int(extra.item())):
         trainer.epoch_step()
     n_warm += int(extra.item())
-    _barrier(ctx)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # no cyclic-GC pass between the graph launches of the timed region (what timeit does: at the driver's K = 20 the region is
+    # four launches / 0.4 ms long, and a collection landing between two of them stalls the GPU for longer than a step)
+    gc.collect()
+    gc.disable()
+    _barrier(ctx)
     clocks.mark_begin(expected_s=per_step * steps)
     e0.record(stream)
     trainer.epoch_steps(steps)              # exactly K steps: K / spg replays of the spg-step graph
     e1.record(stream)
     _barrier(ctx)
     clocks.mark_end()
+    gc.enable()
     trainer.check()
     launches = kernels_per_step * steps
     ms_step = _max_over_ranks(ctx, e0.elapsed_time(e1)) / steps
@@ -612,6 +618,8 @@ def run_leg(ctx, name, wl, B, steps, warmup, exchange, *, main, steps_per_graph=
         dist.broadcast(reps, 0)
     for _ in range(int(reps.item())):
         e2e_run(e2e_steps_n, False)
+    gc.collect()
+    gc.disable()
     _barrier(ctx)
     clocks.mark_begin(expected_s=per_call)
     e0.record(stream)
@@ -619,6 +627,7 @@ def run_leg(ctx, name, wl, B, steps, warmup, exchange, *, main, steps_per_graph=
     e1.record(stream)
     _barrier(ctx)
     clocks.mark_end()
+    gc.enable()
     trainer.check()
     clk = clocks.stop() if rank == 0 else None
     e2e_ms = _max_over_ranks(ctx, e0.elapsed_time(e1))
